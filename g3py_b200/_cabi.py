@@ -1,0 +1,287 @@
+"""ctypes binding of libg3b.so (include/g3b.h).  PyTorch-free; NumPy arrays in and out.
+
+There is no CPU fallback: if the shared library is missing or no sm_100 device is present,
+`load()` / `Context()` raise.  Contexts are created lazily per process (fork-safe) and are
+dropped on pickling, like the compiled functions of the reference's `makefn`
+(g3py/libs/tensors.py:35-74; pickling at g3py/processes/stochastic.py:107-119).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+G3_MAX_NODES = 16
+G3_MAX_THETA = 32
+G3_MAX_DIM = 16
+
+# leaf / node opcodes (include/g3b.h)
+K_SE, K_OU, K_MAT32, K_MAT52, K_RQ, K_SIN, K_NOISE, K_WN = 1, 2, 3, 4, 5, 6, 7, 8
+K_SUM, K_PROD, K_SCALE, K_SHIFT = 16, 17, 18, 19
+KF_PROCESS_NOISE = 1
+
+ST_NONFINITE_INPUT, ST_DIAG_SHIFT, ST_JITTER, ST_POTRF_FAILED, ST_NONFINITE_RESULT = 1, 2, 4, 8, 16
+KIND_GAUSS, KIND_STUDENT = 0, 1
+POST_NOISE, POST_COV = 1, 2
+
+
+class KNode(C.Structure):
+    _fields_ = [("op", C.c_int32), ("dim0", C.c_int32), ("dim1", C.c_int32), ("var_idx", C.c_int32),
+                ("p0_idx", C.c_int32), ("p1_idx", C.c_int32), ("flags", C.c_int32), ("value", C.c_double)]
+
+
+class KernelDesc(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("n_theta", C.c_int32), ("nodes", KNode * G3_MAX_NODES)]
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_ctxp = C.c_void_p
+
+SIGNATURES = {
+    "g3_ctx_create": (C.c_int, [C.c_int, C.POINTER(_ctxp)]),
+    "g3_ctx_destroy": (C.c_int, [_ctxp]),
+    "g3_last_error": (C.c_char_p, [_ctxp]),
+    "g3_sync": (C.c_int, [_ctxp]),
+    "g3_set_jitter": (C.c_int, [_ctxp, C.c_double, C.c_int]),
+    "g3_set_potrf_block": (C.c_int, [_ctxp, C.c_int]),
+    "g3_timer_begin": (C.c_int, [_ctxp]),
+    "g3_timer_end": (C.c_int, [_ctxp, C.POINTER(C.c_float)]),
+    "g3_launch_count": (C.c_int64, [_ctxp]),
+    "g3_set_data": (C.c_int, [_ctxp, _dp, C.c_int, C.c_int]),
+    "g3_gram": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _ip]),
+    "g3_gram_vjp": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp]),
+    "g3_potrf_robust": (C.c_int, [_ctxp, _dp, C.c_int, C.c_int, C.c_int, _ip, _dp]),
+    "g3_gp_logp_grad": (C.c_int, [_ctxp, C.POINTER(KernelDesc), C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, _dp, _dp,
+                                  _dp, _dp, _ip]),
+    "g3_gp_upload": (C.c_int, [_ctxp, C.POINTER(KernelDesc), C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int]),
+    "g3_gp_run": (C.c_int, [_ctxp]),
+    "g3_gp_download": (C.c_int, [_ctxp, _dp, _dp, _dp, _dp, _ip]),
+    "g3_gp_posterior": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp, _ip]),
+    "g3_gram_potrf_device": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, _dp, _ip, C.POINTER(C.c_float),
+                                       C.POINTER(C.c_float)]),
+}
+
+_LIB = None
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libg3b.so")
+
+
+def load():
+    """Load libg3b.so and set the prototypes.  Raises if the library was not built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError("libg3b.so not found at %s: build it with `make -C g3py_b200/csrc` "
+                           "(or __graft_entry__.build()); there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing: loud by design
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class G3Error(RuntimeError):
+    pass
+
+
+class Context:
+    """One device context (one stream, cached workspaces)."""
+
+    def __init__(self, device=0):
+        self._lib = load()
+        h = _ctxp()
+        rc = self._lib.g3_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            why = {-3: "no CUDA device visible", -4: "device is not sm_100 (B200)", -1: "bad device index"}.get(rc, "CUDA error")
+            raise G3Error("g3_ctx_create(device=%d) failed (%d): %s; there is no CPU fallback" % (device, rc, why))
+        self._h = h
+        self.device = device
+        self.N = 0
+        self.D = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.g3_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            msg = self._lib.g3_last_error(self._h)
+            raise G3Error("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+    # ---- configuration / timing
+    def set_jitter(self, jitter_rel, max_tries=20):
+        self._ck(self._lib.g3_set_jitter(self._h, float(jitter_rel), int(max_tries)), "g3_set_jitter")
+
+    def set_potrf_block(self, w):
+        self._ck(self._lib.g3_set_potrf_block(self._h, int(w)), "g3_set_potrf_block")
+
+    def sync(self):
+        self._ck(self._lib.g3_sync(self._h), "g3_sync")
+
+    def timer_begin(self):
+        self._ck(self._lib.g3_timer_begin(self._h), "g3_timer_begin")
+
+    def timer_end(self):
+        ms = C.c_float()
+        self._ck(self._lib.g3_timer_end(self._h, C.byref(ms)), "g3_timer_end")
+        return float(ms.value)
+
+    def launch_count(self):
+        return int(self._lib.g3_launch_count(self._h))
+
+    # ---- data
+    def set_data(self, X):
+        X = _f64(X)
+        if X.ndim == 1:
+            X = X[:, None]
+        self._ck(self._lib.g3_set_data(self._h, _d(X), X.shape[0], X.shape[1]), "g3_set_data")
+        self.N, self.D = X.shape
+
+    # ---- gram
+    def gram(self, desc, X1, X2, theta):
+        X1 = _f64(X1)
+        theta = np.atleast_2d(_f64(theta))
+        B = theta.shape[0]
+        n1, D = X1.shape
+        if X2 is None:
+            n2, x2p = n1, None
+        else:
+            X2 = _f64(X2)
+            n2, x2p = X2.shape[0], _d(X2)
+        K = np.empty((B, n1, n2))
+        st = np.zeros(B, dtype=np.int32)
+        self._ck(self._lib.g3_gram(self._h, C.byref(desc), _d(X1), n1, x2p, n2, D, _d(theta), B, _d(K), _i(st)), "g3_gram")
+        return K, st
+
+    def gram_vjp(self, desc, X1, X2, theta, W):
+        X1 = _f64(X1)
+        theta = np.atleast_2d(_f64(theta))
+        B = theta.shape[0]
+        n1, D = X1.shape
+        if X2 is None:
+            n2, x2p = n1, None
+        else:
+            X2 = _f64(X2)
+            n2, x2p = X2.shape[0], _d(X2)
+        W = _f64(W).reshape(B, n1, n2)
+        g = np.zeros((B, desc.n_theta))
+        self._ck(self._lib.g3_gram_vjp(self._h, C.byref(desc), _d(X1), n1, x2p, n2, D, _d(theta), B, _d(W), _d(g)),
+                 "g3_gram_vjp")
+        return g
+
+    # ---- cholesky
+    def potrf_robust(self, A):
+        """A: (B, n, n) or (n, n) symmetric; returns (L, info, jitter).  Input is not modified."""
+        A = np.array(A, dtype=np.float64, order="C", copy=True)
+        single = A.ndim == 2
+        if single:
+            A = A[None]
+        B, n, _ = A.shape
+        info = np.zeros(B, dtype=np.int32)
+        jit = np.zeros(B)
+        self._ck(self._lib.g3_potrf_robust(self._h, _d(A), n, n, B, _i(info), _d(jit)), "g3_potrf_robust")
+        if single:
+            return A[0], int(info[0]), float(jit[0])
+        return A, info, jit
+
+    # ---- fused logp + grad
+    def gp_logp_grad(self, desc, kind, delta, theta, nu=None, want_grad=True):
+        """delta: (N,) shared or (B, N); theta: (B, P_kernel) natural space.
+        Returns dict(beta, logdet, dtheta, ddelta, status)."""
+        theta = np.atleast_2d(_f64(theta))
+        B = theta.shape[0]
+        delta = _f64(delta)
+        stride = 0 if delta.ndim == 1 else self.N
+        if delta.ndim == 2 and delta.shape[0] != B:
+            raise ValueError("delta must be (N,) or (B, N)")
+        if delta.shape[-1] != self.N:
+            raise ValueError("delta length %d != N %d" % (delta.shape[-1], self.N))
+        nu_a = _f64(np.broadcast_to(nu, (B,))) if nu is not None else None
+        beta = np.empty(B)
+        logdet = np.empty(B)
+        st = np.zeros(B, dtype=np.int32)
+        dth = np.zeros((B, max(desc.n_theta, 1))) if want_grad else None
+        ddl = np.zeros((B, self.N)) if want_grad else None
+        self._ck(self._lib.g3_gp_logp_grad(self._h, C.byref(desc), int(kind), _d(delta), stride, _d(theta), B, _d(nu_a),
+                                           _d(beta), _d(logdet), _d(dth), _d(ddl), _i(st)), "g3_gp_logp_grad")
+        return {"beta": beta, "logdet": logdet, "dtheta": None if dth is None else dth[:, :desc.n_theta],
+                "ddelta": ddl, "status": st}
+
+    def gp_upload(self, desc, kind, delta, theta, nu=None, want_grad=True):
+        theta = np.atleast_2d(_f64(theta))
+        B = theta.shape[0]
+        delta = _f64(delta)
+        stride = 0 if delta.ndim == 1 else self.N
+        nu_a = _f64(np.broadcast_to(nu, (B,))) if nu is not None else None
+        self._ck(self._lib.g3_gp_upload(self._h, C.byref(desc), int(kind), _d(delta), stride, _d(theta), B, _d(nu_a),
+                                        1 if want_grad else 0), "g3_gp_upload")
+        self._up = (B, desc.n_theta, bool(want_grad))
+
+    def gp_run(self):
+        self._ck(self._lib.g3_gp_run(self._h), "g3_gp_run")
+
+    def gp_download(self):
+        B, P, want_grad = self._up
+        beta = np.empty(B)
+        logdet = np.empty(B)
+        st = np.zeros(B, dtype=np.int32)
+        dth = np.zeros((B, max(P, 1))) if want_grad else None
+        ddl = np.zeros((B, self.N)) if want_grad else None
+        self._ck(self._lib.g3_gp_download(self._h, _d(beta), _d(logdet), _d(dth), _d(ddl), _i(st)), "g3_gp_download")
+        return {"beta": beta, "logdet": logdet, "dtheta": None if dth is None else dth[:, :P], "ddelta": ddl, "status": st}
+
+    # ---- posterior
+    def gp_posterior(self, desc, Xs, delta, theta, noise=False, cov=False):
+        Xs = _f64(Xs)
+        if Xs.ndim == 1:
+            Xs = Xs[:, None]
+        M = Xs.shape[0]
+        delta = _f64(delta)
+        theta = _f64(theta).ravel()
+        mean = np.empty(M)
+        var = np.empty(M)
+        covm = np.empty((M, M)) if cov else None
+        beta = C.c_double()
+        st = C.c_int()
+        flags = (POST_NOISE if noise else 0) | (POST_COV if cov else 0)
+        self._ck(self._lib.g3_gp_posterior(self._h, C.byref(desc), _d(Xs), M, _d(delta), _d(theta), flags, _d(mean),
+                                           _d(var), _d(covm), C.cast(C.byref(beta), _dp), C.cast(C.byref(st), _ip)),
+                 "g3_gp_posterior")
+        return {"mean": mean, "var": var, "cov": covm, "beta": float(beta.value), "status": int(st.value)}
+
+    # ---- big-matrix Cholesky
+    def gram_potrf_device(self, desc, theta):
+        theta = _f64(theta).ravel()
+        ld = C.c_double()
+        info = C.c_int()
+        mg = C.c_float()
+        mp = C.c_float()
+        self._ck(self._lib.g3_gram_potrf_device(self._h, C.byref(desc), _d(theta), C.cast(C.byref(ld), _dp),
+                                                C.cast(C.byref(info), _ip), C.byref(mg), C.byref(mp)),
+                 "g3_gram_potrf_device")
+        return {"logdet": float(ld.value), "info": int(info.value), "ms_gram": float(mg.value), "ms_potrf": float(mp.value)}

@@ -1,0 +1,129 @@
+// Internal declarations shared by the translation units of libg3b.so (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/g3b.h"
+
+#define G3_TILE 128          // factorisation block size: every device matrix is padded to a multiple
+#define G3_BM 64             // GEMM CTA tile rows   (two CTAs per 128-row block)
+#define G3_BN 128            // GEMM CTA tile cols
+#define G3_BK 16             // doubles per k-tile = 128 bytes = one SWIZZLE_128B row
+#define G3_STAGES 4
+
+struct g3_buf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct g3_gp_state {
+  g3_kernel_desc desc;
+  int kind = 0, B = 0, want_grad = 0, delta_stride = 0, valid = 0;
+};
+
+struct g3_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  double jitter_rel = 9.999999974752427e-07;  // float32(1e-6), libs/tensors.py:204
+  int max_tries = 20;
+  // resident observations
+  double* dX = nullptr;
+  int N = 0, D = 0;
+  std::map<std::string, g3_buf> bufs;  // grow-only named workspaces
+  g3_gp_state gp;
+  void* encode_fn = nullptr;           // cuTensorMapEncodeTiled
+  int sm_count = 148;
+  bool gemm_ready = false, diag_ready = false;
+  int potrf_w = 1 << 20;               // tile columns per right-looking outer block, batched path (left-looking)
+  int potrf_w_big = 8;                 // same, single big matrix (g3_gram_potrf_device)
+};
+
+// ---- host helpers (ctx.cu) ----
+int g3_fail(g3_ctx* ctx, const char* what, cudaError_t e, const char* file, int line);
+int g3_fail_msg(g3_ctx* ctx, const std::string& msg);
+void* g3_ws(g3_ctx* ctx, const char* name, size_t bytes);   // returns nullptr on failure (err set)
+int g3_make_tmap(g3_ctx* ctx, CUtensorMap* out, const double* base, uint64_t cols, uint64_t rows,
+                 uint64_t batch, uint64_t ld, uint64_t batch_stride, uint32_t box_rows);
+
+#define G3_CUDA(ctx, call)                                                     \
+  do {                                                                         \
+    cudaError_t _e = (call);                                                   \
+    if (_e != cudaSuccess) return g3_fail((ctx), #call, _e, __FILE__, __LINE__); \
+  } while (0)
+
+#define G3_LAUNCH_CHECK(ctx)                                                   \
+  do {                                                                         \
+    (ctx)->launches++;                                                         \
+    cudaError_t _e = cudaGetLastError();                                       \
+    if (_e != cudaSuccess) return g3_fail((ctx), "kernel launch", _e, __FILE__, __LINE__); \
+  } while (0)
+
+static inline int g3_pad(int n) { return (n + G3_TILE - 1) / G3_TILE * G3_TILE; }
+
+// ---- GEMM (gemm.cu):  D[m][n] = beta*D[m][n] + alpha * sum_k A[m][k] * B[n][k] ----
+// Both operands are K-contiguous ("NT"), fetched by TMA (3-D maps: k, row, batch).
+// Tile (x,y) of a launch addresses operands through affine maps so that every blocked step of
+// potrf / trtri / lauum / trsm is one launch of the same kernel.
+struct GemmArgs {
+  double* D;
+  long long ldd, strideD;
+  int mode;               // 0: RECT ntx x nty tiles, 1: TRI (x >= y), size ntx
+  int ntx, nty;
+  int d_r0, d_c0;         // D tile (x,y) starts at (d_r0 + 128x, d_c0 + 128y)
+  int a_r0, a_rx, a_ry;   // A rows start at a_r0 + x*a_rx + y*a_ry
+  int b_r0, b_rx, b_ry;
+  int ka0, ka_x, ka_y;    // first k column in A
+  int kb0, kb_x, kb_y;    // first k column in B
+  int kl0, kl_x, kl_y;    // contraction length (multiple of 16)
+  double alpha, beta;
+  const int* bmap;        // optional: launch batch index -> matrix index
+};
+int g3_gemm_launch(g3_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int B);
+
+// ---- factorisation (potrf.cu) ----
+// All matrices: Np x Np (Np multiple of 128), row-major, ld = Np, batch stride Np*Np.
+// Dinv: [B][T][128][128] inverses of the diagonal blocks of L (lower, explicit zeros above).
+int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, double* logdet, int* info,
+                     const int* bmap, int nb, int w_outer);
+int g3_trtri_batched(g3_ctx* ctx, const double* L, double* U, int Np, int B, const double* Dinv);
+int g3_lauum_batched(g3_ctx* ctx, const double* U, double* Kinv, int Np, int B);
+int g3_trsv_fwd(g3_ctx* ctx, const double* L, const double* Dinv, double* r, double* u, double* beta,
+                int Np, int B);
+int g3_trsv_bwd(g3_ctx* ctx, const double* L, const double* Dinv, double* s, double* alpha, int Np, int B);
+
+// ---- Gram (gram.cu) ----
+struct GramArgs {
+  const double* X1; const double* X2;  // row-major n x D
+  int n1, n2, D;
+  int same;                 // x1 is x2 (Noise/WN -> var*I)
+  int lower_only;           // write only tiles with row-tile >= col-tile (same==1)
+  int pad_identity;         // out is Np1 x Np2 padded; write identity on the padding diagonal
+  int skip_process_noise;   // noise=False selectors: the auto-added Noise leaf evaluates to 0 (elliptical.py:73-74)
+  const double* theta; int P;       // B x P natural-space hypers
+  const double* diag_shift;         // optional B: added on the diagonal (tt_to_cov / jitter), may be null
+  double* K; long long ldk, strideK;
+  int* status;              // optional B
+  const int* bmap;
+};
+int g3_gram_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const GramArgs& a, int B);
+// min over the diagonal of cov(X) for each theta (tt_to_cov needs it): out[b]
+int g3_gram_diag_min(g3_ctx* ctx, const g3_kernel_desc& desc, const double* X, int n, int D,
+                     const double* theta, int P, int B, double* diag_min, double* diag_mean, int* status,
+                     int skip_process_noise);
+int g3_check_desc(g3_ctx* ctx, const g3_kernel_desc& d, int D);
+struct VjpArgs {
+  const double* X1; const double* X2;
+  int n1, n2, D, same, lower_only;
+  const double* theta; int P;
+  const double* W; long long ldw, strideW;   // weights; if alpha != null: W_ij = cfac*alpha_i*alpha_j - W_ij
+  const double* alpha; long long strideAlpha; const double* cfac;
+  double scale;             // result multiplied by scale (0.5 for the GP gradient)
+  double* dtheta;           // B x P
+};
+int g3_gram_vjp_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const VjpArgs& a, int B);

@@ -1,0 +1,209 @@
+// Batched fp64 "NT" GEMM for sm_100a:  D[m][n] = beta*D[m][n] + alpha * sum_k A[m][k]*B[n][k]
+//
+// * operands: TMA (cp.async.bulk.tensor.3d, SWIZZLE_128B) into a 4-stage shared-memory ring,
+//   completion on mbarriers; one elected thread is the producer.
+// * math: DMMA.8x8x4 (mma.sync.m8n8k4.f64), 8 warps as 2(m) x 4(n), 32x32 per warp.
+//   A lane reads 16-byte chunks (two consecutive k) and the four k4-steps of a k-tile use the
+//   permuted contraction sets {e, 4+e, 8+e, 12+e}; A and B use the same permutation so the
+//   sum is unchanged while every fragment load is a conflict-free LDS.128.
+// * CTA tile 64 x 128, 96 KiB of shared memory -> two CTAs per SM so that one CTA's epilogue
+//   (read-modify-write of the 64x128 D tile) overlaps the other's main loop.
+// This one kernel implements every level-3 step of potrf / trtri / lauum / trsm (see potrf.cu);
+// the reference does these through LAPACK dpotrf and Theano's Murray reverse mode
+// (g3py/libs/tensors.py:198,224-260).
+#include "g3b_internal.cuh"
+
+namespace {
+
+constexpr int kStageBytesA = G3_BM * G3_BK * 8;  // 8 KiB
+constexpr int kStageBytesB = G3_BN * G3_BK * 8;  // 16 KiB
+constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+constexpr int kSmemBytes = G3_STAGES * kStageBytes + 1024;  // + manual 1024-B alignment slack
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void lds128(uint32_t addr, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+}
+
+__global__ void __launch_bounds__(256, 2)
+dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * G3_STAGES];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, t4 = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;
+
+  // ---- tile decode -------------------------------------------------------------------
+  const int h = blockIdx.x & 1;  // which 64-row half of the 128-row block
+  const int tile = blockIdx.x >> 1;
+  int x, y;
+  if (g.mode == 0) {
+    x = tile % g.ntx;
+    y = tile / g.ntx;
+  } else {
+    x = (int)((sqrt(8.0 * (double)tile + 1.0) - 1.0) * 0.5);
+    while ((long long)x * (x + 1) / 2 > tile) --x;
+    while ((long long)(x + 1) * (x + 2) / 2 <= tile) ++x;
+    y = tile - (int)((long long)x * (x + 1) / 2);
+  }
+  const int bidx = g.bmap ? g.bmap[blockIdx.y] : (int)blockIdx.y;
+  const int a_row = g.a_r0 + x * g.a_rx + y * g.a_ry + h * G3_BM;
+  const int b_row = g.b_r0 + x * g.b_rx + y * g.b_ry;
+  const int ka = g.ka0 + x * g.ka_x + y * g.ka_y;
+  const int kb = g.kb0 + x * g.kb_x + y * g.kb_y;
+  const int nk = (g.kl0 + x * g.kl_x + y * g.kl_y) / G3_BK;
+  double* Dt = g.D + (long long)bidx * g.strideD + (long long)(g.d_r0 + x * G3_TILE + h * G3_BM) * g.ldd +
+               (g.d_c0 + y * G3_TILE);
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (G3_STAGES + s); };
+
+  if (tid == 0) {
+    for (int s = 0; s < G3_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int kt) {  // thread 0 only
+    const int s = kt % G3_STAGES;
+    const uint32_t dstA = smem_base + s * kStageBytes;
+    const uint32_t dstB = dstA + kStageBytesA;
+    mbar_expect_tx(full_bar(s), kStageBytes);
+    tma_load_3d(dstA, &tmA, full_bar(s), ka + kt * G3_BK, a_row, bidx);
+    tma_load_3d(dstB, &tmB, full_bar(s), kb + kt * G3_BK, b_row, bidx);
+  };
+
+  if (tid == 0) {
+    const int pre = nk < G3_STAGES ? nk : G3_STAGES;
+    for (int kt = 0; kt < pre; ++kt) issue(kt);
+  }
+
+  // Pull the D tile towards L2 while the main loop runs (read-modify-write epilogue).
+  if (g.beta != 0.0) {
+    for (int l = tid; l < G3_BM * 8; l += 256) {
+      const double* p = Dt + (long long)(l >> 3) * g.ldd + (l & 7) * 16;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+  }
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // per-thread fragment offsets inside a stage: row*128 + ((chunk ^ (row&7)) << 4), row&7 == grp
+  const uint32_t offA = (uint32_t)((wm * 32 + grp) * 128);
+  const uint32_t offB = (uint32_t)(kStageBytesA + (wn * 32 + grp) * 128);
+  const uint32_t sw0 = (uint32_t)(((2 * t4 + 0) ^ grp) << 4);
+  const uint32_t sw1 = (uint32_t)(((2 * t4 + 1) ^ grp) << 4);
+
+  for (int kt = 0; kt < nk; ++kt) {
+    const int s = kt % G3_STAGES;
+    const uint32_t ph = (uint32_t)((kt / G3_STAGES) & 1);
+    // producer: refill the stage released one iteration ago
+    if (tid == 0 && kt >= 1 && kt - 1 + G3_STAGES < nk) {
+      const int sp = (kt - 1) % G3_STAGES;
+      mbar_wait(empty_bar(sp), (uint32_t)(((kt - 1) / G3_STAGES) & 1));
+      issue(kt - 1 + G3_STAGES);
+    }
+    mbar_wait(full_bar(s), ph);
+    const uint32_t st = smem_base + s * kStageBytes;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const uint32_t sw = c ? sw1 : sw0;
+      double a[4][2], b[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) lds128(st + offA + i * 1024 + sw, a[i][0], a[i][1]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) lds128(st + offB + j * 1024 + sw, b[j][0], b[j][1]);
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i][e], b[j][e]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar(s));
+  }
+
+  // ---- epilogue ------------------------------------------------------------------------
+  const double alpha = g.alpha, beta = g.beta;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double* rowp = Dt + (long long)(wm * 32 + i * 8 + grp) * g.ldd + wn * 32 + 2 * t4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double2* p = reinterpret_cast<double2*>(rowp + j * 8);
+      double2 v;
+      if (beta != 0.0) {
+        v = *p;
+        v.x = beta * v.x + alpha * acc[i][j][0];
+        v.y = beta * v.y + alpha * acc[i][j][1];
+      } else {
+        v.x = alpha * acc[i][j][0];
+        v.y = alpha * acc[i][j][1];
+      }
+      *p = v;
+    }
+  }
+}
+
+}  // namespace
+
+int g3_gemm_launch(g3_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int B) {
+  if (!ctx->gemm_ready) {
+    G3_CUDA(ctx, cudaFuncSetAttribute(dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    ctx->gemm_ready = true;
+  }
+  long long ntiles = a.mode == 0 ? (long long)a.ntx * a.nty : (long long)a.ntx * (a.ntx + 1) / 2;
+  if (ntiles <= 0 || B <= 0) return 0;
+  dim3 grid((unsigned)(ntiles * 2), (unsigned)B, 1);
+  dgemm_nt_kernel<<<grid, 256, kSmemBytes, ctx->stream>>>(tmA, tmB, a);
+  G3_LAUNCH_CHECK(ctx);
+  return 0;
+}

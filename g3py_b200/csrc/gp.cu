@@ -1,0 +1,700 @@
+// C-ABI entry points of libg3b.so: Gram / VJP / robust Cholesky on host arrays, the fused
+// marginal-likelihood + gradient pipeline, posterior moments, and the big-matrix Cholesky.
+//
+// Pipeline of g3_gp_run for B hyper samples (everything on ctx->stream, no host sync inside):
+//   gram_diag  -> tt_to_cov shift            (g3py/libs/tensors.py:95-98)
+//   gram_fwd   -> K_b lower tiles, padded    (kernels.py:106-110, elliptical.py:71)
+//   potrf      -> L_b, Dinv, logdet, info    (tensors.py:197-201)
+//   trsv_fwd   -> u = L^-1 delta, beta       (gaussian.py:212-215, studentT.py:118-119)
+//   [grad] trsv_bwd -> alpha; trtri -> U = L^-T; lauum -> K^-1 (over L); gram_vjp with
+//          W = c alpha alpha' - K^-1 -> dtheta; ddelta = -c alpha          
+// The jitter ladder (tensors.py:203-213) runs in g3_gp_download only for items whose info != 0.
+#include "g3b_internal.cuh"
+#include <math.h>
+#include <string.h>
+
+namespace {
+
+constexpr int TS = G3_TILE;
+
+__global__ void gp_prep_kernel(const double* __restrict__ dmin, double jitter, double* __restrict__ shift,
+                               double* __restrict__ beta, double* __restrict__ logdet, int* __restrict__ info,
+                               int* __restrict__ status, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double m = dmin[b];
+  int st = status[b];
+  if (m > 0.0) {
+    shift[b] = 0.0;
+  } else {  // tt_to_cov: r + (1e-6 - m) * eye
+    shift[b] = jitter - m;
+    st |= G3_ST_DIAG_SHIFT;
+  }
+  status[b] = st;
+  beta[b] = 0.0;
+  logdet[b] = 0.0;
+  info[b] = 0;
+}
+
+// r[b][i] = delta[b*stride + i] (i < N), 0 on the padding.  Non-finite delta -> status.
+__global__ void gp_expand_delta_kernel(const double* __restrict__ delta, int stride, int N, int Np,
+                                       double* __restrict__ r, int* __restrict__ status) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Np) return;
+  double v = 0.0;
+  if (i < N) {
+    v = delta[(long long)b * stride + i];
+    if (!isfinite(v)) atomicOr(status + b, G3_ST_NONFINITE_RESULT);
+  }
+  r[(long long)b * Np + i] = v;
+}
+
+__global__ void gp_zero_sub_kernel(double* __restrict__ beta, double* __restrict__ logdet, int* __restrict__ info,
+                                   const int* __restrict__ bmap, int nb) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nb) return;
+  const int b = bmap[k];
+  if (beta) beta[b] = 0.0;
+  logdet[b] = 0.0;
+  info[b] = 0;
+}
+
+__global__ void gp_zero_beta_kernel(double* __restrict__ beta, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) beta[b] = 0.0;
+}
+
+// c_b = 1 (gauss) or (nu+N)/(nu-2+beta) (student).  Also the final non-finite check.
+__global__ void gp_cfac_kernel(int kind, const double* __restrict__ nu, const double* __restrict__ beta,
+                               const double* __restrict__ logdet, double n, double* __restrict__ cfac,
+                               int* __restrict__ status, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  cfac[b] = (kind == G3_KIND_STUDENT) ? (nu[b] + n) / (nu[b] - 2.0 + beta[b]) : 1.0;
+  if (!isfinite(beta[b]) || !isfinite(logdet[b])) status[b] |= G3_ST_NONFINITE_RESULT;
+}
+
+__global__ void gp_ddelta_kernel(const double* __restrict__ alpha, const double* __restrict__ cfac, int N, int Np,
+                                 double* __restrict__ ddelta) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) ddelta[(long long)b * N + i] = -cfac[b] * alpha[(long long)b * Np + i];
+}
+
+// A (n x n, ld) += shift on the diagonal; padding of the Np x Np device matrix set to identity.
+__global__ void mat_pad_shift_kernel(double* __restrict__ A, int n, int Np, long long strideA,
+                                     const double* __restrict__ shift, const int* __restrict__ bmap) {
+  const int b = bmap ? bmap[blockIdx.y] : (int)blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Np) return;
+  double* d = A + (long long)b * strideA + (long long)i * Np + i;
+  if (i < n) {
+    if (shift) *d += shift[b];
+  } else {
+    *d = 1.0;
+  }
+}
+
+// zero the strictly-upper 128x128 tiles (the factor leaves K's upper tiles untouched).
+__global__ void __launch_bounds__(256)
+zero_upper_tiles_kernel(double* __restrict__ A, int Np, long long strideA, int T) {
+  const int b = blockIdx.y;
+  int tile = blockIdx.x;  // enumerates (x, y), x < y
+  int y = (int)((sqrt(8.0 * (double)tile + 1.0) + 1.0) * 0.5);
+  while ((long long)y * (y - 1) / 2 > tile) --y;
+  while ((long long)(y + 1) * y / 2 <= tile) ++y;
+  const int x = tile - (int)((long long)y * (y - 1) / 2);
+  double* At = A + (long long)b * strideA + (long long)x * TS * Np + (long long)y * TS;
+  for (int idx = threadIdx.x; idx < TS * TS / 2; idx += 256) {
+    const int r = idx >> 6, c = (idx & 63) * 2;
+    *reinterpret_cast<double2*>(At + (long long)r * Np + c) = make_double2(0.0, 0.0);
+  }
+}
+
+// kss[0] = min diag of cov(space); kss[2] = tt_to_cov shift (only the noisy selector applies tt_to_cov).
+__global__ void post_kss_shift_kernel(double* kss, double jitter, int apply) {
+  if (threadIdx.x == 0) kss[2] = (apply && !(kss[0] > 0.0)) ? jitter - kss[0] : 0.0;
+}
+
+// mean[m] = sum_n Vt[m][n] u[n];  var[m] = max(kss - sum_n Vt[m][n]^2, 0).  One warp per row.
+__global__ void __launch_bounds__(256)
+post_moments_kernel(const double* __restrict__ Vt, int Np, int M, const double* __restrict__ u,
+                    const double* __restrict__ kss, const double* __restrict__ kss_shift,
+                    double* __restrict__ mean, double* __restrict__ var) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const double* row = Vt + (long long)m * Np;
+  double s1 = 0.0, s2 = 0.0;
+  for (int n = lane * 2; n < Np; n += 64) {
+    const double2 v = *reinterpret_cast<const double2*>(row + n);
+    const double2 w = *reinterpret_cast<const double2*>(u + n);
+    s1 += v.x * w.x + v.y * w.y;
+    s2 += v.x * v.x + v.y * v.y;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) {
+    mean[m] = s1;
+    const double v = (kss[0] + kss_shift[0]) - s2;
+    var[m] = v < 0.0 ? 0.0 : v;   // tt_to_bounded(extract_diag(..), 0)  elliptical.py:94-97
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+static GemmArgs gz() {
+  GemmArgs g;
+  memset(&g, 0, sizeof g);
+  return g;
+}
+
+struct GpBufs {
+  double *theta, *delta, *nu, *A, *U, *Dinv, *r, *u, *s, *alpha, *beta, *logdet, *shift, *dmin, *dmean, *cfac, *dtheta,
+      *ddelta, *shift2;
+  int *info, *status, *bmap;
+};
+
+static int gp_alloc(g3_ctx* ctx, GpBufs& w, int B, int P, int N, int want_grad, int delta_rows) {
+  const int Np = g3_pad(N), T = Np / TS;
+  const size_t mat = sizeof(double) * (size_t)B * Np * Np;
+#define WS(field, name, bytes)                          \
+  w.field = (decltype(w.field))g3_ws(ctx, name, bytes); \
+  if (!w.field) return -2;
+  WS(theta, "gp_theta", sizeof(double) * (size_t)B * (P > 0 ? P : 1));
+  WS(delta, "gp_delta", sizeof(double) * (size_t)delta_rows * N);
+  WS(nu, "gp_nu", sizeof(double) * B);
+  WS(A, "gp_A", mat);
+  WS(Dinv, "gp_Dinv", sizeof(double) * (size_t)B * T * TS * TS);
+  WS(r, "gp_r", sizeof(double) * (size_t)B * Np);
+  WS(u, "gp_u", sizeof(double) * (size_t)B * Np);
+  WS(s, "gp_s", sizeof(double) * (size_t)B * Np);
+  WS(alpha, "gp_alpha", sizeof(double) * (size_t)B * Np);
+  WS(beta, "gp_beta", sizeof(double) * B);
+  WS(logdet, "gp_logdet", sizeof(double) * B);
+  WS(shift, "gp_shift", sizeof(double) * B);
+  WS(shift2, "gp_shift2", sizeof(double) * B);
+  WS(dmin, "gp_dmin", sizeof(double) * B);
+  WS(dmean, "gp_dmean", sizeof(double) * B);
+  WS(cfac, "gp_cfac", sizeof(double) * B);
+  WS(dtheta, "gp_dtheta", sizeof(double) * (size_t)B * (P > 0 ? P : 1));
+  WS(ddelta, "gp_ddelta", sizeof(double) * (size_t)B * N);
+  WS(info, "gp_info", sizeof(int) * B);
+  WS(status, "gp_status", sizeof(int) * B);
+  WS(bmap, "gp_bmap", sizeof(int) * B);
+  if (want_grad) {
+    WS(U, "gp_U", mat);
+  } else {
+    w.U = nullptr;
+  }
+#undef WS
+  return 0;
+}
+
+// Stages after the factorisation: solves, beta, and (optionally) the gradient.
+static int gp_after_potrf(g3_ctx* ctx, GpBufs& w) {
+  const g3_gp_state& st = ctx->gp;
+  const int B = st.B, N = ctx->N, Np = g3_pad(N), T = Np / TS, P = st.desc.n_theta;
+  int rc;
+  gp_zero_beta_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(w.beta, B);
+  G3_LAUNCH_CHECK(ctx);
+  gp_expand_delta_kernel<<<dim3((Np + 255) / 256, B), 256, 0, ctx->stream>>>(w.delta, st.delta_stride, N, Np, w.r,
+                                                                             w.status);
+  G3_LAUNCH_CHECK(ctx);
+  if ((rc = g3_trsv_fwd(ctx, w.A, w.Dinv, w.r, w.u, w.beta, Np, B))) return rc;
+  gp_cfac_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(st.kind, w.nu, w.beta, w.logdet, (double)N, w.cfac,
+                                                           w.status, B);
+  G3_LAUNCH_CHECK(ctx);
+  if (!st.want_grad) return 0;
+  G3_CUDA(ctx, cudaMemcpyAsync(w.s, w.u, sizeof(double) * (size_t)B * Np, cudaMemcpyDeviceToDevice, ctx->stream));
+  if ((rc = g3_trsv_bwd(ctx, w.A, w.Dinv, w.s, w.alpha, Np, B))) return rc;
+  if ((rc = g3_trtri_batched(ctx, w.A, w.U, Np, B, w.Dinv))) return rc;
+  if ((rc = g3_lauum_batched(ctx, w.U, w.A, Np, B))) return rc;  // K^-1 (lower tiles) overwrites L
+  VjpArgs v;
+  memset(&v, 0, sizeof v);
+  v.X1 = ctx->dX; v.X2 = ctx->dX; v.n1 = N; v.n2 = N; v.D = ctx->D; v.same = 1; v.lower_only = 1;
+  v.theta = w.theta; v.P = P;
+  v.W = w.A; v.ldw = Np; v.strideW = (long long)Np * Np;
+  v.alpha = w.alpha; v.strideAlpha = Np; v.cfac = w.cfac;
+  v.scale = 0.5;
+  v.dtheta = w.dtheta;
+  if ((rc = g3_gram_vjp_launch(ctx, st.desc, v, B))) return rc;
+  gp_ddelta_kernel<<<dim3((N + 255) / 256, B), 256, 0, ctx->stream>>>(w.alpha, w.cfac, N, Np, w.ddelta);
+  G3_LAUNCH_CHECK(ctx);
+  (void)T;
+  return 0;
+}
+
+static int gp_build_and_factor(g3_ctx* ctx, GpBufs& w, const double* shift, const int* bmap, int nb) {
+  const g3_gp_state& st = ctx->gp;
+  const int N = ctx->N, Np = g3_pad(N);
+  GramArgs a;
+  memset(&a, 0, sizeof a);
+  a.X1 = ctx->dX; a.X2 = ctx->dX; a.n1 = N; a.n2 = N; a.D = ctx->D;
+  a.same = 1; a.lower_only = 1; a.pad_identity = 1;
+  a.theta = w.theta; a.P = st.desc.n_theta;
+  a.diag_shift = shift;
+  a.K = w.A; a.ldk = Np; a.strideK = (long long)Np * Np;
+  a.status = w.status; a.bmap = bmap;
+  int rc;
+  if ((rc = g3_gram_launch(ctx, st.desc, a, bmap ? nb : st.B))) return rc;
+  return g3_potrf_batched(ctx, w.A, Np, st.B, w.Dinv, w.logdet, w.info, bmap, nb, ctx->potrf_w);
+}
+
+extern "C" {
+
+int g3_set_potrf_block(g3_ctx* ctx, int w_outer) {
+  ctx->potrf_w = w_outer;
+  return 0;
+}
+
+int g3_gp_upload(g3_ctx* ctx, const g3_kernel_desc* desc, int kind, const double* delta, int delta_stride,
+                 const double* theta, int B, const double* nu_or_NULL, int want_grad) {
+  if (!ctx || !desc || !delta || B <= 0) return g3_fail_msg(ctx, "g3_gp_upload: bad arguments");
+  if (!ctx->dX) return g3_fail_msg(ctx, "g3_gp_upload: call g3_set_data first");
+  if (desc->n_theta > 0 && !theta) return g3_fail_msg(ctx, "g3_gp_upload: theta is NULL");
+  if (kind == G3_KIND_STUDENT && !nu_or_NULL) return g3_fail_msg(ctx, "g3_gp_upload: student kind needs nu");
+  if (delta_stride != 0 && delta_stride != ctx->N) return g3_fail_msg(ctx, "g3_gp_upload: delta_stride must be 0 or N");
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = g3_check_desc(ctx, *desc, ctx->D);
+  if (rc) return rc;
+  const int N = ctx->N, P = desc->n_theta;
+  GpBufs w;
+  const int drows = delta_stride ? B : 1;
+  if ((rc = gp_alloc(ctx, w, B, P, N, want_grad, drows))) return rc;
+  ctx->gp.desc = *desc;
+  ctx->gp.kind = kind;
+  ctx->gp.B = B;
+  ctx->gp.want_grad = want_grad;
+  ctx->gp.delta_stride = delta_stride;
+  if (P > 0)
+    G3_CUDA(ctx, cudaMemcpyAsync(w.theta, theta, sizeof(double) * (size_t)B * P, cudaMemcpyHostToDevice, ctx->stream));
+  G3_CUDA(ctx, cudaMemcpyAsync(w.delta, delta, sizeof(double) * (size_t)drows * N, cudaMemcpyHostToDevice, ctx->stream));
+  if (nu_or_NULL)
+    G3_CUDA(ctx, cudaMemcpyAsync(w.nu, nu_or_NULL, sizeof(double) * B, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->gp.valid = 1;
+  return 0;
+}
+
+int g3_gp_run(g3_ctx* ctx) {
+  if (!ctx || !ctx->gp.valid) return g3_fail_msg(ctx, "g3_gp_run: nothing uploaded");
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  const g3_gp_state& st = ctx->gp;
+  const int B = st.B, N = ctx->N, P = st.desc.n_theta;
+  GpBufs w;
+  int rc;
+  if ((rc = gp_alloc(ctx, w, B, P, N, st.want_grad, st.delta_stride ? B : 1))) return rc;
+  G3_CUDA(ctx, cudaMemsetAsync(w.status, 0, sizeof(int) * B, ctx->stream));
+  if ((rc = g3_gram_diag_min(ctx, st.desc, ctx->dX, N, ctx->D, w.theta, P, B, w.dmin, w.dmean, w.status, 0))) return rc;
+  gp_prep_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(w.dmin, ctx->jitter_rel, w.shift, w.beta, w.logdet, w.info,
+                                                           w.status, B);
+  G3_LAUNCH_CHECK(ctx);
+  if ((rc = gp_build_and_factor(ctx, w, w.shift, nullptr, 0))) return rc;
+  return gp_after_potrf(ctx, w);
+}
+
+int g3_gp_download(g3_ctx* ctx, double* beta, double* logdet, double* dtheta_or_NULL, double* ddelta_or_NULL,
+                   int* status) {
+  if (!ctx || !ctx->gp.valid) return g3_fail_msg(ctx, "g3_gp_download: nothing uploaded");
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  const g3_gp_state& st = ctx->gp;
+  const int B = st.B, N = ctx->N, P = st.desc.n_theta;
+  GpBufs w;
+  int rc;
+  if ((rc = gp_alloc(ctx, w, B, P, N, st.want_grad, st.delta_stride ? B : 1))) return rc;
+  std::vector<int> info(B), stat(B);
+  G3_CUDA(ctx, cudaMemcpyAsync(info.data(), w.info, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<int> failed;
+  for (int b = 0; b < B; ++b)
+    if (info[b] != 0) failed.push_back(b);
+  std::vector<int> tries(B, 0), exhausted(B, 0);
+  if (!failed.empty()) {
+    // CholeskyRobust._cholesky ladder (tensors.py:203-213): dK = mean(diag K) * jitter, x10 per try.
+    std::vector<double> dmean(B), shift(B), dK(B), sh2(B);
+    G3_CUDA(ctx, cudaMemcpyAsync(dmean.data(), w.dmean, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    G3_CUDA(ctx, cudaMemcpyAsync(shift.data(), w.shift, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int b : failed) dK[b] = (dmean[b] + shift[b]) * ctx->jitter_rel;
+    for (int t = 1; t <= ctx->max_tries && !failed.empty(); ++t) {
+      for (int b = 0; b < B; ++b) sh2[b] = shift[b] + dK[b];
+      const int nb = (int)failed.size();
+      G3_CUDA(ctx, cudaMemcpyAsync(w.shift2, sh2.data(), sizeof(double) * B, cudaMemcpyHostToDevice, ctx->stream));
+      G3_CUDA(ctx, cudaMemcpyAsync(w.bmap, failed.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+      gp_zero_sub_kernel<<<(nb + 127) / 128, 128, 0, ctx->stream>>>(nullptr, w.logdet, w.info, w.bmap, nb);
+      G3_LAUNCH_CHECK(ctx);
+      if ((rc = gp_build_and_factor(ctx, w, w.shift2, w.bmap, nb))) return rc;
+      G3_CUDA(ctx, cudaMemcpyAsync(info.data(), w.info, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+      G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      std::vector<int> still;
+      for (int b : failed) {
+        if (info[b] != 0) {
+          still.push_back(b);
+          dK[b] *= 10.0;
+        } else {
+          tries[b] = t;
+        }
+      }
+      failed.swap(still);
+    }
+    for (int b : failed) exhausted[b] = 1;
+    // The items repaired by the ladder need their solves / gradient again; the stages are idempotent
+    // given (L, delta), so they are simply re-run for the whole batch (rare path).  K^-1 overwrote L for
+    // the items that had succeeded, so with gradients on the whole batch is rebuilt first.
+    if (st.want_grad) {
+      for (int b = 0; b < B; ++b) sh2[b] = shift[b] + (tries[b] ? dK[b] : 0.0);
+      G3_CUDA(ctx, cudaMemcpyAsync(w.shift2, sh2.data(), sizeof(double) * B, cudaMemcpyHostToDevice, ctx->stream));
+      G3_CUDA(ctx, cudaMemsetAsync(w.logdet, 0, sizeof(double) * B, ctx->stream));
+      G3_CUDA(ctx, cudaMemsetAsync(w.info, 0, sizeof(int) * B, ctx->stream));
+      if ((rc = gp_build_and_factor(ctx, w, w.shift2, nullptr, 0))) return rc;
+    }
+    if ((rc = gp_after_potrf(ctx, w))) return rc;
+  }
+  G3_CUDA(ctx, cudaMemcpyAsync(beta, w.beta, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaMemcpyAsync(logdet, w.logdet, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaMemcpyAsync(stat.data(), w.status, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  if (st.want_grad && dtheta_or_NULL && P > 0)
+    G3_CUDA(ctx, cudaMemcpyAsync(dtheta_or_NULL, w.dtheta, sizeof(double) * (size_t)B * P, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+  if (st.want_grad && ddelta_or_NULL)
+    G3_CUDA(ctx, cudaMemcpyAsync(ddelta_or_NULL, w.ddelta, sizeof(double) * (size_t)B * N, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+  G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (status) {
+    for (int b = 0; b < B; ++b) {
+      int s = stat[b];
+      if (tries[b]) s |= G3_ST_JITTER | (tries[b] << 8);
+      if (exhausted[b]) s |= G3_ST_POTRF_FAILED | G3_ST_JITTER | (ctx->max_tries << 8);
+      status[b] = s;
+    }
+  }
+  return 0;
+}
+
+int g3_gp_logp_grad(g3_ctx* ctx, const g3_kernel_desc* desc, int kind, const double* delta, int delta_stride,
+                    const double* theta, int B, const double* nu_or_NULL, double* beta, double* logdet,
+                    double* dtheta_or_NULL, double* ddelta_or_NULL, int* status) {
+  if (!beta || !logdet) return g3_fail_msg(ctx, "g3_gp_logp_grad: beta/logdet outputs are required");
+  const int want_grad = (dtheta_or_NULL || ddelta_or_NULL) ? 1 : 0;
+  int rc;
+  if ((rc = g3_gp_upload(ctx, desc, kind, delta, delta_stride, theta, B, nu_or_NULL, want_grad))) return rc;
+  if ((rc = g3_gp_run(ctx))) return rc;
+  return g3_gp_download(ctx, beta, logdet, dtheta_or_NULL, ddelta_or_NULL, status);
+}
+
+// ---- Gram on host arrays -----------------------------------------------------------------
+int g3_gram(g3_ctx* ctx, const g3_kernel_desc* desc, const double* X1, int n1, const double* X2, int n2, int D,
+            const double* theta, int B, double* K_out, int* status) {
+  if (!ctx || !desc || !X1 || !K_out || n1 <= 0 || B <= 0 || D <= 0 || D > G3_MAX_DIM)
+    return g3_fail_msg(ctx, "g3_gram: bad arguments");
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int same = X2 == nullptr;
+  if (same) n2 = n1;
+  if (n2 <= 0) return g3_fail_msg(ctx, "g3_gram: n2 <= 0");
+  const int P = desc->n_theta;
+  const int Np1 = g3_pad(n1), Np2 = g3_pad(n2);
+  double* dX1 = (double*)g3_ws(ctx, "gram_X1", sizeof(double) * (size_t)n1 * D);
+  double* dX2 = same ? dX1 : (double*)g3_ws(ctx, "gram_X2", sizeof(double) * (size_t)n2 * D);
+  double* dth = (double*)g3_ws(ctx, "gram_theta", sizeof(double) * (size_t)B * (P > 0 ? P : 1));
+  double* dK = (double*)g3_ws(ctx, "gram_K", sizeof(double) * (size_t)B * Np1 * Np2);
+  int* dst = (int*)g3_ws(ctx, "gram_status", sizeof(int) * B);
+  if (!dX1 || !dX2 || !dth || !dK || !dst) return -2;
+  G3_CUDA(ctx, cudaMemcpyAsync(dX1, X1, sizeof(double) * (size_t)n1 * D, cudaMemcpyHostToDevice, ctx->stream));
+  if (!same) G3_CUDA(ctx, cudaMemcpyAsync(dX2, X2, sizeof(double) * (size_t)n2 * D, cudaMemcpyHostToDevice, ctx->stream));
+  if (P > 0) G3_CUDA(ctx, cudaMemcpyAsync(dth, theta, sizeof(double) * (size_t)B * P, cudaMemcpyHostToDevice, ctx->stream));
+  G3_CUDA(ctx, cudaMemsetAsync(dst, 0, sizeof(int) * B, ctx->stream));
+  GramArgs a;
+  memset(&a, 0, sizeof a);
+  a.X1 = dX1; a.X2 = dX2; a.n1 = n1; a.n2 = n2; a.D = D; a.same = same;
+  a.theta = dth; a.P = P;
+  a.K = dK; a.ldk = Np2; a.strideK = (long long)Np1 * Np2; a.status = dst;
+  int rc;
+  if ((rc = g3_gram_launch(ctx, *desc, a, B))) return rc;
+  G3_CUDA(ctx, cudaMemcpy2DAsync(K_out, sizeof(double) * n2, dK, sizeof(double) * Np2, sizeof(double) * n2,
+                                 (size_t)n1, cudaMemcpyDeviceToHost, ctx->stream));
+  for (int b = 1; b < B; ++b)
+    G3_CUDA(ctx, cudaMemcpy2DAsync(K_out + (size_t)b * n1 * n2, sizeof(double) * n2, dK + (size_t)b * Np1 * Np2,
+                                   sizeof(double) * Np2, sizeof(double) * n2, (size_t)n1, cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+  if (status) G3_CUDA(ctx, cudaMemcpyAsync(status, dst, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int g3_gram_vjp(g3_ctx* ctx, const g3_kernel_desc* desc, const double* X1, int n1, const double* X2, int n2, int D,
+                const double* theta, int B, const double* W, double* dtheta) {
+  if (!ctx || !desc || !X1 || !W || !dtheta || n1 <= 0 || B <= 0 || D <= 0 || D > G3_MAX_DIM)
+    return g3_fail_msg(ctx, "g3_gram_vjp: bad arguments");
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int same = X2 == nullptr;
+  if (same) n2 = n1;
+  const int P = desc->n_theta;
+  if (P <= 0) return 0;
+  const int Np1 = g3_pad(n1), Np2 = g3_pad(n2);
+  double* dX1 = (double*)g3_ws(ctx, "gram_X1", sizeof(double) * (size_t)n1 * D);
+  double* dX2 = same ? dX1 : (double*)g3_ws(ctx, "gram_X2", sizeof(double) * (size_t)n2 * D);
+  double* dth = (double*)g3_ws(ctx, "gram_theta", sizeof(double) * (size_t)B * P);
+  double* dW = (double*)g3_ws(ctx, "gram_K", sizeof(double) * (size_t)B * Np1 * Np2);
+  double* dg = (double*)g3_ws(ctx, "gram_dtheta", sizeof(double) * (size_t)B * P);
+  if (!dX1 || !dX2 || !dth || !dW || !dg) return -2;
+  G3_CUDA(ctx, cudaMemcpyAsync(dX1, X1, sizeof(double) * (size_t)n1 * D, cudaMemcpyHostToDevice, ctx->stream));
+  if (!same) G3_CUDA(ctx, cudaMemcpyAsync(dX2, X2, sizeof(double) * (size_t)n2 * D, cudaMemcpyHostToDevice, ctx->stream));
+  G3_CUDA(ctx, cudaMemcpyAsync(dth, theta, sizeof(double) * (size_t)B * P, cudaMemcpyHostToDevice, ctx->stream));
+  G3_CUDA(ctx, cudaMemsetAsync(dW, 0, sizeof(double) * (size_t)B * Np1 * Np2, ctx->stream));
+  for (int b = 0; b < B; ++b)
+    G3_CUDA(ctx, cudaMemcpy2DAsync(dW + (size_t)b * Np1 * Np2, sizeof(double) * Np2, W + (size_t)b * n1 * n2,
+                                   sizeof(double) * n2, sizeof(double) * n2, (size_t)n1, cudaMemcpyHostToDevice,
+                                   ctx->stream));
+  VjpArgs v;
+  memset(&v, 0, sizeof v);
+  v.X1 = dX1; v.X2 = dX2; v.n1 = n1; v.n2 = n2; v.D = D; v.same = same; v.lower_only = 0;
+  v.theta = dth; v.P = P; v.W = dW; v.ldw = Np2; v.strideW = (long long)Np1 * Np2;
+  v.scale = 1.0; v.dtheta = dg;
+  int rc;
+  if ((rc = g3_gram_vjp_launch(ctx, *desc, v, B))) return rc;
+  G3_CUDA(ctx, cudaMemcpyAsync(dtheta, dg, sizeof(double) * (size_t)B * P, cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---- robust Cholesky on host matrices -------------------------------------------------------
+int g3_potrf_robust(g3_ctx* ctx, double* A, int n, int lda, int B, int* info_out, double* jitter_out) {
+  if (!ctx || !A || n <= 0 || lda < n || B <= 0 || !info_out) return g3_fail_msg(ctx, "g3_potrf_robust: bad arguments");
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int Np = g3_pad(n), T = Np / TS;
+  const size_t mat = (size_t)Np * Np;
+  double* dA = (double*)g3_ws(ctx, "pr_A", sizeof(double) * mat * B);
+  double* dDinv = (double*)g3_ws(ctx, "pr_Dinv", sizeof(double) * (size_t)B * T * TS * TS);
+  double* dld = (double*)g3_ws(ctx, "pr_logdet", sizeof(double) * B);
+  double* dsh = (double*)g3_ws(ctx, "pr_shift", sizeof(double) * B);
+  int* dinfo = (int*)g3_ws(ctx, "pr_info", sizeof(int) * B);
+  int* dbmap = (int*)g3_ws(ctx, "pr_bmap", sizeof(int) * B);
+  if (!dA || !dDinv || !dld || !dsh || !dinfo || !dbmap) return -2;
+  int rc;
+  auto upload = [&](int b) -> int {
+    double* d = dA + mat * b;
+    if (Np != n) G3_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(double) * mat, ctx->stream));
+    G3_CUDA(ctx, cudaMemcpy2DAsync(d, sizeof(double) * Np, A + (size_t)b * n * lda, sizeof(double) * lda,
+                                   sizeof(double) * n, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+  };
+  for (int b = 0; b < B; ++b)
+    if ((rc = upload(b))) return rc;
+  mat_pad_shift_kernel<<<dim3((Np + 255) / 256, B), 256, 0, ctx->stream>>>(dA, n, Np, (long long)mat, nullptr, nullptr);
+  G3_LAUNCH_CHECK(ctx);
+  G3_CUDA(ctx, cudaMemsetAsync(dld, 0, sizeof(double) * B, ctx->stream));
+  G3_CUDA(ctx, cudaMemsetAsync(dinfo, 0, sizeof(int) * B, ctx->stream));
+  if ((rc = g3_potrf_batched(ctx, dA, Np, B, dDinv, dld, dinfo, nullptr, 0, ctx->potrf_w))) return rc;
+  std::vector<int> info(B);
+  G3_CUDA(ctx, cudaMemcpyAsync(info.data(), dinfo, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<int> failed;
+  for (int b = 0; b < B; ++b) {
+    info_out[b] = 0;
+    if (jitter_out) jitter_out[b] = 0.0;
+    if (info[b] != 0) failed.push_back(b);
+  }
+  if (!failed.empty()) {
+    std::vector<double> dK(B, 0.0), pre(B, 0.0), sh(B, 0.0);
+    for (int b : failed) {  // tensors.py:203-207 (host O(n) scan of the caller's diagonal)
+      const double* Ab = A + (size_t)b * n * lda;
+      double sum = 0.0, mn = INFINITY;
+      bool nonpos = false;
+      for (int i = 0; i < n; ++i) {
+        const double d = Ab[(size_t)i * lda + i];
+        sum += d;
+        if (d < mn) mn = d;
+        if (d <= 0.0) nonpos = true;
+      }
+      const double mean = sum / n;
+      dK[b] = mean * ctx->jitter_rel;
+      if (nonpos) pre[b] = mean * ctx->jitter_rel - mn;
+    }
+    for (int t = 1; t <= ctx->max_tries && !failed.empty(); ++t) {
+      const int nb = (int)failed.size();
+      for (int b : failed) {
+        sh[b] = pre[b] + dK[b];
+        if ((rc = upload(b))) return rc;
+      }
+      G3_CUDA(ctx, cudaMemcpyAsync(dsh, sh.data(), sizeof(double) * B, cudaMemcpyHostToDevice, ctx->stream));
+      G3_CUDA(ctx, cudaMemcpyAsync(dbmap, failed.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
+      mat_pad_shift_kernel<<<dim3((Np + 255) / 256, nb), 256, 0, ctx->stream>>>(dA, n, Np, (long long)mat, dsh, dbmap);
+      G3_LAUNCH_CHECK(ctx);
+      gp_zero_sub_kernel<<<(nb + 127) / 128, 128, 0, ctx->stream>>>(nullptr, dld, dinfo, dbmap, nb);
+      G3_LAUNCH_CHECK(ctx);
+      if ((rc = g3_potrf_batched(ctx, dA, Np, B, dDinv, dld, dinfo, dbmap, nb, ctx->potrf_w))) return rc;
+      G3_CUDA(ctx, cudaMemcpyAsync(info.data(), dinfo, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+      G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      std::vector<int> still;
+      for (int b : failed) {
+        if (info[b] != 0) {
+          still.push_back(b);
+          dK[b] *= 10.0;
+        } else {
+          info_out[b] = t;
+          if (jitter_out) jitter_out[b] = sh[b];
+        }
+      }
+      failed.swap(still);
+    }
+    for (int b : failed) info_out[b] = -1;
+  }
+  if (T > 1) {
+    zero_upper_tiles_kernel<<<dim3(T * (T - 1) / 2, B), 256, 0, ctx->stream>>>(dA, Np, (long long)mat, T);
+    G3_LAUNCH_CHECK(ctx);
+  }
+  for (int b = 0; b < B; ++b) {
+    if (info_out[b] < 0) continue;  // caller applies the 1e-10*I fallback (tensors.py:218-222)
+    G3_CUDA(ctx, cudaMemcpy2DAsync(A + (size_t)b * n * lda, sizeof(double) * lda, dA + mat * b, sizeof(double) * Np,
+                                   sizeof(double) * n, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---- posterior moments for one theta -----------------------------------------------------------
+int g3_gp_posterior(g3_ctx* ctx, const g3_kernel_desc* desc, const double* Xs, int M, const double* delta,
+                    const double* theta, int flags, double* mean_out, double* var_out, double* cov_out,
+                    double* beta_out, int* status) {
+  if (!ctx || !desc || !Xs || M <= 0 || !delta || !mean_out || !var_out)
+    return g3_fail_msg(ctx, "g3_gp_posterior: bad arguments");
+  if (!ctx->dX) return g3_fail_msg(ctx, "g3_gp_posterior: call g3_set_data first");
+  if ((flags & G3_POST_COV) && !cov_out) return g3_fail_msg(ctx, "g3_gp_posterior: G3_POST_COV needs cov_out");
+  int rc;
+  // factor K (and run the ladder if needed) through the logp path: leaves L, Dinv, u in the gp_* buffers
+  double beta = 0.0, logdet = 0.0;
+  int st = 0;
+  if ((rc = g3_gp_upload(ctx, desc, G3_KIND_GAUSS, delta, 0, theta, 1, nullptr, 0))) return rc;
+  if ((rc = g3_gp_run(ctx))) return rc;
+  if ((rc = g3_gp_download(ctx, &beta, &logdet, nullptr, nullptr, &st))) return rc;
+  if (beta_out) *beta_out = beta;
+  if (status) *status = st;
+  const int N = ctx->N, D = ctx->D, P = desc->n_theta, Np = g3_pad(N), Mp = g3_pad(M), T = Np / TS, TM = Mp / TS;
+  GpBufs w;
+  if ((rc = gp_alloc(ctx, w, 1, P, N, 0, 1))) return rc;
+  const int skip_pn = (flags & G3_POST_NOISE) ? 0 : 1;
+  double* dXs = (double*)g3_ws(ctx, "post_Xs", sizeof(double) * (size_t)M * D);
+  double* Vt = (double*)g3_ws(ctx, "post_Vt", sizeof(double) * (size_t)Mp * Np);
+  double* dmean = (double*)g3_ws(ctx, "post_mean", sizeof(double) * Mp);
+  double* dvar = (double*)g3_ws(ctx, "post_var", sizeof(double) * Mp);
+  double* kss = (double*)g3_ws(ctx, "post_kss", sizeof(double) * 4);
+  if (!dXs || !Vt || !dmean || !dvar || !kss) return -2;
+  G3_CUDA(ctx, cudaMemcpyAsync(dXs, Xs, sizeof(double) * (size_t)M * D, cudaMemcpyHostToDevice, ctx->stream));
+  // K* = cov(space, inputs)  (cross form: Noise contributes zeros, kernels.py:367-371), tt_to_num scrubbed
+  GramArgs a;
+  memset(&a, 0, sizeof a);
+  a.X1 = dXs; a.X2 = ctx->dX; a.n1 = M; a.n2 = N; a.D = D; a.same = 0; a.skip_process_noise = skip_pn;
+  a.theta = w.theta; a.P = P; a.K = Vt; a.ldk = Np; a.strideK = (long long)Mp * Np; a.status = nullptr;
+  if ((rc = g3_gram_launch(ctx, *desc, a, 1))) return rc;
+  // Vt = K* L^-T by blocked forward substitution; all level-3 through the NT GEMM
+  CUtensorMap tmV, tmL, tmD;
+  if ((rc = g3_make_tmap(ctx, &tmV, Vt, Np, Mp, 1, Np, (uint64_t)Mp * Np, G3_BM))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmL, w.A, Np, Np, 1, Np, (uint64_t)Np * Np, G3_BN))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmD, w.Dinv, TS, (uint64_t)T * TS, 1, TS, (uint64_t)T * TS * TS, G3_BN))) return rc;
+  for (int j = 0; j < T; ++j) {
+    if (j > 0) {  // Vt[:, j] -= sum_{k<j} Vt[:, k] L[j][k]^T
+      GemmArgs g = gz();
+      g.D = Vt; g.ldd = Np; g.strideD = 0;
+      g.mode = 0; g.ntx = TM; g.nty = 1;
+      g.d_r0 = 0; g.d_c0 = j * TS;
+      g.a_r0 = 0; g.a_rx = TS; g.ka0 = 0;
+      g.b_r0 = j * TS; g.kb0 = 0;
+      g.kl0 = j * TS;
+      g.alpha = -1.0; g.beta = 1.0;
+      if ((rc = g3_gemm_launch(ctx, tmV, tmL, g, 1))) return rc;
+    }
+    GemmArgs g = gz();  // Vt[:, j] = Vt[:, j] Linv_jj^T
+    g.D = Vt; g.ldd = Np; g.strideD = 0;
+    g.mode = 0; g.ntx = TM; g.nty = 1;
+    g.d_r0 = 0; g.d_c0 = j * TS;
+    g.a_r0 = 0; g.a_rx = TS; g.ka0 = j * TS;
+    g.b_r0 = j * TS; g.kb0 = 0;
+    g.kl0 = TS;
+    g.alpha = 1.0; g.beta = 0.0;
+    if ((rc = g3_gemm_launch(ctx, tmV, tmD, g, 1))) return rc;
+  }
+  // K** diagonal: every leaf is stationary, so diag(cov(space)) is the tree evaluated at d = 0
+  if ((rc = g3_gram_diag_min(ctx, *desc, dXs, M, D, w.theta, P, 1, kss, kss + 1, nullptr, skip_pn))) return rc;
+  // tt_to_cov on prior_kernel_space only for the noisy selector (elliptical.py:70 vs :73)
+  post_kss_shift_kernel<<<1, 32, 0, ctx->stream>>>(kss, ctx->jitter_rel, (flags & G3_POST_NOISE) ? 1 : 0);
+  G3_LAUNCH_CHECK(ctx);
+  post_moments_kernel<<<(M + 7) / 8, 256, 0, ctx->stream>>>(Vt, Np, M, w.u, kss, kss + 2, dmean, dvar);
+  G3_LAUNCH_CHECK(ctx);
+  G3_CUDA(ctx, cudaMemcpyAsync(mean_out, dmean, sizeof(double) * M, cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaMemcpyAsync(var_out, dvar, sizeof(double) * M, cudaMemcpyDeviceToHost, ctx->stream));
+  if (flags & G3_POST_COV) {
+    double* C = (double*)g3_ws(ctx, "post_C", sizeof(double) * (size_t)Mp * Mp);
+    if (!C) return -2;
+    GramArgs c;
+    memset(&c, 0, sizeof c);
+    c.X1 = dXs; c.X2 = dXs; c.n1 = M; c.n2 = M; c.D = D; c.same = 1; c.skip_process_noise = skip_pn;
+    c.theta = w.theta; c.P = P; c.K = C; c.ldk = Mp; c.strideK = (long long)Mp * Mp;
+    c.diag_shift = (flags & G3_POST_NOISE) ? kss + 2 : nullptr;
+    if ((rc = g3_gram_launch(ctx, *desc, c, 1))) return rc;
+    CUtensorMap tmVb;
+    if ((rc = g3_make_tmap(ctx, &tmVb, Vt, Np, Mp, 1, Np, (uint64_t)Mp * Np, G3_BN))) return rc;
+    GemmArgs g = gz();  // C -= Vt Vt^T
+    g.D = C; g.ldd = Mp; g.strideD = 0;
+    g.mode = 0; g.ntx = TM; g.nty = TM;
+    g.a_r0 = 0; g.a_rx = TS; g.b_r0 = 0; g.b_ry = TS;
+    g.kl0 = Np;
+    g.alpha = -1.0; g.beta = 1.0;
+    if ((rc = g3_gemm_launch(ctx, tmV, tmVb, g, 1))) return rc;
+    G3_CUDA(ctx, cudaMemcpy2DAsync(cov_out, sizeof(double) * M, C, sizeof(double) * Mp, sizeof(double) * M, (size_t)M,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---- big single-matrix Cholesky (BASELINE metric 2) -------------------------------------------
+int g3_gram_potrf_device(g3_ctx* ctx, const g3_kernel_desc* desc, const double* theta, double* logdet, int* info,
+                         float* ms_gram, float* ms_potrf) {
+  if (!ctx || !desc || !logdet || !info) return g3_fail_msg(ctx, "g3_gram_potrf_device: bad arguments");
+  if (!ctx->dX) return g3_fail_msg(ctx, "g3_gram_potrf_device: call g3_set_data first");
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int N = ctx->N, Np = g3_pad(N), T = Np / TS, P = desc->n_theta;
+  int rc = g3_check_desc(ctx, *desc, ctx->D);
+  if (rc) return rc;
+  double* A = (double*)g3_ws(ctx, "gp_A", sizeof(double) * (size_t)Np * Np);
+  double* Dinv = (double*)g3_ws(ctx, "gp_Dinv", sizeof(double) * (size_t)T * TS * TS);
+  double* dth = (double*)g3_ws(ctx, "gp_theta", sizeof(double) * (P > 0 ? P : 1));
+  double* sc = (double*)g3_ws(ctx, "big_scalars", sizeof(double) * 8);
+  int* di = (int*)g3_ws(ctx, "big_info", sizeof(int) * 4);
+  if (!A || !Dinv || !dth || !sc || !di) return -2;
+  ctx->gp.valid = 0;
+  if (P > 0) G3_CUDA(ctx, cudaMemcpyAsync(dth, theta, sizeof(double) * P, cudaMemcpyHostToDevice, ctx->stream));
+  G3_CUDA(ctx, cudaMemsetAsync(di, 0, sizeof(int) * 4, ctx->stream));
+  if ((rc = g3_gram_diag_min(ctx, *desc, ctx->dX, N, ctx->D, dth, P, 1, sc, sc + 1, di + 1, 0))) return rc;
+  gp_prep_kernel<<<1, 32, 0, ctx->stream>>>(sc, ctx->jitter_rel, sc + 2, sc + 3, sc + 4, di, di + 1, 1);
+  G3_LAUNCH_CHECK(ctx);
+  cudaEvent_t e0, e1, e2;
+  G3_CUDA(ctx, cudaEventCreate(&e0));
+  G3_CUDA(ctx, cudaEventCreate(&e1));
+  G3_CUDA(ctx, cudaEventCreate(&e2));
+  G3_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+  GramArgs a;
+  memset(&a, 0, sizeof a);
+  a.X1 = ctx->dX; a.X2 = ctx->dX; a.n1 = N; a.n2 = N; a.D = ctx->D;
+  a.same = 1; a.lower_only = 1; a.pad_identity = 1;
+  a.theta = dth; a.P = P; a.diag_shift = sc + 2;
+  a.K = A; a.ldk = Np; a.strideK = (long long)Np * Np; a.status = di + 1;
+  if ((rc = g3_gram_launch(ctx, *desc, a, 1))) return rc;
+  G3_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+  if ((rc = g3_potrf_batched(ctx, A, Np, 1, Dinv, sc + 4, di, nullptr, 0, ctx->potrf_w_big))) return rc;
+  G3_CUDA(ctx, cudaEventRecord(e2, ctx->stream));
+  G3_CUDA(ctx, cudaMemcpyAsync(logdet, sc + 4, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaMemcpyAsync(info, di, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float t;
+  if (ms_gram) { cudaEventElapsedTime(&t, e0, e1); *ms_gram = t; }
+  if (ms_potrf) { cudaEventElapsedTime(&t, e1, e2); *ms_potrf = t; }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  return 0;
+}
+
+}  // extern "C"

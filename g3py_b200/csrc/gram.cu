@@ -1,0 +1,579 @@
+// Gram-matrix construction and its vector-Jacobian product for sm_100a.
+//
+// gram_fwd : Kernel.cov(x1, x2) for B hyper samples (g3py/processes/hypers/kernels.py:106-110,
+//            192-245,360-472; metrics.py:11-13,89-102) fused with tt_to_num / tt_to_cov
+//            (g3py/libs/tensors.py:90-98).  The reference materialises an N1 x N2 x D difference
+//            tensor and one N1 x N2 temporary per tree node; here one CTA stages two 128-row X
+//            tiles in shared memory, evaluates the whole expression tree in registers and writes
+//            the 128x128 output tile with coalesced 16-byte stores.  No pairwise-distance tensor.
+// gram_vjp : dtheta_p = scale * sum_ij W_ij dK_ij/dtheta_p, recomputing the K tile from X instead
+//            of reading dK/dtheta (replaces Theano's reverse mode through Kernel.cov, which needs
+//            several N^2 D passes, tensors.py:11-22).  Per-thread accumulators live in shared
+//            memory; CTA partials are reduced in a fixed order (deterministic).
+#include "g3b_internal.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int TS = G3_TILE;
+constexpr double kInfRepl = 1e10;  // tt_to_num: +-inf -> float32(1e10) == 1e10 exactly
+
+struct TileXY {
+  int x, y;
+};
+__device__ __forceinline__ TileXY decode_tile(int tile, int lower_only, int ntx) {
+  TileXY t;
+  if (!lower_only) {
+    t.x = tile % ntx;
+    t.y = tile / ntx;
+  } else {
+    int x = (int)((sqrt(8.0 * (double)tile + 1.0) - 1.0) * 0.5);
+    while ((long long)x * (x + 1) / 2 > tile) --x;
+    while ((long long)(x + 1) * (x + 2) / 2 <= tile) ++x;
+    t.x = x;
+    t.y = tile - (int)((long long)x * (x + 1) / 2);
+  }
+  return t;
+}
+
+// Stage the two X tiles: x1s[r][d] (row-major), x2s[d][c] (transposed so lanes read consecutive c).
+__device__ __forceinline__ void stage_x(const double* X1, const double* X2, int n1, int n2, int D, int r0, int c0,
+                                        double* x1s, double* x2s) {
+  for (int idx = threadIdx.x; idx < TS * D; idx += blockDim.x) {
+    const int r = idx / D, d = idx - r * D;
+    x1s[idx] = (r0 + r < n1) ? X1[(long long)(r0 + r) * D + d] : 0.0;
+    x2s[d * TS + r] = (c0 + r < n2) ? X2[(long long)(c0 + r) * D + d] : 0.0;
+  }
+}
+
+// value of one leaf for 4 columns at once; same_diag[e] = element lies on the diagonal of cov(x, x)
+__device__ __forceinline__ void leaf_value4(const g3_knode& nd, const double* __restrict__ th,
+                                            const double* __restrict__ x1row, const double* __restrict__ x2s,
+                                            const int* cc, const bool* same_diag, int same, int skip_pn,
+                                            double* out) {
+  const double var = nd.var_idx >= 0 ? th[nd.var_idx] : nd.value;
+  const int nd_ = nd.dim1 - nd.dim0;
+  double d[4] = {0.0, 0.0, 0.0, 0.0};
+  switch (nd.op) {
+    case G3_K_SE:
+    case G3_K_MAT32:
+    case G3_K_MAT52:
+    case G3_K_RQ:
+      for (int k = 0; k < nd_; ++k) {
+        const double r = th[nd.p0_idx + k];
+        const double hr2 = 0.5 * r * r;
+        const double xi = x1row[nd.dim0 + k];
+        const double* x2 = x2s + (nd.dim0 + k) * TS;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double df = xi - x2[cc[e]];
+          d[e] += df * df * hr2;
+        }
+      }
+      break;
+    case G3_K_OU:
+      for (int k = 0; k < nd_; ++k) {
+        const double r = th[nd.p0_idx + k];
+        const double xi = x1row[nd.dim0 + k];
+        const double* x2 = x2s + (nd.dim0 + k) * TS;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) d[e] += fabs(xi - x2[cc[e]]) * r;
+      }
+      break;
+    case G3_K_SIN:
+      for (int k = 0; k < nd_; ++k) {
+        const double fq = th[nd.p1_idx + k];
+        const double r = th[nd.p0_idx + k];
+        const double xi = x1row[nd.dim0 + k];
+        const double* x2 = x2s + (nd.dim0 + k) * TS;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double sn = sinpi((xi - x2[cc[e]]) * fq);
+          d[e] += sn * sn * r;
+        }
+      }
+      break;
+    case G3_K_WN:
+      if (!same)
+        for (int k = 0; k < nd_; ++k) {
+          const double xi = x1row[nd.dim0 + k];
+          const double* x2 = x2s + (nd.dim0 + k) * TS;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) d[e] += (xi - x2[cc[e]] == 0.0) ? 1.0 : 0.0;
+        }
+      break;
+    default:
+      break;
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    double v;
+    switch (nd.op) {
+      case G3_K_SE:
+      case G3_K_OU:
+        v = var * exp(-d[e]);
+        break;
+      case G3_K_MAT32: {
+        const double s = sqrt(3.0 * d[e]);
+        v = var * ((1.0 + s) * exp(-s));
+      } break;
+      case G3_K_MAT52: {
+        const double s = sqrt(5.0 * d[e]);
+        v = var * ((1.0 + s + 5.0 * d[e] / 3.0) * exp(-s));
+      } break;
+      case G3_K_RQ: {
+        const double al = th[nd.p1_idx];
+        v = var * pow(1.0 + d[e] / al, -al);
+      } break;
+      case G3_K_SIN:
+        v = var * exp(2.0 * d[e]);
+        break;
+      case G3_K_NOISE:
+        v = (same_diag[e] && !(skip_pn && (nd.flags & G3_KF_PROCESS_NOISE))) ? var : 0.0;
+        break;
+      case G3_K_WN:
+        v = same ? (same_diag[e] ? var : 0.0) : var * d[e];
+        break;
+      default:
+        v = 0.0;
+    }
+    out[e] = v;
+  }
+}
+
+__device__ __forceinline__ double scrub(double v, int& flag) {
+  if (isnan(v)) { flag = 1; return 0.0; }
+  if (isinf(v)) { flag = 1; return kInfRepl; }
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+gram_fwd_kernel(const __grid_constant__ g3_kernel_desc desc, const GramArgs a, int ntx) {
+  extern __shared__ double sm[];
+  double* x1s = sm;                     // [128][D]
+  double* x2s = sm + TS * a.D;          // [D][128]
+  double* th = x2s + TS * a.D;          // [P]
+  const int b = a.bmap ? a.bmap[blockIdx.y] : (int)blockIdx.y;
+  const TileXY t = decode_tile(blockIdx.x, a.lower_only, ntx);
+  const int r0 = t.x * TS, c0 = t.y * TS;
+  stage_x(a.X1, a.X2, a.n1, a.n2, a.D, r0, c0, x1s, x2s);
+  for (int p = threadIdx.x; p < a.P; p += blockDim.x) th[p] = a.theta[(long long)b * a.P + p];
+  __syncthreads();
+
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int cc[4] = {2 * tx, 2 * tx + 1, 64 + 2 * tx, 64 + 2 * tx + 1};
+  const double shift = (a.diag_shift && a.same) ? a.diag_shift[b] : 0.0;
+  double* Kb = a.K + (long long)b * a.strideK;
+  int flag = 0;
+  for (int q = 0; q < 16; ++q) {
+    const int rl = ty + 8 * q;
+    const int gi = r0 + rl;
+    bool sd[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sd[e] = a.same && (gi == c0 + cc[e]);
+    // shift-register evaluation stack (depth 6) for 4 columns
+    double s0[4], s1[4], s2[4], s3[4], s4[4], s5[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s0[e] = s1[e] = s2[e] = s3[e] = s4[e] = s5[e] = 0.0;
+    for (int n = 0; n < desc.n_nodes; ++n) {
+      const g3_knode& nd = desc.nodes[n];
+      if (nd.op < G3_K_SUM) {
+        double v[4];
+        leaf_value4(nd, th, x1s + rl * a.D, x2s, cc, sd, a.same, a.skip_process_noise, v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { s5[e] = s4[e]; s4[e] = s3[e]; s3[e] = s2[e]; s2[e] = s1[e]; s1[e] = s0[e]; s0[e] = v[e]; }
+      } else if (nd.op == G3_K_SUM || nd.op == G3_K_PROD) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          s0[e] = nd.op == G3_K_SUM ? s1[e] + s0[e] : s1[e] * s0[e];
+          s1[e] = s2[e]; s2[e] = s3[e]; s3[e] = s4[e]; s4[e] = s5[e];
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s0[e] = nd.op == G3_K_SCALE ? nd.value * s0[e] : nd.value + s0[e];
+      }
+    }
+    double v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int gj = c0 + cc[e];
+      double val = scrub(s0[e], flag);
+      if (sd[e]) val += shift;
+      if (gi >= a.n1 || gj >= a.n2) val = (a.pad_identity && gi == gj) ? 1.0 : 0.0;
+      v[e] = val;
+    }
+    double* rowp = Kb + (long long)gi * a.ldk + c0;
+    *reinterpret_cast<double2*>(rowp + cc[0]) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(rowp + cc[2]) = make_double2(v[2], v[3]);
+  }
+  if (a.status && flag) atomicOr(a.status + b, G3_ST_NONFINITE_INPUT);
+}
+
+// min and mean of diag(cov(X, X)) per theta (after tt_to_num scrubbing).  grid (B), 256 threads.
+__global__ void __launch_bounds__(256)
+gram_diag_kernel(const __grid_constant__ g3_kernel_desc desc, const double* __restrict__ X, int n, int D,
+                 const double* __restrict__ theta, int P, double* __restrict__ dmin, double* __restrict__ dmean,
+                 int* __restrict__ status, int skip_pn) {
+  __shared__ double th[G3_MAX_THETA];
+  __shared__ double rmin[8], rsum[8];
+  const int b = blockIdx.x;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) th[p] = theta[(long long)b * P + p];
+  __syncthreads();
+  // diagonal element: all differences are zero -> every stationary leaf evaluates at d = 0
+  double vmin = INFINITY, vsum = 0.0;
+  int flag = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double st[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < desc.n_nodes; ++k) {
+      const g3_knode& nd = desc.nodes[k];
+      if (nd.op < G3_K_SUM) {
+        const double var = nd.var_idx >= 0 ? th[nd.var_idx] : nd.value;
+        double v = var;  // k(0) = 1 for SE/OU/MAT/RQ/SIN; Noise/WN: var on the diagonal
+        if (nd.op == G3_K_NOISE && skip_pn && (nd.flags & G3_KF_PROCESS_NOISE)) v = 0.0;
+        if (nd.op == G3_K_RQ) v = var * pow(1.0, -th[nd.p1_idx]);
+        st[5] = st[4]; st[4] = st[3]; st[3] = st[2]; st[2] = st[1]; st[1] = st[0]; st[0] = v;
+      } else if (nd.op == G3_K_SUM || nd.op == G3_K_PROD) {
+        st[0] = nd.op == G3_K_SUM ? st[1] + st[0] : st[1] * st[0];
+        st[1] = st[2]; st[2] = st[3]; st[3] = st[4]; st[4] = st[5];
+      } else {
+        st[0] = nd.op == G3_K_SCALE ? nd.value * st[0] : nd.value + st[0];
+      }
+    }
+    const double v = scrub(st[0], flag);
+    vmin = fmin(vmin, v);
+    vsum += v;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { rmin[warp] = vmin; rsum[warp] = vsum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = rmin[0], s = rsum[0];
+    for (int w = 1; w < 8; ++w) { m = fmin(m, rmin[w]); s += rsum[w]; }
+    dmin[b] = m;
+    dmean[b] = s / (double)n;
+  }
+  if (status && flag) atomicOr(status + b, G3_ST_NONFINITE_INPUT);
+}
+
+// ---- VJP -------------------------------------------------------------------------------
+// One CTA per 128x128 tile; thread mapping as in gram_fwd.  acc[p][tid] in shared memory.
+__global__ void __launch_bounds__(256)
+gram_vjp_kernel(const __grid_constant__ g3_kernel_desc desc, const VjpArgs a, int ntx, double* __restrict__ partials,
+                int ntiles) {
+  extern __shared__ double sm[];
+  double* x1s = sm;
+  double* x2s = sm + TS * a.D;
+  double* th = x2s + TS * a.D;
+  double* al_r = th + G3_MAX_THETA;      // alpha rows [128]
+  double* al_c = al_r + TS;              // alpha cols [128]
+  double* acc = al_c + TS;               // [P][256]
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const TileXY t = decode_tile(blockIdx.x, a.lower_only, ntx);
+  const int r0 = t.x * TS, c0 = t.y * TS;
+  stage_x(a.X1, a.X2, a.n1, a.n2, a.D, r0, c0, x1s, x2s);
+  for (int p = tid; p < a.P; p += blockDim.x) th[p] = a.theta[(long long)b * a.P + p];
+  if (a.alpha && tid < TS) {
+    al_r[tid] = (r0 + tid < a.n1) ? a.alpha[(long long)b * a.strideAlpha + r0 + tid] : 0.0;
+    al_c[tid] = (c0 + tid < a.n2) ? a.alpha[(long long)b * a.strideAlpha + c0 + tid] : 0.0;
+  }
+  for (int p = 0; p < a.P; ++p) acc[p * 256 + tid] = 0.0;
+  __syncthreads();
+  const double cf = (a.alpha && a.cfac) ? a.cfac[b] : 1.0;
+
+  const int tx = tid & 31, ty = tid >> 5;
+  const int cc[4] = {2 * tx, 2 * tx + 1, 64 + 2 * tx, 64 + 2 * tx + 1};
+  const double* Wb = a.W + (long long)b * a.strideW;
+  for (int q = 0; q < 16; ++q) {
+    const int rl = ty + 8 * q;
+    const int gi = r0 + rl;
+    const double* x1row = x1s + rl * a.D;
+    bool sd[4];
+    double w[4];
+    {
+      const double* wrow = Wb + (long long)gi * a.ldw + c0;
+      const bool row_ok = gi < a.n1;
+      double2 w01 = make_double2(0.0, 0.0), w23 = make_double2(0.0, 0.0);
+      if (row_ok) {
+        w01 = *reinterpret_cast<const double2*>(wrow + cc[0]);
+        w23 = *reinterpret_cast<const double2*>(wrow + cc[2]);
+      }
+      w[0] = w01.x; w[1] = w01.y; w[2] = w23.x; w[3] = w23.y;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int gj = c0 + cc[e];
+        sd[e] = a.same && (gi == gj);
+        if (a.alpha) w[e] = cf * al_r[rl] * al_c[cc[e]] - w[e];
+        double f = 1.0;
+        if (a.lower_only) f = (gi > gj) ? 2.0 : (gi == gj ? 1.0 : 0.0);
+        if (!row_ok || gj >= a.n2) f = 0.0;
+        w[e] = f == 0.0 ? 0.0 : w[e] * f;   // also kills NaN garbage in masked positions
+      }
+    }
+    // forward: node values, leaf auxiliaries
+    double val[G3_MAX_NODES][4], aux[G3_MAX_NODES][4], dd[G3_MAX_NODES][4], adj[G3_MAX_NODES][4];
+    for (int n = 0; n < desc.n_nodes; ++n) {
+      const g3_knode& nd = desc.nodes[n];
+      if (nd.op < G3_K_SUM) {
+        const double var = nd.var_idx >= 0 ? th[nd.var_idx] : nd.value;
+        const int nd_ = nd.dim1 - nd.dim0;
+        double d[4] = {0.0, 0.0, 0.0, 0.0};
+        if (nd.op == G3_K_SE || nd.op == G3_K_MAT32 || nd.op == G3_K_MAT52 || nd.op == G3_K_RQ) {
+          for (int k = 0; k < nd_; ++k) {
+            const double r = th[nd.p0_idx + k];
+            const double hr2 = 0.5 * r * r, xi = x1row[nd.dim0 + k];
+            const double* x2 = x2s + (nd.dim0 + k) * TS;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const double df = xi - x2[cc[e]]; d[e] += df * df * hr2; }
+          }
+        } else if (nd.op == G3_K_OU) {
+          for (int k = 0; k < nd_; ++k) {
+            const double r = th[nd.p0_idx + k], xi = x1row[nd.dim0 + k];
+            const double* x2 = x2s + (nd.dim0 + k) * TS;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) d[e] += fabs(xi - x2[cc[e]]) * r;
+          }
+        } else if (nd.op == G3_K_SIN) {
+          for (int k = 0; k < nd_; ++k) {
+            const double fq = th[nd.p1_idx + k], r = th[nd.p0_idx + k], xi = x1row[nd.dim0 + k];
+            const double* x2 = x2s + (nd.dim0 + k) * TS;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const double sn = sinpi((xi - x2[cc[e]]) * fq); d[e] += sn * sn * r; }
+          }
+        } else if (nd.op == G3_K_WN && !a.same) {
+          for (int k = 0; k < nd_; ++k) {
+            const double xi = x1row[nd.dim0 + k];
+            const double* x2 = x2s + (nd.dim0 + k) * TS;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) d[e] += (xi - x2[cc[e]] == 0.0) ? 1.0 : 0.0;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          double kk, dk = 0.0;  // kk = k(d) (unit variance), dk = d k / d d
+          switch (nd.op) {
+            case G3_K_SE: kk = exp(-d[e]); dk = -kk; break;
+            case G3_K_OU: kk = exp(-d[e]); dk = -kk; break;
+            case G3_K_MAT32: { const double s = sqrt(3.0 * d[e]); const double ex = exp(-s); kk = (1.0 + s) * ex; dk = -1.5 * ex; } break;
+            case G3_K_MAT52: { const double s = sqrt(5.0 * d[e]); const double ex = exp(-s);
+                               kk = (1.0 + s + 5.0 * d[e] / 3.0) * ex; dk = -(5.0 / 6.0) * (1.0 + s) * ex; } break;
+            case G3_K_RQ: { const double al = th[nd.p1_idx]; const double base = 1.0 + d[e] / al;
+                            kk = pow(base, -al); dk = -kk / base; } break;
+            case G3_K_SIN: kk = exp(2.0 * d[e]); dk = 0.0; break;
+            case G3_K_NOISE: kk = sd[e] ? 1.0 : 0.0; break;
+            case G3_K_WN: kk = a.same ? (sd[e] ? 1.0 : 0.0) : d[e]; break;
+            default: kk = 0.0;
+          }
+          val[n][e] = var * kk;
+          aux[n][e] = kk;
+          dd[n][e] = (nd.op == G3_K_RQ) ? d[e] : var * dk;
+        }
+      } else if (nd.op == G3_K_SUM || nd.op == G3_K_PROD) {
+        const int l = nd.dim0, r = nd.dim1;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) val[n][e] = nd.op == G3_K_SUM ? val[l][e] + val[r][e] : val[l][e] * val[r][e];
+      } else {
+        const int c = nd.dim0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) val[n][e] = nd.op == G3_K_SCALE ? nd.value * val[c][e] : nd.value + val[c][e];
+      }
+    }
+    // backward
+    for (int n = 0; n < desc.n_nodes; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) adj[n][e] = 0.0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) adj[desc.n_nodes - 1][e] = w[e];
+    for (int n = desc.n_nodes - 1; n >= 0; --n) {
+      const g3_knode& nd = desc.nodes[n];
+      if (nd.op == G3_K_SUM) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { adj[nd.dim0][e] += adj[n][e]; adj[nd.dim1][e] += adj[n][e]; }
+      } else if (nd.op == G3_K_PROD) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          adj[nd.dim0][e] += adj[n][e] * val[nd.dim1][e];
+          adj[nd.dim1][e] += adj[n][e] * val[nd.dim0][e];
+        }
+      } else if (nd.op == G3_K_SCALE) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) adj[nd.dim0][e] += adj[n][e] * nd.value;
+      } else if (nd.op == G3_K_SHIFT) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) adj[nd.dim0][e] += adj[n][e];
+      } else {
+        // leaf: scatter into the per-thread accumulators
+        const int nd_ = nd.dim1 - nd.dim0;
+        if (nd.var_idx >= 0) {
+          double s = 0.0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) s += adj[n][e] * aux[n][e];
+          acc[nd.var_idx * 256 + tid] += s;
+        }
+        if (nd.op == G3_K_SE || nd.op == G3_K_MAT32 || nd.op == G3_K_MAT52 || nd.op == G3_K_RQ) {
+          const bool rq = nd.op == G3_K_RQ;
+          double gk[4];  // adj * var * dk/dd
+          if (rq) {
+            const double al = th[nd.p1_idx];
+            double s = 0.0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const double base = 1.0 + dd[n][e] / al;
+              gk[e] = -adj[n][e] * val[n][e] / base;
+              s += adj[n][e] * val[n][e] * (-log1p(dd[n][e] / al) + dd[n][e] / (al + dd[n][e]));
+            }
+            acc[nd.p1_idx * 256 + tid] += s;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) gk[e] = adj[n][e] * dd[n][e];
+          }
+          for (int k = 0; k < nd_; ++k) {
+            const double r = th[nd.p0_idx + k], xi = x1row[nd.dim0 + k];
+            const double* x2 = x2s + (nd.dim0 + k) * TS;
+            double s = 0.0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const double df = xi - x2[cc[e]]; s += gk[e] * df * df; }
+            acc[(nd.p0_idx + k) * 256 + tid] += s * r;
+          }
+        } else if (nd.op == G3_K_OU) {
+          for (int k = 0; k < nd_; ++k) {
+            const double xi = x1row[nd.dim0 + k];
+            const double* x2 = x2s + (nd.dim0 + k) * TS;
+            double s = 0.0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s -= adj[n][e] * val[n][e] * fabs(xi - x2[cc[e]]);
+            acc[(nd.p0_idx + k) * 256 + tid] += s;
+          }
+        } else if (nd.op == G3_K_SIN) {
+          for (int k = 0; k < nd_; ++k) {
+            const double fq = th[nd.p1_idx + k], r = th[nd.p0_idx + k], xi = x1row[nd.dim0 + k];
+            const double* x2 = x2s + (nd.dim0 + k) * TS;
+            double sf = 0.0, sr = 0.0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const double df = xi - x2[cc[e]];
+              const double sn = sinpi(df * fq);
+              const double gK = adj[n][e] * val[n][e];
+              sr += gK * 2.0 * sn * sn;
+              sf += gK * 2.0 * r * sinpi(2.0 * df * fq) * (M_PI * df);
+            }
+            acc[(nd.p1_idx + k) * 256 + tid] += sf;
+            acc[(nd.p0_idx + k) * 256 + tid] += sr;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // block reduction per parameter, fixed order
+  const int warp = tid >> 5, lane = tid & 31;
+  __shared__ double red[8];
+  for (int p = 0; p < a.P; ++p) {
+    double v = acc[p * 256 + tid];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += red[w];
+      partials[((long long)b * ntiles + blockIdx.x) * a.P + p] = s;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+vjp_reduce_kernel(const double* __restrict__ partials, int ntiles, int P, double scale, double* __restrict__ dtheta) {
+  __shared__ double red[8];
+  const int b = blockIdx.y, p = blockIdx.x;
+  double v = 0.0;
+  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) v += partials[((long long)b * ntiles + t) * P + p];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    dtheta[(long long)b * P + p] = s * scale;
+  }
+}
+
+}  // namespace
+
+int g3_check_desc(g3_ctx* ctx, const g3_kernel_desc& d, int D) {
+  if (d.n_nodes < 1 || d.n_nodes > G3_MAX_NODES) return g3_fail_msg(ctx, "kernel desc: 1 <= n_nodes <= 16");
+  if (d.n_theta < 0 || d.n_theta > G3_MAX_THETA) return g3_fail_msg(ctx, "kernel desc: n_theta <= 32");
+  int depth = 0;
+  for (int n = 0; n < d.n_nodes; ++n) {
+    const g3_knode& nd = d.nodes[n];
+    if (nd.op < G3_K_SUM) {
+      if (nd.op < G3_K_SE || nd.op > G3_K_WN) return g3_fail_msg(ctx, "kernel desc: unknown leaf op");
+      if (nd.op != G3_K_NOISE && (nd.dim0 < 0 || nd.dim1 > D || nd.dim1 <= nd.dim0))
+        return g3_fail_msg(ctx, "kernel desc: leaf dims outside [0, D)");
+      const int w = nd.dim1 - nd.dim0;
+      if (nd.var_idx >= d.n_theta) return g3_fail_msg(ctx, "kernel desc: var_idx outside theta");
+      const bool has_rate = nd.op != G3_K_NOISE && nd.op != G3_K_WN;
+      if (has_rate && (nd.p0_idx < 0 || nd.p0_idx + w > d.n_theta)) return g3_fail_msg(ctx, "kernel desc: rate index outside theta");
+      if (nd.op == G3_K_RQ && (nd.p1_idx < 0 || nd.p1_idx >= d.n_theta)) return g3_fail_msg(ctx, "kernel desc: alpha index outside theta");
+      if (nd.op == G3_K_SIN && (nd.p1_idx < 0 || nd.p1_idx + w > d.n_theta)) return g3_fail_msg(ctx, "kernel desc: freq index outside theta");
+      ++depth;
+    } else if (nd.op == G3_K_SUM || nd.op == G3_K_PROD) {
+      if (depth < 2) return g3_fail_msg(ctx, "kernel desc: malformed post-order tree");
+      if (nd.dim0 < 0 || nd.dim0 >= n || nd.dim1 < 0 || nd.dim1 >= n) return g3_fail_msg(ctx, "kernel desc: bad child index");
+      --depth;
+    } else if (nd.op == G3_K_SCALE || nd.op == G3_K_SHIFT) {
+      if (depth < 1 || nd.dim0 < 0 || nd.dim0 >= n) return g3_fail_msg(ctx, "kernel desc: malformed unary node");
+    } else {
+      return g3_fail_msg(ctx, "kernel desc: unknown op");
+    }
+    if (depth > 6) return g3_fail_msg(ctx, "kernel desc: expression stack deeper than 6");
+  }
+  if (depth != 1) return g3_fail_msg(ctx, "kernel desc: tree does not reduce to one value");
+  return 0;
+}
+
+int g3_gram_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const GramArgs& a, int B) {
+  int rc = g3_check_desc(ctx, desc, a.D);
+  if (rc) return rc;
+  const int tr = (a.n1 + TS - 1) / TS, tc = (a.n2 + TS - 1) / TS;
+  const long long ntiles = a.lower_only ? (long long)tr * (tr + 1) / 2 : (long long)tr * tc;
+  const size_t smem = sizeof(double) * (2 * TS * a.D + G3_MAX_THETA);
+  gram_fwd_kernel<<<dim3((unsigned)ntiles, B), 256, smem, ctx->stream>>>(desc, a, tr);
+  G3_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int g3_gram_diag_min(g3_ctx* ctx, const g3_kernel_desc& desc, const double* X, int n, int D, const double* theta,
+                     int P, int B, double* diag_min, double* diag_mean, int* status, int skip_process_noise) {
+  int rc = g3_check_desc(ctx, desc, D);
+  if (rc) return rc;
+  gram_diag_kernel<<<B, 256, 0, ctx->stream>>>(desc, X, n, D, theta, P, diag_min, diag_mean, status,
+                                               skip_process_noise);
+  G3_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int g3_gram_vjp_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const VjpArgs& a, int B) {
+  int rc = g3_check_desc(ctx, desc, a.D);
+  if (rc) return rc;
+  const int tr = (a.n1 + TS - 1) / TS, tc = (a.n2 + TS - 1) / TS;
+  const long long ntiles = a.lower_only ? (long long)tr * (tr + 1) / 2 : (long long)tr * tc;
+  double* partials = (double*)g3_ws(ctx, "vjp_partials", sizeof(double) * (size_t)B * ntiles * (a.P > 0 ? a.P : 1));
+  if (!partials) return -2;
+  const size_t smem = sizeof(double) * (2 * TS * a.D + G3_MAX_THETA + 2 * TS + (size_t)a.P * 256);
+  static bool attr = false;
+  if (!attr) {
+    G3_CUDA(ctx, cudaFuncSetAttribute(gram_vjp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr = true;
+  }
+  if (a.P == 0) return 0;
+  gram_vjp_kernel<<<dim3((unsigned)ntiles, B), 256, smem, ctx->stream>>>(desc, a, tr, partials, (int)ntiles);
+  G3_LAUNCH_CHECK(ctx);
+  vjp_reduce_kernel<<<dim3(a.P, B), 256, 0, ctx->stream>>>(partials, (int)ntiles, a.P, a.scale, a.dtheta);
+  G3_LAUNCH_CHECK(ctx);
+  return 0;
+}

@@ -1,0 +1,336 @@
+// Blocked, batched fp64 Cholesky / triangular inverse / K^-1 and triangular solves for sm_100a.
+//
+// Replaces CholeskyRobust.perform -> scipy dpotrf (g3py/libs/tensors.py:198) and, for the
+// gradient, CholeskyRobust.grad (Murray reverse mode, tensors.py:224-260) by the analytic route
+// K^-1 = U U^T with U = L^-T.
+//
+// Layout: every matrix is Np x Np row-major (Np multiple of 128, identity on the padding),
+// batch stride Np*Np.  Only the lower triangle of K / L is ever read.  U = L^-T is stored
+// row-major upper, so that every level-3 step is the same "NT" GEMM (gemm.cu):
+//   potrf :  A[i][j] -= sum_k L[i][k] L[j][k]^T            (left-looking inside an outer block of
+//            L[i][j]  = A[i][j] Linv_jj^T                   `w` tile columns, right-looking between)
+//   trtri :  U[j][i]  = -(sum_{k=j}^{i-1} U[j][k] L[i][k]^T) Linv_ii^T
+//   lauum :  Kinv[i][j] = sum_{k>=i} U[i][k] U[j][k]^T      (i >= j)
+// The 128x128 diagonal blocks are factored AND inverted by one CTA in shared memory
+// (potrf_diag_kernel); their inverses (Dinv) turn every triangular solve into a GEMM/GEMV.
+#include "g3b_internal.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int TS = G3_TILE;       // 128
+constexpr int LDS_ = TS + 1;      // padded row stride of the shared tile
+
+// One CTA per matrix: factor the diagonal tile j in place, build Linv (-> Dinv) and Linv^T (-> U).
+// Shared tile S[128][129]: L (and the not yet eliminated part of A) lives at S[i][c], c <= i;
+// row i of R/X = Linv lives transposed in the strictly-upper part, X[i][c] = S[c][i+1], c <= i.
+__global__ void __launch_bounds__(256)
+potrf_diag_kernel(double* __restrict__ A, int Np, long long strideA, int j, double* __restrict__ Dinv, int T,
+                  double* __restrict__ U, double* __restrict__ logdet, int* __restrict__ info,
+                  const int* __restrict__ bmap) {
+  extern __shared__ double S[];
+  __shared__ int first_bad;
+  const int tid = threadIdx.x;
+  const int b = bmap ? bmap[blockIdx.x] : (int)blockIdx.x;
+  double* At = A + (long long)b * strideA + (long long)j * TS * Np + (long long)j * TS;
+  if (tid == 0) first_bad = -1;
+  // load lower triangle; initialise R = I in the transposed upper storage
+  for (int idx = tid; idx < TS * TS; idx += 256) {
+    const int r = idx >> 7, c = idx & 127;
+    if (c <= r) S[r * LDS_ + c] = At[(long long)r * Np + c];
+  }
+  for (int idx = tid; idx < TS * TS; idx += 256) {
+    const int r = idx >> 7, q = (idx & 127) + 1;  // q in 1..128
+    if (q > r) S[r * LDS_ + q] = (q == r + 1) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+
+  const int tx = tid & 15, ty = tid >> 4;
+  for (int k = 0; k < TS; ++k) {
+    const double d = S[k * LDS_ + k];
+    const bool ok = d > 0.0;  // false for NaN too
+    const double s = sqrt(d);
+    const double inv = 1.0 / s;
+    __syncthreads();  // everyone has read S[k][k]
+    if (tid == 0 && !ok && first_bad < 0) first_bad = k;
+    if (tid < TS) {
+      const int q = tid;
+      if (q > k) {
+        S[q * LDS_ + k] *= inv;        // column k of L
+      } else {
+        S[q * LDS_ + k + 1] *= inv;    // row k of X: X[k][q] = R[k][q] / L[k][k]
+        if (q == k) S[k * LDS_ + k] = s;
+      }
+    }
+    __syncthreads();
+    for (int i = k + 1 + ty; i < TS; i += 16) {
+      const double lik = S[i * LDS_ + k];
+      for (int e = tx; e <= i; e += 16) {
+        if (e <= k)
+          S[e * LDS_ + i + 1] -= lik * S[e * LDS_ + k + 1];   // R[i][e] -= L[i][k] X[k][e]
+        else
+          S[i * LDS_ + e] -= lik * S[e * LDS_ + k];           // A[i][e] -= L[i][k] L[e][k]
+      }
+    }
+    // next iteration's first __syncthreads orders these writes before the column scale
+    __syncthreads();
+  }
+
+  // write back: L tile (upper zeroed), Dinv (lower, zeros above), U diagonal tile (upper)
+  double* Dj = Dinv + ((long long)b * T + j) * TS * TS;
+  double* Ut = U ? U + (long long)b * strideA + (long long)j * TS * Np + (long long)j * TS : nullptr;
+  for (int idx = tid; idx < TS * TS; idx += 256) {
+    const int r = idx >> 7, c = idx & 127;
+    At[(long long)r * Np + c] = (c <= r) ? S[r * LDS_ + c] : 0.0;
+    Dj[idx] = (c <= r) ? S[c * LDS_ + r + 1] : 0.0;             // Linv[r][c] = X[r][c]
+    if (Ut) Ut[(long long)r * Np + c] = (c >= r) ? S[r * LDS_ + c + 1] : 0.0;  // U[r][c] = X[c][r]
+  }
+  // log-determinant contribution and failure index (deterministic: one thread, sequential steps)
+  if (tid < 32) {
+    double acc = 0.0;
+    for (int k = tid; k < TS; k += 32) acc += log(S[k * LDS_ + k]);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (tid == 0) {
+      if (logdet) logdet[b] += acc;
+      if (info && first_bad >= 0 && info[b] == 0) info[b] = j * TS + first_bad + 1;
+    }
+  }
+}
+
+// Forward substitution step j of u = L^-1 r (right-looking).  grid (T-j, B).
+// CTA x=0 finalises u_j = Linv_jj r_j and accumulates beta += |u_j|^2;
+// CTA x>0 recomputes u_j and updates r_{j+x} -= L[j+x][j] u_j.
+__global__ void __launch_bounds__(256)
+trsv_fwd_step_kernel(const double* __restrict__ L, const double* __restrict__ Dinv, double* __restrict__ r,
+                     double* __restrict__ u, double* __restrict__ beta, int j, int Np, int T) {
+  __shared__ double rj[TS], uj[TS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, x = blockIdx.x;
+  const double* Dj = Dinv + ((long long)b * T + j) * TS * TS;
+  double* rb = r + (long long)b * Np;
+  if (tid < TS) rj[tid] = rb[j * TS + tid];
+  __syncthreads();
+  for (int a = warp; a < TS; a += 8) {           // warp per row, coalesced 1 KiB rows
+    const double4 v = *reinterpret_cast<const double4*>(Dj + a * TS + lane * 4);
+    double acc = v.x * rj[lane * 4] + v.y * rj[lane * 4 + 1] + v.z * rj[lane * 4 + 2] + v.w * rj[lane * 4 + 3];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) uj[a] = acc;
+  }
+  __syncthreads();
+  if (x == 0) {
+    if (tid < TS) u[(long long)b * Np + j * TS + tid] = uj[tid];
+    if (warp == 0 && beta) {
+      double acc = 0.0;
+      for (int k = lane; k < TS; k += 32) acc += uj[k] * uj[k];
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+      if (lane == 0) beta[b] += acc;
+    }
+    return;
+  }
+  const int i = j + x;
+  const double* Lt = L + (long long)b * Np * Np + (long long)i * TS * Np + (long long)j * TS;
+  for (int a = warp; a < TS; a += 8) {
+    const double4 v = *reinterpret_cast<const double4*>(Lt + (long long)a * Np + lane * 4);
+    double acc = v.x * uj[lane * 4] + v.y * uj[lane * 4 + 1] + v.z * uj[lane * 4 + 2] + v.w * uj[lane * 4 + 3];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) rb[i * TS + a] -= acc;
+  }
+}
+
+// Backward substitution step j (j = T-1 .. 0) of alpha = L^-T s.  grid (j+1, B).
+// CTA x=0 finalises alpha_j = Linv_jj^T s_j; CTA x>0 updates s_{i} -= L[j][i]^T alpha_j, i = x-1.
+__global__ void __launch_bounds__(256)
+trsv_bwd_step_kernel(const double* __restrict__ L, const double* __restrict__ Dinv, double* __restrict__ s,
+                     double* __restrict__ alpha, int j, int Np, int T) {
+  __shared__ double sj[TS], aj[TS], part[2][TS];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y, x = blockIdx.x;
+  const double* Dj = Dinv + ((long long)b * T + j) * TS * TS;
+  double* sb = s + (long long)b * Np;
+  if (tid < TS) sj[tid] = sb[j * TS + tid];
+  __syncthreads();
+  const int c = tid & 127, half = tid >> 7;       // thread per column, two row halves
+  {
+    double acc = 0.0;
+    for (int a = half * 64; a < half * 64 + 64; ++a) acc += Dj[a * TS + c] * sj[a];
+    part[half][c] = acc;
+  }
+  __syncthreads();
+  if (tid < TS) aj[tid] = part[0][tid] + part[1][tid];
+  __syncthreads();
+  if (x == 0) {
+    if (tid < TS) alpha[(long long)b * Np + j * TS + tid] = aj[tid];
+    return;
+  }
+  const int i = x - 1;
+  const double* Lt = L + (long long)b * Np * Np + (long long)j * TS * Np + (long long)i * TS;
+  {
+    double acc = 0.0;
+    for (int a = half * 64; a < half * 64 + 64; ++a) acc += Lt[(long long)a * Np + c] * aj[a];
+    part[half][c] = acc;
+  }
+  __syncthreads();
+  if (tid < TS) sb[i * TS + tid] -= part[0][tid] + part[1][tid];
+}
+
+}  // namespace
+
+static constexpr int kDiagSmem = TS * LDS_ * (int)sizeof(double);
+
+static GemmArgs gemm_zero() {
+  GemmArgs g;
+  memset(&g, 0, sizeof g);
+  return g;
+}
+
+int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, double* logdet, int* info,
+                     const int* bmap, int nb, int w_outer) {
+  const int T = Np / TS;
+  if (!ctx->diag_ready) {
+    G3_CUDA(ctx, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem));
+    ctx->diag_ready = true;
+  }
+  if (w_outer < 1) w_outer = 1;
+  // The tensor maps span the whole allocation (Btotal matrices); bmap (nb entries) picks the batch
+  // coordinate of each launched CTA column, so the jitter ladder can refactor a subset in place.
+  const int B = bmap ? nb : Btotal;
+  CUtensorMap tmA, tmB, tmD;
+  const uint64_t batch_extent = (uint64_t)Btotal;
+  int rc;
+  if ((rc = g3_make_tmap(ctx, &tmA, A, Np, Np, batch_extent, Np, (uint64_t)Np * Np, G3_BM))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmB, A, Np, Np, batch_extent, Np, (uint64_t)Np * Np, G3_BN))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmD, Dinv, TS, (uint64_t)T * TS, batch_extent, TS, (uint64_t)T * TS * TS, G3_BN))) return rc;
+  const long long strideA = (long long)Np * Np;
+
+  for (int jo = 0; jo < T; jo += w_outer) {
+    const int je = jo + w_outer < T ? jo + w_outer : T;
+    for (int j = jo; j < je; ++j) {
+      if (j > jo) {  // left-looking update of tile column j with the columns of this outer block
+        GemmArgs g = gemm_zero();
+        g.D = A; g.ldd = Np; g.strideD = strideA;
+        g.mode = 0; g.ntx = T - j; g.nty = 1;
+        g.d_r0 = j * TS; g.d_c0 = j * TS;
+        g.a_r0 = j * TS; g.a_rx = TS;
+        g.b_r0 = j * TS;
+        g.ka0 = jo * TS; g.kb0 = jo * TS; g.kl0 = (j - jo) * TS;
+        g.alpha = -1.0; g.beta = 1.0; g.bmap = bmap;
+        if ((rc = g3_gemm_launch(ctx, tmA, tmB, g, B))) return rc;
+      }
+      potrf_diag_kernel<<<B, 256, kDiagSmem, ctx->stream>>>(A, Np, strideA, j, Dinv, T, nullptr, logdet, info, bmap);
+      G3_LAUNCH_CHECK(ctx);
+      if (j < T - 1) {  // L[i][j] = A[i][j] Linv_jj^T for the tiles below the diagonal
+        GemmArgs g = gemm_zero();
+        g.D = A; g.ldd = Np; g.strideD = strideA;
+        g.mode = 0; g.ntx = T - j - 1; g.nty = 1;
+        g.d_r0 = (j + 1) * TS; g.d_c0 = j * TS;
+        g.a_r0 = (j + 1) * TS; g.a_rx = TS; g.ka0 = j * TS;
+        g.b_r0 = j * TS; g.kb0 = 0;
+        g.kl0 = TS;
+        g.alpha = 1.0; g.beta = 0.0; g.bmap = bmap;
+        if ((rc = g3_gemm_launch(ctx, tmA, tmD, g, B))) return rc;
+      }
+    }
+    if (je < T) {  // right-looking update of the trailing matrix with the finished outer block
+      GemmArgs g = gemm_zero();
+      g.D = A; g.ldd = Np; g.strideD = strideA;
+      g.mode = 1; g.ntx = T - je;
+      g.d_r0 = je * TS; g.d_c0 = je * TS;
+      g.a_r0 = je * TS; g.a_rx = TS;
+      g.b_r0 = je * TS; g.b_ry = TS;
+      g.ka0 = jo * TS; g.kb0 = jo * TS; g.kl0 = (je - jo) * TS;
+      g.alpha = -1.0; g.beta = 1.0; g.bmap = bmap;
+      if ((rc = g3_gemm_launch(ctx, tmA, tmB, g, B))) return rc;
+    }
+  }
+  return 0;
+}
+
+// U = L^-T (row-major upper).  Diagonal tiles of U are Linv_jj^T, rebuilt here from Dinv.
+namespace {
+__global__ void __launch_bounds__(256)
+u_diag_from_dinv_kernel(const double* __restrict__ Dinv, double* __restrict__ U, int Np, int T) {
+  __shared__ double tile[32][33];
+  const int b = blockIdx.z, j = blockIdx.y;
+  const int bx = blockIdx.x & 3, by = blockIdx.x >> 2;  // 4x4 sub-tiles of 32x32
+  const double* Dj = Dinv + ((long long)b * T + j) * TS * TS;
+  double* Ut = U + (long long)b * Np * Np + (long long)j * TS * Np + (long long)j * TS;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = Dj[(by * 32 + r) * TS + bx * 32 + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) Ut[(long long)(bx * 32 + r) * Np + by * 32 + tx] = tile[tx][r];
+}
+}  // namespace
+
+int g3_trtri_batched(g3_ctx* ctx, const double* L, double* U, int Np, int B, const double* Dinv) {
+  const int T = Np / TS;
+  int rc;
+  u_diag_from_dinv_kernel<<<dim3(16, T, B), 256, 0, ctx->stream>>>(Dinv, U, Np, T);
+  G3_LAUNCH_CHECK(ctx);
+  CUtensorMap tmU, tmL, tmD;
+  if ((rc = g3_make_tmap(ctx, &tmU, U, Np, Np, B, Np, (uint64_t)Np * Np, G3_BM))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmL, L, Np, Np, B, Np, (uint64_t)Np * Np, G3_BN))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmD, Dinv, TS, (uint64_t)T * TS, B, TS, (uint64_t)T * TS * TS, G3_BN))) return rc;
+  const long long strideU = (long long)Np * Np;
+  for (int i = 1; i < T; ++i) {
+    {  // S[j][i] = sum_{k in [j, i)} U[j][k] L[i][k]^T  -> stored in U tile (j, i)
+      GemmArgs g = gemm_zero();
+      g.D = U; g.ldd = Np; g.strideD = strideU;
+      g.mode = 0; g.ntx = i; g.nty = 1;
+      g.d_r0 = 0; g.d_c0 = i * TS;
+      g.a_r0 = 0; g.a_rx = TS;
+      g.b_r0 = i * TS;
+      g.ka0 = 0; g.ka_x = TS; g.kb0 = 0; g.kb_x = TS;
+      g.kl0 = i * TS; g.kl_x = -TS;
+      g.alpha = 1.0; g.beta = 0.0;
+      if ((rc = g3_gemm_launch(ctx, tmU, tmL, g, B))) return rc;
+    }
+    {  // U[j][i] = -S Linv_ii^T
+      GemmArgs g = gemm_zero();
+      g.D = U; g.ldd = Np; g.strideD = strideU;
+      g.mode = 0; g.ntx = i; g.nty = 1;
+      g.d_r0 = 0; g.d_c0 = i * TS;
+      g.a_r0 = 0; g.a_rx = TS; g.ka0 = i * TS;
+      g.b_r0 = i * TS; g.kb0 = 0;
+      g.kl0 = TS;
+      g.alpha = -1.0; g.beta = 0.0;
+      if ((rc = g3_gemm_launch(ctx, tmU, tmD, g, B))) return rc;
+    }
+  }
+  return 0;
+}
+
+int g3_lauum_batched(g3_ctx* ctx, const double* U, double* Kinv, int Np, int B) {
+  const int T = Np / TS;
+  int rc;
+  CUtensorMap tmA, tmB;
+  if ((rc = g3_make_tmap(ctx, &tmA, U, Np, Np, B, Np, (uint64_t)Np * Np, G3_BM))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmB, U, Np, Np, B, Np, (uint64_t)Np * Np, G3_BN))) return rc;
+  GemmArgs g = gemm_zero();
+  g.D = Kinv; g.ldd = Np; g.strideD = (long long)Np * Np;
+  g.mode = 1; g.ntx = T;
+  g.d_r0 = 0; g.d_c0 = 0;
+  g.a_r0 = 0; g.a_rx = TS;
+  g.b_r0 = 0; g.b_ry = TS;
+  g.ka0 = 0; g.ka_x = TS; g.kb0 = 0; g.kb_x = TS;
+  g.kl0 = Np; g.kl_x = -TS;
+  g.alpha = 1.0; g.beta = 0.0;
+  return g3_gemm_launch(ctx, tmA, tmB, g, B);
+}
+
+int g3_trsv_fwd(g3_ctx* ctx, const double* L, const double* Dinv, double* r, double* u, double* beta, int Np, int B) {
+  const int T = Np / TS;
+  for (int j = 0; j < T; ++j) {
+    trsv_fwd_step_kernel<<<dim3(T - j, B), 256, 0, ctx->stream>>>(L, Dinv, r, u, beta, j, Np, T);
+    G3_LAUNCH_CHECK(ctx);
+  }
+  return 0;
+}
+
+int g3_trsv_bwd(g3_ctx* ctx, const double* L, const double* Dinv, double* s, double* alpha, int Np, int B) {
+  const int T = Np / TS;
+  for (int j = T - 1; j >= 0; --j) {
+    trsv_bwd_step_kernel<<<dim3(j + 1, B), 256, 0, ctx->stream>>>(L, Dinv, s, alpha, j, Np, T);
+    G3_LAUNCH_CHECK(ctx);
+  }
+  return 0;
+}

@@ -1,0 +1,327 @@
+"""Kernel algebra (mirror of g3py/processes/hypers/kernels.py for the hot-path kernels).
+
+The reference's `Kernel.cov` builds a Theano expression; here each kernel *compiles* itself into the
+post-order `g3_kernel_desc` tree that the CUDA Gram kernels interpret (include/g3b.h), so that
+`k1 + k2`, `k1 * k2`, `c * k`, `c + k` (kernels.py:51-75) keep working unchanged.
+"""
+import numpy as np
+
+from . import Hypers, HyperVar
+from .. import _cabi as cabi
+
+__all__ = ["Kernel", "KernelStationary", "KernelSum", "KernelProd", "KernelScale", "KernelShift", "KernelNoise", "WN",
+           "SE", "OU", "MAT32", "MAT52", "RQ", "SIN", "KernelPeriodic", "DescBuilder"]
+
+
+class DescBuilder:
+    """Collects nodes and the kernel-theta layout (free hypers first come, constants in extra slots)."""
+
+    def __init__(self, D):
+        self.D = D
+        self.nodes = []
+        self.slots = []          # (HyperVar | None, size, constant ndarray | None)
+        self.n_theta = 0
+
+    def slot(self, h, size):
+        """Index of hyper `h` (HyperVar, or a fixed number / array) in the kernel theta vector."""
+        if isinstance(h, HyperVar):
+            for hv, off, sz, _ in self.slots:
+                if hv is h:
+                    return off
+            off = self.n_theta
+            self.slots.append((h, off, h.size, None))
+            self.n_theta += h.size
+            return off
+        val = np.broadcast_to(np.asarray(h, dtype=np.float64), (size,)).copy()
+        off = self.n_theta
+        self.slots.append((None, off, size, val))
+        self.n_theta += size
+        return off
+
+    def node(self, op, dim0=0, dim1=0, var_idx=-1, p0=-1, p1=-1, flags=0, value=0.0):
+        if len(self.nodes) >= cabi.G3_MAX_NODES:
+            raise ValueError("kernel expression has more than %d nodes" % cabi.G3_MAX_NODES)
+        self.nodes.append((op, dim0, dim1, var_idx, p0, p1, flags, float(value)))
+        return len(self.nodes) - 1
+
+    def finish(self):
+        if self.n_theta > cabi.G3_MAX_THETA:
+            raise ValueError("kernel has more than %d hyper slots" % cabi.G3_MAX_THETA)
+        d = cabi.KernelDesc()
+        d.n_nodes = len(self.nodes)
+        d.n_theta = self.n_theta
+        for i, (op, d0, d1, vi, p0, p1, fl, val) in enumerate(self.nodes):
+            n = d.nodes[i]
+            n.op, n.dim0, n.dim1, n.var_idx, n.p0_idx, n.p1_idx, n.flags, n.value = op, d0, d1, vi, p0, p1, fl, val
+        return d
+
+
+class Kernel(Hypers):
+    """kernels.py:13-79."""
+
+    def __init__(self, x=None, name=None, var=None):
+        super().__init__(x, name)
+        self.var = var
+
+    def check_hypers(self, parent="", reg=None):
+        if self.var is None:
+            self.var = reg.FlatExp(parent + self.name + "_var")          # kernels.py:22-24
+        if isinstance(self.var, HyperVar) and self.var not in self.hypers:
+            self.hypers += [self.var]
+
+    def default_hypers(self, x=None, y=None):
+        return {self.var: float(np.var(y))} if isinstance(self.var, HyperVar) else {}   # kernels.py:33-40
+
+    def compile(self, b, process_noise=False):
+        raise NotImplementedError
+
+    def cov(self, x1, x2=None, **hypers):
+        """Numeric Kernel.cov through the device (kernels.py:106-110); hypers by bare name, natural space."""
+        from ..processes import kernel_cov
+        return kernel_cov(self, x1, x2, hypers)
+
+    def __mul__(self, other):
+        return KernelProd(self, other) if isinstance(other, Kernel) else KernelScale(self, other)
+    __imul__ = __mul__
+
+    def __rmul__(self, other):
+        return KernelProd(other, self) if isinstance(other, Kernel) else KernelScale(self, other)
+
+    def __add__(self, other):
+        return KernelSum(self, other) if isinstance(other, Kernel) else KernelShift(self, other)
+    __iadd__ = __add__
+
+    def __radd__(self, other):
+        return KernelSum(other, self) if isinstance(other, Kernel) else KernelShift(self, other)
+
+
+class KernelOperation(Kernel):
+    """kernels.py:112-139 — scalar (*) or (+) kernel."""
+    OP = None
+
+    def __init__(self, _k, _element):
+        self.k = _k
+        self.element = float(_element)
+        self.hypers = []
+        self.potential = None
+
+    @property
+    def name(self):
+        return str(self.element) + " " + self.op + " " + self.k.name
+
+    def check_hypers(self, parent="", reg=None):
+        self.k.check_hypers(parent=parent, reg=reg)
+        self.hypers = self.k.hypers
+
+    def check_dims(self, x=None):
+        self.k.check_dims(x)
+
+    def default_hypers_dims(self, x=None, y=None):
+        return self.k.default_hypers_dims(x, y)
+
+    def compile(self, b, process_noise=False):
+        c = self.k.compile(b)
+        return b.node(self.OP, dim0=c, value=self.element)
+
+
+class KernelScale(KernelOperation):
+    OP = cabi.K_SCALE
+    op = "*"
+
+
+class KernelShift(KernelOperation):
+    OP = cabi.K_SHIFT
+    op = "+"
+
+
+class KernelComposition(Kernel):
+    """kernels.py:142-189."""
+    OP = None
+
+    def __init__(self, _k1, _k2):
+        self.k1 = _k1
+        self.k2 = _k2
+        self.hypers = []
+        self.potential = None
+
+    @property
+    def name(self):
+        return self.k1.name + " " + self.op + " " + self.k2.name
+
+    def check_hypers(self, parent="", reg=None):
+        self.k1.check_hypers(parent=parent, reg=reg)
+        self.k2.check_hypers(parent=parent, reg=reg)
+        self.hypers = self.k1.hypers + self.k2.hypers
+
+    def check_dims(self, x=None):
+        self.k1.check_dims(x)
+        self.k2.check_dims(x)
+
+    def default_hypers_dims(self, x=None, y=None):
+        return {**self.k1.default_hypers_dims(x, y), **self.k2.default_hypers_dims(x, y)}
+
+    def compile(self, b, process_noise=False):
+        l = self.k1.compile(b)
+        r = self.k2.compile(b, process_noise=process_noise)
+        return b.node(self.OP, dim0=l, dim1=r)
+
+
+class KernelProd(KernelComposition):
+    OP = cabi.K_PROD
+    op = "*"
+
+    def __init__(self, _k1, _k2):
+        super().__init__(_k1, _k2)
+        # kernels.py:215-219: two leaf kernels that both have var=None -> the second var is fixed to 1.0
+        if hasattr(self.k1, "var") and hasattr(self.k2, "var"):
+            if self.k1.var is None and self.k2.var is None:
+                self.k2.var = 1.0
+
+
+class KernelSum(KernelComposition):
+    OP = cabi.K_SUM
+    op = "+"
+
+
+class KernelStationary(Kernel):
+    """kernels.py:96-110: cov = var * k(metric.gram(x1, x2)); metric hypers follow `var`."""
+    OPCODE = None
+    RATE_DEFAULT = "l2"
+
+    def __init__(self, x=None, name=None, var=None, rate=None):
+        super().__init__(x, name, var)
+        self.rate = rate
+
+    def check_hypers(self, parent="", reg=None):
+        super().check_hypers(parent, reg)
+        if self.rate is None:                                            # metrics.py:79-83  (ARD.check_hypers)
+            self.rate = reg.FlatExp(parent + self.name + "_rate", shape=self.shape)
+        if isinstance(self.rate, HyperVar) and self.rate not in self.hypers:
+            self.hypers += [self.rate]
+
+    def default_hypers(self, x=None, y=None):
+        d = super().default_hypers(x, y)
+        if isinstance(self.rate, HyperVar):
+            try:
+                m = np.abs(x[1:] - x[:-1]).mean(axis=0)
+                d[self.rate] = (0.5 if self.RATE_DEFAULT == "l2" else 1.0) / m   # metrics.py:93-94,104-108
+            except Exception:
+                pass
+        return d
+
+    def _common(self, b):
+        d0, d1 = self.dim_range(b.D)
+        nd = d1 - d0
+        if isinstance(self.var, HyperVar):
+            vi, val = b.slot(self.var, 1), 0.0
+        else:
+            vi, val = -1, float(self.var)
+        return d0, d1, nd, vi, val
+
+    def compile(self, b, process_noise=False):
+        d0, d1, nd, vi, val = self._common(b)
+        p0 = b.slot(self.rate, nd)
+        return b.node(self.OPCODE, d0, d1, vi, p0, -1, 0, val)
+
+
+class SE(KernelStationary):          # kernels.py:434-436
+    OPCODE = cabi.K_SE
+
+
+class OU(KernelStationary):          # kernels.py:429-431 (ARD_L1 metric)
+    OPCODE = cabi.K_OU
+    RATE_DEFAULT = "l1"
+
+
+class MAT32(KernelStationary):       # kernels.py:406-412
+    OPCODE = cabi.K_MAT32
+
+
+class MAT52(KernelStationary):       # kernels.py:415-421
+    OPCODE = cabi.K_MAT52
+
+
+class RQ(KernelStationary):          # kernels.py:388-403
+    OPCODE = cabi.K_RQ
+
+    def __init__(self, x=None, name=None, var=None, rate=None, alpha=None):
+        super().__init__(x, name, var, rate)
+        self.alpha = alpha
+
+    def check_hypers(self, parent="", reg=None):
+        super().check_hypers(parent, reg)
+        if self.alpha is None:
+            self.alpha = reg.FlatExp(parent + self.name + "_alpha")
+        if isinstance(self.alpha, HyperVar) and self.alpha not in self.hypers:
+            self.hypers += [self.alpha]
+
+    def default_hypers(self, x=None, y=None):
+        d = super().default_hypers(x, y)
+        if isinstance(self.alpha, HyperVar):
+            d[self.alpha] = 1.0
+        return d
+
+    def compile(self, b, process_noise=False):
+        d0, d1, nd, vi, val = self._common(b)
+        p0 = b.slot(self.rate, nd)
+        p1 = b.slot(self.alpha, 1)
+        return b.node(self.OPCODE, d0, d1, vi, p0, p1, 0, val)
+
+
+class KernelPeriodic(KernelStationary):
+    """kernels.py:439-459: Difference metric (no hypers); freq is created before rate."""
+
+    def __init__(self, x=None, name=None, var=None, freq=None, rate=None):
+        super().__init__(x, name, var, rate)
+        self.freq = freq
+
+    def check_hypers(self, parent="", reg=None):
+        Kernel.check_hypers(self, parent, reg)
+        if self.freq is None:
+            self.freq = reg.FlatExp(parent + self.name + "_freq", shape=self.shape)
+        if self.rate is None:
+            self.rate = reg.FlatExp(parent + self.name + "_rate", shape=self.shape)
+        for h in (self.rate, self.freq):
+            if isinstance(h, HyperVar) and h not in self.hypers:
+                self.hypers += [h]
+
+    def default_hypers(self, x=None, y=None):
+        d = Kernel.default_hypers(self, x, y)
+        if isinstance(self.freq, HyperVar):
+            d[self.freq] = 1.0 / (x.max(axis=0) - x.min(axis=0))
+        if isinstance(self.rate, HyperVar):
+            d[self.rate] = 1.0 / np.abs(x[1:] - x[:-1]).mean(axis=0)
+        return d
+
+
+class SIN(KernelPeriodic):           # kernels.py:470-472
+    OPCODE = cabi.K_SIN
+
+    def compile(self, b, process_noise=False):
+        d0, d1, nd, vi, val = self._common(b)
+        p1 = b.slot(self.freq, nd)
+        p0 = b.slot(self.rate, nd)
+        return b.node(self.OPCODE, d0, d1, vi, p0, p1, 0, val)
+
+
+class KernelNoise(Kernel):           # kernels.py:360-371
+    OPCODE = cabi.K_NOISE
+
+    def compile(self, b, process_noise=False):
+        if isinstance(self.var, HyperVar):
+            vi, val = b.slot(self.var, 1), 0.0
+        else:
+            vi, val = -1, float(self.var)
+        return b.node(self.OPCODE, 0, 0, vi, -1, -1, cabi.KF_PROCESS_NOISE if process_noise else 0, val)
+
+
+class WN(Kernel):                    # kernels.py:374-385
+    OPCODE = cabi.K_WN
+
+    def compile(self, b, process_noise=False):
+        d0, d1 = self.dim_range(b.D)
+        if isinstance(self.var, HyperVar):
+            vi, val = b.slot(self.var, 1), 0.0
+        else:
+            vi, val = -1, float(self.var)
+        return b.node(self.OPCODE, d0, d1, vi, -1, -1, 0, val)

@@ -1,0 +1,339 @@
+"""Warpings T — mirror of the closed-form maps of g3py/processes/hypers/mappings.py.
+
+O(N) elementwise work that stays on the host: `inv(y)` and `logdet_dinv(y)` feed `delta` and
+`det_m` to the device path; `dinv`/`dlogdet` are the hyper-derivatives Theano's autodiff would
+produce for them.  Hyper values come through `p(h)` (natural space).
+"""
+import numpy as np
+
+from . import Hypers, HyperVar
+
+__all__ = ["Mapping", "Identity", "LinearMapping", "LogShifted", "BoxCoxShifted", "BoxCoxLinear", "ArcsinhLinear",
+           "SinhArcsinh", "MappingComposed"]
+
+_F32_1EM32 = float(np.float32(1e-32))
+_F32_1EM5 = float(np.float32(1e-5))
+
+
+def _v(p, h):
+    return float(p(h)) if isinstance(h, HyperVar) else float(h)
+
+
+class Mapping(Hypers):
+    def __call__(self, z, p):
+        raise NotImplementedError
+
+    def inv(self, y, p):
+        raise NotImplementedError
+
+    def logdet_dinv(self, y, p):
+        raise NotImplementedError
+
+    def grads(self, y, p):
+        """({HyperVar: d inv/d h (n,)}, {HyperVar: d logdet/d h}) in natural space."""
+        return {}, {}
+
+    def dinv_dy(self, y, p):
+        """d inv / d y (n,), needed to chain composed maps."""
+        raise NotImplementedError
+
+    def _reg(self, parent, reg, attr, positive):
+        h = getattr(self, attr)
+        if h is None:
+            h = (reg.FlatExp if positive else reg.Flat)(parent + self.name + "_" + attr)
+            setattr(self, attr, h)
+        if isinstance(h, HyperVar) and h not in self.hypers:
+            self.hypers += [h]
+
+    def __matmul__(self, other):
+        return MappingComposed(self, other)
+    __imatmul__ = __matmul__
+
+
+class MappingComposed(Mapping):      # mappings.py:56-71
+    def __init__(self, m1, m2):
+        self.m1, self.m2 = m1, m2
+        self.hypers = []
+        self.name = m1.name + " " + m2.name
+        self.dims = None
+        self.shape = None
+
+    def check_hypers(self, parent="", reg=None):
+        self.m1.check_hypers(parent=parent, reg=reg)
+        self.m2.check_hypers(parent=parent, reg=reg)
+        self.hypers = self.m1.hypers + self.m2.hypers
+
+    def check_dims(self, x=None):
+        self.m1.check_dims(x)
+        self.m2.check_dims(x)
+
+    def default_hypers_dims(self, x=None, y=None):
+        return {**self.m1.default_hypers_dims(x, y), **self.m2.default_hypers_dims(x, y)}
+
+    def __call__(self, z, p):
+        return self.m1(self.m2(z, p), p)
+
+    def inv(self, y, p):
+        return self.m2.inv(self.m1.inv(y, p), p)
+
+    def logdet_dinv(self, y, p):
+        return self.m2.logdet_dinv(self.m1.inv(y, p), p) + self.m1.logdet_dinv(y, p)
+
+    def dinv_dy(self, y, p):
+        w = self.m1.inv(y, p)
+        return self.m2.dinv_dy(w, p) * self.m1.dinv_dy(y, p)
+
+    def grads(self, y, p):
+        # numerical hyper-derivatives by 4th-order central differences would hide errors; composed maps use
+        # the chain rule on the pieces: inv = m2.inv(m1.inv(y)), logdet = m2.logdet(m1.inv(y)) + m1.logdet(y)
+        w = self.m1.inv(y, p)
+        di1, dl1 = self.m1.grads(y, p)
+        di2, dl2 = self.m2.grads(w, p)
+        d2dw = self.m2.dinv_dy(w, p)
+        # d logdet2 / d w (n,) by differentiating m2.logdet_dinv = sum log|d inv2/dw|: use finite differences
+        # of dinv_dy (elementwise maps): d/dw log|dinv2/dw|
+        h = 1e-6 * np.maximum(1.0, np.abs(w))
+        dlog = (np.log(np.abs(self.m2.dinv_dy(w + h, p))) - np.log(np.abs(self.m2.dinv_dy(w - h, p)))) / (2 * h)
+        dinv = {k: d2dw * v for k, v in di1.items()}
+        dld = {k: v + float(np.sum(dlog * di1[k])) for k, v in dl1.items()}
+        for k, v in di2.items():
+            dinv[k] = v
+        for k, v in dl2.items():
+            dld[k] = v
+        return dinv, dld
+
+
+class Identity(Mapping):             # mappings.py:88-99
+    def __init__(self, y=None, name=None):
+        super().__init__(y, name)
+
+    def __call__(self, z, p=None):
+        return z
+
+    def inv(self, y, p=None):
+        return y
+
+    def logdet_dinv(self, y, p=None):
+        return 0.0
+
+    def dinv_dy(self, y, p=None):
+        return np.ones_like(y)
+
+
+class LinearMapping(Mapping):        # mappings.py:102-125
+    def __init__(self, y=None, name=None, shift=None, scale=None):
+        super().__init__(y, name)
+        self.shift, self.scale = shift, scale
+
+    def check_hypers(self, parent="", reg=None):
+        self._reg(parent, reg, "shift", False)
+        self._reg(parent, reg, "scale", True)
+
+    def default_hypers(self, x=None, y=None):
+        return {h: v for h, v in ((self.shift, 0.0), (self.scale, 1.0)) if isinstance(h, HyperVar)}
+
+    def __call__(self, z, p):
+        return _v(p, self.scale) * (z - _v(p, self.shift))
+
+    def inv(self, y, p):
+        return y / _v(p, self.scale) + _v(p, self.shift)
+
+    def logdet_dinv(self, y, p):
+        return -float(y.shape[0]) * np.log(_v(p, self.scale))
+
+    def dinv_dy(self, y, p):
+        return np.ones_like(y) / _v(p, self.scale)
+
+    def grads(self, y, p):
+        s = _v(p, self.scale)
+        n = float(y.shape[0])
+        return ({self.shift: np.ones_like(y), self.scale: -y / s ** 2}, {self.shift: 0.0, self.scale: -n / s})
+
+
+class LogShifted(Mapping):           # mappings.py:128-149
+    def __init__(self, y=None, name=None, shift=None):
+        super().__init__(y, name)
+        self.shift = shift
+
+    def check_hypers(self, parent="", reg=None):
+        self._reg(parent, reg, "shift", False)
+
+    def default_hypers(self, x=None, y=None):
+        return {self.shift: float(np.min(y)) - 1.0} if isinstance(self.shift, HyperVar) else {}
+
+    def __call__(self, z, p):
+        return np.exp(z) + _v(p, self.shift)
+
+    def inv(self, y, p):
+        return np.log(np.maximum(y - _v(p, self.shift), _F32_1EM32))
+
+    def logdet_dinv(self, y, p):
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return -np.sum(np.log(y - _v(p, self.shift)))
+
+    def dinv_dy(self, y, p):
+        return 1.0 / (y - _v(p, self.shift))
+
+    def grads(self, y, p):
+        sh = y - _v(p, self.shift)
+        live = sh > _F32_1EM32
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return {self.shift: np.where(live, -1.0 / sh, 0.0)}, {self.shift: float(np.sum(1.0 / sh))}
+
+
+class _BoxCox(Mapping):
+    def _params(self, p):
+        raise NotImplementedError
+
+    def inv(self, y, p):
+        shift, scale, power, thr = self._params(p)
+        sh = scale * (y + shift)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            if power < thr:
+                return np.log(sh)
+            return (np.sign(sh) * np.abs(sh) ** power - 1.0) / power
+
+    def dinv_dy(self, y, p):
+        shift, scale, power, thr = self._params(p)
+        sh = scale * (y + shift)
+        return np.abs(sh) ** (power - 1.0) * scale
+
+    def _grads(self, y, p):
+        shift, scale, power, thr = self._params(p)
+        n = float(y.shape[0])
+        sh = scale * (y + shift)
+        a = np.abs(sh)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            sp = np.sign(sh) * a ** power
+            d_shift = a ** (power - 1.0) * scale
+            d_scale = a ** (power - 1.0) * (y + shift)
+            d_power = (sp * np.log(a) * power - (sp - 1.0)) / power ** 2
+            ld_shift = (power - 1.0) * float(np.sum(1.0 / (y + shift)))
+            ld_power = float(np.sum(np.log(a)))
+        return d_shift, d_scale, d_power, ld_shift, power * n / scale, ld_power
+
+
+class BoxCoxShifted(_BoxCox):        # mappings.py:152-179
+    def __init__(self, y=None, name="BoxShift", shift=None, power=None):
+        super().__init__(y, name)
+        self.shift, self.power = shift, power
+
+    def check_hypers(self, parent="", reg=None):
+        self._reg(parent, reg, "shift", False)
+        self._reg(parent, reg, "power", True)
+
+    def default_hypers(self, x=None, y=None):
+        return {h: 1.0 for h in (self.shift, self.power) if isinstance(h, HyperVar)}
+
+    def _params(self, p):
+        return _v(p, self.shift), 1.0, _v(p, self.power), 1e-5
+
+    def __call__(self, z, p):
+        shift, _, power, _ = self._params(p)
+        sc = power * z + 1.0
+        return np.sign(sc) * np.abs(sc) ** (1.0 / power) - shift
+
+    def logdet_dinv(self, y, p):
+        shift, _, power, _ = self._params(p)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return (power - 1.0) * np.sum(np.log(np.abs(y + shift)))
+
+    def grads(self, y, p):
+        d_shift, _, d_power, ld_shift, _, ld_power = self._grads(y, p)
+        return {self.shift: d_shift, self.power: d_power}, {self.shift: ld_shift, self.power: ld_power}
+
+
+class BoxCoxLinear(_BoxCox):         # mappings.py:182-215
+    def __init__(self, y=None, name=None, shift=None, scale=None, power=None):
+        super().__init__(y, name)
+        self.shift, self.scale, self.power = shift, scale, power
+
+    def check_hypers(self, parent="", reg=None):
+        self._reg(parent, reg, "shift", False)
+        self._reg(parent, reg, "scale", True)
+        self._reg(parent, reg, "power", True)
+
+    def default_hypers(self, x=None, y=None):
+        return {h: 1.0 for h in (self.shift, self.scale, self.power) if isinstance(h, HyperVar)}
+
+    def _params(self, p):
+        return _v(p, self.shift), _v(p, self.scale), _v(p, self.power), _F32_1EM5
+
+    def __call__(self, z, p):
+        shift, scale, power, _ = self._params(p)
+        sc = power * z + 1.0
+        return np.sign(sc) * np.abs(sc) ** (1.0 / power) / scale - shift
+
+    def logdet_dinv(self, y, p):
+        shift, scale, power, _ = self._params(p)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return (power - 1.0) * np.sum(np.log(np.abs(scale * (y + shift)))) + float(y.shape[0]) * np.log(scale)
+
+    def grads(self, y, p):
+        d_shift, d_scale, d_power, ld_shift, ld_scale, ld_power = self._grads(y, p)
+        return ({self.shift: d_shift, self.scale: d_scale, self.power: d_power},
+                {self.shift: ld_shift, self.scale: ld_scale, self.power: ld_power})
+
+
+class ArcsinhLinear(Mapping):        # mappings.py:309-333
+    def __init__(self, y=None, name=None, shift=None, scale=None):
+        super().__init__(y, name)
+        self.shift, self.scale = shift, scale
+
+    def check_hypers(self, parent="", reg=None):
+        self._reg(parent, reg, "shift", False)
+        self._reg(parent, reg, "scale", True)
+
+    def default_hypers(self, x=None, y=None):
+        return {h: v for h, v in ((self.shift, float(np.mean(y))), (self.scale, float(np.std(y)))) if isinstance(h, HyperVar)}
+
+    def __call__(self, z, p):
+        return np.sinh((z - _v(p, self.shift)) / _v(p, self.scale))
+
+    def inv(self, y, p):
+        return np.arcsinh(y) * _v(p, self.scale) + _v(p, self.shift)
+
+    def logdet_dinv(self, y, p):
+        return float(y.shape[0]) * np.log(_v(p, self.scale)) - 0.5 * np.sum(np.log1p(y ** 2))
+
+    def dinv_dy(self, y, p):
+        return _v(p, self.scale) / np.sqrt(1.0 + y ** 2)
+
+    def grads(self, y, p):
+        n = float(y.shape[0])
+        return ({self.shift: np.ones_like(y), self.scale: np.arcsinh(y)}, {self.shift: 0.0, self.scale: n / _v(p, self.scale)})
+
+
+class SinhArcsinh(Mapping):          # mappings.py:336-358
+    def __init__(self, y=None, name=None, shift=None, scale=None):
+        super().__init__(y, name)
+        self.shift, self.scale = shift, scale
+
+    def check_hypers(self, parent="", reg=None):
+        self._reg(parent, reg, "shift", False)
+        self._reg(parent, reg, "scale", True)
+
+    def default_hypers(self, x=None, y=None):
+        return {h: v for h, v in ((self.shift, 0.0), (self.scale, 1.0)) if isinstance(h, HyperVar)}
+
+    def __call__(self, z, p):
+        return np.sinh((np.arcsinh(z) - _v(p, self.shift)) / _v(p, self.scale))
+
+    def inv(self, y, p):
+        return np.sinh(_v(p, self.shift) + _v(p, self.scale) * np.arcsinh(y))
+
+    def logdet_dinv(self, y, p):
+        w = _v(p, self.shift) + _v(p, self.scale) * np.arcsinh(y)
+        return (np.sum(np.log(np.cosh(w))) + float(y.shape[0]) * np.log(_v(p, self.scale)) - 0.5 * np.sum(np.log1p(y ** 2)))
+
+    def dinv_dy(self, y, p):
+        w = _v(p, self.shift) + _v(p, self.scale) * np.arcsinh(y)
+        return np.cosh(w) * _v(p, self.scale) / np.sqrt(1.0 + y ** 2)
+
+    def grads(self, y, p):
+        s = _v(p, self.scale)
+        ash = np.arcsinh(y)
+        w = _v(p, self.shift) + s * ash
+        n = float(y.shape[0])
+        return ({self.shift: np.cosh(w), self.scale: np.cosh(w) * ash},
+                {self.shift: float(np.sum(np.tanh(w))), self.scale: float(np.sum(np.tanh(w) * ash)) + n / s})

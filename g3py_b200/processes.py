@@ -1,0 +1,701 @@
+"""Process API: GaussianProcess / WarpedGaussianProcess / StudentTProcess / WarpedStudentTProcess.
+
+Host-side mirror of g3py/processes/{stochastic,elliptical,gaussian,studentT}.py for the exact-GP hot
+path.  The reference compiles one Theano function per method (`_method_name`,
+stochastic.py:385-430); here every method assembles O(N) host terms (mean, warping, scalar
+constants) around ONE call into libg3b.so, which does the Gram matrix, Cholesky, solves and the
+analytic gradient on the GPU for a whole batch of hyper samples.  No CPU fallback exists: without
+the library or a B200 the calls raise.
+"""
+import math
+
+import numpy as np
+from scipy import stats
+from scipy.special import gammaln, digamma
+
+from . import _cabi as cabi
+from .hypers import Registry, HyperVar, Freedom
+from .hypers.kernels import KernelSum, KernelNoise, DescBuilder, Kernel
+from .hypers.mappings import Identity
+
+__all__ = ["StochasticProcess", "EllipticalProcess", "GaussianProcess", "WarpedGaussianProcess", "StudentTProcess",
+           "WarpedStudentTProcess", "GP", "WGP", "TP", "WTP", "Consts", "kernel_cov", "get_context"]
+
+f32 = np.float32
+_CONTEXTS = {}
+
+
+def get_context(device=0):
+    """Per-process, per-device context, created on first use (fork-safe)."""
+    import os
+    key = (os.getpid(), int(device))
+    ctx = _CONTEXTS.get(key)
+    if ctx is None:
+        ctx = cabi.Context(device)
+        _CONTEXTS[key] = ctx
+    return ctx
+
+
+class Consts:
+    """Scalar constants of the reference graph.  strict=True keeps the float32-rounded literals that
+    survive in an fp64 run of g3py (gaussian.py:218, studentT.py:122-128, tensors.py:98,204,221)."""
+
+    def __init__(self, strict=True):
+        self.strict = strict
+        if strict:
+            self.log_2pi = float(np.log(f32(2.0 * np.pi)))
+            self.pi = float(f32(np.pi))
+            self.log_2pi_student = float(np.log(f32(2.0) * f32(np.pi)))
+            self.jitter = float(f32(1e-6))
+            self.guard = float(f32(-1e30))
+            self.fallback = float(f32(1e-10))
+        else:
+            self.log_2pi = math.log(2.0 * math.pi)
+            self.pi = math.pi
+            self.log_2pi_student = math.log(2.0 * math.pi)
+            self.jitter = 1e-6
+            self.guard = -1e30
+            self.fallback = 1e-10
+
+
+class DictObj(dict):
+    """libs/__init__.py:17-44 — dict with attribute access."""
+    __getattr__ = dict.get
+    __setattr__ = dict.__setitem__
+
+    def clone(self):
+        return DictObj(self.copy())
+
+
+def tt_to_num(r, nan=0.0, inf=1e10):
+    """libs/tensors.py:90-92 applied to host vectors (the gradient scrub of stochastic.py:308-309)."""
+    r = np.asarray(r, dtype=np.float64)
+    return np.where(np.isnan(r), nan, np.where(np.isinf(r), inf, r))
+
+
+class StochasticProcess:
+    """stochastic.py:20-201 — data handling, parameter dictionaries, bijection."""
+
+    def __init__(self, space=None, order=None, inputs=None, outputs=None, hidden=None, index=None, name="SP",
+                 device=0, strict_constants=True, **kwargs):
+        ndim = 1
+        if space is not None:
+            if hasattr(space, "shape"):
+                if len(space.shape) > 1:
+                    ndim = space.shape[1]
+            else:
+                ndim = int(space)
+                space = None
+        self.nspace = ndim
+        self.name = name
+        self.device = device
+        self.consts = Consts(strict_constants)
+        # the reference's 2-point dummy dataset (stochastic.py:46-56)
+        self.space = np.array([[0.0, 1.0]] * ndim).T
+        self.inputs = np.array([[0.0, 1.0]] * ndim).T
+        self.outputs = np.array([0.0, 1.0])
+        self.order = np.array([0.0, 1.0])
+        self.index = np.array([0.0, 1.0])
+        self.hidden = None
+        self.is_observed = False
+        self.executed = {"logp": 0, "dlogp": 0, "predict": 0}
+        self._data_version = 0
+        self._ctx_version = -1
+        self.registry = Registry()
+        self._check_hypers()
+        self._define_process()
+        self.set_space(space=space, hidden=hidden, order=order, inputs=inputs, outputs=outputs, index=index)
+        self._params = None
+
+    # ---- pickling: the device context is per process and never pickled (stochastic.py:107-119)
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_ctx_version"] = -1
+        return d
+
+    @property
+    def ctx(self):
+        ctx = get_context(self.device)
+        tag = (id(self), self._data_version)
+        if getattr(ctx, "_data_tag", None) != tag:
+            ctx.set_jitter(self.consts.jitter, 20)
+            ctx.set_data(self.inputs)
+            ctx._data_tag = tag
+        return ctx
+
+    def set_space(self, space=None, hidden=None, order=None, inputs=None, outputs=None, index=None):
+        # stochastic.py:150-185
+        if space is not None:
+            space = np.asarray(space, dtype=np.float64)
+            if space.ndim < 2:
+                space = space.reshape(len(space), 1)
+            self.space = space
+        if hidden is not None:
+            self.hidden = np.asarray(hidden, dtype=np.float64).reshape(-1)
+        if order is not None:
+            self.order = np.asarray(order).reshape(-1)
+        elif self.nspace == 1:
+            self.order = self.space.reshape(len(self.space))
+        if inputs is not None:
+            inputs = np.asarray(inputs, dtype=np.float64)
+            if inputs.ndim < 2:
+                inputs = inputs.reshape(len(inputs), 1)
+            self.inputs = np.ascontiguousarray(inputs)
+            self._data_version += 1
+        if outputs is not None:
+            self.outputs = np.asarray(outputs, dtype=np.float64).reshape(-1)
+        if index is not None:
+            self.index = np.asarray(index).reshape(-1)
+        elif self.nspace == 1:
+            self.index = self.inputs.reshape(len(self.inputs))
+        if len(self.order) != len(self.space):
+            self.order = np.arange(len(self.space))
+        if len(self.index) != len(self.inputs):
+            self.index = np.arange(len(self.inputs))
+
+    def observed(self, inputs=None, outputs=None, order=None, index=None, hidden=None):
+        # stochastic.py:187-201
+        self.set_space(inputs=inputs, outputs=outputs, order=order, index=index, hidden=hidden)
+        self.is_observed = not (inputs is None and outputs is None)
+        self._params = None
+
+    # ---- theta layout / bijection (bayesian/models.py:143-203)
+    def _finish_layout(self):
+        off = 0
+        for v in self.registry.vars:
+            v.offset = off
+            off += v.size
+        self.ndim = off
+        self.positive_mask = np.zeros(off, dtype=bool)
+        for v in self.registry.vars:
+            self.positive_mask[v.offset:v.offset + v.size] = v.positive
+
+    @property
+    def layout(self):
+        return [(v.name, v.size, v.positive) for v in self.registry.vars]
+
+    def dict_to_array(self, params):
+        """DictToArrayBijection.map: dict keyed by transformed names (`*_log__`, log values) -> flat theta.
+        Bare names are accepted too and taken as natural-space values."""
+        theta = self.dict_to_array_default()
+        for v in self.registry.vars:
+            sl = slice(v.offset, v.offset + v.size)
+            for key, is_log in ((v.tname, True), (v.name + "_log_", True), (v.name, False)):
+                if key in params:
+                    val = np.asarray(params[key], dtype=np.float64).reshape(-1)
+                    if v.positive and not is_log:
+                        val = np.log(val)
+                    theta[sl] = val
+                    break
+        return theta
+
+    def dict_to_array_default(self):
+        return np.zeros(self.ndim)
+
+    def array_to_dict(self, theta):
+        """DictToArrayBijection.rmap."""
+        theta = np.asarray(theta, dtype=np.float64)
+        out = DictObj()
+        for v in self.registry.vars:
+            val = theta[v.offset:v.offset + v.size]
+            out[v.tname] = float(val[0]) if v.scalar else val.copy()
+        return out
+
+    def natural(self, theta):
+        theta = np.asarray(theta, dtype=np.float64)
+        m = self.positive_mask
+        with np.errstate(over="ignore"):
+            return np.where(m, np.exp(np.where(m, theta, 0.0)), theta)
+
+    @property
+    def params_test(self):
+        """model.test_point: Flat -> 0, FlatExp -> 1 (log value 0) (hypers/__init__.py:116-126)."""
+        return self.array_to_dict(np.zeros(self.ndim))
+
+    @property
+    def params_default(self):
+        """bayesian/models.py:174-182: test point overwritten with the components' default_hypers."""
+        theta = np.zeros(self.ndim)
+        for h, val in self.default_hypers().items():
+            if not isinstance(h, HyperVar):
+                continue
+            val = np.broadcast_to(np.asarray(val, dtype=np.float64).reshape(-1), (h.size,))
+            theta[h.offset:h.offset + h.size] = np.log(val) if h.positive else val
+        return self.array_to_dict(theta)
+
+    @property
+    def params(self):
+        if self._params is None:
+            self._params = self.params_default if self.is_observed else self.params_test
+        return self._params
+
+    @params.setter
+    def params(self, p):
+        self._params = DictObj(p)
+
+    def _theta(self, params, array):
+        if params is None:
+            return self.dict_to_array(self.params)
+        if array or isinstance(params, np.ndarray):
+            return np.asarray(params, dtype=np.float64)
+        return self.dict_to_array(params)
+
+    def default_hypers(self):
+        return {}
+
+    def _check_hypers(self):
+        pass
+
+    def _define_process(self):
+        pass
+
+
+class EllipticalProcess(StochasticProcess):
+    """elliptical.py:18-107 — location + kernel (+ auto Noise) + mapping (+ degree)."""
+    KIND = cabi.KIND_GAUSS
+    WARPED = False
+
+    def __init__(self, space=None, location=None, kernel=None, mapping=None, degree=None, noisy=True, var_noise=None,
+                 *args, **kwargs):
+        from .hypers.means import Zero
+        self.f_location = location if location is not None else Zero()
+        self.f_degree = degree
+        self.f_mapping = mapping if mapping is not None else Identity()
+        self.f_kernel = kernel
+        self.noisy = bool(noisy)
+        if noisy:                                               # elliptical.py:26-28
+            self.f_kernel_noise = KernelSum(self.f_kernel, KernelNoise(name="Noise", var=var_noise))
+        else:
+            self.f_kernel_noise = self.f_kernel
+        kwargs["space"] = space
+        super().__init__(*args, **kwargs)
+
+    def _check_hypers(self):
+        # creation order = theta order (elliptical.py:35-52)
+        x = self.inputs
+        self.f_location.check_dims(x)
+        self.f_kernel_noise.check_dims(x)
+        self.f_mapping.check_dims(x)
+        parent = self.name + "_"
+        self.f_location.check_hypers(parent, self.registry)
+        self.f_kernel_noise.check_hypers(parent, self.registry)
+        self.f_mapping.check_hypers(parent, self.registry)
+        if self.f_degree is not None:
+            self.f_degree.check_dims(None)
+            self.f_degree.check_hypers(parent, self.registry)
+        self._finish_layout()
+
+    def _define_process(self):
+        b = DescBuilder(self.nspace)
+        if self.noisy:
+            self.f_kernel_noise.compile(b, process_noise=True)
+        else:
+            self.f_kernel_noise.compile(b)
+        self.desc = b.finish()
+        self._slots = b.slots
+        bf = DescBuilder(self.nspace)                 # f_kernel alone: prior selectors with noise=False
+        self.f_kernel.compile(bf)
+        self.desc_f = bf.finish()
+        self._slots_f = bf.slots
+
+    def __getstate__(self):
+        d = super().__getstate__()
+        d.pop("desc", None)      # ctypes structures: rebuilt on load
+        d.pop("desc_f", None)
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._define_process()
+
+    def default_hypers(self):
+        x, y = self.inputs, self.outputs
+        return {**self.f_location.default_hypers_dims(x, y), **self.f_kernel_noise.default_hypers_dims(x, y),
+                **self.f_mapping.default_hypers_dims(x, y)}      # elliptical.py:54-58 (degree not included)
+
+    # ---- pieces ----------------------------------------------------------------------------
+    def _accessor(self, nat):
+        def p(h):
+            v = nat[h.offset:h.offset + h.size]
+            return float(v[0]) if h.scalar else v
+        return p
+
+    def _kernel_theta(self, nat2d, slots=None, n_theta=None):
+        """(B, n_slots) natural-space kernel hypers in the slot order of the compiled descriptor."""
+        slots = self._slots if slots is None else slots
+        n_theta = self.desc.n_theta if n_theta is None else n_theta
+        B = nat2d.shape[0]
+        th = np.empty((B, max(n_theta, 1)))
+        for h, off, size, const in slots:
+            if h is None:
+                th[:, off:off + size] = const
+            else:
+                th[:, off:off + size] = nat2d[:, h.offset:h.offset + h.size]
+        return th[:, :n_theta]
+
+    def _nu(self, nat2d):
+        if self.f_degree is None:
+            return None
+        d = self.f_degree.degree
+        deg = nat2d[:, d.offset] if isinstance(d, HyperVar) else np.full(nat2d.shape[0], float(d))
+        return self.f_degree.bound + deg                                  # hypers/__init__.py:159-160
+
+    def logprior_batch(self, Theta):
+        """Free-RV terms: Flat = 0, NonTransformLog barrier -inf at exp(theta) <= 1e-6."""
+        nat = self.natural(np.atleast_2d(Theta))
+        bad = np.any((nat <= 1e-6) & self.positive_mask[None, :], axis=1)
+        return np.where(bad, -np.inf, 0.0)
+
+    def _host_terms(self, nat2d, inputs, outputs, want_grad):
+        """delta (B,N) or (N,), det_m (B,), and the host Jacobians of the location / mapping hypers."""
+        B = nat2d.shape[0]
+        loc_h = [h for h in self.f_location.hypers if isinstance(h, HyperVar)]
+        map_h = [h for h in self.f_mapping.hypers if isinstance(h, HyperVar)]
+        varying = B > 1 and any(np.ptp(nat2d[:, h.offset:h.offset + h.size], axis=0).max() > 0 for h in loc_h + map_h)
+        rows = B if varying else 1
+        delta = np.empty((rows, len(outputs)))
+        det_m = np.empty(rows)
+        jac = []
+        for b in range(rows):
+            p = self._accessor(nat2d[b])
+            with np.errstate(all="ignore"):
+                delta[b] = self.f_mapping.inv(outputs, p) - self.f_location(inputs, p)   # gaussian.py:208
+                det_m[b] = self.f_mapping.logdet_dinv(outputs, p)
+            if want_grad:
+                with np.errstate(all="ignore"):
+                    jl = self.f_location.jacobian(inputs, p) if loc_h else {}
+                    dinv, dld = self.f_mapping.grads(outputs, p) if map_h else ({}, {})
+                jac.append((jl, dinv, dld))
+        if not varying:
+            det_m = np.broadcast_to(det_m, (B,)).copy()
+            return delta[0], det_m, jac, False
+        return delta, det_m, jac, True
+
+    def _eval_batch(self, Theta, inputs=None, outputs=None, want_grad=True):
+        """Core of logp/dlogp for a (B, P) array of theta (transformed space).  Returns
+        (loglike (B,), dlogp (B,P) or None, info dict)."""
+        Theta = np.atleast_2d(np.asarray(Theta, dtype=np.float64))
+        if Theta.shape[1] != self.ndim:
+            raise ValueError("theta has %d entries, the model has %d hypers" % (Theta.shape[1], self.ndim))
+        if inputs is not None or outputs is not None:
+            self.set_space(inputs=inputs, outputs=outputs)
+        X, y = self.inputs, self.outputs
+        N = len(y)
+        B = Theta.shape[0]
+        c = self.consts
+        nat = self.natural(Theta)
+        delta, det_m, jac, varying = self._host_terms(nat, X, y, want_grad)
+        nu = self._nu(nat)
+        thk = self._kernel_theta(nat)
+        res = self.ctx.gp_logp_grad(self.desc, self.KIND, delta, thk, nu=nu, want_grad=want_grad)
+        beta, logdet, st = res["beta"], res["logdet"], res["status"]
+        failed = (st & cabi.ST_POTRF_FAILED) != 0
+        if np.any(failed):      # CholeskyRobust.perform fallback L = 1e-10 * I (tensors.py:218-222)
+            d2 = np.sum(np.atleast_2d(delta) ** 2, axis=1)
+            d2 = np.broadcast_to(d2, (B,))
+            beta = np.where(failed, d2 / c.fallback ** 2, beta)
+            logdet = np.where(failed, N * math.log(c.fallback), logdet)
+        n = float(N)
+        with np.errstate(all="ignore"):
+            if self.KIND == cabi.KIND_GAUSS:                              # gaussian.py:218-232
+                ll = -0.5 * n * c.log_2pi + (-0.5 * beta) + (-logdet) + det_m
+            else:                                                         # studentT.py:126-137
+                r1 = -0.5 * (nu + n) * np.log1p(beta / (nu - 2.0))
+                r2 = np.where(nu >= 1e6, -n * 0.5 * c.log_2pi_student,
+                              gammaln((nu + n) * 0.5) - gammaln(nu * 0.5) - 0.5 * n * np.log((nu - 2.0) * c.pi))
+                ll = r1 + r2 + (-logdet) + det_m
+        # guards (gaussian.py:234-241): non-finite delta / det_m / L / lcho -> float32(-1e30)
+        bad = ((st & cabi.ST_NONFINITE_RESULT) != 0) | ~np.isfinite(det_m) | ~np.isfinite(beta) | ~np.isfinite(logdet)
+        ll = np.where(bad, c.guard, ll)
+        info = {"beta": beta, "logdet": logdet, "det_m": det_m, "status": st, "nu": nu}
+        self.executed["logp"] += B
+        if not want_grad:
+            return ll, None, info
+        self.executed["dlogp"] += B
+        g_nat = np.zeros((B, self.ndim))
+        dth, ddl = res["dtheta"], res["ddelta"]
+        for h, off, size, const in self._slots:
+            if h is not None:
+                g_nat[:, h.offset:h.offset + h.size] += dth[:, off:off + size]
+        for b in range(B):
+            jl, dinv, dld = jac[b if varying else 0]
+            gd = ddl[b]
+            for h, J in jl.items():                                       # d delta / d loc = -J
+                g_nat[b, h.offset:h.offset + h.size] += -(np.atleast_2d(J) @ gd)
+            for h, J in dinv.items():
+                g_nat[b, h.offset] += float(np.dot(J, gd)) + dld[h]
+        if self.KIND == cabi.KIND_STUDENT and isinstance(self.f_degree.degree, HyperVar):
+            with np.errstate(all="ignore"):
+                bn = beta / (nu - 2.0)
+                d_r1 = -0.5 * np.log1p(bn) + 0.5 * (nu + n) * bn / ((nu - 2.0) * (1.0 + bn))
+                d_r2 = np.where(nu >= 1e6, 0.0,
+                                0.5 * digamma((nu + n) * 0.5) - 0.5 * digamma(nu * 0.5) - 0.5 * n / (nu - 2.0))
+            g_nat[:, self.f_degree.degree.offset] += d_r1 + d_r2
+        g = np.where(self.positive_mask[None, :], g_nat * nat, g_nat)     # chain rule through exp
+        g[failed | bad] = 0.0
+        return ll, tt_to_num(g), info                                     # stochastic.py:308-309
+
+    # ---- public methods (stochastic.py:365-366 binds th_logp/th_dlogp/th_loglike) -----------------
+    def logp(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+             array=False):
+        theta = self._theta(params, array)
+        lp = float(self.logprior_batch(theta)[0])
+        if prior or not self.is_observed and inputs is None:
+            return lp
+        ll, _, _ = self._eval_batch(theta, inputs, outputs, want_grad=False)
+        return lp + float(ll[0])
+
+    def loglike(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+                array=False):
+        ll, _, _ = self._eval_batch(self._theta(params, array), inputs, outputs, want_grad=False)
+        return float(ll[0])
+
+    def dlogp(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+              array=False):
+        theta = self._theta(params, array)
+        if prior:
+            return np.zeros(self.ndim)
+        _, g, _ = self._eval_batch(theta, inputs, outputs, want_grad=True)
+        return g[0]
+
+    def logp_dlogp(self, theta):
+        ll, g, _ = self._eval_batch(theta, want_grad=True)
+        return float(self.logprior_batch(theta)[0] + ll[0]), g[0]
+
+    # batched entries replacing the per-theta loops of stochastic.py:515-564
+    def logp_batch(self, Theta, prior=False):
+        Theta = np.atleast_2d(Theta)
+        lp = self.logprior_batch(Theta)
+        if prior:
+            return lp
+        ll, _, _ = self._eval_batch(Theta, want_grad=False)
+        return lp + ll
+
+    def dlogp_batch(self, Theta):
+        _, g, _ = self._eval_batch(np.atleast_2d(Theta), want_grad=True)
+        return g
+
+    def logp_dlogp_batch(self, Theta):
+        Theta = np.atleast_2d(Theta)
+        ll, g, info = self._eval_batch(Theta, want_grad=True)
+        return self.logprior_batch(Theta) + ll, g, info
+
+    def logp_chain(self, chain, prior=False):
+        """stochastic.py:515-520, vectorised (the reference's own TODO)."""
+        return self.logp_batch(np.asarray(chain), prior=prior)
+
+    # ---- posterior --------------------------------------------------------------------------
+    def _posterior(self, theta, space, noise=False, cov=False, prior=False):
+        nat = self.natural(theta)
+        p = self._accessor(nat)
+        X, y = self.inputs, self.outputs
+        thk = self._kernel_theta(nat[None, :])[0]
+        loc_s = self.f_location(space, p)
+        out = {}
+        if prior:
+            if noise or not self.noisy:
+                K, _ = self.ctx.gram(self.desc, space, None, thk[None, :])
+            else:
+                K, _ = self.ctx.gram(self.desc_f, space, None,
+                                     self._kernel_theta(nat[None, :], self._slots_f, self.desc_f.n_theta))
+            K = K[0]
+            if noise:
+                m = np.min(np.diag(K))
+                if not m > 0.0:
+                    K = K + (self.consts.jitter - m) * np.eye(len(K))        # tt_to_cov, elliptical.py:70
+            out.update(location=loc_s, kernel_diag=np.maximum(np.diag(K), 0.0), kernel=K if cov else None)
+            return out, nat, p
+        with np.errstate(all="ignore"):
+            delta = tt_to_num(self.f_mapping.inv(y, p)) - self.f_location(X, p)   # elliptical.py:63,83
+        r = self.ctx.gp_posterior(self.desc, space, delta, thk, noise=noise, cov=cov)
+        out.update(location=loc_s + r["mean"], kernel_diag=r["var"], kernel=r["cov"], beta=r["beta"], status=r["status"])
+        self.executed["predict"] += 1
+        return out, nat, p
+
+    def _scaling(self, post, nat):
+        return 1.0
+
+    def _quantile_z(self, q, nat):
+        return stats.norm.ppf(q)                                            # gaussian.py:69-71
+
+    def predict(self, params=None, space=None, inputs=None, outputs=None, mean=True, std=True, var=False, cov=False,
+                median=False, quantiles=False, quantiles_noise=False, samples=0, distribution=False, prior=False,
+                noise=False, simulations=None, array=False):
+        """stochastic.py:444-513 (mean / variance / std / covariance / median / quantiles)."""
+        theta = self._theta(params, array)
+        if not self.is_observed:
+            prior = True
+        if inputs is not None or outputs is not None:
+            self.set_space(inputs=inputs, outputs=outputs)
+        if space is None:
+            space = self.space
+        space = np.asarray(space, dtype=np.float64)
+        if space.ndim < 2:
+            space = space.reshape(len(space), 1)
+        post, nat, p = self._posterior(theta, space, noise=noise, cov=cov, prior=prior)
+        mu, kd = post["location"], post["kernel_diag"]
+        sd = np.sqrt(kd)
+        T = lambda v: self.f_mapping(v, p)
+        scaling = 1.0 if prior else self._scaling(post, nat)
+        values = DictObj()
+        if self.WARPED:                                                      # gaussian.py:127-174
+            a, w = np.polynomial.hermite.hermgauss(10)
+            grille = mu[None, :] + sd[None, :] * np.sqrt(2.0) * a[:, None]
+            tg = T(grille.ravel()).reshape(grille.shape)
+            m1 = w.dot(tg) / np.sqrt(np.pi)
+            m2 = w.dot(tg ** 2) / np.sqrt(np.pi)
+            v_mean, v_var = m1, m2 - m1 ** 2
+        else:                                                                # elliptical.py:194-200, studentT.py:45-46
+            v_mean, v_var = T(mu), kd * scaling
+        if mean:
+            values["mean"] = v_mean
+        if var:
+            values["variance"] = v_var
+        if std:
+            values["std"] = np.sqrt(v_var)
+        if cov:
+            values["covariance"] = post["kernel"] * scaling
+        if median:
+            values["median"] = T(mu)                                         # elliptical.py:190-192
+        if quantiles:
+            z = self._quantile_z(0.975, nat) if not prior else self._quantile_z_prior(0.975, nat)
+            values["quantile_up"] = T(mu + z * sd)
+            values["quantile_down"] = T(mu - z * sd)
+        if quantiles_noise:
+            pn, _, _ = self._posterior(theta, space, noise=True, cov=False, prior=prior)
+            sdn = np.sqrt(pn["kernel_diag"])
+            z = self._quantile_z(0.975, nat) if not prior else self._quantile_z_prior(0.975, nat)
+            values["noise_std"] = sdn * math.sqrt(scaling)
+            values["noise_up"] = T(pn["location"] + z * sdn)
+            values["noise_down"] = T(pn["location"] - z * sdn)
+        if samples > 0:
+            values["samples"] = self.sampler(theta, space, samples=samples, prior=prior, noise=noise)
+        return values
+
+    def _quantile_z_prior(self, q, nat):
+        return self._quantile_z(q, nat)
+
+    def sampler(self, theta, space, samples=1, prior=False, noise=False, rng=None):
+        """gaussian.py:75-97: location + chol(posterior covariance) @ randn, mapped through T."""
+        rng = rng or np.random.default_rng()
+        post, nat, p = self._posterior(theta, space, noise=noise, cov=True, prior=prior)
+        L, info, _ = self.ctx.potrf_robust(post["kernel"])
+        if info < 0:
+            L = self.consts.fallback * np.eye(len(L))
+        z = rng.standard_normal((len(space), samples))
+        f = post["location"][:, None] + L.dot(z)
+        return np.array([self.f_mapping(k, p) for k in f.T]).T
+
+    # ---- MAP (stochastic.py:566-674; optimiser wrappers bayesian/selection.py:14-42) --------
+    def find_MAP(self, start=None, points=1, display=False, powell=False, bfgs=True, max_time=None, return_points=False,
+                 **kwargs):
+        import scipy.optimize as spo
+        if start is None:
+            start = self.params
+        x0 = self.dict_to_array(start) if isinstance(start, dict) else np.asarray(start, dtype=np.float64)
+
+        def f(x):
+            try:
+                v = -self.logp(x, array=True)
+                return 1e100 if np.isnan(v) else v                          # libs/__init__.py:61-62 nan_to_high
+            except Exception:
+                return 1e32
+
+        def df(x):
+            try:
+                return np.nan_to_num(-self.dlogp(x, array=True))
+            except Exception:
+                return np.full_like(x, 1e32)
+
+        pts = [("start", -f(x0), x0)]
+        x = x0
+        for i in range(max(points, 1)):
+            if bfgs:
+                x = spo.fmin_bfgs(f, x, fprime=df, disp=display, **kwargs)
+                pts.append(("bfgs", -f(x), x))
+            if powell:
+                x = spo.fmin_powell(f, x, disp=display)
+                pts.append(("powell", -f(x), x))
+        best = max(pts, key=lambda t: t[1])
+        params = self.array_to_dict(best[2])
+        if return_points:
+            return params, pts
+        return params
+
+
+class GaussianProcess(EllipticalProcess):
+    KIND = cabi.KIND_GAUSS
+
+    def __init__(self, *args, **kwargs):
+        kwargs.setdefault("name", "GP")
+        super().__init__(*args, **kwargs)
+
+
+class WarpedGaussianProcess(GaussianProcess):
+    WARPED = True
+
+    def __init__(self, *args, **kwargs):
+        kwargs.setdefault("name", "WGP")
+        super().__init__(*args, **kwargs)
+
+
+class StudentTProcess(EllipticalProcess):
+    KIND = cabi.KIND_STUDENT
+
+    def __init__(self, *args, **kwargs):
+        kwargs.setdefault("name", "TP")
+        if kwargs.get("degree") is None:
+            kwargs["degree"] = Freedom()                                    # studentT.py:21-22
+        super().__init__(*args, **kwargs)
+
+    def _scaling(self, post, nat):
+        # studentT.py:36-43: (nu + beta - 2) / (nu + N - 2)
+        nu = float(self._nu(nat[None, :])[0])
+        return (nu + post["beta"] - 2.0) / (nu + len(self.outputs) - 2.0)
+
+    def _quantile_z(self, q, nat):
+        nu = float(self._nu(nat[None, :])[0])
+        return stats.t.ppf(q, df=nu + len(self.outputs))                    # studentT.py:51-55 (posterior freedom)
+
+    def _quantile_z_prior(self, q, nat):
+        return stats.t.ppf(q, df=float(self._nu(nat[None, :])[0]))
+
+
+class WarpedStudentTProcess(StudentTProcess):
+    WARPED = True
+
+    def __init__(self, *args, **kwargs):
+        kwargs.setdefault("name", "WTP")
+        super().__init__(*args, **kwargs)
+
+
+GP = GaussianProcess
+WGP = WarpedGaussianProcess
+TP = StudentTProcess
+WTP = WarpedStudentTProcess
+
+
+def kernel_cov(kernel, x1, x2=None, hypers=None, device=0):
+    """Numeric `Kernel.cov(x1, x2)` (kernels.py:106-110) for a free-standing kernel expression.
+    `hypers`: {bare hyper name: natural value}, e.g. {"SE_var": 1.0, "SE_rate": [1, 2]}."""
+    x1 = np.asarray(x1, dtype=np.float64)
+    if x1.ndim < 2:
+        x1 = x1[:, None]
+    reg = Registry()
+    kernel.check_dims(x1)
+    if not getattr(kernel, "_standalone_reg", None):
+        kernel.check_hypers("", reg)
+        kernel._standalone_reg = reg
+    reg = kernel._standalone_reg
+    b = DescBuilder(x1.shape[1])
+    kernel.compile(b)
+    desc = b.finish()
+    th = np.ones(max(desc.n_theta, 1))
+    hypers = hypers or {}
+    for h, off, size, const in b.slots:
+        if h is None:
+            th[off:off + size] = const
+        elif h.name in hypers:
+            th[off:off + size] = np.asarray(hypers[h.name], dtype=np.float64).reshape(-1)
+    K, _ = get_context(device).gram(desc, x1, x2, th[None, :desc.n_theta] if desc.n_theta else th[None, :0])
+    return K[0]

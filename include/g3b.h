@@ -1,0 +1,184 @@
+/* g3b.h — C ABI of the B200-native exact-GP hot path (libg3b.so).
+ *
+ * Plain pointers and sizes only; no torch / numpy types.  All matrices that
+ * cross this boundary are row-major, C-contiguous float64 HOST arrays owned by
+ * the caller (NumPy / Theano `perform` storage); the library copies in/out and
+ * keeps its own device buffers per context.
+ *
+ * Each entry point names the reference (griosd/g3py) interface it replaces,
+ * path:line relative to the reference tree.
+ *
+ * Error convention: functions return 0 on success, <0 for a bad
+ * argument or a CUDA error (text via g3_last_error).  Numerical trouble is NEVER
+ * an error: it is reported per batch item in `status[]` / `info[]`, and the
+ * Python Op maps it to the reference's conventions (L = 1e-10*I, logp = -1e30).
+ */
+#ifndef G3B_H
+#define G3B_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct g3_ctx g3_ctx;
+
+/* ---- kernel expression tree ------------------------------------------------------------
+ * Post-order flattening of g3py's Kernel algebra:
+ *   leaves  KernelStationary subclasses   g3py/processes/hypers/kernels.py:96-110,360-472
+ *   nodes   KernelSum/Prod/Scale/Shift    g3py/processes/hypers/kernels.py:192-245
+ *   `dim0,dim1` = Hypers.dims column slice g3py/processes/hypers/__init__.py:55-83
+ * theta indices address the NATURAL-space (already exponentiated) hyper vector of one
+ * batch item, in pymc3 creation order (var, then metric hypers; SIN: var, freq[], rate[]).
+ */
+enum {
+  G3_K_SE = 1,    /* var*exp(-d),  d = sum_k 0.5*rate_k^2*(x_ik-x_jk)^2   kernels.py:434-436, metrics.py:100-102 */
+  G3_K_OU = 2,    /* var*exp(-d),  d = sum_k rate_k*|x_ik-x_jk|           kernels.py:429-431, metrics.py:89-91  */
+  G3_K_MAT32 = 3, /* var*(1+s)exp(-s), s = sqrt(3d)                        kernels.py:406-412 */
+  G3_K_MAT52 = 4, /* var*(1+s+5d/3)exp(-s), s = sqrt(5d)                   kernels.py:415-421 */
+  G3_K_RQ = 5,    /* var*(1+d/alpha)^-alpha                                kernels.py:388-403 */
+  G3_K_SIN = 6,   /* var*exp(+2*sum_k rate_k*sin^2(pi*(x_ik-x_jk)*freq_k)) kernels.py:470-472 */
+  G3_K_NOISE = 7, /* var*I when x1 is x2, zeros otherwise                  kernels.py:360-371 */
+  G3_K_WN = 8,    /* var*I when x1 is x2, var*#equal coords otherwise      kernels.py:374-385 */
+  G3_K_SUM = 16, G3_K_PROD = 17, G3_K_SCALE = 18, G3_K_SHIFT = 19
+};
+
+typedef struct {
+  int32_t op;
+  int32_t dim0, dim1;  /* [dim0, dim1) columns of X used by the metric */
+  int32_t var_idx;     /* theta index of `var`; -1 = use `value` (KernelProd fixes k2.var = 1.0, kernels.py:215-219) */
+  int32_t p0_idx;      /* theta index of rate[dim1-dim0] (SE/OU/MAT32/MAT52/RQ/SIN), else -1 */
+  int32_t p1_idx;      /* theta index of RQ alpha, or of SIN freq[dim1-dim0], else -1 */
+  int32_t flags;       /* G3_KF_PROCESS_NOISE on the KernelNoise leaf EllipticalProcess adds itself (elliptical.py:26-28) */
+  double value;        /* fixed var (var_idx < 0) or the constant of SCALE / SHIFT */
+} g3_knode;
+
+enum { G3_KF_PROCESS_NOISE = 1 };
+
+#define G3_MAX_NODES 16
+#define G3_MAX_THETA 32
+#define G3_MAX_DIM 16
+
+typedef struct {
+  int32_t n_nodes;
+  int32_t n_theta;     /* natural-space hypers per batch item consumed by this tree */
+  g3_knode nodes[G3_MAX_NODES];
+} g3_kernel_desc;
+
+/* ---- per-item status bits ------------------------------------------------------------- */
+enum {
+  G3_ST_NONFINITE_INPUT = 1,  /* NaN/inf scrubbed while building K (tt_to_num, libs/tensors.py:90-92) */
+  G3_ST_DIAG_SHIFT = 2,       /* min diag <= 0: tt_to_cov shift applied (libs/tensors.py:95-98) */
+  G3_ST_JITTER = 4,           /* jitter ladder used (libs/tensors.py:203-213); tries in bits 8..15 */
+  G3_ST_POTRF_FAILED = 8,     /* ladder exhausted -> caller applies the 1e-10*I fallback (libs/tensors.py:218-222) */
+  G3_ST_NONFINITE_RESULT = 16 /* NaN/inf in L, u or delta -> caller returns -1e30 (gaussian.py:234-241) */
+};
+
+enum { G3_KIND_GAUSS = 0, G3_KIND_STUDENT = 1 };
+
+/* flags for g3_gp_posterior */
+enum { G3_POST_NOISE = 1,   /* noise=True: K** gets the Noise variance (elliptical.py:70,86-88) */
+       G3_POST_COV = 2 };   /* also return the full M x M posterior covariance */
+
+/* ---- context --------------------------------------------------------------------------
+ * One context = one device + one stream + cached workspaces.  Created lazily per process
+ * (fork-safe: no CUDA state at library load).  Replaces nothing in the reference; it is
+ * where theano's `perform` keeps device state between calls (libs/tensors.py:215-222). */
+int g3_ctx_create(int device, g3_ctx** out);
+int g3_ctx_destroy(g3_ctx* ctx);
+const char* g3_last_error(g3_ctx* ctx);
+int g3_sync(g3_ctx* ctx);
+/* constants of the reference graph, supplied by the host so that "strict" (float32-rounded)
+ * and exact modes agree bit-for-bit with the oracle: jitter = float32(1e-6) (tensors.py:98,204). */
+int g3_set_jitter(g3_ctx* ctx, double jitter_rel, int max_tries);
+/* Blocking of the factorisation: tile columns (of 128) per right-looking outer block; a value
+ * >= N/128 makes it fully left-looking (default for the batched path). */
+int g3_set_potrf_block(g3_ctx* ctx, int w_outer);
+
+/* Device timing on the context's stream (CUDA events; used by bench.py). */
+int g3_timer_begin(g3_ctx* ctx);
+int g3_timer_end(g3_ctx* ctx, float* ms);
+/* Number of kernels launched by this context since creation (bench.py "gpu_launches"). */
+int64_t g3_launch_count(g3_ctx* ctx);
+
+/* ---- observations ---------------------------------------------------------------------
+ * Keeps the training inputs resident on the device across calls; replaces the per-call
+ * re-upload of th_inputs in makefn.__call__ (libs/tensors.py:60-69). */
+int g3_set_data(g3_ctx* ctx, const double* X, int N, int D);
+
+/* ---- Gram matrix ----------------------------------------------------------------------
+ * Kernel.cov(x1, x2) for B hyper samples (kernels.py:106-110,225-241; metrics.py:11-13),
+ * with tt_to_num scrubbing (tensors.py:90-92).  X2 == NULL means cov(x1) (x1 is x2: Noise/WN
+ * contribute var*I).  K_out: B x n1 x n2.  status may be NULL. */
+int g3_gram(g3_ctx* ctx, const g3_kernel_desc* desc, const double* X1, int n1,
+            const double* X2_or_NULL, int n2, int D, const double* theta, int B,
+            double* K_out, int* status);
+
+/* dtheta[b][p] = sum_ij W[b][i][j] * dK[b][i][j]/dtheta_p — the contraction Theano's reverse
+ * mode performs through Kernel.cov (gradient(), tensors.py:11-22); dK/dtheta never stored. */
+int g3_gram_vjp(g3_ctx* ctx, const g3_kernel_desc* desc, const double* X1, int n1,
+                const double* X2_or_NULL, int n2, int D, const double* theta, int B,
+                const double* W, double* dtheta);
+
+/* ---- robust Cholesky ------------------------------------------------------------------
+ * CholeskyRobust.perform / _cholesky (libs/tensors.py:197-222): lower Cholesky of B
+ * matrices (row-major, n x n, leading dimension lda), in place on the host array; upper
+ * triangle zeroed.  On failure of item b the jitter ladder is run on the device copy:
+ * dK = mean(diag)*jitter_rel, x10 per try, max_tries.  info[b]: 0 ok, k>0 succeeded at
+ * ladder try k, -1 exhausted (A[b] left untouched; caller applies 1e-10*I).
+ * jitter[b] (may be NULL) = the dK finally added. */
+int g3_potrf_robust(g3_ctx* ctx, double* A, int n, int lda, int B, int* info, double* jitter);
+
+/* ---- fused marginal likelihood + gradient ---------------------------------------------
+ * WarpedGaussianDistribution.logp_cho / WarpedStudentTDistribution.logp_cho core
+ * (gaussian.py:208-224, studentT.py:116-129) and its gradient (which the reference obtains
+ * by tt.grad through CholeskyRobust.grad, tensors.py:224-260), for B hyper samples on the
+ * data given to g3_set_data:
+ *   K_b  = tt_to_cov(cov(X; theta_b))            elliptical.py:71
+ *   L_b  = cholesky_robust(K_b)                  tensors.py:197-222
+ *   u_b  = L_b^-1 delta_b, beta_b = u'u, logdet_b = sum log diag L_b
+ *   alpha_b = K_b^-1 delta_b
+ *   dtheta[b][p] = 1/2 sum_ij (c_b alpha alpha' - K^-1)_ij dK_ij/dtheta_p      (natural space)
+ *   ddelta[b]    = -c_b alpha_b
+ *   c_b = 1 (gauss) or (nu_b + N)/(nu_b - 2 + beta_b) (student; d r1/d beta, studentT.py:126)
+ * delta: B x N (delta_stride = N) or one shared vector (delta_stride = 0).
+ * dtheta / ddelta may be NULL (logp only: no inverse is formed).  status: B ints. */
+int g3_gp_logp_grad(g3_ctx* ctx, const g3_kernel_desc* desc, int kind,
+                    const double* delta, int delta_stride, const double* theta, int B,
+                    const double* nu_or_NULL, double* beta, double* logdet,
+                    double* dtheta_or_NULL, double* ddelta_or_NULL, int* status);
+
+/* Split form of the same call for benchmarking with inputs resident in HBM:
+ * upload copies theta/delta/nu host->device, run launches the device pipeline only,
+ * download copies the results device->host. */
+int g3_gp_upload(g3_ctx* ctx, const g3_kernel_desc* desc, int kind, const double* delta,
+                 int delta_stride, const double* theta, int B, const double* nu_or_NULL, int want_grad);
+int g3_gp_run(g3_ctx* ctx);
+int g3_gp_download(g3_ctx* ctx, double* beta, double* logdet, double* dtheta_or_NULL,
+                   double* ddelta_or_NULL, int* status);
+
+/* ---- posterior moments ----------------------------------------------------------------
+ * EllipticalProcess.th_define_process posterior block (elliptical.py:78-107) for ONE theta:
+ *   mean_out = K* K^-1 delta                (caller adds m(X*), elliptical.py:81-84)
+ *   var_out  = max(diag(K** - K* K^-1 K*'), 0)                    elliptical.py:86-97
+ *   cov_out  = K** - K* K^-1 K*'  (M x M, only with G3_POST_COV)
+ * K* uses the cross form of `desc` (Noise contributes 0, kernels.py:367-371); K** gets the
+ * Noise variance only with G3_POST_NOISE.  beta_out (may be NULL) = delta' K^-1 delta, which
+ * StudentTProcess.th_scaling needs (studentT.py:36-43). */
+int g3_gp_posterior(g3_ctx* ctx, const g3_kernel_desc* desc, const double* Xs, int M,
+                    const double* delta, const double* theta, int flags,
+                    double* mean_out, double* var_out, double* cov_out_or_NULL,
+                    double* beta_out_or_NULL, int* status);
+
+/* ---- stand-alone Cholesky benchmark entry (BASELINE metric 2) --------------------------
+ * Builds K = cov(X; theta) (+ tt_to_cov) for the resident data directly in device memory
+ * (lower triangle only) and factors it in place; nothing N x N crosses the host boundary.
+ * Returns logdet and info; ms (may be NULL) = device time of the factorisation alone. */
+int g3_gram_potrf_device(g3_ctx* ctx, const g3_kernel_desc* desc, const double* theta,
+                         double* logdet, int* info, float* ms_gram, float* ms_potrf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G3B_H */

@@ -1,0 +1,797 @@
+"""NumPy/SciPy fp64 restatement of g3py's exact-GP hot path (TEST INFRASTRUCTURE).
+
+Every function cites the reference file:line (relative to /root/reference) it
+follows.  The reference builds Theano expressions; here the same arithmetic is
+executed eagerly with NumPy, in the same order of operations where that matters
+(N1 x N2 x D broadcast metric, tt_to_cov, dpotrf + jitter ladder, triangular
+solve, guard scans, Murray reverse-mode Cholesky gradient).
+
+A model is described by a neutral nested-dict *spec* (see `build_process`), so
+that tests can hand the identical description to the oracle and to the CUDA
+front-end without either importing the other.
+
+Constants mode (`strict=True`, default): the float32-rounded literals that stay
+in the reference graph when it is run with floatX='float64' are reproduced
+(gaussian.py:218, studentT.py:122-128, tensors.py:98,204).  `strict=False` uses
+exact doubles.
+"""
+import math
+
+import numpy as np
+import scipy.linalg as sla
+from scipy.special import gammaln, digamma
+
+__all__ = [
+    "tt_to_num", "tt_to_cov", "cholesky_robust", "murray_cholesky_grad",
+    "Consts", "build_kernel", "build_process", "OracleProcess",
+    "c2_inputs", "c1_inputs", "c3_inputs", "c4_inputs", "c5_inputs",
+]
+
+f32 = np.float32
+
+
+# --------------------------------------------------------------------------- constants
+class Consts:
+    """Scalar constants of the reference graph (strict) or exact doubles."""
+
+    def __init__(self, strict=True):
+        self.strict = strict
+        if strict:
+            # gaussian.py:218  tt.log(np.float32(2.0*np.pi)) -> float32 log of a float32 constant
+            self.log_2pi = float(np.log(f32(2.0 * np.pi)))
+            # studentT.py:122-124
+            self.pi = float(f32(np.pi))
+            # studentT.py:127  np.log(np2 * npi) is a NumPy float32 expression
+            self.log_2pi_student = float(np.log(f32(2.0) * f32(np.pi)))
+            # tensors.py:98 and :204
+            self.jitter = float(f32(1e-6))
+            # gaussian.py:238-241 / studentT.py:143-146
+            self.guard = float(f32(-1e30))
+            # tensors.py:221
+            self.fallback = float(f32(1e-10))
+        else:
+            self.log_2pi = math.log(2.0 * math.pi)
+            self.pi = math.pi
+            self.log_2pi_student = math.log(2.0 * math.pi)
+            self.jitter = 1e-6
+            self.guard = -1e30
+            self.fallback = 1e-10
+
+
+# --------------------------------------------------------------------------- tensors.py
+def tt_to_num(r, nan=0.0, inf=1e10):
+    """libs/tensors.py:90-92 — NaN -> 0, +inf AND -inf -> +1e10 (sign lost)."""
+    r = np.asarray(r, dtype=np.float64)
+    return np.where(np.isnan(r), nan, np.where(np.isinf(r), inf, r))
+
+
+def tt_to_cov(c, consts=None):
+    """libs/tensors.py:95-98 — scrub, then shift the diagonal if its minimum is <= 0."""
+    consts = consts or Consts()
+    r = tt_to_num(c)
+    m = np.min(np.diag(r))
+    if m > 0.0:
+        return r
+    return r + (consts.jitter - m) * np.eye(c.shape[0])
+
+
+def cholesky_robust(K, consts=None, maxtries=20, return_info=False):
+    """libs/tensors.py:197-222 — dpotrf, then the jitter ladder, then the 1e-10*I fallback.
+
+    info: 0 = plain success, k>0 = succeeded at ladder try k (1-based), -1 = fallback.
+    """
+    consts = consts or Consts()
+    K = np.asarray(K, dtype=np.float64)
+    L, info = sla.lapack.dpotrf(K, lower=1)
+    if info == 0:
+        L = np.tril(L)
+        return (L, 0) if return_info else L
+    diagK = np.diag(K)
+    n = K.shape[0]
+    dK = np.eye(n) * diagK.mean() * consts.jitter                      # :204
+    if np.any(diagK <= 0.0):                                            # :205-206
+        K = K + np.eye(n) * (diagK.mean() * consts.jitter - diagK.min())
+    for tries in range(maxtries):                                       # :208-212
+        try:
+            L = np.nan_to_num(sla.cholesky(K + dK, lower=True))
+            return (L, tries + 1) if return_info else L
+        except Exception:
+            dK = dK * 10.0
+    L = 0 * K + consts.fallback * np.eye(n)                             # :221
+    return (L, -1) if return_info else L
+
+
+def murray_cholesky_grad(L, Lbar):
+    """libs/tensors.py:224-260 — reverse-mode of L = chol(K) (Murray 2016, level-3 form).
+
+    Returns the lower-triangular Kbar the reference returns:
+    tril(S + S^T) - diag(diag(S)),  S = L^-T tril_half(L^T Lbar) L^-1.
+    """
+    def tril_and_halve_diagonal(m):
+        return np.tril(m) - np.diag(np.diagonal(m) / 2.0)
+
+    def conjugate_solve_triangular(outer, inner):
+        # L^-T P L^-1 via two upper-triangular solves with outer.T (:245-248)
+        a = sla.solve_triangular(outer.T, tt_to_num(inner).T, lower=False)
+        return sla.solve_triangular(outer.T, a.T, lower=False)
+
+    s = conjugate_solve_triangular(L, tril_and_halve_diagonal(tt_to_num(L.T.dot(Lbar))))
+    return np.tril(s + s.T) - np.diag(np.diagonal(s))
+
+
+# --------------------------------------------------------------------------- metrics.py
+def _gram_broadcast(x1, x2, dims):
+    """hypers/metrics.py:11-13 — (N1,1,D) - (1,N2,D): the materialised difference tensor."""
+    a = x1[:, dims[0]:dims[1]][:, None, :]
+    b = x2[:, dims[0]:dims[1]][None, :, :]
+    return a - b
+
+
+def ard_l2(x1, x2, dims, rate):
+    """hypers/metrics.py:100-102 — dot((x1-x2)**2, 0.5*rate**2)."""
+    return np.dot(_gram_broadcast(x1, x2, dims) ** 2, 0.5 * rate ** 2)
+
+
+def ard_l1(x1, x2, dims, rate):
+    """hypers/metrics.py:89-91 — dot(abs(x1-x2), rate)."""
+    return np.dot(np.abs(_gram_broadcast(x1, x2, dims)), rate)
+
+
+def delta_gram(x1, x2, dims):
+    """hypers/metrics.py:30-35 — number of equal coordinates (0..D)."""
+    return tt_to_num((_gram_broadcast(x1, x2, dims) == 0.0).sum(axis=2).astype(np.float64))
+
+
+# --------------------------------------------------------------------------- kernels.py
+class _Hyper:
+    def __init__(self, name, size, positive):
+        self.name, self.size, self.positive = name, int(size), bool(positive)
+
+
+class KernelNode:
+    """Base: `hypers` in pymc3 creation order; cov()/dcov() take the natural-space values."""
+    hypers = ()
+
+    def layout(self):
+        return list(self.hypers)
+
+    def n_theta(self):
+        return sum(h.size for h in self.layout())
+
+
+class _Leaf(KernelNode):
+    def __init__(self, spec, D):
+        self.kind = spec["type"]
+        self.name = spec.get("name", self.kind)
+        dims = spec.get("dims")
+        self.dims = (0, D) if dims is None else (int(dims[0]), int(dims[1]))
+        self.nd = self.dims[1] - self.dims[0]
+        self.fixed_var = spec.get("var")                      # KernelProd second var = 1.0 (kernels.py:215-219)
+        hy = []
+        if self.fixed_var is None:
+            hy.append(_Hyper(self.name + "_var", 1, True))     # kernels.py:22-24
+        k = self.kind
+        if k in ("SE", "MAT32", "MAT52", "RQ", "OU"):
+            hy.append(_Hyper(self.name + "_rate", self.nd, True))  # metrics.py:79-83
+        if k == "RQ":
+            hy.append(_Hyper(self.name + "_alpha", 1, True))   # kernels.py:394-397
+        if k == "SIN":                                         # kernels.py:446-454: freq created before rate
+            hy.append(_Hyper(self.name + "_freq", self.nd, True))
+            hy.append(_Hyper(self.name + "_rate", self.nd, True))
+        self.hypers = tuple(hy)
+
+    def _split(self, th):
+        i = 0
+        out = {}
+        if self.fixed_var is None:
+            out["var"] = th[0]
+            i = 1
+        else:
+            out["var"] = float(self.fixed_var)
+        for h in self.hypers:
+            key = h.name[len(self.name) + 1:]
+            if key == "var":
+                continue
+            out[key] = th[i:i + h.size] if h.size > 1 or key in ("rate", "freq") else th[i]
+            i += h.size
+        return out
+
+    # value of k(d) and the pieces the gradient needs -------------------------------------
+    def cov(self, th, x1, x2, same):
+        p = self._split(th)
+        k = self.kind
+        n1, n2 = x1.shape[0], x2.shape[0]
+        if k == "Noise":                                       # kernels.py:367-371
+            return p["var"] * np.eye(n1) if same else np.zeros((n1, n2))
+        if k == "WN":                                          # kernels.py:381-385
+            return p["var"] * np.eye(n1) if same else p["var"] * delta_gram(x1, x2, self.dims)
+        if k == "SE":                                          # kernels.py:424-436 exp(-d), ARD_L2
+            return p["var"] * np.exp(-ard_l2(x1, x2, self.dims, p["rate"]))
+        if k == "OU":                                          # kernels.py:429-431 exp(-d), ARD_L1
+            return p["var"] * np.exp(-ard_l1(x1, x2, self.dims, p["rate"]))
+        if k == "MAT32":                                       # kernels.py:406-412
+            d3 = np.sqrt(3 * ard_l2(x1, x2, self.dims, p["rate"]))
+            return p["var"] * ((1 + d3) * np.exp(-d3))
+        if k == "MAT52":                                       # kernels.py:415-421
+            d = ard_l2(x1, x2, self.dims, p["rate"])
+            d5 = np.sqrt(5 * d)
+            return p["var"] * ((1 + d5 + 5 * d / 3) * np.exp(-d5))
+        if k == "RQ":                                          # kernels.py:388-403
+            d = ard_l2(x1, x2, self.dims, p["rate"])
+            return p["var"] * np.power(1 + d / p["alpha"], -p["alpha"])
+        if k == "SIN":                                         # kernels.py:470-472 (positive exponent, as written)
+            diff = _gram_broadcast(x1, x2, self.dims)
+            return p["var"] * np.exp(2 * np.dot(np.sin(np.pi * diff * p["freq"]) ** 2, p["rate"]))
+        raise ValueError(k)
+
+    def dcov(self, th, x1, x2, same, nan_quirk=False):
+        """List of dK/dtheta_p (natural space), one N1xN2 array per scalar hyper, layout order.
+
+        Analytic limits are used at d = 0 for the sqrt-kernels.  With
+        `nan_quirk=True` the reference's behaviour is emulated instead: Theano's grad(sqrt) gives
+        NaN where d == 0, `tt_to_num` (stochastic.py:309) turns the *whole* rate-gradient
+        component NaN -> 0.
+        """
+        p = self._split(th)
+        k = self.kind
+        out = []
+        K = self.cov(th, x1, x2, same)
+        if self.fixed_var is None:
+            out.append(K / p["var"])
+        if k in ("Noise", "WN"):
+            return out
+        diff = _gram_broadcast(x1, x2, self.dims)
+        if k in ("SE", "MAT32", "MAT52", "RQ"):
+            r = p["rate"]
+            d = np.dot(diff ** 2, 0.5 * r ** 2)
+            if k == "SE":
+                dkdd = -np.exp(-d)
+            elif k == "MAT32":
+                dkdd = -1.5 * np.exp(-np.sqrt(3 * d))
+            elif k == "MAT52":
+                s = np.sqrt(5 * d)
+                dkdd = -(5.0 / 6.0) * (1 + s) * np.exp(-s)
+            else:
+                a = p["alpha"]
+                dkdd = -np.power(1 + d / a, -a - 1)
+            for j in range(self.nd):
+                g = p["var"] * dkdd * (r[j] * diff[:, :, j] ** 2)
+                if nan_quirk and k in ("MAT32", "MAT52") and np.any(d == 0.0):
+                    g = np.full_like(g, np.nan)
+                out.append(g)
+            if k == "RQ":
+                a = p["alpha"]
+                out.append(K * (-np.log1p(d / a) + d / (a + d)))
+            return out
+        if k == "OU":
+            r = p["rate"]
+            for j in range(self.nd):
+                out.append(-K * np.abs(diff[:, :, j]))
+            return out
+        if k == "SIN":
+            fr, r = p["freq"], p["rate"]
+            for j in range(self.nd):                          # freq first (creation order)
+                out.append(K * 2 * r[j] * np.sin(2 * np.pi * diff[:, :, j] * fr[j]) * np.pi * diff[:, :, j])
+            for j in range(self.nd):
+                out.append(K * 2 * np.sin(np.pi * diff[:, :, j] * fr[j]) ** 2)
+            return out
+        raise ValueError(k)
+
+
+class _Binary(KernelNode):
+    """KernelSum / KernelProd (kernels.py:213-245)."""
+
+    def __init__(self, op, k1, k2):
+        self.op, self.k1, self.k2 = op, k1, k2
+
+    def layout(self):
+        return self.k1.layout() + self.k2.layout()
+
+    def cov(self, th, x1, x2, same):
+        n1 = self.k1.n_theta()
+        a = self.k1.cov(th[:n1], x1, x2, same)
+        b = self.k2.cov(th[n1:], x1, x2, same)
+        return a + b if self.op == "sum" else a * b
+
+    def dcov(self, th, x1, x2, same, nan_quirk=False):
+        n1 = self.k1.n_theta()
+        da = self.k1.dcov(th[:n1], x1, x2, same, nan_quirk)
+        db = self.k2.dcov(th[n1:], x1, x2, same, nan_quirk)
+        if self.op == "sum":
+            return da + db
+        a = self.k1.cov(th[:n1], x1, x2, same)
+        b = self.k2.cov(th[n1:], x1, x2, same)
+        return [g * b for g in da] + [a * g for g in db]
+
+
+class _Unary(KernelNode):
+    """KernelScale / KernelShift with a constant element (kernels.py:192-210)."""
+
+    def __init__(self, op, c, k):
+        self.op, self.c, self.k = op, float(c), k
+
+    def layout(self):
+        return self.k.layout()
+
+    def cov(self, th, x1, x2, same):
+        a = self.k.cov(th, x1, x2, same)
+        return self.c * a if self.op == "scale" else self.c + a
+
+    def dcov(self, th, x1, x2, same, nan_quirk=False):
+        d = self.k.dcov(th, x1, x2, same, nan_quirk)
+        return [self.c * g for g in d] if self.op == "scale" else d
+
+
+def build_kernel(spec, D):
+    t = spec["type"]
+    if t in ("sum", "prod"):
+        k2s = dict(spec["k2"])
+        leaf = lambda sp: sp["type"] not in ("sum", "prod", "scale", "shift")
+        # kernels.py:215-219: a product of two leaf kernels that both have var=None fixes k2.var = 1.0
+        if t == "prod" and leaf(spec["k1"]) and leaf(k2s) and spec["k1"].get("var") is None and k2s.get("var") is None:
+            k2s["var"] = 1.0
+        return _Binary(t, build_kernel(spec["k1"], D), build_kernel(k2s, D))
+    if t in ("scale", "shift"):
+        return _Unary(t, spec["c"], build_kernel(spec["k"], D))
+    return _Leaf(spec, D)
+
+
+# --------------------------------------------------------------------------- means.py
+class _Mean:
+    def __init__(self, spec, D):
+        self.kind = spec["type"]
+        self.name = spec.get("name", self.kind)
+        dims = spec.get("dims")
+        self.dims = (0, D) if dims is None else tuple(dims)
+        nd = self.dims[1] - self.dims[0]
+        if self.kind == "Zero":
+            self.hypers = ()
+        elif self.kind == "Bias":                              # means.py:127-131
+            self.hypers = (_Hyper(self.name + "_Bias", 1, False),)
+        elif self.kind == "Linear":                            # means.py:147-152
+            self.hypers = (_Hyper(self.name + "_Constant", 1, False), _Hyper(self.name + "_Coeff", nd, False))
+        else:
+            raise ValueError(self.kind)
+
+    def layout(self):
+        return list(self.hypers)
+
+    def n_theta(self):
+        return sum(h.size for h in self.hypers)
+
+    def __call__(self, th, x):
+        n = x.shape[0]
+        if self.kind == "Zero":                                # means.py:117-119
+            return np.zeros(n)
+        if self.kind == "Bias":                                # means.py:136-137
+            return th[0] * np.ones(n)
+        xs = x[:, self.dims[0]:self.dims[1]]
+        return th[0] + xs.dot(th[1:])                          # means.py:158-159
+
+    def jac(self, th, x):
+        """d mean / d theta: (P_mean, n)."""
+        n = x.shape[0]
+        if self.kind == "Zero":
+            return np.zeros((0, n))
+        if self.kind == "Bias":
+            return np.ones((1, n))
+        xs = x[:, self.dims[0]:self.dims[1]]
+        return np.vstack([np.ones((1, n)), xs.T])
+
+
+# --------------------------------------------------------------------------- mappings.py
+class _Mapping:
+    """Closed-form warpings: inv(y), logdet_dinv(y), forward T(z) and their hyper-derivatives."""
+
+    def __init__(self, spec):
+        self.kind = spec["type"]
+        self.name = spec.get("name", "BoxShift" if self.kind == "BoxCoxShifted" else self.kind)
+        H = lambda s, pos: _Hyper(self.name + "_" + s, 1, pos)
+        self.hypers = {
+            "Identity": (),
+            "LinearMapping": (H("shift", False), H("scale", True)),        # mappings.py:107-112
+            "LogShifted": (H("shift", False),),                            # mappings.py:134-137
+            "BoxCoxShifted": (H("shift", False), H("power", True)),        # mappings.py:158-163
+            "BoxCoxLinear": (H("shift", False), H("scale", True), H("power", True)),  # :190-197
+            "ArcsinhLinear": (H("shift", False), H("scale", True)),        # mappings.py:315-320
+            "SinhArcsinh": (H("shift", False), H("scale", True)),          # mappings.py:340-345
+        }[self.kind]
+
+    def layout(self):
+        return list(self.hypers)
+
+    def n_theta(self):
+        return len(self.hypers)
+
+    def inv(self, th, y):
+        k = self.kind
+        if k == "Identity":
+            return y                                           # mappings.py:95-96
+        if k == "LinearMapping":
+            return y / th[1] + th[0]                           # :121-122
+        if k == "LogShifted":
+            return np.log(np.maximum(y - th[0], float(f32(1e-32))))   # :145-146
+        if k == "BoxCoxShifted":                               # :173-175
+            sh = y + th[0]
+            if th[1] < 1e-5:
+                return np.log(sh)
+            return (np.sign(sh) * np.abs(sh) ** th[1] - 1.0) / th[1]
+        if k == "BoxCoxLinear":                                # :209-211
+            sh = th[1] * (y + th[0])
+            if th[2] < float(f32(1e-5)):
+                return np.log(sh)
+            return (np.sign(sh) * np.abs(sh) ** th[2] - 1.0) / th[2]
+        if k == "ArcsinhLinear":
+            return np.arcsinh(y) * th[1] + th[0]               # :329-330
+        if k == "SinhArcsinh":
+            return np.sinh(th[0] + th[1] * np.arcsinh(y))      # :354-355
+        raise ValueError(k)
+
+    def logdet_dinv(self, th, y):
+        k = self.kind
+        n = float(y.shape[0])
+        if k == "Identity":
+            return 0.0                                         # :98-99
+        if k == "LinearMapping":
+            return -n * np.log(th[1])                          # :124-125
+        if k == "LogShifted":
+            return -np.sum(np.log(y - th[0]))                  # :148-149
+        if k == "BoxCoxShifted":
+            return (th[1] - 1.0) * np.sum(np.log(np.abs(y + th[0])))   # :177-179
+        if k == "BoxCoxLinear":                                # :213-215
+            return (th[2] - 1.0) * np.sum(np.log(np.abs(th[1] * (y + th[0])))) + n * np.log(th[1])
+        if k == "ArcsinhLinear":
+            return n * np.log(th[1]) - 0.5 * np.sum(np.log1p(y ** 2))  # :332-333
+        if k == "SinhArcsinh":                                 # :357-358
+            return (np.sum(np.log(np.cosh(th[0] + th[1] * np.arcsinh(y)))) + n * np.log(th[1])
+                    - 0.5 * np.sum(np.log1p(y ** 2)))
+        raise ValueError(k)
+
+    def forward(self, th, z):
+        k = self.kind
+        if k == "Identity":
+            return z
+        if k == "LinearMapping":
+            return th[1] * (z - th[0])                         # :118-119
+        if k == "LogShifted":
+            return np.exp(z) + th[0]                           # :142-143
+        if k == "BoxCoxShifted":                               # :168-171
+            sc = th[1] * z + 1.0
+            return np.sign(sc) * np.abs(sc) ** (1.0 / th[1]) - th[0]
+        if k == "BoxCoxLinear":                                # :204-207
+            sc = th[2] * z + 1.0
+            return np.sign(sc) * np.abs(sc) ** (1.0 / th[2]) / th[1] - th[0]
+        if k == "ArcsinhLinear":
+            return np.sinh((z - th[0]) / th[1])                # :326-327
+        if k == "SinhArcsinh":
+            return np.sinh((np.arcsinh(z) - th[0]) / th[1])    # :351-352
+        raise ValueError(k)
+
+    def grads(self, th, y):
+        """Analytic (d inv / d theta [P_map, n], d logdet / d theta [P_map]) of the closed forms above."""
+        k = self.kind
+        n = float(y.shape[0])
+        one = np.ones_like(y)
+        if k == "Identity":
+            return np.zeros((0, y.shape[0])), np.zeros(0)
+        if k == "LinearMapping":
+            return np.vstack([one, -y / th[1] ** 2]), np.array([0.0, -n / th[1]])
+        if k == "LogShifted":
+            live = (y - th[0]) > float(f32(1e-32))
+            return np.vstack([np.where(live, -1.0 / (y - th[0]), 0.0)]), np.array([np.sum(1.0 / (y - th[0]))])
+        if k in ("BoxCoxShifted", "BoxCoxLinear"):
+            if k == "BoxCoxShifted":
+                shift, scale, p = th[0], 1.0, th[1]
+            else:
+                shift, scale, p = th[0], th[1], th[2]
+            sh = scale * (y + shift)
+            a = np.abs(sh)
+            sp = np.sign(sh) * a ** p
+            d_shift = a ** (p - 1.0) * scale
+            d_scale = a ** (p - 1.0) * (y + shift)
+            d_p = (sp * np.log(a) * p - (sp - 1.0)) / p ** 2
+            ld_shift = (p - 1.0) * np.sum(1.0 / (y + shift))
+            ld_p = np.sum(np.log(a))
+            if k == "BoxCoxShifted":
+                return np.vstack([d_shift, d_p]), np.array([ld_shift, ld_p])
+            return np.vstack([d_shift, d_scale, d_p]), np.array([ld_shift, p * n / scale, ld_p])
+        if k == "ArcsinhLinear":
+            return np.vstack([one, np.arcsinh(y)]), np.array([0.0, n / th[1]])
+        if k == "SinhArcsinh":
+            w = th[0] + th[1] * np.arcsinh(y)
+            return (np.vstack([np.cosh(w), np.cosh(w) * np.arcsinh(y)]),
+                    np.array([np.sum(np.tanh(w)), np.sum(np.tanh(w) * np.arcsinh(y)) + n / th[1]]))
+        raise ValueError(k)
+
+    def grads_fd(self, th, y):
+        """4th-order central differences of inv / logdet_dinv (used by tests to check `grads`)."""
+        P = len(self.hypers)
+        dinv = np.zeros((P, y.shape[0]))
+        dld = np.zeros(P)
+        for i in range(P):
+            h = 1e-4 * max(1.0, abs(th[i]))
+            def at(s):
+                t = np.array(th, dtype=np.float64)
+                t[i] += s * h
+                return self.inv(t, y), self.logdet_dinv(t, y)
+            (a2, b2), (a1, b1), (c1, d1), (c2, d2) = at(2), at(1), at(-1), at(-2)
+            dinv[i] = (-a2 + 8 * a1 - 8 * c1 + c2) / (12 * h)
+            dld[i] = (-b2 + 8 * b1 - 8 * d1 + d2) / (12 * h)
+        return dinv, dld
+
+
+# --------------------------------------------------------------------------- processes
+def build_process(spec, D):
+    return OracleProcess(spec, D)
+
+
+class OracleProcess:
+    """EllipticalProcess + Gaussian / Student-t distribution (elliptical.py, gaussian.py, studentT.py).
+
+    spec = {"kind": "gauss"|"student", "name": "GP", "location": {...}, "kernel": {...},
+            "mapping": {...}, "noisy": True}
+    theta (flat, pymc3 bijection order = creation order, elliptical.py:35-52):
+      [location..., kernel (+ Noise var)..., mapping..., degree]; positive hypers stored as logs
+      (hypers/__init__.py:124-126,190-202: FlatExp = Flat prior + log transform, zero Jacobian,
+      -inf when exp(theta) <= 1e-6).
+    """
+
+    def __init__(self, spec, D, strict=True):
+        self.spec = spec
+        self.kind = spec.get("kind", "gauss")
+        self.D = D
+        self.consts = Consts(strict)
+        self.location = _Mean(spec.get("location", {"type": "Zero"}), D)
+        self.f_kernel = build_kernel(spec["kernel"], D)
+        self.noisy = spec.get("noisy", True)
+        if self.noisy:                                         # elliptical.py:26-28
+            self.k_noise = _Binary("sum", self.f_kernel, _Leaf({"type": "Noise", "name": "Noise"}, D))
+        else:
+            self.k_noise = self.f_kernel
+        self.mapping = _Mapping(spec.get("mapping", {"type": "Identity"}))
+        lay = self.location.layout() + self.k_noise.layout() + self.mapping.layout()
+        if self.kind == "student":                             # hypers/__init__.py:151-155
+            lay = lay + [_Hyper("Freedom_degree", 1, True)]
+        self._layout = lay
+        self.n_loc = self.location.n_theta()
+        self.n_ker = self.k_noise.n_theta()
+        self.n_map = self.mapping.n_theta()
+        self.P = sum(h.size for h in lay)
+
+    # ---- theta handling ------------------------------------------------------------------
+    def layout(self):
+        """[(name, size, positive)] in theta order."""
+        return [(h.name, h.size, h.positive) for h in self._layout]
+
+    def positive_mask(self):
+        return np.concatenate([np.full(h.size, h.positive) for h in self._layout]) if self._layout else np.zeros(0, bool)
+
+    def natural(self, theta):
+        theta = np.asarray(theta, dtype=np.float64)
+        m = self.positive_mask()
+        return np.where(m, np.exp(np.where(m, theta, 0.0)), theta)
+
+    def split(self, nat):
+        a = self.n_loc
+        b = a + self.n_ker
+        c = b + self.n_map
+        return nat[:a], nat[a:b], nat[b:c], nat[c:]
+
+    def logprior(self, theta):
+        """Sum of free-RV logp: Flat (0) + NonTransformLog.jacobian_det (hypers/__init__.py:200-201)."""
+        nat = self.natural(theta)
+        m = self.positive_mask()
+        return 0.0 if np.all(nat[m] > 1e-6) else -np.inf
+
+    # ---- pieces --------------------------------------------------------------------------
+    def cov_inputs(self, nat_k, X):
+        """prior_kernel_inputs = tt_to_cov(f_kernel_noise.cov(inputs)) (elliptical.py:71)."""
+        return tt_to_cov(self.k_noise.cov(nat_k, X, X, True), self.consts)
+
+    def _core(self, theta, X, y):
+        nat = self.natural(theta)
+        t_loc, t_ker, t_map, t_deg = self.split(nat)
+        K = self.cov_inputs(t_ker, X)
+        L, info = cholesky_robust(K, self.consts, return_info=True)
+        z = tt_to_num(self.mapping.inv(t_map, y))               # elliptical.py:63 (mapping_outputs)
+        delta = self.mapping.inv(t_map, y) - self.location(t_loc, X)   # gaussian.py:208 (raw inv in logp_cho)
+        det_m = self.mapping.logdet_dinv(t_map, y)
+        return nat, K, L, info, z, delta, det_m
+
+    def logp_terms(self, theta, X, y):
+        """Returns dict of the terms of logp_cho (gaussian.py:193-241 / studentT.py:115-146)."""
+        c = self.consts
+        nat, K, L, info, z, delta, det_m = self._core(theta, X, y)
+        n = float(X.shape[0])
+        lcho = sla.solve_triangular(L, delta, lower=True)       # gaussian.py:212
+        beta = float(lcho.dot(lcho))                            # gaussian.py:215
+        logdet = float(np.sum(np.log(np.diag(L))))
+        out = {"beta": beta, "logdet": logdet, "det_m": float(det_m), "info": info}
+        if self.kind == "gauss":
+            npi = -0.5 * n * c.log_2pi                          # gaussian.py:218
+            out.update(npi=npi, dot2=-0.5 * beta, det_k=-logdet)
+            r = npi + (-0.5 * beta) + (-logdet) + det_m
+        else:
+            nu = 2.0 + nat[-1]                                  # hypers/__init__.py:159-160 bound + degree
+            r1 = -0.5 * (nu + n) * np.log1p(beta / (nu - 2.0))  # studentT.py:126
+            if 1e6 <= nu:                                       # studentT.py:127
+                r2 = -n * 0.5 * c.log_2pi_student
+            else:                                               # studentT.py:128
+                r2 = gammaln((nu + n) * 0.5) - gammaln(nu * 0.5) - 0.5 * n * np.log((nu - 2.0) * c.pi)
+            out.update(r1=float(r1), r2=float(r2), r3=-logdet, nu=nu)
+            r = r1 + r2 + (-logdet) + det_m
+        bad = (not np.all(np.isfinite(delta)) or not np.isfinite(det_m)
+               or not np.all(np.isfinite(L)) or not np.all(np.isfinite(lcho)))   # gaussian.py:234-241
+        out["loglike"] = c.guard if bad else float(r)
+        return out
+
+    def loglike(self, theta, X, y):
+        return self.logp_terms(theta, X, y)["loglike"]
+
+    def logp(self, theta, X, y):
+        """th_logp posterior (stochastic.py:300-306): free-RV terms + observed term."""
+        return self.logprior(theta) + self.loglike(theta, X, y)
+
+    # ---- gradient ------------------------------------------------------------------------
+    def dlogp(self, theta, X, y, method="analytic", nan_quirk=False):
+        """d logp / d theta (theta = transformed/log space), bijection order.
+
+        method="analytic": G = 1/2 (c alpha alpha^T - K^-1)  
+        method="murray":   reverse-mode through chol like the reference (tensors.py:224-260)
+        Both contract G with the per-kernel dK/dtheta.  Result passed through tt_to_num
+        (stochastic.py:308-309).
+        """
+        nat, K, L, info, z, delta, det_m = self._core(theta, X, y)
+        t_loc, t_ker, t_map, t_deg = self.split(nat)
+        n = float(X.shape[0])
+        u = sla.solve_triangular(L, delta, lower=True)
+        beta = float(u.dot(u))
+        alpha = sla.solve_triangular(L.T, u, lower=False)
+        if self.kind == "gauss":
+            cfac = 1.0
+        else:
+            nu = 2.0 + nat[-1]
+            cfac = (nu + n) / (nu - 2.0 + beta)
+        if method == "analytic":
+            Kinv = sla.cho_solve((L, True), np.eye(L.shape[0]))
+            G = 0.5 * (cfac * np.outer(alpha, alpha) - Kinv)
+        else:
+            # dlogp/dL: quadratic term  d(-c/2 u'u)/dL = c * L^-T u u^T (lower), logdet term -1/L_ii
+            Lbar = cfac * np.tril(np.outer(alpha, u)) - np.diag(1.0 / np.diag(L))
+            Kbar = murray_cholesky_grad(L, Lbar)
+            G = 0.5 * (Kbar + Kbar.T)                           # symmetric form of the tril gradient
+        dK = self.k_noise.dcov(t_ker, X, X, True, nan_quirk)
+        g_ker = np.array([np.sum(G * d) for d in dK])
+        g_delta = -cfac * alpha
+        g_loc = -(self.location.jac(t_loc, X) @ g_delta) if self.n_loc else np.zeros(0)
+        if self.n_map:
+            dinv, dld = self.mapping.grads(t_map, y)
+            g_map = dinv @ g_delta + dld
+        else:
+            g_map = np.zeros(0)
+        parts = [g_loc, g_ker, g_map]
+        if self.kind == "student":
+            bn = beta / (nu - 2.0)
+            d_r1 = -0.5 * np.log1p(bn) + 0.5 * (nu + n) * bn / ((nu - 2.0) * (1.0 + bn))
+            if 1e6 <= nu:
+                d_r2 = 0.0
+            else:
+                d_r2 = 0.5 * digamma((nu + n) * 0.5) - 0.5 * digamma(nu * 0.5) - 0.5 * n / (nu - 2.0)
+            parts.append(np.array([d_r1 + d_r2]))
+        g_nat = np.concatenate(parts)
+        m = self.positive_mask()
+        g = np.where(m, g_nat * nat, g_nat)                     # chain rule through exp (log-space hypers)
+        return tt_to_num(g)
+
+    # ---- posterior -----------------------------------------------------------------------
+    def posterior(self, theta, Xs, X, y, noise=False, cov=False, solver="lu"):
+        """elliptical.py:78-107.  solver="lu" follows the reference (tsl.solve = general LU);
+        solver="chol" is the Cholesky route the CUDA path takes."""
+        nat = self.natural(theta)
+        t_loc, t_ker, t_map, t_deg = self.split(nat)
+        Kxx = self.cov_inputs(t_ker, X)
+        kern = self.k_noise if noise else self.f_kernel
+        th_k = t_ker if (noise or not self.noisy) else t_ker[:self.f_kernel.n_theta()]
+        Ksx = tt_to_num(kern.cov(th_k, Xs, X, False))           # elliptical.py:78-79
+        Kss = kern.cov(th_k, Xs, Xs, True)
+        if noise:
+            Kss = tt_to_cov(Kss, self.consts)                   # elliptical.py:70
+        delta = tt_to_num(self.mapping.inv(t_map, y)) - self.location(t_loc, X)
+        if solver == "lu":
+            a = sla.solve(Kxx, delta)
+            B = sla.solve(Kxx, Ksx.T)
+        else:
+            Lc = cholesky_robust(Kxx, self.consts)
+            a = sla.cho_solve((Lc, True), delta)
+            B = sla.cho_solve((Lc, True), Ksx.T)
+        mean = self.location(t_loc, Xs) + Ksx.dot(a)            # elliptical.py:81-84
+        C = Kss - Ksx.dot(B)                                    # elliptical.py:86-92
+        var = np.maximum(np.diag(C), 0.0)                       # elliptical.py:94-97 tt_to_bounded(.., 0)
+        out = {"location": mean, "kernel_diag": var, "kernel_sd": np.sqrt(var)}
+        if cov:
+            out["kernel"] = C
+        if self.kind == "student":                              # studentT.py:36-49
+            Lc = cholesky_robust(Kxx, self.consts)
+            al = sla.solve_triangular(Lc, delta, lower=True)
+            beta = al.dot(al)
+            nu = 2.0 + nat[-1]
+            out["scaling"] = (nu + beta - 2.0) / (nu + X.shape[0] - 2.0)
+        return out
+
+    def predict(self, theta, Xs, X, y, noise=False, n_gh=10):
+        """mean / variance / std / median / quantiles as `predict` assembles them
+        (stochastic.py:488-513; gaussian.py:56-73,127-174; studentT.py:45-55)."""
+        from scipy import stats
+        nat = self.natural(theta)
+        t_map = self.split(nat)[2]
+        post = self.posterior(theta, Xs, X, y, noise=noise)
+        mu, var = post["location"], post["kernel_diag"]
+        T = lambda v: self.mapping.forward(t_map, v)
+        # gaussian.py:115-174: only the Warped* classes integrate T by Gauss-Hermite; the plain classes use T(mu)
+        warped = self.spec.get("warped", self.mapping.kind != "Identity")
+        scaling = post.get("scaling", 1.0)
+        if warped:                                              # gaussian.py:127-174 Gauss-Hermite n=10
+            a, w = np.polynomial.hermite.hermgauss(n_gh)
+            sd = np.sqrt(var)
+            grille = mu[None, :] + sd[None, :] * np.sqrt(2.0) * a[:, None]
+            mean = w.dot(T(grille.ravel()).reshape(grille.shape)) / np.sqrt(np.pi)
+            m2 = w.dot((T(grille.ravel()) ** 2).reshape(grille.shape)) / np.sqrt(np.pi)
+            variance = m2 - mean ** 2
+        else:
+            mean = T(mu)                                        # elliptical.py:194-196
+            variance = var * scaling                            # studentT.py:45-46
+        out = {"mean": mean, "variance": variance, "std": np.sqrt(variance), "median": T(mu)}
+        if self.kind == "student":
+            q = stats.t.ppf(0.975, df=2.0 + nat[-1] + X.shape[0])   # studentT.py:53 (freedom posterior)
+        else:
+            q = stats.norm.ppf(0.975)
+        sd = np.sqrt(var)
+        out["quantile_up"] = T(mu + q * sd)
+        out["quantile_down"] = T(mu - q * sd)
+        return out
+
+
+# --------------------------------------------------------------------------- synthetic inputs
+def c1_inputs():
+    rng = np.random.default_rng(0)
+    x = np.linspace(0, 10, 200)[:, None]
+    y = np.sin(x[:, 0]) + 0.1 * rng.standard_normal(200)
+    return x, y
+
+
+def c2_inputs(N=4096, B=64):
+    rng = np.random.default_rng(1)
+    X = rng.uniform(0, 10, size=(N, 3))
+    f = np.sin(X[:, 0]) + np.cos(X[:, 1] / 2) + 0.1 * X[:, 2]
+    y = f + 0.1 * rng.standard_normal(N)
+    rng2 = np.random.default_rng(2)
+    # theta-bar: Bias 0 ; SE var 1, rates 1,1,1 ; MAT52 var 0.5, rates .5,.5,.5 ; noise 0.05
+    tbar = np.array([0.0, 1.0, 1.0, 1.0, 1.0, 0.5, 0.5, 0.5, 0.5, 0.05])
+    Theta = np.tile(np.concatenate([[0.0], np.log(tbar[1:])]), (B, 1))
+    Theta = Theta + 0.1 * rng2.standard_normal(Theta.shape)
+    return X, y, Theta
+
+
+def c3_inputs(N=2048, M=10000):
+    rng = np.random.default_rng(3)
+    x = np.sort(rng.uniform(0, 20, size=N))[:, None]
+    f = np.sin(2 * np.pi * x[:, 0] / 5.0) * np.exp(-0.02 * x[:, 0]) + 0.05 * rng.standard_normal(N)
+    y = np.exp(0.3 * f) + 0.5
+    xs = np.linspace(0, 20, M)[:, None]
+    return x, y, xs
+
+
+def c4_inputs(N=16384, M=4096):
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((N, 5))
+    f = np.sin(X[:, 0]) + 0.5 * X[:, 1] * X[:, 2] + np.cos(X[:, 3]) - 0.3 * X[:, 4]
+    y = f + 0.1 * rng.standard_normal(N)
+    Xs = rng.standard_normal((M, 5))
+    return X, y, Xs
+
+
+def c5_inputs(N=65536):
+    rng = np.random.default_rng(5)
+    X = rng.uniform(0, N ** (1.0 / 3.0), size=(N, 3))
+    y = np.sin(X[:, 0]) + 0.1 * rng.standard_normal(N)
+    return X, y

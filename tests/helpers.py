@@ -1,0 +1,64 @@
+"""Shared test helpers: build the g3py_b200 objects from the oracle's neutral model spec, so that the
+identical description drives both sides (the product never imports the oracle)."""
+import numpy as np
+
+import g3py_b200 as g3
+
+LEAVES = {"SE": g3.SE, "OU": g3.OU, "MAT32": g3.MAT32, "MAT52": g3.MAT52, "RQ": g3.RQ, "SIN": g3.SIN, "WN": g3.WN,
+          "Noise": g3.KernelNoise}
+MAPS = {"Identity": g3.Identity, "LinearMapping": g3.LinearMapping, "LogShifted": g3.LogShifted,
+        "BoxCoxShifted": g3.BoxCoxShifted, "BoxCoxLinear": g3.BoxCoxLinear, "ArcsinhLinear": g3.ArcsinhLinear,
+        "SinhArcsinh": g3.SinhArcsinh}
+MEANS = {"Zero": g3.Zero, "Bias": g3.Bias, "Linear": g3.Linear}
+
+
+def _x_arg(X, dims):
+    if dims is None:
+        return X
+    return (X, slice(int(dims[0]), int(dims[1])))
+
+
+def build_kernel(spec, X):
+    t = spec["type"]
+    if t == "sum":
+        return build_kernel(spec["k1"], X) + build_kernel(spec["k2"], X)
+    if t == "prod":
+        return build_kernel(spec["k1"], X) * build_kernel(spec["k2"], X)
+    if t == "scale":
+        return spec["c"] * build_kernel(spec["k"], X)
+    if t == "shift":
+        return spec["c"] + build_kernel(spec["k"], X)
+    kw = {}
+    if "name" in spec:
+        kw["name"] = spec["name"]
+    if spec.get("var") is not None:
+        kw["var"] = spec["var"]
+    return LEAVES[t](_x_arg(X, spec.get("dims")), **kw)
+
+
+def build_process(spec, X, strict=True):
+    kind = spec.get("kind", "gauss")
+    warped = spec.get("warped", spec.get("mapping", {"type": "Identity"})["type"] != "Identity")
+    cls = {("gauss", False): g3.GP, ("gauss", True): g3.WGP, ("student", False): g3.TP, ("student", True): g3.WTP}[(kind, warped)]
+    loc = spec.get("location", {"type": "Zero"})
+    lkw = {"name": loc["name"]} if "name" in loc else {}
+    location = MEANS[loc["type"]](_x_arg(X, loc.get("dims")), **lkw)
+    mp = spec.get("mapping", {"type": "Identity"})
+    mkw = {"name": mp["name"]} if "name" in mp else {}
+    mapping = MAPS[mp["type"]](**mkw)
+    kw = {}
+    if "name" in spec:
+        kw["name"] = spec["name"]
+    return cls(X, location, build_kernel(spec["kernel"], X), mapping, noisy=spec.get("noisy", True),
+               strict_constants=strict, **kw)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))) if a.size else 0.0
+
+
+def scaled_err(a, b):
+    """max |a-b| / max|b| — for vectors whose small entries are sums of large cancelling terms."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)) if a.size else 0.0

@@ -1,0 +1,354 @@
+"""Parity of the CUDA path (through the C ABI / ctypes) against the NumPy oracle.  Needs a B200.
+
+Tolerances: the north star asks for 1e-9 relative on fp64 logp, gradients and posterior moments;
+element-wise Gram values are held to 1e-12.
+"""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+import g3py_b200 as g3
+from g3py_b200 import _cabi as cabi
+from oracle import g3_oracle as orc
+from helpers import build_process, build_kernel, rel_err, scaled_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return g3.processes.get_context(0)
+
+
+def _desc_and_theta(kspec, X, rng):
+    """compile a kernel spec through the product algebra; random natural hypers in oracle order."""
+    D = X.shape[1]
+    ok = orc.build_kernel(kspec, D)
+    k = build_kernel(kspec, X)
+    reg = g3.Registry()
+    k.check_dims(X)
+    k.check_hypers("", reg)
+    b = g3.DescBuilder(D)
+    k.compile(b)
+    desc = b.finish()
+    off = 0
+    for v in reg.vars:
+        v.offset = off
+        off += v.size
+    names_o = [(h.name, h.size) for h in ok.layout()]
+    names_p = [(v.name, v.size) for v in reg.vars]
+    assert names_o == names_p, (names_o, names_p)
+    th_o = np.exp(rng.normal(0.0, 0.4, size=off))
+    th_p = np.empty(desc.n_theta)
+    for h, o, size, const in b.slots:
+        th_p[o:o + size] = const if h is None else th_o[h.offset:h.offset + h.size]
+    return ok, desc, th_o, th_p, b.slots
+
+
+KSPECS = {
+    "SE": {"type": "SE"},
+    "OU": {"type": "OU"},
+    "MAT32": {"type": "MAT32"},
+    "MAT52": {"type": "MAT52"},
+    "RQ": {"type": "RQ"},
+    "SIN": {"type": "SIN"},
+    "WN": {"type": "WN"},
+    "SE+MAT52+Noise": {"type": "sum", "k1": {"type": "sum", "k1": {"type": "SE"}, "k2": {"type": "MAT52"}},
+                       "k2": {"type": "Noise"}},
+    "SINxSE": {"type": "prod", "k1": {"type": "SIN"}, "k2": {"type": "SE"}},
+    "2*(RQ)+0.5": {"type": "shift", "c": 0.5, "k": {"type": "scale", "c": 2.0, "k": {"type": "RQ"}}},
+    "SE[0:1]*OU[1:3]+MAT32": {"type": "sum", "k1": {"type": "prod", "k1": {"type": "SE", "dims": [0, 1]},
+                                                     "k2": {"type": "OU", "dims": [1, 3], "var": 1.0}},
+                              "k2": {"type": "MAT32"}},
+}
+
+
+@pytest.mark.parametrize("name", list(KSPECS))
+@pytest.mark.parametrize("n1,n2,D", [(1, 1, 1), (5, 3, 2), (127, 129, 3), (300, 257, 3)])
+def test_gram_parity(ctx, name, n1, n2, D):
+    kspec = KSPECS[name]
+    if "dims" in str(kspec) and D < 3:
+        pytest.skip("spec needs 3 columns")
+    rng = np.random.default_rng(hash((name, n1, n2, D)) % 2 ** 32)
+    X1 = rng.uniform(0, 3, size=(n1, D))
+    X2 = rng.uniform(0, 3, size=(n2, D))
+    X2[: min(n1, n2) // 2] = X1[: min(n1, n2) // 2]           # exact coincidences (WN, d = 0)
+    ok, desc, th_o, th_p, _ = _desc_and_theta(kspec, X1, rng)
+    Kc, st = ctx.gram(desc, X1, X2, th_p[None, :])
+    Ko = orc.tt_to_num(ok.cov(th_o, X1, X2, False))
+    assert scaled_err(Kc[0], Ko) < 1e-12
+    Ks, st = ctx.gram(desc, X1, None, th_p[None, :])
+    Kso = orc.tt_to_num(ok.cov(th_o, X1, X1, True))
+    assert scaled_err(Ks[0], Kso) < 1e-12
+    assert np.array_equal(Ks[0], Ks[0].T)                      # symmetric to the bit
+
+
+def test_gram_batched_and_nonfinite(ctx):
+    rng = np.random.default_rng(7)
+    X = rng.uniform(0, 3, size=(200, 2))
+    ok, desc, th_o, th_p, slots = _desc_and_theta(KSPECS["SE+MAT52+Noise"], X, rng)
+    B = 5
+    Th = np.tile(th_p, (B, 1)) * np.exp(rng.normal(0, 0.2, size=(B, len(th_p))))
+    K, st = ctx.gram(desc, X, None, Th)
+    for b in range(B):
+        th_b = np.empty_like(th_o)
+        for h, o, size, const in slots:
+            th_b[h.offset:h.offset + size] = Th[b, o:o + size]
+        assert scaled_err(K[b], ok.cov(th_b, X, X, True)) < 1e-12
+    assert np.all(st == 0)
+    Th[2, 0] = np.inf                                           # var = inf -> inf*exp(-d): scrubbed like tt_to_num
+    K, st = ctx.gram(desc, X, None, Th)
+    assert st[2] & cabi.ST_NONFINITE_INPUT and st[0] == 0
+    assert np.all(np.isfinite(K))
+
+
+@pytest.mark.parametrize("name", list(KSPECS))
+def test_gram_vjp_parity(ctx, name):
+    kspec = KSPECS[name]
+    rng = np.random.default_rng(11)
+    n1, n2, D = 150, 131, 3
+    X1 = rng.uniform(0, 3, size=(n1, D))
+    X2 = rng.uniform(0, 3, size=(n2, D))
+    ok, desc, th_o, th_p, slots = _desc_and_theta(kspec, X1, rng)
+    for same in (False, True):
+        xb = X1 if same else X2
+        W = rng.standard_normal((n1, xb.shape[0]))
+        g = ctx.gram_vjp(desc, X1, None if same else X2, th_p[None, :], W[None])[0]
+        dK = ok.dcov(th_o, X1, xb, same)
+        go = np.array([np.sum(W * d) for d in dK])
+        gp = np.empty_like(go)
+        for h, o, size, const in slots:
+            if h is not None:
+                gp[h.offset:h.offset + size] = g[o:o + size]
+        assert scaled_err(gp, go) < 1e-11, (name, same)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 128, 129, 300, 1000])
+def test_potrf_parity(ctx, n):
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n + 3))
+    K = A @ A.T + n * 1e-3 * np.eye(n)
+    L, info, jit = ctx.potrf_robust(K)
+    Lo = sla.cholesky(K, lower=True)
+    assert info == 0 and jit == 0.0
+    assert np.all(np.triu(L, 1) == 0.0)
+    assert scaled_err(L, Lo) < 1e-11
+    assert scaled_err(L @ L.T, K) < 1e-13
+
+
+def test_potrf_jitter_ladder(ctx):
+    """Rank-deficient and indefinite inputs: same ladder outcome as CholeskyRobust (tensors.py:197-222)."""
+    rng = np.random.default_rng(3)
+    n = 200
+    A = rng.standard_normal((n, 20))
+    K_psd = A @ A.T                                              # rank 20: dpotrf fails, jitter repairs it
+    K_neg = K_psd - 5.0 * np.eye(n)                              # negative diagonal entries
+    K_bad = -np.eye(n) * 1e30                                    # ladder exhausted? (pre-shift makes it PD)
+    for K in (K_psd, K_neg, K_bad):
+        Lo, info_o = orc.cholesky_robust(K, return_info=True)
+        L, info, jit = ctx.potrf_robust(K)
+        assert info == info_o, (info, info_o)
+        if info_o > 0:
+            assert scaled_err(L @ L.T, Lo @ Lo.T) < 1e-9
+    Kb = np.stack([K_psd + np.eye(n), K_psd, K_neg])
+    Lb, infob, jitb = ctx.potrf_robust(Kb)
+    assert infob[0] == 0 and infob[1] > 0 and infob[2] > 0
+    assert scaled_err(Lb[0], sla.cholesky(Kb[0], lower=True)) < 1e-11
+    Knan = K_psd.copy()
+    Knan[3, 3] = np.nan
+    L, info, jit = ctx.potrf_robust(Knan)
+    assert info == -1                                            # caller applies the 1e-10*I fallback
+
+
+# ------------------------------------------------------------------------------------------- logp / dlogp
+SPECS = {
+    "C1": {"kind": "gauss", "location": {"type": "Bias"}, "kernel": {"type": "SE"}},
+    "C2": {"kind": "gauss", "location": {"type": "Bias"},
+           "kernel": {"type": "sum", "k1": {"type": "SE"}, "k2": {"type": "MAT52"}}},
+    "C3": {"kind": "gauss", "warped": True, "location": {"type": "Bias"},
+           "kernel": {"type": "prod", "k1": {"type": "SIN"}, "k2": {"type": "SE"}},
+           "mapping": {"type": "BoxCoxShifted"}},
+    "C4": {"kind": "student", "location": {"type": "Bias"}, "kernel": {"type": "SE"}},
+    "WTP": {"kind": "student", "warped": True, "location": {"type": "Linear"},
+            "kernel": {"type": "sum", "k1": {"type": "RQ"}, "k2": {"type": "OU"}},
+            "mapping": {"type": "ArcsinhLinear"}},
+    "noiseless": {"kind": "gauss", "location": {"type": "Zero"}, "noisy": False,
+                  "kernel": {"type": "sum", "k1": {"type": "MAT32"}, "k2": {"type": "WN"}}},
+}
+
+
+def _data(name, N):
+    if name == "C1":
+        x, y = orc.c1_inputs()
+        return x[:N], y[:N]
+    if name in ("C2", "noiseless"):
+        X, y, _ = orc.c2_inputs(N, 1)
+        return X, y
+    if name == "C3":
+        x, y, _ = orc.c3_inputs(N, 8)
+        return x, y
+    X, y, _ = orc.c4_inputs(N, 8)
+    return X, y
+
+
+def _theta0(name, gp, op, X, y, rng, B):
+    """default hypers of the product, perturbed; kernels kept well conditioned (noise floor)."""
+    th = gp.dict_to_array(gp.params_default)
+    Th = np.tile(th, (B, 1)) + 0.1 * rng.standard_normal((B, len(th)))
+    lay = gp.layout
+    off = 0
+    for nm, size, pos in lay:
+        if nm.endswith("SIN_rate"):
+            Th[:, off:off + size] = np.log(0.1)                  # a3-iii: keeps the periodic kernel PD
+        if nm.endswith("SIN_freq"):
+            Th[:, off:off + size] = np.log(0.2)
+        if nm.endswith("Freedom_degree"):
+            Th[:, off:off + size] = np.log(5.0) + 0.1 * rng.standard_normal((B, size))
+        if nm.endswith("BoxShift_power"):
+            Th[:, off:off + size] = np.log(0.7) + 0.05 * rng.standard_normal((B, size))
+        off += size
+    return Th
+
+
+@pytest.mark.parametrize("name,N", [("C1", 200), ("C2", 333), ("C3", 256), ("C4", 300), ("WTP", 130), ("noiseless", 257)])
+def test_logp_dlogp_parity(name, N):
+    spec = SPECS[name]
+    X, y = _data(name, N)
+    rng = np.random.default_rng(5)
+    gp = build_process(spec, X)
+    gp.observed(X, y)
+    op = orc.OracleProcess(spec, X.shape[1])
+    assert [(a.split("_", 1)[1], b, c) for a, b, c in gp.layout] == op.layout()
+    B = 3
+    Th = _theta0(name, gp, op, X, y, rng, B)
+    lp, g, info = gp.logp_dlogp_batch(Th)
+    for b in range(B):
+        t = op.logp_terms(Th[b], X, y)
+        assert t["info"] == 0
+        assert abs(info["beta"][b] - t["beta"]) <= TOL * abs(t["beta"])
+        assert abs(info["logdet"][b] - t["logdet"]) <= TOL * max(abs(t["logdet"]), 1.0)
+        lo = op.logp(Th[b], X, y)
+        assert abs(lp[b] - lo) <= TOL * abs(lo), (name, b, lp[b], lo)
+        go = op.dlogp(Th[b], X, y, method="analytic")
+        assert scaled_err(g[b], go) < TOL, (name, b, g[b], go)
+        gm = op.dlogp(Th[b], X, y, method="murray")             # the reference's own reverse-mode route
+        assert scaled_err(g[b], gm) < 1e-7
+    # single-theta entries agree with the batch, dict and array forms agree
+    assert abs(gp.logp(Th[0], array=True) - lp[0]) <= 1e-12 * abs(lp[0])
+    assert abs(gp.logp(gp.array_to_dict(Th[0])) - lp[0]) <= 1e-12 * abs(lp[0])
+    assert scaled_err(gp.dlogp(Th[1], array=True), g[1]) < 1e-12
+
+
+def test_student_kat_notebook():
+    """The only known-answer vectors in the reference tree (notebooks/07-Student-t-Process.ipynb:206-218):
+    WarpedStudentTProcess(x, Bias(), SE(x), ArcsinhLinear()) on X=[[0],[1]], y=[0,1]."""
+    X = np.array([[0.0], [1.0]])
+    y = np.array([0.0, 1.0])
+    tp = g3.WTP(X, g3.Bias(), g3.SE(X), g3.ArcsinhLinear(y))
+    tp.observed(X, y)
+    assert [n for n, _, _ in tp.layout] == ["WTP_Bias_Bias", "WTP_SE_var", "WTP_SE_rate", "WTP_Noise_var",
+                                            "WTP_ArcsinhLinear_shift", "WTP_ArcsinhLinear_scale", "WTP_Freedom_degree"]
+    kat = [(np.zeros(7), -2.620996), (np.array([0.5, np.log(0.25), np.log(0.5), np.log(0.25), 0.5, np.log(0.5), 0.0]), -2.654731)]
+    for th, want in kat:
+        got = tp.logp(th, array=True)
+        assert abs(got - want) < 5e-6, (got, want)              # float32 prints in the notebook
+
+
+def test_jitter_ladder_in_logp():
+    """Duplicated inputs without noise -> singular K: the ladder result equals the oracle's."""
+    rng = np.random.default_rng(9)
+    X = rng.uniform(0, 5, size=(150, 2))
+    X[75:] = X[:75]
+    y = np.sin(X[:, 0])
+    spec = {"kind": "gauss", "location": {"type": "Zero"}, "kernel": {"type": "SE"}, "noisy": False}
+    gp = build_process(spec, X)
+    gp.observed(X, y)
+    op = orc.OracleProcess(spec, 2)
+    th = np.array([0.0, np.log(0.3), np.log(0.3)])
+    t = op.logp_terms(th, X, y)
+    ll, g, info = gp.logp_dlogp_batch(th[None])
+    assert t["info"] > 0
+    assert (info["status"][0] & cabi.ST_JITTER) and ((info["status"][0] >> 8) & 0xFF) == t["info"]
+    assert abs(info["logdet"][0] - t["logdet"]) <= 1e-6 * abs(t["logdet"])
+    assert abs(ll[0] - t["loglike"]) <= 1e-6 * abs(t["loglike"])
+
+
+def test_guards():
+    """Non-finite delta -> float32(-1e30) like gaussian.py:234-241."""
+    x, y = orc.c1_inputs()
+    y = y.copy()
+    y[5] = np.nan
+    gp = build_process(SPECS["C1"], x)
+    gp.observed(x, y)
+    assert gp.logp() == float(np.float32(-1e30))
+    assert np.all(gp.dlogp() == 0.0)
+
+
+# ------------------------------------------------------------------------------------------- posterior
+@pytest.mark.parametrize("name,N,M", [("C1", 200, 333), ("C3", 256, 500), ("C4", 300, 129), ("noiseless", 200, 64)])
+@pytest.mark.parametrize("noise", [False, True])
+def test_posterior_parity(name, N, M, noise):
+    spec = SPECS[name]
+    X, y = _data(name, N)
+    rng = np.random.default_rng(13)
+    Xs = X[rng.integers(0, N, size=M)] + 0.05 * rng.standard_normal((M, X.shape[1]))
+    gp = build_process(spec, X)
+    gp.observed(X, y)
+    op = orc.OracleProcess(spec, X.shape[1])
+    th = _theta0(name, gp, op, X, y, rng, 1)[0]
+    out = gp.predict(th, space=Xs, array=True, mean=True, std=True, var=True, cov=True, median=True, quantiles=True,
+                     noise=noise)
+    for solver, tol in (("chol", TOL), ("lu", 1e-8)):            # the reference's LU route: bounded by kappa(K) * eps
+        po = op.posterior(th, Xs, X, y, noise=noise, cov=True, solver=solver)
+        post, _, _ = gp._posterior(th, Xs, noise=noise, cov=True)
+        assert scaled_err(post["location"], po["location"]) < tol
+        assert scaled_err(post["kernel_diag"], po["kernel_diag"]) < tol * 10
+        assert scaled_err(post["kernel"], po["kernel"]) < tol * 10
+    pr = op.predict(th, Xs, X, y, noise=noise)
+    for k in ("mean", "variance", "std", "median", "quantile_up", "quantile_down"):
+        assert scaled_err(out[k], pr[k]) < 1e-8, k
+
+
+def test_find_map_c1():
+    """BASELINE config 1: SE + noise on the 1-D sine, BFGS through logp/dlogp."""
+    x, y = orc.c1_inputs()
+    gp = g3.GP(x, g3.Bias(), g3.SE(x))
+    gp.observed(x, y)
+    op = orc.OracleProcess(SPECS["C1"], 1)
+    th0 = gp.dict_to_array(gp.params_default)
+    assert abs(gp.logp(th0, array=True) - op.logp(th0, x, y)) <= TOL * abs(op.logp(th0, x, y))
+    best, pts = gp.find_MAP(return_points=True)
+    thm = gp.dict_to_array(best)
+    assert gp.logp(thm, array=True) > gp.logp(th0, array=True)
+    assert np.linalg.norm(gp.dlogp(thm, array=True)) < 1e-2
+    assert abs(gp.logp(thm, array=True) - op.logp(thm, x, y)) <= TOL * abs(op.logp(thm, x, y))
+
+
+# ------------------------------------------------------------------------------------------- full size
+def test_c2_full_size_properties():
+    """N=4096, B=64 (BASELINE config 2): two items against the oracle, the rest through
+    size-independent properties (batch == single evaluation; finite, ordered status)."""
+    X, y, Theta = orc.c2_inputs(4096, 64)
+    gp = build_process(SPECS["C2"], X)
+    gp.observed(X, y)
+    op = orc.OracleProcess(SPECS["C2"], 3)
+    lp, g, info = gp.logp_dlogp_batch(Theta)
+    assert np.all(info["status"] == 0) and np.all(np.isfinite(lp)) and np.all(np.isfinite(g))
+    for b in (0, 63):
+        lo = op.logp(Theta[b], X, y)
+        go = op.dlogp(Theta[b], X, y)
+        assert abs(lp[b] - lo) <= TOL * abs(lo)
+        assert scaled_err(g[b], go) < TOL
+    l1, g1, _ = gp.logp_dlogp_batch(Theta[17:18])
+    assert abs(l1[0] - lp[17]) <= 1e-12 * abs(lp[17])
+    assert scaled_err(g1[0], g[17]) < 1e-11
+    # directional derivative by central differences of the batched logp itself
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(Theta.shape[1])
+    v /= np.linalg.norm(v)
+    h = 1e-4
+    lpp = gp.logp_batch(np.stack([Theta[5] + h * v, Theta[5] - h * v]))
+    fd = (lpp[0] - lpp[1]) / (2 * h)
+    assert abs(fd - g[5].dot(v)) <= 1e-6 * max(1.0, abs(fd))
