@@ -47,6 +47,8 @@ SIGNATURES = {
     "g3_timer_begin": (C.c_int, [_ctxp]),
     "g3_timer_end": (C.c_int, [_ctxp, C.POINTER(C.c_float)]),
     "g3_launch_count": (C.c_int64, [_ctxp]),
+    "g3_prof_enable": (C.c_int, [_ctxp, C.c_int]),
+    "g3_prof_read": (C.c_int, [_ctxp, _dp, C.POINTER(C.c_int64)]),
     "g3_set_data": (C.c_int, [_ctxp, _dp, C.c_int, C.c_int]),
     "g3_gram": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _ip]),
     "g3_gram_vjp": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp]),
@@ -150,6 +152,17 @@ class Context:
         ms = C.c_float()
         self._ck(self._lib.g3_timer_end(self._h, C.byref(ms)), "g3_timer_end")
         return float(ms.value)
+
+    PROF_CLASSES = ("dgemm_nt", "potrf_diag", "gram_fwd", "gram_vjp", "trsv", "other")
+
+    def prof_enable(self, on=True):
+        self._ck(self._lib.g3_prof_enable(self._h, 1 if on else 0), "g3_prof_enable")
+
+    def prof_read(self):
+        ms = np.zeros(6)
+        n = np.zeros(6, dtype=np.int64)
+        self._ck(self._lib.g3_prof_read(self._h, _d(ms), n.ctypes.data_as(C.POINTER(C.c_int64))), "g3_prof_read")
+        return {k: {"ms": float(ms[i]), "launches": int(n[i])} for i, k in enumerate(self.PROF_CLASSES)}
 
     def launch_count(self):
         return int(self._lib.g3_launch_count(self._h))

@@ -61,7 +61,47 @@ int g3_make_tmap(g3_ctx* ctx, CUtensorMap* out, const double* base, uint64_t col
   return 0;
 }
 
+void g3_prof_begin(g3_ctx* ctx, int cls) {
+  if (!ctx->prof_on) return;
+  if (ctx->prof_used * 2 >= ctx->prof_events.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    ctx->prof_events.push_back(a);
+    ctx->prof_events.push_back(b);
+    ctx->prof_class.push_back(cls);
+  }
+  ctx->prof_class[ctx->prof_used] = cls;
+  cudaEventRecord(ctx->prof_events[ctx->prof_used * 2], ctx->stream);
+}
+
+void g3_prof_end(g3_ctx* ctx) {
+  if (!ctx->prof_on) return;
+  cudaEventRecord(ctx->prof_events[ctx->prof_used * 2 + 1], ctx->stream);
+  ctx->prof_used++;
+}
+
 extern "C" {
+
+int g3_prof_enable(g3_ctx* ctx, int on) {
+  ctx->prof_on = on != 0;
+  ctx->prof_used = 0;
+  return 0;
+}
+
+int g3_prof_read(g3_ctx* ctx, double* ms, int64_t* launches) {
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int c = 0; c < G3_PROF_N; ++c) { ms[c] = 0.0; launches[c] = 0; }
+  for (size_t i = 0; i < ctx->prof_used; ++i) {
+    float t = 0.f;
+    G3_CUDA(ctx, cudaEventElapsedTime(&t, ctx->prof_events[2 * i], ctx->prof_events[2 * i + 1]));
+    ms[ctx->prof_class[i]] += t;
+    launches[ctx->prof_class[i]]++;
+  }
+  ctx->prof_used = 0;
+  return 0;
+}
 
 int g3_ctx_create(int device, g3_ctx** out) {
   if (!out) return -1;
@@ -94,6 +134,7 @@ int g3_ctx_destroy(g3_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->bufs)
     if (kv.second.p) cudaFree(kv.second.p);
+  for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   if (ctx->dX) cudaFree(ctx->dX);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);

@@ -40,9 +40,18 @@ struct g3_ctx {
   void* encode_fn = nullptr;           // cuTensorMapEncodeTiled
   int sm_count = 148;
   bool gemm_ready = false, diag_ready = false;
+  // optional per-launch-class device timing (bench.py roofline): event pairs recorded around launches
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_events;     // pairs
+  std::vector<int> prof_class;
+  size_t prof_used = 0;                     // pairs in use
   int potrf_w = 1 << 20;               // tile columns per right-looking outer block, batched path (left-looking)
   int potrf_w_big = 8;                 // same, single big matrix (g3_gram_potrf_device)
 };
+
+enum { G3_PROF_GEMM = 0, G3_PROF_DIAG = 1, G3_PROF_GRAM = 2, G3_PROF_VJP = 3, G3_PROF_TRSV = 4, G3_PROF_OTHER = 5, G3_PROF_N = 6 };
+void g3_prof_begin(g3_ctx* ctx, int cls);
+void g3_prof_end(g3_ctx* ctx);
 
 // ---- host helpers (ctx.cu) ----
 int g3_fail(g3_ctx* ctx, const char* what, cudaError_t e, const char* file, int line);

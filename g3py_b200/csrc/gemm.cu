@@ -203,7 +203,9 @@ int g3_gemm_launch(g3_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   long long ntiles = a.mode == 0 ? (long long)a.ntx * a.nty : (long long)a.ntx * (a.ntx + 1) / 2;
   if (ntiles <= 0 || B <= 0) return 0;
   dim3 grid((unsigned)(ntiles * 2), (unsigned)B, 1);
+  g3_prof_begin(ctx, G3_PROF_GEMM);
   dgemm_nt_kernel<<<grid, 256, kSmemBytes, ctx->stream>>>(tmA, tmB, a);
+  g3_prof_end(ctx);
   G3_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -60,6 +60,11 @@ __global__ void gp_zero_sub_kernel(double* __restrict__ beta, double* __restrict
   info[b] = 0;
 }
 
+__global__ void gp_clear_bits_kernel(int* __restrict__ status, int mask, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) status[b] &= ~mask;
+}
+
 __global__ void gp_zero_beta_kernel(double* __restrict__ beta, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) beta[b] = 0.0;
@@ -352,6 +357,9 @@ int g3_gp_download(g3_ctx* ctx, double* beta, double* logdet, double* dtheta_or_
       G3_CUDA(ctx, cudaMemsetAsync(w.info, 0, sizeof(int) * B, ctx->stream));
       if ((rc = gp_build_and_factor(ctx, w, w.shift2, nullptr, 0))) return rc;
     }
+    // the first pass flagged the failed items' NaN beta/logdet; the repaired values are re-checked
+    gp_clear_bits_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(w.status, G3_ST_NONFINITE_RESULT, B);
+    G3_LAUNCH_CHECK(ctx);
     if ((rc = gp_after_potrf(ctx, w))) return rc;
   }
   G3_CUDA(ctx, cudaMemcpyAsync(beta, w.beta, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream));

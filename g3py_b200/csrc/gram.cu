@@ -542,7 +542,9 @@ int g3_gram_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const GramArgs& a, i
   const int tr = (a.n1 + TS - 1) / TS, tc = (a.n2 + TS - 1) / TS;
   const long long ntiles = a.lower_only ? (long long)tr * (tr + 1) / 2 : (long long)tr * tc;
   const size_t smem = sizeof(double) * (2 * TS * a.D + G3_MAX_THETA);
+  g3_prof_begin(ctx, G3_PROF_GRAM);
   gram_fwd_kernel<<<dim3((unsigned)ntiles, B), 256, smem, ctx->stream>>>(desc, a, tr);
+  g3_prof_end(ctx);
   G3_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -571,7 +573,9 @@ int g3_gram_vjp_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const VjpArgs& a
     attr = true;
   }
   if (a.P == 0) return 0;
+  g3_prof_begin(ctx, G3_PROF_VJP);
   gram_vjp_kernel<<<dim3((unsigned)ntiles, B), 256, smem, ctx->stream>>>(desc, a, tr, partials, (int)ntiles);
+  g3_prof_end(ctx);
   G3_LAUNCH_CHECK(ctx);
   vjp_reduce_kernel<<<dim3(a.P, B), 256, 0, ctx->stream>>>(partials, (int)ntiles, a.P, a.scale, a.dtheta);
   G3_LAUNCH_CHECK(ctx);

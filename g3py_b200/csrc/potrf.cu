@@ -216,7 +216,9 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
         g.alpha = -1.0; g.beta = 1.0; g.bmap = bmap;
         if ((rc = g3_gemm_launch(ctx, tmA, tmB, g, B))) return rc;
       }
+      g3_prof_begin(ctx, G3_PROF_DIAG);
       potrf_diag_kernel<<<B, 256, kDiagSmem, ctx->stream>>>(A, Np, strideA, j, Dinv, T, nullptr, logdet, info, bmap);
+      g3_prof_end(ctx);
       G3_LAUNCH_CHECK(ctx);
       if (j < T - 1) {  // L[i][j] = A[i][j] Linv_jj^T for the tiles below the diagonal
         GemmArgs g = gemm_zero();
@@ -319,18 +321,22 @@ int g3_lauum_batched(g3_ctx* ctx, const double* U, double* Kinv, int Np, int B) 
 
 int g3_trsv_fwd(g3_ctx* ctx, const double* L, const double* Dinv, double* r, double* u, double* beta, int Np, int B) {
   const int T = Np / TS;
+  g3_prof_begin(ctx, G3_PROF_TRSV);
   for (int j = 0; j < T; ++j) {
     trsv_fwd_step_kernel<<<dim3(T - j, B), 256, 0, ctx->stream>>>(L, Dinv, r, u, beta, j, Np, T);
     G3_LAUNCH_CHECK(ctx);
   }
+  g3_prof_end(ctx);
   return 0;
 }
 
 int g3_trsv_bwd(g3_ctx* ctx, const double* L, const double* Dinv, double* s, double* alpha, int Np, int B) {
   const int T = Np / TS;
+  g3_prof_begin(ctx, G3_PROF_TRSV);
   for (int j = T - 1; j >= 0; --j) {
     trsv_bwd_step_kernel<<<dim3(j + 1, B), 256, 0, ctx->stream>>>(L, Dinv, s, alpha, j, Np, T);
     G3_LAUNCH_CHECK(ctx);
   }
+  g3_prof_end(ctx);
   return 0;
 }

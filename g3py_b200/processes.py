@@ -405,7 +405,8 @@ class EllipticalProcess(StochasticProcess):
                               gammaln((nu + n) * 0.5) - gammaln(nu * 0.5) - 0.5 * n * np.log((nu - 2.0) * c.pi))
                 ll = r1 + r2 + (-logdet) + det_m
         # guards (gaussian.py:234-241): non-finite delta / det_m / L / lcho -> float32(-1e30)
-        bad = ((st & cabi.ST_NONFINITE_RESULT) != 0) | ~np.isfinite(det_m) | ~np.isfinite(beta) | ~np.isfinite(logdet)
+        dev_bad = ((st & cabi.ST_NONFINITE_RESULT) != 0) & ~failed          # fallback items: L = 1e-10*I is finite
+        bad = dev_bad | ~np.isfinite(det_m) | ~np.isfinite(beta) | ~np.isfinite(logdet)
         ll = np.where(bad, c.guard, ll)
         info = {"beta": beta, "logdet": logdet, "det_m": det_m, "status": st, "nu": nu}
         self.executed["logp"] += B

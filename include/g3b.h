@@ -99,6 +99,11 @@ int g3_set_potrf_block(g3_ctx* ctx, int w_outer);
 /* Device timing on the context's stream (CUDA events; used by bench.py). */
 int g3_timer_begin(g3_ctx* ctx);
 int g3_timer_end(g3_ctx* ctx, float* ms);
+/* Optional per-kernel-class device timing (CUDA event pairs around each launch on the context's
+ * stream).  g3_prof_read synchronises, sums the elapsed ms and launch counts per class
+ * {0 dgemm_nt, 1 potrf_diag, 2 gram_fwd, 3 gram_vjp, 4 trsv (whole sweep), 5 other} and resets. */
+int g3_prof_enable(g3_ctx* ctx, int on);
+int g3_prof_read(g3_ctx* ctx, double* ms6, int64_t* launches6);
 /* Number of kernels launched by this context since creation (bench.py "gpu_launches"). */
 int64_t g3_launch_count(g3_ctx* ctx);
 

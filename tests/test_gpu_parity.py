@@ -56,7 +56,7 @@ KSPECS = {
     "SIN": {"type": "SIN"},
     "WN": {"type": "WN"},
     "SE+MAT52+Noise": {"type": "sum", "k1": {"type": "sum", "k1": {"type": "SE"}, "k2": {"type": "MAT52"}},
-                       "k2": {"type": "Noise"}},
+                       "k2": {"type": "Noise", "name": "Noise"}},
     "SINxSE": {"type": "prod", "k1": {"type": "SIN"}, "k2": {"type": "SE"}},
     "2*(RQ)+0.5": {"type": "shift", "c": 0.5, "k": {"type": "scale", "c": 2.0, "k": {"type": "RQ"}}},
     "SE[0:1]*OU[1:3]+MAT32": {"type": "sum", "k1": {"type": "prod", "k1": {"type": "SE", "dims": [0, 1]},
