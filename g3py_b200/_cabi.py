@@ -49,6 +49,9 @@ SIGNATURES = {
     "g3_launch_count": (C.c_int64, [_ctxp]),
     "g3_prof_enable": (C.c_int, [_ctxp, C.c_int]),
     "g3_prof_read": (C.c_int, [_ctxp, _dp, C.POINTER(C.c_int64)]),
+    "g3_debug_read": (C.c_int, [_ctxp, C.c_char_p, C.c_void_p, C.c_size_t]),
+    "g3_debug_potrf_stress": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, C.c_int, _ip, _dp]),
+    "g3_debug_gemm_stress": (C.c_int, [_ctxp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
     "g3_set_data": (C.c_int, [_ctxp, _dp, C.c_int, C.c_int]),
     "g3_gram": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _ip]),
     "g3_gram_vjp": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp]),
@@ -163,6 +166,24 @@ class Context:
         n = np.zeros(6, dtype=np.int64)
         self._ck(self._lib.g3_prof_read(self._h, _d(ms), n.ctypes.data_as(C.POINTER(C.c_int64))), "g3_prof_read")
         return {k: {"ms": float(ms[i]), "launches": int(n[i])} for i, k in enumerate(self.PROF_CLASSES)}
+
+    def debug_read(self, name, shape, dtype=np.float64):
+        out = np.empty(shape, dtype=dtype)
+        self._ck(self._lib.g3_debug_read(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes), "g3_debug_read")
+        return out
+
+    def debug_potrf_stress(self, desc, theta, iters):
+        theta = np.atleast_2d(_f64(theta))
+        out = np.zeros((iters, 4), dtype=np.int32)
+        tiles = np.zeros((2, 128, 128))
+        self._ck(self._lib.g3_debug_potrf_stress(self._h, C.byref(desc), _d(theta), theta.shape[0], iters, _i(out), _d(tiles)),
+                 "g3_debug_potrf_stress")
+        return out, tiles
+
+    def debug_gemm_stress(self, rows, B, launches, inplace, kdepth=128):
+        out = (C.c_longlong * 4)()
+        self._ck(self._lib.g3_debug_gemm_stress(self._h, rows, B, launches, inplace, kdepth, out), "g3_debug_gemm_stress")
+        return list(out)
 
     def launch_count(self):
         return int(self._lib.g3_launch_count(self._h))

@@ -83,6 +83,16 @@ void g3_prof_end(g3_ctx* ctx) {
 
 extern "C" {
 
+// Debug / test accessor: copy the first `bytes` of a named workspace to the host.
+int g3_debug_read(g3_ctx* ctx, const char* name, void* host, size_t bytes) {
+  auto it = ctx->bufs.find(name);
+  if (it == ctx->bufs.end() || !it->second.p || it->second.bytes < bytes) return g3_fail_msg(ctx, "g3_debug_read: no such buffer / too small");
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  G3_CUDA(ctx, cudaMemcpy(host, it->second.p, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int g3_prof_enable(g3_ctx* ctx, int on) {
   ctx->prof_on = on != 0;
   ctx->prof_used = 0;

@@ -12,6 +12,7 @@
 // the reference does these through LAPACK dpotrf and Theano's Murray reverse mode
 // (g3py/libs/tensors.py:198,224-260).
 #include "g3b_internal.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -122,7 +123,7 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 
   // Pull the D tile towards L2 while the main loop runs (read-modify-write epilogue).
-  if (g.beta != 0.0) {
+  if (g.beta != 0.0 && !(g.dbg & 1)) {
     for (int l = tid; l < G3_BM * 8; l += 256) {
       const double* p = Dt + (long long)(l >> 3) * g.ldd + (l & 7) * 16;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -148,6 +149,7 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (tid == 0 && kt >= 1 && kt - 1 + G3_STAGES < nk) {
       const int sp = (kt - 1) % G3_STAGES;
       mbar_wait(empty_bar(sp), (uint32_t)(((kt - 1) / G3_STAGES) & 1));
+      if (g.dbg & 8) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       issue(kt - 1 + G3_STAGES);
     }
     mbar_wait(full_bar(s), ph);
@@ -167,8 +169,15 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i][e], b[j][e]);
     }
+    // Release the stage.  The LDS above are asynchronous: ptxas hoists the arrive right behind the last LDS
+    // *issue*, and an mbarrier arrive does not wait for this warp's outstanding shared-memory reads, so the
+    // TMA refill (async proxy) could overwrite the stage under the last fragment loads (seen as rare, per-warp
+    // garbage in the b[3] fragment).  The proxy fence drains this thread's loads and orders them before the
+    // async-proxy write that the arrive enables.
+    if (!(g.dbg & 32)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_bar(s));
+    if (g.dbg & 16) __syncthreads();
   }
 
   // ---- epilogue ------------------------------------------------------------------------
@@ -203,9 +212,19 @@ int g3_gemm_launch(g3_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   long long ntiles = a.mode == 0 ? (long long)a.ntx * a.nty : (long long)a.ntx * (a.ntx + 1) / 2;
   if (ntiles <= 0 || B <= 0) return 0;
   dim3 grid((unsigned)(ntiles * 2), (unsigned)B, 1);
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("G3_DBG"); dbg = e ? atoi(e) : 0; }
+  GemmArgs a2 = a;
+  a2.dbg = dbg;
+  static bool big = false;
+  if ((dbg & 4) && !big) {
+    G3_CUDA(ctx, cudaFuncSetAttribute(dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
+    big = true;
+  }
   g3_prof_begin(ctx, G3_PROF_GEMM);
-  dgemm_nt_kernel<<<grid, 256, kSmemBytes, ctx->stream>>>(tmA, tmB, a);
+  dgemm_nt_kernel<<<grid, 256, (dbg & 4) ? 140 * 1024 : kSmemBytes, ctx->stream>>>(tmA, tmB, a2);
   g3_prof_end(ctx);
   G3_LAUNCH_CHECK(ctx);
+  if (dbg & 2) G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }

@@ -149,6 +149,27 @@ post_moments_kernel(const double* __restrict__ Vt, int Np, int M, const double* 
   }
 }
 
+// debug: count lower-triangle mismatches per 128x128 tile between two factor buffers
+__global__ void __launch_bounds__(256)
+dbg_tile_mismatch_kernel(const double* __restrict__ A, const double* __restrict__ R, int Np, int T, int* __restrict__ out) {
+  const int b = blockIdx.z, ti = blockIdx.y, tj = blockIdx.x;
+  if (tj > ti) return;
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const long long base = (long long)b * Np * Np + (long long)ti * TS * Np + (long long)tj * TS;
+  int c = 0;
+  for (int idx = threadIdx.x; idx < TS * TS; idx += 256) {
+    const int r = idx >> 7, q = idx & 127;
+    if (ti == tj && q > r) continue;
+    const double x = A[base + (long long)r * Np + q], y = R[base + (long long)r * Np + q];
+    if (!(x == y)) ++c;
+  }
+  if (c) atomicAdd(&cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0) out[((long long)b * T + ti) * T + tj] = cnt;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -392,6 +413,140 @@ int g3_gp_logp_grad(g3_ctx* ctx, const g3_kernel_desc* desc, int kind, const dou
   if ((rc = g3_gp_upload(ctx, desc, kind, delta, delta_stride, theta, B, nu_or_NULL, want_grad))) return rc;
   if ((rc = g3_gp_run(ctx))) return rc;
   return g3_gp_download(ctx, beta, logdet, dtheta_or_NULL, ddelta_or_NULL, status);
+}
+
+// Debug stress: build K once, then factor it `iters` times from a backup and compare every factor with the
+// first one tile by tile.  out[it][0..3] = {#mismatching tiles, b, tile row, tile col of the first one}.
+int g3_debug_potrf_stress(g3_ctx* ctx, const g3_kernel_desc* desc, const double* theta, int B, int iters, int* out,
+                          double* tiles /* 2 x 128 x 128: bad tile, reference tile of the first mismatch */) {
+  if (!ctx->dX) return g3_fail_msg(ctx, "stress: call g3_set_data first");
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int N = ctx->N, Np = g3_pad(N), T = Np / TS, P = desc->n_theta;
+  GpBufs w;
+  int rc;
+  if ((rc = gp_alloc(ctx, w, B, P, N, 1, 1))) return rc;
+  const size_t mat = sizeof(double) * (size_t)B * Np * Np;
+  double* Kb = (double*)g3_ws(ctx, "dbg_K", mat);
+  int* mm = (int*)g3_ws(ctx, "dbg_mm", sizeof(int) * (size_t)B * T * T);
+  if (!Kb || !mm) return -2;
+  ctx->gp.desc = *desc; ctx->gp.B = B; ctx->gp.kind = 0; ctx->gp.want_grad = 1; ctx->gp.delta_stride = 0; ctx->gp.valid = 0;
+  G3_CUDA(ctx, cudaMemcpyAsync(w.theta, theta, sizeof(double) * (size_t)B * P, cudaMemcpyHostToDevice, ctx->stream));
+  G3_CUDA(ctx, cudaMemsetAsync(w.status, 0, sizeof(int) * B, ctx->stream));
+  G3_CUDA(ctx, cudaMemsetAsync(w.A, 0, mat, ctx->stream));
+  GramArgs a;
+  memset(&a, 0, sizeof a);
+  a.X1 = ctx->dX; a.X2 = ctx->dX; a.n1 = N; a.n2 = N; a.D = ctx->D; a.same = 1; a.lower_only = 1; a.pad_identity = 1;
+  a.theta = w.theta; a.P = P; a.K = w.A; a.ldk = Np; a.strideK = (long long)Np * Np; a.status = w.status;
+  if ((rc = g3_gram_launch(ctx, *desc, a, B))) return rc;
+  G3_CUDA(ctx, cudaMemcpyAsync(Kb, w.A, mat, cudaMemcpyDeviceToDevice, ctx->stream));
+  std::vector<int> h((size_t)B * T * T);
+  bool dumped = false;
+  for (int it = 0; it < iters; ++it) {
+    G3_CUDA(ctx, cudaMemcpyAsync(w.A, Kb, mat, cudaMemcpyDeviceToDevice, ctx->stream));
+    G3_CUDA(ctx, cudaMemsetAsync(w.logdet, 0, sizeof(double) * B, ctx->stream));
+    G3_CUDA(ctx, cudaMemsetAsync(w.info, 0, sizeof(int) * B, ctx->stream));
+    if ((rc = g3_potrf_batched(ctx, w.A, Np, B, w.Dinv, w.logdet, w.info, nullptr, 0, ctx->potrf_w))) return rc;
+    out[4 * it + 0] = out[4 * it + 1] = out[4 * it + 2] = out[4 * it + 3] = 0;
+    if (it == 0) {
+      G3_CUDA(ctx, cudaMemcpyAsync(w.U, w.A, mat, cudaMemcpyDeviceToDevice, ctx->stream));
+      continue;
+    }
+    dbg_tile_mismatch_kernel<<<dim3(T, T, B), 256, 0, ctx->stream>>>(w.A, w.U, Np, T, mm);
+    G3_LAUNCH_CHECK(ctx);
+    G3_CUDA(ctx, cudaMemcpyAsync(h.data(), mm, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int nbad = 0;
+    for (int b = 0; b < B; ++b)
+      for (int ti = 0; ti < T; ++ti)
+        for (int tj = 0; tj <= ti; ++tj)
+          if (h[((size_t)b * T + ti) * T + tj]) {
+            if (!nbad) {
+              out[4 * it + 1] = b; out[4 * it + 2] = ti; out[4 * it + 3] = tj;
+              if (tiles && !dumped) {
+                const size_t off = (size_t)b * Np * Np + (size_t)ti * TS * Np + (size_t)tj * TS;
+                cudaMemcpy2D(tiles, sizeof(double) * TS, w.A + off, sizeof(double) * Np, sizeof(double) * TS, TS, cudaMemcpyDeviceToHost);
+                cudaMemcpy2D(tiles + TS * TS, sizeof(double) * TS, w.U + off, sizeof(double) * Np, sizeof(double) * TS, TS, cudaMemcpyDeviceToHost);
+                dumped = true;
+              }
+            }
+            ++nbad;
+          }
+    out[4 * it + 0] = nbad;
+  }
+  return 0;
+}
+
+namespace {
+__global__ void dbg_fill_kernel(double* p, size_t n, unsigned seed) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    unsigned long long z = (i + 1) * 0x9E3779B97F4A7C15ull + seed;
+    z ^= z >> 31; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 29;
+    p[i] = (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+  }
+}
+__global__ void dbg_cmp_kernel(const double* a, const double* b, size_t n, unsigned long long* cnt, unsigned long long* first) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride)
+    if (!(a[i] == b[i])) {
+      atomicAdd(cnt, 1ull);
+      atomicMin(first, (unsigned long long)i);
+    }
+}
+}  // namespace
+
+// GEMM determinism stress: D[rows x 128] = A[rows x 128] * Dm[128 x 128]^T for `B` batch items (the trsm-shaped
+// launch of potrf), `launches` times; inplace=1 writes over A (restored from a backup before each launch).
+// out[0] = launches with a mismatch vs the first launch, out[1] = mismatching elements in total,
+// out[2] = first mismatching element index of the first bad launch, out[3] = index of the first bad launch.
+int g3_debug_gemm_stress(g3_ctx* ctx, int rows, int B, int launches, int inplace, int kdepth, long long* out) {
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int Np = g3_pad(rows), T = Np / TS;
+  const int KD = kdepth > 0 ? kdepth : TS;          // contraction depth (columns of A)
+  const size_t nA = (size_t)B * Np * KD, nD = (size_t)B * TS * KD, nO = (size_t)B * Np * TS;
+  double* A = (double*)g3_ws(ctx, "st_A", sizeof(double) * nA);
+  double* A0 = (double*)g3_ws(ctx, "st_A0", sizeof(double) * nA);
+  double* Dm = (double*)g3_ws(ctx, "st_D", sizeof(double) * nD);
+  double* O = (double*)g3_ws(ctx, "st_O", sizeof(double) * nO);
+  double* R = (double*)g3_ws(ctx, "st_R", sizeof(double) * nO);
+  unsigned long long* cnt = (unsigned long long*)g3_ws(ctx, "st_cnt", 16);
+  if (!A || !A0 || !Dm || !O || !R || !cnt) return -2;
+  if (inplace && KD != TS) return g3_fail_msg(ctx, "stress: inplace needs kdepth 128");
+  dbg_fill_kernel<<<1024, 256, 0, ctx->stream>>>(A0, nA, 1u);
+  dbg_fill_kernel<<<1024, 256, 0, ctx->stream>>>(Dm, nD, 2u);
+  CUtensorMap tmA, tmD;
+  int rc;
+  if ((rc = g3_make_tmap(ctx, &tmA, A, KD, Np, B, KD, (uint64_t)Np * KD, G3_BM))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmD, Dm, KD, TS, B, KD, (uint64_t)TS * KD, G3_BN))) return rc;
+  out[0] = out[1] = 0; out[2] = out[3] = -1;
+  for (int it = 0; it < launches; ++it) {
+    G3_CUDA(ctx, cudaMemcpyAsync(A, A0, sizeof(double) * nA, cudaMemcpyDeviceToDevice, ctx->stream));
+    GemmArgs g = gz();
+    g.D = inplace ? A : O; g.ldd = inplace ? KD : TS; g.strideD = inplace ? (long long)Np * KD : (long long)Np * TS;
+    g.mode = 0; g.ntx = T; g.nty = 1;
+    g.a_r0 = 0; g.a_rx = TS; g.ka0 = 0; g.b_r0 = 0; g.kb0 = 0; g.kl0 = KD;
+    g.alpha = 1.0; g.beta = 0.0;
+    if ((rc = g3_gemm_launch(ctx, tmA, tmD, g, B))) return rc;
+    const double* res = inplace ? A : O;
+    if (it == 0) {
+      G3_CUDA(ctx, cudaMemcpyAsync(R, res, sizeof(double) * nO, cudaMemcpyDeviceToDevice, ctx->stream));
+      continue;
+    }
+    G3_CUDA(ctx, cudaMemsetAsync(cnt, 0, 8, ctx->stream));
+    G3_CUDA(ctx, cudaMemsetAsync(cnt + 1, 0xff, 8, ctx->stream));
+    dbg_cmp_kernel<<<1024, 256, 0, ctx->stream>>>(res, R, nO, cnt, cnt + 1);
+    unsigned long long h[2];
+    G3_CUDA(ctx, cudaMemcpyAsync(h, cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h[0]) {
+      if (out[0] == 0) { out[2] = (long long)h[1]; out[3] = it; }
+      out[0]++;
+      out[1] += (long long)h[0];
+    }
+  }
+  return 0;
 }
 
 // ---- Gram on host arrays -----------------------------------------------------------------

@@ -104,6 +104,14 @@ int g3_timer_end(g3_ctx* ctx, float* ms);
  * {0 dgemm_nt, 1 potrf_diag, 2 gram_fwd, 3 gram_vjp, 4 trsv (whole sweep), 5 other} and resets. */
 int g3_prof_enable(g3_ctx* ctx, int on);
 int g3_prof_read(g3_ctx* ctx, double* ms6, int64_t* launches6);
+/* Test accessor: copy the first `bytes` of a named device workspace (e.g. "gp_A", "gp_U", "gp_Dinv")
+ * to the host after synchronising the stream. */
+int g3_debug_read(g3_ctx* ctx, const char* name, void* host, size_t bytes);
+/* Determinism stress test: factor the same batch `iters` times and compare tile by tile with the first
+ * factor; out[it] = {#mismatching tiles, batch item, tile row, tile col of the first mismatch}. */
+int g3_debug_potrf_stress(g3_ctx* ctx, const g3_kernel_desc* desc, const double* theta, int B, int iters, int* out4,
+                          double* tiles2);
+int g3_debug_gemm_stress(g3_ctx* ctx, int rows, int B, int launches, int inplace, int kdepth, long long* out4);
 /* Number of kernels launched by this context since creation (bench.py "gpu_launches"). */
 int64_t g3_launch_count(g3_ctx* ctx);
 

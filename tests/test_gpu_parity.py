@@ -352,3 +352,19 @@ def test_c2_full_size_properties():
     lpp = gp.logp_batch(np.stack([Theta[5] + h * v, Theta[5] - h * v]))
     fd = (lpp[0] - lpp[1]) / (2 * h)
     assert abs(fd - g[5].dot(v)) <= 1e-6 * max(1.0, abs(fd))
+
+
+def test_repeat_runs_bitwise_identical(ctx):
+    """Determinism stress of the batched factorisation: the same 64-item batch factored repeatedly must give
+    bit-identical tiles (guards the TMA-pipeline stage-release ordering in dgemm_nt_kernel)."""
+    X, y, Theta = orc.c2_inputs(2048, 64)
+    gp = build_process(SPECS["C2"], X)
+    gp.observed(X, y)
+    thk = gp._kernel_theta(gp.natural(Theta))
+    out, _ = gp.ctx.debug_potrf_stress(gp.desc, thk, 12)
+    assert not out[:, 0].any(), out
+    res = []
+    for _ in range(3):
+        lp, g, info = gp.logp_dlogp_batch(Theta)
+        res.append(np.concatenate([lp, g.ravel()]))
+    assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2])
