@@ -23,6 +23,7 @@ __all__ = ["StochasticProcess", "EllipticalProcess", "GaussianProcess", "WarpedG
 
 f32 = np.float32
 _CONTEXTS = {}
+_TOKENS = __import__("itertools").count(1)     # unique per process object (id() can be recycled after GC)
 
 
 def get_context(device=0):
@@ -100,7 +101,7 @@ class StochasticProcess:
         self.is_observed = False
         self.executed = {"logp": 0, "dlogp": 0, "predict": 0}
         self._data_version = 0
-        self._ctx_version = -1
+        self._token = next(_TOKENS)
         self.registry = Registry()
         self._check_hypers()
         self._define_process()
@@ -110,13 +111,15 @@ class StochasticProcess:
     # ---- pickling: the device context is per process and never pickled (stochastic.py:107-119)
     def __getstate__(self):
         d = dict(self.__dict__)
-        d["_ctx_version"] = -1
+        d.pop("_token", None)
         return d
 
     @property
     def ctx(self):
         ctx = get_context(self.device)
-        tag = (id(self), self._data_version)
+        if "_token" not in self.__dict__:
+            self._token = next(_TOKENS)          # unpickled object
+        tag = (self._token, self._data_version)
         if getattr(ctx, "_data_tag", None) != tag:
             ctx.set_jitter(self.consts.jitter, 20)
             ctx.set_data(self.inputs)
