@@ -44,6 +44,7 @@ SIGNATURES = {
     "g3_sync": (C.c_int, [_ctxp]),
     "g3_set_jitter": (C.c_int, [_ctxp, C.c_double, C.c_int]),
     "g3_set_potrf_block": (C.c_int, [_ctxp, C.c_int]),
+    "g3_set_groups": (C.c_int, [_ctxp, C.c_int]),
     "g3_timer_begin": (C.c_int, [_ctxp]),
     "g3_timer_end": (C.c_int, [_ctxp, C.POINTER(C.c_float)]),
     "g3_launch_count": (C.c_int64, [_ctxp]),
@@ -144,6 +145,9 @@ class Context:
 
     def set_potrf_block(self, w):
         self._ck(self._lib.g3_set_potrf_block(self._h, int(w)), "g3_set_potrf_block")
+
+    def set_groups(self, n):
+        self._ck(self._lib.g3_set_groups(self._h, int(n)), "g3_set_groups")
 
     def sync(self):
         self._ck(self._lib.g3_sync(self._h), "g3_sync")

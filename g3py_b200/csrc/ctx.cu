@@ -129,6 +129,11 @@ int g3_ctx_create(int device, g3_ctx** out) {
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return -2; }
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
+  cudaEventCreateWithFlags(&c->gev_start, cudaEventDisableTiming);
+  for (int g = 0; g < G3_MAX_GROUPS; ++g) {
+    cudaStreamCreateWithFlags(&c->gstream[g], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->gev_done[g], cudaEventDisableTiming);
+  }
   cudaDriverEntryPointQueryResult q;
   void* fn = nullptr;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
@@ -148,6 +153,11 @@ int g3_ctx_destroy(g3_ctx* ctx) {
   if (ctx->dX) cudaFree(ctx->dX);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->gev_start);
+  for (int g = 0; g < G3_MAX_GROUPS; ++g) {
+    cudaStreamDestroy(ctx->gstream[g]);
+    cudaEventDestroy(ctx->gev_done[g]);
+  }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;

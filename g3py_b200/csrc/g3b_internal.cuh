@@ -13,6 +13,7 @@
 #define G3_BN 128            // GEMM CTA tile cols
 #define G3_BK 16             // doubles per k-tile = 128 bytes = one SWIZZLE_128B row
 #define G3_STAGES 4
+#define G3_MAX_GROUPS 8      // batch groups processed concurrently on their own streams
 
 struct g3_buf {
   void* p = nullptr;
@@ -26,7 +27,10 @@ struct g3_gp_state {
 
 struct g3_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // stream launches are issued to (switched to a group stream inside g3_gp_run)
+  cudaStream_t gstream[G3_MAX_GROUPS] = {};
+  cudaEvent_t gev_start = nullptr, gev_done[G3_MAX_GROUPS] = {};
+  int n_groups = 4;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   int64_t launches = 0;
@@ -135,5 +139,6 @@ struct VjpArgs {
   const double* alpha; long long strideAlpha; const double* cfac;
   double scale;             // result multiplied by scale (0.5 for the GP gradient)
   double* dtheta;           // B x P
+  double* partials;         // optional caller-provided scratch: B x ntiles x P
 };
 int g3_gram_vjp_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const VjpArgs& a, int B);

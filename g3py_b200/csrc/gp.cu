@@ -183,6 +183,8 @@ struct GpBufs {
   double *theta, *delta, *nu, *A, *U, *Dinv, *r, *u, *s, *alpha, *beta, *logdet, *shift, *dmin, *dmean, *cfac, *dtheta,
       *ddelta, *shift2;
   int *info, *status, *bmap;
+  double* partials;            // gram_vjp per-tile partial sums, partials_per_item doubles per batch item
+  size_t partials_per_item;
 };
 
 static int gp_alloc(g3_ctx* ctx, GpBufs& w, int B, int P, int N, int want_grad, int delta_rows) {
@@ -212,8 +214,12 @@ static int gp_alloc(g3_ctx* ctx, GpBufs& w, int B, int P, int N, int want_grad, 
   WS(info, "gp_info", sizeof(int) * B);
   WS(status, "gp_status", sizeof(int) * B);
   WS(bmap, "gp_bmap", sizeof(int) * B);
+  w.partials = nullptr;
+  w.partials_per_item = 0;
   if (want_grad) {
     WS(U, "gp_U", mat);
+    w.partials_per_item = (size_t)T * (T + 1) / 2 * (P > 0 ? P : 1);
+    WS(partials, "gp_vjp_partials", sizeof(double) * (size_t)B * w.partials_per_item);
   } else {
     w.U = nullptr;
   }
@@ -222,9 +228,29 @@ static int gp_alloc(g3_ctx* ctx, GpBufs& w, int B, int P, int N, int want_grad, 
 }
 
 // Stages after the factorisation: solves, beta, and (optionally) the gradient.
-static int gp_after_potrf(g3_ctx* ctx, GpBufs& w) {
+// View of the workspaces for the batch items [b0, b0 + ...): every per-item pointer advanced by b0 items.
+static GpBufs gp_view(const GpBufs& w, int b0, int N, int P, int delta_stride) {
+  const int Np = g3_pad(N), T = Np / TS;
+  GpBufs v = w;
+  const size_t m = (size_t)Np * Np;
+  v.theta += (size_t)b0 * P;
+  if (delta_stride) v.delta += (size_t)b0 * N;
+  v.nu += b0;
+  v.A += m * b0;
+  if (v.U) v.U += m * b0;
+  v.Dinv += (size_t)b0 * T * TS * TS;
+  v.r += (size_t)b0 * Np; v.u += (size_t)b0 * Np; v.s += (size_t)b0 * Np; v.alpha += (size_t)b0 * Np;
+  v.beta += b0; v.logdet += b0; v.shift += b0; v.shift2 += b0; v.dmin += b0; v.dmean += b0; v.cfac += b0;
+  v.dtheta += (size_t)b0 * P;
+  v.ddelta += (size_t)b0 * N;
+  v.info += b0; v.status += b0;
+  if (v.partials) v.partials += (size_t)b0 * v.partials_per_item;
+  return v;
+}
+
+static int gp_after_potrf(g3_ctx* ctx, GpBufs& w, int B) {
   const g3_gp_state& st = ctx->gp;
-  const int B = st.B, N = ctx->N, Np = g3_pad(N), T = Np / TS, P = st.desc.n_theta;
+  const int N = ctx->N, Np = g3_pad(N), T = Np / TS, P = st.desc.n_theta;
   int rc;
   gp_zero_beta_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(w.beta, B);
   G3_LAUNCH_CHECK(ctx);
@@ -248,6 +274,7 @@ static int gp_after_potrf(g3_ctx* ctx, GpBufs& w) {
   v.alpha = w.alpha; v.strideAlpha = Np; v.cfac = w.cfac;
   v.scale = 0.5;
   v.dtheta = w.dtheta;
+  v.partials = w.partials;
   if ((rc = g3_gram_vjp_launch(ctx, st.desc, v, B))) return rc;
   gp_ddelta_kernel<<<dim3((N + 255) / 256, B), 256, 0, ctx->stream>>>(w.alpha, w.cfac, N, Np, w.ddelta);
   G3_LAUNCH_CHECK(ctx);
@@ -255,7 +282,7 @@ static int gp_after_potrf(g3_ctx* ctx, GpBufs& w) {
   return 0;
 }
 
-static int gp_build_and_factor(g3_ctx* ctx, GpBufs& w, const double* shift, const int* bmap, int nb) {
+static int gp_build_and_factor(g3_ctx* ctx, GpBufs& w, int B, const double* shift, const int* bmap, int nb) {
   const g3_gp_state& st = ctx->gp;
   const int N = ctx->N, Np = g3_pad(N);
   GramArgs a;
@@ -267,14 +294,19 @@ static int gp_build_and_factor(g3_ctx* ctx, GpBufs& w, const double* shift, cons
   a.K = w.A; a.ldk = Np; a.strideK = (long long)Np * Np;
   a.status = w.status; a.bmap = bmap;
   int rc;
-  if ((rc = g3_gram_launch(ctx, st.desc, a, bmap ? nb : st.B))) return rc;
-  return g3_potrf_batched(ctx, w.A, Np, st.B, w.Dinv, w.logdet, w.info, bmap, nb, ctx->potrf_w);
+  if ((rc = g3_gram_launch(ctx, st.desc, a, bmap ? nb : B))) return rc;
+  return g3_potrf_batched(ctx, w.A, Np, B, w.Dinv, w.logdet, w.info, bmap, nb, ctx->potrf_w);
 }
 
 extern "C" {
 
 int g3_set_potrf_block(g3_ctx* ctx, int w_outer) {
   ctx->potrf_w = w_outer;
+  return 0;
+}
+
+int g3_set_groups(g3_ctx* ctx, int n_groups) {
+  ctx->n_groups = n_groups < 1 ? 1 : (n_groups > G3_MAX_GROUPS ? G3_MAX_GROUPS : n_groups);
   return 0;
 }
 
@@ -319,8 +351,31 @@ int g3_gp_run(g3_ctx* ctx) {
   gp_prep_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(w.dmin, ctx->jitter_rel, w.shift, w.beta, w.logdet, w.info,
                                                            w.status, B);
   G3_LAUNCH_CHECK(ctx);
-  if ((rc = gp_build_and_factor(ctx, w, w.shift, nullptr, 0))) return rc;
-  return gp_after_potrf(ctx, w);
+  // Independent batch items are processed in groups on separate streams: the serial per-column chain of one
+  // group (update GEMM -> diagonal kernel -> solve GEMM) leaves SMs idle in its kernel tails and during the
+  // 16..64-CTA diagonal kernels; the other groups' kernels fill them.
+  int groups = ctx->n_groups < 1 ? 1 : ctx->n_groups;
+  if (groups > G3_MAX_GROUPS) groups = G3_MAX_GROUPS;
+  while (groups > 1 && B / groups < 8) --groups;
+  if (groups == 1) {
+    if ((rc = gp_build_and_factor(ctx, w, B, w.shift, nullptr, 0))) return rc;
+    return gp_after_potrf(ctx, w, B);
+  }
+  cudaStream_t main_stream = ctx->stream;
+  G3_CUDA(ctx, cudaEventRecord(ctx->gev_start, main_stream));
+  rc = 0;
+  for (int g = 0; g < groups && !rc; ++g) {
+    const int b0 = (int)((long long)B * g / groups), b1 = (int)((long long)B * (g + 1) / groups);
+    GpBufs v = gp_view(w, b0, N, P, st.delta_stride);
+    ctx->stream = ctx->gstream[g];
+    cudaStreamWaitEvent(ctx->stream, ctx->gev_start, 0);
+    rc = gp_build_and_factor(ctx, v, b1 - b0, v.shift, nullptr, 0);
+    if (!rc) rc = gp_after_potrf(ctx, v, b1 - b0);
+    cudaEventRecord(ctx->gev_done[g], ctx->stream);
+    cudaStreamWaitEvent(main_stream, ctx->gev_done[g], 0);
+  }
+  ctx->stream = main_stream;
+  return rc;
 }
 
 int g3_gp_download(g3_ctx* ctx, double* beta, double* logdet, double* dtheta_or_NULL, double* ddelta_or_NULL,
@@ -353,7 +408,7 @@ int g3_gp_download(g3_ctx* ctx, double* beta, double* logdet, double* dtheta_or_
       G3_CUDA(ctx, cudaMemcpyAsync(w.bmap, failed.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->stream));
       gp_zero_sub_kernel<<<(nb + 127) / 128, 128, 0, ctx->stream>>>(nullptr, w.logdet, w.info, w.bmap, nb);
       G3_LAUNCH_CHECK(ctx);
-      if ((rc = gp_build_and_factor(ctx, w, w.shift2, w.bmap, nb))) return rc;
+      if ((rc = gp_build_and_factor(ctx, w, B, w.shift2, w.bmap, nb))) return rc;
       G3_CUDA(ctx, cudaMemcpyAsync(info.data(), w.info, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
       G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       std::vector<int> still;
@@ -376,12 +431,12 @@ int g3_gp_download(g3_ctx* ctx, double* beta, double* logdet, double* dtheta_or_
       G3_CUDA(ctx, cudaMemcpyAsync(w.shift2, sh2.data(), sizeof(double) * B, cudaMemcpyHostToDevice, ctx->stream));
       G3_CUDA(ctx, cudaMemsetAsync(w.logdet, 0, sizeof(double) * B, ctx->stream));
       G3_CUDA(ctx, cudaMemsetAsync(w.info, 0, sizeof(int) * B, ctx->stream));
-      if ((rc = gp_build_and_factor(ctx, w, w.shift2, nullptr, 0))) return rc;
+      if ((rc = gp_build_and_factor(ctx, w, B, w.shift2, nullptr, 0))) return rc;
     }
     // the first pass flagged the failed items' NaN beta/logdet; the repaired values are re-checked
     gp_clear_bits_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(w.status, G3_ST_NONFINITE_RESULT, B);
     G3_LAUNCH_CHECK(ctx);
-    if ((rc = gp_after_potrf(ctx, w))) return rc;
+    if ((rc = gp_after_potrf(ctx, w, B))) return rc;
   }
   G3_CUDA(ctx, cudaMemcpyAsync(beta, w.beta, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream));
   G3_CUDA(ctx, cudaMemcpyAsync(logdet, w.logdet, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream));

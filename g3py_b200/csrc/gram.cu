@@ -564,7 +564,8 @@ int g3_gram_vjp_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const VjpArgs& a
   if (rc) return rc;
   const int tr = (a.n1 + TS - 1) / TS, tc = (a.n2 + TS - 1) / TS;
   const long long ntiles = a.lower_only ? (long long)tr * (tr + 1) / 2 : (long long)tr * tc;
-  double* partials = (double*)g3_ws(ctx, "vjp_partials", sizeof(double) * (size_t)B * ntiles * (a.P > 0 ? a.P : 1));
+  double* partials = a.partials ? a.partials
+                                : (double*)g3_ws(ctx, "vjp_partials", sizeof(double) * (size_t)B * ntiles * (a.P > 0 ? a.P : 1));
   if (!partials) return -2;
   const size_t smem = sizeof(double) * (2 * TS * a.D + G3_MAX_THETA + 2 * TS + (size_t)a.P * 256);
   static bool attr = false;

@@ -95,6 +95,9 @@ int g3_set_jitter(g3_ctx* ctx, double jitter_rel, int max_tries);
 /* Blocking of the factorisation: tile columns (of 128) per right-looking outer block; a value
  * >= N/128 makes it fully left-looking (default for the batched path). */
 int g3_set_potrf_block(g3_ctx* ctx, int w_outer);
+/* Number of batch groups g3_gp_run processes concurrently on separate streams (default 4, max 8;
+ * 1 = a single stream, which is what the per-kernel timers of g3_prof_* need). */
+int g3_set_groups(g3_ctx* ctx, int n_groups);
 
 /* Device timing on the context's stream (CUDA events; used by bench.py). */
 int g3_timer_begin(g3_ctx* ctx);
