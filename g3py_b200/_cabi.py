@@ -53,6 +53,11 @@ SIGNATURES = {
     "g3_debug_read": (C.c_int, [_ctxp, C.c_char_p, C.c_void_p, C.c_size_t]),
     "g3_debug_potrf_stress": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, C.c_int, _ip, _dp]),
     "g3_debug_gemm_stress": (C.c_int, [_ctxp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
+    "g3_set_stream": (C.c_int, [_ctxp, C.c_void_p]),
+    "g3_dev_gram_block": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                    C.c_void_p, C.c_longlong]),
+    "g3_dev_potrf_panel": (C.c_int, [_ctxp, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "g3_dev_syrk_panel": (C.c_int, [_ctxp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "g3_set_data": (C.c_int, [_ctxp, _dp, C.c_int, C.c_int]),
     "g3_gram": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _ip]),
     "g3_gram_vjp": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp]),
@@ -148,6 +153,23 @@ class Context:
 
     def set_groups(self, n):
         self._ck(self._lib.g3_set_groups(self._h, int(n)), "g3_set_groups")
+
+    # ---- device-pointer building blocks (multi-GPU Cholesky); pointers are integers (tensor.data_ptr())
+    def set_stream(self, cuda_stream):
+        self._ck(self._lib.g3_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None), "g3_set_stream")
+
+    def dev_gram_block(self, desc, theta, row0, col0, rows, cols, diag_shift, out_ptr, ld):
+        theta = _f64(theta).ravel()
+        self._ck(self._lib.g3_dev_gram_block(self._h, C.byref(desc), _d(theta), row0, col0, rows, cols, float(diag_shift),
+                                             C.c_void_p(out_ptr), ld), "g3_dev_gram_block")
+
+    def dev_potrf_panel(self, p_ptr, rows, nb, logdet_ptr, info_ptr):
+        self._ck(self._lib.g3_dev_potrf_panel(self._h, C.c_void_p(p_ptr), rows, nb, C.c_void_p(logdet_ptr),
+                                              C.c_void_p(info_ptr)), "g3_dev_potrf_panel")
+
+    def dev_syrk_panel(self, p_ptr, rows_p, nb, row_off, d_ptr, rows_d):
+        self._ck(self._lib.g3_dev_syrk_panel(self._h, C.c_void_p(p_ptr), rows_p, nb, row_off, C.c_void_p(d_ptr), rows_d),
+                 "g3_dev_syrk_panel")
 
     def sync(self):
         self._ck(self._lib.g3_sync(self._h), "g3_sync")

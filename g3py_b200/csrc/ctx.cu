@@ -127,6 +127,7 @@ int g3_ctx_create(int device, g3_ctx** out) {
   if (prop.major != 10) { delete c; return -4; }  // sm_100a only
   c->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return -2; }
+  c->own_stream = c->stream;
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
   cudaEventCreateWithFlags(&c->gev_start, cudaEventDisableTiming);
@@ -158,7 +159,7 @@ int g3_ctx_destroy(g3_ctx* ctx) {
     cudaStreamDestroy(ctx->gstream[g]);
     cudaEventDestroy(ctx->gev_done[g]);
   }
-  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return 0;
 }
@@ -168,6 +169,13 @@ const char* g3_last_error(g3_ctx* ctx) { return ctx ? ctx->err.c_str() : "null c
 int g3_sync(g3_ctx* ctx) {
   G3_CUDA(ctx, cudaSetDevice(ctx->device));
   G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int g3_set_stream(g3_ctx* ctx, void* stream_or_NULL) {
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = stream_or_NULL ? (cudaStream_t)stream_or_NULL : ctx->own_stream;
   return 0;
 }
 

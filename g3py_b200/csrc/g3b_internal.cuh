@@ -28,6 +28,7 @@ struct g3_gp_state {
 struct g3_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;       // stream launches are issued to (switched to a group stream inside g3_gp_run)
+  cudaStream_t own_stream = nullptr;   // the stream created by g3_ctx_create (g3_set_stream can substitute another)
   cudaStream_t gstream[G3_MAX_GROUPS] = {};
   cudaEvent_t gev_start = nullptr, gev_done[G3_MAX_GROUPS] = {};
   int n_groups = 4;
@@ -105,6 +106,10 @@ int g3_gemm_launch(g3_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, 
 // Dinv: [B][T][128][128] inverses of the diagonal blocks of L (lower, explicit zeros above).
 int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, double* logdet, int* info,
                      const int* bmap, int nb, int w_outer);
+// Tall panel (rows x nb, ld = nb, rows/nb multiples of 128): factor the top nb x nb block and solve the rows below.
+int g3_potrf_panel(g3_ctx* ctx, double* P, int rows, int nb, double* Dinv, double* logdet, int* info);
+// D[x][y] -= sum_k P[row_off + x][k] P[row_off + y][k]   (D: rowsD x nb, ld = nb; P: rowsP x nb)
+int g3_syrk_panel(g3_ctx* ctx, const double* P, int rowsP, int nb, int row_off, double* D, int rowsD);
 int g3_trtri_batched(g3_ctx* ctx, const double* L, double* U, int Np, int B, const double* Dinv);
 int g3_lauum_batched(g3_ctx* ctx, const double* U, double* Kinv, int Np, int B);
 int g3_trsv_fwd(g3_ctx* ctx, const double* L, const double* Dinv, double* r, double* u, double* beta,
@@ -118,6 +123,7 @@ struct GramArgs {
   int same;                 // x1 is x2 (Noise/WN -> var*I)
   int lower_only;           // write only tiles with row-tile >= col-tile (same==1)
   int pad_identity;         // out is Np1 x Np2 padded; write identity on the padding diagonal
+  int diag_off;             // global row - global col of element (0,0) of this block: diagonal is gi + diag_off == gj
   int skip_process_noise;   // noise=False selectors: the auto-added Noise leaf evaluates to 0 (elliptical.py:73-74)
   const double* theta; int P;       // B x P natural-space hypers
   const double* diag_shift;         // optional B: added on the diagonal (tt_to_cov / jitter), may be null

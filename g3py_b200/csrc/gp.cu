@@ -869,6 +869,48 @@ int g3_gp_posterior(g3_ctx* ctx, const g3_kernel_desc* desc, const double* Xs, i
   return 0;
 }
 
+// ---- device-pointer entry points for the multi-GPU block-cyclic Cholesky (g3py_b200/dist_potrf.py) ---------
+int g3_dev_gram_block(g3_ctx* ctx, const g3_kernel_desc* desc, const double* theta, int row0, int col0, int rows,
+                      int cols, double diag_shift, double* out, long long ld) {
+  if (!ctx || !desc || !out || rows <= 0 || cols <= 0 || row0 < 0 || col0 < 0) return g3_fail_msg(ctx, "g3_dev_gram_block: bad arguments");
+  if (!ctx->dX) return g3_fail_msg(ctx, "g3_dev_gram_block: call g3_set_data first");
+  if (rows % TS || cols % TS) return g3_fail_msg(ctx, "g3_dev_gram_block: rows/cols must be multiples of 128");
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int N = ctx->N, P = desc->n_theta;
+  int rc = g3_check_desc(ctx, *desc, ctx->D);
+  if (rc) return rc;
+  double* dth = (double*)g3_ws(ctx, "blk_theta", sizeof(double) * ((P > 0 ? P : 1) + 1));
+  if (!dth) return -2;
+  std::vector<double> h(P + 1);
+  for (int p = 0; p < P; ++p) h[p] = theta[p];
+  h[P] = diag_shift;
+  G3_CUDA(ctx, cudaMemcpyAsync(dth, h.data(), sizeof(double) * (P + 1), cudaMemcpyHostToDevice, ctx->stream));
+  if (N % TS) return g3_fail_msg(ctx, "g3_dev_gram_block: N must be a multiple of 128 on the multi-GPU path");
+  if (row0 + rows > N || col0 + cols > N) return g3_fail_msg(ctx, "g3_dev_gram_block: block outside the matrix");
+  GramArgs a;
+  memset(&a, 0, sizeof a);
+  a.X1 = ctx->dX + (size_t)row0 * ctx->D; a.X2 = ctx->dX + (size_t)col0 * ctx->D;
+  a.n1 = rows; a.n2 = cols;
+  a.D = ctx->D; a.same = 1; a.lower_only = 0; a.pad_identity = 0; a.diag_off = row0 - col0;
+  a.theta = dth; a.P = P; a.diag_shift = dth + P;
+  a.K = out; a.ldk = ld; a.strideK = 0;
+  return g3_gram_launch(ctx, *desc, a, 1);
+}
+
+int g3_dev_potrf_panel(g3_ctx* ctx, double* P, int rows, int nb, double* logdet_dev, int* info_dev) {
+  if (!ctx || !P || !logdet_dev || !info_dev) return g3_fail_msg(ctx, "g3_dev_potrf_panel: bad arguments");
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  double* Dinv = (double*)g3_ws(ctx, "blk_Dinv", sizeof(double) * (size_t)(nb / TS) * TS * TS);
+  if (!Dinv) return -2;
+  return g3_potrf_panel(ctx, P, rows, nb, Dinv, logdet_dev, info_dev);
+}
+
+int g3_dev_syrk_panel(g3_ctx* ctx, const double* P, int rowsP, int nb, int row_off, double* D, int rowsD) {
+  if (!ctx || !P || !D) return g3_fail_msg(ctx, "g3_dev_syrk_panel: bad arguments");
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  return g3_syrk_panel(ctx, P, rowsP, nb, row_off, D, rowsD);
+}
+
 // ---- big single-matrix Cholesky (BASELINE metric 2) -------------------------------------------
 int g3_gram_potrf_device(g3_ctx* ctx, const g3_kernel_desc* desc, const double* theta, double* logdet, int* info,
                          float* ms_gram, float* ms_potrf) {

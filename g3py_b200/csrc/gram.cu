@@ -170,7 +170,7 @@ gram_fwd_kernel(const __grid_constant__ g3_kernel_desc desc, const GramArgs a, i
     const int gi = r0 + rl;
     bool sd[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) sd[e] = a.same && (gi == c0 + cc[e]);
+    for (int e = 0; e < 4; ++e) sd[e] = a.same && (gi + a.diag_off == c0 + cc[e]);
     // shift-register evaluation stack (depth 6) for 4 columns
     double s0[4], s1[4], s2[4], s3[4], s4[4], s5[4];
 #pragma unroll
@@ -199,7 +199,7 @@ gram_fwd_kernel(const __grid_constant__ g3_kernel_desc desc, const GramArgs a, i
       const int gj = c0 + cc[e];
       double val = scrub(s0[e], flag);
       if (sd[e]) val += shift;
-      if (gi >= a.n1 || gj >= a.n2) val = (a.pad_identity && gi == gj) ? 1.0 : 0.0;
+      if (gi >= a.n1 || gj >= a.n2) val = (a.pad_identity && gi + a.diag_off == gj) ? 1.0 : 0.0;
       v[e] = val;
     }
     double* rowp = Kb + (long long)gi * a.ldk + c0;

@@ -247,6 +247,66 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
   return 0;
 }
 
+int g3_potrf_panel(g3_ctx* ctx, double* P, int rows, int nb, double* Dinv, double* logdet, int* info) {
+  if (rows % TS || nb % TS || rows < nb) return g3_fail_msg(ctx, "potrf_panel: rows/nb must be multiples of 128, rows >= nb");
+  const int Tr = rows / TS, w = nb / TS;
+  if (!ctx->diag_ready) {
+    G3_CUDA(ctx, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem));
+    ctx->diag_ready = true;
+  }
+  CUtensorMap tmA, tmB, tmD;
+  int rc;
+  if ((rc = g3_make_tmap(ctx, &tmA, P, nb, rows, 1, nb, (uint64_t)rows * nb, G3_BM))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmB, P, nb, rows, 1, nb, (uint64_t)rows * nb, G3_BN))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmD, Dinv, TS, (uint64_t)w * TS, 1, TS, (uint64_t)w * TS * TS, G3_BN))) return rc;
+  for (int j = 0; j < w; ++j) {
+    if (j > 0) {  // left-looking inside the panel
+      GemmArgs g = gemm_zero();
+      g.D = P; g.ldd = nb; g.strideD = 0;
+      g.mode = 0; g.ntx = Tr - j; g.nty = 1;
+      g.d_r0 = j * TS; g.d_c0 = j * TS;
+      g.a_r0 = j * TS; g.a_rx = TS;
+      g.b_r0 = j * TS;
+      g.ka0 = 0; g.kb0 = 0; g.kl0 = j * TS;
+      g.alpha = -1.0; g.beta = 1.0;
+      if ((rc = g3_gemm_launch(ctx, tmA, tmB, g, 1))) return rc;
+    }
+    g3_prof_begin(ctx, G3_PROF_DIAG);
+    potrf_diag_kernel<<<1, 256, kDiagSmem, ctx->stream>>>(P, nb, 0, j, Dinv, w, nullptr, logdet, info, nullptr);
+    g3_prof_end(ctx);
+    G3_LAUNCH_CHECK(ctx);
+    if (Tr - j - 1 > 0) {
+      GemmArgs g = gemm_zero();
+      g.D = P; g.ldd = nb; g.strideD = 0;
+      g.mode = 0; g.ntx = Tr - j - 1; g.nty = 1;
+      g.d_r0 = (j + 1) * TS; g.d_c0 = j * TS;
+      g.a_r0 = (j + 1) * TS; g.a_rx = TS; g.ka0 = j * TS;
+      g.b_r0 = j * TS; g.kb0 = 0;
+      g.kl0 = TS;
+      g.alpha = 1.0; g.beta = 0.0;
+      if ((rc = g3_gemm_launch(ctx, tmA, tmD, g, 1))) return rc;
+    }
+  }
+  return 0;
+}
+
+int g3_syrk_panel(g3_ctx* ctx, const double* P, int rowsP, int nb, int row_off, double* D, int rowsD) {
+  if (rowsP % TS || nb % TS || rowsD % TS || row_off % TS || row_off + rowsD > rowsP)
+    return g3_fail_msg(ctx, "syrk_panel: bad geometry");
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = g3_make_tmap(ctx, &tmA, P, nb, rowsP, 1, nb, (uint64_t)rowsP * nb, G3_BM))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmB, P, nb, rowsP, 1, nb, (uint64_t)rowsP * nb, G3_BN))) return rc;
+  GemmArgs g = gemm_zero();
+  g.D = D; g.ldd = nb; g.strideD = 0;
+  g.mode = 0; g.ntx = rowsD / TS; g.nty = nb / TS;
+  g.a_r0 = row_off; g.a_rx = TS;
+  g.b_r0 = row_off; g.b_ry = TS;
+  g.kl0 = nb;
+  g.alpha = -1.0; g.beta = 1.0;
+  return g3_gemm_launch(ctx, tmA, tmB, g, 1);
+}
+
 // U = L^-T (row-major upper).  Diagonal tiles of U are Linv_jj^T, rebuilt here from Dinv.
 namespace {
 __global__ void __launch_bounds__(256)

@@ -1,0 +1,200 @@
+"""Exact GP too large / too slow for one GPU: block-cyclic Cholesky across the GPUs of one node.
+
+Not in the reference (its only parallelism is `multiprocessing.Pool.map` over chains,
+g3py/processes/stochastic.py:775-783); this is SURVEY §2.2 K17 / §8e.
+
+Layout.  2-D block-cyclic with block nb (default 1024 = 8 tile columns) on a 1 x G process grid: panel J
+(columns [J nb, (J+1) nb)) lives on rank J mod G.  Only the lower trapezoid of each panel is stored, as its
+own contiguous tall matrix (rows J nb .. N, leading dimension nb), so (a) a rank holds N^2/(2G) doubles,
+(b) every panel is already the K-contiguous operand the fp64 GEMM wants and is broadcast in place (no
+packing), (c) each rank generates its own panels from the replicated X (MBs) - K never crosses a link.
+NVSwitch gives every GPU full bandwidth to every peer, so the column broadcast of a 1 x G grid (N^2/2
+doubles received per rank in total, ~0.2 s at N = 131072) hides completely under the trailing update; the
+row broadcasts of a Pr > 1 grid would only add latency.
+
+Schedule (right-looking between panels, left-looking inside one, with look-ahead):
+    owner(J+1): update panel J+1 with panel J -> factor panel J+1 -> start its broadcast (async)
+    everyone  : update the remaining local panels with panel J while panel J+1 is in flight
+The panel primitives are libg3b.so kernels on device pointers (`g3_dev_*`); torch.distributed (NCCL) is
+used only for the broadcast and torch only for device memory and streams.
+"""
+import math
+
+import numpy as np
+
+
+def panel_owner(J, world):
+    return J % world
+
+
+def local_panels(n_panels, rank, world):
+    return list(range(rank, n_panels, world))
+
+
+class LibBackend:
+    """Panel primitives through the C ABI on torch-owned device memory."""
+
+    def __init__(self, ctx, desc, theta, diag_shift, torch, stream):
+        self.ctx, self.desc, self.theta, self.shift, self.torch = ctx, desc, np.asarray(theta, dtype=np.float64), diag_shift, torch
+        self.stream = stream
+        ctx.set_stream(stream.cuda_stream)
+
+    def alloc(self, n):
+        return self.torch.empty(n, dtype=self.torch.float64, device="cuda")
+
+    def scalars(self):
+        return (self.torch.zeros(1, dtype=self.torch.float64, device="cuda"),
+                self.torch.zeros(1, dtype=self.torch.int32, device="cuda"))
+
+    def gram(self, out, row0, col0, rows, cols):
+        self.ctx.dev_gram_block(self.desc, self.theta, row0, col0, rows, cols, self.shift, out.data_ptr(), cols)
+
+    def factor(self, P, rows, nb, logdet, info):
+        self.ctx.dev_potrf_panel(P.data_ptr(), rows, nb, logdet.data_ptr(), info.data_ptr())
+
+    def update(self, P, rows_p, nb, row_off, D, rows_d):
+        self.ctx.dev_syrk_panel(P.data_ptr(), rows_p, nb, row_off, D.data_ptr(), rows_d)
+
+    def close(self):
+        self.ctx.set_stream(0)
+
+
+class DistCholesky:
+    """Block-cyclic lower Cholesky of K = cov(X) (+ shift on the diagonal) over `world` ranks.
+
+    backend: object with alloc / scalars / gram / factor / update (LibBackend on GPUs; the CPU tests pass a
+    NumPy double).  dist: torch.distributed module or None (single rank)."""
+
+    def __init__(self, N, nb, rank, world, backend, dist=None, lookahead=True):
+        if N % nb or nb % 128:
+            raise ValueError("N must be a multiple of nb, nb a multiple of 128")
+        self.N, self.nb, self.rank, self.world = N, nb, rank, world
+        self.nP = N // nb
+        self.be, self.dist, self.lookahead = backend, dist, lookahead
+        self.mine = local_panels(self.nP, rank, world)
+        self.rows = {J: N - J * nb for J in range(self.nP)}
+        sizes = [self.rows[J] * nb for J in self.mine]
+        self.store = backend.alloc(max(sum(sizes), 1))
+        self.off = {}
+        o = 0
+        for J, sz in zip(self.mine, sizes):
+            self.off[J] = o
+            o += sz
+        self.pbuf = [backend.alloc(N * nb), backend.alloc(N * nb)] if world > 1 else None
+        self.logdet, self.info = backend.scalars()
+
+    def panel(self, J):
+        return self.store[self.off[J]: self.off[J] + self.rows[J] * self.nb]
+
+    def local_bytes(self):
+        return 8 * sum(self.rows[J] * self.nb for J in self.mine)
+
+    def build(self):
+        """Each rank generates its own panels of K from the replicated X."""
+        for J in self.mine:
+            self.be.gram(self.panel(J), J * self.nb, J * self.nb, self.rows[J], self.nb)
+
+    def _bcast(self, J):
+        o = panel_owner(J, self.world)
+        if self.world == 1:
+            return self.panel(J), None
+        t = self.panel(J) if self.rank == o else self.pbuf[J % 2][: self.rows[J] * self.nb]
+        work = self.dist.broadcast(t, src=o, async_op=True)
+        return t, work
+
+    def _update(self, PJ, J, Jp):
+        """local panel Jp (> J) -= PJ[rows of Jp] PJ[cols of Jp]^T"""
+        self.be.update(PJ, self.rows[J], self.nb, (Jp - J) * self.nb, self.panel(Jp), self.rows[Jp])
+
+    def factor(self):
+        nb, nP, me = self.nb, self.nP, self.rank
+        if panel_owner(0, self.world) == me:
+            self.be.factor(self.panel(0), self.rows[0], nb, self.logdet, self.info)
+        cur = self._bcast(0)
+        for J in range(nP):
+            PJ, work = cur
+            if work is not None:
+                work.wait()
+            nxt = None
+            done_early = None
+            if J + 1 < nP:
+                if panel_owner(J + 1, self.world) == me:
+                    if self.lookahead or self.world == 1:
+                        self._update(PJ, J, J + 1)
+                        done_early = J + 1
+                        self.be.factor(self.panel(J + 1), self.rows[J + 1], nb, self.logdet, self.info)
+                if self.lookahead:
+                    nxt = self._bcast(J + 1)
+            for Jp in self.mine:
+                if Jp > J and Jp != done_early:
+                    self._update(PJ, J, Jp)
+            if J + 1 < nP and not self.lookahead:
+                if panel_owner(J + 1, self.world) == me and self.world > 1:
+                    self.be.factor(self.panel(J + 1), self.rows[J + 1], nb, self.logdet, self.info)
+                nxt = self._bcast(J + 1)
+            cur = nxt
+        return self
+
+    def flops(self):
+        return float(self.N) ** 3 / 3.0
+
+
+def run_dist_cholesky(N, D=3, nb=1024, theta=None, lookahead=True, seed=5, verify=False):
+    """One timed distributed factorisation of the SE(+noise) Gram of the config-5 inputs.  Launch one
+    process per GPU (torchrun); returns a dict on every rank (times are max over ranks)."""
+    import os
+    import torch
+    import torch.distributed as dist
+    import g3py_b200 as g3
+    from g3py_b200 import workloads
+    from g3py_b200.processes import get_context
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    X, y = workloads.c5_inputs(N)
+    k = g3.SE(X) + g3.KernelNoise(name="Noise")
+    reg = g3.Registry()
+    k.check_dims(X)
+    k.check_hypers("", reg)
+    b = g3.DescBuilder(D)
+    k.compile(b)
+    desc = b.finish()
+    th = np.array([1.0, 1.0, 1.0, 1.0, 0.01]) if theta is None else np.asarray(theta, dtype=np.float64)
+    ctx = get_context(local)
+    ctx.set_data(X)
+    ctx._data_tag = None
+    stream = torch.cuda.Stream()
+    be = LibBackend(ctx, desc, th, 0.0, torch, stream)
+    out = {}
+    try:
+        with torch.cuda.stream(stream):
+            ch = DistCholesky(N, nb, rank, world, be, dist if world > 1 else None, lookahead=lookahead)
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e[0].record()
+            ch.build()
+            e[1].record()
+            ch.factor()
+            e[2].record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])], dtype=torch.float64, device="cuda")
+            ld = ch.logdet.clone()
+            info = ch.info.clone().to(torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dist.all_reduce(ld, op=dist.ReduceOp.SUM)
+                dist.all_reduce(info, op=dist.ReduceOp.MAX)
+            ms_gram, ms_potrf = (float(v) for v in t.cpu())
+            out = {"N": N, "nb": nb, "n_gpus": world, "ms_gram": ms_gram, "ms_potrf": ms_potrf,
+                   "tflops": ch.flops() / (ms_potrf * 1e-3) / 1e12, "logdet": float(ld.item()), "info": int(info.item()),
+                   "local_gib": ch.local_bytes() / 2 ** 30, "lookahead": bool(lookahead)}
+            if verify:
+                out["panels"] = {J: ch.panel(J).cpu().numpy().reshape(ch.rows[J], nb) for J in ch.mine}
+    finally:
+        be.close()
+    return out

@@ -187,6 +187,22 @@ int g3_gp_posterior(g3_ctx* ctx, const g3_kernel_desc* desc, const double* Xs, i
                     double* mean_out, double* var_out, double* cov_out_or_NULL,
                     double* beta_out_or_NULL, int* status);
 
+/* ---- multi-GPU exact GP: device-pointer building blocks ---------------------------------------
+ * Used by g3py_b200/dist_potrf.py (2-D block-cyclic Cholesky on a 1 x G process grid, panel
+ * broadcast over NCCL).  Not in the reference.  All pointers below are DEVICE
+ * pointers owned by the caller (torch tensors); work is issued on the context's stream, which
+ * g3_set_stream can point at the caller's stream so that it orders with torch.distributed.
+ *   g3_dev_gram_block : K[row0:row0+rows, col0:col0+cols] of cov(X) for the resident X (tt_to_cov
+ *                       shift `diag_shift` and Noise on the global diagonal), into out (leading dim ld)
+ *   g3_dev_potrf_panel: P (rows x nb, ld = nb): Cholesky of the top nb x nb block, rows below solved;
+ *                       sum(log diag) is ADDED to *logdet_dev, first bad pivot (+1) stored in *info_dev
+ *   g3_dev_syrk_panel : D[x][y] -= sum_k P[row_off+x][k] * P[row_off+y][k]   (D rowsD x nb, ld = nb) */
+int g3_set_stream(g3_ctx* ctx, void* cuda_stream_or_NULL);
+int g3_dev_gram_block(g3_ctx* ctx, const g3_kernel_desc* desc, const double* theta, int row0, int col0,
+                      int rows, int cols, double diag_shift, double* out_dev, long long ld);
+int g3_dev_potrf_panel(g3_ctx* ctx, double* P_dev, int rows, int nb, double* logdet_dev, int* info_dev);
+int g3_dev_syrk_panel(g3_ctx* ctx, const double* P_dev, int rowsP, int nb, int row_off, double* D_dev, int rowsD);
+
 /* ---- stand-alone Cholesky benchmark entry (BASELINE metric 2) --------------------------
  * Builds K = cov(X; theta) (+ tt_to_cov) for the resident data directly in device memory
  * (lower triangle only) and factors it in place; nothing N x N crosses the host boundary.

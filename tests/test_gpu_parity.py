@@ -368,3 +368,21 @@ def test_repeat_runs_bitwise_identical(ctx):
         lp, g, info = gp.logp_dlogp_batch(Theta)
         res.append(np.concatenate([lp, g.ravel()]))
     assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2])
+
+
+def test_block_cyclic_cholesky_single_gpu():
+    """The multi-GPU Cholesky driver with world=1 (device panel primitives g3_dev_*): factor == NumPy's."""
+    from g3py_b200.dist_potrf import run_dist_cholesky
+    from g3py_b200 import workloads
+    N, nb = 2048, 256
+    r = run_dist_cholesky(N, nb=nb, verify=True)
+    X, y = workloads.c5_inputs(N)
+    d = ((X[:, None, :] - X[None, :, :]) ** 2 * 0.5).sum(-1)
+    L = np.linalg.cholesky(np.exp(-d) + 0.01 * np.eye(N))
+    assert r["info"] == 0
+    assert abs(r["logdet"] - np.log(np.diag(L)).sum()) <= 1e-9 * abs(np.log(np.diag(L)).sum())
+    for J, P in r["panels"].items():
+        want = L[J * nb:, J * nb:(J + 1) * nb]
+        assert np.abs(np.tril(P[:nb]) - want[:nb]).max() < 1e-11
+        if P.shape[0] > nb:
+            assert np.abs(P[nb:] - want[nb:]).max() < 1e-11

@@ -261,3 +261,63 @@ def test_theta_sharding_gloo_world2():
                            capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARD_OK" in r.stdout
+
+
+_DIST_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["G3_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from g3py_b200.dist_potrf import DistCholesky, panel_owner
+world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+if world > 1:
+    dist.init_process_group("gloo")
+N, nb = 1536, 256
+rng = np.random.default_rng(0)
+A = rng.standard_normal((N, N + 8)); K = A @ A.T / N + np.eye(N)
+Lref = np.linalg.cholesky(K)
+
+class NumpyBackend:                       # CPU double of the three g3_dev_* panel primitives
+    def alloc(self, n): return torch.zeros(n, dtype=torch.float64)
+    def scalars(self): return torch.zeros(1, dtype=torch.float64), torch.zeros(1, dtype=torch.int32)
+    def gram(self, out, row0, col0, rows, cols): out.copy_(torch.from_numpy(K[row0:row0 + rows, col0:col0 + cols].copy()).reshape(-1))
+    def factor(self, P, rows, nb, logdet, info):
+        M = P.numpy().reshape(rows, nb)
+        L = np.linalg.cholesky(M[:nb]); M[:nb] = L
+        if rows > nb: M[nb:] = np.linalg.solve(L, M[nb:].T).T
+        logdet += float(np.log(np.diag(L)).sum())
+    def update(self, P, rows_p, nb, row_off, D, rows_d):
+        Pm = P.numpy().reshape(rows_p, nb); Dm = D.numpy().reshape(rows_d, nb)
+        Dm -= Pm[row_off:row_off + rows_d] @ Pm[row_off:row_off + nb].T
+
+for la in (True, False):
+    ch = DistCholesky(N, nb, rank, world, NumpyBackend(), dist if world > 1 else None, lookahead=la)
+    ch.build(); ch.factor()
+    for J in ch.mine:
+        got = ch.panel(J).numpy().reshape(ch.rows[J], nb)
+        want = Lref[J * nb:, J * nb:(J + 1) * nb]
+        err = np.abs(np.tril(got[:nb]) - want[:nb]).max() + (np.abs(got[nb:] - want[nb:]).max() if ch.rows[J] > nb else 0.0)
+        assert err < 1e-10, (la, J, err)
+    ld = ch.logdet.clone()
+    if world > 1: dist.all_reduce(ld)
+    assert abs(ld.item() - np.log(np.diag(Lref)).sum()) < 1e-9
+    assert ch.local_bytes() == 8 * sum((N - J * nb) * nb for J in range(rank, N // nb, world))
+if rank == 0: print("DIST_OK", flush=True)
+if world > 1: dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_block_cyclic_cholesky_schedule(world):
+    """Schedule / indexing / look-ahead of the multi-GPU Cholesky with NumPy panel primitives over gloo."""
+    env = dict(os.environ, G3_ROOT=ROOT, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "w.py")
+        open(f, "w").write(_DIST_WORKER)
+        if world == 1:
+            cmd = [sys.executable, f]
+        else:
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world,
+                   "--master-addr", "127.0.0.1", "--master-port", str(29520 + world), f]
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "DIST_OK" in r.stdout
