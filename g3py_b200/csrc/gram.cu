@@ -12,6 +12,7 @@
 //            memory; CTA partials are reduced in a fixed order (deterministic).
 #include "g3b_internal.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -536,6 +537,17 @@ int g3_check_desc(g3_ctx* ctx, const g3_kernel_desc& d, int D) {
   return 0;
 }
 
+// fast paths for additive trees on <= 4 input columns (gram_add.cu)
+bool g3_desc_is_additive(const g3_kernel_desc& d);
+void g3_gram_fwd_add_launch(const g3_kernel_desc& desc, const GramArgs& a, int ntx, dim3 grid, cudaStream_t s);
+int g3_gram_vjp_add_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const VjpArgs& a, int ntx, double* partials,
+                           int ntiles, dim3 grid, cudaStream_t s);
+static bool use_fast_path(const g3_kernel_desc& desc, int D) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("G3_NO_FAST"); off = (e && e[0] == '1') ? 1 : 0; }
+  return !off && D <= 4 && g3_desc_is_additive(desc);
+}
+
 int g3_gram_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const GramArgs& a, int B) {
   int rc = g3_check_desc(ctx, desc, a.D);
   if (rc) return rc;
@@ -543,7 +555,10 @@ int g3_gram_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const GramArgs& a, i
   const long long ntiles = a.lower_only ? (long long)tr * (tr + 1) / 2 : (long long)tr * tc;
   const size_t smem = sizeof(double) * (2 * TS * a.D + G3_MAX_THETA);
   g3_prof_begin(ctx, G3_PROF_GRAM);
-  gram_fwd_kernel<<<dim3((unsigned)ntiles, B), 256, smem, ctx->stream>>>(desc, a, tr);
+  if (use_fast_path(desc, a.D))
+    g3_gram_fwd_add_launch(desc, a, tr, dim3((unsigned)ntiles, B), ctx->stream);
+  else
+    gram_fwd_kernel<<<dim3((unsigned)ntiles, B), 256, smem, ctx->stream>>>(desc, a, tr);
   g3_prof_end(ctx);
   G3_LAUNCH_CHECK(ctx);
   return 0;
@@ -575,7 +590,11 @@ int g3_gram_vjp_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const VjpArgs& a
   }
   if (a.P == 0) return 0;
   g3_prof_begin(ctx, G3_PROF_VJP);
-  gram_vjp_kernel<<<dim3((unsigned)ntiles, B), 256, smem, ctx->stream>>>(desc, a, tr, partials, (int)ntiles);
+  if (use_fast_path(desc, a.D)) {
+    if ((rc = g3_gram_vjp_add_launch(ctx, desc, a, tr, partials, (int)ntiles, dim3((unsigned)ntiles, B), ctx->stream))) return rc;
+  } else {
+    gram_vjp_kernel<<<dim3((unsigned)ntiles, B), 256, smem, ctx->stream>>>(desc, a, tr, partials, (int)ntiles);
+  }
   g3_prof_end(ctx);
   G3_LAUNCH_CHECK(ctx);
   vjp_reduce_kernel<<<dim3(a.P, B), 256, 0, ctx->stream>>>(partials, (int)ntiles, a.P, a.scale, a.dtheta);

@@ -627,6 +627,59 @@ class EllipticalProcess(StochasticProcess):
         return params
 
 
+    # ---- batched drivers: the loops of stochastic.py:566-800 on top of logp_batch ---------------
+    def find_MAP_multistart(self, starts, display=False, **kwargs):
+        """Multi-start MAP: every start is scored in ONE batched launch, the best few are polished by BFGS
+        (stochastic.py:606-613 scores the list of starts one at a time)."""
+        S = np.array([self.dict_to_array(s) if isinstance(s, dict) else np.asarray(s, dtype=np.float64) for s in starts])
+        lp = self.logp_batch(S)
+        order = np.argsort(-lp)
+        best, best_lp = None, -np.inf
+        for i in order[:max(1, min(3, len(order)))]:
+            p = self.find_MAP(start=S[i], display=display, **kwargs)
+            v = self.logp(p)
+            if v > best_lp:
+                best, best_lp = p, v
+        return best
+
+    def sample_hypers(self, start=None, samples=200, chains=None, noise_mult=0.1, noise_sum=0.01, seed=None, a=2.0):
+        """Affine-invariant ensemble sampler (Goodman & Weare stretch move, what emcee's EnsembleSampler runs for
+        bayesian/average.py:20-54) with each half-ensemble proposal evaluated as one `logp_batch` call instead of
+        chains/2 sequential Theano calls.  Returns (chain [samples, chains, ndim], logp [samples, chains])."""
+        rng = np.random.default_rng(seed)
+        nd = self.ndim
+        chains = 2 * nd if chains is None else int(chains)
+        chains += chains % 2
+        x0 = self.dict_to_array(self.params if start is None else start) if not isinstance(start, np.ndarray) else start
+        # stochastic.py:745-752: walkers start in a small ball around the start point
+        pos = x0[None, :] * (1.0 + noise_mult * rng.standard_normal((chains, nd))) + noise_sum * rng.standard_normal((chains, nd))
+        lp = self.logp_batch(pos)
+        out = np.empty((samples, chains, nd))
+        out_lp = np.empty((samples, chains))
+        half = chains // 2
+        for it in range(samples):
+            for first in (True, False):
+                S = slice(0, half) if first else slice(half, chains)
+                C = slice(half, chains) if first else slice(0, half)
+                z = ((a - 1.0) * rng.random(half) + 1.0) ** 2 / a
+                partner = pos[C][rng.integers(0, half, size=half)]
+                prop = partner + z[:, None] * (pos[S] - partner)
+                lp_prop = self.logp_batch(prop)                       # ONE launch for the whole half-ensemble
+                with np.errstate(all="ignore"):
+                    logr = (nd - 1.0) * np.log(z) + lp_prop - lp[S]
+                acc = np.log(rng.random(half)) < logr
+                acc &= np.isfinite(lp_prop)
+                newpos = pos[S].copy()
+                newpos[acc] = prop[acc]
+                pos[S] = newpos
+                newlp = lp[S].copy()
+                newlp[acc] = lp_prop[acc]
+                lp[S] = newlp
+            out[it] = pos
+            out_lp[it] = lp
+        return out, out_lp
+
+
 class GaussianProcess(EllipticalProcess):
     KIND = cabi.KIND_GAUSS
 

@@ -321,3 +321,21 @@ def test_block_cyclic_cholesky_schedule(world):
         r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "DIST_OK" in r.stdout
+
+
+def test_batched_drivers_on_fake(fake):
+    """sample_hypers (stretch move on logp_batch) and multi-start MAP: one device call per half-ensemble."""
+    x, y = workloads.c1_inputs()
+    x, y = x[::5], y[::5]
+    gp = g3.GP(x, g3.Bias(), g3.SE(x))
+    gp.observed(x, y)
+    calls0 = fake.calls
+    chain, lp = gp.sample_hypers(samples=5, chains=8, seed=0)
+    assert chain.shape == (5, 8, gp.ndim) and lp.shape == (5, 8)
+    assert fake.calls - calls0 == 1 + 5 * 2                         # init + two half-ensembles per sweep
+    assert np.all(np.isfinite(lp))
+    for c in range(8):                                              # stored logp is the logp of the stored position
+        assert gp.logp(chain[-1, c], array=True) == pytest.approx(lp[-1, c], rel=1e-12)
+    starts = [gp.params_default, gp.params_test]
+    best = gp.find_MAP_multistart(starts)
+    assert gp.logp(best) >= max(gp.logp(s) for s in starts)
