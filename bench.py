@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-metric2", action="store_true")
+    ap.add_argument("--dist-n", type=int, default=131072, help="N of the multi-GPU exact-GP Cholesky (runs when --gpus > 1)")
     ap.add_argument("--groups", type=int, default=4, help="batch groups run concurrently on separate streams")
     ap.add_argument("--n", type=int, default=N_OBS, help=argparse.SUPPRESS)
     ap.add_argument("--b", type=int, default=B_THETA, help=argparse.SUPPRESS)
@@ -245,6 +246,21 @@ def main():
     h2d = 8 * (B * P_k + delta.size)
     d2h = 8 * (2 * B + B * P_k + B * N) + 4 * B
 
+    # exact GP too large for one GPU: block-cyclic Cholesky across the ranks (all ranks take part)
+    dist_metric = None
+    if world > 1 and not args.no_metric2:
+        try:
+            from g3py_b200.dist_potrf import run_dist_cholesky
+            run_dist_cholesky(16384, nb=1024)                      # warm-up: NCCL channels, allocator
+            r = run_dist_cholesky(args.dist_n, nb=1024)
+            one_gpu_tflops = 34.83                                  # measured, same code, world=1 (profiles/r01_dist_cholesky_131072.jsonl)
+            dist_metric = {"metric": "exact-GP Cholesky N=%d, block-cyclic (nb=1024, 1x%d grid, panel broadcast over NCCL, look-ahead)" % (args.dist_n, world),
+                           "value": r["tflops"], "unit": "TFLOP/s", "ms_potrf": r["ms_potrf"], "ms_gram": r["ms_gram"],
+                           "n_gpus": world, "per_gpu_frac_of_fp64_peak": r["tflops"] / world / peaks()["fp64_tflops"],
+                           "parallel_efficiency_vs_1gpu_same_code": r["tflops"] / world / one_gpu_tflops,
+                           "logdet": r["logdet"], "info": r["info"], "local_gib": r["local_gib"]}
+        except Exception as e:
+            dist_metric = {"error": repr(e)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -285,6 +301,8 @@ def main():
             line["metric2"] = metric2(ctx, pk)
         except Exception as e:                                  # reported, never hidden
             line["metric2"] = {"error": str(e)}
+    if dist_metric is not None:
+        line["metric3"] = dist_metric
     if not args.no_cpu_baseline:
         v, dt = cpu_reference_sample(1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",

@@ -680,6 +680,38 @@ class EllipticalProcess(StochasticProcess):
         return out, out_lp
 
 
+    def sample_hmc(self, start=None, samples=100, chains=8, step=0.02, n_leapfrog=10, noise_sum=0.01, seed=None):
+        """Hamiltonian Monte Carlo over `chains` independent chains advanced in lockstep: every leapfrog step is
+        ONE batched logp+gradient launch (the gradient PyMC3's HMC/NUTS obtains through the Op boundary,
+        SURVEY §3 F).  One chain per GPU = the same call with chains=1 in each process.
+        Returns (chain [samples, chains, ndim], logp [samples, chains], accept_rate [chains])."""
+        rng = np.random.default_rng(seed)
+        nd = self.ndim
+        x0 = self.dict_to_array(self.params if start is None else start) if not isinstance(start, np.ndarray) else start
+        q = x0[None, :] + noise_sum * rng.standard_normal((chains, nd))
+        lp, g, _ = self.logp_dlogp_batch(q)
+        out = np.empty((samples, chains, nd))
+        out_lp = np.empty((samples, chains))
+        n_acc = np.zeros(chains)
+        for it in range(samples):
+            p = rng.standard_normal((chains, nd))
+            h0 = -lp + 0.5 * np.sum(p * p, axis=1)
+            qn, pn, gn, lpn = q.copy(), p.copy(), g.copy(), lp.copy()
+            for _ in range(n_leapfrog):
+                pn = pn + 0.5 * step * gn
+                qn = qn + step * pn
+                lpn, gn, _ = self.logp_dlogp_batch(qn)
+                gn = np.nan_to_num(gn)
+                pn = pn + 0.5 * step * gn
+            h1 = -lpn + 0.5 * np.sum(pn * pn, axis=1)
+            with np.errstate(all="ignore"):
+                acc = (np.log(rng.random(chains)) < (h0 - h1)) & np.isfinite(lpn)
+            q[acc], g[acc], lp[acc] = qn[acc], gn[acc], lpn[acc]
+            n_acc += acc
+            out[it], out_lp[it] = q, lp
+        return out, out_lp, n_acc / max(samples, 1)
+
+
 class GaussianProcess(EllipticalProcess):
     KIND = cabi.KIND_GAUSS
 

@@ -386,3 +386,72 @@ def test_block_cyclic_cholesky_single_gpu():
         assert np.abs(np.tril(P[:nb]) - want[:nb]).max() < 1e-11
         if P.shape[0] > nb:
             assert np.abs(P[nb:] - want[nb:]).max() < 1e-11
+
+
+def test_c3_full_size_posterior():
+    """BASELINE config 3 at full size: warped GP, periodic x SE kernel, N=2048, posterior mean/variance on 10k
+    test points, against the oracle (Cholesky route 1e-9, the reference's LU route 1e-7)."""
+    x, y, xs = orc.c3_inputs(2048, 10000)
+    gp = build_process(SPECS["C3"], x)
+    gp.observed(x, y)
+    op = orc.OracleProcess(SPECS["C3"], 1)
+    rng = np.random.default_rng(21)
+    th = _theta0("C3", gp, op, x, y, rng, 1)[0]
+    lo = op.logp(th, x, y)
+    assert abs(gp.logp(th, array=True) - lo) <= TOL * abs(lo)
+    assert scaled_err(gp.dlogp(th, array=True), op.dlogp(th, x, y)) < TOL
+    for noise in (False, True):
+        post, _, _ = gp._posterior(th, xs, noise=noise)
+        pc = op.posterior(th, xs, x, y, noise=noise, solver="chol")
+        assert scaled_err(post["location"], pc["location"]) < TOL
+        assert scaled_err(post["kernel_diag"], pc["kernel_diag"]) < 1e-8
+    pl = op.posterior(th, xs, x, y, noise=False, solver="lu")
+    post, _, _ = gp._posterior(th, xs, noise=False)
+    assert scaled_err(post["location"], pl["location"]) < 1e-7
+    out = gp.predict(th, space=xs, array=True, var=True, median=True, quantiles=True)
+    pr = op.predict(th, xs, x, y)
+    for k in ("mean", "variance", "median", "quantile_up", "quantile_down"):
+        assert scaled_err(out[k], pr[k]) < 1e-7, k
+    # 8 chains in lockstep (one batched launch per leapfrog step), finite and moving
+    chain, lp, acc = gp.sample_hmc(start=th, samples=3, chains=8, step=0.01, n_leapfrog=3, seed=0)
+    assert np.all(np.isfinite(lp)) and chain.shape == (3, 8, gp.ndim)
+
+
+def test_c4_full_size_properties(ctx):
+    """BASELINE config 4: StudentTProcess, N=16384, D=5 (generic Gram interpreter path, D > 4).  The oracle
+    needs minutes at this size, so the checks are size-independent: K alpha = delta from the returned
+    d logp / d delta, a directional finite difference of the batched logp, and predictive moments at
+    training points."""
+    X, y, Xs = orc.c4_inputs(16384, 512)
+    gp = build_process(SPECS["C4"], X)
+    gp.observed(X, y)
+    th = gp.dict_to_array(gp.params_default)
+    lay = [n for n, s, _ in gp.layout for _ in range(s)]
+    th[lay.index("TP_Freedom_degree")] = np.log(5.0)
+    th[lay.index("TP_Noise_var")] = np.log(0.05)
+    lp, g, info = gp.logp_dlogp_batch(th[None])
+    assert info["status"][0] == 0 and np.isfinite(lp[0]) and np.all(np.isfinite(g))
+    nat = gp.natural(th)
+    nu, beta, n = info["nu"][0], info["beta"][0], len(y)
+    c = (nu + n) / (nu - 2.0 + beta)
+    delta = y - nat[0]
+    res = gp.ctx.gp_logp_grad(gp.desc, cabi.KIND_STUDENT, delta, gp._kernel_theta(nat[None]), nu=np.array([nu]))
+    alpha = -res["ddelta"][0] / c
+    Ka = np.zeros(n)
+    thk = gp._kernel_theta(nat[None])
+    for r0 in range(0, n, 2048):                                # K alpha through the Gram entry, row blocks
+        Kb, _ = gp.ctx.gram(gp.desc, X[r0:r0 + 2048], X, thk)
+        Ka[r0:r0 + 2048] = Kb[0] @ alpha
+    Ka += nat[lay.index("TP_Noise_var")] * alpha                # cross-form Gram carries no Noise term
+    assert np.max(np.abs(Ka - delta)) <= 1e-9 * np.max(np.abs(delta))
+    assert abs(alpha @ delta - beta) <= 1e-9 * beta
+    rng = np.random.default_rng(4)
+    v = rng.standard_normal(len(th))
+    v /= np.linalg.norm(v)
+    h = 1e-4
+    lpp = gp.logp_batch(np.stack([th + h * v, th - h * v]))
+    fd = (lpp[0] - lpp[1]) / (2 * h)
+    assert abs(fd - g[0].dot(v)) <= 1e-6 * max(1.0, abs(fd))
+    out = gp.predict(th, space=X[:512], array=True, var=True, noise=False)
+    resid = out["mean"] - y[:512]
+    assert np.sqrt(np.mean(resid ** 2)) < 0.3 and np.all(out["variance"] >= 0) and np.all(out["variance"] < nat[1] * 5)

@@ -339,3 +339,16 @@ def test_batched_drivers_on_fake(fake):
     starts = [gp.params_default, gp.params_test]
     best = gp.find_MAP_multistart(starts)
     assert gp.logp(best) >= max(gp.logp(s) for s in starts)
+
+
+def test_batched_hmc_on_fake(fake):
+    x, y = workloads.c1_inputs()
+    x, y = x[::5], y[::5]
+    gp = g3.GP(x, g3.Bias(), g3.SE(x))
+    gp.observed(x, y)
+    best = gp.find_MAP()
+    c0 = fake.calls
+    chain, lp, acc = gp.sample_hmc(start=best, samples=6, chains=4, step=0.05, n_leapfrog=5, seed=1)
+    assert fake.calls - c0 == 1 + 6 * 5                              # one batched launch per leapfrog step
+    assert chain.shape == (6, 4, gp.ndim) and np.all(np.isfinite(lp)) and np.all(acc > 0.3)
+    assert gp.logp(chain[-1, 2], array=True) == pytest.approx(lp[-1, 2], rel=1e-12)
