@@ -19,7 +19,8 @@ namespace {
 constexpr int kStageBytesA = G3_BM * G3_BK * 8;  // 8 KiB
 constexpr int kStageBytesB = G3_BN * G3_BK * 8;  // 16 KiB
 constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-constexpr int kSmemBytes = G3_STAGES * kStageBytes + 1024;  // + manual 1024-B alignment slack
+constexpr int kSmemBytes = G3_STAGES * kStageBytes + 64;  // stages (1024-B aligned base) + 8 mbarriers; NO static smem,
+// so that one GEMM CTA (98,368 B + 1 KiB system reserve) leaves room for a 128x128 fp64 diagonal-block CTA on the same SM
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -63,8 +64,8 @@ __device__ __forceinline__ void lds128(uint32_t addr, double& x, double& y) {
 
 __global__ void __launch_bounds__(256, 2)
 dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
-  extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * G3_STAGES];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + G3_STAGES * kStageBytes);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -93,7 +94,8 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   double* Dt = g.D + (long long)bidx * g.strideD + (long long)(g.d_r0 + x * G3_TILE + h * G3_BM) * g.ldd +
                (g.d_c0 + y * G3_TILE);
 
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();  // SWIZZLE_128B needs 1024-B aligned stages
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (G3_STAGES + s); };
@@ -207,6 +209,7 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 int g3_gemm_launch(g3_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int B) {
   if (!ctx->gemm_ready) {
     G3_CUDA(ctx, cudaFuncSetAttribute(dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    G3_CUDA(ctx, cudaFuncSetAttribute(dgemm_nt_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     ctx->gemm_ready = true;
   }
   long long ntiles = a.mode == 0 ? (long long)a.ntx * a.nty : (long long)a.ntx * (a.ntx + 1) / 2;

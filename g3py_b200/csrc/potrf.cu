@@ -21,75 +21,160 @@ namespace {
 constexpr int TS = G3_TILE;       // 128
 constexpr int LDS_ = TS + 1;      // padded row stride of the shared tile
 
-// One CTA per matrix: factor the diagonal tile j in place, build Linv (-> Dinv) and Linv^T (-> U).
-// Shared tile S[128][129]: L (and the not yet eliminated part of A) lives at S[i][c], c <= i;
-// row i of R/X = Linv lives transposed in the strictly-upper part, X[i][c] = S[c][i+1], c <= i.
+// One CTA per matrix: factor the diagonal tile j in place and build Linv (-> Dinv).
+// Blocked in shared memory with 32x32 sub-blocks so that only ~25 block-wide barriers are needed (the first version
+// eliminated one column per three barriers: 246 us per tile, all of it latency):
+//   A  for kb = 0..3:  one warp factors the 32x32 diagonal sub-block in registers (row per lane, shuffles) and
+//                      inverts it (column per lane); all warps solve the sub-blocks below and update the rest
+//   B  Linv off-diagonal sub-blocks by block forward substitution, X[I][J] = -Xd_I * sum_K L[I][K] X[K][J]
+// Shared tile S[128][129]: L at S[i][c] (c <= i); X = Linv strictly below the diagonal is stored transposed in the
+// strict upper part, X[i][c] = S[c][i] (c < i); its diagonal lives in xd[].
+constexpr int SB = 32;           // sub-block
+constexpr int LDT = 33;          // scratch leading dimension
+
+__device__ __forceinline__ void warp_potrf32(double (&a)[SB], int lane, int& bad) {
+#pragma unroll
+  for (int k = 0; k < SB; ++k) {
+    const double d = __shfl_sync(0xffffffffu, a[k], k);
+    if (!(d > 0.0) && bad < 0) bad = k;
+    const double s = sqrt(d);
+    const double inv = 1.0 / s;
+    if (lane > k) a[k] *= inv;
+    else if (lane == k) a[k] = s;
+    const double lrk = a[k];
+#pragma unroll
+    for (int c = k + 1; c < SB; ++c) {
+      const double lck = __shfl_sync(0xffffffffu, lrk, c);
+      if (lane >= c) a[c] -= lrk * lck;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 potrf_diag_kernel(double* __restrict__ A, int Np, long long strideA, int j, double* __restrict__ Dinv, int T,
                   double* __restrict__ U, double* __restrict__ logdet, int* __restrict__ info,
                   const int* __restrict__ bmap) {
-  extern __shared__ double S[];
+  extern __shared__ double S[];                 // [128][129] + scratch 3 x [32][33]
+  double* Tm = S + TS * LDS_;
+  __shared__ double xd[TS];
   __shared__ int first_bad;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = bmap ? bmap[blockIdx.x] : (int)blockIdx.x;
   double* At = A + (long long)b * strideA + (long long)j * TS * Np + (long long)j * TS;
   if (tid == 0) first_bad = -1;
-  // load lower triangle; initialise R = I in the transposed upper storage
   for (int idx = tid; idx < TS * TS; idx += 256) {
     const int r = idx >> 7, c = idx & 127;
     if (c <= r) S[r * LDS_ + c] = At[(long long)r * Np + c];
   }
-  for (int idx = tid; idx < TS * TS; idx += 256) {
-    const int r = idx >> 7, q = (idx & 127) + 1;  // q in 1..128
-    if (q > r) S[r * LDS_ + q] = (q == r + 1) ? 1.0 : 0.0;
-  }
   __syncthreads();
 
-  const int tx = tid & 15, ty = tid >> 4;
-  for (int k = 0; k < TS; ++k) {
-    const double d = S[k * LDS_ + k];
-    const bool ok = d > 0.0;  // false for NaN too
-    const double s = sqrt(d);
-    const double inv = 1.0 / s;
-    __syncthreads();  // everyone has read S[k][k]
-    if (tid == 0 && !ok && first_bad < 0) first_bad = k;
-    if (tid < TS) {
-      const int q = tid;
-      if (q > k) {
-        S[q * LDS_ + k] *= inv;        // column k of L
-      } else {
-        S[q * LDS_ + k + 1] *= inv;    // row k of X: X[k][q] = R[k][q] / L[k][k]
-        if (q == k) S[k * LDS_ + k] = s;
+  // ---- phase A: blocked Cholesky ----------------------------------------------------------------
+  for (int kb = 0; kb < TS / SB; ++kb) {
+    const int o = kb * SB;
+    if (warp == 0) {
+      double a[SB];
+#pragma unroll
+      for (int c = 0; c < SB; ++c) a[c] = (c <= lane) ? S[(o + lane) * LDS_ + o + c] : 0.0;
+      int bad = -1;
+      warp_potrf32(a, lane, bad);
+      if (lane == 0 && bad >= 0 && first_bad < 0) first_bad = o + bad;
+#pragma unroll
+      for (int c = 0; c < SB; ++c)
+        if (c <= lane) S[(o + lane) * LDS_ + o + c] = a[c];
+      __syncwarp();
+      // inverse of the sub-block, column `lane` per lane: x[r] = X[r][lane]
+      double x[SB];
+#pragma unroll
+      for (int r = 0; r < SB; ++r) {
+        double acc = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < SB; ++k)
+          if (k < r) acc -= S[(o + r) * LDS_ + o + k] * x[k];
+        x[r] = (r >= lane) ? acc / S[(o + r) * LDS_ + o + r] : 0.0;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < SB; ++r) {
+        if (r > lane) S[(o + lane) * LDS_ + o + r] = x[r];     // X[r][lane] -> S[lane][r]
+        else if (r == lane) xd[o + r] = x[r];
       }
     }
     __syncthreads();
-    for (int i = k + 1 + ty; i < TS; i += 16) {
-      const double lik = S[i * LDS_ + k];
-      for (int e = tx; e <= i; e += 16) {
-        if (e <= k)
-          S[e * LDS_ + i + 1] -= lik * S[e * LDS_ + k + 1];   // R[i][e] -= L[i][k] X[k][e]
-        else
-          S[i * LDS_ + e] -= lik * S[e * LDS_ + k];           // A[i][e] -= L[i][k] L[e][k]
+    const int below = TS - o - SB;            // rows under the diagonal sub-block
+    if (below > 0) {
+      // A2: L[r][o+jj] = sum_{c <= jj} A[r][o+c] * Xd[jj][c]   (registers first: in-place)
+      double outv[12];
+#pragma unroll
+      for (int it = 0; it < 12; ++it) {
+        const int e = tid + it * 256;
+        outv[it] = 0.0;
+        if (e < below * SB) {
+          const int r = o + SB + e / SB, jj = e % SB;
+          double acc = S[r * LDS_ + o + jj] * xd[o + jj];
+          for (int c = 0; c < jj; ++c) acc += S[r * LDS_ + o + c] * S[(o + c) * LDS_ + o + jj];
+          outv[it] = acc;
+        }
       }
+      __syncthreads();
+#pragma unroll
+      for (int it = 0; it < 12; ++it) {
+        const int e = tid + it * 256;
+        if (e < below * SB) {
+          const int r = o + SB + e / SB, jj = e % SB;
+          S[r * LDS_ + o + jj] = outv[it];
+        }
+      }
+      __syncthreads();
+      // A3: A[r][c] -= sum_k L[r][o+k] L[c][o+k]   for o+SB <= c <= r
+      for (int e = tid; e < below * below; e += 256) {
+        const int r = o + SB + e / below, c = o + SB + e % below;
+        if (c > r) continue;
+        double acc = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < SB; ++k) acc += S[r * LDS_ + o + k] * S[c * LDS_ + o + k];
+        S[r * LDS_ + c] -= acc;
+      }
+      __syncthreads();
     }
-    // next iteration's first __syncthreads orders these writes before the column scale
+  }
+
+  // ---- phase B: off-diagonal sub-blocks of X = L^-1 --------------------------------------------------
+  for (int dist = 1; dist < TS / SB; ++dist) {
+    const int nblk = TS / SB - dist;
+    // T[I][J] = sum_{k in [J*32, I*32)} L[r][k] X[k][c]
+    for (int e = tid; e < nblk * SB * SB; e += 256) {
+      const int blk = e / (SB * SB), rr = (e / SB) % SB, cc = e % SB;
+      const int J = blk, I = blk + dist;
+      const int r = I * SB + rr, c = J * SB + cc;
+      double acc = S[r * LDS_ + c] * xd[c];                       // k == c
+      for (int k = c + 1; k < I * SB; ++k) acc += S[r * LDS_ + k] * S[c * LDS_ + k];   // X[k][c] = S[c][k], k > c
+      Tm[(blk * SB + rr) * LDT + cc] = acc;
+    }
+    __syncthreads();
+    // X[I][J] = -Xd_I T   ->  X[r][c] stored at S[c][r]
+    for (int e = tid; e < nblk * SB * SB; e += 256) {
+      const int blk = e / (SB * SB), cc = (e / SB) % SB, rr = e % SB;   // rr fastest: S[c][r] writes coalesce in banks
+      const int J = blk, I = blk + dist;
+      const int r = I * SB + rr, c = J * SB + cc;
+      double acc = xd[r] * Tm[(blk * SB + rr) * LDT + cc];
+      for (int m = 0; m < rr; ++m) acc += S[(I * SB + m) * LDS_ + r] * Tm[(blk * SB + m) * LDT + cc];  // Xd_I[rr][m] = S[m][r]
+      S[c * LDS_ + r] = -acc;
+    }
     __syncthreads();
   }
 
-  // write back: L tile (upper zeroed), Dinv (lower, zeros above), U diagonal tile (upper)
+  // write back: L tile (upper zeroed), Dinv (lower, zeros above)
   double* Dj = Dinv + ((long long)b * T + j) * TS * TS;
-  double* Ut = U ? U + (long long)b * strideA + (long long)j * TS * Np + (long long)j * TS : nullptr;
   for (int idx = tid; idx < TS * TS; idx += 256) {
     const int r = idx >> 7, c = idx & 127;
     At[(long long)r * Np + c] = (c <= r) ? S[r * LDS_ + c] : 0.0;
-    Dj[idx] = (c <= r) ? S[c * LDS_ + r + 1] : 0.0;             // Linv[r][c] = X[r][c]
-    if (Ut) Ut[(long long)r * Np + c] = (c >= r) ? S[r * LDS_ + c + 1] : 0.0;  // U[r][c] = X[c][r]
+    Dj[idx] = (c < r) ? S[c * LDS_ + r] : (c == r ? xd[r] : 0.0);
   }
-  // log-determinant contribution and failure index (deterministic: one thread, sequential steps)
+  (void)U;
   if (tid < 32) {
     double acc = 0.0;
     for (int k = tid; k < TS; k += 32) acc += log(S[k * LDS_ + k]);
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o2);
     if (tid == 0) {
       if (logdet) logdet[b] += acc;
       if (info && first_bad >= 0 && info[b] == 0) info[b] = j * TS + first_bad + 1;
@@ -175,7 +260,7 @@ trsv_bwd_step_kernel(const double* __restrict__ L, const double* __restrict__ Di
 
 }  // namespace
 
-static constexpr int kDiagSmem = TS * LDS_ * (int)sizeof(double);
+static constexpr int kDiagSmem = (TS * LDS_ + 3 * SB * LDT) * (int)sizeof(double);
 
 static GemmArgs gemm_zero() {
   GemmArgs g;
