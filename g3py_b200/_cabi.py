@@ -56,7 +56,8 @@ SIGNATURES = {
     "g3_set_stream": (C.c_int, [_ctxp, C.c_void_p]),
     "g3_dev_gram_block": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                     C.c_void_p, C.c_longlong]),
-    "g3_dev_potrf_panel": (C.c_int, [_ctxp, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "g3_dev_potrf_panel": (C.c_int, [_ctxp, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "g3_dev_trsv_panel": (C.c_int, [_ctxp, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "g3_dev_syrk_panel": (C.c_int, [_ctxp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "g3_set_data": (C.c_int, [_ctxp, _dp, C.c_int, C.c_int]),
     "g3_gram": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _ip]),
@@ -163,9 +164,13 @@ class Context:
         self._ck(self._lib.g3_dev_gram_block(self._h, C.byref(desc), _d(theta), row0, col0, rows, cols, float(diag_shift),
                                              C.c_void_p(out_ptr), ld), "g3_dev_gram_block")
 
-    def dev_potrf_panel(self, p_ptr, rows, nb, logdet_ptr, info_ptr):
-        self._ck(self._lib.g3_dev_potrf_panel(self._h, C.c_void_p(p_ptr), rows, nb, C.c_void_p(logdet_ptr),
-                                              C.c_void_p(info_ptr)), "g3_dev_potrf_panel")
+    def dev_potrf_panel(self, p_ptr, rows, nb, logdet_ptr, info_ptr, dinv_ptr=0):
+        self._ck(self._lib.g3_dev_potrf_panel(self._h, C.c_void_p(p_ptr), rows, nb, C.c_void_p(dinv_ptr) if dinv_ptr else None,
+                                              C.c_void_p(logdet_ptr), C.c_void_p(info_ptr)), "g3_dev_potrf_panel")
+
+    def dev_trsv_panel(self, p_ptr, rows, nb, dinv_ptr, r_ptr, u_ptr, beta_ptr):
+        self._ck(self._lib.g3_dev_trsv_panel(self._h, C.c_void_p(p_ptr), rows, nb, C.c_void_p(dinv_ptr), C.c_void_p(r_ptr),
+                                             C.c_void_p(u_ptr), C.c_void_p(beta_ptr)), "g3_dev_trsv_panel")
 
     def dev_syrk_panel(self, p_ptr, rows_p, nb, row_off, d_ptr, rows_d):
         self._ck(self._lib.g3_dev_syrk_panel(self._h, C.c_void_p(p_ptr), rows_p, nb, row_off, C.c_void_p(d_ptr), rows_d),

@@ -897,12 +897,21 @@ int g3_dev_gram_block(g3_ctx* ctx, const g3_kernel_desc* desc, const double* the
   return g3_gram_launch(ctx, *desc, a, 1);
 }
 
-int g3_dev_potrf_panel(g3_ctx* ctx, double* P, int rows, int nb, double* logdet_dev, int* info_dev) {
+int g3_dev_potrf_panel(g3_ctx* ctx, double* P, int rows, int nb, double* Dinv_dev_or_NULL, double* logdet_dev,
+                       int* info_dev) {
   if (!ctx || !P || !logdet_dev || !info_dev) return g3_fail_msg(ctx, "g3_dev_potrf_panel: bad arguments");
   G3_CUDA(ctx, cudaSetDevice(ctx->device));
-  double* Dinv = (double*)g3_ws(ctx, "blk_Dinv", sizeof(double) * (size_t)(nb / TS) * TS * TS);
+  double* Dinv = Dinv_dev_or_NULL ? Dinv_dev_or_NULL
+                                  : (double*)g3_ws(ctx, "blk_Dinv", sizeof(double) * (size_t)(nb / TS) * TS * TS);
   if (!Dinv) return -2;
   return g3_potrf_panel(ctx, P, rows, nb, Dinv, logdet_dev, info_dev);
+}
+
+int g3_dev_trsv_panel(g3_ctx* ctx, const double* P, int rows, int nb, const double* Dinv_dev, double* r_dev,
+                      double* u_dev, double* beta_dev) {
+  if (!ctx || !P || !Dinv_dev || !r_dev || !u_dev) return g3_fail_msg(ctx, "g3_dev_trsv_panel: bad arguments");
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  return g3_trsv_panel(ctx, P, rows, nb, Dinv_dev, r_dev, u_dev, beta_dev);
 }
 
 int g3_dev_syrk_panel(g3_ctx* ctx, const double* P, int rowsP, int nb, int row_off, double* D, int rowsD) {

@@ -475,6 +475,21 @@ int g3_trsv_fwd(g3_ctx* ctx, const double* L, const double* Dinv, double* r, dou
   return 0;
 }
 
+// Forward substitution with one factored panel (rows x nb, ld = nb): u = L_top^-1 r[0:nb] and
+// r[nb:rows] -= L_below u (r is updated in place, beta += |u|^2).
+int g3_trsv_panel(g3_ctx* ctx, const double* P, int rows, int nb, const double* Dinv, double* r, double* u,
+                  double* beta) {
+  if (rows % TS || nb % TS || rows < nb) return g3_fail_msg(ctx, "trsv_panel: bad geometry");
+  const int Tr = rows / TS, w = nb / TS;
+  g3_prof_begin(ctx, G3_PROF_TRSV);
+  for (int j = 0; j < w; ++j) {
+    trsv_fwd_step_kernel<<<dim3(Tr - j, 1), 256, 0, ctx->stream>>>(P, Dinv, r, u, beta, j, nb, w);
+    G3_LAUNCH_CHECK(ctx);
+  }
+  g3_prof_end(ctx);
+  return 0;
+}
+
 int g3_trsv_bwd(g3_ctx* ctx, const double* L, const double* Dinv, double* s, double* alpha, int Np, int B) {
   const int T = Np / TS;
   g3_prof_begin(ctx, G3_PROF_TRSV);

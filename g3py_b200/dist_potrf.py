@@ -49,8 +49,12 @@ class LibBackend:
     def gram(self, out, row0, col0, rows, cols):
         self.ctx.dev_gram_block(self.desc, self.theta, row0, col0, rows, cols, self.shift, out.data_ptr(), cols)
 
-    def factor(self, P, rows, nb, logdet, info):
-        self.ctx.dev_potrf_panel(P.data_ptr(), rows, nb, logdet.data_ptr(), info.data_ptr())
+    def factor(self, P, rows, nb, logdet, info, dinv=None):
+        self.ctx.dev_potrf_panel(P.data_ptr(), rows, nb, logdet.data_ptr(), info.data_ptr(),
+                                 dinv.data_ptr() if dinv is not None else 0)
+
+    def trsv(self, P, rows, nb, dinv, r, u, beta):
+        self.ctx.dev_trsv_panel(P.data_ptr(), rows, nb, dinv.data_ptr(), r.data_ptr(), u.data_ptr(), beta.data_ptr())
 
     def update(self, P, rows_p, nb, row_off, D, rows_d):
         self.ctx.dev_syrk_panel(P.data_ptr(), rows_p, nb, row_off, D.data_ptr(), rows_d)
@@ -82,6 +86,8 @@ class DistCholesky:
             o += sz
         self.pbuf = [backend.alloc(N * nb), backend.alloc(N * nb)] if world > 1 else None
         self.logdet, self.info = backend.scalars()
+        self.dinv = backend.alloc(max(len(self.mine), 1) * nb * 128)       # 128x128 block inverses of my panels
+        self.dinv_of = {J: self.dinv[i * nb * 128:(i + 1) * nb * 128] for i, J in enumerate(self.mine)}
 
     def panel(self, J):
         return self.store[self.off[J]: self.off[J] + self.rows[J] * self.nb]
@@ -109,7 +115,7 @@ class DistCholesky:
     def factor(self):
         nb, nP, me = self.nb, self.nP, self.rank
         if panel_owner(0, self.world) == me:
-            self.be.factor(self.panel(0), self.rows[0], nb, self.logdet, self.info)
+            self.be.factor(self.panel(0), self.rows[0], nb, self.logdet, self.info, self.dinv_of[0])
         cur = self._bcast(0)
         for J in range(nP):
             PJ, work = cur
@@ -122,7 +128,7 @@ class DistCholesky:
                     if self.lookahead or self.world == 1:
                         self._update(PJ, J, J + 1)
                         done_early = J + 1
-                        self.be.factor(self.panel(J + 1), self.rows[J + 1], nb, self.logdet, self.info)
+                        self.be.factor(self.panel(J + 1), self.rows[J + 1], nb, self.logdet, self.info, self.dinv_of[J + 1])
                 if self.lookahead:
                     nxt = self._bcast(J + 1)
             for Jp in self.mine:
@@ -130,10 +136,32 @@ class DistCholesky:
                     self._update(PJ, J, Jp)
             if J + 1 < nP and not self.lookahead:
                 if panel_owner(J + 1, self.world) == me and self.world > 1:
-                    self.be.factor(self.panel(J + 1), self.rows[J + 1], nb, self.logdet, self.info)
+                    self.be.factor(self.panel(J + 1), self.rows[J + 1], nb, self.logdet, self.info, self.dinv_of[J + 1])
                 nxt = self._bcast(J + 1)
             cur = nxt
         return self
+
+    def solve(self, delta, make_zero, all_reduce_sum):
+        """u = L^-1 delta across the ranks; returns (u pieces {J: tensor[nb]}, beta tensor (local part)).
+
+        Every rank carries a length-N residual `c` (rank 0 starts with delta, the others with 0); the true
+        residual of panel J is the sum over ranks of c[J rows], obtained with ONE nb-sized all-reduce per panel;
+        the owner then solves with its panel and pushes the update into its own `c` (rows below).  No panel
+        data moves; L is read exactly once."""
+        nb = self.nb
+        c = delta.clone() if self.rank == 0 else make_zero(self.N)
+        beta = make_zero(1)
+        u = {}
+        for J in range(self.nP):
+            seg = c[J * nb:(J + 1) * nb]
+            if self.world > 1:
+                all_reduce_sum(seg)                      # everyone now holds the true residual of panel J
+            if panel_owner(J, self.world) == self.rank:
+                u[J] = make_zero(nb)
+                self.be.trsv(self.panel(J), self.rows[J], nb, self.dinv_of[J], c[J * nb:], u[J], beta)
+            else:
+                seg.zero_()                              # rows of a finished panel are never read again
+        return u, beta
 
     def flops(self):
         return float(self.N) ** 3 / 3.0
@@ -172,7 +200,7 @@ def run_dist_cholesky(N, D=3, nb=1024, theta=None, lookahead=True, seed=5, verif
     try:
         with torch.cuda.stream(stream):
             ch = DistCholesky(N, nb, rank, world, be, dist if world > 1 else None, lookahead=lookahead)
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
@@ -181,20 +209,30 @@ def run_dist_cholesky(N, D=3, nb=1024, theta=None, lookahead=True, seed=5, verif
             e[1].record()
             ch.factor()
             e[2].record()
+            delta = torch.from_numpy(np.ascontiguousarray(y)).to("cuda")
+            zeros = lambda n: torch.zeros(n, dtype=torch.float64, device="cuda")
+            upieces, beta = ch.solve(delta, zeros, (lambda t_: dist.all_reduce(t_)) if world > 1 else (lambda t_: None))
+            e[3].record()
             torch.cuda.synchronize()
-            t = torch.tensor([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])], dtype=torch.float64, device="cuda")
+            t = torch.tensor([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(beta)
             ld = ch.logdet.clone()
             info = ch.info.clone().to(torch.float64)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dist.all_reduce(ld, op=dist.ReduceOp.SUM)
                 dist.all_reduce(info, op=dist.ReduceOp.MAX)
-            ms_gram, ms_potrf = (float(v) for v in t.cpu())
-            out = {"N": N, "nb": nb, "n_gpus": world, "ms_gram": ms_gram, "ms_potrf": ms_potrf,
-                   "tflops": ch.flops() / (ms_potrf * 1e-3) / 1e12, "logdet": float(ld.item()), "info": int(info.item()),
-                   "local_gib": ch.local_bytes() / 2 ** 30, "lookahead": bool(lookahead)}
+            ms_gram, ms_potrf, ms_solve = (float(v) for v in t.cpu())
+            n = float(N)
+            logdet, betav = float(ld.item()), float(beta.item())
+            out = {"N": N, "nb": nb, "n_gpus": world, "ms_gram": ms_gram, "ms_potrf": ms_potrf, "ms_solve": ms_solve,
+                   "tflops": ch.flops() / (ms_potrf * 1e-3) / 1e12, "logdet": logdet, "beta": betav,
+                   "logp": -0.5 * n * math.log(2 * math.pi) - 0.5 * betav - logdet,      # exact-constant Gaussian logp, zero mean
+                   "info": int(info.item()), "local_gib": ch.local_bytes() / 2 ** 30, "lookahead": bool(lookahead)}
             if verify:
                 out["panels"] = {J: ch.panel(J).cpu().numpy().reshape(ch.rows[J], nb) for J in ch.mine}
+                out["u"] = {J: v.cpu().numpy() for J, v in upieces.items()}
     finally:
         be.close()
     return out

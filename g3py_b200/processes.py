@@ -574,19 +574,44 @@ class EllipticalProcess(StochasticProcess):
             values["noise_down"] = T(pn["location"] - z * sdn)
         if samples > 0:
             values["samples"] = self.sampler(theta, space, samples=samples, prior=prior, noise=noise)
+        if distribution:                                                     # stochastic.py:509-512
+            values["logpredictive"] = lambda x: self.logpredictive(theta, space, vector=x, prior=prior, array=True)
         return values
+
+    def logpredictive(self, params=None, space=None, vector=None, prior=False, noise=False, array=False):
+        """GaussianProcess.th_logpredictive (gaussian.py:42-54): logp_cho of `vector` under the predictive
+        location with the DIAGONAL Cholesky of the noisy predictive variance (cho = diag(sd))."""
+        if self.KIND != cabi.KIND_GAUSS:
+            raise NotImplementedError("the reference defines th_logpredictive for GaussianProcess only")
+        theta = self._theta(params, array)
+        space = self.space if space is None else np.asarray(space, dtype=np.float64).reshape(len(space), -1)
+        x = np.asarray(vector, dtype=np.float64).reshape(-1)
+        loc, nat, p = self._posterior(theta, space, noise=noise, prior=prior)
+        sdn = np.sqrt(self._posterior(theta, space, noise=True, prior=prior)[0]["kernel_diag"])
+        c = self.consts
+        with np.errstate(all="ignore"):
+            delta = self.f_mapping.inv(x, p) - loc["location"]
+            lcho = delta / sdn
+            det_m = self.f_mapping.logdet_dinv(x, p)
+            r = -0.5 * len(x) * c.log_2pi - 0.5 * float(lcho @ lcho) - float(np.sum(np.log(sdn))) + det_m
+        bad = not (np.all(np.isfinite(delta)) and np.isfinite(det_m) and np.all(np.isfinite(sdn)) and np.all(np.isfinite(lcho)))
+        return c.guard if bad else float(r)
 
     def _quantile_z_prior(self, q, nat):
         return self._quantile_z(q, nat)
 
     def sampler(self, theta, space, samples=1, prior=False, noise=False, rng=None):
-        """gaussian.py:75-97: location + chol(posterior covariance) @ randn, mapped through T."""
+        """gaussian.py:75-97 / studentT.py:57-67: location + chol(posterior covariance) @ randn (Student-t: the
+        normal draws are scaled by inverse-gamma draws), mapped through T.  The Cholesky runs on the device."""
         rng = rng or np.random.default_rng()
         post, nat, p = self._posterior(theta, space, noise=noise, cov=True, prior=prior)
         L, info, _ = self.ctx.potrf_robust(post["kernel"])
         if info < 0:
             L = self.consts.fallback * np.eye(len(L))
         z = rng.standard_normal((len(space), samples))
+        if self.KIND == cabi.KIND_STUDENT:
+            free = float(self._nu(nat[None, :])[0]) + (0 if prior else len(self.outputs))
+            z = z * stats.invgamma.rvs(a=free / 2.0, scale=(free - 2.0) / 2.0, size=samples, random_state=rng)
         f = post["location"][:, None] + L.dot(z)
         return np.array([self.f_mapping(k, p) for k in f.T]).T
 

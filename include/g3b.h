@@ -196,11 +196,17 @@ int g3_gp_posterior(g3_ctx* ctx, const g3_kernel_desc* desc, const double* Xs, i
  *                       shift `diag_shift` and Noise on the global diagonal), into out (leading dim ld)
  *   g3_dev_potrf_panel: P (rows x nb, ld = nb): Cholesky of the top nb x nb block, rows below solved;
  *                       sum(log diag) is ADDED to *logdet_dev, first bad pivot (+1) stored in *info_dev
+ *                       (the 128x128 block inverses go to Dinv_dev if given: needed later by g3_dev_trsv_panel)
  *   g3_dev_syrk_panel : D[x][y] -= sum_k P[row_off+x][k] * P[row_off+y][k]   (D rowsD x nb, ld = nb) */
 int g3_set_stream(g3_ctx* ctx, void* cuda_stream_or_NULL);
 int g3_dev_gram_block(g3_ctx* ctx, const g3_kernel_desc* desc, const double* theta, int row0, int col0,
                       int rows, int cols, double diag_shift, double* out_dev, long long ld);
-int g3_dev_potrf_panel(g3_ctx* ctx, double* P_dev, int rows, int nb, double* logdet_dev, int* info_dev);
+int g3_dev_potrf_panel(g3_ctx* ctx, double* P_dev, int rows, int nb, double* Dinv_dev_or_NULL, double* logdet_dev,
+                       int* info_dev);
+/* forward substitution with one factored panel: u = L_top^-1 r[0:nb]; r[nb:rows] -= L_below u; *beta_dev += |u|^2.
+ * Dinv_dev = the (nb/128) x 128 x 128 block inverses g3_dev_potrf_panel wrote for this panel. */
+int g3_dev_trsv_panel(g3_ctx* ctx, const double* P_dev, int rows, int nb, const double* Dinv_dev, double* r_dev,
+                      double* u_dev, double* beta_dev);
 int g3_dev_syrk_panel(g3_ctx* ctx, const double* P_dev, int rowsP, int nb, int row_off, double* D_dev, int rowsD);
 
 /* ---- stand-alone Cholesky benchmark entry (BASELINE metric 2) --------------------------

@@ -386,6 +386,12 @@ def test_block_cyclic_cholesky_single_gpu():
         assert np.abs(np.tril(P[:nb]) - want[:nb]).max() < 1e-11
         if P.shape[0] > nb:
             assert np.abs(P[nb:] - want[nb:]).max() < 1e-11
+    uref = np.linalg.solve(L, y)                                # distributed forward solve (here world = 1)
+    for J, v in r["u"].items():
+        assert np.abs(v - uref[J * nb:(J + 1) * nb]).max() < 1e-10
+    assert abs(r["beta"] - uref @ uref) <= 1e-10 * (uref @ uref)
+    want_logp = -0.5 * N * np.log(2 * np.pi) - 0.5 * (uref @ uref) - np.log(np.diag(L)).sum()
+    assert abs(r["logp"] - want_logp) <= 1e-10 * abs(want_logp)
 
 
 def test_c3_full_size_posterior():

@@ -280,11 +280,16 @@ class NumpyBackend:                       # CPU double of the three g3_dev_* pan
     def alloc(self, n): return torch.zeros(n, dtype=torch.float64)
     def scalars(self): return torch.zeros(1, dtype=torch.float64), torch.zeros(1, dtype=torch.int32)
     def gram(self, out, row0, col0, rows, cols): out.copy_(torch.from_numpy(K[row0:row0 + rows, col0:col0 + cols].copy()).reshape(-1))
-    def factor(self, P, rows, nb, logdet, info):
+    def factor(self, P, rows, nb, logdet, info, dinv=None):
         M = P.numpy().reshape(rows, nb)
         L = np.linalg.cholesky(M[:nb]); M[:nb] = L
         if rows > nb: M[nb:] = np.linalg.solve(L, M[nb:].T).T
         logdet += float(np.log(np.diag(L)).sum())
+    def trsv(self, P, rows, nb, dinv, r, u, beta):
+        M = P.numpy().reshape(rows, nb); rv = r.numpy()
+        uu = np.linalg.solve(np.tril(M[:nb]), rv[:nb]); u.copy_(torch.from_numpy(uu))
+        if rows > nb: rv[nb:] -= M[nb:] @ uu
+        beta += float(uu @ uu)
     def update(self, P, rows_p, nb, row_off, D, rows_d):
         Pm = P.numpy().reshape(rows_p, nb); Dm = D.numpy().reshape(rows_d, nb)
         Dm -= Pm[row_off:row_off + rows_d] @ Pm[row_off:row_off + nb].T
@@ -300,6 +305,13 @@ for la in (True, False):
     ld = ch.logdet.clone()
     if world > 1: dist.all_reduce(ld)
     assert abs(ld.item() - np.log(np.diag(Lref)).sum()) < 1e-9
+    dvec = torch.from_numpy(np.sin(np.arange(N) * 0.01))
+    up, beta = ch.solve(dvec, lambda n: torch.zeros(n, dtype=torch.float64), (lambda t: dist.all_reduce(t)) if world > 1 else (lambda t: None))
+    uref = np.linalg.solve(Lref, dvec.numpy())
+    for J, v in up.items():
+        assert np.abs(v.numpy() - uref[J * nb:(J + 1) * nb]).max() < 1e-10
+    if world > 1: dist.all_reduce(beta)
+    assert abs(beta.item() - uref @ uref) < 1e-9 * (uref @ uref)
     assert ch.local_bytes() == 8 * sum((N - J * nb) * nb for J in range(rank, N // nb, world))
 if rank == 0: print("DIST_OK", flush=True)
 if world > 1: dist.destroy_process_group()
@@ -352,3 +364,21 @@ def test_batched_hmc_on_fake(fake):
     assert fake.calls - c0 == 1 + 6 * 5                              # one batched launch per leapfrog step
     assert chain.shape == (6, 4, gp.ndim) and np.all(np.isfinite(lp)) and np.all(acc > 0.3)
     assert gp.logp(chain[-1, 2], array=True) == pytest.approx(lp[-1, 2], rel=1e-12)
+
+
+def test_logpredictive_and_sampler_on_fake(fake):
+    x, y = workloads.c1_inputs()
+    x, y = x[::4], y[::4]
+    gp = g3.GP(x, g3.Bias(), g3.SE(x))
+    gp.observed(x, y)
+    fake.potrf_robust = lambda A: (np.linalg.cholesky(A + 1e-9 * np.eye(len(A))), 0, 0.0)
+    th = gp.dict_to_array(gp.params_default)
+    xs = x[:7] + 0.1
+    v = gp.predict(th, space=xs, array=True, var=True, samples=5, distribution=True, noise=True)
+    assert v["samples"].shape == (7, 5)
+    # logpredictive = sum of independent normal log-densities with the noisy predictive variance
+    from scipy import stats
+    want = stats.norm.logpdf(y[:7], loc=v["mean"], scale=np.sqrt(v["variance"])).sum()
+    got = v["logpredictive"](y[:7])
+    strict_shift = -0.5 * 7 * (np.log(np.float32(2 * np.pi)) - np.log(2 * np.pi))
+    assert got == pytest.approx(want + strict_shift, rel=1e-9)

@@ -20,6 +20,10 @@ if verify:
     for J, P in r.pop("panels").items():
         want = L[J * nb:, J * nb:(J + 1) * nb]
         err = max(err, np.abs(np.tril(P[:nb]) - want[:nb]).max(), np.abs(P[nb:] - want[nb:]).max() if P.shape[0] > nb else 0.0)
+    uref = np.linalg.solve(L, y)
+    for J, v in r.pop("u").items():
+        err = max(err, np.abs(v - uref[J * nb:(J + 1) * nb]).max())
+    assert abs(r["beta"] - uref @ uref) < 1e-9 * (uref @ uref), (r["beta"], uref @ uref)
     r["max_abs_err_vs_numpy"] = float(err)
     r["logdet_numpy"] = float(np.log(np.diag(L)).sum())
     assert err < 1e-10 and abs(r["logdet"] - r["logdet_numpy"]) < 1e-8 * abs(r["logdet_numpy"]), r
