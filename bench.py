@@ -283,7 +283,9 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["fp64_tflops"], "unit": "TFLOP/s",
-                     "frac": (achieved / pk["fp64_tflops"]) if achieved else None, "traffic": None,
+                     "frac": (achieved / pk["fp64_tflops"]) if achieved else None,
+                     "traffic": 1.0977e9 if (N == N_OBS and B == B_THETA) else None,
+                     "traffic_note": "dram__bytes_read+write per dgemm_nt launch, mean over the 125 launches of one step (137.2 GB/step; ncu, profiles/r01b_dgemm_dram_per_launch.csv); the one lauum launch moves 8.83 GB for 8.6 GB of algorithmic operand+result bytes",
                      "kernel": "dgemm_nt_kernel (all level-3 steps of potrf/trtri/lauum; %d launches/step, %.2f ms/step = %.0f%% of the step)"
                                % (gemm["launches"] // prof_steps, gemm_ms_step, 100 * gemm_ms_step / ms_serial),
                      "algorithmic": "B*N^3 flop per step / summed dgemm_nt time per step (CUDA event pairs on the launch stream, single-stream pass of the same step: %.2f ms/step)" % ms_serial,
