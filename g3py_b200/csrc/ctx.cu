@@ -173,8 +173,7 @@ int g3_sync(g3_ctx* ctx) {
 }
 
 int g3_set_stream(g3_ctx* ctx, void* stream_or_NULL) {
-  G3_CUDA(ctx, cudaSetDevice(ctx->device));
-  G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // no synchronisation: the caller orders the streams it hands in (events / torch stream semantics)
   ctx->stream = stream_or_NULL ? (cudaStream_t)stream_or_NULL : ctx->own_stream;
   return 0;
 }

@@ -37,7 +37,35 @@ class LibBackend:
     def __init__(self, ctx, desc, theta, diag_shift, torch, stream):
         self.ctx, self.desc, self.theta, self.shift, self.torch = ctx, desc, np.asarray(theta, dtype=np.float64), diag_shift, torch
         self.stream = stream
+        self.panel_stream = torch.cuda.Stream(priority=-1)     # critical path: next panel's update, factor, broadcast
         ctx.set_stream(stream.cuda_stream)
+
+    # two-stream look-ahead support: `with be.on_panel_stream():` routes library launches AND torch ops there
+    def on_panel_stream(self):
+        be = self
+
+        class _Ctx:
+            def __enter__(self_):
+                self_.cm = be.torch.cuda.stream(be.panel_stream)
+                self_.cm.__enter__()
+                be.ctx.set_stream(be.panel_stream.cuda_stream)
+
+            def __exit__(self_, *a):
+                be.ctx.set_stream(be.stream.cuda_stream)
+                self_.cm.__exit__(*a)
+        return _Ctx()
+
+    def fence_main_to_panel(self):
+        self.panel_stream.wait_stream(self.stream)
+
+    def fence_panel_to_main(self):
+        self.stream.wait_stream(self.panel_stream)
+
+    def record_panel_event(self):
+        return self.panel_stream.record_event()
+
+    def main_wait_event(self, ev):
+        self.stream.wait_event(ev)
 
     def alloc(self, n):
         return self.torch.empty(n, dtype=self.torch.float64, device="cuda")
@@ -113,6 +141,47 @@ class DistCholesky:
         self.be.update(PJ, self.rows[J], self.nb, (Jp - J) * self.nb, self.panel(Jp), self.rows[Jp])
 
     def factor(self):
+        if self.lookahead and hasattr(self.be, "on_panel_stream"):
+            return self._factor_two_streams()
+        return self._factor_one_stream()
+
+    def _factor_two_streams(self):
+        """Look-ahead with the critical path on its own (high-priority) stream: while the main stream applies
+        panel J to the rank's remaining panels, the panel stream updates, factors and broadcasts panel J+1, so
+        neither the 1-CTA diagonal kernels of the panel factorisation nor the broadcast ever idle the GPU."""
+        nb, nP, me, be = self.nb, self.nP, self.rank, self.be
+        be.fence_main_to_panel()
+        with be.on_panel_stream():
+            if panel_owner(0, self.world) == me:
+                be.factor(self.panel(0), self.rows[0], nb, self.logdet, self.info, self.dinv_of[0])
+            cur = self._bcast(0)
+            ev = be.record_panel_event()              # panel 0 factored (owner) / enqueued
+        for J in range(nP):
+            PJ, work = cur
+            nxt = None
+            done_early = None
+            be.main_wait_event(ev)                    # main stream: panel J is factored (matters on its owner)
+            with be.on_panel_stream():
+                if work is not None:
+                    work.wait()                       # panel stream waits for panel J
+                be.fence_main_to_panel()              # ... and for the main stream's updates of iteration J-1
+                if J + 1 < nP:
+                    if panel_owner(J + 1, self.world) == me:
+                        self._update(PJ, J, J + 1)
+                        done_early = J + 1
+                        be.factor(self.panel(J + 1), self.rows[J + 1], nb, self.logdet, self.info, self.dinv_of[J + 1])
+                    nxt = self._bcast(J + 1)
+                    ev = be.record_panel_event()
+            if work is not None:
+                work.wait()                           # main stream waits for the broadcast of panel J as well
+            for Jp in self.mine:
+                if Jp > J and Jp != done_early:
+                    self._update(PJ, J, Jp)
+            cur = nxt
+        be.fence_panel_to_main()
+        return self
+
+    def _factor_one_stream(self):
         nb, nP, me = self.nb, self.nP, self.rank
         if panel_owner(0, self.world) == me:
             self.be.factor(self.panel(0), self.rows[0], nb, self.logdet, self.info, self.dinv_of[0])
