@@ -97,7 +97,6 @@ struct GemmArgs {
   int kl0, kl_x, kl_y;    // contraction length (multiple of 16)
   double alpha, beta;
   const int* bmap;        // optional: launch batch index -> matrix index
-  int dbg;
 };
 int g3_gemm_launch(g3_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int B);
 

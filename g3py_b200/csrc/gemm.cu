@@ -12,7 +12,6 @@
 // the reference does these through LAPACK dpotrf and Theano's Murray reverse mode
 // (g3py/libs/tensors.py:198,224-260).
 #include "g3b_internal.cuh"
-#include <cstdlib>
 
 namespace {
 
@@ -125,7 +124,7 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 
   // Pull the D tile towards L2 while the main loop runs (read-modify-write epilogue).
-  if (g.beta != 0.0 && !(g.dbg & 1)) {
+  if (g.beta != 0.0) {
     for (int l = tid; l < G3_BM * 8; l += 256) {
       const double* p = Dt + (long long)(l >> 3) * g.ldd + (l & 7) * 16;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -151,7 +150,6 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (tid == 0 && kt >= 1 && kt - 1 + G3_STAGES < nk) {
       const int sp = (kt - 1) % G3_STAGES;
       mbar_wait(empty_bar(sp), (uint32_t)(((kt - 1) / G3_STAGES) & 1));
-      if (g.dbg & 8) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       issue(kt - 1 + G3_STAGES);
     }
     mbar_wait(full_bar(s), ph);
@@ -176,10 +174,9 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // TMA refill (async proxy) could overwrite the stage under the last fragment loads (seen as rare, per-warp
     // garbage in the b[3] fragment).  The proxy fence drains this thread's loads and orders them before the
     // async-proxy write that the arrive enables.
-    if (!(g.dbg & 32)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_bar(s));
-    if (g.dbg & 16) __syncthreads();
   }
 
   // ---- epilogue ------------------------------------------------------------------------
@@ -215,19 +212,9 @@ int g3_gemm_launch(g3_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   long long ntiles = a.mode == 0 ? (long long)a.ntx * a.nty : (long long)a.ntx * (a.ntx + 1) / 2;
   if (ntiles <= 0 || B <= 0) return 0;
   dim3 grid((unsigned)(ntiles * 2), (unsigned)B, 1);
-  static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("G3_DBG"); dbg = e ? atoi(e) : 0; }
-  GemmArgs a2 = a;
-  a2.dbg = dbg;
-  static bool big = false;
-  if ((dbg & 4) && !big) {
-    G3_CUDA(ctx, cudaFuncSetAttribute(dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
-    big = true;
-  }
   g3_prof_begin(ctx, G3_PROF_GEMM);
-  dgemm_nt_kernel<<<grid, 256, (dbg & 4) ? 140 * 1024 : kSmemBytes, ctx->stream>>>(tmA, tmB, a2);
+  dgemm_nt_kernel<<<grid, 256, kSmemBytes, ctx->stream>>>(tmA, tmB, a);
   g3_prof_end(ctx);
   G3_LAUNCH_CHECK(ctx);
-  if (dbg & 2) G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }

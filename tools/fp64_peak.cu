@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/fp64_peak tools/fp64_peak.cu
 // Microbenchmark: sustained FP64 rate of the DMMA.8x8x4 tensor pipe and of the DFMA pipe on one GPU.
 // Used only to record the fp64 roofline denominator (MEASURED_PEAKS.json has no fp64 entry).
 #include <cstdio>
