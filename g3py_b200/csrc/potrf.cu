@@ -22,31 +22,37 @@ constexpr int TS = G3_TILE;       // 128
 constexpr int LDS_ = TS + 1;      // padded row stride of the shared tile
 
 // One CTA per matrix: factor the diagonal tile j in place and build Linv (-> Dinv).
-// Blocked in shared memory with 32x32 sub-blocks so that only ~25 block-wide barriers are needed (the first version
-// eliminated one column per three barriers: 246 us per tile, all of it latency):
-//   A  for kb = 0..3:  one warp factors the 32x32 diagonal sub-block in registers (row per lane, shuffles) and
-//                      inverts it (column per lane); all warps solve the sub-blocks below and update the rest
-//   B  Linv off-diagonal sub-blocks by block forward substitution, X[I][J] = -Xd_I * sum_K L[I][K] X[K][J]
-// Shared tile S[128][129]: L at S[i][c] (c <= i); X = Linv strictly below the diagonal is stored transposed in the
-// strict upper part, X[i][c] = S[c][i] (c < i); its diagonal lives in xd[].
+// Blocked in shared memory with 32x32 sub-blocks; ~25 block-wide barriers in total (the first version eliminated
+// one column per three barriers: 246 us per tile, all of it latency):
+//   A  for kb = 0..3:  warp 0 factors the 32x32 diagonal sub-block in registers (row per lane, shuffles, rsqrt)
+//                      and inverts it (column per lane); all warps then solve the sub-blocks below and update
+//                      the rest with 4x4 register tiles (2 warps per 32x32 block)
+//   B  off-diagonal sub-blocks of Linv by block forward substitution, X[I][J] = -Xd_I * sum_K L[I][K] X[K][J]
+// Shared memory: S[128][129] holds L at S[i][c] (c <= i) and the off-diagonal blocks of X = Linv transposed in the
+// upper blocks (X[i][c] = S[c][i]); XT[4][32][33] holds the inverses of the diagonal sub-blocks, dense and
+// transposed (XT[b][c][k] = Xd_b[k][c], zero for k < c); Tm[3][32][33] is scratch.
 constexpr int SB = 32;           // sub-block
 constexpr int LDT = 33;          // scratch leading dimension
 
-__device__ __forceinline__ void warp_potrf32(double (&a)[SB], int lane, int& bad) {
-#pragma unroll
+// Cholesky of a 32x32 sub-block in shared memory by one warp (lane = row).  `blk` points at its (0,0) element,
+// leading dimension LDS_ (odd: a column is conflict-free across lanes).  inv_out[k] = 1 / L[k][k].
+__device__ __forceinline__ void warp_potrf32(double* blk, int lane, int& bad, double* inv_out) {
+  double* row = blk + lane * LDS_;
   for (int k = 0; k < SB; ++k) {
-    const double d = __shfl_sync(0xffffffffu, a[k], k);
+    const double d = blk[k * LDS_ + k];           // broadcast
     if (!(d > 0.0) && bad < 0) bad = k;
-    const double s = sqrt(d);
-    const double inv = 1.0 / s;
-    if (lane > k) a[k] *= inv;
-    else if (lane == k) a[k] = s;
-    const double lrk = a[k];
-#pragma unroll
+    const double inv = rsqrt(d);
+    const double s = d * inv;                     // sqrt(d); NaN for d <= 0, which is what a failed pivot must give
+    double lrk = row[k];
+    if (lane > k) { lrk *= inv; row[k] = lrk; }
+    else if (lane == k) { row[k] = s; inv_out[k] = inv; }
+    __syncwarp();
+#pragma unroll 4
     for (int c = k + 1; c < SB; ++c) {
-      const double lck = __shfl_sync(0xffffffffu, lrk, c);
-      if (lane >= c) a[c] -= lrk * lck;
+      const double lck = blk[c * LDS_ + k];       // broadcast: L[c][k], scaled above by lane c
+      if (lane >= c) row[c] -= lrk * lck;
     }
+    __syncwarp();
   }
 }
 
@@ -54,9 +60,10 @@ __global__ void __launch_bounds__(256)
 potrf_diag_kernel(double* __restrict__ A, int Np, long long strideA, int j, double* __restrict__ Dinv, int T,
                   double* __restrict__ U, double* __restrict__ logdet, int* __restrict__ info,
                   const int* __restrict__ bmap) {
-  extern __shared__ double S[];                 // [128][129] + scratch 3 x [32][33]
-  double* Tm = S + TS * LDS_;
-  __shared__ double xd[TS];
+  extern __shared__ double S[];                 // [128][129] | XT [4][32][33] | Tm [3][32][33]
+  double* XT = S + TS * LDS_;
+  double* Tm = XT + 4 * SB * LDT;
+  __shared__ double invd[TS];
   __shared__ int first_bad;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = bmap ? bmap[blockIdx.x] : (int)blockIdx.x;
@@ -68,71 +75,98 @@ potrf_diag_kernel(double* __restrict__ A, int Np, long long strideA, int j, doub
   }
   __syncthreads();
 
+  // 4x4 register tile of a 32x32 block: 64 threads (slot g) per block
+  const int g = tid >> 6, t64 = tid & 63, tr = (t64 >> 3) * 4, tc = (t64 & 7) * 4;
+
   // ---- phase A: blocked Cholesky ----------------------------------------------------------------
   for (int kb = 0; kb < TS / SB; ++kb) {
     const int o = kb * SB;
     if (warp == 0) {
-      double a[SB];
-#pragma unroll
-      for (int c = 0; c < SB; ++c) a[c] = (c <= lane) ? S[(o + lane) * LDS_ + o + c] : 0.0;
       int bad = -1;
-      warp_potrf32(a, lane, bad);
+      warp_potrf32(S + o * LDS_ + o, lane, bad, invd + o);
       if (lane == 0 && bad >= 0 && first_bad < 0) first_bad = o + bad;
-#pragma unroll
-      for (int c = 0; c < SB; ++c)
-        if (c <= lane) S[(o + lane) * LDS_ + o + c] = a[c];
       __syncwarp();
-      // inverse of the sub-block, column `lane` per lane: x[r] = X[r][lane]
-      double x[SB];
-#pragma unroll
+      // inverse of the sub-block, column `lane` per lane: x[r] = Xd[r][lane], kept in this lane's row of XT
+      // (XT[c = lane][k = r]); four partial sums break the dependent FMA chain
+      double* xrow = XT + (kb * SB + lane) * LDT;
+#pragma unroll 1
       for (int r = 0; r < SB; ++r) {
-        double acc = (r == lane) ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < SB; ++k)
-          if (k < r) acc -= S[(o + r) * LDS_ + o + k] * x[k];
-        x[r] = (r >= lane) ? acc / S[(o + r) * LDS_ + o + r] : 0.0;
-      }
-      __syncwarp();
-#pragma unroll
-      for (int r = 0; r < SB; ++r) {
-        if (r > lane) S[(o + lane) * LDS_ + o + r] = x[r];     // X[r][lane] -> S[lane][r]
-        else if (r == lane) xd[o + r] = x[r];
+        double p0 = (r == lane) ? 1.0 : 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+        const double* lrow = S + (o + r) * LDS_ + o;
+        int k = 0;
+        for (; k + 4 <= r; k += 4) {
+          p0 -= lrow[k + 0] * xrow[k + 0];
+          p1 -= lrow[k + 1] * xrow[k + 1];
+          p2 -= lrow[k + 2] * xrow[k + 2];
+          p3 -= lrow[k + 3] * xrow[k + 3];
+        }
+        for (; k < r; ++k) p0 -= lrow[k] * xrow[k];
+        xrow[r] = (r >= lane) ? ((p0 + p1) + (p2 + p3)) * invd[o + r] : 0.0;
       }
     }
     __syncthreads();
-    const int below = TS - o - SB;            // rows under the diagonal sub-block
-    if (below > 0) {
-      // A2: L[r][o+jj] = sum_{c <= jj} A[r][o+c] * Xd[jj][c]   (registers first: in-place)
-      double outv[12];
+    const int nbelow = TS / SB - kb - 1;          // sub-blocks under the diagonal one
+    if (nbelow > 0) {
+      // A2: L[I][kb] = A[I][kb] Xd^T :  out[r][jj] = sum_c A[r][o+c] * XT[c][jj]
+      double acc[4][4];
 #pragma unroll
-      for (int it = 0; it < 12; ++it) {
-        const int e = tid + it * 256;
-        outv[it] = 0.0;
-        if (e < below * SB) {
-          const int r = o + SB + e / SB, jj = e % SB;
-          double acc = S[r * LDS_ + o + jj] * xd[o + jj];
-          for (int c = 0; c < jj; ++c) acc += S[r * LDS_ + o + c] * S[(o + c) * LDS_ + o + jj];
-          outv[it] = acc;
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[i][q] = 0.0;
+      const int rowA = (kb + 1 + g) * SB + tr;
+      if (g < nbelow) {
+        for (int c = 0; c < SB; ++c) {
+          double pa[4], qb[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pa[i] = S[(rowA + i) * LDS_ + o + c];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) qb[q] = XT[(kb * SB + c) * LDT + tc + q];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][q] += pa[i] * qb[q];
         }
       }
       __syncthreads();
+      if (g < nbelow) {
 #pragma unroll
-      for (int it = 0; it < 12; ++it) {
-        const int e = tid + it * 256;
-        if (e < below * SB) {
-          const int r = o + SB + e / SB, jj = e % SB;
-          S[r * LDS_ + o + jj] = outv[it];
-        }
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) S[(rowA + i) * LDS_ + o + tc + q] = acc[i][q];
       }
       __syncthreads();
-      // A3: A[r][c] -= sum_k L[r][o+k] L[c][o+k]   for o+SB <= c <= r
-      for (int e = tid; e < below * below; e += 256) {
-        const int r = o + SB + e / below, c = o + SB + e % below;
-        if (c > r) continue;
-        double acc = 0.0;
-#pragma unroll 8
-        for (int k = 0; k < SB; ++k) acc += S[r * LDS_ + o + k] * S[c * LDS_ + o + k];
-        S[r * LDS_ + c] -= acc;
+      // A3: A[I][J] -= L[I][kb] L[J][kb]^T for kb < J <= I
+      const int npair = nbelow * (nbelow + 1) / 2;
+      for (int p0 = 0; p0 < npair; p0 += 4) {
+        const int p = p0 + g;
+        if (p < npair) {
+          int I = 0, J = 0, cnt = 0;                       // enumerate pairs (I, J), J <= I, relative to kb + 1
+          for (int ii = 0; ii < nbelow; ++ii)
+            for (int jj = 0; jj <= ii; ++jj, ++cnt)
+              if (cnt == p) { I = ii; J = jj; }
+          const int rI = (kb + 1 + I) * SB + tr, rJ = (kb + 1 + J) * SB + tc;
+          double c2[4][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c2[i][q] = 0.0;
+          for (int k = 0; k < SB; ++k) {
+            double pa[4], qb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pa[i] = S[(rI + i) * LDS_ + o + k];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) qb[q] = S[(rJ + q) * LDS_ + o + k];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) c2[i][q] += pa[i] * qb[q];
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (I != J || rJ + q <= rI + i) S[(rI + i) * LDS_ + rJ + q] -= c2[i][q];   // lower part only on diagonal blocks
+        }
       }
       __syncthreads();
     }
@@ -141,24 +175,64 @@ potrf_diag_kernel(double* __restrict__ A, int Np, long long strideA, int j, doub
   // ---- phase B: off-diagonal sub-blocks of X = L^-1 --------------------------------------------------
   for (int dist = 1; dist < TS / SB; ++dist) {
     const int nblk = TS / SB - dist;
-    // T[I][J] = sum_{k in [J*32, I*32)} L[r][k] X[k][c]
-    for (int e = tid; e < nblk * SB * SB; e += 256) {
-      const int blk = e / (SB * SB), rr = (e / SB) % SB, cc = e % SB;
-      const int J = blk, I = blk + dist;
-      const int r = I * SB + rr, c = J * SB + cc;
-      double acc = S[r * LDS_ + c] * xd[c];                       // k == c
-      for (int k = c + 1; k < I * SB; ++k) acc += S[r * LDS_ + k] * S[c * LDS_ + k];   // X[k][c] = S[c][k], k > c
-      Tm[(blk * SB + rr) * LDT + cc] = acc;
+    const int J = g, I = g + dist;
+    if (g < nblk) {
+      // T[rr][cc] = sum_{k in [J*32, I*32)} L[I*32+rr][k] X[k][J*32+cc]
+      double acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[i][q] = 0.0;
+      for (int k = 0; k < SB; ++k) {                         // K == J: X[k][c] = XT[J][c][k]
+        double pa[4], qb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pa[i] = S[(I * SB + tr + i) * LDS_ + J * SB + k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) qb[q] = XT[(J * SB + tc + q) * LDT + k];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[i][q] += pa[i] * qb[q];
+      }
+      for (int k = (J + 1) * SB; k < I * SB; ++k) {          // K > J: X[k][c] = S[c][k]
+        double pa[4], qb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pa[i] = S[(I * SB + tr + i) * LDS_ + k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) qb[q] = S[(J * SB + tc + q) * LDS_ + k];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[i][q] += pa[i] * qb[q];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Tm[(g * SB + tr + i) * LDT + tc + q] = acc[i][q];
     }
     __syncthreads();
-    // X[I][J] = -Xd_I T   ->  X[r][c] stored at S[c][r]
-    for (int e = tid; e < nblk * SB * SB; e += 256) {
-      const int blk = e / (SB * SB), cc = (e / SB) % SB, rr = e % SB;   // rr fastest: S[c][r] writes coalesce in banks
-      const int J = blk, I = blk + dist;
-      const int r = I * SB + rr, c = J * SB + cc;
-      double acc = xd[r] * Tm[(blk * SB + rr) * LDT + cc];
-      for (int m = 0; m < rr; ++m) acc += S[(I * SB + m) * LDS_ + r] * Tm[(blk * SB + m) * LDT + cc];  // Xd_I[rr][m] = S[m][r]
-      S[c * LDS_ + r] = -acc;
+    if (g < nblk) {
+      // X[I][J] = -Xd_I T :  out[rr][cc] = -sum_m XT[I][m][rr] * T[m][cc]   ->  S[c][r]
+      double acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[i][q] = 0.0;
+      for (int m = 0; m < SB; ++m) {
+        double pa[4], qb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pa[i] = XT[(I * SB + m) * LDT + tr + i];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) qb[q] = Tm[(g * SB + m) * LDT + tc + q];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[i][q] += pa[i] * qb[q];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) S[(J * SB + tc + q) * LDS_ + I * SB + tr + i] = -acc[i][q];
     }
     __syncthreads();
   }
@@ -168,7 +242,9 @@ potrf_diag_kernel(double* __restrict__ A, int Np, long long strideA, int j, doub
   for (int idx = tid; idx < TS * TS; idx += 256) {
     const int r = idx >> 7, c = idx & 127;
     At[(long long)r * Np + c] = (c <= r) ? S[r * LDS_ + c] : 0.0;
-    Dj[idx] = (c < r) ? S[c * LDS_ + r] : (c == r ? xd[r] : 0.0);
+    double xv = 0.0;
+    if (c <= r) xv = ((r >> 5) == (c >> 5)) ? XT[((r >> 5) * SB + (c & 31)) * LDT + (r & 31)] : S[c * LDS_ + r];
+    Dj[idx] = xv;
   }
   (void)U;
   if (tid < 32) {
@@ -260,7 +336,7 @@ trsv_bwd_step_kernel(const double* __restrict__ L, const double* __restrict__ Di
 
 }  // namespace
 
-static constexpr int kDiagSmem = (TS * LDS_ + 3 * SB * LDT) * (int)sizeof(double);
+static constexpr int kDiagSmem = (TS * LDS_ + 7 * SB * LDT) * (int)sizeof(double);
 
 static GemmArgs gemm_zero() {
   GemmArgs g;
