@@ -461,3 +461,33 @@ def test_c4_full_size_properties(ctx):
     out = gp.predict(th, space=X[:512], array=True, var=True, noise=False)
     resid = out["mean"] - y[:512]
     assert np.sqrt(np.mean(resid ** 2)) < 0.3 and np.all(out["variance"] >= 0) and np.all(out["variance"] < nat[1] * 5)
+
+
+def test_jitter_ladder_inside_grouped_batch():
+    """A 40-item batch (4 stream groups) in which every third item has a numerically singular K (noise 1e-30):
+    those run the ladder, the others must be untouched; every item equals its single-item evaluation."""
+    X, y, _ = orc.c2_inputs(384, 1)
+    X[192:] = X[:192]                                      # duplicated inputs: K is singular without noise
+    spec = {"kind": "gauss", "location": {"type": "Zero"}, "kernel": {"type": "SE"}}
+    gp = build_process(spec, X)
+    gp.observed(X, y)
+    op = orc.OracleProcess(spec, 3)
+    rng = np.random.default_rng(8)
+    B = 40
+    Th = np.tile(np.array([0.0, np.log(0.4), np.log(0.4), np.log(0.4), np.log(0.05)]), (B, 1)) + 0.05 * rng.standard_normal((B, 5))
+    Th[::3, 4] = np.log(1e-30)
+    lp, g, info = gp._eval_batch(Th)                         # log-likelihood part (the 1e-30 noise is behind the prior barrier)
+    assert np.all(gp.logprior_batch(Th)[::3] == -np.inf)
+    jit = (info["status"] & cabi.ST_JITTER) != 0
+    assert np.array_equal(jit, np.arange(B) % 3 == 0)
+    for b in (0, 1, 2, 3, 38, 39):
+        l1, g1, i1 = gp._eval_batch(Th[b:b + 1])
+        assert abs(l1[0] - lp[b]) <= 1e-12 * abs(lp[b]) and scaled_err(g1[0], g[b]) < 1e-10
+        assert i1["status"][0] == info["status"][b]
+        t = op.logp_terms(Th[b], X, y)
+        assert (t["info"] > 0) == bool(jit[b])
+        if not jit[b]:
+            assert abs(lp[b] - t["loglike"]) <= TOL * abs(t["loglike"])
+        else:
+            assert ((info["status"][b] >> 8) & 0xFF) == t["info"]
+            assert abs(info["logdet"][b] - t["logdet"]) <= 1e-6 * abs(t["logdet"])
