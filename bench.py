@@ -103,6 +103,11 @@ def cpu_reference_sample(n_evals, theta_seed=2):
     broadcast Gram, dpotrf, triangular solve, Murray reverse-mode Cholesky gradient.  n_evals theta rows
     of the same workload; returns (evals/s, seconds)."""
     from oracle import g3_oracle as orc
+    try:        # torchrun exports OMP_NUM_THREADS=1: give the CPU baseline every host core back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     X, y, Theta = orc.c2_inputs(N_OBS, B_THETA)
     spec = {"kind": "gauss", "location": {"type": "Bias"},
             "kernel": {"type": "sum", "k1": {"type": "SE"}, "k2": {"type": "MAT52"}}}
