@@ -284,7 +284,7 @@ def main():
                    "N": N, "D": D_IN, "B": B, "parallelism": "theta-batch sharded, %d rank(s), no collective" % world, "stream_groups": args.groups,
                    "l2": "inputs larger than L2 (working set %.1f GiB per GPU)" % (3 * B * N * N * 8 / 2 ** 30)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "note": "process.logp_dlogp_batch(Theta): NumPy in/out through ctypes, host O(N) terms included; host buffers are pageable NumPy arrays"},
+                "note": "process.logp_dlogp_batch(Theta): NumPy in/out through ctypes, host O(N) terms included; NumPy arrays staged through page-locked buffers inside the library (async DMA both ways)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["fp64_tflops"], "unit": "TFLOP/s",

@@ -38,6 +38,29 @@ void* g3_ws(g3_ctx* ctx, const char* name, size_t bytes) {
   return b.p;
 }
 
+void* g3_pinned(g3_ctx* ctx, const char* name, size_t bytes) {
+  g3_buf& b = ctx->pinned[name];
+  if (b.bytes >= bytes && b.p) return b.p;
+  if (b.p) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFreeHost(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+  }
+  size_t want = (bytes + 4095) & ~size_t(4095);
+  cudaError_t e = cudaHostAlloc(&b.p, want, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cudaHostAlloc(%s, %zu bytes) failed: %s", name, want, cudaGetErrorString(e));
+    ctx->err = buf;
+    b.p = nullptr;
+    cudaGetLastError();
+    return nullptr;
+  }
+  b.bytes = want;
+  return b.p;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -130,6 +153,7 @@ int g3_ctx_create(int device, g3_ctx** out) {
   c->own_stream = c->stream;
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
+  cudaEventCreateWithFlags(&c->ev_h2d, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->gev_start, cudaEventDisableTiming);
   for (int g = 0; g < G3_MAX_GROUPS; ++g) {
     cudaStreamCreateWithFlags(&c->gstream[g], cudaStreamNonBlocking);
@@ -150,6 +174,9 @@ int g3_ctx_destroy(g3_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->bufs)
     if (kv.second.p) cudaFree(kv.second.p);
+  for (auto& kv : ctx->pinned)
+    if (kv.second.p) cudaFreeHost(kv.second.p);
+  cudaEventDestroy(ctx->ev_h2d);
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   if (ctx->dX) cudaFree(ctx->dX);
   cudaEventDestroy(ctx->ev0);

@@ -41,6 +41,8 @@ struct g3_ctx {
   double* dX = nullptr;
   int N = 0, D = 0;
   std::map<std::string, g3_buf> bufs;  // grow-only named workspaces
+  std::map<std::string, g3_buf> pinned;  // grow-only page-locked host staging buffers (hot-path H2D / D2H)
+  cudaEvent_t ev_h2d = nullptr;        // last staged upload has left the pinned buffers
   g3_gp_state gp;
   void* encode_fn = nullptr;           // cuTensorMapEncodeTiled
   int sm_count = 148;
@@ -62,6 +64,7 @@ void g3_prof_end(g3_ctx* ctx);
 int g3_fail(g3_ctx* ctx, const char* what, cudaError_t e, const char* file, int line);
 int g3_fail_msg(g3_ctx* ctx, const std::string& msg);
 void* g3_ws(g3_ctx* ctx, const char* name, size_t bytes);   // returns nullptr on failure (err set)
+void* g3_pinned(g3_ctx* ctx, const char* name, size_t bytes);   // page-locked host staging, nullptr on failure
 int g3_make_tmap(g3_ctx* ctx, CUtensorMap* out, const double* base, uint64_t cols, uint64_t rows,
                  uint64_t batch, uint64_t ld, uint64_t batch_stride, uint32_t box_rows);
 

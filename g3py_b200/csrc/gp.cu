@@ -329,11 +329,19 @@ int g3_gp_upload(g3_ctx* ctx, const g3_kernel_desc* desc, int kind, const double
   ctx->gp.B = B;
   ctx->gp.want_grad = want_grad;
   ctx->gp.delta_stride = delta_stride;
-  if (P > 0)
-    G3_CUDA(ctx, cudaMemcpyAsync(w.theta, theta, sizeof(double) * (size_t)B * P, cudaMemcpyHostToDevice, ctx->stream));
-  G3_CUDA(ctx, cudaMemcpyAsync(w.delta, delta, sizeof(double) * (size_t)drows * N, cudaMemcpyHostToDevice, ctx->stream));
-  if (nu_or_NULL)
-    G3_CUDA(ctx, cudaMemcpyAsync(w.nu, nu_or_NULL, sizeof(double) * B, cudaMemcpyHostToDevice, ctx->stream));
+  // stage through page-locked memory so that the H2D copies are true async DMA (the caller's arrays are pageable)
+  const size_t n_th = (size_t)B * P, n_dl = (size_t)drows * N, n_nu = nu_or_NULL ? (size_t)B : 0;
+  double* stage = (double*)g3_pinned(ctx, "gp_h2d", sizeof(double) * (n_th + n_dl + n_nu + 1));
+  if (!stage) return -2;
+  G3_CUDA(ctx, cudaEventSynchronize(ctx->ev_h2d));          // previous upload has left the staging buffer
+  if (n_th) memcpy(stage, theta, sizeof(double) * n_th);
+  memcpy(stage + n_th, delta, sizeof(double) * n_dl);
+  if (n_nu) memcpy(stage + n_th + n_dl, nu_or_NULL, sizeof(double) * n_nu);
+  if (n_th) G3_CUDA(ctx, cudaMemcpyAsync(w.theta, stage, sizeof(double) * n_th, cudaMemcpyHostToDevice, ctx->stream));
+  G3_CUDA(ctx, cudaMemcpyAsync(w.delta, stage + n_th, sizeof(double) * n_dl, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_nu)
+    G3_CUDA(ctx, cudaMemcpyAsync(w.nu, stage + n_th + n_dl, sizeof(double) * n_nu, cudaMemcpyHostToDevice, ctx->stream));
+  G3_CUDA(ctx, cudaEventRecord(ctx->ev_h2d, ctx->stream));
   ctx->gp.valid = 1;
   return 0;
 }
@@ -438,16 +446,25 @@ int g3_gp_download(g3_ctx* ctx, double* beta, double* logdet, double* dtheta_or_
     G3_LAUNCH_CHECK(ctx);
     if ((rc = gp_after_potrf(ctx, w, B))) return rc;
   }
-  G3_CUDA(ctx, cudaMemcpyAsync(beta, w.beta, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream));
-  G3_CUDA(ctx, cudaMemcpyAsync(logdet, w.logdet, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream));
-  G3_CUDA(ctx, cudaMemcpyAsync(stat.data(), w.status, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
-  if (st.want_grad && dtheta_or_NULL && P > 0)
-    G3_CUDA(ctx, cudaMemcpyAsync(dtheta_or_NULL, w.dtheta, sizeof(double) * (size_t)B * P, cudaMemcpyDeviceToHost,
-                                 ctx->stream));
-  if (st.want_grad && ddelta_or_NULL)
-    G3_CUDA(ctx, cudaMemcpyAsync(ddelta_or_NULL, w.ddelta, sizeof(double) * (size_t)B * N, cudaMemcpyDeviceToHost,
-                                 ctx->stream));
+  // results come back through page-locked staging (async DMA), then one host memcpy into the caller's arrays
+  const bool get_th = st.want_grad && dtheta_or_NULL && P > 0, get_dl = st.want_grad && ddelta_or_NULL;
+  const size_t o_beta = 0, o_ld = (size_t)B, o_th = 2 * (size_t)B, o_dl = o_th + (get_th ? (size_t)B * P : 0);
+  const size_t o_st = o_dl + (get_dl ? (size_t)B * N : 0);
+  double* out = (double*)g3_pinned(ctx, "gp_d2h", sizeof(double) * (o_st + (size_t)B + 1));
+  if (!out) return -2;
+  G3_CUDA(ctx, cudaMemcpyAsync(out + o_beta, w.beta, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaMemcpyAsync(out + o_ld, w.logdet, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaMemcpyAsync(out + o_st, w.status, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  if (get_th)
+    G3_CUDA(ctx, cudaMemcpyAsync(out + o_th, w.dtheta, sizeof(double) * (size_t)B * P, cudaMemcpyDeviceToHost, ctx->stream));
+  if (get_dl)
+    G3_CUDA(ctx, cudaMemcpyAsync(out + o_dl, w.ddelta, sizeof(double) * (size_t)B * N, cudaMemcpyDeviceToHost, ctx->stream));
   G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(beta, out + o_beta, sizeof(double) * B);
+  memcpy(logdet, out + o_ld, sizeof(double) * B);
+  memcpy(stat.data(), out + o_st, sizeof(int) * B);
+  if (get_th) memcpy(dtheta_or_NULL, out + o_th, sizeof(double) * (size_t)B * P);
+  if (get_dl) memcpy(ddelta_or_NULL, out + o_dl, sizeof(double) * (size_t)B * N);
   if (status) {
     for (int b = 0; b < B; ++b) {
       int s = stat[b];
