@@ -34,26 +34,73 @@ constexpr int LDS_ = TS + 1;      // padded row stride of the shared tile
 constexpr int SB = 32;           // sub-block
 constexpr int LDT = 33;          // scratch leading dimension
 
-// Cholesky of a 32x32 sub-block in shared memory by one warp (lane = row).  `blk` points at its (0,0) element,
-// leading dimension LDS_ (odd: a column is conflict-free across lanes).  inv_out[k] = 1 / L[k][k].
+// Cholesky of a 32x32 sub-block by one warp, left-looking, lane = row: the lane keeps its row in registers
+// (all indices static after unrolling) and publishes each finished entry to shared memory, from where the
+// pivot row L[k][0..k) is read as a broadcast.  inv_out[k] = 1 / L[k][k].
 __device__ __forceinline__ void warp_potrf32(double* blk, int lane, int& bad, double* inv_out) {
-  double* row = blk + lane * LDS_;
+  double rw[SB];
+#pragma unroll
+  for (int c = 0; c < SB; ++c) rw[c] = blk[lane * LDS_ + c];     // entries above the diagonal are never used
+#pragma unroll
   for (int k = 0; k < SB; ++k) {
-    const double d = blk[k * LDS_ + k];           // broadcast
+    double p0 = rw[k], p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+    for (int m = 0; m < SB; m += 4) {
+      if (m + 0 < k) p0 -= rw[m + 0] * blk[k * LDS_ + m + 0];
+      if (m + 1 < k) p1 -= rw[m + 1] * blk[k * LDS_ + m + 1];
+      if (m + 2 < k) p2 -= rw[m + 2] * blk[k * LDS_ + m + 2];
+      if (m + 3 < k) p3 -= rw[m + 3] * blk[k * LDS_ + m + 3];
+    }
+    const double v = (p0 + p1) + (p2 + p3);
+    const double d = __shfl_sync(0xffffffffu, v, k);
     if (!(d > 0.0) && bad < 0) bad = k;
     const double inv = rsqrt(d);
-    const double s = d * inv;                     // sqrt(d); NaN for d <= 0, which is what a failed pivot must give
-    double lrk = row[k];
-    if (lane > k) { lrk *= inv; row[k] = lrk; }
-    else if (lane == k) { row[k] = s; inv_out[k] = inv; }
-    __syncwarp();
-#pragma unroll 4
-    for (int c = k + 1; c < SB; ++c) {
-      const double lck = blk[c * LDS_ + k];       // broadcast: L[c][k], scaled above by lane c
-      if (lane >= c) row[c] -= lrk * lck;
-    }
+    const double lv = (lane == k) ? d * inv : v * inv;   // sqrt(d) on the diagonal; NaN for d <= 0 (a failed pivot)
+    rw[k] = lv;
+    if (lane >= k) blk[lane * LDS_ + k] = lv;
+    if (lane == k) inv_out[k] = inv;
     __syncwarp();
   }
+}
+
+// One thread per row: solve  y L^T = a  with the 32x32 lower-triangular block L (broadcast reads), y overwrites a.
+__device__ __forceinline__ void row_trsolve32(double* prow, const double* Lblk, const double* inv) {
+  double y[SB];
+#pragma unroll
+  for (int q = 0; q < SB; ++q) y[q] = prow[q];
+#pragma unroll
+  for (int q = 0; q < SB; ++q) {
+    double p0 = y[q], p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+    for (int c = 0; c < SB; c += 4) {
+      if (c + 0 < q) p0 -= y[c + 0] * Lblk[q * LDS_ + c + 0];
+      if (c + 1 < q) p1 -= y[c + 1] * Lblk[q * LDS_ + c + 1];
+      if (c + 2 < q) p2 -= y[c + 2] * Lblk[q * LDS_ + c + 2];
+      if (c + 3 < q) p3 -= y[c + 3] * Lblk[q * LDS_ + c + 3];
+    }
+    y[q] = ((p0 + p1) + (p2 + p3)) * inv[q];
+  }
+#pragma unroll
+  for (int q = 0; q < SB; ++q) prow[q] = y[q];
+}
+
+// One thread per column c of Xd = L^-1 (32x32 lower): x[r] = Xd[r][c]; written to xt[r] (= XT[c][r]).
+__device__ __forceinline__ void col_inverse32(const double* Lblk, const double* inv, int c, double* xt) {
+  double x[SB];
+#pragma unroll
+  for (int r = 0; r < SB; ++r) {
+    double p0 = (r == c) ? 1.0 : 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+    for (int k = 0; k < SB; k += 4) {
+      if (k + 0 < r) p0 -= Lblk[r * LDS_ + k + 0] * x[k + 0];
+      if (k + 1 < r) p1 -= Lblk[r * LDS_ + k + 1] * x[k + 1];
+      if (k + 2 < r) p2 -= Lblk[r * LDS_ + k + 2] * x[k + 2];
+      if (k + 3 < r) p3 -= Lblk[r * LDS_ + k + 3] * x[k + 3];
+    }
+    x[r] = (r >= c) ? ((p0 + p1) + (p2 + p3)) * inv[r] : 0.0;
+  }
+#pragma unroll
+  for (int r = 0; r < SB; ++r) xt[r] = x[r];
 }
 
 __global__ void __launch_bounds__(256)
@@ -85,55 +132,12 @@ potrf_diag_kernel(double* __restrict__ A, int Np, long long strideA, int j, doub
       int bad = -1;
       warp_potrf32(S + o * LDS_ + o, lane, bad, invd + o);
       if (lane == 0 && bad >= 0 && first_bad < 0) first_bad = o + bad;
-      __syncwarp();
-      // inverse of the sub-block, column `lane` per lane: x[r] = Xd[r][lane], kept in this lane's row of XT
-      // (XT[c = lane][k = r]); four partial sums break the dependent FMA chain
-      double* xrow = XT + (kb * SB + lane) * LDT;
-#pragma unroll 1
-      for (int r = 0; r < SB; ++r) {
-        double p0 = (r == lane) ? 1.0 : 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-        const double* lrow = S + (o + r) * LDS_ + o;
-        int k = 0;
-        for (; k + 4 <= r; k += 4) {
-          p0 -= lrow[k + 0] * xrow[k + 0];
-          p1 -= lrow[k + 1] * xrow[k + 1];
-          p2 -= lrow[k + 2] * xrow[k + 2];
-          p3 -= lrow[k + 3] * xrow[k + 3];
-        }
-        for (; k < r; ++k) p0 -= lrow[k] * xrow[k];
-        xrow[r] = (r >= lane) ? ((p0 + p1) + (p2 + p3)) * invd[o + r] : 0.0;
-      }
     }
     __syncthreads();
     const int nbelow = TS / SB - kb - 1;          // sub-blocks under the diagonal one
     if (nbelow > 0) {
-      // A2: L[I][kb] = A[I][kb] Xd^T :  out[r][jj] = sum_c A[r][o+c] * XT[c][jj]
-      double acc[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[i][q] = 0.0;
-      const int rowA = (kb + 1 + g) * SB + tr;
-      if (g < nbelow) {
-        for (int c = 0; c < SB; ++c) {
-          double pa[4], qb[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) pa[i] = S[(rowA + i) * LDS_ + o + c];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) qb[q] = XT[(kb * SB + c) * LDT + tc + q];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[i][q] += pa[i] * qb[q];
-        }
-      }
-      __syncthreads();
-      if (g < nbelow) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) S[(rowA + i) * LDS_ + o + tc + q] = acc[i][q];
-      }
+      // A2: rows below: L[r][o..o+32) = A[r][o..o+32) L_kk^-T, one thread per row (triangular solve)
+      if (tid < nbelow * SB) row_trsolve32(S + (o + SB + tid) * LDS_ + o, S + o * LDS_ + o, invd + o);
       __syncthreads();
       // A3: A[I][J] -= L[I][kb] L[J][kb]^T for kb < J <= I
       const int npair = nbelow * (nbelow + 1) / 2;
@@ -171,6 +175,13 @@ potrf_diag_kernel(double* __restrict__ A, int Np, long long strideA, int j, doub
       __syncthreads();
     }
   }
+
+  // ---- phase B0: inverses of the four diagonal sub-blocks, one thread per column ------------------------
+  if (tid < TS) {
+    const int blk = tid >> 5, c = tid & 31;
+    col_inverse32(S + (blk * SB) * LDS_ + blk * SB, invd + blk * SB, c, XT + (blk * SB + c) * LDT);
+  }
+  __syncthreads();
 
   // ---- phase B: off-diagonal sub-blocks of X = L^-1 --------------------------------------------------
   for (int dist = 1; dist < TS / SB; ++dist) {
