@@ -123,19 +123,27 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int kt = 0; kt < pre; ++kt) issue(kt);
   }
 
-  // Pull the D tile towards L2 while the main loop runs (read-modify-write epilogue).
-  if (g.beta != 0.0) {
-    for (int l = tid; l < G3_BM * 8; l += 256) {
-      const double* p = Dt + (long long)(l >> 3) * g.ldd + (l & 7) * 16;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    }
-  }
-
+  // beta != 0: the D tile enters through the accumulators (acc = (beta/alpha) * D, loaded while the TMA pipeline
+  // fills), so the epilogue is a pure store and no global-load latency sits between the last DMMA and the write.
   double acc[4][4][2];
+  if (g.beta != 0.0) {
+    const double sc = g.beta / g.alpha;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i) {
+      const double* rowp = Dt + (long long)(wm * 32 + i * 8 + grp) * g.ldd + wn * 32 + 2 * t4;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int j = 0; j < 4; ++j) {
+        const double2 v = *reinterpret_cast<const double2*>(rowp + j * 8);
+        acc[i][j][0] = sc * v.x;
+        acc[i][j][1] = sc * v.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  }
 
   // per-thread fragment offsets inside a stage: row*128 + ((chunk ^ (row&7)) << 4), row&7 == grp
   const uint32_t offA = (uint32_t)((wm * 32 + grp) * 128);
@@ -180,24 +188,13 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 
   // ---- epilogue ------------------------------------------------------------------------
-  const double alpha = g.alpha, beta = g.beta;
+  const double alpha = g.alpha;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     double* rowp = Dt + (long long)(wm * 32 + i * 8 + grp) * g.ldd + wn * 32 + 2 * t4;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      double2* p = reinterpret_cast<double2*>(rowp + j * 8);
-      double2 v;
-      if (beta != 0.0) {
-        v = *p;
-        v.x = beta * v.x + alpha * acc[i][j][0];
-        v.y = beta * v.y + alpha * acc[i][j][1];
-      } else {
-        v.x = alpha * acc[i][j][0];
-        v.y = alpha * acc[i][j][1];
-      }
-      *p = v;
-    }
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<double2*>(rowp + j * 8) = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
   }
 }
 
