@@ -52,7 +52,9 @@ def theta(name, op, X, y):
         if nm.endswith("Bias_Bias"):
             th[off:off + size] += np.mean(y) if name != "C3" else 0.0
         if nm.endswith("SIN_rate"):
-            th[off:off + size] = np.log(0.1)
+            th[off:off + size] = np.log(0.05)
+        if nm.endswith("Noise_var") and name == "C3":
+            th[off:off + size] = np.log(0.05)
         if nm.endswith("SIN_freq"):
             th[off:off + size] = np.log(0.2)
         if nm.endswith("Freedom_degree"):
@@ -70,6 +72,7 @@ def main():
         op = orc.OracleProcess(spec, X.shape[1])
         th = theta(name, op, X, y)
         t = op.logp_terms(th, X, y)
+        assert t["info"] == 0, (name, "golden theta must factor without the jitter ladder")
         rec = {"spec": spec, "N": N, "theta": th.tolist(), "layout": op.layout(),
                "logp": op.logp(th, X, y), "beta": t["beta"], "logdet": t["logdet"], "det_m": t["det_m"],
                "dlogp": op.dlogp(th, X, y).tolist(), "dlogp_murray": op.dlogp(th, X, y, method="murray").tolist()}

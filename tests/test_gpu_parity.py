@@ -491,3 +491,33 @@ def test_jitter_ladder_inside_grouped_batch():
         else:
             assert ((info["status"][b] >> 8) & 0xFF) == t["info"]
             assert abs(info["logdet"][b] - t["logdet"]) <= 1e-6 * abs(t["logdet"])
+
+
+def test_posterior_under_jitter_ladder():
+    """A theta whose K needs the jitter ladder (periodic x SE with little noise): the posterior path must use the
+    same repaired factor as the oracle's cholesky_robust."""
+    x, y, xs = orc.c3_inputs(192, 41)
+    spec = SPECS["C3"]
+    gp = build_process(spec, x)
+    gp.observed(x, y)
+    op = orc.OracleProcess(spec, 1)
+    lay = [n for n, s, _ in gp.layout for _ in range(s)]
+    th = np.zeros(gp.ndim)
+    th[lay.index("WGP_SIN_var")] = np.log(np.var(y))
+    th[lay.index("WGP_SIN_freq")] = np.log(0.2)
+    th[lay.index("WGP_SIN_rate")] = np.log(0.1)
+    th[lay.index("WGP_SE_rate")] = 0.0
+    th[lay.index("WGP_Noise_var")] = np.log(0.05 * np.var(y))
+    th[lay.index("WGP_BoxShift_shift")] = 0.1
+    th[lay.index("WGP_BoxShift_power")] = np.log(0.7)
+    t = op.logp_terms(th, x, y)
+    assert t["info"] > 0
+    ll, g, info = gp._eval_batch(th[None])
+    assert ((info["status"][0] >> 8) & 0xFF) == t["info"]
+    assert abs(info["logdet"][0] - t["logdet"]) <= 1e-7 * abs(t["logdet"])
+    assert abs(info["beta"][0] - t["beta"]) <= 1e-6 * abs(t["beta"])
+    for noise in (False, True):
+        post, _, _ = gp._posterior(th, xs, noise=noise)
+        po = op.posterior(th, xs, x, y, noise=noise, solver="chol")
+        assert scaled_err(post["location"], po["location"]) < 1e-6, noise
+        assert scaled_err(post["kernel_diag"], po["kernel_diag"]) < 1e-5, noise
