@@ -496,20 +496,18 @@ def test_jitter_ladder_inside_grouped_batch():
 def test_posterior_under_jitter_ladder():
     """A theta whose K needs the jitter ladder (periodic x SE with little noise): the posterior path must use the
     same repaired factor as the oracle's cholesky_robust."""
-    x, y, xs = orc.c3_inputs(192, 41)
-    spec = SPECS["C3"]
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as mg
+    spec, N = mg.SPECS["C3"]
+    x, y, xs = mg.data("C3", N)
     gp = build_process(spec, x)
     gp.observed(x, y)
     op = orc.OracleProcess(spec, 1)
-    lay = [n for n, s, _ in gp.layout for _ in range(s)]
-    th = np.zeros(gp.ndim)
-    th[lay.index("WGP_SIN_var")] = np.log(np.var(y))
-    th[lay.index("WGP_SIN_freq")] = np.log(0.2)
-    th[lay.index("WGP_SIN_rate")] = np.log(0.1)
-    th[lay.index("WGP_SE_rate")] = 0.0
-    th[lay.index("WGP_Noise_var")] = np.log(0.05 * np.var(y))
-    th[lay.index("WGP_BoxShift_shift")] = 0.1
-    th[lay.index("WGP_BoxShift_power")] = np.log(0.7)
+    th = mg.theta("C3", op, x, y)
+    names = [n for n, s_, _ in op.layout() for _ in range(s_)]
+    th[names.index("SIN_rate")] = np.log(0.1)
+    th[names.index("Noise_var")] = np.log(0.05 * np.var(y))
     t = op.logp_terms(th, x, y)
     assert t["info"] > 0
     ll, g, info = gp._eval_batch(th[None])
