@@ -100,6 +100,11 @@ struct GemmArgs {
   int kl0, kl_x, kl_y;    // contraction length (multiple of 16)
   double alpha, beta;
   const int* bmap;        // optional: launch batch index -> matrix index
+  int tri_b;              // B operand is a lower-triangular 128x128 block (B[n][k] = 0 for k > n, K = 128):
+                          // a warp skips the k-tiles beyond its 32 output columns
+  int upper;              // bit0: tiles x == y are diagonal tiles of a symmetric result, bit1: tile x == 0 is,
+                          // (only their lower triangle is needed: the upper-right 64x64 quarter is not computed)
+                          // bit2: tiles with x < y are void (skipped entirely)
 };
 int g3_gemm_launch(g3_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int B);
 

@@ -84,6 +84,11 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     while ((long long)(x + 1) * (x + 2) / 2 <= tile) ++x;
     y = tile - (int)((long long)x * (x + 1) / 2);
   }
+  if ((g.upper & 4) && x < y) return;                       // void tile (strictly above the block diagonal)
+  const bool diag_tile = ((g.upper & 1) && x == y) || ((g.upper & 2) && x == 0);
+  // warps of the upper-right 64x64 quarter of a diagonal tile have nothing to compute; they only pace the ring
+  const bool idle = diag_tile && h == 0 && wn >= 2;
+  const int kt_lim = g.tri_b ? 2 * wn + 2 : 0x7fffffff;     // triangular B: k-tiles this warp's columns reach
   const int bidx = g.bmap ? g.bmap[blockIdx.y] : (int)blockIdx.y;
   const int a_row = g.a_r0 + x * g.a_rx + y * g.a_ry + h * G3_BM;
   const int b_row = g.b_r0 + x * g.b_rx + y * g.b_ry;
@@ -126,7 +131,7 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   // beta != 0: the D tile enters through the accumulators (acc = (beta/alpha) * D, loaded while the TMA pipeline
   // fills), so the epilogue is a pure store and no global-load latency sits between the last DMMA and the write.
   double acc[4][4][2];
-  if (g.beta != 0.0) {
+  if (g.beta != 0.0 && !idle) {
     const double sc = g.beta / g.alpha;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -162,6 +167,7 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     mbar_wait(full_bar(s), ph);
     const uint32_t st = smem_base + s * kStageBytes;
+    if (!idle && kt < kt_lim) {
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const uint32_t sw = c ? sw1 : sw0;
@@ -177,6 +183,7 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i][e], b[j][e]);
     }
+    }
     // Release the stage.  The LDS above are asynchronous: ptxas hoists the arrive right behind the last LDS
     // *issue*, and an mbarrier arrive does not wait for this warp's outstanding shared-memory reads, so the
     // TMA refill (async proxy) could overwrite the stage under the last fragment loads (seen as rare, per-warp
@@ -188,6 +195,7 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 
   // ---- epilogue ------------------------------------------------------------------------
+  if (idle) return;
   const double alpha = g.alpha;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

@@ -849,7 +849,7 @@ int g3_gp_posterior(g3_ctx* ctx, const g3_kernel_desc* desc, const double* Xs, i
     g.a_r0 = 0; g.a_rx = TS; g.ka0 = j * TS;
     g.b_r0 = j * TS; g.kb0 = 0;
     g.kl0 = TS;
-    g.alpha = 1.0; g.beta = 0.0;
+    g.alpha = 1.0; g.beta = 0.0; g.tri_b = 1;
     if ((rc = g3_gemm_launch(ctx, tmV, tmD, g, 1))) return rc;
   }
   // K** diagonal: every leaf is stationary, so diag(cov(space)) is the tree evaluated at d = 0

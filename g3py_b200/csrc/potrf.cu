@@ -385,7 +385,7 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
         g.a_r0 = j * TS; g.a_rx = TS;
         g.b_r0 = j * TS;
         g.ka0 = jo * TS; g.kb0 = jo * TS; g.kl0 = (j - jo) * TS;
-        g.alpha = -1.0; g.beta = 1.0; g.bmap = bmap;
+        g.alpha = -1.0; g.beta = 1.0; g.bmap = bmap; g.upper = 2;
         if ((rc = g3_gemm_launch(ctx, tmA, tmB, g, B))) return rc;
       }
       g3_prof_begin(ctx, G3_PROF_DIAG);
@@ -400,7 +400,7 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
         g.a_r0 = (j + 1) * TS; g.a_rx = TS; g.ka0 = j * TS;
         g.b_r0 = j * TS; g.kb0 = 0;
         g.kl0 = TS;
-        g.alpha = 1.0; g.beta = 0.0; g.bmap = bmap;
+        g.alpha = 1.0; g.beta = 0.0; g.bmap = bmap; g.tri_b = 1;
         if ((rc = g3_gemm_launch(ctx, tmA, tmD, g, B))) return rc;
       }
     }
@@ -412,7 +412,7 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
       g.a_r0 = je * TS; g.a_rx = TS;
       g.b_r0 = je * TS; g.b_ry = TS;
       g.ka0 = jo * TS; g.kb0 = jo * TS; g.kl0 = (je - jo) * TS;
-      g.alpha = -1.0; g.beta = 1.0; g.bmap = bmap;
+      g.alpha = -1.0; g.beta = 1.0; g.bmap = bmap; g.upper = 1;
       if ((rc = g3_gemm_launch(ctx, tmA, tmB, g, B))) return rc;
     }
   }
@@ -440,7 +440,7 @@ int g3_potrf_panel(g3_ctx* ctx, double* P, int rows, int nb, double* Dinv, doubl
       g.a_r0 = j * TS; g.a_rx = TS;
       g.b_r0 = j * TS;
       g.ka0 = 0; g.kb0 = 0; g.kl0 = j * TS;
-      g.alpha = -1.0; g.beta = 1.0;
+      g.alpha = -1.0; g.beta = 1.0; g.upper = 2;
       if ((rc = g3_gemm_launch(ctx, tmA, tmB, g, 1))) return rc;
     }
     g3_prof_begin(ctx, G3_PROF_DIAG);
@@ -455,7 +455,7 @@ int g3_potrf_panel(g3_ctx* ctx, double* P, int rows, int nb, double* Dinv, doubl
       g.a_r0 = (j + 1) * TS; g.a_rx = TS; g.ka0 = j * TS;
       g.b_r0 = j * TS; g.kb0 = 0;
       g.kl0 = TS;
-      g.alpha = 1.0; g.beta = 0.0;
+      g.alpha = 1.0; g.beta = 0.0; g.tri_b = 1;
       if ((rc = g3_gemm_launch(ctx, tmA, tmD, g, 1))) return rc;
     }
   }
@@ -475,7 +475,7 @@ int g3_syrk_panel(g3_ctx* ctx, const double* P, int rowsP, int nb, int row_off, 
   g.a_r0 = row_off; g.a_rx = TS;
   g.b_r0 = row_off; g.b_ry = TS;
   g.kl0 = nb;
-  g.alpha = -1.0; g.beta = 1.0;
+  g.alpha = -1.0; g.beta = 1.0; g.upper = 1 | 4;
   return g3_gemm_launch(ctx, tmA, tmB, g, 1);
 }
 
@@ -526,7 +526,7 @@ int g3_trtri_batched(g3_ctx* ctx, const double* L, double* U, int Np, int B, con
       g.a_r0 = 0; g.a_rx = TS; g.ka0 = i * TS;
       g.b_r0 = i * TS; g.kb0 = 0;
       g.kl0 = TS;
-      g.alpha = -1.0; g.beta = 0.0;
+      g.alpha = -1.0; g.beta = 0.0; g.tri_b = 1;
       if ((rc = g3_gemm_launch(ctx, tmU, tmD, g, B))) return rc;
     }
   }
@@ -547,7 +547,7 @@ int g3_lauum_batched(g3_ctx* ctx, const double* U, double* Kinv, int Np, int B) 
   g.b_r0 = 0; g.b_ry = TS;
   g.ka0 = 0; g.ka_x = TS; g.kb0 = 0; g.kb_x = TS;
   g.kl0 = Np; g.kl_x = -TS;
-  g.alpha = 1.0; g.beta = 0.0;
+  g.alpha = 1.0; g.beta = 0.0; g.upper = 1;
   return g3_gemm_launch(ctx, tmA, tmB, g, B);
 }
 
