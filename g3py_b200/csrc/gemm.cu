@@ -69,7 +69,9 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 2, t4 = lane & 3;
-  const int wm = warp & 1, wn = warp >> 1;
+  // warp -> (row group wm, column group wn); column groups are paired (0,3) and (1,2) on the same SM sub-partition
+  // (warp % 4) so that the k-tile skipping of a triangular B operand stays balanced across the four DMMA pipes
+  const int wm = warp & 1, wn = warp < 4 ? (warp >> 1) : 3 - ((warp - 4) >> 1);
 
   // ---- tile decode -------------------------------------------------------------------
   const int h = blockIdx.x & 1;  // which 64-row half of the 128-row block
@@ -86,8 +88,9 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   if ((g.upper & 4) && x < y) return;                       // void tile (strictly above the block diagonal)
   const bool diag_tile = ((g.upper & 1) && x == y) || ((g.upper & 2) && x == 0);
-  // warps of the upper-right 64x64 quarter of a diagonal tile have nothing to compute; they only pace the ring
-  const bool idle = diag_tile && h == 0 && wn >= 2;
+  // warps whose 32x32 block lies strictly above the diagonal of a diagonal tile have nothing to compute; they
+  // only pace the ring (rows h*64 + wm*32 .. +31, columns wn*32 .. +31)
+  const bool idle = diag_tile && wn > 2 * h + wm;
   const int kt_lim = g.tri_b ? 2 * wn + 2 : 0x7fffffff;     // triangular B: k-tiles this warp's columns reach
   const int bidx = g.bmap ? g.bmap[blockIdx.y] : (int)blockIdx.y;
   const int a_row = g.a_r0 + x * g.a_rx + y * g.a_ry + h * G3_BM;
