@@ -519,3 +519,48 @@ def test_posterior_under_jitter_ladder():
         po = op.posterior(th, xs, x, y, noise=noise, solver="chol")
         assert scaled_err(post["location"], po["location"]) < 1e-6, noise
         assert scaled_err(post["kernel_diag"], po["kernel_diag"]) < 1e-5, noise
+
+
+def test_cabi_error_convention(ctx):
+    """Bad arguments -> negative return code + message (never a crash); numerical trouble -> status bits only."""
+    import ctypes as C
+    lib = cabi.load()
+    X = np.random.default_rng(0).uniform(0, 1, size=(20, 2))
+    gp = g3.GP(X, g3.Zero(), g3.SE(X))
+    desc = gp.desc
+    th = np.ones((1, desc.n_theta))
+    # malformed descriptor: binary node without two operands
+    bad = cabi.KernelDesc()
+    bad.n_nodes, bad.n_theta = 1, 0
+    bad.nodes[0].op = cabi.K_SUM
+    with pytest.raises(g3.G3Error, match="malformed|child"):
+        ctx.gram(bad, X, None, np.zeros((1, 0)))
+    # leaf whose dims exceed D
+    bad2 = cabi.KernelDesc()
+    bad2.n_nodes, bad2.n_theta = 1, 4
+    n0 = bad2.nodes[0]
+    n0.op, n0.dim0, n0.dim1, n0.var_idx, n0.p0_idx, n0.p1_idx = cabi.K_SE, 0, 3, 0, 1, -1
+    with pytest.raises(g3.G3Error, match="dims"):
+        ctx.gram(bad2, X, None, np.ones((1, 4)))
+    # theta index outside theta
+    bad3 = cabi.KernelDesc()
+    bad3.n_nodes, bad3.n_theta = 1, 2
+    n0 = bad3.nodes[0]
+    n0.op, n0.dim0, n0.dim1, n0.var_idx, n0.p0_idx, n0.p1_idx = cabi.K_SE, 0, 2, 0, 1, -1
+    with pytest.raises(g3.G3Error, match="outside theta"):
+        ctx.gram(bad3, X, None, np.ones((1, 2)))
+    # logp before set_data on a fresh context, wrong delta length
+    c2 = g3.Context(0)
+    with pytest.raises(g3.G3Error, match="g3_set_data"):
+        c2.gp_upload(desc, 0, np.zeros(20), th)
+    c2.set_data(X)
+    with pytest.raises(ValueError):
+        c2.gp_logp_grad(desc, 0, np.zeros(19), th)
+    rc = lib.g3_gp_run(c2._h)                                   # nothing uploaded
+    assert rc < 0 and b"nothing uploaded" in lib.g3_last_error(c2._h)
+    # numerical trouble is not an error: NaN theta -> status bits, finite return code
+    r = c2.gp_logp_grad(desc, 0, np.zeros(20), np.full((1, desc.n_theta), np.nan))
+    assert r["status"][0] != 0
+    c2.close()
+    with pytest.raises(g3.G3Error):
+        g3.Context(99)                                          # no such device
