@@ -16,6 +16,7 @@ G3_MAX_DIM = 16
 
 # leaf / node opcodes (include/g3b.h)
 K_SE, K_OU, K_MAT32, K_MAT52, K_RQ, K_SIN, K_NOISE, K_WN = 1, 2, 3, 4, 5, 6, 7, 8
+K_COS, K_SINC, K_SM = 9, 10, 11
 K_SUM, K_PROD, K_SCALE, K_SHIFT = 16, 17, 18, 19
 KF_PROCESS_NOISE = 1
 

@@ -47,6 +47,26 @@ __device__ __forceinline__ void stage_x(const double* X1, const double* X2, int 
   }
 }
 
+constexpr double kPi2 = 9.869604401089358;   // pi^2 (kernels.py:10)
+
+// one factor of the product-form periodic kernels and its derivative with respect to freq
+//   COS / SM: cos(2 pi d f)              kernels.py:466-467,486-487
+//   SINC    : sin(2 pi^2 d f)/(2 pi^2 f d), 1 at d = 0   kernels.py:479-482
+__device__ __forceinline__ double periodic_factor(int op, double df, double fq) {
+  if (op == G3_K_SINC) {
+    const double b = 2.0 * kPi2 * df * fq;
+    return df != 0.0 ? sin(b) / b : 1.0;
+  }
+  return cospi(2.0 * df * fq);
+}
+__device__ __forceinline__ double periodic_dfactor(int op, double df, double fq, double fac) {
+  if (op == G3_K_SINC) {
+    const double b = 2.0 * kPi2 * df * fq;
+    return df != 0.0 ? (cos(b) - fac) / fq : 0.0;
+  }
+  return -sinpi(2.0 * df * fq) * (2.0 * M_PI * df);
+}
+
 // value of one leaf for 4 columns at once; same_diag[e] = element lies on the diagonal of cov(x, x)
 __device__ __forceinline__ void leaf_value4(const g3_knode& nd, const double* __restrict__ th,
                                             const double* __restrict__ x1row, const double* __restrict__ x2s,
@@ -55,6 +75,7 @@ __device__ __forceinline__ void leaf_value4(const g3_knode& nd, const double* __
   const double var = nd.var_idx >= 0 ? th[nd.var_idx] : nd.value;
   const int nd_ = nd.dim1 - nd.dim0;
   double d[4] = {0.0, 0.0, 0.0, 0.0};
+  double pr[4] = {1.0, 1.0, 1.0, 1.0};
   switch (nd.op) {
     case G3_K_SE:
     case G3_K_MAT32:
@@ -103,6 +124,22 @@ __device__ __forceinline__ void leaf_value4(const g3_knode& nd, const double* __
           for (int e = 0; e < 4; ++e) d[e] += (xi - x2[cc[e]] == 0.0) ? 1.0 : 0.0;
         }
       break;
+    case G3_K_COS:
+    case G3_K_SINC:
+    case G3_K_SM:
+      for (int k = 0; k < nd_; ++k) {
+        const double fq = th[nd.p1_idx + k];
+        const double r = nd.op == G3_K_SM ? th[nd.p0_idx + k] : 0.0;
+        const double xi = x1row[nd.dim0 + k];
+        const double* x2 = x2s + (nd.dim0 + k) * TS;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const double df = xi - x2[cc[e]];
+          pr[e] *= periodic_factor(nd.op, df, fq);
+          d[e] += df * df * r * r;
+        }
+      }
+      break;
     default:
       break;
   }
@@ -110,6 +147,13 @@ __device__ __forceinline__ void leaf_value4(const g3_knode& nd, const double* __
   for (int e = 0; e < 4; ++e) {
     double v;
     switch (nd.op) {
+      case G3_K_COS:
+      case G3_K_SINC:
+        v = var * pr[e];
+        break;
+      case G3_K_SM:
+        v = var * (exp(-2.0 * kPi2 * d[e]) * pr[e]);
+        break;
       case G3_K_SE:
       case G3_K_OU:
         v = var * exp(-d[e]);
@@ -353,6 +397,20 @@ gram_vjp_kernel(const __grid_constant__ g3_kernel_desc desc, const VjpArgs a, in
             for (int e = 0; e < 4; ++e) d[e] += (xi - x2[cc[e]] == 0.0) ? 1.0 : 0.0;
           }
         }
+        double pr[4] = {1.0, 1.0, 1.0, 1.0};
+        if (nd.op == G3_K_COS || nd.op == G3_K_SINC || nd.op == G3_K_SM) {
+          for (int k = 0; k < nd_; ++k) {
+            const double fq = th[nd.p1_idx + k], r = nd.op == G3_K_SM ? th[nd.p0_idx + k] : 0.0;
+            const double xi = x1row[nd.dim0 + k];
+            const double* x2 = x2s + (nd.dim0 + k) * TS;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const double df = xi - x2[cc[e]];
+              pr[e] *= periodic_factor(nd.op, df, fq);
+              d[e] += df * df * r * r;
+            }
+          }
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           double kk, dk = 0.0;  // kk = k(d) (unit variance), dk = d k / d d
@@ -365,6 +423,9 @@ gram_vjp_kernel(const __grid_constant__ g3_kernel_desc desc, const VjpArgs a, in
             case G3_K_RQ: { const double al = th[nd.p1_idx]; const double base = 1.0 + d[e] / al;
                             kk = pow(base, -al); dk = -kk / base; } break;
             case G3_K_SIN: kk = exp(2.0 * d[e]); dk = 0.0; break;
+            case G3_K_COS:
+            case G3_K_SINC: kk = pr[e]; break;
+            case G3_K_SM: kk = exp(-2.0 * kPi2 * d[e]) * pr[e]; break;
             case G3_K_NOISE: kk = sd[e] ? 1.0 : 0.0; break;
             case G3_K_WN: kk = a.same ? (sd[e] ? 1.0 : 0.0) : d[e]; break;
             default: kk = 0.0;
@@ -449,6 +510,29 @@ gram_vjp_kernel(const __grid_constant__ g3_kernel_desc desc, const VjpArgs a, in
             for (int e = 0; e < 4; ++e) s -= adj[n][e] * val[n][e] * fabs(xi - x2[cc[e]]);
             acc[(nd.p0_idx + k) * 256 + tid] += s;
           }
+        } else if (nd.op == G3_K_COS || nd.op == G3_K_SINC || nd.op == G3_K_SM) {
+          const double var = nd.var_idx >= 0 ? th[nd.var_idx] : nd.value;
+          for (int k = 0; k < nd_; ++k) {
+            const double fq = th[nd.p1_idx + k], xi = x1row[nd.dim0 + k];
+            const double* x2 = x2s + (nd.dim0 + k) * TS;
+            double sf = 0.0, sr = 0.0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const double df = xi - x2[cc[e]];
+              const double fac = periodic_factor(nd.op, df, fq);
+              double others = 1.0, dsum = 0.0;                  // product of the other dims' factors (and SM envelope)
+              for (int j2 = 0; j2 < nd_; ++j2) {
+                const double df2 = x1row[nd.dim0 + j2] - x2s[(nd.dim0 + j2) * TS + cc[e]];
+                if (j2 != k) others *= periodic_factor(nd.op, df2, th[nd.p1_idx + j2]);
+                if (nd.op == G3_K_SM) { const double r2 = th[nd.p0_idx + j2]; dsum += df2 * df2 * r2 * r2; }
+              }
+              const double env = nd.op == G3_K_SM ? exp(-2.0 * kPi2 * dsum) : 1.0;
+              sf += adj[n][e] * var * env * periodic_dfactor(nd.op, df, fq, fac) * others;
+              if (nd.op == G3_K_SM) sr += adj[n][e] * val[n][e] * (-4.0 * kPi2 * df * df * th[nd.p0_idx + k]);
+            }
+            acc[(nd.p1_idx + k) * 256 + tid] += sf;
+            if (nd.op == G3_K_SM) acc[(nd.p0_idx + k) * 256 + tid] += sr;
+          }
         } else if (nd.op == G3_K_SIN) {
           for (int k = 0; k < nd_; ++k) {
             const double fq = th[nd.p1_idx + k], r = th[nd.p0_idx + k], xi = x1row[nd.dim0 + k];
@@ -512,15 +596,16 @@ int g3_check_desc(g3_ctx* ctx, const g3_kernel_desc& d, int D) {
   for (int n = 0; n < d.n_nodes; ++n) {
     const g3_knode& nd = d.nodes[n];
     if (nd.op < G3_K_SUM) {
-      if (nd.op < G3_K_SE || nd.op > G3_K_WN) return g3_fail_msg(ctx, "kernel desc: unknown leaf op");
+      if (nd.op < G3_K_SE || nd.op > G3_K_SM) return g3_fail_msg(ctx, "kernel desc: unknown leaf op");
       if (nd.op != G3_K_NOISE && (nd.dim0 < 0 || nd.dim1 > D || nd.dim1 <= nd.dim0))
         return g3_fail_msg(ctx, "kernel desc: leaf dims outside [0, D)");
       const int w = nd.dim1 - nd.dim0;
       if (nd.var_idx >= d.n_theta) return g3_fail_msg(ctx, "kernel desc: var_idx outside theta");
-      const bool has_rate = nd.op != G3_K_NOISE && nd.op != G3_K_WN;
+      const bool has_rate = nd.op != G3_K_NOISE && nd.op != G3_K_WN && nd.op != G3_K_COS && nd.op != G3_K_SINC;
       if (has_rate && (nd.p0_idx < 0 || nd.p0_idx + w > d.n_theta)) return g3_fail_msg(ctx, "kernel desc: rate index outside theta");
       if (nd.op == G3_K_RQ && (nd.p1_idx < 0 || nd.p1_idx >= d.n_theta)) return g3_fail_msg(ctx, "kernel desc: alpha index outside theta");
-      if (nd.op == G3_K_SIN && (nd.p1_idx < 0 || nd.p1_idx + w > d.n_theta)) return g3_fail_msg(ctx, "kernel desc: freq index outside theta");
+      const bool has_freq = nd.op == G3_K_SIN || nd.op == G3_K_COS || nd.op == G3_K_SINC || nd.op == G3_K_SM;
+      if (has_freq && (nd.p1_idx < 0 || nd.p1_idx + w > d.n_theta)) return g3_fail_msg(ctx, "kernel desc: freq index outside theta");
       ++depth;
     } else if (nd.op == G3_K_SUM || nd.op == G3_K_PROD) {
       if (depth < 2) return g3_fail_msg(ctx, "kernel desc: malformed post-order tree");

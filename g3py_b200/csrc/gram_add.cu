@@ -57,13 +57,16 @@ __device__ __forceinline__ int build_leaf_table(const g3_kernel_desc& desc, cons
     t.flags = nd.flags;
     t.var = nd.var_idx >= 0 ? th[nd.var_idx] : nd.value;
     if (nd.op == G3_K_NOISE && skip_pn && (nd.flags & G3_KF_PROCESS_NOISE)) t.var = 0.0;
+    const bool has_freq = nd.op == G3_K_SIN || nd.op == G3_K_COS || nd.op == G3_K_SINC || nd.op == G3_K_SM;
     for (int k = 0; k < 4; ++k) {
       t.c[k] = 0.0; t.f[k] = 0.0; t.r[k] = 0.0;
-      if (k >= nd.dim0 && k < nd.dim1 && nd.p0_idx >= 0) {
-        const double r = th[nd.p0_idx + (k - nd.dim0)];
-        t.r[k] = r;
-        t.c[k] = (nd.op == G3_K_OU || nd.op == G3_K_SIN) ? r : 0.5 * r * r;
-        if (nd.op == G3_K_SIN) t.f[k] = th[nd.p1_idx + (k - nd.dim0)];
+      if (k >= nd.dim0 && k < nd.dim1) {
+        if (nd.p0_idx >= 0) {
+          const double r = th[nd.p0_idx + (k - nd.dim0)];
+          t.r[k] = r;
+          t.c[k] = (nd.op == G3_K_OU || nd.op == G3_K_SIN) ? r : (nd.op == G3_K_SM ? r * r : 0.5 * r * r);
+        }
+        if (has_freq) t.f[k] = th[nd.p1_idx + (k - nd.dim0)];
       }
     }
     if (nd.op == G3_K_RQ) t.f[0] = th[nd.p1_idx];
@@ -76,7 +79,7 @@ template <int DT>
 __device__ __forceinline__ void leaf_metric(const LeafTab& t, const double (&df)[DT][4], int same, double (&d)[4]) {
 #pragma unroll
   for (int e = 0; e < 4; ++e) d[e] = 0.0;
-  if (t.op == G3_K_SE || t.op == G3_K_MAT32 || t.op == G3_K_MAT52 || t.op == G3_K_RQ) {
+  if (t.op == G3_K_SE || t.op == G3_K_MAT32 || t.op == G3_K_MAT52 || t.op == G3_K_RQ || t.op == G3_K_SM) {
 #pragma unroll
     for (int k = 0; k < DT; ++k) {
       const double c = t.c[k];
@@ -113,6 +116,40 @@ __device__ __forceinline__ void leaf_metric(const LeafTab& t, const double (&df)
   }
 }
 
+constexpr double kPi2 = 9.869604401089358;   // pi^2
+
+__device__ __forceinline__ double pfactor(int op, double df, double fq) {      // see gram.cu periodic_factor
+  if (op == G3_K_SINC) {
+    const double b = 2.0 * kPi2 * df * fq;
+    return df != 0.0 ? sin(b) / b : 1.0;
+  }
+  return cospi(2.0 * df * fq);
+}
+__device__ __forceinline__ double pdfactor(int op, double df, double fq, double fac) {
+  if (op == G3_K_SINC) {
+    const double b = 2.0 * kPi2 * df * fq;
+    return df != 0.0 ? (cos(b) - fac) / fq : 0.0;
+  }
+  return -sinpi(2.0 * df * fq) * (2.0 * M_PI * df);
+}
+__device__ __forceinline__ bool is_product_leaf(int op) { return op == G3_K_COS || op == G3_K_SINC || op == G3_K_SM; }
+
+// product-form periodic leaves: fac[k][e] (1 outside the leaf's dims), pr[e] = prod_k fac
+template <int DT>
+__device__ __forceinline__ void leaf_product(const LeafTab& t, const double (&df)[DT][4], double (&fac)[DT][4], double (&pr)[4]) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) pr[e] = 1.0;
+#pragma unroll
+  for (int k = 0; k < DT; ++k) {
+    const bool in = k >= t.dim0 && k < t.dim1;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      fac[k][e] = in ? pfactor(t.op, df[k][e], t.f[k]) : 1.0;
+      pr[e] *= fac[k][e];
+    }
+  }
+}
+
 // k(d) (unit variance) and dk/dd
 __device__ __forceinline__ void leaf_k(const LeafTab& t, double d, bool on_diag, int same, double& kk, double& dk) {
   dk = 0.0;
@@ -124,6 +161,9 @@ __device__ __forceinline__ void leaf_k(const LeafTab& t, double d, bool on_diag,
                        dk = -(5.0 / 6.0) * (1.0 + s) * ex; } break;
     case G3_K_RQ: { const double al = t.f[0], base = 1.0 + d / al; kk = pow(base, -al); dk = -kk / base; } break;
     case G3_K_SIN: kk = exp(2.0 * d); break;
+    case G3_K_COS:
+    case G3_K_SINC: kk = 1.0; break;                       // times the product, applied by the caller
+    case G3_K_SM: kk = exp(-2.0 * kPi2 * d); break;        // envelope; times the product, applied by the caller
     case G3_K_NOISE: kk = on_diag ? 1.0 : 0.0; break;
     case G3_K_WN: kk = same ? (on_diag ? 1.0 : 0.0) : d; break;
     default: kk = 0.0;
@@ -178,11 +218,16 @@ gram_fwd_add_kernel(const __grid_constant__ g3_kernel_desc desc, const GramArgs 
       const LeafTab& t = tab[l];
       double d[4];
       leaf_metric<DT>(t, df, a.same, d);
+      double pr[4] = {1.0, 1.0, 1.0, 1.0};
+      if (is_product_leaf(t.op)) {
+        double fac[DT][4];
+        leaf_product<DT>(t, df, fac, pr);
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         double kk, dk;
         leaf_k(t, d[e], sd[e], a.same, kk, dk);
-        sum[e] += t.var * kk;
+        sum[e] += t.var * kk * pr[e];
       }
     }
     double v[4];
@@ -284,6 +329,35 @@ gram_vjp_add_kernel(const __grid_constant__ g3_kernel_desc desc, const VjpArgs a
       const LeafTab& t = tab[l];
       double d[4], kk[4], gk[4];            // gk = w * var * dk/dd
       leaf_metric<DT>(t, df, a.same, d);
+      if (is_product_leaf(t.op)) {
+        double fac[DT][4], pr[4], env[4];
+        leaf_product<DT>(t, df, fac, pr);
+        double svar2 = 0.0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          env[e] = t.op == G3_K_SM ? exp(-2.0 * kPi2 * d[e]) : 1.0;
+          svar2 += w[e] * env[e] * pr[e];
+        }
+        if (t.var_idx >= 0) acc[t.var_idx * 256 + tid] += svar2;
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+          if (k >= t.dim0 && k < t.dim1) {
+            double sf = 0.0, sr = 0.0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              double others = 1.0;
+#pragma unroll
+              for (int j2 = 0; j2 < DT; ++j2)
+                if (j2 != k) others *= fac[j2][e];
+              sf += w[e] * t.var * env[e] * pdfactor(t.op, df[k][e], t.f[k], fac[k][e]) * others;
+              sr += w[e] * t.var * env[e] * pr[e] * (-4.0 * kPi2 * df[k][e] * df[k][e] * t.r[k]);
+            }
+            acc[(t.p1_idx + k - t.dim0) * 256 + tid] += sf;
+            if (t.op == G3_K_SM) acc[(t.p0_idx + k - t.dim0) * 256 + tid] += sr;
+          }
+        }
+        continue;
+      }
       double svar = 0.0, salpha = 0.0;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {

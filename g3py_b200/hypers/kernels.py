@@ -10,7 +10,7 @@ from . import Hypers, HyperVar
 from .. import _cabi as cabi
 
 __all__ = ["Kernel", "KernelStationary", "KernelSum", "KernelProd", "KernelScale", "KernelShift", "KernelNoise", "WN",
-           "SE", "OU", "MAT32", "MAT52", "RQ", "SIN", "KernelPeriodic", "DescBuilder"]
+           "SE", "OU", "MAT32", "MAT52", "RQ", "SIN", "COS", "SINC", "SM", "KernelPeriodic", "DescBuilder"]
 
 
 class DescBuilder:
@@ -296,6 +296,32 @@ class KernelPeriodic(KernelStationary):
 
 class SIN(KernelPeriodic):           # kernels.py:470-472
     OPCODE = cabi.K_SIN
+
+    def compile(self, b, process_noise=False):
+        d0, d1, nd, vi, val = self._common(b)
+        p1 = b.slot(self.freq, nd)
+        p0 = b.slot(self.rate, nd)
+        return b.node(self.OPCODE, d0, d1, vi, p0, p1, 0, val)
+
+
+class COS(KernelPeriodic):           # kernels.py:462-467: rate is the constant 1.0, only freq is a hyper
+    OPCODE = cabi.K_COS
+
+    def __init__(self, x=None, name=None, var=None, freq=None):
+        super().__init__(x, name, var, freq, rate=1.0)
+
+    def compile(self, b, process_noise=False):
+        d0, d1, nd, vi, val = self._common(b)
+        p1 = b.slot(self.freq, nd)
+        return b.node(self.OPCODE, d0, d1, vi, -1, p1, 0, val)
+
+
+class SINC(COS):                     # kernels.py:475-482
+    OPCODE = cabi.K_SINC
+
+
+class SM(KernelPeriodic):            # kernels.py:485-487 (spectral mixture component)
+    OPCODE = cabi.K_SM
 
     def compile(self, b, process_noise=False):
         d0, d1, nd, vi, val = self._common(b)

@@ -41,6 +41,9 @@ enum {
   G3_K_SIN = 6,   /* var*exp(+2*sum_k rate_k*sin^2(pi*(x_ik-x_jk)*freq_k)) kernels.py:470-472 */
   G3_K_NOISE = 7, /* var*I when x1 is x2, zeros otherwise                  kernels.py:360-371 */
   G3_K_WN = 8,    /* var*I when x1 is x2, var*#equal coords otherwise      kernels.py:374-385 */
+  G3_K_COS = 9,   /* var*prod_k cos(2 pi (x_ik-x_jk) freq_k)                kernels.py:462-467 */
+  G3_K_SINC = 10, /* var*prod_k sinc_k, sinc = sin(2 pi^2 d f)/(2 pi^2 f d), 1 at d = 0   kernels.py:475-482 */
+  G3_K_SM = 11,   /* var*exp(-2 pi^2 sum_k d_k^2 rate_k^2)*prod_k cos(2 pi d_k freq_k)    kernels.py:485-487 */
   G3_K_SUM = 16, G3_K_PROD = 17, G3_K_SCALE = 18, G3_K_SHIFT = 19
 };
 
@@ -48,8 +51,8 @@ typedef struct {
   int32_t op;
   int32_t dim0, dim1;  /* [dim0, dim1) columns of X used by the metric */
   int32_t var_idx;     /* theta index of `var`; -1 = use `value` (KernelProd fixes k2.var = 1.0, kernels.py:215-219) */
-  int32_t p0_idx;      /* theta index of rate[dim1-dim0] (SE/OU/MAT32/MAT52/RQ/SIN), else -1 */
-  int32_t p1_idx;      /* theta index of RQ alpha, or of SIN freq[dim1-dim0], else -1 */
+  int32_t p0_idx;      /* theta index of rate[dim1-dim0] (SE/OU/MAT32/MAT52/RQ/SIN/SM), else -1 */
+  int32_t p1_idx;      /* theta index of RQ alpha, or of SIN/COS/SINC/SM freq[dim1-dim0], else -1 */
   int32_t flags;       /* G3_KF_PROCESS_NOISE on the KernelNoise leaf EllipticalProcess adds itself (elliptical.py:26-28) */
   double value;        /* fixed var (var_idx < 0) or the constant of SCALE / SHIFT */
 } g3_knode;

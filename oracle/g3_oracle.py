@@ -185,9 +185,11 @@ class _Leaf(KernelNode):
             hy.append(_Hyper(self.name + "_rate", self.nd, True))  # metrics.py:79-83
         if k == "RQ":
             hy.append(_Hyper(self.name + "_alpha", 1, True))   # kernels.py:394-397
-        if k == "SIN":                                         # kernels.py:446-454: freq created before rate
+        if k in ("SIN", "SM"):                                 # kernels.py:446-454: freq created before rate
             hy.append(_Hyper(self.name + "_freq", self.nd, True))
             hy.append(_Hyper(self.name + "_rate", self.nd, True))
+        if k in ("COS", "SINC"):                               # kernels.py:463,476: rate=1.0 constant, freq only
+            hy.append(_Hyper(self.name + "_freq", self.nd, True))
         self.hypers = tuple(hy)
 
     def _split(self, th):
@@ -232,6 +234,20 @@ class _Leaf(KernelNode):
         if k == "SIN":                                         # kernels.py:470-472 (positive exponent, as written)
             diff = _gram_broadcast(x1, x2, self.dims)
             return p["var"] * np.exp(2 * np.dot(np.sin(np.pi * diff * p["freq"]) ** 2, p["rate"]))
+        if k == "COS":                                         # kernels.py:466-467
+            diff = _gram_broadcast(x1, x2, self.dims)
+            return p["var"] * np.prod(np.cos(2 * np.pi * diff * p["freq"]), axis=2)
+        if k == "SINC":                                        # kernels.py:479-482 (pi2 = pi**2, as written)
+            diff = _gram_broadcast(x1, x2, self.dims)
+            pi2 = np.pi ** 2
+            with np.errstate(invalid="ignore", divide="ignore"):
+                sinc = np.sin(2 * pi2 * diff * p["freq"]) / (2 * pi2 * p["freq"] * diff)
+            return p["var"] * np.prod(np.where(diff != 0.0, sinc, 1.0), axis=2)
+        if k == "SM":                                          # kernels.py:486-487
+            diff = _gram_broadcast(x1, x2, self.dims)
+            pi2 = np.pi ** 2
+            return p["var"] * (np.exp(-2 * pi2 * np.dot(diff ** 2, p["rate"] ** 2))
+                               * np.prod(np.cos(2 * np.pi * diff * p["freq"]), axis=2))
         raise ValueError(k)
 
     def dcov(self, th, x1, x2, same, nan_quirk=False):
@@ -284,6 +300,26 @@ class _Leaf(KernelNode):
                 out.append(K * 2 * r[j] * np.sin(2 * np.pi * diff[:, :, j] * fr[j]) * np.pi * diff[:, :, j])
             for j in range(self.nd):
                 out.append(K * 2 * np.sin(np.pi * diff[:, :, j] * fr[j]) ** 2)
+            return out
+        if k in ("COS", "SINC", "SM"):
+            fr = p["freq"]
+            pi2 = np.pi ** 2
+            if k == "SINC":
+                b = 2 * pi2 * diff * fr
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    fac = np.where(diff != 0.0, np.sin(b) / b, 1.0)
+                    dfac = np.where(diff != 0.0, (np.cos(b) - fac) / fr, 0.0)
+            else:
+                a = 2 * np.pi * diff * fr
+                fac = np.cos(a)
+                dfac = -np.sin(a) * 2 * np.pi * diff
+            env = p["var"] * (np.exp(-2 * pi2 * np.dot(diff ** 2, p["rate"] ** 2)) if k == "SM" else 1.0)
+            for j in range(self.nd):                          # freq first (creation order)
+                others = np.prod(np.delete(fac, j, axis=2), axis=2)
+                out.append(env * dfac[:, :, j] * others)
+            if k == "SM":
+                for j in range(self.nd):
+                    out.append(K * (-4 * pi2 * diff[:, :, j] ** 2 * p["rate"][j]))
             return out
         raise ValueError(k)
 

@@ -44,6 +44,26 @@ def _eval_desc(desc, th, X1, X2, same, skip_pn=False, grad=False):
                 for j in range(w):
                     g[nd.p0_idx + j] = var * k * 2 * np.sin(np.pi * diff[:, :, j] * f[j]) ** 2
                     g[nd.p1_idx + j] = var * k * 2 * r[j] * np.sin(2 * np.pi * diff[:, :, j] * f[j]) * np.pi * diff[:, :, j]
+            elif op in (cabi.K_COS, cabi.K_SINC, cabi.K_SM):
+                f = th[nd.p1_idx:nd.p1_idx + w]
+                pi2 = np.pi ** 2
+                if op == cabi.K_SINC:
+                    bb = 2 * pi2 * diff * f
+                    with np.errstate(invalid="ignore", divide="ignore"):
+                        fac = np.where(diff != 0, np.sin(bb) / bb, 1.0)
+                        dfac = np.where(diff != 0, (np.cos(bb) - fac) / f, 0.0)
+                else:
+                    fac = np.cos(2 * np.pi * diff * f)
+                    dfac = -np.sin(2 * np.pi * diff * f) * 2 * np.pi * diff
+                env = 1.0
+                if op == cabi.K_SM:
+                    r = th[nd.p0_idx:nd.p0_idx + w]
+                    env = np.exp(-2 * pi2 * (diff ** 2 * r ** 2).sum(-1))
+                k = env * fac.prod(-1)
+                for j in range(w):
+                    g[nd.p1_idx + j] = var * env * dfac[:, :, j] * np.delete(fac, j, axis=2).prod(-1)
+                    if op == cabi.K_SM:
+                        g[nd.p0_idx + j] = var * k * (-4 * pi2 * diff[:, :, j] ** 2 * r[j])
             elif op == cabi.K_NOISE:
                 k = eye * (0.0 if (skip_pn and nd.flags & cabi.KF_PROCESS_NOISE) else 1.0)
             elif op == cabi.K_WN:

@@ -4,7 +4,7 @@ import numpy as np
 
 import g3py_b200 as g3
 
-LEAVES = {"SE": g3.SE, "OU": g3.OU, "MAT32": g3.MAT32, "MAT52": g3.MAT52, "RQ": g3.RQ, "SIN": g3.SIN, "WN": g3.WN,
+LEAVES = {"SE": g3.SE, "OU": g3.OU, "MAT32": g3.MAT32, "MAT52": g3.MAT52, "RQ": g3.RQ, "SIN": g3.SIN, "COS": g3.COS, "SINC": g3.SINC, "SM": g3.SM, "WN": g3.WN,
           "Noise": g3.KernelNoise}
 MAPS = {"Identity": g3.Identity, "LinearMapping": g3.LinearMapping, "LogShifted": g3.LogShifted,
         "BoxCoxShifted": g3.BoxCoxShifted, "BoxCoxLinear": g3.BoxCoxLinear, "ArcsinhLinear": g3.ArcsinhLinear,

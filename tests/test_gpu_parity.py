@@ -55,6 +55,11 @@ KSPECS = {
     "RQ": {"type": "RQ"},
     "SIN": {"type": "SIN"},
     "WN": {"type": "WN"},
+    "COS": {"type": "COS"},
+    "SINC": {"type": "SINC"},
+    "SM": {"type": "SM"},
+    "SM+COS+SINC": {"type": "sum", "k1": {"type": "sum", "k1": {"type": "SM"}, "k2": {"type": "COS"}}, "k2": {"type": "SINC"}},
+    "SMxSE": {"type": "prod", "k1": {"type": "SM"}, "k2": {"type": "SE"}},
     "SE+MAT52+Noise": {"type": "sum", "k1": {"type": "sum", "k1": {"type": "SE"}, "k2": {"type": "MAT52"}},
                        "k2": {"type": "Noise", "name": "Noise"}},
     "SINxSE": {"type": "prod", "k1": {"type": "SIN"}, "k2": {"type": "SE"}},

@@ -10,7 +10,7 @@ from oracle import g3_oracle as orc
 from helpers import build_kernel, scaled_err
 from fake_ctx import _eval_desc
 
-LEAVES = ["SE", "OU", "MAT32", "MAT52", "RQ", "SIN", "WN"]
+LEAVES = ["SE", "OU", "MAT32", "MAT52", "RQ", "SIN", "WN", "COS", "SINC", "SM"]
 
 
 def random_spec(rng, D, depth, names):
