@@ -258,7 +258,7 @@ def main():
             from g3py_b200.dist_potrf import run_dist_cholesky
             run_dist_cholesky(16384, nb=1024)                      # warm-up: NCCL channels, allocator
             r = run_dist_cholesky(args.dist_n, nb=1024)
-            one_gpu_tflops = 34.83                                  # measured, same code, world=1 (profiles/r01_dist_cholesky_131072.jsonl)
+            one_gpu_tflops = 35.59                                  # measured, same code, world=1 (profiles/r01_dist_cholesky_131072.jsonl)
             dist_metric = {"metric": "exact-GP Cholesky N=%d, block-cyclic (nb=1024, 1x%d grid, panel broadcast over NCCL, look-ahead)" % (args.dist_n, world),
                            "value": r["tflops"], "unit": "TFLOP/s", "ms_potrf": r["ms_potrf"], "ms_gram": r["ms_gram"],
                            "n_gpus": world, "per_gpu_frac_of_fp64_peak": r["tflops"] / world / peaks()["fp64_tflops"],
