@@ -85,8 +85,9 @@ enum { G3_POST_NOISE = 1,   /* noise=True: K** gets the Noise variance (elliptic
        G3_POST_COV = 2 };   /* also return the full M x M posterior covariance */
 
 /* ---- context --------------------------------------------------------------------------
- * One context = one device + one stream + cached workspaces.  Created lazily per process
- * (fork-safe: no CUDA state at library load).  Replaces nothing in the reference; it is
+ * One context = one device + one stream (+ group streams) + cached workspaces.  Created lazily per
+ * process (fork-safe: no CUDA state at library load).  A context is NOT thread-safe: use one per
+ * thread; different contexts (same or different devices) may be used concurrently.  Replaces nothing in the reference; it is
  * where theano's `perform` keeps device state between calls (libs/tensors.py:215-222). */
 int g3_ctx_create(int device, g3_ctx** out);
 int g3_ctx_destroy(g3_ctx* ctx);
