@@ -245,6 +245,10 @@ lp0, g0, _ = gp.logp_dlogp_batch(Theta)
 assert np.array_equal(lp, lp0) and np.array_equal(g, g0), (lp, lp0)
 lo, hi = sharding.shard_bounds(7, dist.get_rank(), dist.get_world_size())
 assert (hi - lo) in (3, 4) and calls_sharded == 1
+Xs = X[:9] + 0.05
+m, v = sharding.predict_sharded(gp, Theta[0], Xs)
+full = gp.predict(Theta[0], space=Xs, array=True, var=True)
+assert np.allclose(m, full["mean"], rtol=1e-13) and np.allclose(v, full["variance"], rtol=1e-13, atol=1e-15)
 if dist.get_rank() == 0:
     print("SHARD_OK", flush=True)
 dist.destroy_process_group()
