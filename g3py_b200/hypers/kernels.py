@@ -75,6 +75,12 @@ class Kernel(Hypers):
     def compile(self, b, process_noise=False):
         raise NotImplementedError
 
+    def nan_quirk_hypers(self):
+        """Hypers whose gradient the reference returns as 0: Theano's autodiff gives NaN for them on the diagonal
+        (d = 0) and `th_dlogp` scrubs NaN -> 0 (stochastic.py:308-309).  Confirmed by executing the reference
+        (tests/golden/reference_g3py.json).  Empty for most kernels."""
+        return []
+
     def cov(self, x1, x2=None, **hypers):
         """Numeric Kernel.cov through the device (kernels.py:106-110); hypers by bare name, natural space."""
         from ..processes import kernel_cov
@@ -123,6 +129,9 @@ class KernelOperation(Kernel):
         c = self.k.compile(b)
         return b.node(self.OP, dim0=c, value=self.element)
 
+    def nan_quirk_hypers(self):
+        return self.k.nan_quirk_hypers()
+
 
 class KernelScale(KernelOperation):
     OP = cabi.K_SCALE
@@ -164,6 +173,9 @@ class KernelComposition(Kernel):
         l = self.k1.compile(b)
         r = self.k2.compile(b, process_noise=process_noise)
         return b.node(self.OP, dim0=l, dim1=r)
+
+    def nan_quirk_hypers(self):
+        return self.k1.nan_quirk_hypers() + self.k2.nan_quirk_hypers()
 
 
 class KernelProd(KernelComposition):
@@ -236,9 +248,15 @@ class OU(KernelStationary):          # kernels.py:429-431 (ARD_L1 metric)
 class MAT32(KernelStationary):       # kernels.py:406-412
     OPCODE = cabi.K_MAT32
 
+    def nan_quirk_hypers(self):          # grad(sqrt(3 d)) at d = 0 is 0/0
+        return [self.rate] if isinstance(self.rate, HyperVar) else []
+
 
 class MAT52(KernelStationary):       # kernels.py:415-421
     OPCODE = cabi.K_MAT52
+
+    def nan_quirk_hypers(self):          # grad(sqrt(5 d)) at d = 0 is 0/0
+        return [self.rate] if isinstance(self.rate, HyperVar) else []
 
 
 class RQ(KernelStationary):          # kernels.py:388-403
@@ -318,6 +336,9 @@ class COS(KernelPeriodic):           # kernels.py:462-467: rate is the constant 
 
 class SINC(COS):                     # kernels.py:475-482
     OPCODE = cabi.K_SINC
+
+    def nan_quirk_hypers(self):          # the unselected switch branch sin(0)/0 has a NaN gradient (kernels.py:479-480)
+        return [self.freq] if isinstance(self.freq, HyperVar) else []
 
 
 class SM(KernelPeriodic):            # kernels.py:485-487 (spectral mixture component)

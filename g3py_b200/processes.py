@@ -44,9 +44,9 @@ class Consts:
     def __init__(self, strict=True):
         self.strict = strict
         if strict:
-            self.log_2pi = float(np.log(f32(2.0 * np.pi)))
+            self.log_2pi = float(f32(math.log(float(f32(2.0 * np.pi)))))
             self.pi = float(f32(np.pi))
-            self.log_2pi_student = float(np.log(f32(2.0) * f32(np.pi)))
+            self.log_2pi_student = float(f32(math.log(float(f32(2.0) * f32(np.pi)))))
             self.jitter = float(f32(1e-6))
             self.guard = float(f32(-1e30))
             self.fallback = float(f32(1e-10))
@@ -78,7 +78,7 @@ class StochasticProcess:
     """stochastic.py:20-201 — data handling, parameter dictionaries, bijection."""
 
     def __init__(self, space=None, order=None, inputs=None, outputs=None, hidden=None, index=None, name="SP",
-                 device=0, strict_constants=True, **kwargs):
+                 device=0, strict_constants=True, reference_nan_quirk=False, **kwargs):
         ndim = 1
         if space is not None:
             if hasattr(space, "shape"):
@@ -91,6 +91,9 @@ class StochasticProcess:
         self.name = name
         self.device = device
         self.consts = Consts(strict_constants)
+        # True: return 0 for the gradient components the reference's autodiff loses to NaN (Matern rates, SINC
+        # freq) instead of their analytic value -- literal drop-in behaviour for dlogp
+        self.reference_nan_quirk = bool(reference_nan_quirk)
         # the reference's 2-point dummy dataset (stochastic.py:46-56)
         self.space = np.array([[0.0, 1.0]] * ndim).T
         self.inputs = np.array([[0.0, 1.0]] * ndim).T
@@ -374,7 +377,7 @@ class EllipticalProcess(StochasticProcess):
             return delta[0], det_m, jac, False
         return delta, det_m, jac, True
 
-    def _eval_batch(self, Theta, inputs=None, outputs=None, want_grad=True):
+    def _eval_batch(self, Theta, inputs=None, outputs=None, want_grad=True, nan_quirk=None):
         """Core of logp/dlogp for a (B, P) array of theta (transformed space).  Returns
         (loglike (B,), dlogp (B,P) or None, info dict)."""
         Theta = np.atleast_2d(np.asarray(Theta, dtype=np.float64))
@@ -437,6 +440,9 @@ class EllipticalProcess(StochasticProcess):
             g_nat[:, self.f_degree.degree.offset] += d_r1 + d_r2
         g = np.where(self.positive_mask[None, :], g_nat * nat, g_nat)     # chain rule through exp
         g[failed | bad] = 0.0
+        if self.reference_nan_quirk if nan_quirk is None else nan_quirk:
+            for h in self.f_kernel_noise.nan_quirk_hypers():
+                g[:, h.offset:h.offset + h.size] = 0.0
         return ll, tt_to_num(g), info                                     # stochastic.py:308-309
 
     # ---- public methods (stochastic.py:365-366 binds th_logp/th_dlogp/th_loglike) -----------------
@@ -455,15 +461,15 @@ class EllipticalProcess(StochasticProcess):
         return float(ll[0])
 
     def dlogp(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
-              array=False):
+              array=False, reference_nan_quirk=None):
         theta = self._theta(params, array)
         if prior:
             return np.zeros(self.ndim)
-        _, g, _ = self._eval_batch(theta, inputs, outputs, want_grad=True)
+        _, g, _ = self._eval_batch(theta, inputs, outputs, want_grad=True, nan_quirk=reference_nan_quirk)
         return g[0]
 
-    def logp_dlogp(self, theta):
-        ll, g, _ = self._eval_batch(theta, want_grad=True)
+    def logp_dlogp(self, theta, reference_nan_quirk=None):
+        ll, g, _ = self._eval_batch(theta, want_grad=True, nan_quirk=reference_nan_quirk)
         return float(self.logprior_batch(theta)[0] + ll[0]), g[0]
 
     # batched entries replacing the per-theta loops of stochastic.py:515-564
@@ -475,13 +481,13 @@ class EllipticalProcess(StochasticProcess):
         ll, _, _ = self._eval_batch(Theta, want_grad=False)
         return lp + ll
 
-    def dlogp_batch(self, Theta):
-        _, g, _ = self._eval_batch(np.atleast_2d(Theta), want_grad=True)
+    def dlogp_batch(self, Theta, reference_nan_quirk=None):
+        _, g, _ = self._eval_batch(np.atleast_2d(Theta), want_grad=True, nan_quirk=reference_nan_quirk)
         return g
 
-    def logp_dlogp_batch(self, Theta):
+    def logp_dlogp_batch(self, Theta, reference_nan_quirk=None):
         Theta = np.atleast_2d(Theta)
-        ll, g, info = self._eval_batch(Theta, want_grad=True)
+        ll, g, info = self._eval_batch(Theta, want_grad=True, nan_quirk=reference_nan_quirk)
         return self.logprior_batch(Theta) + ll, g, info
 
     def logp_chain(self, chain, prior=False):
@@ -577,6 +583,105 @@ class EllipticalProcess(StochasticProcess):
         if distribution:                                                     # stochastic.py:509-512
             values["logpredictive"] = lambda x: self.logpredictive(theta, space, vector=x, prior=prior, array=True)
         return values
+
+    # ---- selectors bound by EllipticalProcess._compile_methods (elliptical.py:206-215, stochastic.py:330-366):
+    #      called as f(params, space, inputs, outputs, prior=, noise=, array=) and returning NumPy arrays
+    def _selector(self, params, space, inputs, outputs, prior, noise, array, cov=False):
+        theta = self._theta(params, array)
+        if not self.is_observed and inputs is None:
+            prior = True
+        if inputs is not None or outputs is not None:
+            self.set_space(inputs=inputs, outputs=outputs)
+        space = self.space if space is None else np.asarray(space, dtype=np.float64)
+        if space.ndim < 2:
+            space = space.reshape(len(space), 1)
+        post, nat, p = self._posterior(theta, space, noise=noise, cov=cov, prior=prior)
+        return post, nat, p, theta, space, prior
+
+    def location(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+                 array=False):
+        """th_location (elliptical.py:121-129)."""
+        return self._selector(params, space, inputs, outputs, prior, noise, array)[0]["location"]
+
+    def kernel(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+               array=False):
+        """th_kernel (elliptical.py:131-141): prior Gram on `space` or posterior covariance."""
+        return self._selector(params, space, inputs, outputs, prior, noise, array, cov=True)[0]["kernel"]
+
+    def kernel_diag(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+                    array=False):
+        """th_kernel_diag (elliptical.py:154-164), clamped at 0 (`:94-97`)."""
+        return self._selector(params, space, inputs, outputs, prior, noise, array)[0]["kernel_diag"]
+
+    def kernel_sd(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+                  array=False):
+        """th_kernel_sd (elliptical.py:166-176)."""
+        return np.sqrt(self.kernel_diag(params, space, inputs, outputs, vector, prior, noise, array))
+
+    def cholesky(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+                 array=False):
+        """th_cholesky (elliptical.py:143-152): CholeskyRobust of the prior / posterior covariance on `space`."""
+        K = self.kernel(params, space, inputs, outputs, vector, prior, noise, array)
+        L, info, _ = self.ctx.potrf_robust(K)
+        return self.consts.fallback * np.eye(len(K)) if info < 0 else L
+
+    def _moment(self, key, params, space, inputs, outputs, prior, noise, array):
+        flags = dict(mean=False, std=False, var=False, median=False, cov=False)
+        flags[{"variance": "var", "covariance": "cov"}.get(key, key)] = True
+        theta = self._theta(params, array)
+        return self.predict(theta, space, inputs, outputs, prior=prior, noise=noise, array=True, **flags)[key]
+
+    def mean(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+             array=False, simulations=None):
+        return self._moment("mean", params, space, inputs, outputs, prior, noise, array)
+
+    def median(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+               array=False, simulations=None):
+        return self._moment("median", params, space, inputs, outputs, prior, noise, array)
+
+    def variance(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+                 array=False, simulations=None):
+        return self._moment("variance", params, space, inputs, outputs, prior, noise, array)
+
+    def std(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+            array=False, simulations=None):
+        return self._moment("std", params, space, inputs, outputs, prior, noise, array)
+
+    def covariance(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+                   array=False):
+        return self._moment("covariance", params, space, inputs, outputs, prior, noise, array)
+
+    def quantiler(self, params=None, space=None, inputs=None, outputs=None, q=0.975, prior=False, noise=False,
+                  simulations=None, array=False):
+        """gaussian.py:56-73 / studentT.py:51-55: T(location + z_q * kernel_sd)."""
+        post, nat, p, _, _, prior = self._selector(params, space, inputs, outputs, prior, noise, array)
+        z = self._quantile_z_prior(q, nat) if prior else self._quantile_z(q, nat)
+        return self.f_mapping(post["location"] + z * np.sqrt(post["kernel_diag"]), p)
+
+    def mapping(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+                array=False):
+        """th_mapping (elliptical.py:118-119): T(outputs)."""
+        nat = self.natural(self._theta(params, array))
+        y = self.outputs if outputs is None else np.asarray(outputs, dtype=np.float64)
+        return tt_to_num(self.f_mapping(y, self._accessor(nat)))
+
+    def mapping_inv(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+                    array=False):
+        """th_mapping_inv (elliptical.py:115-116): T^-1(outputs), NaN/inf scrubbed (`:63`)."""
+        nat = self.natural(self._theta(params, array))
+        y = self.outputs if outputs is None else np.asarray(outputs, dtype=np.float64)
+        with np.errstate(all="ignore"):
+            return tt_to_num(self.f_mapping.inv(y, self._accessor(nat)))
+
+    def freedom(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+                array=False):
+        """th_freedom (elliptical.py:109-113): nu, plus N for the posterior."""
+        if self.f_degree is None:
+            raise AttributeError("freedom is defined for Student-t processes")
+        nat = self.natural(self._theta(params, array))
+        nu = float(self._nu(nat[None, :])[0])
+        n = len(self.inputs if inputs is None else inputs)
+        return nu if prior else nu + n
 
     def logpredictive(self, params=None, space=None, vector=None, prior=False, noise=False, array=False):
         """GaussianProcess.th_logpredictive (gaussian.py:42-54): logp_cho of `vector` under the predictive

@@ -47,12 +47,17 @@ class Consts:
     def __init__(self, strict=True):
         self.strict = strict
         if strict:
-            # gaussian.py:218  tt.log(np.float32(2.0*np.pi)) -> float32 log of a float32 constant
-            self.log_2pi = float(np.log(f32(2.0 * np.pi)))
+            # gaussian.py:218  tt.log(np.float32(2.0*np.pi)) -> float32 log of a float32 constant, folded by
+            # Theano's C thunk (glibc logf == double log rounded to float32 = 1.8378770351409912).  NumPy's
+            # SIMD float32 log returns the neighbouring float (1.8378771543502808) on this CPU, i.e. the
+            # constant is implementation-defined to 1 float32 ulp (6e-8 * N/2 on logp); the correctly
+            # rounded value is used, computed in double so that it does not depend on the host's libm.
+            self.log_2pi = float(f32(math.log(float(f32(2.0 * np.pi)))))
             # studentT.py:122-124
             self.pi = float(f32(np.pi))
-            # studentT.py:127  np.log(np2 * npi) is a NumPy float32 expression
-            self.log_2pi_student = float(np.log(f32(2.0) * f32(np.pi)))
+            # studentT.py:127  np.log(np2 * npi) is a NumPy float32 expression (only used when nu >= 1e6);
+            # same remark, same correctly rounded value
+            self.log_2pi_student = float(f32(math.log(float(f32(2.0) * f32(np.pi)))))
             # tensors.py:98 and :204
             self.jitter = float(f32(1e-6))
             # gaussian.py:238-241 / studentT.py:143-146
@@ -256,7 +261,9 @@ class _Leaf(KernelNode):
         Analytic limits are used at d = 0 for the sqrt-kernels.  With
         `nan_quirk=True` the reference's behaviour is emulated instead: Theano's grad(sqrt) gives
         NaN where d == 0, `tt_to_num` (stochastic.py:309) turns the *whole* rate-gradient
-        component NaN -> 0.
+        component NaN -> 0.  The same happens to the `freq` gradient of SINC: the unselected
+        branch of its `switch` is sin(0)/0 (kernels.py:479-480) and its gradient is NaN at delta = 0.
+        Both are confirmed by executing the reference (tests/golden/reference_g3py.json).
         """
         p = self._split(th)
         k = self.kind
@@ -316,7 +323,10 @@ class _Leaf(KernelNode):
             env = p["var"] * (np.exp(-2 * pi2 * np.dot(diff ** 2, p["rate"] ** 2)) if k == "SM" else 1.0)
             for j in range(self.nd):                          # freq first (creation order)
                 others = np.prod(np.delete(fac, j, axis=2), axis=2)
-                out.append(env * dfac[:, :, j] * others)
+                g = env * dfac[:, :, j] * others
+                if nan_quirk and k == "SINC" and np.any(diff[:, :, j] == 0.0):
+                    g = np.full_like(g, np.nan)
+                out.append(g)
             if k == "SM":
                 for j in range(self.nd):
                     out.append(K * (-4 * pi2 * diff[:, :, j] ** 2 * p["rate"][j]))

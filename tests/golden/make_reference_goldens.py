@@ -1,0 +1,257 @@
+"""Golden vectors from the UNMODIFIED reference (`/root/reference/g3py`) -> tests/golden/reference_g3py.json.
+
+The reference is Theano + PyMC3 code; neither can be installed in this container (no network, not in the
+wheelhouse).  `tests/golden/refshim/` provides stand-ins for the slice of the Theano / PyMC3 API that g3py
+touches (lazy expression graph evaluated with torch CPU, dtype-preserving; reverse-mode autodiff for
+`tt.grad`; the reference's own `CholeskyRobust.perform` / `.grad` run as written), so that
+
+    import g3py;  gp = g3py.GP(x, g3py.Bias(), g3py.SE(x));  gp.observed(x, y);  gp.logp(); gp.dlogp(); gp.predict()
+
+execute the reference's own source files: kernels.py, metrics.py, means.py, mappings.py, tensors.py,
+elliptical.py, gaussian.py, studentT.py, stochastic.py, models.py.  What this pins and what it cannot:
+  + every formula, constant (incl. float32 literals), guard, hyper-parameter order and transform in those files;
+  + the NaN->0 scrub of Matern rate gradients (Theano's sqrt gradient at d=0; torch has the same 0/0);
+  - Theano's graph *optimiser* (rewrites may change rounding at the 1e-16 level and NaN propagation), its
+    BLAS/LAPACK build, and `graph.inputs` ordering of `dlogp` components (stored per variable name here).
+
+Run in this container only (needs /root/reference):   python tests/golden/make_reference_goldens.py
+The fixture is committed; tests read the JSON, never the reference.
+"""
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+warnings.filterwarnings('ignore')
+
+
+def _import_reference():
+    import refshim
+    refshim.install()
+    import torch
+    torch.set_default_dtype(torch.float64)
+    sys.path.insert(0, '/root/reference')
+    import g3py as g3
+    import theano as th
+    th.config.floatX = 'float64'           # g3py/config.py defaults to float32; this is the fp64 run
+    return g3
+
+
+# ------------------------------------------------------------------ neutral spec -> reference objects
+def _x_arg(X, dims):
+    # column subsets: the reference's `(domain, slice)` form sizes `rate` with the full D (hypers/__init__.py:63-68)
+    # and then fails in `tt.dot`; the list-of-columns form (`:60-62`) is the one that works
+    return X if dims is None else list(range(int(dims[0]), int(dims[1])))
+
+
+def ref_kernel(g3, spec, X):
+    t = spec['type']
+    if t == 'sum':
+        return ref_kernel(g3, spec['k1'], X) + ref_kernel(g3, spec['k2'], X)
+    if t == 'prod':
+        return ref_kernel(g3, spec['k1'], X) * ref_kernel(g3, spec['k2'], X)
+    if t == 'scale':
+        return spec['c'] * ref_kernel(g3, spec['k'], X)
+    if t == 'shift':
+        return spec['c'] + ref_kernel(g3, spec['k'], X)
+    kw = {}
+    if 'name' in spec:
+        kw['name'] = spec['name']
+    if spec.get('var') is not None:
+        kw['var'] = spec['var']
+    cls = g3.KernelNoise if t == 'Noise' else getattr(g3, t)
+    return cls(_x_arg(X, spec.get('dims')), **kw)
+
+
+def ref_process(g3, spec, X):
+    kind = spec.get('kind', 'gauss')
+    mp = spec.get('mapping', {'type': 'Identity'})
+    warped = spec.get('warped', mp['type'] != 'Identity')
+    cls = {('gauss', False): g3.GP, ('gauss', True): g3.WGP, ('student', False): g3.TP,
+           ('student', True): g3.WTP}[(kind, warped)]
+    loc = spec.get('location', {'type': 'Zero'})
+    lkw = {'name': loc['name']} if 'name' in loc else {}
+    location = getattr(g3, loc['type'])(_x_arg(X, loc.get('dims')), **lkw)
+    mkw = {'name': mp['name']} if 'name' in mp else {}
+    mapping = getattr(g3, mp['type'])(**mkw)
+    kw = {'name': spec['name']} if 'name' in spec else {}
+    return cls(X, location, ref_kernel(g3, spec['kernel'], X), mapping, noisy=spec.get('noisy', True), **kw)
+
+
+# ------------------------------------------------------------------ cases
+def _data(seed, N, D, M, positive=False):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(0.0, 6.0, size=(N, D))
+    f = np.sin(X[:, 0]) + (0.5 * np.cos(0.7 * X[:, 1]) if D > 1 else 0.0) + (0.1 * X[:, -1] if D > 2 else 0.0)
+    y = f + 0.1 * rng.standard_normal(N)
+    if positive:
+        y = np.exp(0.5 * y) + 0.2
+    Xs = rng.uniform(0.0, 6.0, size=(M, D))
+    return X, y, Xs
+
+
+K = lambda t, **kw: dict(type=t, **kw)
+CASES = {
+    # BASELINE configs, down-sized
+    'C1_gp_se':        dict(spec=dict(kind='gauss', location=K('Bias'), kernel=K('SE')), N=60, D=1, M=17, seed=10),
+    'C2_gp_se_mat52':  dict(spec=dict(kind='gauss', location=K('Bias'), kernel=K('sum', k1=K('SE'), k2=K('MAT52'))),
+                            N=64, D=3, M=13, seed=11),
+    'C3_wgp_sinxse':   dict(spec=dict(kind='gauss', warped=True, location=K('Bias'),
+                                      kernel=K('prod', k1=K('SIN'), k2=K('SE')), mapping=K('BoxCoxShifted')),
+                            N=48, D=1, M=15, seed=12, positive=True),
+    'C4_tp_se':        dict(spec=dict(kind='student', location=K('Bias'), kernel=K('SE')), N=56, D=5, M=11, seed=13),
+    # leaf zoo (SURVEY a2 + f4)
+    'leaf_ou':         dict(spec=dict(kind='gauss', location=K('Zero'), kernel=K('OU')), N=24, D=2, M=7, seed=20),
+    'leaf_mat32':      dict(spec=dict(kind='gauss', location=K('Zero'), kernel=K('MAT32')), N=24, D=2, M=7, seed=21),
+    'leaf_rq':         dict(spec=dict(kind='gauss', location=K('Bias'), kernel=K('RQ')), N=24, D=2, M=7, seed=22),
+    'leaf_sin':        dict(spec=dict(kind='gauss', location=K('Zero'), kernel=K('SIN')), N=24, D=1, M=7, seed=23,
+                            sin_rate=0.001),
+    'leaf_sin_indef':  dict(spec=dict(kind='gauss', location=K('Zero'), kernel=K('SIN')), N=24, D=1, M=7, seed=23,
+                            sin_rate=0.1),    # indefinite K: logp through the jitter ladder, posterior through LU
+    'leaf_cos':        dict(spec=dict(kind='gauss', location=K('Zero'), kernel=K('sum', k1=K('COS'), k2=K('SE'))),
+                            N=24, D=2, M=7, seed=24),
+    'leaf_sinc':       dict(spec=dict(kind='gauss', location=K('Zero'), kernel=K('sum', k1=K('SINC'), k2=K('SE'))),
+                            N=24, D=1, M=7, seed=25),
+    'leaf_sm':         dict(spec=dict(kind='gauss', location=K('Zero'), kernel=K('SM')), N=24, D=2, M=7, seed=26),
+    'leaf_wn':         dict(spec=dict(kind='gauss', location=K('Zero'), kernel=K('sum', k1=K('SE'), k2=K('WN'))),
+                            N=24, D=2, M=7, seed=27),
+    # operator algebra (a4), column subsets, fixed variances
+    'alg_scale_shift': dict(spec=dict(kind='gauss', location=K('Bias'),
+                                      kernel=K('shift', c=0.3, k=K('scale', c=1.7, k=K('SE')))), N=24, D=2, M=7, seed=30),
+    'alg_prod_dims':   dict(spec=dict(kind='gauss', location=K('Linear'),
+                                      kernel=K('sum', k1=K('prod', k1=K('SE', dims=[0, 2]), k2=K('MAT32', dims=[2, 3])),
+                                               k2=K('RQ', dims=[1, 3], name='RQb'))), N=32, D=3, M=9, seed=31),
+    # mappings (a7 det_m, a12)
+    'map_logshifted':  dict(spec=dict(kind='gauss', location=K('Bias'), kernel=K('SE'), mapping=K('LogShifted')),
+                            N=24, D=1, M=7, seed=40, positive=True),
+    'map_boxcoxlin':   dict(spec=dict(kind='gauss', location=K('Bias'), kernel=K('SE'), mapping=K('BoxCoxLinear')),
+                            N=24, D=1, M=7, seed=41, positive=True),
+    'map_arcsinh':     dict(spec=dict(kind='gauss', location=K('Bias'), kernel=K('SE'), mapping=K('ArcsinhLinear')),
+                            N=24, D=1, M=7, seed=42),
+    'map_sinharcsinh': dict(spec=dict(kind='gauss', location=K('Bias'), kernel=K('SE'), mapping=K('SinhArcsinh')),
+                            N=24, D=1, M=7, seed=43),
+    'map_linear':      dict(spec=dict(kind='gauss', location=K('Bias'), kernel=K('SE'), mapping=K('LinearMapping')),
+                            N=24, D=1, M=7, seed=44),
+    'wtp_boxcox':      dict(spec=dict(kind='student', warped=True, location=K('Bias'), kernel=K('MAT52'),
+                                      mapping=K('BoxCoxShifted')), N=32, D=2, M=9, seed=45, positive=True),
+    # robustness (a5, a6): noise-free kernel on duplicated inputs -> jitter ladder of CholeskyRobust
+    'jitter_ladder':   dict(spec=dict(kind='gauss', location=K('Zero'), kernel=K('SE'), noisy=False), N=20, D=1, M=5,
+                            seed=50, duplicate=True, logp_only=True),   # LU `tsl.solve` of the posterior is singular here
+}
+
+
+def theta_for(layout, y, rng, case):
+    """Moderate hyper-parameters in the oracle's layout order (positive ones as logs)."""
+    th = []
+    for name, size, pos in layout:
+        v = 0.15 * rng.standard_normal(size)
+        if name.endswith('Noise_var'):
+            v += np.log(0.05 * max(np.var(y), 1e-3))
+        elif name.endswith('_var'):
+            v += np.log(max(np.var(y), 1e-3))
+        elif name.endswith('SIN_rate'):
+            # SIN = exp(+2 r sin^2) >= its own diagonal (kernels.py:472): K is indefinite unless r is tiny
+            v = np.full(size, np.log(case.get('sin_rate', 0.01)))
+        elif name.endswith('_freq'):
+            v += np.log(0.2)
+        elif name.endswith('SM_rate'):
+            v += np.log(0.15)
+        elif name.endswith('Freedom_degree'):
+            v = np.full(size, np.log(5.0))
+        elif name.endswith('_power'):
+            v = np.full(size, np.log(0.7))
+        elif name.endswith('_Bias') or name.endswith('_Constant'):
+            v += np.mean(y) if 'mapping' not in case['spec'] else 0.0
+        elif name.endswith('_Coeff'):
+            v *= 0.3
+        elif name.endswith('LogShifted_shift'):
+            v = np.full(size, np.min(y) - 0.5)
+        elif name.endswith('_shift'):
+            v = 0.05 * v
+        th.append(v)
+    return np.concatenate(th) if th else np.zeros(0)
+
+
+def short(name, proc):
+    s = name[len(proc) + 1:]
+    for suf in ('_log__', '_log_'):
+        if s.endswith(suf):
+            s = s[:-len(suf)]
+    return s
+
+
+def main():
+    g3 = _import_reference()
+    from oracle import g3_oracle as orc     # only for the neutral layout (names / order), not for any value
+    out = {}
+    for cname, case in CASES.items():
+        X, y, Xs = _data(case['seed'], case['N'], case['D'], case['M'], case.get('positive', False))
+        if case.get('duplicate'):
+            X[1::2] = X[0::2]                       # exact duplicates: singular noise-free Gram
+            y[1::2] = y[0::2]
+        spec = case['spec']
+        proc = ref_process(g3, spec, X)
+        proc.observed(X, y)
+        vmap = proc.active.bijection.ordering.vmap
+        names = [m.var for m in vmap]
+        layout = orc.OracleProcess(spec, X.shape[1]).layout()
+        assert [short(n, proc.name) for n in names] == [l[0] for l in layout], (names, layout)
+        assert [int(np.prod(m.shp)) for m in vmap] == [l[1] for l in layout]
+        assert [n.endswith('__') for n in names] == [bool(l[2]) for l in layout]
+        th = theta_for(layout, y, np.random.default_rng(1000 + case['seed']), case)
+        params = proc.active.array_to_dict(th)
+        rec = dict(spec=spec, X=X.tolist(), y=y.tolist(), Xs=Xs.tolist(), theta=th.tolist(),
+                   ref_names=names, layout=[list(l) for l in layout],
+                   default_params={k: np.asarray(v, dtype=np.float64).ravel().tolist()
+                                   for k, v in proc.params_default.items()})
+        Kin = np.asarray(proc.kernel(params=params, space=X, inputs=X, outputs=y, prior=True, noise=True))
+        rec['min_eig_K'] = float(np.linalg.eigvalsh(0.5 * (Kin + Kin.T)).min())
+        rec['logp'] = float(proc.logp(th, array=True))
+        rec['logp_prior'] = float(proc.logp(th, array=True, prior=True))
+        rec['loglike'] = float(proc.loglike(th, array=True))
+        # dlogp: reference order is graph-traversal order -> store per variable
+        import pymc3 as pm
+        wrt = pm.inputvars(pm.cont_inputs(proc.th_logp()))
+        flat = np.asarray(proc.dlogp(th, array=True), dtype=np.float64)
+        off, d = 0, {}
+        for v in wrt:
+            size = int(np.prod(np.shape(v.tag.test_value)))
+            d[v.name] = flat[off:off + size].tolist()
+            off += size
+        assert off == flat.size
+        rec['dlogp_order'] = [v.name for v in wrt]
+        rec['dlogp'] = d
+        kw = dict(params=params, space=Xs, inputs=X, outputs=y)
+        for noise in (() if case.get('logp_only') else (False, True)):
+            r = {}
+            for key in ('location', 'kernel_diag', 'kernel_sd', 'mean', 'median', 'variance', 'std'):
+                r[key] = np.asarray(getattr(proc, key)(prior=False, noise=noise, **kw), dtype=np.float64).tolist()
+            r['kernel'] = np.asarray(proc.kernel(prior=False, noise=noise, **kw)).tolist()
+            r['prior_kernel'] = np.asarray(proc.kernel(prior=True, noise=noise, **kw)).tolist()
+            r['quantile_up'] = np.asarray(proc.quantiler(q=0.975, prior=False, noise=noise, **kw)).tolist()
+            r['quantile_down'] = np.asarray(proc.quantiler(q=0.025, prior=False, noise=noise, **kw)).tolist()
+            if hasattr(proc, 'covariance') and proc.th_covariance() is not None:
+                r['covariance'] = np.asarray(proc.covariance(prior=False, noise=noise, **kw)).tolist()
+            rec['post_noise%d' % noise] = r
+        if spec.get('kind', 'gauss') == 'gauss' and not case.get('logp_only'):
+            v = np.asarray(rec['post_noise1']['median']) * 1.01 + 0.01
+            rec['logpredictive_at'] = v.tolist()
+            rec['logpredictive'] = float(proc.logpredictive(vector=v, prior=False, noise=True, **kw))
+        if spec.get('kind') == 'student':
+            rec['freedom_post'] = float(proc.freedom(prior=False, **kw))
+        out[cname] = rec
+        print('%-18s N=%3d P=%2d logp=% .12e  |dlogp|=%.3e  min eig K=% .2e' % (cname, len(y), len(th), rec['logp'],
+              np.linalg.norm(flat), rec['min_eig_K']))
+    with open(os.path.join(HERE, 'reference_g3py.json'), 'w') as f:
+        json.dump(out, f)
+    print('wrote reference_g3py.json', os.path.getsize(os.path.join(HERE, 'reference_g3py.json')), 'bytes')
+
+
+if __name__ == '__main__':
+    main()
