@@ -14,6 +14,8 @@ from .hypers import Hypers, HyperVar, Registry, Freedom
 from .hypers.kernels import *    # noqa: F401,F403
 from .hypers.means import *      # noqa: F401,F403
 from .hypers.mappings import *   # noqa: F401,F403
+from .hypers.transports import *  # noqa: F401,F403
 from .processes import *         # noqa: F401,F403
+from .transport import *         # noqa: F401,F403
 
 __version__ = "0.1.0"

@@ -155,6 +155,20 @@ class KernelComposition(Kernel):
 
     @property
     def name(self):
+        # kernels.py:169-186: "k1(start,stop) op k2(start,stop)" with the reference's cascade of fallbacks (the name
+        # ends up in hyper names, e.g. TKernel's 'Noise' + kernel.name, transports.py:205-206)
+        def full(k):
+            return k.name + "(" + str(k.dims.start) + "," + str(k.dims.stop) + ")"
+
+        def plain(k):
+            return k.name + "(" + str(k.dims) + ")"
+
+        for a, b in ((full, full), (plain, plain), (None, plain), (plain, None)):
+            try:
+                return ((a(self.k1) if a else self.k1.name) + " " + self.op + " "
+                        + (b(self.k2) if b else self.k2.name))
+            except Exception:
+                continue
         return self.k1.name + " " + self.op + " " + self.k2.name
 
     def check_hypers(self, parent="", reg=None):

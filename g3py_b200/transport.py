@@ -1,0 +1,203 @@
+"""TransportGaussianProcess — mirror of g3py/processes/transport.py:17-246.
+
+y = t_1(t_2(... t_n(eps))), eps ~ N(0, I).  For chains `[ID | TMapping | TLocation]* @ TKernel` the density
+(`TransportGaussianDistribution.logp_t`, transport.py:220-243)
+
+    logp = -N/2 log(2 pi) - 1/2 |L^-1 (T^-1(y) - m(X))|^2 - sum log L_ii + log|dT^-1| (+ 1 per ID)
+
+is the warped-GP density, so logp / dlogp run through the same device pipeline as `WGP` (Gram -> blocked fp64
+Cholesky -> triangular solve -> trtri/lauum gradient); only the hyper-parameter ORDER differs (the transport chain
+creates hypers outermost first: mapping, location, kernel, `Noise<kernel>`), and the sampling selectors
+`transport / transport_inv / transport_diag` push a white-noise vector through the prior or the posterior.  The
+posterior needs the Cholesky factor of the (N+M) x (N+M) joint covariance (`transports.py:236-257`), factored on
+the device by `g3_potrf_robust`.
+"""
+import numpy as np
+import scipy.linalg as sla
+
+from . import _cabi as cabi
+from .hypers.mappings import Identity, MappingComposed
+from .hypers.means import MeanSum, Zero
+from .hypers.transports import ID, TKernel, TLocation, TMapping, Transport
+from .processes import DictObj, EllipticalProcess, StochasticProcess
+
+__all__ = ["TransportGaussianProcess", "TGP"]
+
+
+class TransportGaussianProcess(EllipticalProcess):
+    KIND = cabi.KIND_GAUSS
+    WARPED = True
+
+    def __init__(self, space=None, transport=None, *args, **kwargs):
+        kwargs.setdefault("name", "TGP")
+        if not isinstance(transport, Transport):
+            raise TypeError("TransportGaussianProcess(space, transport): transport must be a Transport")
+        chain = transport.chain()
+        if not isinstance(chain[-1], TKernel) or any(isinstance(t, TKernel) for t in chain[:-1]):
+            raise NotImplementedError("supported chains: [ID | TMapping | TLocation]* @ TKernel (one kernel, innermost)")
+        kinds = [type(t) for t in chain[:-1]]
+        if any(k not in (ID, TMapping, TLocation) for k in kinds):
+            raise NotImplementedError("only ID, TMapping and TLocation may precede the TKernel")
+        order = [k for k in kinds if k is not ID]
+        if TLocation in order and TMapping in order[order.index(TLocation):]:
+            raise NotImplementedError("TMapping inside a TLocation is not supported (put the mappings outermost)")
+        self.f_transport = transport
+        self.n_id = kinds.count(ID)
+        maps = [t.mapping for t in chain[:-1] if isinstance(t, TMapping)]
+        locs = [t.location for t in chain[:-1] if isinstance(t, TLocation)]
+        self.f_mapping = Identity()
+        if maps:
+            self.f_mapping = maps[0]
+            for m in maps[1:]:
+                self.f_mapping = MappingComposed(self.f_mapping, m)     # inv = m2.inv(m1.inv(y)), transports.py:108-109
+        self.f_location = Zero()
+        if locs:
+            self.f_location = locs[0]
+            for m in locs[1:]:
+                self.f_location = MeanSum(self.f_location, m)
+        tk = chain[-1]
+        self.f_degree = None
+        self.f_kernel = tk.kernel
+        self.noisy = tk.is_noisy
+        self.f_kernel_noise = tk.noisy
+        kwargs["space"] = space
+        StochasticProcess.__init__(self, *args, **kwargs)
+
+    def _check_hypers(self):
+        # transport.py:24-27: hypers are created along the chain, outermost transport first
+        x = self.inputs
+        parent = self.name + "_"
+        self.f_transport.check_dims(x)
+        self.f_transport.check_hypers(parent, self.registry)
+        for comp in (self.f_location, self.f_mapping):        # composites collect the hypers created above
+            comp.check_dims(x)
+            comp.check_hypers(parent, self.registry)
+        self._finish_layout()
+
+    def _eval_batch(self, Theta, inputs=None, outputs=None, want_grad=True, nan_quirk=None):
+        ll, g, info = super()._eval_batch(Theta, inputs, outputs, want_grad, nan_quirk)
+        if self.n_id:                                         # ID.logdet_dinv = tt.ones(()) (transports.py:129-130)
+            ll = np.where(ll == self.consts.guard, ll, ll + float(self.n_id))
+        return ll, g, info
+
+    # ---- transports of a white-noise vector (transport.py:34-100) ------------------------------
+    def _gram(self, X1, X2, nat, noise):
+        if noise and self.noisy:
+            K, _ = self.ctx.gram(self.desc, X1, X2, self._kernel_theta(nat[None, :]))
+        else:
+            K, _ = self.ctx.gram(self.desc_f, X1, X2, self._kernel_theta(nat[None, :], self._slots_f, self.desc_f.n_theta))
+        return K[0]
+
+    def _chol(self, K):
+        L, info, _ = self.ctx.potrf_robust(K)                 # CholeskyRobust incl. ladder and 1e-10*I fallback
+        return self.consts.fallback * np.eye(len(K)) if info < 0 else np.tril(L)
+
+    def _tk_posterior(self, space, pred, nat, p, noise_pred):
+        """TKernel.posterior (transports.py:236-257) with noise_obs=True."""
+        X, y = self.inputs, self.outputs
+        with np.errstate(all="ignore"):
+            pre = self.f_mapping.inv(y, p) - self.f_location(X, p)
+        u = sla.solve_triangular(self._chol(self._gram(X, None, nat, True)), pre, lower=True)
+        Kxs = self._gram(X, space, nat, False)                # kernel.cov(inputs, space): no noise on the cross block
+        joint = np.block([[self._gram(X, None, nat, True), Kxs], [Kxs.T, self._gram(space, None, nat, noise_pred)]])
+        L = self._chol(joint)
+        n = len(y)
+        return L[n:, :n] @ u + L[n:, n:] @ pred
+
+    def _transport(self, which, params, space, inputs, outputs, vector, prior, noise, array):
+        theta = self._theta(params, array)
+        if not self.is_observed and inputs is None:
+            prior = True
+        if inputs is not None or outputs is not None:
+            self.set_space(inputs=inputs, outputs=outputs)
+        space = self.space if space is None else np.asarray(space, dtype=np.float64)
+        if space.ndim < 2:
+            space = space.reshape(len(space), 1)
+        v = np.asarray(vector, dtype=np.float64).reshape(-1)
+        if len(v) != len(space):
+            raise ValueError("vector must have one entry per point of space")
+        nat = self.natural(theta)
+        p = self._accessor(nat)
+        elementwise = len(self.f_transport.chain()) > 1
+        self.executed["predict"] += 1
+        if not prior:
+            # TKernel.posterior and TElemwise.posterior ignore their `inv` / `diag` flags: the three posterior
+            # selectors coincide in the reference (transports.py:134-136,236-257)
+            return self.f_mapping(self.f_location(space, p) + self._tk_posterior(space, v, nat, p, noise), p)
+        if which == "inv":                                    # transports.py:227-232 after the element-wise inverses
+            with np.errstate(all="ignore"):
+                pre = self.f_mapping.inv(v, p) - self.f_location(space, p)
+            return sla.solve_triangular(self._chol(self._gram(space, None, nat, noise)), pre, lower=True)
+        K = self._gram(space, None, nat, noise)
+        if which == "diag" and not elementwise:               # TKernel.diag (transports.py:218-225)
+            return np.sqrt(np.diag(K)) * v
+        return self.f_mapping(self.f_location(space, p) + self._chol(K) @ v, p)
+
+    def transport(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+                  array=False):
+        return self._transport("call", params, space, inputs, outputs, vector, prior, noise, array)
+
+    def transport_inv(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+                      array=False):
+        return self._transport("inv", params, space, inputs, outputs, vector, prior, noise, array)
+
+    def transport_diag(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False,
+                       noise=False, array=False):
+        return self._transport("diag", params, space, inputs, outputs, vector, prior, noise, array)
+
+    # ---- Monte-Carlo summaries (transport.py:171-211): 30 transported white-noise draws by default -------------
+    def sampler(self, params=None, space=None, inputs=None, outputs=None, samples=1, prior=False, noise=False,
+                array=False, rng=None):
+        rng = rng or np.random.default_rng()
+        space = self.space if space is None else np.asarray(space, dtype=np.float64).reshape(len(space), -1)
+        rand = rng.standard_normal((len(space), samples))
+        return np.array([self.transport(params, space, inputs, outputs, vector=rand[:, i], prior=prior, noise=noise,
+                                        array=array) for i in range(samples)]).T
+
+    def _sims(self, simulations, params, space, inputs, outputs, prior, noise, array, rng):
+        if simulations is None:
+            simulations = 30
+        if isinstance(simulations, int):
+            return self.sampler(params, space, inputs, outputs, samples=simulations, prior=prior, noise=noise,
+                                array=array, rng=rng)
+        return np.asarray(simulations)
+
+    def mean(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+             array=False, simulations=None, rng=None):
+        return self._sims(simulations, params, space, inputs, outputs, prior, noise, array, rng).mean(axis=1)
+
+    def std(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
+            array=False, simulations=None, rng=None):
+        return self._sims(simulations, params, space, inputs, outputs, prior, noise, array, rng).std(axis=1)
+
+    def quantiler(self, params=None, space=None, inputs=None, outputs=None, q=0.975, prior=False, noise=False,
+                  simulations=None, array=False, rng=None):
+        s = self._sims(simulations, params, space, inputs, outputs, prior, noise, array, rng)
+        return np.nanpercentile(s, 100 * q, axis=1)
+
+    def predict(self, params=None, space=None, inputs=None, outputs=None, mean=True, std=True, var=False, cov=False,
+                median=False, quantiles=False, quantiles_noise=False, samples=0, distribution=False, prior=False,
+                noise=False, simulations=None, array=False, rng=None):
+        """stochastic.py:444-513 with the Monte-Carlo selectors above (one set of draws shared by all summaries)."""
+        if not self.is_observed:
+            prior = True
+        sims = self._sims(simulations, params, space, inputs, outputs, prior, noise, array, rng)
+        values = DictObj()
+        if mean:
+            values["mean"] = sims.mean(axis=1)
+        if std:
+            values["std"] = sims.std(axis=1)
+        if var:
+            values["variance"] = sims.var(axis=1)
+        if median:
+            values["median"] = np.nanpercentile(sims, 50, axis=1)
+        if quantiles:
+            values["quantile_up"] = np.nanpercentile(sims, 97.5, axis=1)
+            values["quantile_down"] = np.nanpercentile(sims, 2.5, axis=1)
+        if samples > 0:
+            values["samples"] = self.sampler(params, space, inputs, outputs, samples=samples, prior=prior, noise=noise,
+                                             array=array, rng=rng)
+        return values
+
+
+TGP = TransportGaussianProcess

@@ -577,8 +577,10 @@ class _Mapping:
 
 
 # --------------------------------------------------------------------------- processes
-def build_process(spec, D):
-    return OracleProcess(spec, D)
+def build_process(spec, D, strict=True):
+    if spec.get("kind") == "transport":
+        return OracleTransportProcess(spec, D, strict)
+    return OracleProcess(spec, D, strict)
 
 
 class OracleProcess:
@@ -805,6 +807,190 @@ class OracleProcess:
         out["quantile_up"] = T(mu + q * sd)
         out["quantile_down"] = T(mu - q * sd)
         return out
+
+
+# --------------------------------------------------------------------------- transport.py / transports.py
+class OracleTransportProcess:
+    """TransportGaussianProcess (processes/transport.py:135-246) over a chain of transports
+    (hypers/transports.py), restated literally for chains  [ID | TMapping | TLocation]* @ TKernel.
+
+    spec = {"kind": "transport", "chain": [{"t": "TMapping", "mapping": {...}}, {"t": "TLocation", "location": {...}},
+            {"t": "ID"}, {"t": "TKernel", "kernel": {...}, "noisy": True}]}       (outermost first)
+    theta follows the chain: `check_hypers` runs t1 then t2 of every composition (transports.py:76-79).
+    At most one TMapping and one TLocation (enough for the tests; the product composes several).
+    """
+
+    def __init__(self, spec, D, strict=True):
+        self.spec = spec
+        self.D = D
+        self.consts = Consts(strict)
+        self.chain = spec["chain"]
+        assert self.chain[-1]["t"] == "TKernel"
+        self.parts = []                                          # (kind, object, theta offset, n_theta)
+        off = 0
+        lay = []
+        for t in self.chain:
+            if t["t"] == "ID":
+                obj, hy = None, []
+            elif t["t"] == "TMapping":
+                obj = _Mapping(t["mapping"])
+                hy = obj.layout()
+            elif t["t"] == "TLocation":
+                obj = _Mean(t["location"], D)
+                hy = obj.layout()
+            elif t["t"] == "TKernel":
+                k = build_kernel(t["kernel"], D)
+                self.f_kernel = k
+                self.noisy = bool(t.get("noisy", False))
+                if self.noisy:                                   # transports.py:203-206
+                    kname = t["kernel"].get("name", t["kernel"]["type"])
+                    k = _Binary("sum", k, _Leaf({"type": "Noise", "name": "Noise" + kname}, D))
+                self.k_noise = k
+                obj, hy = k, k.layout()
+            else:
+                raise ValueError(t["t"])
+            n = sum(h.size for h in hy)
+            self.parts.append((t["t"], obj, off, n))
+            lay += hy
+            off += n
+        self._layout = lay
+        self.P = off
+
+    def layout(self):
+        return [(h.name, h.size, h.positive) for h in self._layout]
+
+    def positive_mask(self):
+        return np.concatenate([np.full(h.size, h.positive) for h in self._layout]) if self._layout else np.zeros(0, bool)
+
+    def natural(self, theta):
+        theta = np.asarray(theta, dtype=np.float64)
+        m = self.positive_mask()
+        return np.where(m, np.exp(np.where(m, theta, 0.0)), theta)
+
+    def logprior(self, theta):
+        nat = self.natural(theta)
+        m = self.positive_mask()
+        return 0.0 if np.all(nat[m] > 1e-6) else -np.inf
+
+    # ---- one transport at a time -----------------------------------------------------------
+    def _cov(self, th, x1, x2, noise):
+        if noise and self.noisy:
+            return self.k_noise.cov(th, x1, x1 if x2 is None else x2, x2 is None)
+        return self.f_kernel.cov(th[:self.f_kernel.n_theta()], x1, x1 if x2 is None else x2, x2 is None)
+
+    def _call1(self, part, nat, X, v, noise):
+        kind, obj, off, n = part
+        th = nat[off:off + n]
+        if kind == "ID":
+            return v                                             # transports.py:123-124
+        if kind == "TMapping":
+            return obj.forward(th, v)                            # :190-191
+        if kind == "TLocation":
+            return v + obj(th, X)                                # :152-156
+        return cholesky_robust(self._cov(th, X, None, noise), self.consts).dot(v)     # :210-216
+
+    def _inv1(self, part, nat, X, v, noise):
+        kind, obj, off, n = part
+        th = nat[off:off + n]
+        if kind == "ID":
+            return v
+        if kind == "TMapping":
+            return obj.inv(th, v)                                # :193-194
+        if kind == "TLocation":
+            return v - obj(th, X)                                # :158-159
+        return sla.solve_triangular(cholesky_robust(self._cov(th, X, None, noise), self.consts), v, lower=True)  # :227-232
+
+    def _logdet1(self, part, nat, X, v):
+        kind, obj, off, n = part
+        th = nat[off:off + n]
+        if kind == "ID":
+            return 1.0                                           # :129-130  tt.ones(()) -- not zero
+        if kind == "TMapping":
+            return obj.logdet_dinv(th, v)                        # :196-197
+        if kind == "TLocation":
+            return 0.0                                           # :161-162
+        return -float(np.sum(np.log(np.diag(cholesky_robust(self._cov(th, X, None, True), self.consts)))))   # :234-236
+
+    # ---- chain (TransportComposed, transports.py:93-119) ---------------------------------------
+    def call(self, nat, X, v, noise):
+        for part in reversed(self.parts):
+            v = self._call1(part, nat, X, v, noise)
+        return v
+
+    def inv(self, nat, X, v, noise):
+        for part in self.parts:
+            v = self._inv1(part, nat, X, v, noise)
+        return v
+
+    def logdet_dinv(self, nat, X, v):
+        tot = 0.0
+        for part in self.parts:                                  # t2.logdet(t1.inv(y, noise=True)) + t1.logdet(y)
+            tot = tot + self._logdet1(part, nat, X, v)
+            v = self._inv1(part, nat, X, v, True)
+        return tot
+
+    def loglike(self, theta, X, y):
+        """TransportGaussianDistribution.logp_t (transport.py:220-243)."""
+        nat = self.natural(theta)
+        c = self.consts
+        delta = self.inv(nat, X, y, True)
+        det_m = self.logdet_dinv(nat, X, y)
+        r = -0.5 * float(len(y)) * c.log_2pi + (-0.5) * float(delta.dot(delta)) + det_m
+        bad = not np.all(np.isfinite(delta)) or not np.isfinite(det_m)
+        return c.guard if bad else float(r)
+
+    def logp(self, theta, X, y):
+        return self.logprior(theta) + self.loglike(theta, X, y)
+
+    def dlogp(self, theta, X, y, nan_quirk=False):
+        """Gradient through the equivalent warped GP (same density, permuted theta)."""
+        loc = next((t["location"] for t in self.chain if t["t"] == "TLocation"), {"type": "Zero"})
+        mp = next((t["mapping"] for t in self.chain if t["t"] == "TMapping"), {"type": "Identity"})
+        tk = self.chain[-1]
+        wgp = OracleProcess({"kind": "gauss", "warped": True, "location": loc, "kernel": tk["kernel"], "mapping": mp,
+                             "noisy": self.noisy}, self.D, self.consts.strict)
+        # permutation: chain order -> [location, kernel(+Noise), mapping]
+        src = {}
+        for kind, obj, off, n in self.parts:
+            src[kind] = (off, n)
+        order = [src.get("TLocation", (0, 0)), src["TKernel"], src.get("TMapping", (0, 0))]
+        idx = np.concatenate([np.arange(o, o + n) for o, n in order]).astype(int)
+        g_w = wgp.dlogp(np.asarray(theta)[idx], X, y, nan_quirk=nan_quirk)
+        g = np.zeros(self.P)
+        g[idx] = g_w
+        return g
+
+    # ---- selectors (transport.py:34-100) ------------------------------------------------------
+    def transport(self, theta, space, vector, X=None, y=None, prior=False, noise=False):
+        nat = self.natural(theta)
+        if prior:
+            return self.call(nat, space, vector, noise)
+        # TransportComposed.posterior: element-wise transports act on `space`, TKernel.posterior does the work
+        pre = y
+        for part in self.parts[:-1]:
+            pre = self._inv1(part, nat, X, pre, True)
+        kind, obj, off, n = self.parts[-1]
+        th = nat[off:off + n]
+        outputs_inv = sla.solve_triangular(cholesky_robust(self._cov(th, X, None, True), self.consts), pre, lower=True)
+        cov_space_inputs = self.f_kernel.cov(th[:self.f_kernel.n_theta()], X, space, False)       # :246
+        cov = np.block([[self._cov(th, X, None, True), cov_space_inputs],
+                        [cov_space_inputs.T, self._cov(th, space, None, noise)]])
+        cho = cholesky_robust(cov, self.consts)
+        v = cho.dot(np.concatenate([outputs_inv, vector]))[len(y):]
+        for part in reversed(self.parts[:-1]):
+            v = self._call1(part, nat, space, v, noise)
+        return v
+
+    def transport_inv(self, theta, space, vector, X=None, y=None, prior=False, noise=False):
+        if not prior:                     # `inv=True` is ignored by TKernel.posterior / TElemwise.posterior
+            return self.transport(theta, space, vector, X, y, False, noise)
+        return self.inv(self.natural(theta), space, vector, noise)
+
+    def transport_diag(self, theta, space, vector, X=None, y=None, prior=False, noise=False):
+        if not prior or len(self.parts) > 1:      # Transport.diag = __call__ except for a bare TKernel (:19-20,218-225)
+            return self.transport(theta, space, vector, X, y, prior, noise)
+        nat = self.natural(theta)
+        return np.sqrt(np.diag(self._cov(nat, space, None, noise))) * vector
 
 
 # --------------------------------------------------------------------------- synthetic inputs (SURVEY §8d)

@@ -109,6 +109,11 @@ class FakeContext:
         X2 = X1 if same else np.asarray(X2, dtype=np.float64)
         return np.stack([_eval_desc(desc, t, X1, X2, same) for t in theta]), np.zeros(len(theta), dtype=np.int32)
 
+    def potrf_robust(self, A):
+        from oracle import g3_oracle as orc
+        L, info = orc.cholesky_robust(np.asarray(A, dtype=np.float64), return_info=True)
+        return L, (-1 if info < 0 else 0), 0.0
+
     def _factor(self, desc, t):
         K, dK = _eval_desc(desc, t, self.X, self.X, True, grad=True)
         m = np.min(np.diag(K))

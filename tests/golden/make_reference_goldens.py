@@ -69,8 +69,27 @@ def ref_kernel(g3, spec, X):
     return cls(_x_arg(X, spec.get('dims')), **kw)
 
 
+def ref_transport(g3, spec, X):
+    parts = []
+    for t in spec['chain']:
+        if t['t'] == 'ID':
+            parts.append(g3.ID())
+        elif t['t'] == 'TMapping':
+            parts.append(g3.TMapping(getattr(g3, t['mapping']['type'])()))
+        elif t['t'] == 'TLocation':
+            parts.append(g3.TLocation(getattr(g3, t['location']['type'])(_x_arg(X, t['location'].get('dims')))))
+        else:
+            parts.append(g3.TKernel(ref_kernel(g3, t['kernel'], X), noisy=t.get('noisy', False)))
+    tr = parts[0]
+    for t in parts[1:]:
+        tr = tr @ t
+    return tr
+
+
 def ref_process(g3, spec, X):
     kind = spec.get('kind', 'gauss')
+    if kind == 'transport':
+        return g3.TransportGaussianProcess(X, ref_transport(g3, spec, X))
     mp = spec.get('mapping', {'type': 'Identity'})
     warped = spec.get('warped', mp['type'] != 'Identity')
     cls = {('gauss', False): g3.GP, ('gauss', True): g3.WGP, ('student', False): g3.TP,
@@ -140,6 +159,20 @@ CASES = {
                             N=24, D=1, M=7, seed=44),
     'wtp_boxcox':      dict(spec=dict(kind='student', warped=True, location=K('Bias'), kernel=K('MAT52'),
                                       mapping=K('BoxCoxShifted')), N=32, D=2, M=9, seed=45, positive=True),
+    # TransportGaussianProcess (SURVEY f-3): chains [ID | TMapping | TLocation]* @ TKernel
+    'tgp_canonical':   dict(spec=dict(kind='transport', chain=[dict(t='TMapping', mapping=K('BoxCoxShifted')),
+                                                               dict(t='TLocation', location=K('Bias')),
+                                                               dict(t='TKernel', kernel=K('SE'), noisy=True)]),
+                            N=24, D=1, M=7, seed=60, positive=True),
+    'tgp_id_linear':   dict(spec=dict(kind='transport', chain=[dict(t='ID'), dict(t='TLocation', location=K('Linear')),
+                                                               dict(t='TKernel', kernel=K('MAT32'), noisy=True)]),
+                            N=24, D=2, M=7, seed=61),
+    'tgp_bare_kernel': dict(spec=dict(kind='transport', chain=[dict(t='TKernel', kernel=K('SE'), noisy=True)]),
+                            N=20, D=2, M=6, seed=62),
+    'tgp_noise_free':  dict(spec=dict(kind='transport', chain=[dict(t='TLocation', location=K('Bias')),
+                                                               dict(t='TKernel', kernel=K('sum', k1=K('SE'), k2=K('WN')),
+                                                                    noisy=False)]),
+                            N=20, D=1, M=6, seed=63),
     # robustness (a5, a6): noise-free kernel on duplicated inputs -> jitter ladder of CholeskyRobust
     'jitter_ladder':   dict(spec=dict(kind='gauss', location=K('Zero'), kernel=K('SE'), noisy=False), N=20, D=1, M=5,
                             seed=50, duplicate=True, logp_only=True),   # LU `tsl.solve` of the posterior is singular here
@@ -200,7 +233,7 @@ def main():
         proc.observed(X, y)
         vmap = proc.active.bijection.ordering.vmap
         names = [m.var for m in vmap]
-        layout = orc.OracleProcess(spec, X.shape[1]).layout()
+        layout = orc.build_process(spec, X.shape[1]).layout()
         assert [short(n, proc.name) for n in names] == [l[0] for l in layout], (names, layout)
         assert [int(np.prod(m.shp)) for m in vmap] == [l[1] for l in layout]
         assert [n.endswith('__') for n in names] == [bool(l[2]) for l in layout]
@@ -210,8 +243,12 @@ def main():
                    ref_names=names, layout=[list(l) for l in layout],
                    default_params={k: np.asarray(v, dtype=np.float64).ravel().tolist()
                                    for k, v in proc.params_default.items()})
-        Kin = np.asarray(proc.kernel(params=params, space=X, inputs=X, outputs=y, prior=True, noise=True))
-        rec['min_eig_K'] = float(np.linalg.eigvalsh(0.5 * (Kin + Kin.T)).min())
+        transport = spec.get('kind') == 'transport'
+        if transport:
+            rec['min_eig_K'] = 1.0
+        else:
+            Kin = np.asarray(proc.kernel(params=params, space=X, inputs=X, outputs=y, prior=True, noise=True))
+            rec['min_eig_K'] = float(np.linalg.eigvalsh(0.5 * (Kin + Kin.T)).min())
         rec['logp'] = float(proc.logp(th, array=True))
         rec['logp_prior'] = float(proc.logp(th, array=True, prior=True))
         rec['loglike'] = float(proc.loglike(th, array=True))
@@ -228,6 +265,22 @@ def main():
         rec['dlogp_order'] = [v.name for v in wrt]
         rec['dlogp'] = d
         kw = dict(params=params, space=Xs, inputs=X, outputs=y)
+        if transport:
+            vec = np.random.default_rng(7000 + case['seed']).standard_normal(len(Xs))
+            rec['vector'] = vec.tolist()
+            for sel in ('transport', 'transport_inv', 'transport_diag'):
+                for prior in (False, True):
+                    for noise in (False, True):
+                        # the inverse needs a vector in the range of the warping: use the transported draw
+                        v_in = vec
+                        if sel == 'transport_inv' and prior:
+                            v_in = np.asarray(proc.transport(vector=vec, prior=True, noise=noise, **kw))
+                        out_v = getattr(proc, sel)(vector=v_in, prior=prior, noise=noise, **kw)
+                        rec['%s_prior%d_noise%d' % (sel, prior, noise)] = np.asarray(out_v, dtype=np.float64).tolist()
+            out[cname] = rec
+            print('%-18s N=%3d P=%2d logp=% .12e  |dlogp|=%.3e  (transport)' % (cname, len(y), len(th), rec['logp'],
+                  np.linalg.norm(flat)))
+            continue
         for noise in (() if case.get('logp_only') else (False, True)):
             r = {}
             for key in ('location', 'kernel_diag', 'kernel_sd', 'mean', 'median', 'variance', 'std'):

@@ -36,8 +36,31 @@ def build_kernel(spec, X):
     return LEAVES[t](_x_arg(X, spec.get("dims")), **kw)
 
 
+def build_transport(spec, X):
+    parts = []
+    for t in spec["chain"]:
+        if t["t"] == "ID":
+            parts.append(g3.ID())
+        elif t["t"] == "TMapping":
+            mp = t["mapping"]
+            parts.append(g3.TMapping(MAPS[mp["type"]](**({"name": mp["name"]} if "name" in mp else {}))))
+        elif t["t"] == "TLocation":
+            loc = t["location"]
+            parts.append(g3.TLocation(MEANS[loc["type"]](_x_arg(X, loc.get("dims")),
+                                                        **({"name": loc["name"]} if "name" in loc else {}))))
+        else:
+            parts.append(g3.TKernel(build_kernel(t["kernel"], X), noisy=t.get("noisy", False)))
+    tr = parts[0]
+    for t in parts[1:]:
+        tr = tr @ t
+    return tr
+
+
 def build_process(spec, X, strict=True):
     kind = spec.get("kind", "gauss")
+    if kind == "transport":
+        return g3.TGP(X, build_transport(spec, X), strict_constants=strict,
+                      **({"name": spec["name"]} if "name" in spec else {}))
     warped = spec.get("warped", spec.get("mapping", {"type": "Identity"})["type"] != "Identity")
     cls = {("gauss", False): g3.GP, ("gauss", True): g3.WGP, ("student", False): g3.TP, ("student", True): g3.WTP}[(kind, warped)]
     loc = spec.get("location", {"type": "Zero"})

@@ -18,6 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = json.load(open(os.path.join(HERE, "golden", "reference_g3py.json")))
 CASES = list(REF)
 POST = [c for c in CASES if "post_noise0" in REF[c]]
+TRANSPORT = [c for c in CASES if REF[c]["spec"].get("kind") == "transport"]
 # Cholesky-route posterior (the CUDA path) is comparable with the reference's LU route only where K is positive
 # definite; on an indefinite K (SIN with a large rate) the reference itself is inconsistent: logp sees
 # the jittered factor, predict the raw LU solve.
@@ -48,7 +49,7 @@ def _rel(a, b):
 @pytest.mark.parametrize("name", CASES)
 def test_oracle_layout_and_logp_match_reference(name):
     rec, X, y, Xs, th = _load(name)
-    op = orc.OracleProcess(rec["spec"], X.shape[1])
+    op = orc.build_process(rec["spec"], X.shape[1])
     assert [list(l) for l in op.layout()] == rec["layout"]
     assert _rel(op.logp(th, X, y), rec["logp"]) < 1e-12
     assert _rel(op.loglike(th, X, y), rec["loglike"]) < 1e-12
@@ -58,12 +59,36 @@ def test_oracle_layout_and_logp_match_reference(name):
 @pytest.mark.parametrize("name", CASES)
 def test_oracle_dlogp_matches_reference(name):
     rec, X, y, Xs, th = _load(name)
-    op = orc.OracleProcess(rec["spec"], X.shape[1])
+    op = orc.build_process(rec["spec"], X.shape[1])
     want = _ref_dlogp(rec)
     # the reference's autodiff yields NaN -> 0 for the rate of sqrt-kernels: nan_quirk mode
     for method in ("analytic", "murray"):
-        got = op.dlogp(th, X, y, method=method, nan_quirk=True)
+        kw = {} if name in TRANSPORT else {"method": method}
+        got = op.dlogp(th, X, y, nan_quirk=True, **kw)
         assert scaled_err(got, want) < (1e-10 if name != "jitter_ladder" else 1e-6), method
+
+
+SELECTORS = [(sel, prior, noise) for sel in ("transport", "transport_inv", "transport_diag") for prior in (False, True)
+             for noise in (False, True)]
+
+
+def _transport_input(rec, sel, prior, noise):
+    """The vector each golden selector call was given (the prior inverse gets the transported draw)."""
+    if sel == "transport_inv" and prior:
+        return np.array(rec["transport_prior1_noise%d" % noise])
+    return np.array(rec["vector"])
+
+
+@pytest.mark.parametrize("name", TRANSPORT)
+def test_oracle_transport_selectors_match_reference(name):
+    rec, X, y, Xs, th = _load(name)
+    op = orc.build_process(rec["spec"], X.shape[1])
+    for sel, prior, noise in SELECTORS:
+        got = getattr(op, sel)(th, Xs, _transport_input(rec, sel, prior, noise), X, y, prior=prior, noise=noise)
+        assert scaled_err(got, rec["%s_prior%d_noise%d" % (sel, prior, noise)]) < 1e-9, (sel, prior, noise)
+    # the prior inverse undoes the prior transport
+    back = op.transport_inv(th, Xs, np.array(rec["transport_prior1_noise1"]), prior=True, noise=True)
+    assert scaled_err(back, rec["vector"]) < 1e-8
 
 
 @pytest.mark.parametrize("name", POST)
@@ -145,6 +170,21 @@ def _check_logp_dlogp(name):
     assert _rel(gp.logp(params), rec["logp"]) < TOL
 
 
+def _check_transport(name):
+    rec, X, y, Xs, th = _load(name)
+    gp = build_process(rec["spec"], X)
+    gp.observed(X, y)
+    for sel, prior, noise in SELECTORS:
+        got = getattr(gp, sel)(th, space=Xs, vector=_transport_input(rec, sel, prior, noise), prior=prior, noise=noise,
+                               array=True)
+        # joint (N+M) Cholesky: the trailing block is the factor of a Schur complement, conditioning ~1e3..1e6
+        assert scaled_err(got, rec["%s_prior%d_noise%d" % (sel, prior, noise)]) < 1e-7, (sel, prior, noise)
+    s = gp.sampler(th, space=Xs, samples=4, array=True, rng=np.random.default_rng(0))
+    assert s.shape == (len(Xs), 4) and np.all(np.isfinite(s))
+    out = gp.predict(th, space=Xs, array=True, quantiles=True, simulations=16, rng=np.random.default_rng(1))
+    assert np.all(out["quantile_down"] <= out["quantile_up"]) and out["mean"].shape == (len(Xs),)
+
+
 def _check_posterior(name, noise):
     rec, X, y, Xs, th = _load(name)
     gp = build_process(rec["spec"], X)
@@ -211,6 +251,17 @@ def test_host_logp_dlogp_match_reference(fake, name):
 @pytest.mark.parametrize("noise", [False, True])
 def test_host_posterior_matches_reference(fake, name, noise):
     _check_posterior(name, noise)
+
+
+@pytest.mark.parametrize("name", TRANSPORT)
+def test_host_transport_matches_reference(fake, name):
+    _check_transport(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", TRANSPORT)
+def test_cuda_transport_matches_reference(name):
+    _check_transport(name)
 
 
 @pytest.mark.parametrize("name", POST)
