@@ -140,10 +140,11 @@ struct GramArgs {
   const int* bmap;
 };
 int g3_gram_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const GramArgs& a, int B);
-// min over the diagonal of cov(X) for each theta (tt_to_cov needs it): out[b]
+// min over the diagonal of cov(X) for each theta (tt_to_cov needs it): out[b]; diag_vec (optional, B x n) receives
+// the diagonal itself (the posterior variance of non-stationary kernels needs k(x*, x*) per point)
 int g3_gram_diag_min(g3_ctx* ctx, const g3_kernel_desc& desc, const double* X, int n, int D,
                      const double* theta, int P, int B, double* diag_min, double* diag_mean, int* status,
-                     int skip_process_noise);
+                     int skip_process_noise, double* diag_vec = nullptr);
 int g3_check_desc(g3_ctx* ctx, const g3_kernel_desc& d, int D);
 struct VjpArgs {
   const double* X1; const double* X2;

@@ -122,10 +122,10 @@ __global__ void post_kss_shift_kernel(double* kss, double jitter, int apply) {
   if (threadIdx.x == 0) kss[2] = (apply && !(kss[0] > 0.0)) ? jitter - kss[0] : 0.0;
 }
 
-// mean[m] = sum_n Vt[m][n] u[n];  var[m] = max(kss - sum_n Vt[m][n]^2, 0).  One warp per row.
+// mean[m] = sum_n Vt[m][n] u[n];  var[m] = max(k(x*_m, x*_m) - sum_n Vt[m][n]^2, 0).  One warp per row.
 __global__ void __launch_bounds__(256)
 post_moments_kernel(const double* __restrict__ Vt, int Np, int M, const double* __restrict__ u,
-                    const double* __restrict__ kss, const double* __restrict__ kss_shift,
+                    const double* __restrict__ kss_vec, const double* __restrict__ kss_shift,
                     double* __restrict__ mean, double* __restrict__ var) {
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -144,7 +144,7 @@ post_moments_kernel(const double* __restrict__ Vt, int Np, int M, const double* 
   }
   if (lane == 0) {
     mean[m] = s1;
-    const double v = (kss[0] + kss_shift[0]) - s2;
+    const double v = (kss_vec[m] + kss_shift[0]) - s2;
     var[m] = v < 0.0 ? 0.0 : v;   // tt_to_bounded(extract_diag(..), 0)  elliptical.py:94-97
   }
 }
@@ -817,7 +817,8 @@ int g3_gp_posterior(g3_ctx* ctx, const g3_kernel_desc* desc, const double* Xs, i
   double* dmean = (double*)g3_ws(ctx, "post_mean", sizeof(double) * Mp);
   double* dvar = (double*)g3_ws(ctx, "post_var", sizeof(double) * Mp);
   double* kss = (double*)g3_ws(ctx, "post_kss", sizeof(double) * 4);
-  if (!dXs || !Vt || !dmean || !dvar || !kss) return -2;
+  double* kss_vec = (double*)g3_ws(ctx, "post_kss_vec", sizeof(double) * Mp);
+  if (!dXs || !Vt || !dmean || !dvar || !kss || !kss_vec) return -2;
   G3_CUDA(ctx, cudaMemcpyAsync(dXs, Xs, sizeof(double) * (size_t)M * D, cudaMemcpyHostToDevice, ctx->stream));
   // K* = cov(space, inputs)  (cross form: Noise contributes zeros, kernels.py:367-371), tt_to_num scrubbed
   GramArgs a;
@@ -852,12 +853,12 @@ int g3_gp_posterior(g3_ctx* ctx, const g3_kernel_desc* desc, const double* Xs, i
     g.alpha = 1.0; g.beta = 0.0; g.tri_b = 1;
     if ((rc = g3_gemm_launch(ctx, tmV, tmD, g, 1))) return rc;
   }
-  // K** diagonal: every leaf is stationary, so diag(cov(space)) is the tree evaluated at d = 0
-  if ((rc = g3_gram_diag_min(ctx, *desc, dXs, M, D, w.theta, P, 1, kss, kss + 1, nullptr, skip_pn))) return rc;
+  // K** diagonal: the tree evaluated at (x*, x*) per test point (constant for stationary leaves), and its minimum
+  if ((rc = g3_gram_diag_min(ctx, *desc, dXs, M, D, w.theta, P, 1, kss, kss + 1, nullptr, skip_pn, kss_vec))) return rc;
   // tt_to_cov on prior_kernel_space only for the noisy selector (elliptical.py:70 vs :73)
   post_kss_shift_kernel<<<1, 32, 0, ctx->stream>>>(kss, ctx->jitter_rel, (flags & G3_POST_NOISE) ? 1 : 0);
   G3_LAUNCH_CHECK(ctx);
-  post_moments_kernel<<<(M + 7) / 8, 256, 0, ctx->stream>>>(Vt, Np, M, w.u, kss, kss + 2, dmean, dvar);
+  post_moments_kernel<<<(M + 7) / 8, 256, 0, ctx->stream>>>(Vt, Np, M, w.u, kss_vec, kss + 2, dmean, dvar);
   G3_LAUNCH_CHECK(ctx);
   G3_CUDA(ctx, cudaMemcpyAsync(mean_out, dmean, sizeof(double) * M, cudaMemcpyDeviceToHost, ctx->stream));
   G3_CUDA(ctx, cudaMemcpyAsync(var_out, dvar, sizeof(double) * M, cudaMemcpyDeviceToHost, ctx->stream));

@@ -67,6 +67,41 @@ __device__ __forceinline__ double periodic_dfactor(int op, double df, double fq,
   return -sinpi(2.0 * df * fq) * (2.0 * M_PI * df);
 }
 
+// m^p for a small integer p by repeated squaring (Theano specialises pow(x, int) the same way)
+__device__ __forceinline__ double ipow(double m, int p) {
+  double r = 1.0;
+  while (p > 0) {
+    if (p & 1) r *= m;
+    m *= m;
+    p >>= 1;
+  }
+  return r;
+}
+
+// value of one leaf on the diagonal of cov(x, x) (same = 1, i == j) for the row `x`
+__device__ __forceinline__ double leaf_diag(const g3_knode& nd, const double* __restrict__ th,
+                                            const double* __restrict__ x, int skip_pn) {
+  const double var = nd.var_idx >= 0 ? th[nd.var_idx] : nd.value;
+  switch (nd.op) {
+    case G3_K_NOISE:
+      return (skip_pn && (nd.flags & G3_KF_PROCESS_NOISE)) ? 0.0 : var;
+    case G3_K_RQ:
+      return var * pow(1.0, -th[nd.p1_idx]);
+    case G3_K_DOT: {
+      double m = nd.p1_idx >= 0 ? th[nd.p1_idx] : 0.0;
+      for (int k = nd.dim0; k < nd.dim1; ++k) { const double r = th[nd.p0_idx + k - nd.dim0]; m += r * r * x[k] * x[k]; }
+      return var * ipow(m, G3_KF_POWER(nd.flags));
+    }
+    case G3_K_BW: {
+      double m = 1.0;
+      for (int k = nd.dim0; k < nd.dim1; ++k) m *= x[k];
+      return var * m;
+    }
+    default:   // stationary leaves: k(0) = 1; WN / VAR: var
+      return var;
+  }
+}
+
 // value of one leaf for 4 columns at once; same_diag[e] = element lies on the diagonal of cov(x, x)
 __device__ __forceinline__ void leaf_value4(const g3_knode& nd, const double* __restrict__ th,
                                             const double* __restrict__ x1row, const double* __restrict__ x2s,
@@ -140,6 +175,23 @@ __device__ __forceinline__ void leaf_value4(const g3_knode& nd, const double* __
         }
       }
       break;
+    case G3_K_DOT:
+      for (int k = 0; k < nd_; ++k) {
+        const double r = th[nd.p0_idx + k];
+        const double xr = x1row[nd.dim0 + k] * (r * r);
+        const double* x2 = x2s + (nd.dim0 + k) * TS;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) d[e] += xr * x2[cc[e]];
+      }
+      break;
+    case G3_K_BW:
+      for (int k = 0; k < nd_; ++k) {
+        const double xi = x1row[nd.dim0 + k];
+        const double* x2 = x2s + (nd.dim0 + k) * TS;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pr[e] *= fmin(xi, x2[cc[e]]);
+      }
+      break;
     default:
       break;
   }
@@ -178,6 +230,15 @@ __device__ __forceinline__ void leaf_value4(const g3_knode& nd, const double* __
         break;
       case G3_K_WN:
         v = same ? (same_diag[e] ? var : 0.0) : var * d[e];
+        break;
+      case G3_K_DOT:
+        v = var * ipow((nd.p1_idx >= 0 ? th[nd.p1_idx] : 0.0) + d[e], G3_KF_POWER(nd.flags));
+        break;
+      case G3_K_BW:
+        v = var * pr[e];
+        break;
+      case G3_K_VAR:
+        v = var;
         break;
       default:
         v = 0.0;
@@ -227,10 +288,10 @@ gram_fwd_kernel(const __grid_constant__ g3_kernel_desc desc, const GramArgs a, i
         leaf_value4(nd, th, x1s + rl * a.D, x2s, cc, sd, a.same, a.skip_process_noise, v);
 #pragma unroll
         for (int e = 0; e < 4; ++e) { s5[e] = s4[e]; s4[e] = s3[e]; s3[e] = s2[e]; s2[e] = s1[e]; s1[e] = s0[e]; s0[e] = v[e]; }
-      } else if (nd.op == G3_K_SUM || nd.op == G3_K_PROD) {
+      } else if (nd.op == G3_K_SUM || nd.op == G3_K_PROD || nd.op == G3_K_MAX) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          s0[e] = nd.op == G3_K_SUM ? s1[e] + s0[e] : s1[e] * s0[e];
+          s0[e] = nd.op == G3_K_SUM ? s1[e] + s0[e] : (nd.op == G3_K_PROD ? s1[e] * s0[e] : fmax(s1[e], s0[e]));
           s1[e] = s2[e]; s2[e] = s3[e]; s3[e] = s4[e]; s4[e] = s5[e];
         }
       } else {
@@ -254,17 +315,19 @@ gram_fwd_kernel(const __grid_constant__ g3_kernel_desc desc, const GramArgs a, i
   if (a.status && flag) atomicOr(a.status + b, G3_ST_NONFINITE_INPUT);
 }
 
-// min and mean of diag(cov(X, X)) per theta (after tt_to_num scrubbing).  grid (B), 256 threads.
+// min and mean of diag(cov(X, X)) per theta (after tt_to_num scrubbing), optionally the diagonal itself.
+// grid (B), 256 threads.
 __global__ void __launch_bounds__(256)
 gram_diag_kernel(const __grid_constant__ g3_kernel_desc desc, const double* __restrict__ X, int n, int D,
                  const double* __restrict__ theta, int P, double* __restrict__ dmin, double* __restrict__ dmean,
-                 int* __restrict__ status, int skip_pn) {
+                 int* __restrict__ status, int skip_pn, double* __restrict__ dvec) {
   __shared__ double th[G3_MAX_THETA];
   __shared__ double rmin[8], rsum[8];
   const int b = blockIdx.x;
   for (int p = threadIdx.x; p < P; p += blockDim.x) th[p] = theta[(long long)b * P + p];
   __syncthreads();
-  // diagonal element: all differences are zero -> every stationary leaf evaluates at d = 0
+  // diagonal element: all differences are zero -> every stationary leaf evaluates at d = 0; the dot-product /
+  // Brownian leaves need the row itself
   double vmin = INFINITY, vsum = 0.0;
   int flag = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -272,19 +335,17 @@ gram_diag_kernel(const __grid_constant__ g3_kernel_desc desc, const double* __re
     for (int k = 0; k < desc.n_nodes; ++k) {
       const g3_knode& nd = desc.nodes[k];
       if (nd.op < G3_K_SUM) {
-        const double var = nd.var_idx >= 0 ? th[nd.var_idx] : nd.value;
-        double v = var;  // k(0) = 1 for SE/OU/MAT/RQ/SIN; Noise/WN: var on the diagonal
-        if (nd.op == G3_K_NOISE && skip_pn && (nd.flags & G3_KF_PROCESS_NOISE)) v = 0.0;
-        if (nd.op == G3_K_RQ) v = var * pow(1.0, -th[nd.p1_idx]);
+        const double v = leaf_diag(nd, th, X + (long long)i * D, skip_pn);
         st[5] = st[4]; st[4] = st[3]; st[3] = st[2]; st[2] = st[1]; st[1] = st[0]; st[0] = v;
-      } else if (nd.op == G3_K_SUM || nd.op == G3_K_PROD) {
-        st[0] = nd.op == G3_K_SUM ? st[1] + st[0] : st[1] * st[0];
+      } else if (nd.op == G3_K_SUM || nd.op == G3_K_PROD || nd.op == G3_K_MAX) {
+        st[0] = nd.op == G3_K_SUM ? st[1] + st[0] : (nd.op == G3_K_PROD ? st[1] * st[0] : fmax(st[1], st[0]));
         st[1] = st[2]; st[2] = st[3]; st[3] = st[4]; st[4] = st[5];
       } else {
         st[0] = nd.op == G3_K_SCALE ? nd.value * st[0] : nd.value + st[0];
       }
     }
     const double v = scrub(st[0], flag);
+    if (dvec) dvec[(long long)b * n + i] = v;
     vmin = fmin(vmin, v);
     vsum += v;
   }
@@ -398,6 +459,22 @@ gram_vjp_kernel(const __grid_constant__ g3_kernel_desc desc, const VjpArgs a, in
           }
         }
         double pr[4] = {1.0, 1.0, 1.0, 1.0};
+        if (nd.op == G3_K_DOT) {
+          for (int k = 0; k < nd_; ++k) {
+            const double r = th[nd.p0_idx + k];
+            const double xr = x1row[nd.dim0 + k] * (r * r);
+            const double* x2 = x2s + (nd.dim0 + k) * TS;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) d[e] += xr * x2[cc[e]];
+          }
+        } else if (nd.op == G3_K_BW) {
+          for (int k = 0; k < nd_; ++k) {
+            const double xi = x1row[nd.dim0 + k];
+            const double* x2 = x2s + (nd.dim0 + k) * TS;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pr[e] *= fmin(xi, x2[cc[e]]);
+          }
+        }
         if (nd.op == G3_K_COS || nd.op == G3_K_SINC || nd.op == G3_K_SM) {
           for (int k = 0; k < nd_; ++k) {
             const double fq = th[nd.p1_idx + k], r = nd.op == G3_K_SM ? th[nd.p0_idx + k] : 0.0;
@@ -428,16 +505,23 @@ gram_vjp_kernel(const __grid_constant__ g3_kernel_desc desc, const VjpArgs a, in
             case G3_K_SM: kk = exp(-2.0 * kPi2 * d[e]) * pr[e]; break;
             case G3_K_NOISE: kk = sd[e] ? 1.0 : 0.0; break;
             case G3_K_WN: kk = a.same ? (sd[e] ? 1.0 : 0.0) : d[e]; break;
+            case G3_K_DOT: { const int pw = G3_KF_POWER(nd.flags);
+                             const double m = (nd.p1_idx >= 0 ? th[nd.p1_idx] : 0.0) + d[e];
+                             const double m1 = ipow(m, pw - 1); kk = m1 * m; dk = (double)pw * m1; } break;   // dk = d kk / d m
+            case G3_K_BW: kk = pr[e]; break;
+            case G3_K_VAR: kk = 1.0; break;
             default: kk = 0.0;
           }
           val[n][e] = var * kk;
           aux[n][e] = kk;
           dd[n][e] = (nd.op == G3_K_RQ) ? d[e] : var * dk;
         }
-      } else if (nd.op == G3_K_SUM || nd.op == G3_K_PROD) {
+      } else if (nd.op == G3_K_SUM || nd.op == G3_K_PROD || nd.op == G3_K_MAX) {
         const int l = nd.dim0, r = nd.dim1;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) val[n][e] = nd.op == G3_K_SUM ? val[l][e] + val[r][e] : val[l][e] * val[r][e];
+        for (int e = 0; e < 4; ++e)
+          val[n][e] = nd.op == G3_K_SUM ? val[l][e] + val[r][e]
+                                        : (nd.op == G3_K_PROD ? val[l][e] * val[r][e] : fmax(val[l][e], val[r][e]));
       } else {
         const int c = nd.dim0;
 #pragma unroll
@@ -460,6 +544,12 @@ gram_vjp_kernel(const __grid_constant__ g3_kernel_desc desc, const VjpArgs a, in
         for (int e = 0; e < 4; ++e) {
           adj[nd.dim0][e] += adj[n][e] * val[nd.dim1][e];
           adj[nd.dim1][e] += adj[n][e] * val[nd.dim0][e];
+        }
+      } else if (nd.op == G3_K_MAX) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {          // Theano: d max(x, y) = eq(out, x) * g, eq(out, y) * g
+          if (val[n][e] == val[nd.dim0][e]) adj[nd.dim0][e] += adj[n][e];
+          if (val[n][e] == val[nd.dim1][e]) adj[nd.dim1][e] += adj[n][e];
         }
       } else if (nd.op == G3_K_SCALE) {
 #pragma unroll
@@ -509,6 +599,21 @@ gram_vjp_kernel(const __grid_constant__ g3_kernel_desc desc, const VjpArgs a, in
 #pragma unroll
             for (int e = 0; e < 4; ++e) s -= adj[n][e] * val[n][e] * fabs(xi - x2[cc[e]]);
             acc[(nd.p0_idx + k) * 256 + tid] += s;
+          }
+        } else if (nd.op == G3_K_DOT) {      // m = bias + sum_k r_k^2 x_ik x_jk;  dd = var * d(m^p)/dm
+          if (nd.p1_idx >= 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s += adj[n][e] * dd[n][e];
+            acc[nd.p1_idx * 256 + tid] += s;
+          }
+          for (int k = 0; k < nd_; ++k) {
+            const double r = th[nd.p0_idx + k], xi = x1row[nd.dim0 + k];
+            const double* x2 = x2s + (nd.dim0 + k) * TS;
+            double s = 0.0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s += adj[n][e] * dd[n][e] * (xi * x2[cc[e]]);
+            acc[(nd.p0_idx + k) * 256 + tid] += 2.0 * r * s;
           }
         } else if (nd.op == G3_K_COS || nd.op == G3_K_SINC || nd.op == G3_K_SM) {
           const double var = nd.var_idx >= 0 ? th[nd.var_idx] : nd.value;
@@ -596,18 +701,21 @@ int g3_check_desc(g3_ctx* ctx, const g3_kernel_desc& d, int D) {
   for (int n = 0; n < d.n_nodes; ++n) {
     const g3_knode& nd = d.nodes[n];
     if (nd.op < G3_K_SUM) {
-      if (nd.op < G3_K_SE || nd.op > G3_K_SM) return g3_fail_msg(ctx, "kernel desc: unknown leaf op");
+      if (nd.op < G3_K_SE || nd.op > G3_K_VAR) return g3_fail_msg(ctx, "kernel desc: unknown leaf op");
       if (nd.op != G3_K_NOISE && (nd.dim0 < 0 || nd.dim1 > D || nd.dim1 <= nd.dim0))
         return g3_fail_msg(ctx, "kernel desc: leaf dims outside [0, D)");
       const int w = nd.dim1 - nd.dim0;
       if (nd.var_idx >= d.n_theta) return g3_fail_msg(ctx, "kernel desc: var_idx outside theta");
-      const bool has_rate = nd.op != G3_K_NOISE && nd.op != G3_K_WN && nd.op != G3_K_COS && nd.op != G3_K_SINC;
+      if (nd.op == 15) return g3_fail_msg(ctx, "kernel desc: unknown leaf op");
+      const bool has_rate = nd.op != G3_K_NOISE && nd.op != G3_K_WN && nd.op != G3_K_COS && nd.op != G3_K_SINC &&
+                            nd.op != G3_K_BW && nd.op != G3_K_VAR;
       if (has_rate && (nd.p0_idx < 0 || nd.p0_idx + w > d.n_theta)) return g3_fail_msg(ctx, "kernel desc: rate index outside theta");
       if (nd.op == G3_K_RQ && (nd.p1_idx < 0 || nd.p1_idx >= d.n_theta)) return g3_fail_msg(ctx, "kernel desc: alpha index outside theta");
       const bool has_freq = nd.op == G3_K_SIN || nd.op == G3_K_COS || nd.op == G3_K_SINC || nd.op == G3_K_SM;
       if (has_freq && (nd.p1_idx < 0 || nd.p1_idx + w > d.n_theta)) return g3_fail_msg(ctx, "kernel desc: freq index outside theta");
+      if (nd.op == G3_K_DOT && nd.p1_idx >= d.n_theta) return g3_fail_msg(ctx, "kernel desc: bias index outside theta");
       ++depth;
-    } else if (nd.op == G3_K_SUM || nd.op == G3_K_PROD) {
+    } else if (nd.op == G3_K_SUM || nd.op == G3_K_PROD || nd.op == G3_K_MAX) {
       if (depth < 2) return g3_fail_msg(ctx, "kernel desc: malformed post-order tree");
       if (nd.dim0 < 0 || nd.dim0 >= n || nd.dim1 < 0 || nd.dim1 >= n) return g3_fail_msg(ctx, "kernel desc: bad child index");
       --depth;
@@ -650,11 +758,12 @@ int g3_gram_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const GramArgs& a, i
 }
 
 int g3_gram_diag_min(g3_ctx* ctx, const g3_kernel_desc& desc, const double* X, int n, int D, const double* theta,
-                     int P, int B, double* diag_min, double* diag_mean, int* status, int skip_process_noise) {
+                     int P, int B, double* diag_min, double* diag_mean, int* status, int skip_process_noise,
+                     double* diag_vec) {
   int rc = g3_check_desc(ctx, desc, D);
   if (rc) return rc;
   gram_diag_kernel<<<B, 256, 0, ctx->stream>>>(desc, X, n, D, theta, P, diag_min, diag_mean, status,
-                                               skip_process_noise);
+                                               skip_process_noise, diag_vec);
   G3_LAUNCH_CHECK(ctx);
   return 0;
 }

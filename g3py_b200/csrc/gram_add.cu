@@ -431,8 +431,10 @@ gram_vjp_add_kernel(const __grid_constant__ g3_kernel_desc desc, const VjpArgs a
 }  // namespace
 
 bool g3_desc_is_additive(const g3_kernel_desc& d) {
-  for (int n = 0; n < d.n_nodes; ++n)
+  for (int n = 0; n < d.n_nodes; ++n) {
     if (d.nodes[n].op >= G3_K_SUM && d.nodes[n].op != G3_K_SUM) return false;
+    if (d.nodes[n].op > G3_K_SM && d.nodes[n].op < G3_K_SUM) return false;   // DOT / BW / VAR: generic interpreter
+  }
   return true;
 }
 

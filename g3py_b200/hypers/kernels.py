@@ -10,7 +10,8 @@ from . import Hypers, HyperVar
 from .. import _cabi as cabi
 
 __all__ = ["Kernel", "KernelStationary", "KernelSum", "KernelProd", "KernelScale", "KernelShift", "KernelNoise", "WN",
-           "SE", "OU", "MAT32", "MAT52", "RQ", "SIN", "COS", "SINC", "SM", "KernelPeriodic", "DescBuilder"]
+           "SE", "OU", "MAT32", "MAT52", "RQ", "SIN", "COS", "SINC", "SM", "KernelPeriodic", "DescBuilder",
+           "KernelDot", "LIN", "POL", "BW", "VAR", "KernelMax"]
 
 
 class DescBuilder:
@@ -209,6 +210,11 @@ class KernelSum(KernelComposition):
     op = "+"
 
 
+class KernelMax(KernelComposition):  # kernels.py:247-257
+    OP = cabi.K_MAX
+    op = "max"
+
+
 class KernelStationary(Kernel):
     """kernels.py:96-110: cov = var * k(metric.gram(x1, x2)); metric hypers follow `var`."""
     OPCODE = None
@@ -363,6 +369,77 @@ class SM(KernelPeriodic):            # kernels.py:485-487 (spectral mixture comp
         p1 = b.slot(self.freq, nd)
         p0 = b.slot(self.rate, nd)
         return b.node(self.OPCODE, d0, d1, vi, p0, p1, 0, val)
+
+
+class KernelDot(KernelStationary):
+    """kernels.py:82-96 with the ARD_Dot metric (metrics.py:110-117): var * sum_k rate_k^2 x_ik x_jk.  Subclasses with
+    BIAS use ARD_DotBias (metrics.py:120-137): bias + sum_k ..., hypers created rate first, then bias."""
+    OPCODE = cabi.K_DOT
+    BIAS = False
+    POWER = 1
+
+    def __init__(self, x=None, name=None, var=None, rate=None, bias=None):
+        super().__init__(x, name, var, rate)
+        self.bias = bias
+
+    def check_hypers(self, parent="", reg=None):
+        super().check_hypers(parent, reg)
+        if self.BIAS:
+            if self.bias is None:
+                self.bias = reg.FlatExp(parent + self.name + "_bias")
+            if isinstance(self.bias, HyperVar) and self.bias not in self.hypers:
+                self.hypers += [self.bias]
+
+    def default_hypers(self, x=None, y=None):
+        d = Kernel.default_hypers(self, x, y)
+        x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+        if self.BIAS:                                                    # metrics.py:135-137
+            if isinstance(self.bias, HyperVar):
+                d[self.bias] = np.abs(y).mean() / np.abs(x).mean()
+            if isinstance(self.rate, HyperVar):
+                d[self.rate] = np.sqrt(np.abs(y)).mean(axis=0) / np.abs(x).mean(axis=0)
+        elif isinstance(self.rate, HyperVar):                           # metrics.py:114-115
+            d[self.rate] = 1.0 / (np.sqrt(np.abs(x)).mean(axis=0) / np.abs(y).mean(axis=0))
+        return d
+
+    def compile(self, b, process_noise=False):
+        d0, d1, nd, vi, val = self._common(b)
+        p0 = b.slot(self.rate, nd)
+        p1 = b.slot(self.bias, 1) if self.BIAS else -1
+        return b.node(self.OPCODE, d0, d1, vi, p0, p1, (int(self.POWER) & 0xff) << 8, val)
+
+
+class LIN(KernelDot):                # kernels.py:319-321: var fixed to 1
+    BIAS = True
+
+    def __init__(self, x=None, name=None, var=1, rate=None, bias=None):
+        super().__init__(x, name, var, rate, bias)
+
+
+class POL(KernelDot):                # kernels.py:324-336: var * (bias + sum_k rate_k^2 x_ik x_jk) ** p
+    BIAS = True
+
+    def __init__(self, x=None, p=2, name=None, var=1, rate=None, bias=None):
+        super().__init__(x, name, var, rate, bias)
+        if int(p) != p or not 1 <= int(p) <= 255:
+            raise ValueError("POL: p must be an integer in [1, 255]")
+        self.p = self.POWER = int(p)
+
+
+class BW(Kernel):                    # kernels.py:291-293 with the Minimum metric (metrics.py:49-51): Brownian motion
+    OPCODE = cabi.K_BW
+
+    def compile(self, b, process_noise=False):
+        d0, d1 = self.dim_range(b.D)
+        if isinstance(self.var, HyperVar):
+            vi, val = b.slot(self.var, 1), 0.0
+        else:
+            vi, val = -1, float(self.var)
+        return b.node(self.OPCODE, d0, d1, vi, -1, -1, 0, val)
+
+
+class VAR(BW):                       # kernels.py:296-306: constant kernel var * ones
+    OPCODE = cabi.K_VAR
 
 
 class KernelNoise(Kernel):           # kernels.py:360-371

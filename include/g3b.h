@@ -44,8 +44,16 @@ enum {
   G3_K_COS = 9,   /* var*prod_k cos(2 pi (x_ik-x_jk) freq_k)                kernels.py:462-467 */
   G3_K_SINC = 10, /* var*prod_k sinc_k, sinc = sin(2 pi^2 d f)/(2 pi^2 f d), 1 at d = 0   kernels.py:475-482 */
   G3_K_SM = 11,   /* var*exp(-2 pi^2 sum_k d_k^2 rate_k^2)*prod_k cos(2 pi d_k freq_k)    kernels.py:485-487 */
-  G3_K_SUM = 16, G3_K_PROD = 17, G3_K_SCALE = 18, G3_K_SHIFT = 19
+  /* non-stationary leaves: the diagonal of cov(x, x) depends on x */
+  G3_K_DOT = 12,  /* var*(bias + sum_k rate_k^2 x_ik x_jk)^p: KernelDot/ARD_Dot (p1_idx < 0: bias = 0), LIN and POL with
+                     ARD_DotBias (bias = theta[p1_idx]); integer p >= 1 in flags bits 8..15 (0 means 1)
+                     kernels.py:82-96,319-336, metrics.py:110-137 */
+  G3_K_BW = 13,   /* var*prod_k min(x_ik, x_jk)  (Brownian)                  kernels.py:291-293, metrics.py:49-51 */
+  G3_K_VAR = 14,  /* var (constant kernel)                                   kernels.py:296-306 */
+  G3_K_SUM = 16, G3_K_PROD = 17, G3_K_SCALE = 18, G3_K_SHIFT = 19,
+  G3_K_MAX = 20   /* elementwise max(k1, k2); ties send the gradient to both (Theano's maximum)  kernels.py:247-257 */
 };
+#define G3_KF_POWER(flags) ((((flags) >> 8) & 0xff) ? (((flags) >> 8) & 0xff) : 1)
 
 typedef struct {
   int32_t op;

@@ -182,6 +182,8 @@ class _Leaf(KernelNode):
         self.dims = (0, D) if dims is None else (int(dims[0]), int(dims[1]))
         self.nd = self.dims[1] - self.dims[0]
         self.fixed_var = spec.get("var")                      # KernelProd second var = 1.0 (kernels.py:215-219)
+        if self.kind in ("LIN", "POL") and "var" not in spec:
+            self.fixed_var = 1.0                               # kernels.py:320,325: LIN / POL default var=1
         hy = []
         if self.fixed_var is None:
             hy.append(_Hyper(self.name + "_var", 1, True))     # kernels.py:22-24
@@ -195,6 +197,11 @@ class _Leaf(KernelNode):
             hy.append(_Hyper(self.name + "_rate", self.nd, True))
         if k in ("COS", "SINC"):                               # kernels.py:463,476: rate=1.0 constant, freq only
             hy.append(_Hyper(self.name + "_freq", self.nd, True))
+        if k in ("KernelDot", "LIN", "POL"):                   # metrics.py:79-83 (ARD.rate), :126-128 (bias after rate)
+            hy.append(_Hyper(self.name + "_rate", self.nd, True))
+            if k != "KernelDot":
+                hy.append(_Hyper(self.name + "_bias", 1, True))
+        self.power = int(spec.get("p", 2)) if k == "POL" else 1  # kernels.py:325-327
         self.hypers = tuple(hy)
 
     def _split(self, th):
@@ -253,7 +260,21 @@ class _Leaf(KernelNode):
             pi2 = np.pi ** 2
             return p["var"] * (np.exp(-2 * pi2 * np.dot(diff ** 2, p["rate"] ** 2))
                                * np.prod(np.cos(2 * np.pi * diff * p["freq"]), axis=2))
+        if k in ("KernelDot", "LIN", "POL"):                   # kernels.py:82-96,319-336; metrics.py:110-137
+            return p["var"] * self._dot_metric(p, x1, x2) ** self.power
+        if k == "BW":                                          # kernels.py:291-293; metrics.py:49-51 Minimum
+            a = x1[:, self.dims[0]:self.dims[1]][:, None, :]
+            b = x2[:, self.dims[0]:self.dims[1]][None, :, :]
+            return p["var"] * np.prod(np.minimum(a - b * 0, b - a * 0), axis=2)
+        if k == "VAR":                                         # kernels.py:296-306
+            return p["var"] * np.ones((n1, n2))
         raise ValueError(k)
+
+    def _dot_metric(self, p, x1, x2):
+        a = x1[:, self.dims[0]:self.dims[1]][:, None, :]
+        b = x2[:, self.dims[0]:self.dims[1]][None, :, :]
+        m = np.dot(a * b, p["rate"] ** 2)                      # metrics.py:111-112 ARD_Dot
+        return m if self.kind == "KernelDot" else p["bias"] + m    # metrics.py:131-132 ARD_DotBias
 
     def dcov(self, th, x1, x2, same, nan_quirk=False):
         """List of dK/dtheta_p (natural space), one N1xN2 array per scalar hyper, layout order.
@@ -271,7 +292,17 @@ class _Leaf(KernelNode):
         K = self.cov(th, x1, x2, same)
         if self.fixed_var is None:
             out.append(K / p["var"])
-        if k in ("Noise", "WN"):
+        if k in ("Noise", "WN", "BW", "VAR"):
+            return out
+        if k in ("KernelDot", "LIN", "POL"):
+            a = x1[:, self.dims[0]:self.dims[1]][:, None, :]
+            b = x2[:, self.dims[0]:self.dims[1]][None, :, :]
+            m = self._dot_metric(p, x1, x2)
+            dm = p["var"] * self.power * m ** (self.power - 1)
+            for j in range(self.nd):
+                out.append(dm * 2 * p["rate"][j] * a[:, :, j] * b[:, :, j])
+            if k != "KernelDot":
+                out.append(dm)
             return out
         diff = _gram_broadcast(x1, x2, self.dims)
         if k in ("SE", "MAT32", "MAT52", "RQ"):
@@ -347,6 +378,8 @@ class _Binary(KernelNode):
         n1 = self.k1.n_theta()
         a = self.k1.cov(th[:n1], x1, x2, same)
         b = self.k2.cov(th[n1:], x1, x2, same)
+        if self.op == "max":                                    # kernels.py:247-257
+            return np.maximum(a, b)
         return a + b if self.op == "sum" else a * b
 
     def dcov(self, th, x1, x2, same, nan_quirk=False):
@@ -357,6 +390,9 @@ class _Binary(KernelNode):
             return da + db
         a = self.k1.cov(th[:n1], x1, x2, same)
         b = self.k2.cov(th[n1:], x1, x2, same)
+        if self.op == "max":                                    # Theano: grad of maximum = eq(out, x) * g (both on ties)
+            m = np.maximum(a, b)
+            return [g * (m == a) for g in da] + [g * (m == b) for g in db]
         return [g * b for g in da] + [a * g for g in db]
 
 
@@ -380,9 +416,9 @@ class _Unary(KernelNode):
 
 def build_kernel(spec, D):
     t = spec["type"]
-    if t in ("sum", "prod"):
+    if t in ("sum", "prod", "max"):
         k2s = dict(spec["k2"])
-        leaf = lambda sp: sp["type"] not in ("sum", "prod", "scale", "shift")
+        leaf = lambda sp: sp["type"] not in ("sum", "prod", "max", "scale", "shift")
         # kernels.py:215-219: a product of two leaf kernels that both have var=None fixes k2.var = 1.0
         if t == "prod" and leaf(spec["k1"]) and leaf(k2s) and spec["k1"].get("var") is None and k2s.get("var") is None:
             k2s["var"] = 1.0

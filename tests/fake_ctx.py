@@ -64,6 +64,21 @@ def _eval_desc(desc, th, X1, X2, same, skip_pn=False, grad=False):
                     g[nd.p1_idx + j] = var * env * dfac[:, :, j] * np.delete(fac, j, axis=2).prod(-1)
                     if op == cabi.K_SM:
                         g[nd.p0_idx + j] = var * k * (-4 * pi2 * diff[:, :, j] ** 2 * r[j])
+            elif op == cabi.K_DOT:
+                r = th[nd.p0_idx:nd.p0_idx + w]
+                a, b2 = X1[:, None, nd.dim0:nd.dim1], X2[None, :, nd.dim0:nd.dim1]
+                m = (a * b2 * r ** 2).sum(-1) + (th[nd.p1_idx] if nd.p1_idx >= 0 else 0.0)
+                pw = ((nd.flags >> 8) & 0xff) or 1
+                k = m ** pw
+                dm = var * pw * m ** (pw - 1)
+                for j in range(w):
+                    g[nd.p0_idx + j] = dm * 2 * r[j] * a[:, :, j] * b2[:, :, j]
+                if nd.p1_idx >= 0:
+                    g[nd.p1_idx] = dm
+            elif op == cabi.K_BW:
+                k = np.minimum(X1[:, None, nd.dim0:nd.dim1], X2[None, :, nd.dim0:nd.dim1]).prod(-1)
+            elif op == cabi.K_VAR:
+                k = np.ones((n1, n2))
             elif op == cabi.K_NOISE:
                 k = eye * (0.0 if (skip_pn and nd.flags & cabi.KF_PROCESS_NOISE) else 1.0)
             elif op == cabi.K_WN:
@@ -71,6 +86,14 @@ def _eval_desc(desc, th, X1, X2, same, skip_pn=False, grad=False):
             if nd.var_idx >= 0:
                 g[nd.var_idx] = k
             vals.append(var * k)
+        elif op == cabi.K_MAX:
+            a, b = vals[nd.dim0], vals[nd.dim1]
+            m = np.maximum(a, b)
+            vals.append(m)
+            for i, d in grads[nd.dim0].items():
+                g[i] = g.get(i, 0) + d * (m == a)
+            for i, d in grads[nd.dim1].items():
+                g[i] = g.get(i, 0) + d * (m == b)
         elif op in (cabi.K_SUM, cabi.K_PROD):
             a, b = vals[nd.dim0], vals[nd.dim1]
             vals.append(a + b if op == cabi.K_SUM else a * b)

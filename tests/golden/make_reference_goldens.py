@@ -56,6 +56,8 @@ def ref_kernel(g3, spec, X):
         return ref_kernel(g3, spec['k1'], X) + ref_kernel(g3, spec['k2'], X)
     if t == 'prod':
         return ref_kernel(g3, spec['k1'], X) * ref_kernel(g3, spec['k2'], X)
+    if t == 'max':
+        return g3.KernelMax(ref_kernel(g3, spec['k1'], X), ref_kernel(g3, spec['k2'], X))
     if t == 'scale':
         return spec['c'] * ref_kernel(g3, spec['k'], X)
     if t == 'shift':
@@ -65,6 +67,8 @@ def ref_kernel(g3, spec, X):
         kw['name'] = spec['name']
     if spec.get('var') is not None:
         kw['var'] = spec['var']
+    if t == 'POL' and 'p' in spec:
+        kw['p'] = spec['p']
     cls = g3.KernelNoise if t == 'Noise' else getattr(g3, t)
     return cls(_x_arg(X, spec.get('dims')), **kw)
 
@@ -140,6 +144,16 @@ CASES = {
     'leaf_sm':         dict(spec=dict(kind='gauss', location=K('Zero'), kernel=K('SM')), N=24, D=2, M=7, seed=26),
     'leaf_wn':         dict(spec=dict(kind='gauss', location=K('Zero'), kernel=K('sum', k1=K('SE'), k2=K('WN'))),
                             N=24, D=2, M=7, seed=27),
+    # dot-product / Brownian / constant leaves and KernelMax (SURVEY f-4): non-stationary, diag depends on x
+    'leaf_lin':        dict(spec=dict(kind='gauss', location=K('Zero'), kernel=K('sum', k1=K('LIN'), k2=K('SE'))),
+                            N=24, D=2, M=7, seed=70),
+    'leaf_pol3':       dict(spec=dict(kind='gauss', location=K('Bias'), kernel=K('POL', p=3)), N=24, D=2, M=7, seed=71),
+    'leaf_dot_bw_var': dict(spec=dict(kind='gauss', location=K('Zero'),
+                                      kernel=K('sum', k1=K('sum', k1=K('KernelDot'), k2=K('BW')), k2=K('VAR'))),
+                            N=24, D=2, M=7, seed=72),
+    'alg_max':         dict(spec=dict(kind='gauss', location=K('Zero'),
+                                      kernel=K('max', k1=K('SE'), k2=K('scale', c=0.5, k=K('MAT32')))),
+                            N=24, D=2, M=7, seed=73),
     # operator algebra (a4), column subsets, fixed variances
     'alg_scale_shift': dict(spec=dict(kind='gauss', location=K('Bias'),
                                       kernel=K('shift', c=0.3, k=K('scale', c=1.7, k=K('SE')))), N=24, D=2, M=7, seed=30),
@@ -191,6 +205,10 @@ def theta_for(layout, y, rng, case):
         elif name.endswith('SIN_rate'):
             # SIN = exp(+2 r sin^2) >= its own diagonal (kernels.py:472): K is indefinite unless r is tiny
             v = np.full(size, np.log(case.get('sin_rate', 0.01)))
+        elif name.endswith('_bias'):
+            v += np.log(0.5)
+        elif name.endswith('LIN_rate') or name.endswith('POL_rate') or name.endswith('KernelDot_rate'):
+            v += np.log(0.3)
         elif name.endswith('_freq'):
             v += np.log(0.2)
         elif name.endswith('SM_rate'):

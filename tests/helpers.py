@@ -5,7 +5,7 @@ import numpy as np
 import g3py_b200 as g3
 
 LEAVES = {"SE": g3.SE, "OU": g3.OU, "MAT32": g3.MAT32, "MAT52": g3.MAT52, "RQ": g3.RQ, "SIN": g3.SIN, "COS": g3.COS, "SINC": g3.SINC, "SM": g3.SM, "WN": g3.WN,
-          "Noise": g3.KernelNoise}
+          "Noise": g3.KernelNoise, "KernelDot": g3.KernelDot, "LIN": g3.LIN, "POL": g3.POL, "BW": g3.BW, "VAR": g3.VAR}
 MAPS = {"Identity": g3.Identity, "LinearMapping": g3.LinearMapping, "LogShifted": g3.LogShifted,
         "BoxCoxShifted": g3.BoxCoxShifted, "BoxCoxLinear": g3.BoxCoxLinear, "ArcsinhLinear": g3.ArcsinhLinear,
         "SinhArcsinh": g3.SinhArcsinh}
@@ -24,6 +24,8 @@ def build_kernel(spec, X):
         return build_kernel(spec["k1"], X) + build_kernel(spec["k2"], X)
     if t == "prod":
         return build_kernel(spec["k1"], X) * build_kernel(spec["k2"], X)
+    if t == "max":
+        return g3.KernelMax(build_kernel(spec["k1"], X), build_kernel(spec["k2"], X))
     if t == "scale":
         return spec["c"] * build_kernel(spec["k"], X)
     if t == "shift":
@@ -33,6 +35,8 @@ def build_kernel(spec, X):
         kw["name"] = spec["name"]
     if spec.get("var") is not None:
         kw["var"] = spec["var"]
+    if t == "POL" and "p" in spec:
+        kw["p"] = spec["p"]
     return LEAVES[t](_x_arg(X, spec.get("dims")), **kw)
 
 
