@@ -29,10 +29,11 @@ class HyperVar:
 
 
 class Registry:
-    """Creation-ordered list of hypers (the role `pm.Model` plays for g3py)."""
+    """Creation-ordered list of hypers and potentials (the role `pm.Model` plays for g3py)."""
 
     def __init__(self):
         self.vars = []
+        self.potentials = []     # (name, reg, c, [HyperVar]) -- pm.Potential terms (hypers/__init__.py:94-109)
 
     def Flat(self, name, shape=()):
         return self._add(name, shape, False)
@@ -103,6 +104,23 @@ class Hypers:
 
     def check_hypers(self, parent="", reg=None):
         pass
+
+    def set_potential(self, hypers="", reg="L1", c=1):
+        """hypers/__init__.py:91-92: regulariser -c * sum |h| (L1) or -c * sum h^2 (L2) over this component's hypers
+        whose name contains `hypers` (not at position 0), added to logp as a `pm.Potential`."""
+        self.potential = (hypers, reg, c)
+
+    def potential_hypers(self):
+        """The hypers the reference keeps in `self.hypers` of this component (what `check_potential` iterates over)."""
+        return [h for h in self.hypers if isinstance(h, HyperVar)]
+
+    def check_potential(self, reg=None):
+        # hypers/__init__.py:94-109
+        if getattr(self, "potential", None) is None:
+            return
+        hypers, kind, c = self.potential
+        sel = [h for h in self.potential_hypers() if h.name.find(hypers) > 0]
+        reg.potentials.append((self.name + "_" + hypers + "_" + kind, kind, float(c), sel))
 
     def default_hypers(self, x=None, y=None):
         return {}

@@ -133,6 +133,13 @@ class KernelOperation(Kernel):
     def nan_quirk_hypers(self):
         return self.k.nan_quirk_hypers()
 
+    def check_potential(self, reg=None):                                 # kernels.py:131-133
+        Hypers.check_potential(self, reg)
+        self.k.check_potential(reg)
+
+    def potential_hypers(self):
+        return self.k.potential_hypers()
+
 
 class KernelScale(KernelOperation):
     OP = cabi.K_SCALE
@@ -192,6 +199,14 @@ class KernelComposition(Kernel):
     def nan_quirk_hypers(self):
         return self.k1.nan_quirk_hypers() + self.k2.nan_quirk_hypers()
 
+    def check_potential(self, reg=None):                                 # kernels.py:163-166
+        Hypers.check_potential(self, reg)
+        self.k1.check_potential(reg)
+        self.k2.check_potential(reg)
+
+    def potential_hypers(self):
+        return self.k1.potential_hypers() + self.k2.potential_hypers()
+
 
 class KernelProd(KernelComposition):
     OP = cabi.K_PROD
@@ -240,6 +255,12 @@ class KernelStationary(Kernel):
             except Exception:
                 pass
         return d
+
+    def potential_hypers(self):
+        # the ARD `rate` (and ARD_DotBias `bias`) live on the metric object in the reference (metrics.py:79-83), whose
+        # check_potential is never called: only var (+ alpha / freq / periodic rate) can be regularised
+        skip = [self.rate] + [getattr(self, "bias", None)]
+        return [h for h in self.hypers if isinstance(h, HyperVar) and not any(h is q for q in skip)]
 
     def _common(self, b):
         d0, d1 = self.dim_range(b.D)
@@ -322,6 +343,9 @@ class KernelPeriodic(KernelStationary):
         for h in (self.rate, self.freq):
             if isinstance(h, HyperVar) and h not in self.hypers:
                 self.hypers += [h]
+
+    def potential_hypers(self):                                          # kernels.py:446-454: rate and freq are the kernel's own
+        return [h for h in self.hypers if isinstance(h, HyperVar)]
 
     def default_hypers(self, x=None, y=None):
         d = Kernel.default_hypers(self, x, y)

@@ -67,6 +67,9 @@ class MappingComposed(Mapping):      # mappings.py:56-71
         self.m1.check_dims(x)
         self.m2.check_dims(x)
 
+    def check_potential(self, reg=None):
+        Hypers.check_potential(self, reg)
+
     def default_hypers_dims(self, x=None, y=None):
         return {**self.m1.default_hypers_dims(x, y), **self.m2.default_hypers_dims(x, y)}
 

@@ -286,9 +286,12 @@ class EllipticalProcess(StochasticProcess):
         self.f_location.check_hypers(parent, self.registry)
         self.f_kernel_noise.check_hypers(parent, self.registry)
         self.f_mapping.check_hypers(parent, self.registry)
+        for comp in (self.f_location, self.f_kernel_noise, self.f_mapping):      # elliptical.py:44-46
+            comp.check_potential(self.registry)
         if self.f_degree is not None:
             self.f_degree.check_dims(None)
             self.f_degree.check_hypers(parent, self.registry)
+            self.f_degree.check_potential(self.registry)
         self._finish_layout()
 
     def _define_process(self):
@@ -347,10 +350,26 @@ class EllipticalProcess(StochasticProcess):
         return self.f_degree.bound + deg                                  # hypers/__init__.py:159-160
 
     def logprior_batch(self, Theta):
-        """Free-RV terms: Flat = 0, NonTransformLog barrier -inf at exp(theta) <= 1e-6."""
+        """Free-RV terms (Flat = 0, NonTransformLog barrier -inf at exp(theta) <= 1e-6) plus the `pm.Potential`
+        regularisers (stochastic.py:300-306: logp = sum of RV terms + potentials, for prior and posterior alike)."""
         nat = self.natural(np.atleast_2d(Theta))
         bad = np.any((nat <= 1e-6) & self.positive_mask[None, :], axis=1)
-        return np.where(bad, -np.inf, 0.0)
+        return np.where(bad, -np.inf, 0.0) + self._potentials(nat)[0]
+
+    def _potentials(self, nat2d):
+        """(sum of potentials (B,), d/d natural hypers (B, P)); hypers/__init__.py:94-109 on natural-space values."""
+        val = np.zeros(nat2d.shape[0])
+        g = np.zeros_like(nat2d)
+        for _, kind, c, hs in self.registry.potentials:
+            for h in hs:
+                v = nat2d[:, h.offset:h.offset + h.size]
+                if kind == "L1":
+                    val += -c * np.abs(v).sum(axis=1)
+                    g[:, h.offset:h.offset + h.size] += -c * np.sign(v)
+                elif kind == "L2":
+                    val += -c * (v ** 2).sum(axis=1)
+                    g[:, h.offset:h.offset + h.size] += -2.0 * c * v
+        return val, g
 
     def _host_terms(self, nat2d, inputs, outputs, want_grad):
         """delta (B,N) or (N,), det_m (B,), and the host Jacobians of the location / mapping hypers."""
@@ -440,6 +459,9 @@ class EllipticalProcess(StochasticProcess):
             g_nat[:, self.f_degree.degree.offset] += d_r1 + d_r2
         g = np.where(self.positive_mask[None, :], g_nat * nat, g_nat)     # chain rule through exp
         g[failed | bad] = 0.0
+        if self.registry.potentials:                                      # potentials do not depend on the data
+            gp_nat = self._potentials(nat)[1]
+            g = g + np.where(self.positive_mask[None, :], gp_nat * nat, gp_nat)
         if self.reference_nan_quirk if nan_quirk is None else nan_quirk:
             for h in self.f_kernel_noise.nan_quirk_hypers():
                 g[:, h.offset:h.offset + h.size] = 0.0
@@ -463,8 +485,10 @@ class EllipticalProcess(StochasticProcess):
     def dlogp(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
               array=False, reference_nan_quirk=None):
         theta = self._theta(params, array)
-        if prior:
-            return np.zeros(self.ndim)
+        if prior:                       # free RVs are flat: only the potentials have a gradient
+            nat = self.natural(np.atleast_2d(theta))
+            gp_nat = self._potentials(nat)[1]
+            return np.where(self.positive_mask[None, :], gp_nat * nat, gp_nat)[0]
         _, g, _ = self._eval_batch(theta, inputs, outputs, want_grad=True, nan_quirk=reference_nan_quirk)
         return g[0]
 

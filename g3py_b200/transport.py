@@ -72,6 +72,8 @@ class TransportGaussianProcess(EllipticalProcess):
         for comp in (self.f_location, self.f_mapping):        # composites collect the hypers created above
             comp.check_dims(x)
             comp.check_hypers(parent, self.registry)
+        # transport.py:27 calls f_transport.check_potential(), which Transport does not forward to its parametrics:
+        # potentials set on the pieces of a transport are never registered in the reference
         self._finish_layout()
 
     def _eval_batch(self, Theta, inputs=None, outputs=None, want_grad=True, nan_quirk=None):

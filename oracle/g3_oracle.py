@@ -672,10 +672,74 @@ class OracleProcess:
         return nat[:a], nat[a:b], nat[b:c], nat[c:]
 
     def logprior(self, theta):
-        """Sum of free-RV logp: Flat (0) + NonTransformLog.jacobian_det (hypers/__init__.py:200-201)."""
+        """Sum of free-RV logp: Flat (0) + NonTransformLog.jacobian_det (hypers/__init__.py:200-201), plus the
+        pm.Potential regularisers (stochastic.py:300-306 adds model.potentials for prior and posterior alike)."""
         nat = self.natural(theta)
         m = self.positive_mask()
-        return 0.0 if np.all(nat[m] > 1e-6) else -np.inf
+        return (0.0 if np.all(nat[m] > 1e-6) else -np.inf) + self.potentials(nat)[0]
+
+    def _potential_specs(self):
+        """[(substring, reg, c, [hyper names])] from `"potential": [hypers, reg, c]` entries of the spec, with the hyper
+        lists `check_potential` iterates over (hypers/__init__.py:94-109): a leaf kernel owns var (+ alpha, periodic
+        freq / rate) but not the ARD metric's rate / bias; a composition owns its children's; means and mappings all."""
+        out = []
+
+        def kernel_hypers(sp):
+            t = sp["type"]
+            if t in ("sum", "prod", "max"):
+                return kernel_hypers(sp["k1"]) + kernel_hypers(sp["k2"])
+            if t in ("scale", "shift"):
+                return kernel_hypers(sp["k"])
+            name = sp.get("name", t)
+            fixed = sp.get("var") is not None or (t in ("LIN", "POL") and "var" not in sp)
+            hs = [] if fixed else [name + "_var"]
+            if t == "RQ":
+                hs.append(name + "_alpha")
+            if t in ("SIN", "SM"):
+                hs += [name + "_rate", name + "_freq"]
+            if t in ("COS", "SINC"):
+                hs.append(name + "_freq")
+            return hs
+
+        def walk(sp):
+            t = sp["type"]
+            if "potential" in sp:
+                out.append(tuple(sp["potential"]) + (kernel_hypers(sp),))
+            if t in ("sum", "prod", "max"):
+                walk(sp["k1"]); walk(sp["k2"])
+            elif t in ("scale", "shift"):
+                walk(sp["k"])
+
+        loc = self.spec.get("location", {"type": "Zero"})
+        if "potential" in loc:
+            out.append(tuple(loc["potential"]) + ([h.name for h in self.location.layout()],))
+        walk(self.spec["kernel"])
+        mp = self.spec.get("mapping", {"type": "Identity"})
+        if "potential" in mp:
+            out.append(tuple(mp["potential"]) + ([h.name for h in self.mapping.layout()],))
+        return out
+
+    def potentials(self, nat):
+        """(value, d/d natural hypers)."""
+        pname = self.spec.get("name", {"gauss": "GP", "student": "TP"}[self.kind])
+        if self.spec.get("warped", self.mapping.kind != "Identity"):
+            pname = self.spec.get("name", {"gauss": "WGP", "student": "WTP"}[self.kind])
+        val, g = 0.0, np.zeros(self.P)
+        off = {}
+        o = 0
+        for h in self._layout:
+            off[h.name] = (o, h.size)
+            o += h.size
+        for sub, reg, c, names in self._potential_specs():
+            for nm in names:
+                if (pname + "_" + nm).find(sub) > 0:             # k.name.find(hypers) > 0 on the full variable name
+                    a, n = off[nm]
+                    v = nat[a:a + n]
+                    if reg == "L1":
+                        val += -c * np.sum(np.abs(v)); g[a:a + n] += -c * np.sign(v)
+                    elif reg == "L2":
+                        val += -c * np.sum(v ** 2); g[a:a + n] += -2.0 * c * v
+        return val, g
 
     # ---- pieces --------------------------------------------------------------------------
     def cov_inputs(self, nat_k, X):
@@ -772,7 +836,7 @@ class OracleProcess:
             else:
                 d_r2 = 0.5 * digamma((nu + n) * 0.5) - 0.5 * digamma(nu * 0.5) - 0.5 * n / (nu - 2.0)
             parts.append(np.array([d_r1 + d_r2]))
-        g_nat = np.concatenate(parts)
+        g_nat = np.concatenate(parts) + self.potentials(nat)[1]
         m = self.positive_mask()
         g = np.where(m, g_nat * nat, g_nat)                     # chain rule through exp (log-space hypers)
         return tt_to_num(g)

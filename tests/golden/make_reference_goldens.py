@@ -50,7 +50,17 @@ def _x_arg(X, dims):
     return X if dims is None else list(range(int(dims[0]), int(dims[1])))
 
 
+def _pot(obj, spec):
+    if 'potential' in spec:
+        obj.set_potential(*spec['potential'])
+    return obj
+
+
 def ref_kernel(g3, spec, X):
+    return _pot(_ref_kernel(g3, spec, X), spec)
+
+
+def _ref_kernel(g3, spec, X):
     t = spec['type']
     if t == 'sum':
         return ref_kernel(g3, spec['k1'], X) + ref_kernel(g3, spec['k2'], X)
@@ -100,9 +110,9 @@ def ref_process(g3, spec, X):
            ('student', True): g3.WTP}[(kind, warped)]
     loc = spec.get('location', {'type': 'Zero'})
     lkw = {'name': loc['name']} if 'name' in loc else {}
-    location = getattr(g3, loc['type'])(_x_arg(X, loc.get('dims')), **lkw)
+    location = _pot(getattr(g3, loc['type'])(_x_arg(X, loc.get('dims')), **lkw), loc)
     mkw = {'name': mp['name']} if 'name' in mp else {}
-    mapping = getattr(g3, mp['type'])(**mkw)
+    mapping = _pot(getattr(g3, mp['type'])(**mkw), mp)
     kw = {'name': spec['name']} if 'name' in spec else {}
     return cls(X, location, ref_kernel(g3, spec['kernel'], X), mapping, noisy=spec.get('noisy', True), **kw)
 
@@ -154,6 +164,12 @@ CASES = {
     'alg_max':         dict(spec=dict(kind='gauss', location=K('Zero'),
                                       kernel=K('max', k1=K('SE'), k2=K('scale', c=0.5, k=K('MAT32')))),
                             N=24, D=2, M=7, seed=73),
+    # pm.Potential regularisers (hypers/__init__.py:94-109)
+    'potentials':      dict(spec=dict(kind='gauss', warped=True, location=dict(type='Bias', potential=['Bias', 'L2', 0.3]),
+                                      kernel=dict(type='sum', potential=['var', 'L1', 0.7],
+                                                  k1=dict(type='SE'), k2=dict(type='RQ', potential=['alpha', 'L2', 0.2])),
+                                      mapping=dict(type='BoxCoxShifted', potential=['power', 'L1', 0.4])),
+                            N=24, D=2, M=7, seed=80, positive=True),
     # operator algebra (a4), column subsets, fixed variances
     'alg_scale_shift': dict(spec=dict(kind='gauss', location=K('Bias'),
                                       kernel=K('shift', c=0.3, k=K('scale', c=1.7, k=K('SE')))), N=24, D=2, M=7, seed=30),

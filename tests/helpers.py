@@ -18,7 +18,17 @@ def _x_arg(X, dims):
     return (X, slice(int(dims[0]), int(dims[1])))
 
 
+def _pot(obj, spec):
+    if "potential" in spec:
+        obj.set_potential(*spec["potential"])
+    return obj
+
+
 def build_kernel(spec, X):
+    return _pot(_build_kernel(spec, X), spec)
+
+
+def _build_kernel(spec, X):
     t = spec["type"]
     if t == "sum":
         return build_kernel(spec["k1"], X) + build_kernel(spec["k2"], X)
@@ -69,10 +79,10 @@ def build_process(spec, X, strict=True):
     cls = {("gauss", False): g3.GP, ("gauss", True): g3.WGP, ("student", False): g3.TP, ("student", True): g3.WTP}[(kind, warped)]
     loc = spec.get("location", {"type": "Zero"})
     lkw = {"name": loc["name"]} if "name" in loc else {}
-    location = MEANS[loc["type"]](_x_arg(X, loc.get("dims")), **lkw)
+    location = _pot(MEANS[loc["type"]](_x_arg(X, loc.get("dims")), **lkw), loc)
     mp = spec.get("mapping", {"type": "Identity"})
     mkw = {"name": mp["name"]} if "name" in mp else {}
-    mapping = MAPS[mp["type"]](**mkw)
+    mapping = _pot(MAPS[mp["type"]](**mkw), mp)
     kw = {}
     if "name" in spec:
         kw["name"] = spec["name"]

@@ -73,9 +73,64 @@ def compile_both(D, spec, rng):
     return X, ok, desc, th_o, th_p[:desc.n_theta], b.slots
 
 
-@pytest.mark.parametrize("idx", range(24))
+# second family: the non-stationary leaves (dot-product, Brownian, constant) and the max node mixed in
+LEAVES2 = LEAVES + ["KernelDot", "LIN", "POL", "BW", "VAR"] * 2
+
+
+def random_spec2(rng, D, depth, names):
+    if depth == 0 or rng.random() < 0.35:
+        t = LEAVES2[rng.integers(len(LEAVES2))]
+        lo = int(rng.integers(0, D))
+        hi = int(rng.integers(lo + 1, D + 1))
+        n = "%s%d" % (t, len(names))
+        names.append(n)
+        sp = {"type": t, "name": n, "dims": [lo, hi]}
+        if t == "POL":
+            sp["p"] = int(rng.integers(1, 5))
+        return sp
+    r = rng.random()
+    kids = lambda: (random_spec2(rng, D, depth - 1, names), random_spec2(rng, D, depth - 1, names))
+    if r < 0.35:
+        a, b = kids()
+        return {"type": "sum", "k1": a, "k2": b}
+    if r < 0.6:
+        a, b = kids()
+        return {"type": "prod", "k1": a, "k2": b}
+    if r < 0.8:
+        a, b = kids()
+        return {"type": "max", "k1": a, "k2": b}
+    if r < 0.9:
+        return {"type": "scale", "c": float(np.round(rng.uniform(0.3, 2.0), 3)), "k": random_spec2(rng, D, depth - 1, names)}
+    return {"type": "shift", "c": float(np.round(rng.uniform(0.1, 1.0), 3)), "k": random_spec2(rng, D, depth - 1, names)}
+
+
+def n_nodes2(spec):
+    t = spec["type"]
+    if t in ("sum", "prod", "max"):
+        return 1 + n_nodes2(spec["k1"]) + n_nodes2(spec["k2"])
+    if t in ("scale", "shift"):
+        return 1 + n_nodes2(spec["k"])
+    return 1
+
+
+def cases2(n=16):
+    rng = np.random.default_rng(4048)
+    out = []
+    while len(out) < n:
+        D = int(rng.integers(1, 6))
+        spec = random_spec2(rng, D, 3, [])
+        if n_nodes2(spec) <= 16:
+            out.append((D, spec))
+    return out
+
+
+def _case(idx):
+    return cases()[idx] if idx < 24 else cases2()[idx - 24]
+
+
+@pytest.mark.parametrize("idx", range(40))
 def test_descriptor_matches_oracle_cpu(idx):
-    D, spec = cases()[idx]
+    D, spec = _case(idx)
     rng = np.random.default_rng(idx)
     X, ok, desc, th_o, th_p, slots = compile_both(D, spec, rng)
     X2 = rng.uniform(0, 2, size=(11, D))
@@ -93,9 +148,9 @@ def test_descriptor_matches_oracle_cpu(idx):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("idx", range(24))
+@pytest.mark.parametrize("idx", range(40))
 def test_descriptor_matches_oracle_gpu(idx):
-    D, spec = cases()[idx]
+    D, spec = _case(idx)
     rng = np.random.default_rng(idx)
     X, ok, desc, th_o, th_p, slots = compile_both(D, spec, rng)
     rng2 = np.random.default_rng(1000 + idx)
