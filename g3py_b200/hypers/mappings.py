@@ -9,7 +9,7 @@ import numpy as np
 from . import Hypers, HyperVar
 
 __all__ = ["Mapping", "Identity", "LinearMapping", "LogShifted", "BoxCoxShifted", "BoxCoxLinear", "ArcsinhLinear",
-           "SinhArcsinh", "MappingComposed"]
+           "SinhArcsinh", "MappingComposed", "Logistic", "WarpingTanh", "WarpingBoxCox"]
 
 _F32_1EM32 = float(np.float32(1e-32))
 _F32_1EM5 = float(np.float32(1e-5))
@@ -17,6 +17,14 @@ _F32_1EM5 = float(np.float32(1e-5))
 
 def _v(p, h):
     return float(p(h)) if isinstance(h, HyperVar) else float(h)
+
+
+def _vec(p, h, n):
+    return np.broadcast_to(np.asarray(p(h) if isinstance(h, HyperVar) else h, dtype=np.float64).reshape(-1), (n,))
+
+
+def _tt_to_num(r):
+    return np.where(np.isnan(r), 0.0, np.where(np.isinf(r), 1e10, r))
 
 
 class Mapping(Hypers):
@@ -98,7 +106,7 @@ class MappingComposed(Mapping):      # mappings.py:56-71
         h = 1e-6 * np.maximum(1.0, np.abs(w))
         dlog = (np.log(np.abs(self.m2.dinv_dy(w + h, p))) - np.log(np.abs(self.m2.dinv_dy(w - h, p)))) / (2 * h)
         dinv = {k: d2dw * v for k, v in di1.items()}
-        dld = {k: v + float(np.sum(dlog * di1[k])) for k, v in dl1.items()}
+        dld = {k: v + np.sum(dlog * di1[k], axis=-1) for k, v in dl1.items()}
         for k, v in di2.items():
             dinv[k] = v
         for k, v in dl2.items():
@@ -340,3 +348,185 @@ class SinhArcsinh(Mapping):          # mappings.py:336-358
         n = float(y.shape[0])
         return ({self.shift: np.cosh(w), self.scale: np.cosh(w) * ash},
                 {self.shift: float(np.sum(np.tanh(w))), self.scale: float(np.sum(np.tanh(w) * ash)) + n / s})
+
+
+class Logistic(Mapping):             # mappings.py:363-397
+    def __init__(self, y=None, name=None, lower=None, high=None, location=None, scale=None):
+        super().__init__(y, name)
+        self.lower, self.high, self.location, self.scale = lower, high, location, scale
+
+    def check_hypers(self, parent="", reg=None):
+        self._reg(parent, reg, "lower", False)
+        self._reg(parent, reg, "high", True)
+        self._reg(parent, reg, "location", False)
+        self._reg(parent, reg, "scale", True)
+
+    def default_hypers(self, x=None, y=None):
+        y = np.asarray(y, dtype=np.float64)
+        d = {self.lower: 1.5 * np.min(y) - 0.5 * np.max(y), self.high: 2.0 * (np.max(y) - np.min(y)),
+             self.location: np.mean(y), self.scale: np.std(y)}
+        return {h: float(v) for h, v in d.items() if isinstance(h, HyperVar)}
+
+    def _p(self, y, p):
+        lo, hi = _v(p, self.lower), _v(p, self.high)
+        return np.where(y < lo, 0.0, np.where(y > lo + hi, 1.0, (y - lo) / hi))
+
+    def __call__(self, z, p):
+        return _v(p, self.lower) + _v(p, self.high) * (0.5 + 0.5 * np.tanh((z - _v(p, self.location)) / (2 * _v(p, self.scale))))
+
+    def inv(self, y, p):
+        with np.errstate(all="ignore"):
+            q = self._p(y, p)
+            return _v(p, self.location) + _v(p, self.scale) * _tt_to_num(np.log(q / (1 - q)))
+
+    def logdet_dinv(self, y, p):
+        with np.errstate(all="ignore"):
+            q = self._p(y, p)
+            return float(np.sum(_tt_to_num(np.log(_v(p, self.scale) / (_v(p, self.high) * q * (1 - q))))))
+
+    def dinv_dy(self, y, p):
+        q = self._p(y, p)
+        with np.errstate(all="ignore"):
+            return _tt_to_num(_v(p, self.scale) / (_v(p, self.high) * q * (1 - q)))
+
+    def grads(self, y, p):
+        hi, sc = _v(p, self.high), _v(p, self.scale)
+        q = self._p(y, p)
+        live = (q > 0.0) & (q < 1.0)                  # saturated points are constants of the switch (mappings.py:392)
+        with np.errstate(all="ignore"):
+            dq = np.where(live, 1.0 / (q * (1 - q)), 0.0)
+            dl = np.where(live, -1.0 / q + 1.0 / (1 - q), 0.0)
+            lq = np.where(live, np.log(q / (1 - q)), 0.0)
+        n_live = float(np.sum(live))
+        dinv = {self.lower: sc * dq * (-1.0 / hi), self.high: sc * dq * (-q / hi), self.location: np.ones_like(y),
+                self.scale: lq}
+        dld = {self.lower: float(np.sum(dl * (-1.0 / hi))), self.high: float(-n_live / hi + np.sum(dl * (-q / hi))),
+               self.location: 0.0, self.scale: n_live / sc}
+        return ({h: v for h, v in dinv.items() if isinstance(h, HyperVar)},
+                {h: v for h, v in dld.items() if isinstance(h, HyperVar)})
+
+
+class _NewtonWarping(Mapping):
+    """Warpings given by their inverse only: the forward map is `inverse_function(self.inv, z)` (mappings.py:11-12,
+    libs/tensors.py:134-145) -- a damped Newton iteration from 0 (step 0.1, slopes below 1 replaced by their sign)
+    stopped when max|inv(x) - z| < 1e-3 over the whole vector.  Reproduced literally, so T(z) carries the reference's
+    ~1e-3 error; `logdet_dinv` is the reference's `sum(log(diag(jacobian(inv))))` in closed form."""
+    NAMES = ()
+
+    def __init__(self, y=None, n=1, name=None):
+        super().__init__(y, name)
+        self.n = int(n)
+
+    def _regn(self, parent, reg, attr, positive):
+        h = getattr(self, attr)
+        if h is None:
+            h = (reg.FlatExp if positive else reg.Flat)(parent + self.name + "_" + attr, shape=self.n)
+            setattr(self, attr, h)
+        if isinstance(h, HyperVar) and h not in self.hypers:
+            self.hypers += [h]
+
+    def logdet_dinv(self, y, p):
+        with np.errstate(all="ignore"):
+            return float(np.sum(np.log(self.dinv_dy(y, p))))
+
+    def __call__(self, z, p, tol=1e-3, n_steps=1024, alpha=0.1):
+        z = np.asarray(z, dtype=np.float64)
+        x = 0.0 * z
+        for _ in range(n_steps):
+            diff = self.inv(x, p) - z
+            d = self.dinv_dy(x, p)
+            d = np.where(np.abs(d) < 1.0, np.sign(d), d)
+            x = x - alpha * diff / d
+            if np.max(np.abs(diff)) < tol:
+                break
+        return x
+
+    def grads(self, y, p):
+        dinv, dD = self._partials(y, p)
+        Dy = self.dinv_dy(y, p)
+        hs = [getattr(self, a) for a in self.NAMES]
+        return ({h: v for h, v in zip(hs, dinv) if isinstance(h, HyperVar)},
+                {h: np.sum(v / Dy, axis=1) for h, v in zip(hs, dD) if isinstance(h, HyperVar)})
+
+
+class WarpingTanh(_NewtonWarping):   # mappings.py:253-278: inv(y) = y + sum_j a_j tanh(b_j (y + c_j))
+    NAMES = ("a", "b", "c")
+
+    def __init__(self, y=None, n=1, name=None, a=None, b=None, c=None):
+        super().__init__(y, n, name)
+        self.a, self.b, self.c = a, b, c
+
+    def check_hypers(self, parent="", reg=None):
+        self._regn(parent, reg, "a", True)
+        self._regn(parent, reg, "b", True)
+        self._regn(parent, reg, "c", False)
+
+    def default_hypers(self, x=None, y=None):
+        y = np.asarray(y, dtype=np.float64)
+        one = np.ones(self.n)
+        d = {self.a: 0.1 * one * np.abs(y).max() / self.n, self.b: 0.1 * one / np.abs(y).max(), self.c: one * np.mean(y)}
+        return {h: v for h, v in d.items() if isinstance(h, HyperVar)}
+
+    def _abc(self, p):
+        return _vec(p, self.a, self.n), _vec(p, self.b, self.n), _vec(p, self.c, self.n)
+
+    def inv(self, y, p):
+        a, b, c = self._abc(p)
+        return y + np.dot(np.tanh(b * (y[:, None] + c)), a)
+
+    def dinv_dy(self, y, p):
+        a, b, c = self._abc(p)
+        return 1.0 + np.dot(1.0 / np.cosh(b * (y[:, None] + c)) ** 2, a * b)
+
+    def _partials(self, y, p):
+        a, b, c = self._abc(p)
+        yc = y[:, None] + c
+        u = b * yc
+        t, s2 = np.tanh(u), 1.0 / np.cosh(u) ** 2
+        dinv = (t.T, (a * s2 * yc).T, (a * b * s2).T)
+        dD = ((b * s2).T, (a * s2 - 2.0 * a * b * s2 * t * yc).T, (-2.0 * a * b * b * s2 * t).T)
+        return dinv, dD
+
+
+class WarpingBoxCox(_NewtonWarping):  # mappings.py:281-306: inv(y) = sum_j w_j (sgn(s_j)|s_j|^p_j - 1)/p_j, s_j = y + shift_j
+    NAMES = ("shift", "power", "w")
+
+    def __init__(self, y=None, n=1, name=None, shift=None, power=None, w=None):
+        super().__init__(y, n, name)
+        self.shift, self.power, self.w = shift, power, w
+
+    def check_hypers(self, parent="", reg=None):
+        self._regn(parent, reg, "shift", True)
+        self._regn(parent, reg, "power", True)
+        self._regn(parent, reg, "w", True)
+
+    def default_hypers(self, x=None, y=None):
+        one = np.ones(self.n)
+        d = {self.w: one / self.n, self.shift: one, self.power: one}
+        return {h: v for h, v in d.items() if isinstance(h, HyperVar)}
+
+    def _spw(self, p):
+        return _vec(p, self.shift, self.n), _vec(p, self.power, self.n), _vec(p, self.w, self.n)
+
+    def inv(self, y, p):
+        shift, power, w = self._spw(p)
+        sh = y[:, None] + shift
+        with np.errstate(all="ignore"):
+            return np.dot((np.sign(sh) * np.abs(sh) ** power - 1.0) / power, w)
+
+    def dinv_dy(self, y, p):
+        shift, power, w = self._spw(p)
+        with np.errstate(all="ignore"):
+            return np.dot(np.abs(y[:, None] + shift) ** (power - 1.0), w)
+
+    def _partials(self, y, p):
+        shift, power, w = self._spw(p)
+        sh = y[:, None] + shift
+        with np.errstate(all="ignore"):
+            ab = np.abs(sh)
+            sp = np.sign(sh) * ab ** power
+            dinv = ((w * ab ** (power - 1.0)).T, (w * (sp * np.log(ab) * power - (sp - 1.0)) / power ** 2).T,
+                    ((sp - 1.0) / power).T)
+            dD = ((w * (power - 1.0) * ab ** (power - 2.0) * np.sign(sh)).T, (w * ab ** (power - 1.0) * np.log(ab)).T,
+                  (ab ** (power - 1.0)).T)
+        return dinv, dD

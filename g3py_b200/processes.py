@@ -448,8 +448,8 @@ class EllipticalProcess(StochasticProcess):
             gd = ddl[b]
             for h, J in jl.items():                                       # d delta / d loc = -J
                 g_nat[b, h.offset:h.offset + h.size] += -(np.atleast_2d(J) @ gd)
-            for h, J in dinv.items():
-                g_nat[b, h.offset] += float(np.dot(J, gd)) + dld[h]
+            for h, J in dinv.items():                                     # scalar hypers: J (N,); vector: (size, N)
+                g_nat[b, h.offset:h.offset + h.size] += np.atleast_2d(J) @ gd + np.atleast_1d(dld[h])
         if self.KIND == cabi.KIND_STUDENT and isinstance(self.f_degree.degree, HyperVar):
             with np.errstate(all="ignore"):
                 bn = beta / (nu - 2.0)

@@ -479,6 +479,8 @@ class _Mapping:
         self.kind = spec["type"]
         self.name = spec.get("name", "BoxShift" if self.kind == "BoxCoxShifted" else self.kind)
         H = lambda s, pos: _Hyper(self.name + "_" + s, 1, pos)
+        self.n = int(spec.get("n", 1))
+        Hn = lambda s, pos: _Hyper(self.name + "_" + s, self.n, pos)
         self.hypers = {
             "Identity": (),
             "LinearMapping": (H("shift", False), H("scale", True)),        # mappings.py:107-112
@@ -487,16 +489,56 @@ class _Mapping:
             "BoxCoxLinear": (H("shift", False), H("scale", True), H("power", True)),  # :190-197
             "ArcsinhLinear": (H("shift", False), H("scale", True)),        # mappings.py:315-320
             "SinhArcsinh": (H("shift", False), H("scale", True)),          # mappings.py:340-345
+            "Logistic": (H("lower", False), H("high", True), H("location", False), H("scale", True)),   # :369-377
+            "WarpingTanh": (Hn("a", True), Hn("b", True), Hn("c", False)),                 # mappings.py:262-268
+            "WarpingBoxCox": (Hn("shift", True), Hn("power", True), Hn("w", True)),        # mappings.py:290-296
         }[self.kind]
 
     def layout(self):
         return list(self.hypers)
 
     def n_theta(self):
-        return len(self.hypers)
+        return sum(h.size for h in self.hypers)
+
+    def _dinv_dy(self, th, y):
+        """d inv / d y for the Newton-inverse warpings (what tt.grad(tt.sum(func(x) - z), x) evaluates to)."""
+        n = self.n
+        z = y[:, None]
+        if self.kind == "WarpingTanh":
+            a, b, c = th[:n], th[n:2 * n], th[2 * n:]
+            return 1.0 + np.dot(1.0 / np.cosh(b * (z + c)) ** 2, a * b)
+        shift, power, w = th[:n], th[n:2 * n], th[2 * n:]
+        return np.dot(np.abs(z + shift) ** (power - 1.0), w)
+
+    def _newton_forward(self, th, z, tol=1e-3, n_steps=1024, alpha=0.1):
+        """Mapping.__call__ = inverse_function(self.inv, z) (mappings.py:11-12, libs/tensors.py:134-145): damped
+        Newton from 0, step alpha = 0.1, slopes below 1 replaced by their sign, stopped when max|inv(x) - z| < 1e-3 on
+        the WHOLE vector -- restated literally (the result is only ~1e-3 accurate, by construction)."""
+        x = 0.0 * z
+        for _ in range(n_steps):
+            diff = self.inv(th, x) - z
+            dfunc = self._dinv_dy(th, x)
+            dfunc = np.where(np.abs(dfunc) < 1.0, np.sign(dfunc), dfunc)
+            x = x - alpha * diff / dfunc
+            if np.max(np.abs(diff)) < tol:
+                break
+        return x
 
     def inv(self, th, y):
         k = self.kind
+        if k == "Logistic":                                    # mappings.py:391-393
+            with np.errstate(all="ignore"):
+                p = np.where(y < th[0], 0.0, np.where(y > th[0] + th[1], 1.0, (y - th[0]) / th[1]))
+                return th[2] + th[3] * tt_to_num(np.log(p / (1 - p)))
+        if k == "WarpingTanh":                                 # mappings.py:275-278
+            n = self.n
+            a, b, c = th[:n], th[n:2 * n], th[2 * n:]
+            return y + np.dot(np.tanh(b * (y[:, None] + c)), a)
+        if k == "WarpingBoxCox":                               # mappings.py:303-306
+            n = self.n
+            shift, power, w = th[:n], th[n:2 * n], th[2 * n:]
+            sh = y[:, None] + shift
+            return np.dot((np.sign(sh) * np.abs(sh) ** power - 1.0) / power, w)
         if k == "Identity":
             return y                                           # mappings.py:95-96
         if k == "LinearMapping":
@@ -522,6 +564,13 @@ class _Mapping:
     def logdet_dinv(self, th, y):
         k = self.kind
         n = float(y.shape[0])
+        if k == "Logistic":                                    # mappings.py:395-397
+            with np.errstate(all="ignore"):
+                p = np.where(y < th[0], 0.0, np.where(y > th[0] + th[1], 1.0, (y - th[0]) / th[1]))
+                return float(np.sum(tt_to_num(np.log(th[3] / (th[1] * p * (1 - p))))))
+        if k in ("WarpingTanh", "WarpingBoxCox"):              # mappings.py:19-23: sum log diag(jacobian(inv))
+            with np.errstate(all="ignore"):
+                return float(np.sum(np.log(self._dinv_dy(th, y))))
         if k == "Identity":
             return 0.0                                         # :98-99
         if k == "LinearMapping":
@@ -541,6 +590,10 @@ class _Mapping:
 
     def forward(self, th, z):
         k = self.kind
+        if k == "Logistic":                                    # mappings.py:388-389
+            return th[0] + th[1] * (0.5 + 0.5 * np.tanh((z - th[2]) / (2 * th[3])))
+        if k in ("WarpingTanh", "WarpingBoxCox"):
+            return self._newton_forward(th, z)
         if k == "Identity":
             return z
         if k == "LinearMapping":
@@ -593,11 +646,41 @@ class _Mapping:
             w = th[0] + th[1] * np.arcsinh(y)
             return (np.vstack([np.cosh(w), np.cosh(w) * np.arcsinh(y)]),
                     np.array([np.sum(np.tanh(w)), np.sum(np.tanh(w) * np.arcsinh(y)) + n / th[1]]))
+        if k == "Logistic":                                    # interior points (0 < p < 1)
+            lower, high, loc, scale = th
+            p = (y - lower) / high
+            q = np.log(p / (1 - p))
+            dq = 1.0 / (p * (1 - p))
+            dl = -1.0 / p + 1.0 / (1 - p)                      # d(-log p - log(1-p))/dp
+            return (np.vstack([scale * dq * (-1.0 / high), scale * dq * (-p / high), one, q]),
+                    np.array([np.sum(dl * (-1.0 / high)), np.sum(-1.0 / high + dl * (-p / high)), 0.0, n / scale]))
+        if k == "WarpingTanh":
+            m = self.n
+            a, b, c = th[:m], th[m:2 * m], th[2 * m:]
+            u = b * (y[:, None] + c)
+            t, s2 = np.tanh(u), 1.0 / np.cosh(u) ** 2
+            Dy = 1.0 + np.dot(s2, a * b)
+            dinv = np.vstack([t.T, (a * s2 * (y[:, None] + c)).T, (a * b * s2).T])
+            dD = np.vstack([(b * s2).T, (a * s2 - 2.0 * a * b * s2 * t * (y[:, None] + c)).T,
+                            (-2.0 * a * b * b * s2 * t).T])
+            return dinv, np.sum(dD / Dy, axis=1)
+        if k == "WarpingBoxCox":
+            m = self.n
+            shift, power, w = th[:m], th[m:2 * m], th[2 * m:]
+            sh = y[:, None] + shift
+            ab = np.abs(sh)
+            sp = np.sign(sh) * ab ** power
+            Dy = np.dot(ab ** (power - 1.0), w)
+            dinv = np.vstack([(w * ab ** (power - 1.0)).T, (w * (sp * np.log(ab) * power - (sp - 1.0)) / power ** 2).T,
+                              ((sp - 1.0) / power).T])
+            dD = np.vstack([(w * (power - 1.0) * ab ** (power - 2.0) * np.sign(sh)).T,
+                            (w * ab ** (power - 1.0) * np.log(ab)).T, (ab ** (power - 1.0)).T])
+            return dinv, np.sum(dD / Dy, axis=1)
         raise ValueError(k)
 
     def grads_fd(self, th, y):
         """4th-order central differences of inv / logdet_dinv (used by tests to check `grads`)."""
-        P = len(self.hypers)
+        P = self.n_theta()
         dinv = np.zeros((P, y.shape[0]))
         dld = np.zeros(P)
         for i in range(P):

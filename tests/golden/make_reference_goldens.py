@@ -112,6 +112,8 @@ def ref_process(g3, spec, X):
     lkw = {'name': loc['name']} if 'name' in loc else {}
     location = _pot(getattr(g3, loc['type'])(_x_arg(X, loc.get('dims')), **lkw), loc)
     mkw = {'name': mp['name']} if 'name' in mp else {}
+    if 'n' in mp:
+        mkw['n'] = mp['n']
     mapping = _pot(getattr(g3, mp['type'])(**mkw), mp)
     kw = {'name': spec['name']} if 'name' in spec else {}
     return cls(X, location, ref_kernel(g3, spec['kernel'], X), mapping, noisy=spec.get('noisy', True), **kw)
@@ -187,6 +189,13 @@ CASES = {
                             N=24, D=1, M=7, seed=43),
     'map_linear':      dict(spec=dict(kind='gauss', location=K('Bias'), kernel=K('SE'), mapping=K('LinearMapping')),
                             N=24, D=1, M=7, seed=44),
+    'map_logistic':    dict(spec=dict(kind='gauss', warped=True, location=K('Bias'), kernel=K('SE'), mapping=K('Logistic')),
+                            N=24, D=1, M=7, seed=46, positive=True),
+    # Newton-inverse warpings (SURVEY f-4): forward map = damped Newton with tol 1e-3 (libs/tensors.py:134-145)
+    'map_warptanh':    dict(spec=dict(kind='gauss', warped=True, location=K('Bias'), kernel=K('SE'),
+                                      mapping=K('WarpingTanh', n=2)), N=24, D=1, M=7, seed=47),
+    'map_warpboxcox':  dict(spec=dict(kind='gauss', warped=True, location=K('Bias'), kernel=K('SE'),
+                                      mapping=K('WarpingBoxCox', n=2)), N=24, D=1, M=7, seed=48, positive=True),
     'wtp_boxcox':      dict(spec=dict(kind='student', warped=True, location=K('Bias'), kernel=K('MAT52'),
                                       mapping=K('BoxCoxShifted')), N=32, D=2, M=9, seed=45, positive=True),
     # TransportGaussianProcess (SURVEY f-3): chains [ID | TMapping | TLocation]* @ TKernel
@@ -237,6 +246,18 @@ def theta_for(layout, y, rng, case):
             v += np.mean(y) if 'mapping' not in case['spec'] else 0.0
         elif name.endswith('_Coeff'):
             v *= 0.3
+        elif name.endswith('Logistic_lower'):
+            v = np.full(size, np.min(y) - 0.4)
+        elif name.endswith('Logistic_high'):
+            v = np.full(size, np.log(np.max(y) - np.min(y) + 0.9))
+        elif name.endswith('Logistic_location'):
+            v = np.full(size, 0.1)
+        elif name.endswith('WarpingTanh_a'):
+            v += np.log(0.3)
+        elif name.endswith('WarpingTanh_c'):
+            v += -np.mean(y)
+        elif name.endswith('WarpingBoxCox_w'):
+            v += np.log(0.5)
         elif name.endswith('LogShifted_shift'):
             v = np.full(size, np.min(y) - 0.5)
         elif name.endswith('_shift'):

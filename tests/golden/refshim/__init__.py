@@ -205,7 +205,7 @@ def install():
         tril=lambda x, k=0: op(lambda t: torch.tril(t, k), x), triu=lambda x, k=0: op(lambda t: torch.triu(t, k), x),
         flatten=lambda x, ndim=1: op(lambda t: _T(t).reshape(-1), x),
         grad=lazy.grad,
-        jacobian=lambda *a, **k: (_ for _ in ()).throw(NotImplementedError('tt.jacobian: not in the shim')),
+        jacobian=lazy.jacobian,
     )
     tsl = _mod('theano.tensor.slinalg', solve=_solve, solve_lower_triangular=_solve_tri(True),
                solve_upper_triangular=_solve_tri(False), Solve=_Solve)
@@ -215,15 +215,12 @@ def install():
     ife = _mod('theano.ifelse', ifelse=lazy.ifelse)
     gof = _mod('theano.gof', Op=lazy.Op, Apply=lazy.Apply)
     printing = _mod('theano.printing', Print=_print_op, pydotprint=_Dummy(), debugprint=_Dummy())
-    scan_module = _mod('theano.scan_module', until=_Dummy())
+    scan_module = _mod('theano.scan_module', until=lazy.Until)
     sandbox_linalg = _mod('theano.sandbox.linalg', det=_Dummy())
     sandbox = _mod('theano.sandbox', linalg=sandbox_linalg)
 
-    def _scan(*a, **k):
-        raise NotImplementedError('theano.scan (Newton-inverse warpings) is outside the shim')
-
     th = _mod('theano', tensor=tt, ifelse=ife, gof=gof, printing=printing, scan_module=scan_module,
-              sandbox=sandbox, config=config, shared=lazy.shared, function=lazy.Function, scan=_scan,
+              sandbox=sandbox, config=config, shared=lazy.shared, function=lazy.Function, scan=lazy.scan,
               In=_Dummy, __version__='shim-1.0 (torch %s)' % torch.__version__, _g3b_shim=True)
     th.__path__ = []
     tt.__path__ = []

@@ -107,6 +107,16 @@ def evaluate(node, env):
         else:
             (g,) = torch.autograd.grad(f, w, retain_graph=True, allow_unused=True)
             t = torch.zeros_like(w) if g is None else g
+    elif node.kind == 'jacobian':
+        f = evaluate(node.args[0], env)
+        w = evaluate(node.args[1], env)
+        rows = []
+        for i in range(f.numel()):
+            (g,) = torch.autograd.grad(f.reshape(-1)[i], w, retain_graph=True, create_graph=True, allow_unused=True)
+            rows.append(torch.zeros_like(w) if g is None else g)
+        t = torch.stack(rows)
+    elif node.kind == 'scan':
+        t = _run_scan(node, env)
     elif node.kind == 'opout':
         xs = [evaluate(a, env) for a in node.apply.inputs]
         t = _run_op(node.apply, xs)
@@ -449,6 +459,48 @@ def grad(cost, wrt, disconnected_inputs='raise', **kw):
     if isinstance(wrt, (list, tuple)):
         return [grad(cost, w) for w in wrt]
     return TensorVariable('grad', args=(cost, wrt))
+
+
+def jacobian(expression, wrt, **kw):
+    return TensorVariable('jacobian', args=(expression, wrt))
+
+
+class Until:
+    """theano.scan_module.until(condition)."""
+
+    def __init__(self, condition):
+        self.condition = condition
+
+
+def scan(fn, sequences=None, outputs_info=None, non_sequences=None, n_steps=None, **kw):
+    """The one form the reference uses (libs/tensors.py:134-145): a single recurrent output, one non-sequence,
+    `fn` returning (next value, until(condition)).  Returns (all step values stacked, updates)."""
+    assert sequences is None and n_steps is not None
+    x_in = input_var('scan_x')
+    z_in = input_var('scan_z')
+    r, until = fn(x_in, z_in)
+    node = TensorVariable('scan', args=(outputs_info, non_sequences, r, until.condition))
+    node.scan_inputs = (x_in, z_in)
+    node.n_steps = int(n_steps)
+    return node, {}
+
+
+def _run_scan(node, env):
+    init, nonseq, r, cond = node.args
+    x_in, z_in = node.scan_inputs
+    x = evaluate(init, env).detach()
+    z = evaluate(nonseq, env).detach()
+    base = dict(env['v'])
+    vals = []
+    for _ in range(node.n_steps):
+        e2 = {'v': dict(base), 'givens': env.get('givens'), 'test': env.get('test')}
+        e2['v'][id(x_in)] = x.clone().requires_grad_(True)
+        e2['v'][id(z_in)] = z
+        x = evaluate(r, e2).detach()
+        vals.append(x)
+        if bool(evaluate(cond, e2)):
+            break
+    return torch.stack(vals)
 
 
 def ifelse(cond, a, b, name=None):

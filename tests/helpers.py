@@ -8,7 +8,8 @@ LEAVES = {"SE": g3.SE, "OU": g3.OU, "MAT32": g3.MAT32, "MAT52": g3.MAT52, "RQ": 
           "Noise": g3.KernelNoise, "KernelDot": g3.KernelDot, "LIN": g3.LIN, "POL": g3.POL, "BW": g3.BW, "VAR": g3.VAR}
 MAPS = {"Identity": g3.Identity, "LinearMapping": g3.LinearMapping, "LogShifted": g3.LogShifted,
         "BoxCoxShifted": g3.BoxCoxShifted, "BoxCoxLinear": g3.BoxCoxLinear, "ArcsinhLinear": g3.ArcsinhLinear,
-        "SinhArcsinh": g3.SinhArcsinh}
+        "SinhArcsinh": g3.SinhArcsinh, "Logistic": g3.Logistic, "WarpingTanh": g3.WarpingTanh,
+        "WarpingBoxCox": g3.WarpingBoxCox}
 MEANS = {"Zero": g3.Zero, "Bias": g3.Bias, "Linear": g3.Linear}
 
 
@@ -82,6 +83,8 @@ def build_process(spec, X, strict=True):
     location = _pot(MEANS[loc["type"]](_x_arg(X, loc.get("dims")), **lkw), loc)
     mp = spec.get("mapping", {"type": "Identity"})
     mkw = {"name": mp["name"]} if "name" in mp else {}
+    if "n" in mp:
+        mkw["n"] = mp["n"]
     mapping = _pot(MAPS[mp["type"]](**mkw), mp)
     kw = {}
     if "name" in spec:
