@@ -186,6 +186,11 @@ int g3_ctx_destroy(g3_ctx* ctx) {
     cudaStreamDestroy(ctx->gstream[g]);
     cudaEventDestroy(ctx->gev_done[g]);
   }
+  if (ctx->panel_stream) {
+    cudaStreamDestroy(ctx->panel_stream);
+    cudaEventDestroy(ctx->ev_panel);
+    cudaEventDestroy(ctx->ev_main);
+  }
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return 0;

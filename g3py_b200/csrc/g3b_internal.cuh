@@ -52,8 +52,13 @@ struct g3_ctx {
   std::vector<cudaEvent_t> prof_events;     // pairs
   std::vector<int> prof_class;
   size_t prof_used = 0;                     // pairs in use
-  int potrf_w = 1 << 20;               // tile columns per right-looking outer block, batched path (left-looking)
+  int potrf_w = 0;                     // tile columns per right-looking outer block in the gp path; 0 = choose from B and T
   int potrf_w_big = 8;                 // same, single big matrix (g3_gram_potrf_device)
+  // look-ahead of the right-looking factorisation: the next panel is updated and factored on a high-priority
+  // stream while the rest of the trailing update runs on the main stream
+  cudaStream_t panel_stream = nullptr;
+  cudaEvent_t ev_panel = nullptr, ev_main = nullptr;
+  int lookahead = 1;
 };
 
 enum { G3_PROF_GEMM = 0, G3_PROF_DIAG = 1, G3_PROF_GRAM = 2, G3_PROF_VJP = 3, G3_PROF_TRSV = 4, G3_PROF_OTHER = 5, G3_PROF_N = 6 };

@@ -305,6 +305,11 @@ int g3_set_potrf_block(g3_ctx* ctx, int w_outer) {
   return 0;
 }
 
+int g3_set_lookahead(g3_ctx* ctx, int on) {
+  ctx->lookahead = on ? 1 : 0;
+  return 0;
+}
+
 int g3_set_groups(g3_ctx* ctx, int n_groups) {
   ctx->n_groups = n_groups < 1 ? 1 : (n_groups > G3_MAX_GROUPS ? G3_MAX_GROUPS : n_groups);
   return 0;

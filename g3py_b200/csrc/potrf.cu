@@ -362,10 +362,16 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
     G3_CUDA(ctx, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem));
     ctx->diag_ready = true;
   }
-  if (w_outer < 1) w_outer = 1;
+  const int Blaunch = bmap ? nb : Btotal;
+  if (w_outer < 1) {
+    // auto: fully left-looking when the batch supplies the parallelism (a column update launches 2*B*(T-j) CTAs);
+    // few matrices with many tile columns (a single N=16384 evaluation: B=1, T=128) would leave most SMs idle in
+    // the column updates, so they go right-looking between outer blocks of `potrf_w_big` tile columns
+    w_outer = ((long long)Blaunch * T >= 256) ? (1 << 20) : ctx->potrf_w_big;
+  }
   // The tensor maps span the whole allocation (Btotal matrices); bmap (nb entries) picks the batch
   // coordinate of each launched CTA column, so the jitter ladder can refactor a subset in place.
-  const int B = bmap ? nb : Btotal;
+  const int B = Blaunch;
   CUtensorMap tmA, tmB, tmD;
   const uint64_t batch_extent = (uint64_t)Btotal;
   int rc;
@@ -374,8 +380,8 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
   if ((rc = g3_make_tmap(ctx, &tmD, Dinv, TS, (uint64_t)T * TS, batch_extent, TS, (uint64_t)T * TS * TS, G3_BN))) return rc;
   const long long strideA = (long long)Np * Np;
 
-  for (int jo = 0; jo < T; jo += w_outer) {
-    const int je = jo + w_outer < T ? jo + w_outer : T;
+  // factor the tile columns [jo, je) (left-looking inside the block; earlier blocks were applied right-looking)
+  auto factor_block = [&](int jo, int je) -> int {
     for (int j = jo; j < je; ++j) {
       if (j > jo) {  // left-looking update of tile column j with the columns of this outer block
         GemmArgs g = gemm_zero();
@@ -404,19 +410,64 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
         if ((rc = g3_gemm_launch(ctx, tmA, tmD, g, B))) return rc;
       }
     }
-    if (je < T) {  // right-looking update of the trailing matrix with the finished outer block
-      GemmArgs g = gemm_zero();
-      g.D = A; g.ldd = Np; g.strideD = strideA;
-      g.mode = 1; g.ntx = T - je;
-      g.d_r0 = je * TS; g.d_c0 = je * TS;
-      g.a_r0 = je * TS; g.a_rx = TS;
-      g.b_r0 = je * TS; g.b_ry = TS;
-      g.ka0 = jo * TS; g.kb0 = jo * TS; g.kl0 = (je - jo) * TS;
-      g.alpha = -1.0; g.beta = 1.0; g.bmap = bmap; g.upper = 1;
-      if ((rc = g3_gemm_launch(ctx, tmA, tmB, g, B))) return rc;
+    return 0;
+  };
+  // right-looking update with the finished block [jo, je): tile columns [c0, c1) of the trailing matrix, rows >= c0
+  auto trailing = [&](int jo, int je, int c0, int c1) -> int {
+    GemmArgs g = gemm_zero();
+    g.D = A; g.ldd = Np; g.strideD = strideA;
+    g.a_rx = TS; g.b_ry = TS;
+    g.ka0 = jo * TS; g.kb0 = jo * TS; g.kl0 = (je - jo) * TS;
+    g.alpha = -1.0; g.beta = 1.0; g.bmap = bmap;
+    g.d_r0 = c0 * TS; g.d_c0 = c0 * TS; g.a_r0 = c0 * TS; g.b_r0 = c0 * TS;
+    if (c1 >= T) {          // everything to the right: lower triangle of tiles
+      g.mode = 1; g.ntx = T - c0; g.upper = 1;
+    } else {                // a block of columns: tiles above the block diagonal are void
+      g.mode = 0; g.ntx = T - c0; g.nty = c1 - c0; g.upper = 1 | 4;
+    }
+    return g3_gemm_launch(ctx, tmA, tmB, g, B);
+  };
+
+  const bool look = ctx->lookahead && w_outer < T && T - w_outer > w_outer;
+  if (!look) {
+    for (int jo = 0; jo < T; jo += w_outer) {
+      const int je = jo + w_outer < T ? jo + w_outer : T;
+      if ((rc = factor_block(jo, je))) return rc;
+      if (je < T && (rc = trailing(jo, je, je, T))) return rc;
+    }
+    return 0;
+  }
+  // ---- look-ahead: panel stream P factors block k+1 while the main stream finishes the trailing update of block k
+  if (!ctx->panel_stream) {
+    int lo = 0, hi = 0;
+    G3_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    G3_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->panel_stream, cudaStreamNonBlocking, hi));
+    G3_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_panel, cudaEventDisableTiming));
+    G3_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
+  }
+  cudaStream_t main_stream = ctx->stream, P = ctx->panel_stream;
+  G3_CUDA(ctx, cudaEventRecord(ctx->ev_main, main_stream));      // the Gram matrix is ready
+  G3_CUDA(ctx, cudaStreamWaitEvent(P, ctx->ev_main, 0));
+  rc = 0;
+  for (int jo = 0; jo < T && !rc; jo += w_outer) {
+    const int je = jo + w_outer < T ? jo + w_outer : T;
+    const int je2 = je + w_outer < T ? je + w_outer : T;
+    ctx->stream = P;
+    rc = factor_block(jo, je);
+    if (!rc) cudaEventRecord(ctx->ev_panel, P);
+    if (!rc && je < T) {
+      if (jo > 0) cudaStreamWaitEvent(P, ctx->ev_main, 0);         // the previous block's main-stream update wrote these columns
+      rc = trailing(jo, je, je, je2);                              // next panel's columns first, on P
+      ctx->stream = main_stream;
+      cudaStreamWaitEvent(main_stream, ctx->ev_panel, 0);
+      if (!rc && je2 < T) rc = trailing(jo, je, je2, T);           // the rest, on the main stream
+      cudaEventRecord(ctx->ev_main, main_stream);
     }
   }
-  return 0;
+  ctx->stream = main_stream;
+  cudaEventRecord(ctx->ev_panel, P);
+  cudaStreamWaitEvent(main_stream, ctx->ev_panel, 0);
+  return rc;
 }
 
 int g3_potrf_panel(g3_ctx* ctx, double* P, int rows, int nb, double* Dinv, double* logdet, int* info) {
@@ -505,29 +556,62 @@ int g3_trtri_batched(g3_ctx* ctx, const double* L, double* U, int Np, int B, con
   if ((rc = g3_make_tmap(ctx, &tmL, L, Np, Np, B, Np, (uint64_t)Np * Np, G3_BN))) return rc;
   if ((rc = g3_make_tmap(ctx, &tmD, Dinv, TS, (uint64_t)T * TS, B, TS, (uint64_t)T * TS * TS, G3_BN))) return rc;
   const long long strideU = (long long)Np * Np;
-  for (int i = 1; i < T; ++i) {
-    {  // S[j][i] = sum_{k in [j, i)} U[j][k] L[i][k]^T  -> stored in U tile (j, i)
+  // Row i of L^-1 (tile column i of U) needs S[j][i] = sum_{k=j}^{i-1} U[j][k] L[i][k]^T for every j < i.  With a batch
+  // the rows are done one at a time (2*B*i CTAs per launch).  Few large matrices go by outer blocks of w rows: the
+  // part of the sum over finished rows k < io is ONE launch for the whole block (w times the CTAs), the part inside
+  // the block stays row by row -- the same split as the right-looking potrf above.
+  int w = ctx->potrf_w > 0 ? ctx->potrf_w : (((long long)B * T >= 256) ? T : ctx->potrf_w_big);
+  if (w < 1) w = 1;
+  for (int io = 0; io < T; io += w) {
+    const int ie = io + w < T ? io + w : T;
+    if (io > 0) {  // S[j][i] = sum_{k=j}^{io-1} U[j][k] L[i][k]^T,  j < io <= i < ie
       GemmArgs g = gemm_zero();
       g.D = U; g.ldd = Np; g.strideD = strideU;
-      g.mode = 0; g.ntx = i; g.nty = 1;
-      g.d_r0 = 0; g.d_c0 = i * TS;
+      g.mode = 0; g.ntx = io; g.nty = ie - io;
+      g.d_r0 = 0; g.d_c0 = io * TS;
       g.a_r0 = 0; g.a_rx = TS;
-      g.b_r0 = i * TS;
+      g.b_r0 = io * TS; g.b_ry = TS;
       g.ka0 = 0; g.ka_x = TS; g.kb0 = 0; g.kb_x = TS;
-      g.kl0 = i * TS; g.kl_x = -TS;
+      g.kl0 = io * TS; g.kl_x = -TS;
       g.alpha = 1.0; g.beta = 0.0;
       if ((rc = g3_gemm_launch(ctx, tmU, tmL, g, B))) return rc;
     }
-    {  // U[j][i] = -S Linv_ii^T
-      GemmArgs g = gemm_zero();
-      g.D = U; g.ldd = Np; g.strideD = strideU;
-      g.mode = 0; g.ntx = i; g.nty = 1;
-      g.d_r0 = 0; g.d_c0 = i * TS;
-      g.a_r0 = 0; g.a_rx = TS; g.ka0 = i * TS;
-      g.b_r0 = i * TS; g.kb0 = 0;
-      g.kl0 = TS;
-      g.alpha = -1.0; g.beta = 0.0; g.tri_b = 1;
-      if ((rc = g3_gemm_launch(ctx, tmU, tmD, g, B))) return rc;
+    for (int i = io > 0 ? io : 1; i < ie; ++i) {
+      if (i > io && io > 0) {  // rows above the block: S[j][i] += sum_{k=io}^{i-1} U[j][k] L[i][k]^T,  j < io
+        GemmArgs g = gemm_zero();
+        g.D = U; g.ldd = Np; g.strideD = strideU;
+        g.mode = 0; g.ntx = io; g.nty = 1;
+        g.d_r0 = 0; g.d_c0 = i * TS;
+        g.a_r0 = 0; g.a_rx = TS;
+        g.b_r0 = i * TS;
+        g.ka0 = io * TS; g.kb0 = io * TS;
+        g.kl0 = (i - io) * TS;
+        g.alpha = 1.0; g.beta = 1.0;
+        if ((rc = g3_gemm_launch(ctx, tmU, tmL, g, B))) return rc;
+      }
+      if (i > io) {  // rows inside the block: S[j][i] = sum_{k=j}^{i-1} U[j][k] L[i][k]^T,  io <= j < i
+        GemmArgs g = gemm_zero();
+        g.D = U; g.ldd = Np; g.strideD = strideU;
+        g.mode = 0; g.ntx = i - io; g.nty = 1;
+        g.d_r0 = io * TS; g.d_c0 = i * TS;
+        g.a_r0 = io * TS; g.a_rx = TS;
+        g.b_r0 = i * TS;
+        g.ka0 = io * TS; g.ka_x = TS; g.kb0 = io * TS; g.kb_x = TS;
+        g.kl0 = (i - io) * TS; g.kl_x = -TS;
+        g.alpha = 1.0; g.beta = 0.0;
+        if ((rc = g3_gemm_launch(ctx, tmU, tmL, g, B))) return rc;
+      }
+      {  // U[j][i] = -S[j][i] Linv_ii^T,  j < i
+        GemmArgs g = gemm_zero();
+        g.D = U; g.ldd = Np; g.strideD = strideU;
+        g.mode = 0; g.ntx = i; g.nty = 1;
+        g.d_r0 = 0; g.d_c0 = i * TS;
+        g.a_r0 = 0; g.a_rx = TS; g.ka0 = i * TS;
+        g.b_r0 = i * TS; g.kb0 = 0;
+        g.kl0 = TS;
+        g.alpha = -1.0; g.beta = 0.0; g.tri_b = 1;
+        if ((rc = g3_gemm_launch(ctx, tmU, tmD, g, B))) return rc;
+      }
     }
   }
   return 0;

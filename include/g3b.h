@@ -105,8 +105,12 @@ int g3_sync(g3_ctx* ctx);
  * and exact modes agree bit-for-bit with the oracle: jitter = float32(1e-6) (tensors.py:98,204). */
 int g3_set_jitter(g3_ctx* ctx, double jitter_rel, int max_tries);
 /* Blocking of the factorisation: tile columns (of 128) per right-looking outer block; a value
- * >= N/128 makes it fully left-looking (default for the batched path). */
+ * >= N/128 makes it fully left-looking.  0 (default) chooses from the batch size and N: left-looking
+ * when the batch supplies the parallelism, outer blocks of 8 tile columns for few large matrices. */
 int g3_set_potrf_block(g3_ctx* ctx, int w_outer);
+/* Look-ahead of the blocked (right-looking) factorisation: the next panel is updated and factored on a second,
+ * high-priority stream while the rest of the trailing update runs (default on; results do not depend on it). */
+int g3_set_lookahead(g3_ctx* ctx, int on);
 /* Number of batch groups g3_gp_run processes concurrently on separate streams (default 4, max 8;
  * 1 = a single stream, which is what the per-kernel timers of g3_prof_* need). */
 int g3_set_groups(g3_ctx* ctx, int n_groups);

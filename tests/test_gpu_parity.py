@@ -569,3 +569,28 @@ def test_cabi_error_convention(ctx):
     c2.close()
     with pytest.raises(g3.G3Error):
         g3.Context(99)                                          # no such device
+
+
+@pytest.mark.gpu
+def test_blocked_schedules_agree(ctx):
+    """Few large matrices factor (and invert) by outer blocks of tile columns, batches column by column
+    (g3_set_potrf_block; 0 = chosen from B and N).  Both schedules must give the same logp / gradient, and the
+    automatic choice must match them, for a single matrix and for a small batch."""
+    X, y, Th = orc.c2_inputs(1500, 3)                       # T = 12 tile columns
+    gp = build_process(SPECS["C2"], X)
+    gp.observed(X, y)
+    op = orc.OracleProcess(SPECS["C2"], 3)
+    want_lp = np.array([op.logp(t, X, y) for t in Th])
+    want_g = np.array([op.dlogp(t, X, y) for t in Th])
+    try:
+        for w, look in ((1 << 20, 1), (4, 1), (4, 0), (5, 1), (1, 1), (2, 1), (0, 1)):
+            gp.ctx.set_potrf_block(w)
+            gp.ctx.set_lookahead(look)
+            for sel in (slice(0, 1), slice(0, 3)):
+                lp, g, info = gp.logp_dlogp_batch(Th[sel])
+                assert np.all(info["status"] == 0)
+                assert np.max(np.abs(lp - want_lp[sel]) / np.abs(want_lp[sel])) < TOL, w
+                assert scaled_err(g, want_g[sel]) < TOL, w
+    finally:
+        gp.ctx.set_potrf_block(0)
+        gp.ctx.set_lookahead(1)
