@@ -141,6 +141,11 @@ CASES = {
                                       kernel=K('prod', k1=K('SIN'), k2=K('SE')), mapping=K('BoxCoxShifted')),
                             N=48, D=1, M=15, seed=12, positive=True),
     'C4_tp_se':        dict(spec=dict(kind='student', location=K('Bias'), kernel=K('SE')), N=56, D=5, M=11, seed=13),
+    # multi-tile sizes (3 tiles of 128 with padding) straight from the reference
+    'C2_mid_3tiles':   dict(spec=dict(kind='gauss', location=K('Bias'), kernel=K('sum', k1=K('SE'), k2=K('MAT52'))),
+                            N=300, D=3, M=9, seed=14, slim=True),
+    'C4_mid_3tiles':   dict(spec=dict(kind='student', location=K('Bias'), kernel=K('SE')), N=270, D=5, M=9, seed=15,
+                            slim=True),
     # leaf zoo (SURVEY a2 + f4)
     'leaf_ou':         dict(spec=dict(kind='gauss', location=K('Zero'), kernel=K('OU')), N=24, D=2, M=7, seed=20),
     'leaf_mat32':      dict(spec=dict(kind='gauss', location=K('Zero'), kernel=K('MAT32')), N=24, D=2, M=7, seed=21),
