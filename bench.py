@@ -24,6 +24,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line (rank 0).  Libraries write banners to the C-level stdout (NCCL prints
+# "NCCL version ..." at communicator creation), so file descriptor 1 is pointed at stderr for the whole run and the
+# result line goes to the saved, real stdout.
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 N_OBS, D_IN, B_THETA = 4096, 3, 64
 METRIC = "fp64 GP logp+grad evals/s at N=4096 x64 theta batch"
 UNIT = "evals/s"
@@ -143,7 +154,7 @@ def run_reference(args, rank, world):
                                        "(NxNxD broadcast gram, dpotrf, Murray reverse-mode gradient), NumPy/SciPy "
                                        "OpenBLAS on all host cores; Theano itself is not installable here" % per_step},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -315,7 +326,7 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                 "sample": "1 of the 64 theta rows (%.1f s); oracle port of the reference schedule (NxNxD "
                                           "broadcast gram, dpotrf, Murray reverse-mode gradient) on all host cores" % dt}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
