@@ -66,6 +66,7 @@ SIGNATURES = {
     "g3_gram": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _ip]),
     "g3_gram_vjp": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp]),
     "g3_potrf_robust": (C.c_int, [_ctxp, _dp, C.c_int, C.c_int, C.c_int, _ip, _dp]),
+    "g3_potrf_robust_solve": (C.c_int, [_ctxp, _dp, C.c_int, C.c_int, _dp, _dp, _ip, _dp]),
     "g3_gp_logp_grad": (C.c_int, [_ctxp, C.POINTER(KernelDesc), C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, _dp, _dp,
                                   _dp, _dp, _ip]),
     "g3_gp_upload": (C.c_int, [_ctxp, C.POINTER(KernelDesc), C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int]),
@@ -279,6 +280,20 @@ class Context:
         if single:
             return A[0], int(info[0]), float(jit[0])
         return A, info, jit
+
+    def potrf_robust_solve(self, A, rhs):
+        """One matrix: (L, info, jitter, u = L^-1 rhs), factorisation and substitution both on the device."""
+        A = np.array(A, dtype=np.float64, order="C", copy=True)
+        n = A.shape[0]
+        rhs = _f64(rhs).ravel()
+        if rhs.shape[0] != n:
+            raise ValueError("rhs must have n entries")
+        u = np.empty(n)
+        info = np.zeros(1, dtype=np.int32)
+        jit = np.zeros(1)
+        self._ck(self._lib.g3_potrf_robust_solve(self._h, _d(A), n, n, _d(rhs), _d(u), _i(info), _d(jit)),
+                 "g3_potrf_robust_solve")
+        return A, int(info[0]), float(jit[0]), u
 
     # ---- fused logp + grad
     def gp_logp_grad(self, desc, kind, delta, theta, nu=None, want_grad=True):

@@ -796,6 +796,28 @@ int g3_potrf_robust(g3_ctx* ctx, double* A, int n, int lda, int B, int* info_out
   return 0;
 }
 
+// robust Cholesky of ONE host matrix followed by the forward substitution u = L^-1 rhs on the device (L and the
+// inverses of its diagonal blocks are still resident in the pr_* workspaces)
+int g3_potrf_robust_solve(g3_ctx* ctx, double* A, int n, int lda, const double* rhs, double* u_out, int* info_out,
+                          double* jitter_out) {
+  if (!rhs || !u_out) return g3_fail_msg(ctx, "g3_potrf_robust_solve: bad arguments");
+  int rc = g3_potrf_robust(ctx, A, n, lda, 1, info_out, jitter_out);
+  if (rc) return rc;
+  if (info_out[0] < 0) return 0;                  // exhausted ladder: the caller applies L = 1e-10*I itself
+  const int Np = g3_pad(n);
+  double* dA = (double*)g3_ws(ctx, "pr_A", sizeof(double) * (size_t)Np * Np);
+  double* dDinv = (double*)g3_ws(ctx, "pr_Dinv", sizeof(double) * (size_t)(Np / TS) * TS * TS);
+  double* dr = (double*)g3_ws(ctx, "pr_r", sizeof(double) * (2 * (size_t)Np + 1));
+  if (!dA || !dDinv || !dr) return -2;
+  double* du = dr + Np;
+  G3_CUDA(ctx, cudaMemsetAsync(dr, 0, sizeof(double) * (2 * (size_t)Np + 1), ctx->stream));
+  G3_CUDA(ctx, cudaMemcpyAsync(dr, rhs, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = g3_trsv_fwd(ctx, dA, dDinv, dr, du, du + Np, Np, 1))) return rc;
+  G3_CUDA(ctx, cudaMemcpyAsync(u_out, du, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 // ---- posterior moments for one theta -----------------------------------------------------------
 int g3_gp_posterior(g3_ctx* ctx, const g3_kernel_desc* desc, const double* Xs, int M, const double* delta,
                     const double* theta, int flags, double* mean_out, double* var_out, double* cov_out,

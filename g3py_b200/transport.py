@@ -13,7 +13,6 @@ posterior needs the Cholesky factor of the (N+M) x (N+M) joint covariance (`tran
 the device by `g3_potrf_robust`.
 """
 import numpy as np
-import scipy.linalg as sla
 
 from . import _cabi as cabi
 from .hypers.mappings import Identity, MappingComposed
@@ -94,12 +93,17 @@ class TransportGaussianProcess(EllipticalProcess):
         L, info, _ = self.ctx.potrf_robust(K)                 # CholeskyRobust incl. ladder and 1e-10*I fallback
         return self.consts.fallback * np.eye(len(K)) if info < 0 else np.tril(L)
 
+    def _chol_solve(self, K, rhs):
+        """tsl.solve_lower_triangular(cholesky_robust(K), rhs) (transports.py:227-232), both steps on the device."""
+        L, info, _, u = self.ctx.potrf_robust_solve(K, rhs)
+        return rhs / self.consts.fallback if info < 0 else u
+
     def _tk_posterior(self, space, pred, nat, p, noise_pred):
         """TKernel.posterior (transports.py:236-257) with noise_obs=True."""
         X, y = self.inputs, self.outputs
         with np.errstate(all="ignore"):
             pre = self.f_mapping.inv(y, p) - self.f_location(X, p)
-        u = sla.solve_triangular(self._chol(self._gram(X, None, nat, True)), pre, lower=True)
+        u = self._chol_solve(self._gram(X, None, nat, True), pre)
         Kxs = self._gram(X, space, nat, False)                # kernel.cov(inputs, space): no noise on the cross block
         joint = np.block([[self._gram(X, None, nat, True), Kxs], [Kxs.T, self._gram(space, None, nat, noise_pred)]])
         L = self._chol(joint)
@@ -129,7 +133,7 @@ class TransportGaussianProcess(EllipticalProcess):
         if which == "inv":                                    # transports.py:227-232 after the element-wise inverses
             with np.errstate(all="ignore"):
                 pre = self.f_mapping.inv(v, p) - self.f_location(space, p)
-            return sla.solve_triangular(self._chol(self._gram(space, None, nat, noise)), pre, lower=True)
+            return self._chol_solve(self._gram(space, None, nat, noise), pre)
         K = self._gram(space, None, nat, noise)
         if which == "diag" and not elementwise:               # TKernel.diag (transports.py:218-225)
             return np.sqrt(np.diag(K)) * v

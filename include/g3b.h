@@ -161,6 +161,10 @@ int g3_gram_vjp(g3_ctx* ctx, const g3_kernel_desc* desc, const double* X1, int n
  * ladder try k, -1 exhausted (A[b] left untouched; caller applies 1e-10*I).
  * jitter[b] (may be NULL) = the dK finally added. */
 int g3_potrf_robust(g3_ctx* ctx, double* A, int n, int lda, int B, int* info, double* jitter);
+/* Same for ONE matrix, followed by the forward substitution u = L^-1 rhs on the device (rhs, u_out: n doubles).
+ * Replaces `tsl.solve_lower_triangular(cholesky_robust(K), v)` (g3py/processes/hypers/transports.py:227-232). */
+int g3_potrf_robust_solve(g3_ctx* ctx, double* A, int n, int lda, const double* rhs, double* u_out, int* info,
+                          double* jitter);
 
 /* ---- fused marginal likelihood + gradient ---------------------------------------------
  * WarpedGaussianDistribution.logp_cho / WarpedStudentTDistribution.logp_cho core

@@ -137,6 +137,10 @@ class FakeContext:
         L, info = orc.cholesky_robust(np.asarray(A, dtype=np.float64), return_info=True)
         return L, (-1 if info < 0 else 0), 0.0
 
+    def potrf_robust_solve(self, A, rhs):
+        L, info, jit = self.potrf_robust(A)
+        return L, info, jit, sla.solve_triangular(L, np.asarray(rhs, dtype=np.float64), lower=True)
+
     def _factor(self, desc, t):
         K, dK = _eval_desc(desc, t, self.X, self.X, True, grad=True)
         m = np.min(np.diag(K))
