@@ -59,6 +59,7 @@ struct g3_ctx {
   cudaStream_t panel_stream = nullptr;
   cudaEvent_t ev_panel = nullptr, ev_main = nullptr;
   int lookahead = 1;
+  int splitk = 1;                      // allow split-K for few-tile / deep-K GEMM launches (g3_set_splitk)
 };
 
 enum { G3_PROF_GEMM = 0, G3_PROF_DIAG = 1, G3_PROF_GRAM = 2, G3_PROF_VJP = 3, G3_PROF_TRSV = 4, G3_PROF_OTHER = 5, G3_PROF_N = 6 };
@@ -107,6 +108,9 @@ struct GemmArgs {
   const int* bmap;        // optional: launch batch index -> matrix index
   int tri_b;              // B operand is a lower-triangular 128x128 block (B[n][k] = 0 for k > n, K = 128):
                           // a warp skips the k-tiles beyond its 32 output columns
+  int splitk;             // > 1: the contraction is split over gridDim.z CTAs per tile; partial tiles go to sk_ws and
+  double* sk_ws;          //      the CTA that arrives last sums them in split order (deterministic) and writes D.
+  unsigned* sk_cnt;       //      Set by g3_gemm_launch for launches with few tiles and a deep contraction.
   int upper;              // bit0: tiles x == y are diagonal tiles of a symmetric result, bit1: tile x == 0 is,
                           // (only their lower triangle is needed: the upper-right 64x64 quarter is not computed)
                           // bit2: tiles with x < y are void (skipped entirely)

@@ -12,6 +12,8 @@
 // the reference does these through LAPACK dpotrf and Theano's Murray reverse mode
 // (g3py/libs/tensors.py:198,224-260).
 #include "g3b_internal.cuh"
+#include <stdio.h>
+#include <string>
 
 namespace {
 
@@ -95,9 +97,18 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int bidx = g.bmap ? g.bmap[blockIdx.y] : (int)blockIdx.y;
   const int a_row = g.a_r0 + x * g.a_rx + y * g.a_ry + h * G3_BM;
   const int b_row = g.b_r0 + x * g.b_rx + y * g.b_ry;
-  const int ka = g.ka0 + x * g.ka_x + y * g.ka_y;
-  const int kb = g.kb0 + x * g.kb_x + y * g.kb_y;
-  const int nk = (g.kl0 + x * g.kl_x + y * g.kl_y) / G3_BK;
+  int ka = g.ka0 + x * g.ka_x + y * g.ka_y;
+  int kb = g.kb0 + x * g.kb_x + y * g.kb_y;
+  int nk = (g.kl0 + x * g.kl_x + y * g.kl_y) / G3_BK;
+  const int sk = g.splitk > 1 ? (int)blockIdx.z : 0;
+  if (g.splitk > 1) {  // this CTA's share of the contraction: k-tiles [sk*chunk, (sk+1)*chunk)
+    const int chunk = (nk + g.splitk - 1) / g.splitk;
+    const int lo = sk * chunk;
+    nk = nk - lo < chunk ? nk - lo : chunk;
+    if (nk < 0) nk = 0;
+    ka += lo * G3_BK;
+    kb += lo * G3_BK;
+  }
   double* Dt = g.D + (long long)bidx * g.strideD + (long long)(g.d_r0 + x * G3_TILE + h * G3_BM) * g.ldd +
                (g.d_c0 + y * G3_TILE);
 
@@ -134,7 +145,7 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   // beta != 0: the D tile enters through the accumulators (acc = (beta/alpha) * D, loaded while the TMA pipeline
   // fills), so the epilogue is a pure store and no global-load latency sits between the last DMMA and the write.
   double acc[4][4][2];
-  if (g.beta != 0.0 && !idle) {
+  if (g.beta != 0.0 && !idle && sk == 0) {
     const double sc = g.beta / g.alpha;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -198,6 +209,47 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 
   // ---- epilogue ------------------------------------------------------------------------
+  if (g.splitk > 1) {
+    // split-K: park the partial tile, count arrivals; the last CTA of the tile adds the partials in split order
+    __shared__ int is_last;
+    const long long tile_lin = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+    double* part = g.sk_ws + (tile_lin * g.splitk + sk) * (long long)(G3_BM * G3_BN);
+    if (!idle) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<double2*>(part + (wm * 32 + i * 8 + grp) * G3_BN + wn * 32 + j * 8 + 2 * t4) =
+              make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned prev = atomicAdd(g.sk_cnt + tile_lin, 1u);
+      is_last = prev == (unsigned)(g.splitk - 1);
+      if (is_last) g.sk_cnt[tile_lin] = 0;                    // ready for the next launch on this stream
+    }
+    __syncthreads();
+    if (!is_last || idle) return;
+    __threadfence();
+    const double* base = g.sk_ws + tile_lin * g.splitk * (long long)(G3_BM * G3_BN);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double* rowp = Dt + (long long)(wm * 32 + i * 8 + grp) * g.ldd + wn * 32 + 2 * t4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long off = (wm * 32 + i * 8 + grp) * G3_BN + wn * 32 + j * 8 + 2 * t4;
+        double2 sum = make_double2(0.0, 0.0);
+        for (int q = 0; q < g.splitk; ++q) {
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(base + (long long)q * (G3_BM * G3_BN) + off));
+          sum.x += v.x;
+          sum.y += v.y;
+        }
+        *reinterpret_cast<double2*>(rowp + j * 8) = make_double2(g.alpha * sum.x, g.alpha * sum.y);
+      }
+    }
+    return;
+  }
   if (idle) return;
   const double alpha = g.alpha;
 #pragma unroll
@@ -219,9 +271,43 @@ int g3_gemm_launch(g3_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   }
   long long ntiles = a.mode == 0 ? (long long)a.ntx * a.nty : (long long)a.ntx * (a.ntx + 1) / 2;
   if (ntiles <= 0 || B <= 0) return 0;
-  dim3 grid((unsigned)(ntiles * 2), (unsigned)B, 1);
+  GemmArgs g = a;
+  g.splitk = 1;
+  g.sk_ws = nullptr;
+  g.sk_cnt = nullptr;
+  // Few tiles with a deep contraction (column updates of a single matrix, rows of trtri) leave most SMs idle and
+  // each CTA runs at one SM's fp64 rate: split the contraction over up to 8 CTAs per tile.
+  const long long ctas = ntiles * 2 * B;
+  if (ctx->splitk && !a.tri_b && ctas * 2 <= 2 * ctx->sm_count) {
+    int kmax = a.kl0;
+    if (a.mode == 0) {
+      const int kx = a.kl0 + a.kl_x * (a.ntx - 1), ky = a.kl0 + a.kl_y * (a.nty - 1);
+      kmax = kmax > kx ? kmax : kx;
+      kmax = kmax > ky ? kmax : ky;
+    }
+    int sk = (int)(2 * ctx->sm_count / ctas);
+    if (sk > kmax / 128) sk = kmax / 128;                      // at least 8 k-tiles (one 128-block) per share
+    if (sk > 8) sk = 8;
+    if (sk >= 2) {
+      // per-stream scratch: launches on one stream are ordered, different streams (batch groups, look-ahead) are not
+      char name[64];
+      snprintf(name, sizeof name, "gemm_sk_%p", (void*)ctx->stream);
+      const size_t ws_bytes = sizeof(double) * (size_t)ctas * sk * G3_BM * G3_BN;
+      std::string key(name);
+      const void* before = ctx->bufs.count(key + "_c") ? ctx->bufs[key + "_c"].p : nullptr;
+      double* ws = (double*)g3_ws(ctx, name, ws_bytes);
+      unsigned* cnt = (unsigned*)g3_ws(ctx, (key + "_c").c_str(), sizeof(unsigned) * 4096);
+      if (ws && cnt && ctas <= 4096) {
+        if (cnt != before) G3_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(unsigned) * 4096, ctx->stream));
+        g.splitk = sk;
+        g.sk_ws = ws;
+        g.sk_cnt = cnt;
+      }
+    }
+  }
+  dim3 grid((unsigned)(ntiles * 2), (unsigned)B, (unsigned)g.splitk);
   g3_prof_begin(ctx, G3_PROF_GEMM);
-  dgemm_nt_kernel<<<grid, 256, kSmemBytes, ctx->stream>>>(tmA, tmB, a);
+  dgemm_nt_kernel<<<grid, 256, kSmemBytes, ctx->stream>>>(tmA, tmB, g);
   g3_prof_end(ctx);
   G3_LAUNCH_CHECK(ctx);
   return 0;

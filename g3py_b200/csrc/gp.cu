@@ -310,6 +310,11 @@ int g3_set_lookahead(g3_ctx* ctx, int on) {
   return 0;
 }
 
+int g3_set_splitk(g3_ctx* ctx, int on) {
+  ctx->splitk = on ? 1 : 0;
+  return 0;
+}
+
 int g3_set_groups(g3_ctx* ctx, int n_groups) {
   ctx->n_groups = n_groups < 1 ? 1 : (n_groups > G3_MAX_GROUPS ? G3_MAX_GROUPS : n_groups);
   return 0;

@@ -282,11 +282,16 @@ trsv_fwd_step_kernel(const double* __restrict__ L, const double* __restrict__ Di
   double* rb = r + (long long)b * Np;
   if (tid < TS) rj[tid] = rb[j * TS + tid];
   __syncthreads();
-  for (int a = warp; a < TS; a += 8) {           // warp per row, coalesced 1 KiB rows
-    const double4 v = *reinterpret_cast<const double4*>(Dj + a * TS + lane * 4);
-    double acc = v.x * rj[lane * 4] + v.y * rj[lane * 4 + 1] + v.z * rj[lane * 4 + 2] + v.w * rj[lane * 4 + 3];
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) uj[a] = acc;
+  {  // warp per row, coalesced 1 KiB rows; all 16 rows of a warp are in flight before the first reduction
+    double4 v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = *reinterpret_cast<const double4*>(Dj + (warp + 8 * q) * TS + lane * 4);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      double acc = v[q].x * rj[lane * 4] + v[q].y * rj[lane * 4 + 1] + v[q].z * rj[lane * 4 + 2] + v[q].w * rj[lane * 4 + 3];
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) uj[warp + 8 * q] = acc;
+    }
   }
   __syncthreads();
   if (x == 0) {
@@ -301,11 +306,14 @@ trsv_fwd_step_kernel(const double* __restrict__ L, const double* __restrict__ Di
   }
   const int i = j + x;
   const double* Lt = L + (long long)b * Np * Np + (long long)i * TS * Np + (long long)j * TS;
-  for (int a = warp; a < TS; a += 8) {
-    const double4 v = *reinterpret_cast<const double4*>(Lt + (long long)a * Np + lane * 4);
-    double acc = v.x * uj[lane * 4] + v.y * uj[lane * 4 + 1] + v.z * uj[lane * 4 + 2] + v.w * uj[lane * 4 + 3];
+  double4 v[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) v[q] = *reinterpret_cast<const double4*>(Lt + (long long)(warp + 8 * q) * Np + lane * 4);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    double acc = v[q].x * uj[lane * 4] + v[q].y * uj[lane * 4 + 1] + v[q].z * uj[lane * 4 + 2] + v[q].w * uj[lane * 4 + 3];
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) rb[i * TS + a] -= acc;
+    if (lane == 0) rb[i * TS + warp + 8 * q] -= acc;
   }
 }
 
@@ -324,7 +332,13 @@ trsv_bwd_step_kernel(const double* __restrict__ L, const double* __restrict__ Di
   const int c = tid & 127, half = tid >> 7;       // thread per column, two row halves
   {
     double acc = 0.0;
-    for (int a = half * 64; a < half * 64 + 64; ++a) acc += Dj[a * TS + c] * sj[a];
+    for (int a0 = half * 64; a0 < half * 64 + 64; a0 += 16) {   // 16 loads in flight, same summation order
+      double t[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) t[q] = Dj[(a0 + q) * TS + c];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc += t[q] * sj[a0 + q];
+    }
     part[half][c] = acc;
   }
   __syncthreads();
@@ -338,7 +352,13 @@ trsv_bwd_step_kernel(const double* __restrict__ L, const double* __restrict__ Di
   const double* Lt = L + (long long)b * Np * Np + (long long)j * TS * Np + (long long)i * TS;
   {
     double acc = 0.0;
-    for (int a = half * 64; a < half * 64 + 64; ++a) acc += Lt[(long long)a * Np + c] * aj[a];
+    for (int a0 = half * 64; a0 < half * 64 + 64; a0 += 16) {
+      double t[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) t[q] = Lt[(long long)(a0 + q) * Np + c];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc += t[q] * aj[a0 + q];
+    }
     part[half][c] = acc;
   }
   __syncthreads();

@@ -111,6 +111,9 @@ int g3_set_potrf_block(g3_ctx* ctx, int w_outer);
 /* Look-ahead of the blocked (right-looking) factorisation: the next panel is updated and factored on a second,
  * high-priority stream while the rest of the trailing update runs (default on; results do not depend on it). */
 int g3_set_lookahead(g3_ctx* ctx, int on);
+/* Split-K for GEMM launches with few tiles and a deep contraction (single-matrix evaluations): up to 8 CTAs share
+ * one output tile, partial tiles are added in a fixed order (bitwise reproducible).  Default on. */
+int g3_set_splitk(g3_ctx* ctx, int on);
 /* Number of batch groups g3_gp_run processes concurrently on separate streams (default 4, max 8;
  * 1 = a single stream, which is what the per-kernel timers of g3_prof_* need). */
 int g3_set_groups(g3_ctx* ctx, int n_groups);
