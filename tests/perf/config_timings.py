@@ -1,10 +1,11 @@
 """Per-config timings of the BASELINE.json configs on one GPU (SURVEY §8d "per-config throughput"), through the public
 API (NumPy in / NumPy out, host<->device copies included), with the oracle port timed beside it on a bounded sample.
 
-    python tools/config_timings.py > profiles/r01_config_timings.jsonl
+    python tests/perf/config_timings.py > profiles/r01_config_timings.jsonl
 
 One JSON line per config.  Flop conventions are SURVEY §8d: logp = N^3/3, logp+grad = N^3, posterior variance = N^2 M.
-The oracle is used only for the CPU reference numbers (this is a measurement tool like bench.py's cpu_baseline leg).
+The oracle is used only for the CPU reference numbers (like bench.py's cpu_baseline leg); the script lives under
+tests/ because only tests/, smoke() and bench.py may import oracle/.
 """
 import json
 import os
@@ -13,7 +14,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import g3py_b200 as g3  # noqa: E402
 from g3py_b200 import workloads as wl  # noqa: E402
 
