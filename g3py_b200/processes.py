@@ -371,12 +371,57 @@ class EllipticalProcess(StochasticProcess):
                     g[:, h.offset:h.offset + h.size] += -2.0 * c * v
         return val, g
 
+    def _affine_location(self, inputs):
+        """(loc0 (N,), J (n_loc, N), idx (n_loc,)) when the location is affine in its free hypers (Zero, Bias, Linear
+        and their sums / scalings are): m(X; p) = loc0 + p[idx] @ J, so a whole batch of locations is one GEMM and
+        the gradient chain another.  None otherwise (MeanProd).  Checked numerically once per data set."""
+        key = (self._data_version, id(self.f_location))
+        hit = getattr(self, "_affine_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        loc_h = [h for h in self.f_location.hypers if isinstance(h, HyperVar)]
+        idx = np.concatenate([np.arange(h.offset, h.offset + h.size) for h in loc_h]).astype(int) if loc_h else np.zeros(0, int)
+        out = None
+        try:
+            rng = np.random.default_rng(0)
+            z = np.zeros(self.ndim)
+            loc0 = np.asarray(self.f_location(inputs, self._accessor(z)), dtype=np.float64)
+            p1, p2 = z.copy(), z.copy()
+            p1[idx], p2[idx] = rng.standard_normal(len(idx)), rng.standard_normal(len(idx))
+            J = np.zeros((len(idx), len(loc0)))
+            jl = self.f_location.jacobian(inputs, self._accessor(p1)) if loc_h else {}
+            r = 0
+            for h in loc_h:
+                J[r:r + h.size] = np.atleast_2d(jl[h])
+                r += h.size
+            ok = True
+            for p in (p1, p2, p1 + p2):
+                direct = np.asarray(self.f_location(inputs, self._accessor(p)), dtype=np.float64)
+                scale = max(np.max(np.abs(direct)), 1.0)
+                ok = ok and np.max(np.abs(direct - (loc0 + p[idx] @ J))) <= 1e-13 * scale
+            if ok:
+                out = (loc0, J, idx)
+        except Exception:
+            out = None
+        self._affine_cache = (key, out)
+        return out
+
     def _host_terms(self, nat2d, inputs, outputs, want_grad):
         """delta (B,N) or (N,), det_m (B,), and the host Jacobians of the location / mapping hypers."""
         B = nat2d.shape[0]
         loc_h = [h for h in self.f_location.hypers if isinstance(h, HyperVar)]
         map_h = [h for h in self.f_mapping.hypers if isinstance(h, HyperVar)]
         varying = B > 1 and any(np.ptp(nat2d[:, h.offset:h.offset + h.size], axis=0).max() > 0 for h in loc_h + map_h)
+        aff = self._affine_location(inputs) if not map_h else None
+        if aff is not None:                        # no free warping hypers, affine location: no per-row Python work
+            loc0, J, idx = aff
+            p0 = self._accessor(nat2d[0])
+            with np.errstate(all="ignore"):
+                minv = np.asarray(self.f_mapping.inv(outputs, p0), dtype=np.float64)
+                det = float(self.f_mapping.logdet_dinv(outputs, p0))
+            rows = nat2d if varying else nat2d[:1]
+            delta = minv[None, :] - (loc0[None, :] + rows[:, idx] @ J)
+            return (delta if varying else delta[0]), np.full(B, det), ("affine", J, idx), varying
         rows = B if varying else 1
         delta = np.empty((rows, len(outputs)))
         det_m = np.empty(rows)
@@ -443,7 +488,12 @@ class EllipticalProcess(StochasticProcess):
         for h, off, size, const in self._slots:
             if h is not None:
                 g_nat[:, h.offset:h.offset + h.size] += dth[:, off:off + size]
-        for b in range(B):
+        if isinstance(jac, tuple):                                        # affine location: d delta / d loc = -J
+            _, J, idx = jac
+            if len(idx):
+                g_nat[:, idx] += -(ddl @ J.T)
+            jac = []
+        for b in range(B if jac else 0):
             jl, dinv, dld = jac[b if varying else 0]
             gd = ddl[b]
             for h, J in jl.items():                                       # d delta / d loc = -J
