@@ -115,6 +115,8 @@ class StochasticProcess:
     def __getstate__(self):
         d = dict(self.__dict__)
         d.pop("_token", None)
+        d.pop("_delta_buf", None)
+        d.pop("_affine_cache", None)
         return d
 
     @property
@@ -420,8 +422,21 @@ class EllipticalProcess(StochasticProcess):
                 minv = np.asarray(self.f_mapping.inv(outputs, p0), dtype=np.float64)
                 det = float(self.f_mapping.logdet_dinv(outputs, p0))
             rows = nat2d if varying else nat2d[:1]
-            delta = minv[None, :] - (loc0[None, :] + rows[:, idx] @ J)
-            return (delta if varying else delta[0]), np.full(B, det), ("affine", J, idx), varying
+            buf = getattr(self, "_delta_buf", None)       # reused: a fresh (B, N) array costs more in page faults
+            if buf is None or buf.shape != (rows.shape[0], len(minv)):
+                buf = self._delta_buf = np.empty((rows.shape[0], len(minv)))
+            if 0 < len(idx) <= 4:                          # BLAS is slow on K <= 4: rank-1 broadcasts instead
+                np.multiply(rows[:, idx[0]:idx[0] + 1], J[0], out=buf)
+                for r in range(1, len(idx)):
+                    buf += rows[:, idx[r]:idx[r] + 1] * J[r]
+                buf += loc0
+            elif len(idx):
+                np.matmul(rows[:, idx], J, out=buf)
+                buf += loc0
+            else:
+                buf[:] = loc0
+            np.subtract(minv, buf, out=buf)
+            return (buf if varying else buf[0]), np.full(B, det), ("affine", J, idx), varying
         rows = B if varying else 1
         delta = np.empty((rows, len(outputs)))
         det_m = np.empty(rows)
