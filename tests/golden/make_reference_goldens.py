@@ -279,8 +279,29 @@ def short(name, proc):
     return s
 
 
+def shim_self_check(g3):
+    """The stand-in against REAL Theano output: notebooks/07-Student-t-Process.ipynb (cell 4) prints r1, r2, r3, det_m of
+    the two evaluations `_compile_methods` makes on the 2-point dummy data set (float32 Theano run).  The reference
+    executed through the stand-in must reproduce their sums to float32 print precision."""
+    x = np.linspace(1700, 2008, 309)[:, None]
+    tp = g3.WarpedStudentTProcess(x, g3.Bias(), g3.SE(x), g3.ArcsinhLinear())
+    X2, y2 = np.array([[0.0], [1.0]]), np.array([0.0, 1.0])
+    rows = [(np.zeros(7), (-0.8902489542961121, -0.7392648458480835, -0.6449083089828491, -0.3465735912322998)),
+            (np.array([0.5, np.log(0.25), np.log(0.5), np.log(0.25), 0.5, np.log(0.5), 0.0]),
+             (-0.9840160012245178, -0.7392648458480835, 0.8014175891876221, -1.732867956161499))]
+    out = []
+    for th, terms in rows:
+        got = float(tp.logp(th, inputs=X2, outputs=y2, array=True))
+        assert abs(got - sum(terms)) < 5e-6, (got, sum(terms))
+        out.append(dict(theta=th.tolist(), notebook_terms=list(terms), notebook_sum=sum(terms), shim_logp=got))
+    with open(os.path.join(HERE, 'reference_shim_check.json'), 'w') as f:
+        json.dump(dict(source='notebooks/07-Student-t-Process.ipynb cell 4 (real Theano, float32)', rows=out), f, indent=1)
+    print('shim vs real-Theano notebook prints:', [(r['shim_logp'], r['notebook_sum']) for r in out])
+
+
 def main():
     g3 = _import_reference()
+    shim_self_check(g3)
     from oracle import g3_oracle as orc     # only for the neutral layout (names / order), not for any value
     out = {}
     for cname, case in CASES.items():

@@ -125,6 +125,19 @@ def test_oracle_gram_matches_reference(name):
     assert scaled_err(Kn, rec["post_noise1"]["prior_kernel"]) < 1e-13
 
 
+def test_standin_reproduces_real_theano_notebook_output():
+    """tests/golden/reference_shim_check.json: the reference executed through the Theano/PyMC3 stand-in against the
+    values a real Theano run printed in the reference's notebook (float32 prints), and the oracle against both."""
+    chk = json.load(open(os.path.join(HERE, "golden", "reference_shim_check.json")))
+    spec = {"kind": "student", "warped": True, "location": {"type": "Bias"}, "kernel": {"type": "SE"},
+            "mapping": {"type": "ArcsinhLinear"}}
+    op = orc.OracleProcess(spec, 1)
+    X2, y2 = np.array([[0.0], [1.0]]), np.array([0.0, 1.0])
+    for row in chk["rows"]:
+        assert abs(row["shim_logp"] - row["notebook_sum"]) < 5e-6
+        assert abs(op.logp(np.array(row["theta"]), X2, y2) - row["shim_logp"]) < 1e-12
+
+
 def test_reference_confirms_matern_rate_gradient_quirk():
     """Executed evidence for SURVEY a3-iv: the reference's dlogp has exact zeros for Matern rates."""
     rec = REF["C2_gp_se_mat52"]
