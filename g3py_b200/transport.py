@@ -103,9 +103,10 @@ class TransportGaussianProcess(EllipticalProcess):
         X, y = self.inputs, self.outputs
         with np.errstate(all="ignore"):
             pre = self.f_mapping.inv(y, p) - self.f_location(X, p)
-        u = self._chol_solve(self._gram(X, None, nat, True), pre)
+        Kxx = self._gram(X, None, nat, True)
+        u = self._chol_solve(Kxx, pre)
         Kxs = self._gram(X, space, nat, False)                # kernel.cov(inputs, space): no noise on the cross block
-        joint = np.block([[self._gram(X, None, nat, True), Kxs], [Kxs.T, self._gram(space, None, nat, noise_pred)]])
+        joint = np.block([[Kxx, Kxs], [Kxs.T, self._gram(space, None, nat, noise_pred)]])
         L = self._chol(joint)
         n = len(y)
         return L[n:, :n] @ u + L[n:, n:] @ pred
