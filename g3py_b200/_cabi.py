@@ -48,6 +48,7 @@ SIGNATURES = {
     "g3_set_potrf_block": (C.c_int, [_ctxp, C.c_int]),
     "g3_set_lookahead": (C.c_int, [_ctxp, C.c_int]),
     "g3_set_splitk": (C.c_int, [_ctxp, C.c_int]),
+    "g3_set_trtri_pipeline": (C.c_int, [_ctxp, C.c_int]),
     "g3_set_groups": (C.c_int, [_ctxp, C.c_int]),
     "g3_timer_begin": (C.c_int, [_ctxp]),
     "g3_timer_end": (C.c_int, [_ctxp, C.POINTER(C.c_float)]),
@@ -159,6 +160,9 @@ class Context:
 
     def set_lookahead(self, on):
         self._ck(self._lib.g3_set_lookahead(self._h, int(bool(on))), "g3_set_lookahead")
+
+    def set_trtri_pipeline(self, on):
+        self._ck(self._lib.g3_set_trtri_pipeline(self._h, int(bool(on))), "g3_set_trtri_pipeline")
 
     def set_splitk(self, on):
         self._ck(self._lib.g3_set_splitk(self._h, int(bool(on))), "g3_set_splitk")

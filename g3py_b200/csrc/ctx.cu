@@ -186,6 +186,10 @@ int g3_ctx_destroy(g3_ctx* ctx) {
     cudaStreamDestroy(ctx->gstream[g]);
     cudaEventDestroy(ctx->gev_done[g]);
   }
+  if (ctx->tri_stream) {
+    cudaStreamDestroy(ctx->tri_stream);
+    cudaEventDestroy(ctx->ev_tri);
+  }
   if (ctx->panel_stream) {
     cudaStreamDestroy(ctx->panel_stream);
     cudaEventDestroy(ctx->ev_panel);

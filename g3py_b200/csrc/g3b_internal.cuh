@@ -59,6 +59,9 @@ struct g3_ctx {
   cudaStream_t panel_stream = nullptr;
   cudaEvent_t ev_panel = nullptr, ev_main = nullptr;
   int lookahead = 1;
+  cudaStream_t tri_stream = nullptr;   // U = L^-T pipelined behind the look-ahead factorisation
+  cudaEvent_t ev_tri = nullptr;
+  int trtri_pipeline = 1, trtri_done = 0;
   int splitk = 1;                      // allow split-K for few-tile / deep-K GEMM launches (g3_set_splitk)
 };
 
@@ -120,8 +123,10 @@ int g3_gemm_launch(g3_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, 
 // ---- factorisation (potrf.cu) ----
 // All matrices: Np x Np (Np multiple of 128), row-major, ld = Np, batch stride Np*Np.
 // Dinv: [B][T][128][128] inverses of the diagonal blocks of L (lower, explicit zeros above).
+// U_pipe (optional, blocked look-ahead schedule only): also compute U = L^-T, pipelined behind the factorisation;
+// ctx->trtri_done tells the caller whether that happened.
 int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, double* logdet, int* info,
-                     const int* bmap, int nb, int w_outer);
+                     const int* bmap, int nb, int w_outer, double* U_pipe = nullptr);
 // Tall panel (rows x nb, ld = nb, rows/nb multiples of 128): factor the top nb x nb block and solve the rows below.
 int g3_potrf_panel(g3_ctx* ctx, double* P, int rows, int nb, double* Dinv, double* logdet, int* info);
 // D[x][y] -= sum_k P[row_off + x][k] P[row_off + y][k]   (D: rowsD x nb, ld = nb; P: rowsP x nb)

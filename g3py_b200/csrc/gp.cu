@@ -264,7 +264,8 @@ static int gp_after_potrf(g3_ctx* ctx, GpBufs& w, int B) {
   if (!st.want_grad) return 0;
   G3_CUDA(ctx, cudaMemcpyAsync(w.s, w.u, sizeof(double) * (size_t)B * Np, cudaMemcpyDeviceToDevice, ctx->stream));
   if ((rc = g3_trsv_bwd(ctx, w.A, w.Dinv, w.s, w.alpha, Np, B))) return rc;
-  if ((rc = g3_trtri_batched(ctx, w.A, w.U, Np, B, w.Dinv))) return rc;
+  if (!ctx->trtri_done && (rc = g3_trtri_batched(ctx, w.A, w.U, Np, B, w.Dinv))) return rc;   // else: pipelined behind potrf
+  ctx->trtri_done = 0;
   if ((rc = g3_lauum_batched(ctx, w.U, w.A, Np, B))) return rc;  // K^-1 (lower tiles) overwrites L
   VjpArgs v;
   memset(&v, 0, sizeof v);
@@ -295,7 +296,8 @@ static int gp_build_and_factor(g3_ctx* ctx, GpBufs& w, int B, const double* shif
   a.status = w.status; a.bmap = bmap;
   int rc;
   if ((rc = g3_gram_launch(ctx, st.desc, a, bmap ? nb : B))) return rc;
-  return g3_potrf_batched(ctx, w.A, Np, B, w.Dinv, w.logdet, w.info, bmap, nb, ctx->potrf_w);
+  return g3_potrf_batched(ctx, w.A, Np, B, w.Dinv, w.logdet, w.info, bmap, nb, ctx->potrf_w,
+                          (st.want_grad && !bmap) ? w.U : nullptr);
 }
 
 extern "C" {
@@ -307,6 +309,11 @@ int g3_set_potrf_block(g3_ctx* ctx, int w_outer) {
 
 int g3_set_lookahead(g3_ctx* ctx, int on) {
   ctx->lookahead = on ? 1 : 0;
+  return 0;
+}
+
+int g3_set_trtri_pipeline(g3_ctx* ctx, int on) {
+  ctx->trtri_pipeline = on ? 1 : 0;
   return 0;
 }
 

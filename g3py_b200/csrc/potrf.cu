@@ -375,8 +375,13 @@ static GemmArgs gemm_zero() {
   return g;
 }
 
+static int trtri_block(g3_ctx* ctx, const CUtensorMap& tmU, const CUtensorMap& tmL, const CUtensorMap& tmD, double* U,
+                       int Np, int B, int io, int ie);
+static void launch_u_diag(g3_ctx* ctx, const double* Dinv, double* U, int Np, int T, int B, int j0, int nj);
+
 int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, double* logdet, int* info,
-                     const int* bmap, int nb, int w_outer) {
+                     const int* bmap, int nb, int w_outer, double* U_pipe) {
+  ctx->trtri_done = 0;
   const int T = Np / TS;
   if (!ctx->diag_ready) {
     G3_CUDA(ctx, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem));
@@ -448,7 +453,7 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
     return g3_gemm_launch(ctx, tmA, tmB, g, B);
   };
 
-  const bool look = ctx->lookahead && w_outer < T && T - w_outer > w_outer;
+  const bool look = ctx->lookahead && w_outer < T;              // at least two outer blocks
   if (!look) {
     for (int jo = 0; jo < T; jo += w_outer) {
       const int je = jo + w_outer < T ? jo + w_outer : T;
@@ -468,6 +473,21 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
   cudaStream_t main_stream = ctx->stream, P = ctx->panel_stream;
   G3_CUDA(ctx, cudaEventRecord(ctx->ev_main, main_stream));      // the Gram matrix is ready
   G3_CUDA(ctx, cudaStreamWaitEvent(P, ctx->ev_main, 0));
+  // U = L^-T pipelined behind the factorisation (gradient path, whole batch): rows [jo, je) of L^-1 only need L final
+  // for rows < je, i.e. block [jo, je) factored, and read columns < je of A, which later trailing updates never touch.
+  // They run on a third stream while the panel / main streams go on with the next blocks.
+  const bool pipe = U_pipe != nullptr && bmap == nullptr && ctx->trtri_pipeline;
+  CUtensorMap tmU;
+  cudaStream_t Q = nullptr;
+  if (pipe) {
+    if (!ctx->tri_stream) {
+      G3_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->tri_stream, cudaStreamNonBlocking));
+      G3_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_tri, cudaEventDisableTiming));
+    }
+    Q = ctx->tri_stream;
+    if ((rc = g3_make_tmap(ctx, &tmU, U_pipe, Np, Np, batch_extent, Np, (uint64_t)Np * Np, G3_BM))) return rc;
+    G3_CUDA(ctx, cudaStreamWaitEvent(Q, ctx->ev_main, 0));        // earlier users of U (previous call) are done
+  }
   rc = 0;
   for (int jo = 0; jo < T && !rc; jo += w_outer) {
     const int je = jo + w_outer < T ? jo + w_outer : T;
@@ -475,6 +495,14 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
     ctx->stream = P;
     rc = factor_block(jo, je);
     if (!rc) cudaEventRecord(ctx->ev_panel, P);
+    if (!rc && pipe) {
+      cudaEventRecord(ctx->ev_tri, P);
+      cudaStreamWaitEvent(Q, ctx->ev_tri, 0);
+      ctx->stream = Q;
+      launch_u_diag(ctx, Dinv, U_pipe, Np, T, B, jo, je - jo);
+      rc = trtri_block(ctx, tmU, tmB, tmD, U_pipe, Np, B, jo, je);
+      ctx->stream = P;
+    }
     if (!rc && je < T) {
       if (jo > 0) cudaStreamWaitEvent(P, ctx->ev_main, 0);         // the previous block's main-stream update wrote these columns
       rc = trailing(jo, je, je, je2);                              // next panel's columns first, on P
@@ -487,6 +515,11 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
   ctx->stream = main_stream;
   cudaEventRecord(ctx->ev_panel, P);
   cudaStreamWaitEvent(main_stream, ctx->ev_panel, 0);
+  if (pipe) {
+    cudaEventRecord(ctx->ev_tri, Q);
+    cudaStreamWaitEvent(main_stream, ctx->ev_tri, 0);
+    if (!rc) ctx->trtri_done = 1;
+  }
   return rc;
 }
 
@@ -553,9 +586,9 @@ int g3_syrk_panel(g3_ctx* ctx, const double* P, int rowsP, int nb, int row_off, 
 // U = L^-T (row-major upper).  Diagonal tiles of U are Linv_jj^T, rebuilt here from Dinv.
 namespace {
 __global__ void __launch_bounds__(256)
-u_diag_from_dinv_kernel(const double* __restrict__ Dinv, double* __restrict__ U, int Np, int T) {
+u_diag_from_dinv_kernel(const double* __restrict__ Dinv, double* __restrict__ U, int Np, int T, int j0) {
   __shared__ double tile[32][33];
-  const int b = blockIdx.z, j = blockIdx.y;
+  const int b = blockIdx.z, j = j0 + blockIdx.y;
   const int bx = blockIdx.x & 3, by = blockIdx.x >> 2;  // 4x4 sub-tiles of 32x32
   const double* Dj = Dinv + ((long long)b * T + j) * TS * TS;
   double* Ut = U + (long long)b * Np * Np + (long long)j * TS * Np + (long long)j * TS;
@@ -566,73 +599,86 @@ u_diag_from_dinv_kernel(const double* __restrict__ Dinv, double* __restrict__ U,
 }
 }  // namespace
 
+// Rows [io, ie) of L^-1 (tile columns of U): S[j][i] = sum_{k=j}^{i-1} U[j][k] L[i][k]^T, then U[j][i] = -S Linv_ii^T.
+// The part of the sum over finished rows k < io is ONE launch for the whole block, the part inside the block goes row
+// by row.  Needs rows < io of U complete and L final for rows < ie.
+static int trtri_block(g3_ctx* ctx, const CUtensorMap& tmU, const CUtensorMap& tmL, const CUtensorMap& tmD, double* U,
+                       int Np, int B, int io, int ie) {
+  const long long strideU = (long long)Np * Np;
+  int rc;
+  if (io > 0) {  // S[j][i] = sum_{k=j}^{io-1} U[j][k] L[i][k]^T,  j < io <= i < ie
+    GemmArgs g = gemm_zero();
+    g.D = U; g.ldd = Np; g.strideD = strideU;
+    g.mode = 0; g.ntx = io; g.nty = ie - io;
+    g.d_r0 = 0; g.d_c0 = io * TS;
+    g.a_r0 = 0; g.a_rx = TS;
+    g.b_r0 = io * TS; g.b_ry = TS;
+    g.ka0 = 0; g.ka_x = TS; g.kb0 = 0; g.kb_x = TS;
+    g.kl0 = io * TS; g.kl_x = -TS;
+    g.alpha = 1.0; g.beta = 0.0;
+    if ((rc = g3_gemm_launch(ctx, tmU, tmL, g, B))) return rc;
+  }
+  for (int i = io > 0 ? io : 1; i < ie; ++i) {
+    if (i > io && io > 0) {  // rows above the block: S[j][i] += sum_{k=io}^{i-1} U[j][k] L[i][k]^T,  j < io
+      GemmArgs g = gemm_zero();
+      g.D = U; g.ldd = Np; g.strideD = strideU;
+      g.mode = 0; g.ntx = io; g.nty = 1;
+      g.d_r0 = 0; g.d_c0 = i * TS;
+      g.a_r0 = 0; g.a_rx = TS;
+      g.b_r0 = i * TS;
+      g.ka0 = io * TS; g.kb0 = io * TS;
+      g.kl0 = (i - io) * TS;
+      g.alpha = 1.0; g.beta = 1.0;
+      if ((rc = g3_gemm_launch(ctx, tmU, tmL, g, B))) return rc;
+    }
+    if (i > io) {  // rows inside the block: S[j][i] = sum_{k=j}^{i-1} U[j][k] L[i][k]^T,  io <= j < i
+      GemmArgs g = gemm_zero();
+      g.D = U; g.ldd = Np; g.strideD = strideU;
+      g.mode = 0; g.ntx = i - io; g.nty = 1;
+      g.d_r0 = io * TS; g.d_c0 = i * TS;
+      g.a_r0 = io * TS; g.a_rx = TS;
+      g.b_r0 = i * TS;
+      g.ka0 = io * TS; g.ka_x = TS; g.kb0 = io * TS; g.kb_x = TS;
+      g.kl0 = (i - io) * TS; g.kl_x = -TS;
+      g.alpha = 1.0; g.beta = 0.0;
+      if ((rc = g3_gemm_launch(ctx, tmU, tmL, g, B))) return rc;
+    }
+    {  // U[j][i] = -S[j][i] Linv_ii^T,  j < i
+      GemmArgs g = gemm_zero();
+      g.D = U; g.ldd = Np; g.strideD = strideU;
+      g.mode = 0; g.ntx = i; g.nty = 1;
+      g.d_r0 = 0; g.d_c0 = i * TS;
+      g.a_r0 = 0; g.a_rx = TS; g.ka0 = i * TS;
+      g.b_r0 = i * TS; g.kb0 = 0;
+      g.kl0 = TS;
+      g.alpha = -1.0; g.beta = 0.0; g.tri_b = 1;
+      if ((rc = g3_gemm_launch(ctx, tmU, tmD, g, B))) return rc;
+    }
+  }
+  return 0;
+}
+
+static void launch_u_diag(g3_ctx* ctx, const double* Dinv, double* U, int Np, int T, int B, int j0, int nj) {
+  u_diag_from_dinv_kernel<<<dim3(16, nj, B), 256, 0, ctx->stream>>>(Dinv, U, Np, T, j0);
+  ctx->launches++;
+}
+
 int g3_trtri_batched(g3_ctx* ctx, const double* L, double* U, int Np, int B, const double* Dinv) {
   const int T = Np / TS;
   int rc;
-  u_diag_from_dinv_kernel<<<dim3(16, T, B), 256, 0, ctx->stream>>>(Dinv, U, Np, T);
-  G3_LAUNCH_CHECK(ctx);
+  launch_u_diag(ctx, Dinv, U, Np, T, B, 0, T);
+  G3_CUDA(ctx, cudaGetLastError());
   CUtensorMap tmU, tmL, tmD;
   if ((rc = g3_make_tmap(ctx, &tmU, U, Np, Np, B, Np, (uint64_t)Np * Np, G3_BM))) return rc;
   if ((rc = g3_make_tmap(ctx, &tmL, L, Np, Np, B, Np, (uint64_t)Np * Np, G3_BN))) return rc;
   if ((rc = g3_make_tmap(ctx, &tmD, Dinv, TS, (uint64_t)T * TS, B, TS, (uint64_t)T * TS * TS, G3_BN))) return rc;
-  const long long strideU = (long long)Np * Np;
-  // Row i of L^-1 (tile column i of U) needs S[j][i] = sum_{k=j}^{i-1} U[j][k] L[i][k]^T for every j < i.  With a batch
-  // the rows are done one at a time (2*B*i CTAs per launch).  Few large matrices go by outer blocks of w rows: the
-  // part of the sum over finished rows k < io is ONE launch for the whole block (w times the CTAs), the part inside
-  // the block stays row by row -- the same split as the right-looking potrf above.
+  // With a batch the rows are done one at a time (2*B*i CTAs per launch); few large matrices go by outer blocks of
+  // w rows -- the same split as the right-looking potrf.
   int w = ctx->potrf_w > 0 ? ctx->potrf_w : (((long long)B * T >= 256) ? T : ctx->potrf_w_big);
   if (w < 1) w = 1;
   for (int io = 0; io < T; io += w) {
     const int ie = io + w < T ? io + w : T;
-    if (io > 0) {  // S[j][i] = sum_{k=j}^{io-1} U[j][k] L[i][k]^T,  j < io <= i < ie
-      GemmArgs g = gemm_zero();
-      g.D = U; g.ldd = Np; g.strideD = strideU;
-      g.mode = 0; g.ntx = io; g.nty = ie - io;
-      g.d_r0 = 0; g.d_c0 = io * TS;
-      g.a_r0 = 0; g.a_rx = TS;
-      g.b_r0 = io * TS; g.b_ry = TS;
-      g.ka0 = 0; g.ka_x = TS; g.kb0 = 0; g.kb_x = TS;
-      g.kl0 = io * TS; g.kl_x = -TS;
-      g.alpha = 1.0; g.beta = 0.0;
-      if ((rc = g3_gemm_launch(ctx, tmU, tmL, g, B))) return rc;
-    }
-    for (int i = io > 0 ? io : 1; i < ie; ++i) {
-      if (i > io && io > 0) {  // rows above the block: S[j][i] += sum_{k=io}^{i-1} U[j][k] L[i][k]^T,  j < io
-        GemmArgs g = gemm_zero();
-        g.D = U; g.ldd = Np; g.strideD = strideU;
-        g.mode = 0; g.ntx = io; g.nty = 1;
-        g.d_r0 = 0; g.d_c0 = i * TS;
-        g.a_r0 = 0; g.a_rx = TS;
-        g.b_r0 = i * TS;
-        g.ka0 = io * TS; g.kb0 = io * TS;
-        g.kl0 = (i - io) * TS;
-        g.alpha = 1.0; g.beta = 1.0;
-        if ((rc = g3_gemm_launch(ctx, tmU, tmL, g, B))) return rc;
-      }
-      if (i > io) {  // rows inside the block: S[j][i] = sum_{k=j}^{i-1} U[j][k] L[i][k]^T,  io <= j < i
-        GemmArgs g = gemm_zero();
-        g.D = U; g.ldd = Np; g.strideD = strideU;
-        g.mode = 0; g.ntx = i - io; g.nty = 1;
-        g.d_r0 = io * TS; g.d_c0 = i * TS;
-        g.a_r0 = io * TS; g.a_rx = TS;
-        g.b_r0 = i * TS;
-        g.ka0 = io * TS; g.ka_x = TS; g.kb0 = io * TS; g.kb_x = TS;
-        g.kl0 = (i - io) * TS; g.kl_x = -TS;
-        g.alpha = 1.0; g.beta = 0.0;
-        if ((rc = g3_gemm_launch(ctx, tmU, tmL, g, B))) return rc;
-      }
-      {  // U[j][i] = -S[j][i] Linv_ii^T,  j < i
-        GemmArgs g = gemm_zero();
-        g.D = U; g.ldd = Np; g.strideD = strideU;
-        g.mode = 0; g.ntx = i; g.nty = 1;
-        g.d_r0 = 0; g.d_c0 = i * TS;
-        g.a_r0 = 0; g.a_rx = TS; g.ka0 = i * TS;
-        g.b_r0 = i * TS; g.kb0 = 0;
-        g.kl0 = TS;
-        g.alpha = -1.0; g.beta = 0.0; g.tri_b = 1;
-        if ((rc = g3_gemm_launch(ctx, tmU, tmD, g, B))) return rc;
-      }
-    }
+    if ((rc = trtri_block(ctx, tmU, tmL, tmD, U, Np, B, io, ie))) return rc;
   }
   return 0;
 }

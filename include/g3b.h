@@ -114,6 +114,9 @@ int g3_set_lookahead(g3_ctx* ctx, int on);
 /* Split-K for GEMM launches with few tiles and a deep contraction (single-matrix evaluations): up to 8 CTAs share
  * one output tile, partial tiles are added in a fixed order (bitwise reproducible).  Default on. */
 int g3_set_splitk(g3_ctx* ctx, int on);
+/* Gradient path of few large matrices: compute U = L^-T block by block on a third stream while the look-ahead
+ * factorisation is still running (default on; results do not depend on it). */
+int g3_set_trtri_pipeline(g3_ctx* ctx, int on);
 /* Number of batch groups g3_gp_run processes concurrently on separate streams (default 4, max 8;
  * 1 = a single stream, which is what the per-kernel timers of g3_prof_* need). */
 int g3_set_groups(g3_ctx* ctx, int n_groups);

@@ -583,19 +583,22 @@ def test_blocked_schedules_agree(ctx):
     want_lp = np.array([op.logp(t, X, y) for t in Th])
     want_g = np.array([op.dlogp(t, X, y) for t in Th])
     try:
-        for w, look, sk in ((1 << 20, 1, 1), (1 << 20, 1, 0), (4, 1, 1), (4, 0, 1), (4, 1, 0), (5, 1, 1), (1, 1, 1),
-                            (2, 1, 1), (0, 1, 1), (0, 1, 0)):
+        for w, look, sk, pipe in ((1 << 20, 1, 1, 1), (1 << 20, 1, 0, 1), (4, 1, 1, 1), (4, 1, 1, 0), (4, 0, 1, 1),
+                                  (4, 1, 0, 1), (5, 1, 1, 1), (1, 1, 1, 1), (2, 1, 1, 1), (2, 1, 1, 0), (0, 1, 1, 1),
+                                  (0, 1, 0, 0)):
             gp.ctx.set_potrf_block(w)
             gp.ctx.set_lookahead(look)
             gp.ctx.set_splitk(sk)
+            gp.ctx.set_trtri_pipeline(pipe)
             for sel in (slice(0, 1), slice(0, 3)):
                 lp, g, info = gp.logp_dlogp_batch(Th[sel])
                 assert np.all(info["status"] == 0)
-                assert np.max(np.abs(lp - want_lp[sel]) / np.abs(want_lp[sel])) < TOL, (w, look, sk)
-                assert scaled_err(g, want_g[sel]) < TOL, (w, look, sk)
+                assert np.max(np.abs(lp - want_lp[sel]) / np.abs(want_lp[sel])) < TOL, (w, look, sk, pipe)
+                assert scaled_err(g, want_g[sel]) < TOL, (w, look, sk, pipe)
                 lp2, g2, _ = gp.logp_dlogp_batch(Th[sel])          # split-K adds partial tiles in a fixed order
-                assert np.array_equal(lp, lp2) and np.array_equal(g, g2), (w, look, sk)
+                assert np.array_equal(lp, lp2) and np.array_equal(g, g2), (w, look, sk, pipe)
     finally:
         gp.ctx.set_potrf_block(0)
         gp.ctx.set_lookahead(1)
         gp.ctx.set_splitk(1)
+        gp.ctx.set_trtri_pipeline(1)
