@@ -62,6 +62,7 @@ struct g3_ctx {
   cudaStream_t tri_stream = nullptr;   // U = L^-T pipelined behind the look-ahead factorisation
   cudaEvent_t ev_tri = nullptr;
   int trtri_pipeline = 1, trtri_done = 0;
+  int force_left = 0;                  // set by g3_gp_run for batches of more than 8 items (their stream groups hold 8)
   int splitk = 1;                      // allow split-K for few-tile / deep-K GEMM launches (g3_set_splitk)
 };
 

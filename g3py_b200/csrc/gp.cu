@@ -382,9 +382,12 @@ int g3_gp_run(g3_ctx* ctx) {
   int groups = ctx->n_groups < 1 ? 1 : ctx->n_groups;
   if (groups > G3_MAX_GROUPS) groups = G3_MAX_GROUPS;
   while (groups > 1 && B / groups < 8) --groups;
+  ctx->force_left = B > 8;               // schedule chosen on the whole batch, not per stream group
   if (groups == 1) {
-    if ((rc = gp_build_and_factor(ctx, w, B, w.shift, nullptr, 0))) return rc;
-    return gp_after_potrf(ctx, w, B);
+    rc = gp_build_and_factor(ctx, w, B, w.shift, nullptr, 0);
+    if (!rc) rc = gp_after_potrf(ctx, w, B);
+    ctx->force_left = 0;
+    return rc;
   }
   cudaStream_t main_stream = ctx->stream;
   G3_CUDA(ctx, cudaEventRecord(ctx->gev_start, main_stream));
@@ -400,6 +403,7 @@ int g3_gp_run(g3_ctx* ctx) {
     cudaStreamWaitEvent(main_stream, ctx->gev_done[g], 0);
   }
   ctx->stream = main_stream;
+  ctx->force_left = 0;
   return rc;
 }
 

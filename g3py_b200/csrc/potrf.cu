@@ -375,10 +375,19 @@ static GemmArgs gemm_zero() {
   return g;
 }
 
-// Outer-block width (tile columns) of the blocked schedules for few matrices, from a sweep on B200
-// (tools/sweep_block.py): up to N=4096 every column is its own block (rank-128 trailing updates keep all SMs busy and
-// the look-ahead / pipelined trtri overlap the per-column chains), 4 at N=8192, 8 from N=16384 on.
-static int g3_auto_block(const g3_ctx* ctx, int T) { return T <= 32 ? 1 : (T <= 64 ? 4 : ctx->potrf_w_big); }
+// Outer-block width (tile columns) of the blocked schedules for few matrices, from sweeps on B200
+// (tools/sweep_block.py, tools/sweep_batch.py): up to N=2048 every column is its own block (rank-128 trailing updates
+// keep all SMs busy and the look-ahead / pipelined trtri overlap the per-column chains), at N=4096 too for one or two
+// matrices, 4 for N=4096 with 3..8 matrices and at N=8192, 8 from N=16384 on.
+static int g3_auto_block(const g3_ctx* ctx, int T, int B) {
+  if (T <= 16) return 1;
+  if (T <= 32) return B <= 2 ? 1 : 4;
+  return T <= 64 ? 4 : ctx->potrf_w_big;
+}
+// Up to 8 matrices go by outer blocks (look-ahead, pipelined trtri); larger batches supply the parallelism
+// themselves and stay left-looking (tools/sweep_batch.py).  g3_gp_run decides on the WHOLE batch and pins the choice
+// for its stream groups (8 items each) through ctx->force_left.
+static bool g3_use_blocked(const g3_ctx* ctx, int B) { return !ctx->force_left && B <= 8; }
 
 static int trtri_block(g3_ctx* ctx, const CUtensorMap& tmU, const CUtensorMap& tmL, const CUtensorMap& tmD, double* U,
                        int Np, int B, int io, int ie);
@@ -395,9 +404,8 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
   const int Blaunch = bmap ? nb : Btotal;
   if (w_outer < 1) {
     // auto: fully left-looking when the batch supplies the parallelism (a column update launches 2*B*(T-j) CTAs);
-    // few matrices with many tile columns (a single N=16384 evaluation: B=1, T=128) would leave most SMs idle in
-    // the column updates, so they go right-looking between outer blocks of `potrf_w_big` tile columns
-    w_outer = ((long long)Blaunch * T >= 256) ? (1 << 20) : g3_auto_block(ctx, T);
+    // few matrices would leave most SMs idle in the column updates, so they go right-looking between outer blocks
+    w_outer = g3_use_blocked(ctx, Blaunch) ? g3_auto_block(ctx, T, Blaunch) : (1 << 20);
   }
   // The tensor maps span the whole allocation (Btotal matrices); bmap (nb entries) picks the batch
   // coordinate of each launched CTA column, so the jitter ladder can refactor a subset in place.
@@ -679,7 +687,7 @@ int g3_trtri_batched(g3_ctx* ctx, const double* L, double* U, int Np, int B, con
   if ((rc = g3_make_tmap(ctx, &tmD, Dinv, TS, (uint64_t)T * TS, B, TS, (uint64_t)T * TS * TS, G3_BN))) return rc;
   // With a batch the rows are done one at a time (2*B*i CTAs per launch); few large matrices go by outer blocks of
   // w rows -- the same split as the right-looking potrf.
-  int w = ctx->potrf_w > 0 ? ctx->potrf_w : (((long long)B * T >= 256) ? T : g3_auto_block(ctx, T));
+  int w = ctx->potrf_w > 0 ? ctx->potrf_w : (g3_use_blocked(ctx, B) ? g3_auto_block(ctx, T, B) : T);
   if (w < 1) w = 1;
   for (int io = 0; io < T; io += w) {
     const int ie = io + w < T ? io + w : T;

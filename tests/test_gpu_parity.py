@@ -487,7 +487,10 @@ def test_jitter_ladder_inside_grouped_batch():
     assert np.array_equal(jit, np.arange(B) % 3 == 0)
     for b in (0, 1, 2, 3, 38, 39):
         l1, g1, i1 = gp._eval_batch(Th[b:b + 1])
-        assert abs(l1[0] - lp[b]) <= 1e-12 * abs(lp[b]) and scaled_err(g1[0], g[b]) < 1e-10
+        # a single item takes the blocked schedule, the batch the left-looking one: same result up to rounding, which the
+        # jittered items (K singular up to the 1e-6 shift, condition number ~1e7) amplify
+        tol_l, tol_g = (1e-7, 1e-5) if jit[b] else (1e-12, 1e-10)
+        assert abs(l1[0] - lp[b]) <= tol_l * abs(lp[b]) and scaled_err(g1[0], g[b]) < tol_g, (b, l1[0], lp[b])
         assert i1["status"][0] == info["status"][b]
         t = op.logp_terms(Th[b], X, y)
         assert (t["info"] > 0) == bool(jit[b])
