@@ -171,6 +171,18 @@ def _print_op(name=''):
     return lambda x: x
 
 
+def uninstall():
+    """Remove the stand-in modules again (unit tests call this so that nothing leaks into other test modules)."""
+    for name in [n for n in sys.modules if n.split('.')[0] in ('theano', 'pymc3') + STUB_ROOTS]:
+        mod = sys.modules[name]
+        if name.split('.')[0] in STUB_ROOTS and not isinstance(mod, _StubModule):
+            continue
+        if name.split('.')[0] == 'theano' and not getattr(sys.modules.get('theano'), '_g3b_shim', False):
+            continue
+        del sys.modules[name]
+    sys.meta_path[:] = [f for f in sys.meta_path if not isinstance(f, _StubFinder)]
+
+
 def install():
     if 'theano' in sys.modules and getattr(sys.modules['theano'], '_g3b_shim', False):
         return
