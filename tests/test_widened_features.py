@@ -1,0 +1,113 @@
+"""The SURVEY §8f features (transports, dot-product / Brownian / constant leaves, KernelMax, potentials, Logistic and the
+Newton-inverse warpings) at sizes that span several 128-tiles and in batches, against the oracle — which
+tests/test_reference_goldens.py pins to the executed reference at small N.  CPU: host logic with the NumPy device
+double; GPU: the CUDA path."""
+import numpy as np
+import pytest
+
+from oracle import g3_oracle as orc
+from helpers import build_process, scaled_err
+
+K = lambda t, **kw: dict(type=t, **kw)
+SPECS = {
+    "tgp": dict(kind="transport", chain=[dict(t="TMapping", mapping=K("BoxCoxShifted")), dict(t="TLocation", location=K("Bias")),
+                                         dict(t="TKernel", kernel=K("SE"), noisy=True)]),
+    "lin_se": dict(kind="gauss", location=K("Zero"), kernel=K("sum", k1=K("LIN"), k2=K("SE"))),
+    "pol3": dict(kind="gauss", location=K("Bias"), kernel=K("sum", k1=K("POL", p=3), k2=K("SE"))),
+    "dot_bw_var": dict(kind="gauss", location=K("Zero"), kernel=K("sum", k1=K("sum", k1=K("KernelDot"), k2=K("BW")), k2=K("VAR"))),
+    "max": dict(kind="student", location=K("Bias"), kernel=K("max", k1=K("SE"), k2=K("scale", c=0.5, k=K("MAT32")))),
+    "warptanh": dict(kind="gauss", warped=True, location=K("Bias"), kernel=K("SE"), mapping=K("WarpingTanh", n=2)),
+    "warpboxcox": dict(kind="gauss", warped=True, location=K("Bias"), kernel=K("SE"), mapping=K("WarpingBoxCox", n=2)),
+    "logistic": dict(kind="gauss", warped=True, location=K("Bias"), kernel=K("SE"), mapping=K("Logistic")),
+    "potentials": dict(kind="gauss", warped=True, location=dict(type="Bias", potential=["Bias", "L2", 0.3]),
+                       kernel=dict(type="sum", potential=["var", "L1", 0.7], k1=K("SE"), k2=dict(type="RQ", potential=["alpha", "L2", 0.2])),
+                       mapping=dict(type="BoxCoxShifted", potential=["power", "L1", 0.4])),
+}
+POSITIVE = {"tgp", "warpboxcox", "logistic", "potentials"}
+
+
+def _problem(name, N, B, seed=0):
+    rng = np.random.default_rng(seed)
+    D = 2
+    X = rng.uniform(0.2, 5.0, size=(N, D))
+    y = np.sin(X[:, 0]) + 0.4 * np.cos(0.7 * X[:, 1]) + 0.1 * rng.standard_normal(N)
+    if name in POSITIVE:
+        y = np.exp(0.5 * y) + 0.2
+    op = orc.build_process(SPECS[name], D)
+    th = []
+    for nm, size, pos in op.layout():
+        v = 0.1 * rng.standard_normal((B, size))
+        if "Noise" in nm:                      # max(k1, k2) is not PSD in general: more noise keeps K definite
+            v += np.log((2.0 if name == "max" else 0.05) * np.var(y))
+        elif nm.endswith("_var"):
+            v += np.log(np.var(y))
+        elif nm.endswith("_bias"):
+            v += np.log(0.5)
+        elif nm.endswith("LIN_rate") or nm.endswith("POL_rate") or nm.endswith("KernelDot_rate"):
+            v += np.log(0.3)
+        elif nm.endswith("_power"):
+            v = np.full((B, size), np.log(0.7)) + 0.02 * rng.standard_normal((B, size))
+        elif nm.endswith("Freedom_degree"):
+            v = np.full((B, size), np.log(5.0))
+        elif nm.endswith("Logistic_lower"):
+            v = np.full((B, size), np.min(y) - 0.4)
+        elif nm.endswith("Logistic_high"):
+            v = np.full((B, size), np.log(np.max(y) - np.min(y) + 0.9))
+        elif nm.endswith("WarpingTanh_a"):
+            v += np.log(0.3)
+        elif nm.endswith("WarpingTanh_c"):
+            v += -np.mean(y)
+        elif nm.endswith("WarpingBoxCox_w"):
+            v += np.log(0.5)
+        elif nm.endswith("_Bias") and name not in POSITIVE and "warp" not in name:
+            v += np.mean(y)
+        th.append(v)
+    return X, y, op, np.concatenate(th, axis=1)
+
+
+def _check(name, N, B, M):
+    X, y, op, Th = _problem(name, N, B)
+    gp = build_process(SPECS[name], X)
+    gp.observed(X, y)
+    assert [(n, s) for n, s, _ in op.layout()] == [(v.name[len(gp.name) + 1:], v.size) for v in gp.registry.vars]
+    lp, g, info = gp.logp_dlogp_batch(Th, reference_nan_quirk=True)
+    for b in range(B):
+        want = op.logp(Th[b], X, y)
+        assert abs(lp[b] - want) <= 1e-9 * abs(want), (name, b)
+        assert scaled_err(g[b], op.dlogp(Th[b], X, y, nan_quirk=True)) < 1e-9, (name, b)
+    Xs = X[:M] + 0.05
+    if SPECS[name].get("kind") == "transport":
+        v = np.random.default_rng(5).standard_normal(M)
+        for prior in (True, False):
+            got = gp.transport(Th[0], space=Xs, vector=v, prior=prior, noise=True, array=True)
+            assert scaled_err(got, op.transport(Th[0], Xs, v, X, y, prior=prior, noise=True)) < 1e-7
+        return
+    out = gp.predict(Th[0], space=Xs, array=True, var=True, median=True, quantiles=True, noise=True)
+    pr = op.predict(Th[0], Xs, X, y, noise=True)
+    post, _, _ = gp._posterior(Th[0], Xs, noise=True)
+    pc = op.posterior(Th[0], Xs, X, y, noise=True, solver="chol")
+    assert scaled_err(post["location"], pc["location"]) < 1e-9
+    assert scaled_err(post["kernel_diag"], pc["kernel_diag"]) < 1e-8
+    for key in ("mean", "median", "quantile_up"):
+        assert scaled_err(out[key], pr[key]) < 1e-7, (name, key)
+    assert scaled_err(out["variance"], pr["variance"]) < 1e-6
+
+
+@pytest.fixture
+def fake(monkeypatch):
+    import g3py_b200 as g3
+    from fake_ctx import FakeContext
+    ctx = FakeContext()
+    monkeypatch.setattr(g3.processes, "get_context", lambda device=0: ctx)
+    return ctx
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+def test_host_widened_features(fake, name):
+    _check(name, 60, 2, 7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(SPECS))
+def test_cuda_widened_features_multi_tile(name):
+    _check(name, 300 if "warp" in name else 520, 3, 40)
