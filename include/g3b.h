@@ -16,6 +16,7 @@
 #ifndef G3B_H
 #define G3B_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

@@ -44,6 +44,15 @@ def test_struct_layout_matches_c():
                                      cabi.KernelDesc.nodes.offset]
 
 
+def test_header_is_standalone_c99(tmp_path):
+    """include/g3b.h is the C boundary: it must compile on its own as plain C (no C++, no implicit includes)."""
+    src = tmp_path / "h.c"
+    src.write_text('#include "g3b.h"\nint main(void) { g3_kernel_desc d; d.n_nodes = 0; (void)d; return G3_K_MAX == 20 ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_no_cpu_fallback():
     """Without a GPU the product path fails loudly (this container has none)."""
     try:
