@@ -605,3 +605,31 @@ def test_blocked_schedules_agree(ctx):
         gp.ctx.set_lookahead(1)
         gp.ctx.set_splitk(1)
         gp.ctx.set_trtri_pipeline(1)
+
+
+@pytest.mark.gpu
+def test_pure_c_client_matches_ctypes_path(tmp_path, ctx):
+    """The boundary used from plain C (tests/cabi/client.c, no Python in the process) gives the numbers the ctypes
+    binding gives for the same descriptor, data and hyper samples."""
+    import subprocess
+    from test_host import _build_c_client
+    exe = _build_c_client(tmp_path)
+    N, D = 300, 2
+    r = subprocess.run([str(exe), str(N)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = [l.split() for l in r.stdout.strip().splitlines()]
+    i = np.arange(N)
+    X = np.stack([np.fmod(0.37 * i, 5.0), np.fmod(0.91 * i + 0.5, 3.0)], axis=1)
+    y = np.sin(X[:, 0]) + 0.3 * np.cos(2.0 * X[:, 1])
+    gp = g3.GP(X, g3.Zero(), g3.SE(X))
+    gp.observed(X, y)
+    theta = np.array([[1.0, 0.8, 1.3, 0.05], [0.6, 1.1, 0.7, 0.1]])
+    res = gp.ctx.gp_logp_grad(gp.desc, cabi.KIND_GAUSS, y, theta)
+    op = orc.OracleProcess({"kind": "gauss", "location": {"type": "Zero"}, "kernel": {"type": "SE"}}, D)
+    for b, row in enumerate(rows):
+        assert int(row[0]) == b and int(row[1]) == 0
+        vals = np.array([float(v) for v in row[2:]])
+        want = np.concatenate([[res["beta"][b], res["logdet"][b]], res["dtheta"][b], [res["ddelta"][b][N // 2]]])
+        assert scaled_err(vals, want) < 1e-13
+        t = op.logp_terms(np.log(theta[b]), X, y)
+        assert abs(vals[0] - t["beta"]) <= 1e-9 * t["beta"] and abs(vals[1] - t["logdet"]) <= 1e-9 * abs(t["logdet"])

@@ -395,3 +395,23 @@ def test_logpredictive_and_sampler_on_fake(fake):
     got = v["logpredictive"](y[:7])
     strict_shift = -0.5 * 7 * (1.8378770351409912 - np.log(2 * np.pi))
     assert got == pytest.approx(want + strict_shift, rel=1e-9)
+
+
+def _build_c_client(tmp_path):
+    exe = tmp_path / "cabi_client"
+    libdir = os.path.dirname(g3.lib_path())
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-O1", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "cabi", "client.c"), "-o", str(exe), "-L", libdir, "-lg3b", "-lm",
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_pure_c_client_links_against_the_boundary(tmp_path):
+    """tests/cabi/client.c uses only include/g3b.h: it must compile as C99 and link against libg3b.so; without a GPU
+    it fails loudly at g3_ctx_create (exit code 2), never silently."""
+    exe = _build_c_client(tmp_path)
+    r = subprocess.run([str(exe), "40"], capture_output=True, text=True)
+    assert r.returncode in (0, 2), (r.returncode, r.stderr)
+    if r.returncode == 2:
+        assert "g3_ctx_create failed" in r.stderr
