@@ -11,14 +11,17 @@ that tests can hand the identical description to the oracle and to the CUDA
 front-end without either importing the other.
 
 Status of the pin.  This module is TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and the
-CPU-baseline legs of bench.py may import it; the product (g3py_b200/) never does.  It is pinned against the
-only known-answer vectors the reference tree holds - the two N=2 WarpedStudentTProcess evaluations printed
-in notebooks/07-Student-t-Process.ipynb:206-218 (r1, r2, r3, det_m and their sum; tests/test_oracle.py) -
-which fix the 1/2 rate^2 metric convention, the auto-added Noise kernel, ArcsinhLinear's logdet, nu = 2 +
-degree and the r1/r2/r3 split.  For everything else (Gaussian logp, gradients, other kernels and
-warpings, posterior moments) the reference has no tests and cannot be executed here (Theano / PyMC3 are not
-installable): PARITY UNPINNED beyond those vectors; those parts are cross-checked by finite differences,
-torch fp64 autograd and the LU-vs-Cholesky posterior identity instead.
+CPU-baseline legs of bench.py may import it; the product (g3py_b200/) never does.  PARITY PINNED against outputs
+of the reference itself: tests/golden/make_reference_goldens.py imports the unmodified /root/reference/g3py in the
+build container through a stand-in for the Theano / PyMC3 API (tests/golden/refshim: lazy graph evaluated with torch
+CPU fp64, reverse-mode autodiff, the reference's own CholeskyRobust perform/grad) and records logp, loglike, dlogp,
+Gram matrices, posterior location / covariance, Gauss-Hermite moments, quantiles, transports for 30 cases in
+tests/golden/reference_g3py.json; tests/test_reference_goldens.py holds this module to them (logp 1e-12, gradient
+1e-10, posterior 1e-10).  The stand-in itself reproduces the values a real Theano run printed in
+notebooks/07-Student-t-Process.ipynb:206-218 (tests/golden/reference_shim_check.json), which tests/test_oracle.py
+also checks directly.  Not reproducible by the stand-in: Theano's graph optimiser, its
+BLAS/LAPACK build, the traversal order of dlogp components, the max/min reduction gradient at ties.  Further
+cross-checks: finite differences, torch fp64 autograd of an independently written forward, LU-vs-Cholesky posterior.
 
 Constants mode (`strict=True`, default): the float32-rounded literals that stay
 in the reference graph when it is run with floatX='float64' are reproduced
