@@ -4,7 +4,7 @@ This package is a NumPy/SciPy fp64 restatement of the reference's algorithm
 (griosd/g3py, Theano graph + SciPy LAPACK).  It exists to *check* the CUDA
 path.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s
 `cpu_baseline` / `--impl reference` legs may import it; nothing under
-`g3py_b200/` does (tests/test_layout.py enforces that).
+`g3py_b200/` does (tests/test_host.py::test_oracle_is_imported_only_where_allowed enforces that).
 
 Parity status: PINNED against outputs of the reference itself, executed in the
 build container through a stand-in for the Theano / PyMC3 API (fixtures and

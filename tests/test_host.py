@@ -74,6 +74,35 @@ def test_no_cpu_fallback():
     assert "oracle" not in src.replace("(bench.py must not import the oracle)", "").replace("tests check they equal the oracle's", "")
 
 
+def test_oracle_is_imported_only_where_allowed():
+    """oracle/ is test infrastructure: nothing under g3py_b200/ or tools/ may import it (AST scan of every module), and
+    bench.py only inside its CPU-baseline / reference-arm function."""
+    import ast
+
+    def oracle_imports(path):
+        tree = ast.parse(open(path).read())
+        hits = []
+        for fn in ast.walk(tree):
+            for node in ast.iter_child_nodes(fn):
+                mods = []
+                if isinstance(node, ast.Import):
+                    mods = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    mods = [node.module or ""]
+                if any(m == "oracle" or m.startswith("oracle.") for m in mods):
+                    hits.append(getattr(fn, "name", "<module>"))
+        return hits
+
+    for base in ("g3py_b200", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith(".py"):
+                    assert oracle_imports(os.path.join(dirpath, f)) == [], (dirpath, f)
+    where = oracle_imports(os.path.join(ROOT, "bench.py"))
+    assert where and all("cpu" in w or "reference" in w for w in where), where
+    assert set(oracle_imports(os.path.join(ROOT, "__graft_entry__.py"))) <= {"smoke", "build"}
+
+
 def test_workloads_equal_oracle_inputs():
     for a, b in ((workloads.c1_inputs(), orc.c1_inputs()), (workloads.c2_inputs(64, 4), orc.c2_inputs(64, 4)),
                  (workloads.c3_inputs(32, 8), orc.c3_inputs(32, 8)), (workloads.c4_inputs(32, 8), orc.c4_inputs(32, 8)),
