@@ -817,18 +817,36 @@ class EllipticalProcess(StochasticProcess):
             start = self.params
         x0 = self.dict_to_array(start) if isinstance(start, dict) else np.asarray(start, dtype=np.float64)
 
+        # BFGS's Wolfe line search asks for f and f' at the same trial point: one fused logp+grad evaluation serves both
+        # (the reference compiles and calls `logp` and `dlogp` separately, stochastic.py:591-596)
+        last = {}
+
+        def both(x):
+            key = np.asarray(x, dtype=np.float64).tobytes()
+            if last.get("key") != key:
+                lp, g = self.logp_dlogp(np.asarray(x, dtype=np.float64))
+                last.update(key=key, lp=lp, g=g)
+            return last["lp"], last["g"]
+
         def f(x):
             try:
-                v = -self.logp(x, array=True)
+                v = -(both(x)[0] if bfgs else self.logp(x, array=True))
                 return 1e100 if np.isnan(v) else v                          # libs/__init__.py:61-62 nan_to_high
             except Exception:
                 return 1e32
 
         def df(x):
             try:
-                return np.nan_to_num(-self.dlogp(x, array=True))
+                return np.nan_to_num(-both(x)[1])
             except Exception:
                 return np.full_like(x, 1e32)
+
+        def f_only(x):                     # derivative-free Powell steps: no gradient work
+            try:
+                v = -self.logp(x, array=True)
+                return 1e100 if np.isnan(v) else v
+            except Exception:
+                return 1e32
 
         pts = [("start", -f(x0), x0)]
         x = x0
@@ -837,7 +855,7 @@ class EllipticalProcess(StochasticProcess):
                 x = spo.fmin_bfgs(f, x, fprime=df, disp=display, **kwargs)
                 pts.append(("bfgs", -f(x), x))
             if powell:
-                x = spo.fmin_powell(f, x, disp=display)
+                x = spo.fmin_powell(lambda z: f_only(z), x, disp=display)
                 pts.append(("powell", -f(x), x))
         best = max(pts, key=lambda t: t[1])
         params = self.array_to_dict(best[2])
