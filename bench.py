@@ -27,13 +27,22 @@ sys.path.insert(0, ROOT)
 # stdout carries exactly ONE JSON line (rank 0).  Libraries write banners to the C-level stdout (NCCL prints
 # "NCCL version ..." at communicator creation), so file descriptor 1 is pointed at stderr for the whole run and the
 # result line goes to the saved, real stdout.
-sys.stdout.flush()
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit(line):
-    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    if _REAL_STDOUT is None:
+        print(json.dumps(line), flush=True)
+    else:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 N_OBS, D_IN, B_THETA = 4096, 3, 64
 METRIC = "fp64 GP logp+grad evals/s at N=4096 x64 theta batch"
@@ -357,4 +366,5 @@ def metric2(ctx, pk, N=65536):
 
 
 if __name__ == "__main__":
+    _claim_stdout()
     main()
