@@ -31,7 +31,7 @@ def slices(M, s):
     for _ in range(s):
         R = R * 128.0                                # exact
         q = np.trunc(R)                              # 7 bits + sign, |q| <= 127 (<= 64 after the first if rounded)
-        out.append(q.astype(np.int64))
+        out.append(q)                                # small integers held in float64: products and sums stay exact
         R = R - q                                    # exact remainder, |R| < 1
     return out, e
 
@@ -44,8 +44,8 @@ def ozaki_gemm(A, B, s):
     n_gemm = 0
     for t in range(s):
         for u in range(s - t):
-            P = As[t] @ Bs[u].T                       # exact in int64 (int32 suffices on the device)
-            assert np.max(np.abs(P)) < 2 ** 31
+            P = As[t] @ Bs[u].T                       # integer-valued, |sum| <= K * 127^2 < 2^31: exact in float64
+            assert np.max(np.abs(P)) < 2 ** 31         # (BLAS); int32 accumulators suffice on the device
             C += P.astype(np.longdouble) * np.longdouble(2.0) ** (-7 * (t + u + 2))
             n_gemm += 1
     return (C * np.exp2(ea)[:, None].astype(np.longdouble) * np.exp2(eb)[None, :].astype(np.longdouble)), n_gemm
@@ -77,6 +77,18 @@ def main():
         err = float(np.max(np.abs(C - ref)) / scale)
         print("slices s=%2d: %3d int8 GEMMs (%2d with symmetry), max abs err / max|C| = %.2e,  int8 peak / GEMMs = %.0f TFLOP/s "
               "equivalent (4500 dense int8 TOP/s nominal)" % (s, n, (n + s) // 2, err, 4500.0 / n))
+    # gradient path: K^-1 = U U^T with U = L^-T (lauum).  Rows of U span a wider range than rows of L.
+    m = 768                                            # leading block (the extended-precision reference product is slow)
+    U = sla.solve_triangular(L[:m, :m], np.eye(m), lower=True).T
+    refK = U.astype(np.longdouble) @ U.T.astype(np.longdouble)
+    f64K = U @ U.T
+    sc = np.max(np.abs(refK))
+    rmax = np.max(np.abs(U), axis=1)
+    print("lauum K^-1 = U U^T: |K^-1| ~ %.2e, row maxima of U: %.1e .. %.1e; fp64 GEMM err %.2e"
+          % (sc, rmax.min(), rmax.max(), float(np.max(np.abs(f64K - refK)) / sc)))
+    for s in (7, 8, 9, 10):
+        P, n = ozaki_gemm(U, U, s)
+        print("  slices s=%2d: %3d int8 GEMMs, max abs err / max|K^-1| = %.2e" % (s, n, float(np.max(np.abs(P - refK)) / sc)))
 
 
 if __name__ == "__main__":
