@@ -305,9 +305,31 @@ def shim_self_check(g3):
     print('shim vs real-Theano notebook prints:', [(r['shim_logp'], r['notebook_sum']) for r in out])
 
 
+def c1_find_map(g3):
+    """BASELINE config 1 (the tutorial example) at full size: the reference's own default hypers and its own find_MAP
+    (scipy BFGS through its logp / dlogp), -> tests/golden/reference_c1_find_map.json."""
+    from g3py_b200 import workloads
+    x, y = workloads.c1_inputs()
+    gp = g3.GP(x, g3.Bias(), g3.SE(x))
+    gp.observed(x, y)
+    names = [m.var for m in gp.active.bijection.ordering.vmap]
+    p0 = gp.params
+    th0 = gp.active.dict_to_array(p0)
+    pm_ = gp.find_MAP(start=None, points=1, display=False, plot=False, powell=False)
+    thm = gp.active.dict_to_array(pm_)
+    rec = dict(names=names, theta_default=th0.tolist(), logp_default=float(gp.logp(th0, array=True)),
+               dlogp_default=np.asarray(gp.dlogp(th0, array=True)).tolist(),
+               theta_map=thm.tolist(), logp_map=float(gp.logp(thm, array=True)),
+               dlogp_map=np.asarray(gp.dlogp(thm, array=True)).tolist())
+    with open(os.path.join(HERE, 'reference_c1_find_map.json'), 'w') as f:
+        json.dump(rec, f, indent=1)
+    print('C1 find_MAP (reference): logp %.6f -> %.6f, theta_MAP %s' % (rec['logp_default'], rec['logp_map'], thm))
+
+
 def main():
     g3 = _import_reference()
     shim_self_check(g3)
+    c1_find_map(g3)
     from oracle import g3_oracle as orc     # only for the neutral layout (names / order), not for any value
     out = {}
     for cname, case in CASES.items():

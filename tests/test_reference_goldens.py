@@ -247,6 +247,37 @@ def _check_logpredictive(name):
 
 
 LOGPRED = [c for c in POST_PD if "logpredictive" in REF[c]]
+C1MAP = json.load(open(os.path.join(HERE, "golden", "reference_c1_find_map.json")))
+
+
+def _check_c1_find_map():
+    """BASELINE config 1 at full size (N=200 tutorial example): the reference's default hypers, logp / dlogp there, and
+    the optimum its own find_MAP (scipy BFGS through its logp / dlogp) reached."""
+    import g3py_b200 as g3
+    from g3py_b200 import workloads
+    x, y = workloads.c1_inputs()
+    gp = g3.GP(x, g3.Bias(), g3.SE(x))
+    gp.observed(x, y)
+    assert [h.tname for h in gp.registry.vars] == C1MAP["names"]
+    th0, thm = np.array(C1MAP["theta_default"]), np.array(C1MAP["theta_map"])
+    # params_default of the reference is float32-rounded (hypers/__init__.py:12-16); ours is the unrounded value
+    assert np.allclose(gp.dict_to_array(gp.params_default), th0, rtol=3e-7, atol=1e-7)
+    for th, lp, g in ((th0, C1MAP["logp_default"], C1MAP["dlogp_default"]), (thm, C1MAP["logp_map"], C1MAP["dlogp_map"])):
+        assert _rel(gp.logp(th, array=True), lp) < TOL
+        assert np.max(np.abs(gp.dlogp(th, array=True) - np.array(g))) < TOL * max(np.max(np.abs(C1MAP["dlogp_default"])), 1.0)
+    best = gp.dict_to_array(gp.find_MAP(start=gp.array_to_dict(th0)))
+    assert gp.logp(best, array=True) >= C1MAP["logp_map"] - 1e-6 * abs(C1MAP["logp_map"])   # same optimum (or better)
+    assert np.max(np.abs(best - thm)) < 1e-3
+
+
+def test_oracle_matches_reference_at_c1_default_and_map():
+    from g3py_b200 import workloads
+    x, y = workloads.c1_inputs()
+    op = orc.OracleProcess({"kind": "gauss", "location": {"type": "Bias"}, "kernel": {"type": "SE"}}, 1)
+    for key in ("default", "map"):
+        th = np.array(C1MAP["theta_" + key])
+        assert _rel(op.logp(th, x, y), C1MAP["logp_" + key]) < 1e-12
+        assert np.max(np.abs(op.dlogp(th, x, y) - np.array(C1MAP["dlogp_" + key]))) < 1e-9
 
 
 @pytest.fixture
@@ -289,6 +320,15 @@ def test_host_gram_matches_reference(fake, name):
 @pytest.mark.parametrize("name", LOGPRED)
 def test_host_logpredictive_matches_reference(fake, name):
     _check_logpredictive(name)
+
+
+def test_host_c1_find_map_matches_reference(fake):
+    _check_c1_find_map()
+
+
+@pytest.mark.gpu
+def test_cuda_c1_find_map_matches_reference():
+    _check_c1_find_map()
 
 
 @pytest.mark.gpu
