@@ -326,10 +326,66 @@ def c1_find_map(g3):
     print('C1 find_MAP (reference): logp %.6f -> %.6f, theta_MAP %s' % (rec['logp_default'], rec['logp_map'], thm))
 
 
+def fullsize(g3):
+    """BASELINE configs 2 and 3 at FULL size from the executed reference (inputs are the seeded generators of
+    g3py_b200/workloads.py, so only theta and the outputs are stored) -> tests/golden/reference_fullsize.json."""
+    import time
+    import pymc3 as pm
+    from g3py_b200 import workloads
+    out = {}
+
+    def grads_by_name(proc, th):
+        wrt = pm.inputvars(pm.cont_inputs(proc.th_logp()))
+        flat = np.asarray(proc.dlogp(th, array=True), dtype=np.float64)
+        off, d = 0, {}
+        for v in wrt:
+            size = int(np.prod(np.shape(v.tag.test_value)))
+            d[v.name] = flat[off:off + size].tolist()
+            off += size
+        return d
+
+    # config 2: GP Bias + SE + MAT52 (ARD, D=3) + noise, N=4096, first two rows of the 64-sample theta batch
+    t0 = time.time()
+    X, y, Theta = workloads.c2_inputs(4096, 64)
+    gp = g3.GP(X, g3.Bias(), g3.SE(X) + g3.MAT52(X))
+    gp.observed(X, y)
+    names = [m.var for m in gp.active.bijection.ordering.vmap]
+    rows = []
+    for b in (0, 1):
+        rows.append(dict(b=b, theta=Theta[b].tolist(), logp=float(gp.logp(Theta[b], array=True)),
+                         dlogp=grads_by_name(gp, Theta[b])))
+    out['C2'] = dict(N=4096, names=names, rows=rows)
+    print('C2 full size: logp', [r['logp'] for r in rows], '%.0f s' % (time.time() - t0))
+    # config 3: warped GP, periodic x SE, BoxCoxShifted, N=2048; posterior on 64 of the 10k test points
+    t0 = time.time()
+    x, y, xs = workloads.c3_inputs(2048, 10000)
+    wgp = g3.WGP(x, g3.Bias(), g3.SIN(x) * g3.SE(x), g3.BoxCoxShifted())
+    wgp.observed(x, y)
+    names = [m.var for m in wgp.active.bijection.ordering.vmap]
+    th = wgp.active.dict_to_array(wgp.params)
+    lay = {n: i for i, n in enumerate(names)}
+    th[lay['WGP_SIN_rate_log__']] = np.log(0.01)
+    th[lay['WGP_SIN_freq_log__']] = np.log(0.2)
+    th[lay['WGP_BoxShift_power_log__']] = np.log(0.7)
+    sel = np.arange(0, 10000, 157)[:64]
+    kw = dict(params=wgp.active.array_to_dict(th), space=xs[sel], inputs=x, outputs=y)
+    out['C3'] = dict(N=2048, names=names, theta=th.tolist(), space_index=sel.tolist(),
+                     logp=float(wgp.logp(th, array=True)), dlogp=grads_by_name(wgp, th),
+                     location=np.asarray(wgp.location(prior=False, noise=False, **kw)).tolist(),
+                     kernel_diag=np.asarray(wgp.kernel_diag(prior=False, noise=False, **kw)).tolist(),
+                     mean=np.asarray(wgp.mean(prior=False, noise=False, **kw)).tolist(),
+                     variance=np.asarray(wgp.variance(prior=False, noise=False, **kw)).tolist())
+    print('C3 full size: logp', out['C3']['logp'], '%.0f s' % (time.time() - t0))
+    with open(os.path.join(HERE, 'reference_fullsize.json'), 'w') as f:
+        json.dump(out, f)
+
+
 def main():
     g3 = _import_reference()
     shim_self_check(g3)
     c1_find_map(g3)
+    if '--no-fullsize' not in sys.argv:
+        fullsize(g3)
     from oracle import g3_oracle as orc     # only for the neutral layout (names / order), not for any value
     out = {}
     for cname, case in CASES.items():

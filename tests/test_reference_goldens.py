@@ -270,6 +270,91 @@ def _check_c1_find_map():
     assert np.max(np.abs(best - thm)) < 1e-3
 
 
+FULL = json.load(open(os.path.join(HERE, "golden", "reference_fullsize.json")))
+C2_SPEC = {"kind": "gauss", "location": {"type": "Bias"}, "kernel": {"type": "sum", "k1": {"type": "SE"}, "k2": {"type": "MAT52"}}}
+C3_SPEC = {"kind": "gauss", "warped": True, "location": {"type": "Bias"},
+           "kernel": {"type": "prod", "k1": {"type": "SIN"}, "k2": {"type": "SE"}}, "mapping": {"type": "BoxCoxShifted"}}
+
+
+def _by_name(d, names, sizes):
+    return np.concatenate([np.asarray(d.get(n, [0.0] * s), dtype=np.float64) for n, s in zip(names, sizes)])
+
+
+def _check_fullsize_c2():
+    """BASELINE config 2 at FULL size (N=4096, D=3): two rows of the benchmark's own theta batch against the
+    reference executed at that size (logp 1e-9; gradient 1e-9 except the Matern rates the reference zeroes)."""
+    import g3py_b200 as g3
+    from g3py_b200 import workloads
+    X, y, Theta = workloads.c2_inputs(4096, 64)
+    gp = g3.GP(X, g3.Bias(), g3.SE(X) + g3.MAT52(X))
+    gp.observed(X, y)
+    rec = FULL["C2"]
+    assert [h.tname for h in gp.registry.vars] == rec["names"]
+    sizes = [h.size for h in gp.registry.vars]
+    rows = rec["rows"]
+    Th = np.array([r["theta"] for r in rows])
+    assert np.array_equal(Th, Theta[[r["b"] for r in rows]])
+    lp, g, info = gp.logp_dlogp_batch(Th, reference_nan_quirk=True)
+    for i, r in enumerate(rows):
+        assert _rel(lp[i], r["logp"]) < TOL
+        assert scaled_err(g[i], _by_name(r["dlogp"], rec["names"], sizes)) < TOL
+
+
+def _check_fullsize_c3():
+    """BASELINE config 3 at FULL size (N=2048 warped GP, periodic x SE): logp, gradient and posterior moments at 64 of
+    the 10 000 test points against the reference executed at that size."""
+    import g3py_b200 as g3
+    from g3py_b200 import workloads
+    x, y, xs = workloads.c3_inputs(2048, 10000)
+    gp = g3.WGP(x, g3.Bias(), g3.SIN(x) * g3.SE(x), g3.BoxCoxShifted())
+    gp.observed(x, y)
+    rec = FULL["C3"]
+    assert [h.tname for h in gp.registry.vars] == rec["names"]
+    sizes = [h.size for h in gp.registry.vars]
+    th = np.array(rec["theta"])
+    assert _rel(gp.logp(th, array=True), rec["logp"]) < TOL
+    assert scaled_err(gp.dlogp(th, array=True, reference_nan_quirk=True), _by_name(rec["dlogp"], rec["names"], sizes)) < TOL
+    Xs = xs[np.array(rec["space_index"])]
+    kw = dict(space=Xs, array=True, noise=False)
+    assert scaled_err(gp.location(th, **kw), rec["location"]) < 1e-8
+    assert scaled_err(gp.kernel_diag(th, **kw), rec["kernel_diag"]) < 1e-6      # LU (reference) vs Cholesky, kappa ~ 1e5
+    out = gp.predict(th, mean=True, var=True, **kw)
+    assert scaled_err(out["mean"], rec["mean"]) < 1e-8
+    assert scaled_err(out["variance"], rec["variance"]) < 1e-6
+
+
+def test_oracle_matches_reference_at_full_size():
+    from g3py_b200 import workloads
+    X, y, Theta = workloads.c2_inputs(4096, 64)
+    op = orc.OracleProcess(C2_SPEC, 3)
+    rec = FULL["C2"]
+    sizes = [l[1] for l in op.layout()]
+    r = rec["rows"][0]
+    th = np.array(r["theta"])
+    assert _rel(op.logp(th, X, y), r["logp"]) < 1e-11
+    assert scaled_err(op.dlogp(th, X, y, nan_quirk=True), _by_name(r["dlogp"], rec["names"], sizes)) < 1e-9
+    x, y3, xs = workloads.c3_inputs(2048, 10000)
+    op3 = orc.OracleProcess(C3_SPEC, 1)
+    rec3 = FULL["C3"]
+    th3 = np.array(rec3["theta"])
+    assert _rel(op3.logp(th3, x, y3), rec3["logp"]) < 1e-11
+    assert scaled_err(op3.dlogp(th3, x, y3, nan_quirk=True),
+                      _by_name(rec3["dlogp"], rec3["names"], [l[1] for l in op3.layout()])) < 1e-9
+    po = op3.posterior(th3, xs[np.array(rec3["space_index"])], x, y3, noise=False, solver="lu")
+    assert scaled_err(po["location"], rec3["location"]) < 1e-9
+    assert scaled_err(po["kernel_diag"], rec3["kernel_diag"]) < 1e-7
+
+
+@pytest.mark.gpu
+def test_cuda_matches_reference_at_full_size_c2():
+    _check_fullsize_c2()
+
+
+@pytest.mark.gpu
+def test_cuda_matches_reference_at_full_size_c3():
+    _check_fullsize_c3()
+
+
 def test_oracle_matches_reference_at_c1_default_and_map():
     from g3py_b200 import workloads
     x, y = workloads.c1_inputs()
