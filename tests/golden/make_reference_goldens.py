@@ -376,6 +376,25 @@ def fullsize(g3):
                      mean=np.asarray(wgp.mean(prior=False, noise=False, **kw)).tolist(),
                      variance=np.asarray(wgp.variance(prior=False, noise=False, **kw)).tolist())
     print('C3 full size: logp', out['C3']['logp'], '%.0f s' % (time.time() - t0))
+    # config 4 (Student-t process, SE ARD, D=5) at N=4096 -- the reference's N x N x D metric tensor makes N=16384
+    # (10.7 GB, plus autodiff copies) impractical here; same generator, first 4096 rows
+    t0 = time.time()
+    X4, y4, Xs4 = workloads.c4_inputs(16384, 4096)
+    X4, y4, Xs4 = X4[:4096], y4[:4096], Xs4[:32]
+    tp = g3.TP(X4, g3.Bias(), g3.SE(X4))
+    tp.observed(X4, y4)
+    names = [m.var for m in tp.active.bijection.ordering.vmap]
+    th = tp.active.dict_to_array(tp.params)
+    lay = {n: i for i, n in enumerate(names)}
+    th[lay['TP_Freedom_degree_log__']] = np.log(5.0)
+    th[lay['TP_Noise_var_log__']] = np.log(0.05)
+    kw = dict(params=tp.active.array_to_dict(th), space=Xs4, inputs=X4, outputs=y4)
+    out['C4_4096'] = dict(N=4096, names=names, theta=th.tolist(), logp=float(tp.logp(th, array=True)),
+                          dlogp=grads_by_name(tp, th),
+                          location=np.asarray(tp.location(prior=False, noise=True, **kw)).tolist(),
+                          variance=np.asarray(tp.variance(prior=False, noise=True, **kw)).tolist(),
+                          quantile_up=np.asarray(tp.quantiler(q=0.975, prior=False, noise=True, **kw)).tolist())
+    print('C4 at N=4096: logp', out['C4_4096']['logp'], '%.0f s' % (time.time() - t0))
     with open(os.path.join(HERE, 'reference_fullsize.json'), 'w') as f:
         json.dump(out, f)
 

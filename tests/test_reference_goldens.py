@@ -323,6 +323,45 @@ def _check_fullsize_c3():
     assert scaled_err(out["variance"], rec["variance"]) < 1e-6
 
 
+def _check_c4_4096():
+    """BASELINE config 4 (Student-t process, SE ARD on D=5) on the first 4096 rows of its generator: logp, gradient,
+    predictive location / variance (with the t scaling) / quantile against the reference executed at that size."""
+    import g3py_b200 as g3
+    from g3py_b200 import workloads
+    X, y, Xs = workloads.c4_inputs(16384, 4096)
+    X, y, Xs = X[:4096], y[:4096], Xs[:32]
+    gp = g3.TP(X, g3.Bias(), g3.SE(X))
+    gp.observed(X, y)
+    rec = FULL["C4_4096"]
+    assert [h.tname for h in gp.registry.vars] == rec["names"]
+    th = np.array(rec["theta"])
+    assert _rel(gp.logp(th, array=True), rec["logp"]) < TOL
+    assert scaled_err(gp.dlogp(th, array=True), _by_name(rec["dlogp"], rec["names"], [h.size for h in gp.registry.vars])) < TOL
+    kw = dict(space=Xs, array=True, noise=True)
+    assert scaled_err(gp.location(th, **kw), rec["location"]) < 1e-8
+    assert scaled_err(gp.variance(th, **kw), rec["variance"]) < 1e-7
+    assert scaled_err(gp.quantiler(th, q=0.975, **kw), rec["quantile_up"]) < 1e-8
+
+
+def test_host_c4_4096_oracle_matches_reference():
+    from g3py_b200 import workloads
+    X, y, Xs = workloads.c4_inputs(16384, 4096)
+    X, y, Xs = X[:4096], y[:4096], Xs[:32]
+    op = orc.OracleProcess({"kind": "student", "location": {"type": "Bias"}, "kernel": {"type": "SE"}}, 5)
+    rec = FULL["C4_4096"]
+    th = np.array(rec["theta"])
+    assert _rel(op.logp(th, X, y), rec["logp"]) < 1e-11
+    assert scaled_err(op.dlogp(th, X, y), _by_name(rec["dlogp"], rec["names"], [l[1] for l in op.layout()])) < 1e-9
+    pr = op.predict(th, Xs, X, y, noise=True)
+    assert scaled_err(pr["variance"], rec["variance"]) < 1e-8
+    assert scaled_err(pr["quantile_up"], rec["quantile_up"]) < 1e-9
+
+
+@pytest.mark.gpu
+def test_cuda_matches_reference_c4_at_4096():
+    _check_c4_4096()
+
+
 def test_oracle_matches_reference_at_full_size():
     from g3py_b200 import workloads
     X, y, Theta = workloads.c2_inputs(4096, 64)
