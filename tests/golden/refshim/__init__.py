@@ -231,7 +231,8 @@ def install():
     sandbox_linalg = _mod('theano.sandbox.linalg', det=_Dummy())
     sandbox = _mod('theano.sandbox', linalg=sandbox_linalg)
 
-    th = _mod('theano', tensor=tt, ifelse=ife, gof=gof, printing=printing, scan_module=scan_module,
+    gradient = _mod('theano.gradient', DisconnectedType=lazy.DisconnectedType, grad_undefined=lazy.grad_undefined)
+    th = _mod('theano', tensor=tt, ifelse=ife, gof=gof, printing=printing, scan_module=scan_module, gradient=gradient,
               sandbox=sandbox, config=config, shared=lazy.shared, function=lazy.Function, scan=lazy.scan,
               In=_Dummy, __version__='shim-1.0 (torch %s)' % torch.__version__, _g3b_shim=True)
     th.__path__ = []

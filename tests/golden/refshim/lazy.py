@@ -118,8 +118,11 @@ def evaluate(node, env):
     elif node.kind == 'scan':
         t = _run_scan(node, env)
     elif node.kind == 'opout':
-        xs = [evaluate(a, env) for a in node.apply.inputs]
-        t = _run_op(node.apply, xs)
+        akey = ('apply', id(node.apply))
+        if akey not in memo:                          # all outputs of one Apply come from a single perform()
+            xs = [evaluate(a, env) for a in node.apply.inputs]
+            memo[akey] = _run_op(node.apply, xs)
+        t = memo[akey][node.out_index]
     else:
         raise RuntimeError(node.kind)
     memo[key] = t
@@ -533,37 +536,60 @@ class Apply:
         self.outputs = list(outputs)
 
 
+class DisconnectedType:
+    """theano.gradient.DisconnectedType: `DisconnectedType()()` marks an input no gradient flows to."""
+
+    def __call__(self):
+        return self
+
+
+class _Undefined:
+    pass
+
+
+def grad_undefined(op, x_pos, x, comment=''):
+    return _Undefined()
+
+
 class Op:
-    """theano.gof.Op protocol: make_node / perform / grad (single-output Ops)."""
+    """theano.gof.Op protocol: make_node / perform / grad; one or several outputs."""
 
     def __call__(self, *inputs):
         node = self.make_node(*inputs)
-        assert len(node.outputs) == 1, 'shim supports single-output Ops'
-        out = node.outputs[0]
-        out.kind = 'opout'
-        out.apply = node
-        return out
+        for i, out in enumerate(node.outputs):
+            out.kind = 'opout'
+            out.apply = node
+            out.out_index = i
+        return node.outputs[0] if len(node.outputs) == 1 else list(node.outputs)
 
 
 class _OpFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, apply, *xs):
-        storage = [[None]]
+        storage = [[None] for _ in apply.outputs]
         apply.op.perform(apply, [x.detach().numpy() for x in xs], storage)
         ctx.g3_node = apply
         ctx.save_for_backward(*xs)
-        return torch.from_numpy(np.array(storage[0][0], copy=True))
+        outs = tuple(torch.from_numpy(np.array(s[0], copy=True)) for s in storage)
+        return outs
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, *gs):
         xs = ctx.saved_tensors
         with torch.enable_grad():
             xin = [constant(x.detach()) for x in xs]
-            gin = [constant(g.detach())]
-            gs = ctx.g3_node.op.grad(xin, gin)
-            vals = [evaluate(v, _new_env()).detach() if v is not None else None for v in gs]
+            gin = [constant(torch.zeros(()) if g is None else g.detach()) for g in gs]
+            grads = ctx.g3_node.op.grad(xin, gin)
+            vals = []
+            for x, v in zip(xs, grads):
+                if v is None or isinstance(v, (DisconnectedType, _Undefined)):
+                    vals.append(None)
+                else:
+                    t = evaluate(v, _new_env())
+                    t = t if isinstance(t, torch.Tensor) else torch.tensor(t)
+                    vals.append(t.detach().to(x.dtype).reshape(x.shape) if x.is_floating_point() else None)
         return (None, *vals)
 
 
 def _run_op(apply, xs):
-    return _OpFunction.apply(apply, *xs)
+    return _OpFunction.apply(apply, *xs)              # tuple, one tensor per output

@@ -1,0 +1,124 @@
+"""INTEGRATION.md section 3 executed: the Op classes of g3py_b200/theano_ops.py spliced into the graph of the UNMODIFIED
+reference (its own hyper-parameter variables, mean, warping, shared data), compiled with `theano.function` and
+differentiated with `tt.grad` — all through the Theano/PyMC3 stand-in of tests/golden/refshim.  The fused GPLogpOp must
+reproduce the reference's own logp and dlogp, with the gradient reaching the mean / warping hypers through `delta` and
+`det_m` (plain Theano expressions) and the kernel hypers through GPLogpOp.grad -> GPLogpGradOp.
+
+Needs the reference tree (/root/reference, present in the build container only) and no GPU: the device is the NumPy
+double of tests/fake_ctx.py.  Skipped where the reference is absent."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/g3py"), reason="reference tree not available")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    import torch
+    prev = torch.get_default_dtype()
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import refshim
+    import make_reference_goldens as mr
+    g3ref = mr._import_reference()
+    yield g3ref
+    torch.set_default_dtype(prev)
+    refshim.uninstall()
+    for name in [n for n in sys.modules if n == "g3py" or n.startswith("g3py.")]:
+        del sys.modules[name]
+    sys.path[:] = [p for p in sys.path if p != "/root/reference"]
+
+
+@pytest.fixture
+def fake(monkeypatch):
+    import g3py_b200 as g3
+    from fake_ctx import FakeContext
+    ctx = FakeContext()
+    monkeypatch.setattr(g3.processes, "get_context", lambda device=0: ctx)
+    return ctx
+
+
+CASES = {
+    "gp_se_mat52": ("GP", "Bias", lambda g, X: g.SE(X) + g.MAT52(X), None),
+    "wgp_boxcox_rq": ("WGP", "Linear", lambda g, X: g.RQ(X) * g.SE(X, name="SE2"), "BoxCoxShifted"),
+    "tp_ou": ("TP", "Bias", lambda g, X: g.OU(X), None),
+}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_fused_op_inside_the_reference_graph(ref, fake, case):
+    import theano as th
+    import theano.tensor as tt
+    import pymc3 as pm
+    import g3py_b200 as g3
+    from g3py_b200 import _cabi as cabi, theano_ops
+    from helpers import scaled_err
+
+    cls, mean, kern, mapping = CASES[case]
+    rng = np.random.default_rng(3)
+    N, D = 40, 2
+    X = rng.uniform(0.2, 4.0, size=(N, D))
+    y = np.sin(X[:, 0]) + 0.3 * X[:, 1] + 0.1 * rng.standard_normal(N)
+    if mapping:
+        y = np.exp(0.4 * y) + 0.3
+    # ---- the reference process (its own graph objects) and the product-side process (descriptor + slot order)
+    rargs = [X, getattr(ref, mean)(X), kern(ref, X)] + ([getattr(ref, mapping)()] if mapping else [])
+    rp = getattr(ref, cls)(*rargs)
+    rp.observed(X, y)
+    pargs = [X, getattr(g3, mean)(X), kern(g3, X)] + ([getattr(g3, mapping)()] if mapping else [])
+    pp = getattr(g3, cls)(*pargs)
+    pp.observed(X, y)
+    names = [m.var for m in rp.active.bijection.ordering.vmap]
+    assert [h.tname for h in pp.registry.vars] == names
+    th0 = pp.dict_to_array(pp.params_default) + 0.05 * rng.standard_normal(pp.ndim)
+    if cls == "TP":
+        th0[-1] = np.log(4.0)
+
+    # ---- delta and det_m stay Theano expressions, the kernel part is one fused Op
+    ops = theano_ops.build_ops()
+    model = rp.model
+    theta_k = tt.concatenate([tt.flatten(model[h.name]) if h is not None else tt.as_tensor_variable(np.asarray(c, dtype=np.float64))
+                              for h, off, size, c in pp._slots])          # natural space, descriptor slot order
+    delta = rp.f_mapping.inv(rp.th_outputs) - rp.prior_location_inputs
+    det_m = rp.f_mapping.logdet_dinv(rp.th_outputs)
+    n = rp.th_outputs.shape[0].astype("float64")
+    if cls == "TP":
+        nu = rp.th_freedom(prior=True)
+        core, beta, logdet = ops.GPLogpOp(pp.desc, cabi.KIND_STUDENT)(rp.th_inputs, delta, theta_k, nu)
+        np5, np2, npi = np.float32(0.5), np.float32(2.0), np.float32(np.pi)
+        r2 = tt.gammaln((nu + n) * np5) - tt.gammaln(nu * np5) - np5 * n * tt.log((nu - np2) * npi)   # studentT.py:128
+        loglike = core + r2 + det_m
+    else:
+        core, beta, logdet = ops.GPLogpOp(pp.desc, cabi.KIND_GAUSS)(rp.th_inputs, delta, theta_k)
+        loglike = np.float32(-0.5) * n * tt.log(np.float32(2.0 * np.pi)) + core + det_m             # gaussian.py:218
+    prior = tt.add(*[tt.sum(v.logpt) for v in model.free_RVs])
+    logp = loglike + prior
+    free = list(model.vars)
+    fn = th.function(free, [logp] + [tt.grad(logp, v) for v in free])
+    vals = fn(**rp.active.array_to_dict(th0))
+    got_lp = float(vals[0])
+    got_g = np.concatenate([np.atleast_1d(np.asarray(v, dtype=np.float64)).ravel() for v in vals[1:]])
+
+    # ---- against the reference's own compiled logp / dlogp (per variable name: its order is traversal order)
+    want_lp = float(rp.logp(th0, array=True))
+    wrt = pm.inputvars(pm.cont_inputs(rp.th_logp()))
+    flat = np.asarray(rp.dlogp(th0, array=True), dtype=np.float64)
+    off, by_name = 0, {}
+    for v in wrt:
+        size = int(np.prod(np.shape(v.tag.test_value)))
+        by_name[v.name] = flat[off:off + size]
+        off += size
+    want_g = np.concatenate([by_name.get(v.name, np.zeros(int(np.prod(np.shape(v.tag.test_value))))) for v in free])
+    assert abs(got_lp - want_lp) <= 1e-10 * abs(want_lp)
+    # Matern rates: the reference's autodiff loses them to NaN -> 0, the fused Op returns the analytic value
+    quirk = np.concatenate([np.full(int(np.prod(np.shape(v.tag.test_value))), ("MAT32_rate" in v.name) or ("MAT52_rate" in v.name))
+                            for v in free])
+    assert scaled_err(got_g[~quirk], want_g[~quirk]) < 1e-9
+    if quirk.any():
+        assert np.all(want_g[quirk] == 0.0) and np.all(got_g[quirk] != 0.0)
+    # and the same numbers as the product's own front end
+    assert abs(pp.logp(th0, array=True) - got_lp) <= 1e-10 * abs(got_lp)
+    assert scaled_err(pp.dlogp(th0, array=True), got_g) < 1e-9
