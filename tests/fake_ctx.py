@@ -132,6 +132,19 @@ class FakeContext:
         X2 = X1 if same else np.asarray(X2, dtype=np.float64)
         return np.stack([_eval_desc(desc, t, X1, X2, same) for t in theta]), np.zeros(len(theta), dtype=np.int32)
 
+    def gram_vjp(self, desc, X1, X2, theta, W):
+        theta = np.atleast_2d(theta)
+        same = X2 is None
+        X1 = np.asarray(X1, dtype=np.float64)
+        X2 = X1 if same else np.asarray(X2, dtype=np.float64)
+        W = np.asarray(W, dtype=np.float64).reshape(len(theta), X1.shape[0], X2.shape[0])
+        out = np.zeros((len(theta), desc.n_theta))
+        for b, t in enumerate(theta):
+            _, dK = _eval_desc(desc, t, X1, X2, same, grad=True)
+            for i, g in dK.items():
+                out[b, i] = np.sum(W[b] * g)
+        return out
+
     def potrf_robust(self, A):
         from oracle import g3_oracle as orc
         L, info = orc.cholesky_robust(np.asarray(A, dtype=np.float64), return_info=True)

@@ -122,3 +122,53 @@ def test_fused_op_inside_the_reference_graph(ref, fake, case):
     # and the same numbers as the product's own front end
     assert abs(pp.logp(th0, array=True) - got_lp) <= 1e-10 * abs(got_lp)
     assert scaled_err(pp.dlogp(th0, array=True), got_g) < 1e-9
+
+
+def test_gram_and_posterior_ops_inside_the_reference_graph(ref, fake):
+    """GramOp (+ its gradient through GramVJPOp) against the reference's own `Kernel.cov` expression and its Theano
+    gradient, and GPPosteriorOp against the reference's posterior selectors, inside the same graph."""
+    import theano as th
+    import theano.tensor as tt
+    import g3py_b200 as g3
+    from g3py_b200 import theano_ops
+    from helpers import scaled_err
+
+    rng = np.random.default_rng(5)
+    N, M, D = 30, 9, 2
+    X = rng.uniform(0.2, 4.0, size=(N, D))
+    Xs = rng.uniform(0.2, 4.0, size=(M, D))
+    y = np.sin(X[:, 0]) + 0.3 * X[:, 1] + 0.1 * rng.standard_normal(N)
+    rp = ref.GP(X, ref.Bias(X), ref.SE(X) + ref.RQ(X))
+    rp.observed(X, y)
+    pp = g3.GP(X, g3.Bias(X), g3.SE(X) + g3.RQ(X))
+    pp.observed(X, y)
+    th0 = pp.dict_to_array(pp.params_default) + 0.05 * rng.standard_normal(pp.ndim)
+    params = rp.active.array_to_dict(th0)
+    ops = theano_ops.build_ops()
+    model = rp.model
+    free = list(model.vars)
+
+    def slots(sl):
+        return tt.concatenate([tt.flatten(model[h.name]) if h is not None else tt.as_tensor_variable(np.asarray(c, dtype=np.float64))
+                               for h, off, size, c in sl])
+    # ---- Gram: f_kernel.cov(space, inputs) and d/dtheta of a weighted sum of its entries
+    W = rng.standard_normal((M, N))
+    xs_var, x_var = th.shared(Xs, name="xs"), th.shared(X, name="x")
+    K_op = ops.GramOp(pp.desc_f)(xs_var, x_var, slots(pp._slots_f))
+    K_ref = rp.f_kernel.cov(xs_var, x_var)
+    outs = []
+    for Kx in (K_op, K_ref):
+        s = tt.sum(Kx * W)
+        outs.append(th.function(free, [Kx] + [tt.grad(s, v) for v in free])(**params))
+    assert scaled_err(outs[0][0], outs[1][0]) < 1e-13
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert scaled_err(np.atleast_1d(a), np.atleast_1d(b)) < 1e-11 or (np.max(np.abs(b)) == 0 and np.max(np.abs(a)) == 0)
+    # ---- posterior: location - m(X*) and variance from one Op against the reference's selectors
+    delta = rp.f_mapping.inv(rp.th_outputs) - rp.prior_location_inputs
+    for noise in (False, True):
+        mean, var = ops.GPPosteriorOp(pp.desc, noise)(rp.th_inputs, xs_var, delta, slots(pp._slots))
+        got_m, got_v = th.function(free, [mean, var])(**params)
+        kw = dict(params=params, space=Xs, inputs=X, outputs=y, prior=False, noise=noise)
+        want_loc = np.asarray(rp.location(**kw)) - np.asarray(rp.location(params=params, space=Xs, inputs=X, outputs=y, prior=True))
+        assert scaled_err(got_m, want_loc) < 1e-9
+        assert scaled_err(got_v, rp.kernel_diag(**kw)) < 1e-8
