@@ -172,3 +172,32 @@ def test_gram_and_posterior_ops_inside_the_reference_graph(ref, fake):
         want_loc = np.asarray(rp.location(**kw)) - np.asarray(rp.location(params=params, space=Xs, inputs=X, outputs=y, prior=True))
         assert scaled_err(got_m, want_loc) < 1e-9
         assert scaled_err(got_v, rp.kernel_diag(**kw)) < 1e-8
+
+
+def test_cholesky_robust_gpu_replaces_the_bare_factor(ref, fake, monkeypatch):
+    """CholeskyRobustGPU in place of `cholesky_robust` for the non-differentiated
+    selectors (`th_cholesky`: the factors the samplers use).  Patched into the reference's elliptical module before the
+    process is built, it must return the factor the reference's own Op returns - also through the jitter ladder."""
+    import g3py_b200  # noqa: F401
+    from g3py_b200 import theano_ops
+    from helpers import scaled_err
+    import g3py.processes.elliptical as ell
+
+    rng = np.random.default_rng(7)
+    X = rng.uniform(0.2, 4.0, size=(25, 1))
+    X[1::2] = X[0::2][:12]                               # duplicated inputs: the noise-free prior Gram is singular
+    y = np.sin(X[:, 0]) + 0.1 * rng.standard_normal(25)
+    Xs = np.vstack([X[:6], X[:6]])                       # singular on `space` too -> ladder inside the selector
+    want = {}
+    for patched in (False, True):
+        if patched:
+            monkeypatch.setattr(ell, "cholesky_robust", theano_ops.build_ops().CholeskyRobustGPU())
+        rp = ref.GP(X, ref.Bias(X), ref.SE(X))
+        rp.observed(X, y)
+        for noise in (True, False):
+            L = np.asarray(rp.cholesky(space=Xs, prior=True, noise=noise))
+            if not patched:
+                want[noise] = L
+            else:
+                assert scaled_err(L, want[noise]) < 1e-12
+                assert np.allclose(L @ L.T, np.asarray(rp.kernel(space=Xs, prior=True, noise=noise)), atol=1e-4)
