@@ -36,6 +36,7 @@ def _import_reference():
     refshim.install()
     import torch
     torch.set_default_dtype(torch.float64)
+    sys.dont_write_bytecode = True          # never write __pycache__ into the (read-only by contract) reference tree
     sys.path.insert(0, '/root/reference')
     import g3py as g3
     import theano as th
