@@ -45,6 +45,13 @@ class Mapping(Hypers):
         """d inv / d y (n,), needed to chain composed maps."""
         raise NotImplementedError
 
+    def dlog_dinv_dy(self, y, p):
+        """d/dy log|d inv / d y| (n,): how the log-Jacobian of this map reacts to a shift of its argument (needed when
+        another map feeds it).  Closed forms in the subclasses; this default is a 4th-order central difference."""
+        h = 1e-4 * np.maximum(1.0, np.abs(y))
+        f = lambda t: np.log(np.abs(self.dinv_dy(t, p)))
+        return (-f(y + 2 * h) + 8 * f(y + h) - 8 * f(y - h) + f(y - 2 * h)) / (12 * h)
+
     def _reg(self, parent, reg, attr, positive):
         h = getattr(self, attr)
         if h is None:
@@ -94,17 +101,18 @@ class MappingComposed(Mapping):      # mappings.py:56-71
         w = self.m1.inv(y, p)
         return self.m2.dinv_dy(w, p) * self.m1.dinv_dy(y, p)
 
+    def dlog_dinv_dy(self, y, p):
+        w = self.m1.inv(y, p)
+        return self.m2.dlog_dinv_dy(w, p) * self.m1.dinv_dy(y, p) + self.m1.dlog_dinv_dy(y, p)
+
     def grads(self, y, p):
-        # numerical hyper-derivatives by 4th-order central differences would hide errors; composed maps use
-        # the chain rule on the pieces: inv = m2.inv(m1.inv(y)), logdet = m2.logdet(m1.inv(y)) + m1.logdet(y)
+        # chain rule on the pieces: inv = m2.inv(w), logdet = m2.logdet(w) + m1.logdet(y), w = m1.inv(y);
+        # m1's hypers move w, which moves m2's value (d m2.inv / d w) and m2's log-Jacobian (d log|d m2.inv/dw| / d w)
         w = self.m1.inv(y, p)
         di1, dl1 = self.m1.grads(y, p)
         di2, dl2 = self.m2.grads(w, p)
         d2dw = self.m2.dinv_dy(w, p)
-        # d logdet2 / d w (n,) by differentiating m2.logdet_dinv = sum log|d inv2/dw|: use finite differences
-        # of dinv_dy (elementwise maps): d/dw log|dinv2/dw|
-        h = 1e-6 * np.maximum(1.0, np.abs(w))
-        dlog = (np.log(np.abs(self.m2.dinv_dy(w + h, p))) - np.log(np.abs(self.m2.dinv_dy(w - h, p)))) / (2 * h)
+        dlog = self.m2.dlog_dinv_dy(w, p)
         dinv = {k: d2dw * v for k, v in di1.items()}
         dld = {k: v + np.sum(dlog * di1[k], axis=-1) for k, v in dl1.items()}
         for k, v in di2.items():
@@ -130,6 +138,9 @@ class Identity(Mapping):             # mappings.py:88-99
     def dinv_dy(self, y, p=None):
         return np.ones_like(y)
 
+    def dlog_dinv_dy(self, y, p=None):
+        return np.zeros_like(y)
+
 
 class LinearMapping(Mapping):        # mappings.py:102-125
     def __init__(self, y=None, name=None, shift=None, scale=None):
@@ -154,6 +165,9 @@ class LinearMapping(Mapping):        # mappings.py:102-125
 
     def dinv_dy(self, y, p):
         return np.ones_like(y) / _v(p, self.scale)
+
+    def dlog_dinv_dy(self, y, p):
+        return np.zeros_like(y)
 
     def grads(self, y, p):
         s = _v(p, self.scale)
@@ -185,6 +199,9 @@ class LogShifted(Mapping):           # mappings.py:128-149
     def dinv_dy(self, y, p):
         return 1.0 / (y - _v(p, self.shift))
 
+    def dlog_dinv_dy(self, y, p):
+        return -1.0 / (y - _v(p, self.shift))
+
     def grads(self, y, p):
         sh = y - _v(p, self.shift)
         live = sh > _F32_1EM32
@@ -208,6 +225,10 @@ class _BoxCox(Mapping):
         shift, scale, power, thr = self._params(p)
         sh = scale * (y + shift)
         return np.abs(sh) ** (power - 1.0) * scale
+
+    def dlog_dinv_dy(self, y, p):
+        shift, scale, power, thr = self._params(p)
+        return (power - 1.0) / (y + shift)
 
     def _grads(self, y, p):
         shift, scale, power, thr = self._params(p)
@@ -310,6 +331,9 @@ class ArcsinhLinear(Mapping):        # mappings.py:309-333
     def dinv_dy(self, y, p):
         return _v(p, self.scale) / np.sqrt(1.0 + y ** 2)
 
+    def dlog_dinv_dy(self, y, p):
+        return -y / (1.0 + y ** 2)
+
     def grads(self, y, p):
         n = float(y.shape[0])
         return ({self.shift: np.ones_like(y), self.scale: np.arcsinh(y)}, {self.shift: 0.0, self.scale: n / _v(p, self.scale)})
@@ -340,6 +364,10 @@ class SinhArcsinh(Mapping):          # mappings.py:336-358
     def dinv_dy(self, y, p):
         w = _v(p, self.shift) + _v(p, self.scale) * np.arcsinh(y)
         return np.cosh(w) * _v(p, self.scale) / np.sqrt(1.0 + y ** 2)
+
+    def dlog_dinv_dy(self, y, p):
+        w = _v(p, self.shift) + _v(p, self.scale) * np.arcsinh(y)
+        return np.tanh(w) * _v(p, self.scale) / np.sqrt(1.0 + y ** 2) - y / (1.0 + y ** 2)
 
     def grads(self, y, p):
         s = _v(p, self.scale)
@@ -388,6 +416,11 @@ class Logistic(Mapping):             # mappings.py:363-397
         q = self._p(y, p)
         with np.errstate(all="ignore"):
             return _tt_to_num(_v(p, self.scale) / (_v(p, self.high) * q * (1 - q)))
+
+    def dlog_dinv_dy(self, y, p):
+        q = self._p(y, p)
+        with np.errstate(all="ignore"):
+            return np.where((q > 0.0) & (q < 1.0), (-1.0 / q + 1.0 / (1.0 - q)) / _v(p, self.high), 0.0)
 
     def grads(self, y, p):
         hi, sc = _v(p, self.high), _v(p, self.scale)
@@ -478,6 +511,11 @@ class WarpingTanh(_NewtonWarping):   # mappings.py:253-278: inv(y) = y + sum_j a
         a, b, c = self._abc(p)
         return 1.0 + np.dot(1.0 / np.cosh(b * (y[:, None] + c)) ** 2, a * b)
 
+    def dlog_dinv_dy(self, y, p):
+        a, b, c = self._abc(p)
+        u = b * (y[:, None] + c)
+        return np.dot(-2.0 / np.cosh(u) ** 2 * np.tanh(u), a * b * b) / self.dinv_dy(y, p)
+
     def _partials(self, y, p):
         a, b, c = self._abc(p)
         yc = y[:, None] + c
@@ -518,6 +556,12 @@ class WarpingBoxCox(_NewtonWarping):  # mappings.py:281-306: inv(y) = sum_j w_j 
         shift, power, w = self._spw(p)
         with np.errstate(all="ignore"):
             return np.dot(np.abs(y[:, None] + shift) ** (power - 1.0), w)
+
+    def dlog_dinv_dy(self, y, p):
+        shift, power, w = self._spw(p)
+        sh = y[:, None] + shift
+        with np.errstate(all="ignore"):
+            return np.dot((power - 1.0) * np.abs(sh) ** (power - 2.0) * np.sign(sh), w) / self.dinv_dy(y, p)
 
     def _partials(self, y, p):
         shift, power, w = self._spw(p)

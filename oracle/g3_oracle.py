@@ -513,6 +513,58 @@ class _Mapping:
         shift, power, w = th[:n], th[n:2 * n], th[2 * n:]
         return np.dot(np.abs(z + shift) ** (power - 1.0), w)
 
+    def dinv_dy(self, th, y):
+        """d inv / d y of every closed form above (composition chains through it)."""
+        k = self.kind
+        if k in ("WarpingTanh", "WarpingBoxCox"):
+            return self._dinv_dy(th, y)
+        if k == "Identity":
+            return np.ones_like(y)
+        if k == "LinearMapping":
+            return np.ones_like(y) / th[1]
+        if k == "LogShifted":
+            return 1.0 / (y - th[0])
+        if k == "BoxCoxShifted":
+            return np.abs(y + th[0]) ** (th[1] - 1.0)
+        if k == "BoxCoxLinear":
+            return th[1] * np.abs(th[1] * (y + th[0])) ** (th[2] - 1.0)
+        if k == "ArcsinhLinear":
+            return th[1] / np.sqrt(1.0 + y * y)
+        if k == "SinhArcsinh":
+            return np.cosh(th[0] + th[1] * np.arcsinh(y)) * th[1] / np.sqrt(1.0 + y * y)
+        if k == "Logistic":
+            p = (y - th[0]) / th[1]
+            return th[3] / (th[1] * p * (1 - p))
+        raise ValueError(k)
+
+    def dlog_dinv_dy(self, th, y):
+        """d/dy log|d inv / d y|: the per-point slope of the log-Jacobian (the term a composed map needs when an inner
+        map's hypers move the argument of the outer one)."""
+        k = self.kind
+        if k in ("Identity", "LinearMapping"):
+            return np.zeros_like(y)
+        if k == "LogShifted":
+            return -1.0 / (y - th[0])
+        if k == "BoxCoxShifted":
+            return (th[1] - 1.0) / (y + th[0])
+        if k == "BoxCoxLinear":
+            return (th[2] - 1.0) / (y + th[0])
+        if k == "ArcsinhLinear":
+            return -y / (1.0 + y * y)
+        if k == "SinhArcsinh":
+            return np.tanh(th[0] + th[1] * np.arcsinh(y)) * th[1] / np.sqrt(1.0 + y * y) - y / (1.0 + y * y)
+        if k == "Logistic":
+            p = (y - th[0]) / th[1]
+            return (1.0 / (1 - p) - 1.0 / p) / th[1]
+        m = self.n
+        if k == "WarpingTanh":
+            a, b, c = th[:m], th[m:2 * m], th[2 * m:]
+            u = b * (y[:, None] + c)
+            return np.dot(-2.0 * np.tanh(u) / np.cosh(u) ** 2, a * b * b) / self._dinv_dy(th, y)
+        shift, power, w = th[:m], th[m:2 * m], th[2 * m:]
+        sh = y[:, None] + shift
+        return np.dot((power - 1.0) * np.abs(sh) ** (power - 2.0) * np.sign(sh), w) / self._dinv_dy(th, y)
+
     def _newton_forward(self, th, z, tol=1e-3, n_steps=1024, alpha=0.1):
         """Mapping.__call__ = inverse_function(self.inv, z) (mappings.py:11-12, libs/tensors.py:134-145): damped
         Newton from 0, step alpha = 0.1, slopes below 1 replaced by their sign, stopped when max|inv(x) - z| < 1e-3 on
@@ -698,6 +750,64 @@ class _Mapping:
         return dinv, dld
 
 
+class _MappingComposed:
+    """m1 @ m2 (processes/hypers/mappings.py:57-70): inv(y) = m2.inv(m1.inv(y)), logdet = m2.logdet(m1.inv(y)) +
+    m1.logdet(y), forward T(z) = m1(m2(z)); hypers in the order m1's then m2's (MappingOperation.check_hypers :40-43)."""
+
+    def __init__(self, spec):
+        self.kind = "composed"
+        self.m1, self.m2 = make_mapping(spec["m1"]), make_mapping(spec["m2"])
+        self.name = self.m1.name + " " + self.m2.name
+        self.hypers = tuple(self.m1.layout()) + tuple(self.m2.layout())
+        self.n = 1
+
+    def layout(self):
+        return list(self.hypers)
+
+    def n_theta(self):
+        return self.m1.n_theta() + self.m2.n_theta()
+
+    def _split(self, th):
+        return th[:self.m1.n_theta()], th[self.m1.n_theta():]
+
+    def inv(self, th, y):
+        t1, t2 = self._split(th)
+        return self.m2.inv(t2, self.m1.inv(t1, y))
+
+    def logdet_dinv(self, th, y):
+        t1, t2 = self._split(th)
+        return self.m2.logdet_dinv(t2, self.m1.inv(t1, y)) + self.m1.logdet_dinv(t1, y)
+
+    def forward(self, th, z):
+        t1, t2 = self._split(th)
+        return self.m1.forward(t1, self.m2.forward(t2, z))
+
+    def dinv_dy(self, th, y):
+        t1, t2 = self._split(th)
+        return self.m2.dinv_dy(t2, self.m1.inv(t1, y)) * self.m1.dinv_dy(t1, y)
+
+    def dlog_dinv_dy(self, th, y):
+        t1, t2 = self._split(th)
+        return self.m2.dlog_dinv_dy(t2, self.m1.inv(t1, y)) * self.m1.dinv_dy(t1, y) + self.m1.dlog_dinv_dy(t1, y)
+
+    def grads(self, th, y):
+        t1, t2 = self._split(th)
+        w = self.m1.inv(t1, y)
+        di1, dl1 = self.m1.grads(t1, y)
+        di2, dl2 = self.m2.grads(t2, w)
+        outer = self.m2.dinv_dy(t2, w)                         # d m2.inv / d w
+        slope = self.m2.dlog_dinv_dy(t2, w)                    # d log|d m2.inv / d w| / d w
+        return (np.vstack([di1 * outer[None, :], di2]),
+                np.concatenate([dl1 + np.sum(di1 * slope[None, :], axis=1), dl2]))
+
+    grads_fd = None                                            # bound below (same finite differences as _Mapping)
+
+
+def make_mapping(spec):
+    return _MappingComposed(spec) if spec["type"] == "composed" else _Mapping(spec)
+_MappingComposed.grads_fd = _Mapping.grads_fd
+
+
 # --------------------------------------------------------------------------- processes
 def build_process(spec, D, strict=True):
     if spec.get("kind") == "transport":
@@ -728,7 +838,7 @@ class OracleProcess:
             self.k_noise = _Binary("sum", self.f_kernel, _Leaf({"type": "Noise", "name": "Noise"}, D))
         else:
             self.k_noise = self.f_kernel
-        self.mapping = _Mapping(spec.get("mapping", {"type": "Identity"}))
+        self.mapping = make_mapping(spec.get("mapping", {"type": "Identity"}))
         lay = self.location.layout() + self.k_noise.layout() + self.mapping.layout()
         if self.kind == "student":                             # hypers/__init__.py:151-155
             lay = lay + [_Hyper("Freedom_degree", 1, True)]
@@ -1019,7 +1129,7 @@ class OracleTransportProcess:
             if t["t"] == "ID":
                 obj, hy = None, []
             elif t["t"] == "TMapping":
-                obj = _Mapping(t["mapping"])
+                obj = make_mapping(t["mapping"])
                 hy = obj.layout()
             elif t["t"] == "TLocation":
                 obj = _Mean(t["location"], D)

@@ -101,6 +101,15 @@ def ref_transport(g3, spec, X):
     return tr
 
 
+def ref_mapping(g3, mp):
+    if mp['type'] == 'composed':
+        return ref_mapping(g3, mp['m1']) @ ref_mapping(g3, mp['m2'])
+    mkw = {'name': mp['name']} if 'name' in mp else {}
+    if 'n' in mp:
+        mkw['n'] = mp['n']
+    return _pot(getattr(g3, mp['type'])(**mkw), mp)
+
+
 def ref_process(g3, spec, X):
     kind = spec.get('kind', 'gauss')
     if kind == 'transport':
@@ -112,10 +121,7 @@ def ref_process(g3, spec, X):
     loc = spec.get('location', {'type': 'Zero'})
     lkw = {'name': loc['name']} if 'name' in loc else {}
     location = _pot(getattr(g3, loc['type'])(_x_arg(X, loc.get('dims')), **lkw), loc)
-    mkw = {'name': mp['name']} if 'name' in mp else {}
-    if 'n' in mp:
-        mkw['n'] = mp['n']
-    mapping = _pot(getattr(g3, mp['type'])(**mkw), mp)
+    mapping = ref_mapping(g3, mp)
     kw = {'name': spec['name']} if 'name' in spec else {}
     return cls(X, location, ref_kernel(g3, spec['kernel'], X), mapping, noisy=spec.get('noisy', True), **kw)
 
@@ -202,6 +208,16 @@ CASES = {
                                       mapping=K('WarpingTanh', n=2)), N=24, D=1, M=7, seed=47),
     'map_warpboxcox':  dict(spec=dict(kind='gauss', warped=True, location=K('Bias'), kernel=K('SE'),
                                       mapping=K('WarpingBoxCox', n=2)), N=24, D=1, M=7, seed=48, positive=True),
+    # composed warpings m1 @ m2 (mappings.py:57-70): m1's hypers move the argument of m2's log-Jacobian
+    'map_comp_log_lin': dict(spec=dict(kind='gauss', location=K('Bias'), kernel=K('SE'),
+                                       mapping=K('composed', m1=K('LogShifted'), m2=K('LinearMapping'))),
+                             N=24, D=1, M=7, seed=51, positive=True),
+    'map_comp_boxcox_sas': dict(spec=dict(kind='student', warped=True, location=K('Bias'), kernel=K('MAT52'),
+                                          mapping=K('composed', m1=K('BoxCoxShifted'), m2=K('SinhArcsinh'))),
+                                N=28, D=2, M=8, seed=52, positive=True),
+    'map_comp_three':  dict(spec=dict(kind='gauss', location=K('Bias'), kernel=K('SE'),
+                                      mapping=K('composed', m1=K('composed', m1=K('LinearMapping'), m2=K('ArcsinhLinear')),
+                                                m2=K('SinhArcsinh'))), N=24, D=1, M=7, seed=53),
     'wtp_boxcox':      dict(spec=dict(kind='student', warped=True, location=K('Bias'), kernel=K('MAT52'),
                                       mapping=K('BoxCoxShifted')), N=32, D=2, M=9, seed=45, positive=True),
     # TransportGaussianProcess (SURVEY f-3): chains [ID | TMapping | TLocation]* @ TKernel

@@ -71,6 +71,15 @@ def build_transport(spec, X):
     return tr
 
 
+def build_mapping(mp):
+    if mp["type"] == "composed":
+        return build_mapping(mp["m1"]) @ build_mapping(mp["m2"])
+    mkw = {"name": mp["name"]} if "name" in mp else {}
+    if "n" in mp:
+        mkw["n"] = mp["n"]
+    return _pot(MAPS[mp["type"]](**mkw), mp)
+
+
 def build_process(spec, X, strict=True):
     kind = spec.get("kind", "gauss")
     if kind == "transport":
@@ -81,11 +90,7 @@ def build_process(spec, X, strict=True):
     loc = spec.get("location", {"type": "Zero"})
     lkw = {"name": loc["name"]} if "name" in loc else {}
     location = _pot(MEANS[loc["type"]](_x_arg(X, loc.get("dims")), **lkw), loc)
-    mp = spec.get("mapping", {"type": "Identity"})
-    mkw = {"name": mp["name"]} if "name" in mp else {}
-    if "n" in mp:
-        mkw["n"] = mp["n"]
-    mapping = _pot(MAPS[mp["type"]](**mkw), mp)
+    mapping = build_mapping(spec.get("mapping", {"type": "Identity"}))
     kw = {}
     if "name" in spec:
         kw["name"] = spec["name"]

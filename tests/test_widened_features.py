@@ -111,3 +111,62 @@ def test_host_widened_features(fake, name):
 @pytest.mark.parametrize("name", list(SPECS))
 def test_cuda_widened_features_multi_tile(name):
     _check(name, 300 if "warp" in name else 520, 3, 40)
+
+
+COMPOSED = [
+    ("LogShifted", "LinearMapping"), ("BoxCoxShifted", "SinhArcsinh"), ("LinearMapping", "ArcsinhLinear"),
+    ("BoxCoxLinear", "Logistic"), ("ArcsinhLinear", "WarpingTanh"), ("LogShifted", "WarpingBoxCox"),
+    ("SinhArcsinh", "SinhArcsinh2"),
+]
+
+
+@pytest.mark.parametrize("pair", COMPOSED, ids=lambda p: "@".join(p))
+def test_composed_mapping_gradients_are_the_analytic_chain(pair):
+    """m1 @ m2 (reference mappings.py:57-70): d inv / d theta and d logdet_dinv / d theta of the composition - including
+    the term through which m1's hypers move the argument of m2's log-Jacobian - against 4th-order central differences
+    of the composition's own inv / logdet_dinv."""
+    import g3py_b200 as g3
+    from g3py_b200.hypers import HyperVar
+    rng = np.random.default_rng(11)
+    y = rng.uniform(0.8, 2.2, size=9)
+    vals = {
+        "LogShifted": dict(shift=0.1), "LinearMapping": dict(shift=0.3, scale=1.3), "BoxCoxShifted": dict(shift=0.2, power=0.7),
+        "BoxCoxLinear": dict(shift=0.2, scale=1.2, power=0.7), "SinhArcsinh": dict(shift=0.1, scale=1.2),
+        "SinhArcsinh2": dict(shift=-0.2, scale=0.8), "ArcsinhLinear": dict(shift=0.2, scale=1.4),
+        "Logistic": dict(lower=-3.0, high=9.0, location=0.3, scale=0.8),
+        "WarpingTanh": dict(a=np.array([0.3, 0.5]), b=np.array([0.8, 1.2]), c=np.array([-0.2, 0.4])),
+        "WarpingBoxCox": dict(shift=np.array([4.0, 5.0]), power=np.array([0.7, 1.3]), w=np.array([0.6, 0.4])),
+    }
+    maps, theta, where = [], [], []
+    for nm in pair:
+        cls = getattr(g3, nm.rstrip("2"))
+        m = cls(n=2) if nm.startswith("Warping") else cls(name=nm)
+        for k, v in vals[nm].items():
+            hv = HyperVar(nm + "_" + k, np.size(v), scalar=np.size(v) == 1)
+            where.append((hv, k, len(theta), np.size(v)))
+            theta.extend(np.atleast_1d(v).tolist())
+            setattr(m, k, hv)
+        maps.append(m)
+    comp = maps[0] @ maps[1]
+    theta = np.array(theta)
+
+    def lookup(t):
+        def p(h):
+            _, _, off, size = next(w for w in where if w[0] is h)
+            return t[off] if size == 1 else t[off:off + size]
+        return p
+    dinv, dld = comp.grads(y, lookup(theta))
+    for key, k, off, size in where:
+        for j in range(size):
+            h = 1e-4 * max(1.0, abs(theta[off + j]))
+            f = lambda s: (lambda t: (comp.inv(y, lookup(t)), comp.logdet_dinv(y, lookup(t))))(theta + s * h * np.eye(len(theta))[off + j])
+            (a2, b2), (a1, b1), (c1, d1), (c2, d2) = f(2), f(1), f(-1), f(-2)
+            fd_inv = (-a2 + 8 * a1 - 8 * c1 + c2) / (12 * h)
+            fd_ld = (-b2 + 8 * b1 - 8 * d1 + d2) / (12 * h)
+            got_inv = np.asarray(dinv[key]).reshape(size, -1)[j] if size > 1 else np.asarray(dinv[key])
+            got_ld = np.atleast_1d(dld[key])[j]
+            assert scaled_err(got_inv, fd_inv) < 1e-8, (pair, k, j)
+            assert abs(got_ld - fd_ld) <= 1e-8 * max(1.0, abs(fd_ld)), (pair, k, j)
+    # and the slope itself
+    fd = g3.hypers.mappings.Mapping.dlog_dinv_dy(comp, y, lookup(theta))
+    assert scaled_err(comp.dlog_dinv_dy(y, lookup(theta)), fd) < 1e-8
