@@ -13,7 +13,7 @@ Ops
 ---
 GramOp(desc)(X1, X2, theta)            -> K                      grad: GramVJPOp
 GramVJPOp(desc)(X1, X2, theta, W)      -> dtheta
-CholeskyRobustGPU()(K)                 -> L                      (jitter ladder + 1e-10*I fallback)
+CholeskyRobustGPU()(K)                 -> L                      (jitter ladder + 1e-10*I fallback; symbolic Murray grad)
 GPLogpOp(desc, kind)(X, delta, theta[, nu]) -> (core, beta, logdet)
         core = -1/2 beta - logdet                         (gauss,   gaussian.py:219-224)
         core = -1/2 (nu+N) log1p(beta/(nu-2)) - logdet    (student, studentT.py:126,129)
@@ -126,7 +126,25 @@ def build_ops(theano=None):
             outputs[0][0] = L.astype(x.dtype)
 
         def grad(self, inputs, gradients):
-            raise NotImplementedError("differentiate through GPLogpOp (fused, analytic gradient) instead of the bare factor")
+            """Reverse mode of the factor (Murray, arXiv:1602.07527), symbolic as in the reference's Op
+            (libs/tensors.py:224-261) so that `tt.grad` through the bare factor keeps working when this Op replaces
+            `cholesky_robust`:  Kbar = Psi(L^-T Phi(L^T Lbar) L^-1), Phi = lower triangle with the diagonal halved,
+            Psi(S) = tril(S + S^T) - diag(S); NaN / inf scrubbed where the reference scrubs them (`tt_to_num`).
+            The forward factor inside is this Op again (device); the two triangular solves are Theano's.  The
+            differentiated hot path should use GPLogpOp instead: one fused call and no N x N cotangent."""
+            import importlib
+            tsl = importlib.import_module(theano.__name__ + ".tensor.slinalg")
+            solve_upper = getattr(tsl, "solve_upper_triangular", None) or tsl.Solve(A_structure="upper_triangular", lower=False)
+            zero, big = np.float32(0), np.float32(1e10)
+
+            def scrub(r):
+                return tt.switch(tt.isnan(r), zero, tt.switch(tt.isinf(r), big, r))
+            L = self(inputs[0])
+            P = scrub(tt.dot(L.T, gradients[0]))
+            phi = tt.tril(P) - tt.diag(tt.diagonal(P) / 2.0)
+            right = solve_upper(L.T, scrub(phi).T).T          # Phi L^-1
+            S = solve_upper(L.T, right)                       # L^-T Phi L^-1
+            return [tt.tril(S + S.T) - tt.diag(tt.diagonal(S))]
 
     class GPLogpGradOp(_DescOp):
         __props__ = ("desc_key", "kind", "device")

@@ -201,3 +201,27 @@ def test_cholesky_robust_gpu_replaces_the_bare_factor(ref, fake, monkeypatch):
             else:
                 assert scaled_err(L, want[noise]) < 1e-12
                 assert np.allclose(L @ L.T, np.asarray(rp.kernel(space=Xs, prior=True, noise=noise)), atol=1e-4)
+
+
+def test_cholesky_robust_gpu_gradient_through_the_bare_factor(ref, fake, monkeypatch):
+    """`tt.grad` THROUGH CholeskyRobustGPU (its symbolic Murray reverse mode) when it replaces `cholesky_robust` in the
+    reference's own logp graph: the reference's compiled dlogp must not change."""
+    import g3py_b200  # noqa: F401
+    from g3py_b200 import theano_ops
+    from helpers import scaled_err
+    import g3py.processes.elliptical as ell
+
+    rng = np.random.default_rng(9)
+    X = rng.uniform(0.2, 4.0, size=(30, 2))
+    y = np.exp(0.4 * (np.sin(X[:, 0]) + 0.3 * X[:, 1] + 0.1 * rng.standard_normal(30))) + 0.3
+    got = {}
+    for patched in (False, True):
+        if patched:
+            monkeypatch.setattr(ell, "cholesky_robust", theano_ops.build_ops().CholeskyRobustGPU())
+        rp = ref.WTP(X, ref.Bias(X), ref.SE(X) + ref.RQ(X), ref.BoxCoxShifted())
+        rp.observed(X, y)
+        th0 = rp.active.dict_to_array(rp.params_default) + 0.05 * np.random.default_rng(1).standard_normal(rp.ndim)
+        got[patched] = (float(rp.logp(th0, array=True)), np.asarray(rp.dlogp(th0, array=True), dtype=np.float64))
+    assert abs(got[True][0] - got[False][0]) <= 1e-12 * abs(got[False][0])
+    assert np.max(np.abs(got[False][1])) > 0
+    assert scaled_err(got[True][1], got[False][1]) < 1e-10
