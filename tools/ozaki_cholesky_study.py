@@ -27,8 +27,9 @@ def gram(N, noise_scale=1.0):
     return th[1] * np.exp(-d_se) + th[5] * (1 + s5 + 5 * d_m / 3) * np.exp(-s5) + th[9] * np.eye(N), y
 
 
-def slices(M, s):
-    amax = np.max(np.abs(M), axis=1)
+def slices(M, s, bound=None):
+    """bound: per-row upper bound of |M| to derive the power-of-two scale from (default: the row maximum itself)."""
+    amax = np.max(np.abs(M), axis=1) if bound is None else bound
     _, e = np.frexp(amax)
     R = M * np.ldexp(1.0, -e)[:, None]
     out = []
@@ -40,9 +41,9 @@ def slices(M, s):
     return out, np.ldexp(1.0, e)
 
 
-def ozaki_update(C, A, s):
+def ozaki_update(C, A, s, bound=None):
     """C -= A A^T the way ozaki_kernel does it: levels d = s-1 .. 0, each an exact integer sum, one fp64 RMW per level."""
-    As, sc = slices(A, s)
+    As, sc = slices(A, s, bound)
     for d in range(s - 1, -1, -1):
         P = sum(As[t] @ As[d - t].T for t in range(d + 1))
         C -= P * (sc[:, None] * (sc[None, :] * 2.0 ** (-7 * (d + 2))))
@@ -56,7 +57,7 @@ def blocked_cholesky(K, nb, update):
         A[k:e, k:e] = np.linalg.cholesky(A[k:e, k:e])
         if e < N:
             A[e:, k:e] = sla.solve_triangular(A[k:e, k:e], A[e:, k:e].T, lower=True).T
-            update(A[e:, e:], A[e:, k:e])
+            update(A[e:, e:], A[e:, k:e], e)
     return np.tril(A)
 
 
@@ -103,11 +104,18 @@ def main():
                  float(np.max(np.abs(a - a_ref)) / np.max(np.abs(a_ref))),
                  float(np.max(np.abs(L.astype(np.longdouble) - Lref)) / np.max(np.abs(Lref)))))
 
-    def f64_update(C, A):
+    def f64_update(C, A, row0):
         C -= A @ A.T
     report("fp64 updates (DMMA today)", blocked_cholesky(K, nb, f64_update))
     for s in (7, 8, 9, 10):
-        report("int8 slices s=%d" % s, blocked_cholesky(K, nb, lambda C, A, s=s: ozaki_update(C, A, s)))
+        report("int8 slices s=%d" % s, blocked_cholesky(K, nb, lambda C, A, row0, s=s: ozaki_update(C, A, s)))
+    # ONE scale per row of L for the whole factorisation: |L_ij| <= sqrt(K_ii) (the row of L has norm sqrt(K_ii)), so
+    # 2^ceil(log2 sqrt(K_ii)) is known before anything is factored and the slices of different panels of one row share
+    # it -- what a left-looking schedule (K = all previous columns in ONE accumulation) needs
+    rootd = np.sqrt(np.diag(K)) * (1.0 + 2.0 ** -40)
+    for s in (8, 9, 10):
+        report("s=%d, row scale sqrt(K_ii)" % s,
+               blocked_cholesky(K, nb, lambda C, A, row0, s=s: ozaki_update(C, A, s, rootd[row0:])))
 
 
 if __name__ == "__main__":
