@@ -29,10 +29,21 @@ constexpr int UMMA_K = 32;
 constexpr int STAGE_A = BM * BK, STAGE_B = BN * BK;
 constexpr int STAGES = 4;
 constexpr int TMEM_COLS = 512;
+#ifndef OZAKI_BULK_EPILOGUE
 constexpr int SCRATCH_LD = 33;                               // 32 x 33 words per epilogue warp: conflict-free transpose
 constexpr int EPI_WARPS = 8;                                 // two per tensor-memory lane quarter (128 columns each)
+constexpr int kScratchBytes = EPI_WARPS * 32 * SCRATCH_LD * 4;
+#else
+// NEXT STEP, compiled only with -DOZAKI_BULK_EPILOGUE (make next) and NOT YET RUN ON HARDWARE: the epilogue stages
+// the scaled, negated values of a 32-row x 32-column chunk in shared memory (one 256-byte row segment per lane) and
+// lets the bulk-copy engine add them to C in L2 (cp.reduce.async.bulk ... add.f64): no global loads in the epilogue.
+constexpr int EPI_WARPS = 4;
+constexpr int STAGE_LD = 272;                                // bytes per staged row: 256 + 16 (16-byte aligned, 4-way conflicts)
+constexpr int kScratchBytes = EPI_WARPS * 32 * STAGE_LD;
+#endif
 constexpr int THREADS = 128 + 32 * EPI_WARPS;
-constexpr int kSmemBytes = STAGES * (STAGE_A + STAGE_B) + 8 * (2 * STAGES + 4) + 16 + EPI_WARPS * 32 * SCRATCH_LD * 4;
+constexpr int kSmemBytes = STAGES * (STAGE_A + STAGE_B) + 8 * (2 * STAGES + 4) + 16 + kScratchBytes;
+static_assert(kSmemBytes <= 232448, "shared memory per CTA");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -200,6 +211,7 @@ ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         umma_commit(tfull0 + 8 * buf);
       }
     }
+#ifndef OZAKI_BULK_EPILOGUE
   } else if (warp >= 4) {                                    // ===== epilogue: C -= double(acc) * 2^(ea + eb - 7(d+2))
     const int w = warp & 3, half = (warp - 4) >> 2;          // lanes 32w.. of tensor memory, columns 128*half..
     uint32_t* sc = scratch + (warp - 4) * 32 * SCRATCH_LD;
@@ -241,6 +253,45 @@ ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_arrive(tempty0 + 8 * buf);
     }
   }
+#else
+  } else if (warp >= 4) {                                    // ===== epilogue: C += -(double)acc * 2^(ea + eb - 7(d+2)) in L2
+    const int w = warp & 3;
+    unsigned char* stage = reinterpret_cast<unsigned char*>(scratch) + w * 32 * STAGE_LD;
+    double* myrow = reinterpret_cast<double*>(stage + lane * STAGE_LD);
+    const uint32_t myrow_s = smem_u32(myrow);
+    const double rs = -sa[m0 + 32 * w + lane];               // this lane's row scale, negated: the reduction adds
+    double* crow = C + (size_t)(m0 + 32 * w + lane) * ldc + n0;
+    for (int p = 0; p < S; ++p) {
+      const int d = S - 1 - p, buf = p & 1;
+      const double common = __longlong_as_double((long long)(1023 - 7 * (d + 2)) << 52);   // 2^(-7(d+2))
+      // levels must reach C in order (fp64 addition is not associative): the previous level's reductions are complete
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      mbar_wait(tfull0 + 8 * buf, (p >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const double rsc = rs * common;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(32 * w) << 16) + buf * BN + c, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the engine has read this lane's staged row
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const double2 cs = *reinterpret_cast<const double2*>(sb + n0 + c + j);          // same address in every lane
+          *reinterpret_cast<double2*>(myrow + j) = make_double2((double)(int)v[j] * (rsc * cs.x), (double)(int)v[j + 1] * (rsc * cs.y));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the engine
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
+                     ::"l"(crow + c), "r"(myrow_s), "r"(256)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(tempty0 + 8 * buf);
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+#endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2)
