@@ -116,7 +116,7 @@ def test_cuda_widened_features_multi_tile(name):
 COMPOSED = [
     ("LogShifted", "LinearMapping"), ("BoxCoxShifted", "SinhArcsinh"), ("LinearMapping", "ArcsinhLinear"),
     ("BoxCoxLinear", "Logistic"), ("ArcsinhLinear", "WarpingTanh"), ("LogShifted", "WarpingBoxCox"),
-    ("SinhArcsinh", "SinhArcsinh2"),
+    ("SinhArcsinh", "SinhArcsinh2"), ("WarpingTanh", "SinhArcsinh"), ("WarpingBoxCox", "BoxCoxLinear"),
 ]
 
 
