@@ -218,6 +218,9 @@ CASES = {
     'map_comp_three':  dict(spec=dict(kind='gauss', location=K('Bias'), kernel=K('SE'),
                                       mapping=K('composed', m1=K('composed', m1=K('LinearMapping'), m2=K('ArcsinhLinear')),
                                                 m2=K('SinhArcsinh'))), N=24, D=1, M=7, seed=53),
+    'map_comp_lin_warptanh': dict(spec=dict(kind='gauss', warped=True, location=K('Bias'), kernel=K('SE'),
+                                            mapping=K('composed', m1=K('LinearMapping'), m2=K('WarpingTanh', n=2))),
+                                  N=24, D=1, M=7, seed=54),
     'wtp_boxcox':      dict(spec=dict(kind='student', warped=True, location=K('Bias'), kernel=K('MAT52'),
                                       mapping=K('BoxCoxShifted')), N=32, D=2, M=9, seed=45, positive=True),
     # TransportGaussianProcess (SURVEY f-3): chains [ID | TMapping | TLocation]* @ TKernel
