@@ -120,6 +120,17 @@ class G3Error(RuntimeError):
     pass
 
 
+def _theta2d(theta, desc, what):
+    """(B, n_theta) float64, validated against the descriptor: the C side copies B * n_theta doubles from the
+    caller's buffer, so a mismatched array would be read out of bounds instead of raising."""
+    theta = np.atleast_2d(_f64(theta))
+    if theta.ndim != 2 or theta.shape[1] != max(desc.n_theta, 0):
+        if not (desc.n_theta == 0 and theta.size == 0):
+            raise ValueError("%s: theta has shape %s, the kernel descriptor takes %d hypers per row"
+                             % (what, theta.shape, desc.n_theta))
+    return theta
+
+
 class Context:
     """One device context (one stream, cached workspaces)."""
 
@@ -176,6 +187,8 @@ class Context:
 
     def dev_gram_block(self, desc, theta, row0, col0, rows, cols, diag_shift, out_ptr, ld):
         theta = _f64(theta).ravel()
+        if theta.size != desc.n_theta:
+            raise ValueError("dev_gram_block: theta has %d entries, the descriptor takes %d" % (theta.size, desc.n_theta))
         self._ck(self._lib.g3_dev_gram_block(self._h, C.byref(desc), _d(theta), row0, col0, rows, cols, float(diag_shift),
                                              C.c_void_p(out_ptr), ld), "g3_dev_gram_block")
 
@@ -245,7 +258,7 @@ class Context:
     # ---- gram
     def gram(self, desc, X1, X2, theta):
         X1 = _f64(X1)
-        theta = np.atleast_2d(_f64(theta))
+        theta = _theta2d(theta, desc, "gram")
         B = theta.shape[0]
         n1, D = X1.shape
         if X2 is None:
@@ -260,7 +273,7 @@ class Context:
 
     def gram_vjp(self, desc, X1, X2, theta, W):
         X1 = _f64(X1)
-        theta = np.atleast_2d(_f64(theta))
+        theta = _theta2d(theta, desc, "gram_vjp")
         B = theta.shape[0]
         n1, D = X1.shape
         if X2 is None:
@@ -307,7 +320,7 @@ class Context:
     def gp_logp_grad(self, desc, kind, delta, theta, nu=None, want_grad=True):
         """delta: (N,) shared or (B, N); theta: (B, P_kernel) natural space.
         Returns dict(beta, logdet, dtheta, ddelta, status)."""
-        theta = np.atleast_2d(_f64(theta))
+        theta = _theta2d(theta, desc, "gp_logp_grad")
         B = theta.shape[0]
         delta = _f64(delta)
         stride = 0 if delta.ndim == 1 else self.N
@@ -327,10 +340,12 @@ class Context:
                 "ddelta": ddl, "status": st}
 
     def gp_upload(self, desc, kind, delta, theta, nu=None, want_grad=True):
-        theta = np.atleast_2d(_f64(theta))
+        theta = _theta2d(theta, desc, "gp_upload")
         B = theta.shape[0]
         delta = _f64(delta)
         stride = 0 if delta.ndim == 1 else self.N
+        if delta.shape[-1] != self.N or (delta.ndim == 2 and delta.shape[0] != B) or delta.ndim > 2:
+            raise ValueError("gp_upload: delta must be (N,) or (B, N) with N = %d, B = %d; got %s" % (self.N, B, delta.shape))
         nu_a = _f64(np.broadcast_to(nu, (B,))) if nu is not None else None
         self._ck(self._lib.g3_gp_upload(self._h, C.byref(desc), int(kind), _d(delta), stride, _d(theta), B, _d(nu_a),
                                         1 if want_grad else 0), "g3_gp_upload")
@@ -355,8 +370,12 @@ class Context:
         if Xs.ndim == 1:
             Xs = Xs[:, None]
         M = Xs.shape[0]
-        delta = _f64(delta)
+        delta = _f64(delta).ravel()
         theta = _f64(theta).ravel()
+        if theta.size != desc.n_theta:
+            raise ValueError("gp_posterior: theta has %d entries, the kernel descriptor takes %d" % (theta.size, desc.n_theta))
+        if delta.size != self.N or Xs.shape[1] != self.D:
+            raise ValueError("gp_posterior: delta must have N = %d entries and Xs D = %d columns" % (self.N, self.D))
         mean = np.empty(M)
         var = np.empty(M)
         covm = np.empty((M, M)) if cov else None
@@ -371,6 +390,8 @@ class Context:
     # ---- big-matrix Cholesky
     def gram_potrf_device(self, desc, theta):
         theta = _f64(theta).ravel()
+        if theta.size != desc.n_theta:
+            raise ValueError("gram_potrf_device: theta has %d entries, the descriptor takes %d" % (theta.size, desc.n_theta))
         ld = C.c_double()
         info = C.c_int()
         mg = C.c_float()

@@ -8,6 +8,7 @@ analytic gradient on the GPU for a whole batch of hyper samples.  No CPU fallbac
 the library or a B200 the calls raise.
 """
 import math
+import warnings
 
 import numpy as np
 from scipy import stats
@@ -24,6 +25,7 @@ __all__ = ["StochasticProcess", "EllipticalProcess", "GaussianProcess", "WarpedG
 f32 = np.float32
 _CONTEXTS = {}
 _TOKENS = __import__("itertools").count(1)     # unique per process object (id() can be recycled after GC)
+_VERSIONS = __import__("itertools").count(1)   # unique per data set ever installed (never reused after a restore)
 
 
 def get_context(device=0):
@@ -149,7 +151,7 @@ class StochasticProcess:
             if inputs.ndim < 2:
                 inputs = inputs.reshape(len(inputs), 1)
             self.inputs = np.ascontiguousarray(inputs)
-            self._data_version += 1
+            self._data_version = next(_VERSIONS)
         if outputs is not None:
             self.outputs = np.asarray(outputs, dtype=np.float64).reshape(-1)
         if index is not None:
@@ -160,6 +162,32 @@ class StochasticProcess:
             self.order = np.arange(len(self.space))
         if len(self.index) != len(self.inputs):
             self.index = np.arange(len(self.inputs))
+
+    def _substituted(self, inputs=None, outputs=None):
+        """Per-call `inputs=` / `outputs=` (the reference's lambda_method only substitutes the values for that one
+        call, stochastic.py:385-430, and never touches self.inputs / self.outputs): the observed data are swapped
+        for the duration of the `with` block and restored afterwards, the device copy follows the data version."""
+        proc = self
+
+        class _Swap:
+            def __enter__(self_):
+                self_.saved = None
+                if inputs is None and outputs is None:
+                    return proc
+                self_.saved = {k: proc.__dict__.get(k) for k in ("inputs", "outputs", "index", "_data_version",
+                                                                  "_affine_cache", "_delta_buf")}
+                proc.set_space(inputs=inputs, outputs=outputs)
+                return proc
+
+            def __exit__(self_, *exc):
+                if self_.saved is not None:
+                    for k, v in self_.saved.items():
+                        if v is None:
+                            proc.__dict__.pop(k, None)
+                        else:
+                            proc.__dict__[k] = v
+                return False
+        return _Swap()
 
     def observed(self, inputs=None, outputs=None, order=None, index=None, hidden=None):
         # stochastic.py:187-201
@@ -463,7 +491,8 @@ class EllipticalProcess(StochasticProcess):
         if Theta.shape[1] != self.ndim:
             raise ValueError("theta has %d entries, the model has %d hypers" % (Theta.shape[1], self.ndim))
         if inputs is not None or outputs is not None:
-            self.set_space(inputs=inputs, outputs=outputs)
+            with self._substituted(inputs, outputs):
+                return self._eval_batch(Theta, None, None, want_grad, nan_quirk)
         X, y = self.inputs, self.outputs
         N = len(y)
         B = Theta.shape[0]
@@ -498,6 +527,11 @@ class EllipticalProcess(StochasticProcess):
         if not want_grad:
             return ll, None, info
         self.executed["dlogp"] += B
+        if np.any(st & cabi.ST_DIAG_SHIFT):
+            # tensors.py:95-98 differentiates through m = min(diag K); the shift enters the gradient here as a constant
+            warnings.warn("dlogp: the tt_to_cov diagonal shift is active (min diag K <= 0) for %d item(s); the gradient "
+                          "treats the shift as a constant (logp parity only in this regime)"
+                          % int(np.count_nonzero(st & cabi.ST_DIAG_SHIFT)), RuntimeWarning, stacklevel=3)
         g_nat = np.zeros((B, self.ndim))
         dth, ddl = res["dtheta"], res["ddelta"]
         for h, off, size, const in self._slots:
@@ -607,6 +641,15 @@ class EllipticalProcess(StochasticProcess):
         with np.errstate(all="ignore"):
             delta = tt_to_num(self.f_mapping.inv(y, p)) - self.f_location(X, p)   # elliptical.py:63,83
         r = self.ctx.gp_posterior(self.desc, space, delta, thk, noise=noise, cov=cov)
+        # The reference's posterior LU-solves the raw K (elliptical.py:78-92); here it goes through the robust
+        # Cholesky.  The two agree while K factors cleanly; make every deviation visible instead of silent.
+        if r["status"] & cabi.ST_POTRF_FAILED:
+            warnings.warn("posterior: the Cholesky of K failed even after the jitter ladder (tensors.py:203-213); "
+                          "the returned moments are not finite", RuntimeWarning, stacklevel=3)
+        elif r["status"] & cabi.ST_JITTER:
+            warnings.warn("posterior: K needed jitter (%d ladder tries) to factor; the reference LU-solves the raw K "
+                          "here, so moments differ at the level of the added jitter" % ((r["status"] >> 8) & 0xff),
+                          RuntimeWarning, stacklevel=3)
         out.update(location=loc_s + r["mean"], kernel_diag=r["var"], kernel=r["cov"], beta=r["beta"], status=r["status"])
         self.executed["predict"] += 1
         return out, nat, p
@@ -621,11 +664,13 @@ class EllipticalProcess(StochasticProcess):
                 median=False, quantiles=False, quantiles_noise=False, samples=0, distribution=False, prior=False,
                 noise=False, simulations=None, array=False):
         """stochastic.py:444-513 (mean / variance / std / covariance / median / quantiles)."""
+        if inputs is not None or outputs is not None:          # per-call substitution, self.inputs/outputs untouched
+            with self._substituted(inputs, outputs):
+                return self.predict(params, space, None, None, mean, std, var, cov, median, quantiles, quantiles_noise,
+                                    samples, distribution, prior, noise, simulations, array)
         theta = self._theta(params, array)
         if not self.is_observed:
             prior = True
-        if inputs is not None or outputs is not None:
-            self.set_space(inputs=inputs, outputs=outputs)
         if space is None:
             space = self.space
         space = np.asarray(space, dtype=np.float64)
@@ -675,12 +720,14 @@ class EllipticalProcess(StochasticProcess):
 
     # ---- selectors bound by EllipticalProcess._compile_methods (elliptical.py:206-215, stochastic.py:330-366):
     #      called as f(params, space, inputs, outputs, prior=, noise=, array=) and returning NumPy arrays
-    def _selector(self, params, space, inputs, outputs, prior, noise, array, cov=False):
-        theta = self._theta(params, array)
-        if not self.is_observed and inputs is None:
-            prior = True
+    def _selector(self, params, space, inputs, outputs, prior, noise, array, cov=False, _given=False):
         if inputs is not None or outputs is not None:
-            self.set_space(inputs=inputs, outputs=outputs)
+            with self._substituted(inputs, outputs):
+                return self._selector(params, space, None, None, prior, noise, array, cov,
+                                      _given=True)
+        theta = self._theta(params, array)
+        if not self.is_observed and not _given:
+            prior = True
         space = self.space if space is None else np.asarray(space, dtype=np.float64)
         if space.ndim < 2:
             space = space.reshape(len(space), 1)

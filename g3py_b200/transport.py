@@ -111,12 +111,13 @@ class TransportGaussianProcess(EllipticalProcess):
         n = len(y)
         return L[n:, :n] @ u + L[n:, n:] @ pred
 
-    def _transport(self, which, params, space, inputs, outputs, vector, prior, noise, array):
+    def _transport(self, which, params, space, inputs, outputs, vector, prior, noise, array, _given=False):
+        if inputs is not None or outputs is not None:          # per-call substitution (stochastic.py:385-430)
+            with self._substituted(inputs, outputs):
+                return self._transport(which, params, space, None, None, vector, prior, noise, array, _given=True)
         theta = self._theta(params, array)
-        if not self.is_observed and inputs is None:
+        if not self.is_observed and not _given:
             prior = True
-        if inputs is not None or outputs is not None:
-            self.set_space(inputs=inputs, outputs=outputs)
         space = self.space if space is None else np.asarray(space, dtype=np.float64)
         if space.ndim < 2:
             space = space.reshape(len(space), 1)

@@ -444,3 +444,25 @@ def test_pure_c_client_links_against_the_boundary(tmp_path):
     assert r.returncode in (0, 2), (r.returncode, r.stderr)
     if r.returncode == 2:
         assert "g3_ctx_create failed" in r.stderr
+
+
+def test_per_call_inputs_do_not_replace_observations(fake):
+    """`logp(inputs=, outputs=)` / `predict(inputs=, ...)` substitute the data for that call only, like the reference's
+    lambda_method (g3py/processes/stochastic.py:385-430); the observed data are untouched afterwards."""
+    spec = SPECS["gp"]
+    op, X, y, Th = _problem(spec)
+    gp = build_process(spec, X)
+    gp.observed(X, y)
+    base = gp.loglike(Th[0], array=True)
+    X7, y7 = X[:7] + 0.1, y[:7] * 0.5
+    held = gp.loglike(Th[0], inputs=X7, outputs=y7, array=True)
+    assert held == pytest.approx(op.logp(Th[0], X7, y7), rel=1e-10)
+    assert len(gp.inputs) == len(X) and np.array_equal(gp.inputs, X) and np.array_equal(gp.outputs, y)
+    assert gp.loglike(Th[0], array=True) == base                      # device copy followed the restore
+    out = gp.predict(Th[0], space=X[:5], inputs=X7, outputs=y7, array=True, var=True)
+    pr = op.predict(Th[0], X[:5], X7, y7)
+    assert scaled_err(out["mean"], pr["mean"]) < 1e-9
+    assert len(gp.inputs) == len(X)
+    loc = gp.location(Th[0], space=X[:5], inputs=X7, outputs=y7, array=True)
+    assert scaled_err(loc, pr["location"] if "location" in pr else op.posterior(Th[0], X[:5], X7, y7)["location"]) < 1e-9
+    assert np.array_equal(gp.outputs, y) and gp.loglike(Th[0], array=True) == base
