@@ -49,15 +49,22 @@ METRIC = "fp64 GP logp+grad evals/s at N=4096 x64 theta batch"
 UNIT = "evals/s"
 
 
-def peaks():
-    out = {"fp64_tflops": 37.1, "fp64_source": "measured tools/fp64_peak.cu on this pool's B200 (DMMA.8x8x4 = DFMA = 37.1 TFLOP/s; "
-           "cuBLAS dgemm 8192^3 35.5); MEASURED_PEAKS.json has no fp64 entry"}
+def peaks(ctx):
+    """Roofline denominators.  fp64: measured IN THIS RUN on this GPU (g3_debug_fp64_peak: ~0.5 s of back-to-back
+    DMMA.8x8x4 / DFMA loops, CUDA events) - MEASURED_PEAKS.json has no fp64 entry.  HBM: the driver-written
+    MEASURED_PEAKS.json copy bandwidth (fallback of B200_PROFILING.md if absent); the in-run copy figure is printed
+    beside it."""
+    m = ctx.fp64_peak(0.5, copy=True)
+    out = {"fp64_tflops": m["dmma_tflops"], "dfma_tflops": m["dfma_tflops"], "copy_gbs_in_run": m["copy_gbs"],
+           "fp64_source": "in-run: g3_debug_fp64_peak, sustained DMMA.8x8x4 loop on this GPU (DFMA pipe: %.2f TFLOP/s)" % m["dfma_tflops"]}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             mp = json.load(f)
         out["hbm_gbs"] = mp.get("hbm_gbs")
+        out["hbm_source"] = "MEASURED_PEAKS.json (driver-written copy bandwidth)"
     except Exception:
         out["hbm_gbs"] = 6650.0
+        out["hbm_source"] = "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
     return out
 
 
@@ -281,7 +288,7 @@ def main():
             one_gpu_tflops = 35.59                                  # measured, same code, world=1 (profiles/r01_dist_cholesky_131072.jsonl)
             dist_metric = {"metric": "exact-GP Cholesky N=%d, block-cyclic (nb=1024, 1x%d grid, panel broadcast over NCCL, look-ahead)" % (args.dist_n, world),
                            "value": r["tflops"], "unit": "TFLOP/s", "ms_potrf": r["ms_potrf"], "ms_gram": r["ms_gram"],
-                           "n_gpus": world, "per_gpu_frac_of_fp64_peak": r["tflops"] / world / peaks()["fp64_tflops"],
+                           "n_gpus": world,
                            "parallel_efficiency_vs_1gpu_same_code": r["tflops"] / world / one_gpu_tflops,
                            "logdet": r["logdet"], "info": r["info"], "local_gib": r["local_gib"]}
         except Exception as e:
@@ -291,7 +298,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    pk = peaks()
+    pk = peaks(ctx)
     flops_step = float(B) * float(N) ** 3                     # one logp+grad evaluation = N^3 flop
     gemm = prof["dgemm_nt"]
     gemm_ms_step = gemm["ms"] / prof_steps

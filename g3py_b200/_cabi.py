@@ -58,6 +58,7 @@ SIGNATURES = {
     "g3_debug_read": (C.c_int, [_ctxp, C.c_char_p, C.c_void_p, C.c_size_t]),
     "g3_debug_potrf_stress": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, C.c_int, _ip, _dp]),
     "g3_debug_gemm_stress": (C.c_int, [_ctxp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
+    "g3_debug_fp64_peak": (C.c_int, [_ctxp, C.c_double, _dp, _dp, _dp]),
     "g3_set_stream": (C.c_int, [_ctxp, C.c_void_p]),
     "g3_dev_gram_block": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                     C.c_void_p, C.c_longlong]),
@@ -71,6 +72,7 @@ SIGNATURES = {
     "g3_potrf_robust_solve": (C.c_int, [_ctxp, _dp, C.c_int, C.c_int, _dp, _dp, _ip, _dp]),
     "g3_gp_logp_grad": (C.c_int, [_ctxp, C.POINTER(KernelDesc), C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, _dp, _dp,
                                   _dp, _dp, _ip]),
+    "g3_gp_grad_resume": (C.c_int, [_ctxp, _dp, _dp]),
     "g3_gp_upload": (C.c_int, [_ctxp, C.POINTER(KernelDesc), C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int]),
     "g3_gp_run": (C.c_int, [_ctxp]),
     "g3_gp_download": (C.c_int, [_ctxp, _dp, _dp, _dp, _dp, _ip]),
@@ -235,6 +237,7 @@ class Context:
         theta = np.atleast_2d(_f64(theta))
         out = np.zeros((iters, 4), dtype=np.int32)
         tiles = np.zeros((2, 128, 128))
+        self._resident = None
         self._ck(self._lib.g3_debug_potrf_stress(self._h, C.byref(desc), _d(theta), theta.shape[0], iters, _i(out), _d(tiles)),
                  "g3_debug_potrf_stress")
         return out, tiles
@@ -244,6 +247,13 @@ class Context:
         self._ck(self._lib.g3_debug_gemm_stress(self._h, rows, B, launches, inplace, kdepth, out), "g3_debug_gemm_stress")
         return list(out)
 
+    def fp64_peak(self, seconds=0.5, copy=True):
+        """In-run roofline denominators: {dmma_tflops, dfma_tflops, copy_gbs} measured on this context's GPU."""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self._lib.g3_debug_fp64_peak(self._h, float(seconds), C.cast(C.byref(a), _dp), C.cast(C.byref(b), _dp),
+                                              C.cast(C.byref(c), _dp) if copy else None), "g3_debug_fp64_peak")
+        return {"dmma_tflops": float(a.value), "dfma_tflops": float(b.value), "copy_gbs": float(c.value) if copy else None}
+
     def launch_count(self):
         return int(self._lib.g3_launch_count(self._h))
 
@@ -252,8 +262,21 @@ class Context:
         X = _f64(X)
         if X.ndim == 1:
             X = X[:, None]
+        self._resident = None
         self._ck(self._lib.g3_set_data(self._h, _d(X), X.shape[0], X.shape[1]), "g3_set_data")
         self.N, self.D = X.shape
+        self._data_serial = getattr(self, "_data_serial", 0) + 1
+        self._X_host = X.copy()
+
+    def set_data_if_changed(self, X):
+        """Upload X only when it differs from the resident copy (Theano `perform` hands the same array every call)."""
+        X = _f64(X)
+        if X.ndim == 1:
+            X = X[:, None]
+        cur = getattr(self, "_X_host", None)
+        if cur is None or cur.shape != X.shape or not np.array_equal(cur, X):
+            self.set_data(X)
+            self._data_tag = None
 
     # ---- gram
     def gram(self, desc, X1, X2, theta):
@@ -334,12 +357,37 @@ class Context:
         st = np.zeros(B, dtype=np.int32)
         dth = np.zeros((B, max(desc.n_theta, 1))) if want_grad else None
         ddl = np.zeros((B, self.N)) if want_grad else None
+        self._resident = None
         self._ck(self._lib.g3_gp_logp_grad(self._h, C.byref(desc), int(kind), _d(delta), stride, _d(theta), B, _d(nu_a),
                                            _d(beta), _d(logdet), _d(dth), _d(ddl), _i(st)), "g3_gp_logp_grad")
+        if not want_grad:        # the factor of this evaluation stays on the device: see gp_grad_resume
+            self._resident = (self.eval_key(desc, kind, delta, theta, nu_a), B, desc.n_theta)
         return {"beta": beta, "logdet": logdet, "dtheta": None if dth is None else dth[:, :desc.n_theta],
                 "ddelta": ddl, "status": st}
 
+    def eval_key(self, desc, kind, delta, theta, nu):
+        """Identity of one evaluation on the resident data: bytes of every input of g3_gp_logp_grad."""
+        return (getattr(self, "_data_serial", 0), bytes(desc), int(kind), _f64(delta).tobytes(),
+                np.atleast_2d(_f64(theta)).tobytes(), None if nu is None else _f64(nu).tobytes())
+
+    def resident_matches(self, desc, kind, delta, theta, nu):
+        r = getattr(self, "_resident", None)
+        return r is not None and r[0] == self.eval_key(desc, kind, delta, theta, nu)
+
+    def gp_grad_resume(self):
+        """(dtheta (B, P), ddelta (B, N)) of the last logp-only gp_logp_grad call, from its resident factor."""
+        r = getattr(self, "_resident", None)
+        if r is None:
+            raise G3Error("gp_grad_resume: no resident factor")
+        _, B, P = r
+        self._resident = None
+        dth = np.zeros((B, max(P, 1)))
+        ddl = np.zeros((B, self.N))
+        self._ck(self._lib.g3_gp_grad_resume(self._h, _d(dth), _d(ddl)), "g3_gp_grad_resume")
+        return dth[:, :P], ddl
+
     def gp_upload(self, desc, kind, delta, theta, nu=None, want_grad=True):
+        self._resident = None
         theta = _theta2d(theta, desc, "gp_upload")
         B = theta.shape[0]
         delta = _f64(delta)
@@ -382,6 +430,7 @@ class Context:
         beta = C.c_double()
         st = C.c_int()
         flags = (POST_NOISE if noise else 0) | (POST_COV if cov else 0)
+        self._resident = None
         self._ck(self._lib.g3_gp_posterior(self._h, C.byref(desc), _d(Xs), M, _d(delta), _d(theta), flags, _d(mean),
                                            _d(var), _d(covm), C.cast(C.byref(beta), _dp), C.cast(C.byref(st), _ip)),
                  "g3_gp_posterior")
@@ -396,6 +445,7 @@ class Context:
         info = C.c_int()
         mg = C.c_float()
         mp = C.c_float()
+        self._resident = None
         self._ck(self._lib.g3_gram_potrf_device(self._h, C.byref(desc), _d(theta), C.cast(C.byref(ld), _dp),
                                                 C.cast(C.byref(info), _ip), C.byref(mg), C.byref(mp)),
                  "g3_gram_potrf_device")

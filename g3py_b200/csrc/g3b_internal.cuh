@@ -23,6 +23,7 @@ struct g3_buf {
 struct g3_gp_state {
   g3_kernel_desc desc;
   int kind = 0, B = 0, want_grad = 0, delta_stride = 0, valid = 0;
+  int factor_resident = 0;     // L, Dinv, u of the last logp-only evaluation are still in the workspaces
 };
 
 struct g3_ctx {

@@ -248,9 +248,11 @@ static GpBufs gp_view(const GpBufs& w, int b0, int N, int P, int delta_stride) {
   return v;
 }
 
+static int gp_grad_stage(g3_ctx* ctx, GpBufs& w, int B);
+
 static int gp_after_potrf(g3_ctx* ctx, GpBufs& w, int B) {
   const g3_gp_state& st = ctx->gp;
-  const int N = ctx->N, Np = g3_pad(N), T = Np / TS, P = st.desc.n_theta;
+  const int N = ctx->N, Np = g3_pad(N);
   int rc;
   gp_zero_beta_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(w.beta, B);
   G3_LAUNCH_CHECK(ctx);
@@ -262,6 +264,14 @@ static int gp_after_potrf(g3_ctx* ctx, GpBufs& w, int B) {
                                                            w.status, B);
   G3_LAUNCH_CHECK(ctx);
   if (!st.want_grad) return 0;
+  return gp_grad_stage(ctx, w, B);
+}
+
+// Gradient stages on a resident factor: alpha = L^-T u, U = L^-T, K^-1 = U U^T (over L), W-contraction, d/d delta.
+static int gp_grad_stage(g3_ctx* ctx, GpBufs& w, int B) {
+  const g3_gp_state& st = ctx->gp;
+  const int N = ctx->N, Np = g3_pad(N), T = Np / TS, P = st.desc.n_theta;
+  int rc;
   G3_CUDA(ctx, cudaMemcpyAsync(w.s, w.u, sizeof(double) * (size_t)B * Np, cudaMemcpyDeviceToDevice, ctx->stream));
   if ((rc = g3_trsv_bwd(ctx, w.A, w.Dinv, w.s, w.alpha, Np, B))) return rc;
   if (!ctx->trtri_done && (rc = g3_trtri_batched(ctx, w.A, w.U, Np, B, w.Dinv))) return rc;   // else: pipelined behind potrf
@@ -341,6 +351,7 @@ int g3_gp_upload(g3_ctx* ctx, const g3_kernel_desc* desc, int kind, const double
   GpBufs w;
   const int drows = delta_stride ? B : 1;
   if ((rc = gp_alloc(ctx, w, B, P, N, want_grad, drows))) return rc;
+  ctx->gp.factor_resident = 0;
   ctx->gp.desc = *desc;
   ctx->gp.kind = kind;
   ctx->gp.B = B;
@@ -494,6 +505,36 @@ int g3_gp_download(g3_ctx* ctx, double* beta, double* logdet, double* dtheta_or_
       status[b] = s;
     }
   }
+  // logp-only evaluation: L, Dinv, u, c are final (ladder included) and stay in the workspaces, so the gradient of the
+  // SAME evaluation can be finished later without refactoring (g3_gp_grad_resume)
+  ctx->gp.factor_resident = st.want_grad ? 0 : 1;
+  return 0;
+}
+
+int g3_gp_grad_resume(g3_ctx* ctx, double* dtheta, double* ddelta) {
+  if (!ctx || !ctx->gp.valid || !ctx->gp.factor_resident || ctx->gp.want_grad)
+    return g3_fail_msg(ctx, "g3_gp_grad_resume: no resident factor (call g3_gp_logp_grad without gradient outputs first)");
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  const g3_gp_state& st = ctx->gp;
+  const int B = st.B, N = ctx->N, P = st.desc.n_theta;
+  GpBufs w;
+  int rc;
+  if ((rc = gp_alloc(ctx, w, B, P, N, 1, st.delta_stride ? B : 1))) return rc;
+  ctx->gp.factor_resident = 0;                     // K^-1 is about to overwrite L
+  ctx->trtri_done = 0;
+  ctx->force_left = B > 8;
+  rc = gp_grad_stage(ctx, w, B);
+  ctx->force_left = 0;
+  if (rc) return rc;
+  const bool get_th = dtheta && P > 0, get_dl = ddelta != nullptr;
+  double* out = (double*)g3_pinned(ctx, "gp_d2h", sizeof(double) * ((size_t)B * P + (size_t)B * N + 1));
+  if (!out) return -2;
+  if (get_th) G3_CUDA(ctx, cudaMemcpyAsync(out, w.dtheta, sizeof(double) * (size_t)B * P, cudaMemcpyDeviceToHost, ctx->stream));
+  if (get_dl)
+    G3_CUDA(ctx, cudaMemcpyAsync(out + (size_t)B * P, w.ddelta, sizeof(double) * (size_t)B * N, cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (get_th) memcpy(dtheta, out, sizeof(double) * (size_t)B * P);
+  if (get_dl) memcpy(ddelta, out + (size_t)B * P, sizeof(double) * (size_t)B * N);
   return 0;
 }
 

@@ -24,18 +24,27 @@ __all__ = ["StochasticProcess", "EllipticalProcess", "GaussianProcess", "WarpedG
 
 f32 = np.float32
 _CONTEXTS = {}
+_CONTEXTS_LOCK = __import__("threading").Lock()
 _TOKENS = __import__("itertools").count(1)     # unique per process object (id() can be recycled after GC)
+_TLS = __import__("threading").local()         # per-thread scratch (the (B, N) delta buffer handed to the device call)
 _VERSIONS = __import__("itertools").count(1)   # unique per data set ever installed (never reused after a restore)
 
 
 def get_context(device=0):
-    """Per-process, per-device context, created on first use (fork-safe)."""
+    """Per-process, per-THREAD, per-device context, created on first use.  Fork-safe (no CUDA state before the first
+    call in a process; emcee / PyMC3 fork workers, stochastic.py:775-783) and thread-safe: a g3_ctx owns its streams and
+    workspaces and is not re-entrant, while ctypes releases the GIL during a call, so every thread of a threaded caller
+    (emcee `threads > 1`, bayesian/average.py:29,36) gets its own context instead of racing on a shared one."""
     import os
-    key = (os.getpid(), int(device))
+    import threading
+    key = (os.getpid(), threading.get_ident(), int(device))
     ctx = _CONTEXTS.get(key)
     if ctx is None:
-        ctx = cabi.Context(device)
-        _CONTEXTS[key] = ctx
+        with _CONTEXTS_LOCK:
+            ctx = _CONTEXTS.get(key)
+            if ctx is None:
+                ctx = cabi.Context(device)
+                _CONTEXTS[key] = ctx
     return ctx
 
 
@@ -175,7 +184,7 @@ class StochasticProcess:
                 if inputs is None and outputs is None:
                     return proc
                 self_.saved = {k: proc.__dict__.get(k) for k in ("inputs", "outputs", "index", "_data_version",
-                                                                  "_affine_cache", "_delta_buf")}
+                                                                  "_affine_cache")}
                 proc.set_space(inputs=inputs, outputs=outputs)
                 return proc
 
@@ -450,9 +459,13 @@ class EllipticalProcess(StochasticProcess):
                 minv = np.asarray(self.f_mapping.inv(outputs, p0), dtype=np.float64)
                 det = float(self.f_mapping.logdet_dinv(outputs, p0))
             rows = nat2d if varying else nat2d[:1]
-            buf = getattr(self, "_delta_buf", None)       # reused: a fresh (B, N) array costs more in page faults
-            if buf is None or buf.shape != (rows.shape[0], len(minv)):
-                buf = self._delta_buf = np.empty((rows.shape[0], len(minv)))
+            tls = _TLS.__dict__.setdefault("delta_buf", {})   # reused per thread: a fresh (B, N) array costs more in page faults
+            shp = (rows.shape[0], len(minv))                  # consumed by the device call before this thread's next use
+            buf = tls.get(shp)
+            if buf is None:
+                if len(tls) > 4:
+                    tls.clear()
+                buf = tls[shp] = np.empty(shp)
             if 0 < len(idx) <= 4:                          # BLAS is slow on K <= 4: rank-1 broadcasts instead
                 np.multiply(rows[:, idx[0]:idx[0] + 1], J[0], out=buf)
                 for r in range(1, len(idx)):

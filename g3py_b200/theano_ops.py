@@ -163,10 +163,19 @@ def build_ops(theano=None):
         def perform(self, node, inputs, outputs):
             X, delta, theta, nu = inputs
             ctx = _ctx(self.device)
-            ctx.set_data(X)
-            ctx._data_tag = None
+            ctx.set_data_if_changed(X)                         # X is re-uploaded only when its values changed
             nu_a = np.atleast_1d(np.asarray(nu, dtype=np.float64)) if self.kind == cabi.KIND_STUDENT else None
-            r = ctx.gp_logp_grad(self.desc, self.kind, delta, theta, nu=nu_a, want_grad=True)
+            desc = self.desc
+            hit = getattr(ctx, "_op_last", None)
+            if hit is not None and ctx.resident_matches(desc, self.kind, delta, theta, nu_a):
+                # GPLogpOp.perform just factored K for these very inputs (th_logp and th_dlogp are evaluated back to
+                # back, stochastic.py:300-313): finish the gradient from the resident factor, one N^3 in total
+                dth, ddl = ctx.gp_grad_resume()
+                r = {"status": hit["status"], "beta": hit["beta"], "dtheta": dth, "ddelta": ddl}
+                ctx.op_resumed = getattr(ctx, "op_resumed", 0) + 1
+            else:
+                r = ctx.gp_logp_grad(desc, self.kind, delta, theta, nu=nu_a, want_grad=True)
+            ctx._op_last = None
             bad = bool(r["status"][0] & (cabi.ST_POTRF_FAILED | cabi.ST_NONFINITE_RESULT))
             dth = np.zeros_like(theta) if bad else r["dtheta"][0]
             ddl = np.zeros_like(delta) if bad else r["ddelta"][0]
@@ -196,10 +205,10 @@ def build_ops(theano=None):
         def perform(self, node, inputs, outputs):
             X, delta, theta, nu = inputs
             ctx = _ctx(self.device)
-            ctx.set_data(X)
-            ctx._data_tag = None
+            ctx.set_data_if_changed(X)
             nu_a = np.atleast_1d(np.asarray(nu, dtype=np.float64)) if self.kind == cabi.KIND_STUDENT else None
             r = ctx.gp_logp_grad(self.desc, self.kind, delta, theta, nu=nu_a, want_grad=False)
+            ctx._op_last = {"status": r["status"], "beta": r["beta"]}      # GPLogpGradOp may finish from this factor
             beta, logdet, st = float(r["beta"][0]), float(r["logdet"][0]), int(r["status"][0])
             n = float(len(delta))
             if st & cabi.ST_POTRF_FAILED:                      # L = 1e-10 * I (libs/tensors.py:218-222)
@@ -243,8 +252,7 @@ def build_ops(theano=None):
         def perform(self, node, inputs, outputs):
             X, Xs, delta, theta = inputs
             ctx = _ctx(self.device)
-            ctx.set_data(X)
-            ctx._data_tag = None
+            ctx.set_data_if_changed(X)
             r = ctx.gp_posterior(self.desc, Xs, delta, theta, noise=self.noise, cov=False)
             outputs[0][0] = r["mean"].astype(delta.dtype)
             outputs[1][0] = r["var"].astype(delta.dtype)

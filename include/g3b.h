@@ -138,6 +138,11 @@ int g3_debug_read(g3_ctx* ctx, const char* name, void* host, size_t bytes);
 int g3_debug_potrf_stress(g3_ctx* ctx, const g3_kernel_desc* desc, const double* theta, int B, int iters, int* out4,
                           double* tiles2);
 int g3_debug_gemm_stress(g3_ctx* ctx, int rows, int B, int launches, int inplace, int kdepth, long long* out4);
+/* Roofline denominators measured in the run (bench.py): sustained fp64 rate of the DMMA.8x8x4 tensor pipe and of the
+ * DFMA pipe in TFLOP/s, and a STREAM-style 1 GiB device copy in GB/s (read + written bytes), each timed for about
+ * `seconds` with CUDA events on the context's stream.  Any output pointer may be NULL (that leg is skipped).
+ * Replaces nothing in the reference. */
+int g3_debug_fp64_peak(g3_ctx* ctx, double seconds, double* dmma_tflops, double* dfma_tflops, double* copy_gbs);
 /* Number of kernels launched by this context since creation (bench.py "gpu_launches"). */
 int64_t g3_launch_count(g3_ctx* ctx);
 
@@ -191,6 +196,13 @@ int g3_gp_logp_grad(g3_ctx* ctx, const g3_kernel_desc* desc, int kind,
                     const double* delta, int delta_stride, const double* theta, int B,
                     const double* nu_or_NULL, double* beta, double* logdet,
                     double* dtheta_or_NULL, double* ddelta_or_NULL, int* status);
+
+/* Finish the gradient of the LAST logp-only evaluation (g3_gp_logp_grad with dtheta = ddelta = NULL, nothing else run on
+ * the context since): the factor L, its block inverses and u = L^-1 delta are still resident, so only the K^-1 stages run
+ * (2/3 N^3 instead of a second N^3/3 factorisation + 2/3 N^3).  This is what makes a Theano value-and-gradient pair
+ * (th_logp followed by th_dlogp on the same theta, stochastic.py:300-313; the forward is recomputed inside dlogp in the
+ * reference) cost one factorisation.  Fails (<0) if no matching factor is resident.  dtheta: B x n_theta, ddelta: B x N. */
+int g3_gp_grad_resume(g3_ctx* ctx, double* dtheta_or_NULL, double* ddelta_or_NULL);
 
 /* Split form of the same call for benchmarking with inputs resident in HBM:
  * upload copies theta/delta/nu host->device, run launches the device pipeline only,

@@ -123,7 +123,37 @@ class FakeContext:
 
     def set_data(self, X):
         self.X = np.array(X, dtype=np.float64)
+        if self.X.ndim == 1:
+            self.X = self.X[:, None]
         self.N, self.D = self.X.shape
+        self._resident = None
+        self.uploads = getattr(self, "uploads", 0) + 1
+
+    def set_data_if_changed(self, X):
+        X = np.asarray(X, dtype=np.float64)
+        if X.ndim == 1:
+            X = X[:, None]
+        if getattr(self, "X", None) is None or self.X.shape != X.shape or not np.array_equal(self.X, X):
+            self.set_data(X)
+            self._data_tag = None
+
+    # the resident-factor protocol of _cabi.Context (g3_gp_grad_resume): same call surface, recomputed here
+    def eval_key(self, desc, kind, delta, theta, nu):
+        return (bytes(desc), int(kind), np.asarray(delta, dtype=np.float64).tobytes(),
+                np.atleast_2d(np.asarray(theta, dtype=np.float64)).tobytes(),
+                None if nu is None else np.asarray(nu, dtype=np.float64).tobytes(), self.X.tobytes())
+
+    def resident_matches(self, desc, kind, delta, theta, nu):
+        r = getattr(self, "_resident", None)
+        return r is not None and r[0] == self.eval_key(desc, kind, delta, theta, nu)
+
+    def gp_grad_resume(self):
+        key, args = self._resident
+        self._resident = None
+        self.resumed = getattr(self, "resumed", 0) + 1
+        self.calls -= 1                                   # not a new factorisation
+        r = self.gp_logp_grad(*args, want_grad=True)
+        return r["dtheta"], r["ddelta"]
 
     def gram(self, desc, X1, X2, theta):
         theta = np.atleast_2d(theta)
@@ -163,6 +193,7 @@ class FakeContext:
 
     def gp_logp_grad(self, desc, kind, delta, theta, nu=None, want_grad=True):
         self.calls += 1
+        self._resident = None if want_grad else (self.eval_key(desc, kind, delta, theta, nu), (desc, kind, delta, theta, nu))
         theta = np.atleast_2d(theta)
         B = len(theta)
         delta = np.asarray(delta, dtype=np.float64)

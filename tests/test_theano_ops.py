@@ -99,12 +99,18 @@ def test_ops_cpu_harness(monkeypatch, kind):
     ctx.potrf_robust = lambda A: (np.linalg.cholesky(A), 0, 0.0)
     monkeypatch.setattr(g3.processes, "get_context", lambda device=0: ctx)
     _run(kind)
+    # value-then-gradient on the same inputs finished from the resident factor (no second factorisation), and X was
+    # uploaded once although every perform() receives it
+    assert ctx.resumed >= 1 and ctx.uploads == 1
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind", ["gauss", "student"])
 def test_ops_gpu(kind):
+    ctx = g3.processes.get_context(0)
+    r0 = getattr(ctx, "op_resumed", 0)
     _run(kind)
+    assert getattr(ctx, "op_resumed", 0) > r0       # GPLogpGradOp finished from GPLogpOp's resident factor (g3_gp_grad_resume)
     ops = theano_ops.build_ops(make_module())
     rng = np.random.default_rng(3)
     A = rng.standard_normal((150, 160))
