@@ -42,6 +42,7 @@ _ctxp = C.c_void_p
 SIGNATURES = {
     "g3_ctx_create": (C.c_int, [C.c_int, C.POINTER(_ctxp)]),
     "g3_ctx_destroy": (C.c_int, [_ctxp]),
+    "g3_ctx_trim": (C.c_int, [_ctxp]),
     "g3_last_error": (C.c_char_p, [_ctxp]),
     "g3_sync": (C.c_int, [_ctxp]),
     "g3_set_jitter": (C.c_int, [_ctxp, C.c_double, C.c_int]),
@@ -65,6 +66,23 @@ SIGNATURES = {
     "g3_dev_potrf_panel": (C.c_int, [_ctxp, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "g3_dev_trsv_panel": (C.c_int, [_ctxp, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "g3_dev_syrk_panel": (C.c_int, [_ctxp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "g3_comm_get_unique_id": (C.c_int, [C.c_char_p]),
+    "g3_comm_init": (C.c_int, [_ctxp, C.c_int, C.c_int, C.c_char_p]),
+    "g3_comm_destroy": (C.c_int, [_ctxp]),
+    "g3_comm_size": (C.c_int, [_ctxp]),
+    "g3_comm_rank": (C.c_int, [_ctxp]),
+    "g3_comm_barrier": (C.c_int, [_ctxp]),
+    "g3_comm_allgather": (C.c_int, [_ctxp, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "g3_comm_allreduce": (C.c_int, [_ctxp, _dp, C.c_int, C.c_int]),
+    "g3_dist_factor": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _ip,
+                                 C.POINTER(C.c_float), C.POINTER(C.c_float), _dp]),
+    "g3_dist_solve": (C.c_int, [_ctxp, _dp, _dp, _dp, C.POINTER(C.c_float)]),
+    "g3_dist_residual": (C.c_int, [_ctxp, C.c_int, C.c_uint, _dp]),
+    "g3_dist_read_piece": (C.c_int, [_ctxp, C.c_int, _dp, _ip]),
+    "g3_dist_free": (C.c_int, [_ctxp]),
+    "g3_dist_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip]),
+    "g3_potrf_2d": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _ip,
+                              C.POINTER(C.c_float)]),
     "g3_set_data": (C.c_int, [_ctxp, _dp, C.c_int, C.c_int]),
     "g3_gram": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _ip]),
     "g3_gram_vjp": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp]),
@@ -104,6 +122,24 @@ def load():
         fn.argtypes = args
     _LIB = lib
     return lib
+
+
+def comm_unique_id():
+    """128-byte NCCL id (rank 0 creates it, the host distributes it: g3py_b200/comm.py)."""
+    buf = C.create_string_buffer(128)
+    rc = load().g3_comm_get_unique_id(buf)
+    if rc != 0:
+        raise G3Error("g3_comm_get_unique_id failed (%d): libnccl.so.2 not loadable?" % rc)
+    return buf.raw
+
+
+def dist_layout(N, nb, Pr, Pc, I, J, p):
+    """{owner, first, count, index} of block (I, J) / piece (J, p): pure index arithmetic of the C side."""
+    out = (C.c_int * 4)()
+    rc = load().g3_dist_layout(int(N), int(nb), int(Pr), int(Pc), int(I), int(J), int(p), out)
+    if rc != 0:
+        raise ValueError("g3_dist_layout: bad arguments")
+    return {"owner": out[0], "first": out[1], "count": out[2], "index": out[3]}
 
 
 def _d(a):
@@ -205,6 +241,11 @@ class Context:
     def dev_syrk_panel(self, p_ptr, rows_p, nb, row_off, d_ptr, rows_d):
         self._ck(self._lib.g3_dev_syrk_panel(self._h, C.c_void_p(p_ptr), rows_p, nb, row_off, C.c_void_p(d_ptr), rows_d),
                  "g3_dev_syrk_panel")
+
+    def trim(self):
+        """Free all cached device / pinned workspaces (re-created on demand)."""
+        self._resident = None
+        self._ck(self._lib.g3_ctx_trim(self._h), "g3_ctx_trim")
 
     def sync(self):
         self._ck(self._lib.g3_sync(self._h), "g3_sync")
@@ -392,7 +433,7 @@ class Context:
         B = theta.shape[0]
         delta = _f64(delta)
         stride = 0 if delta.ndim == 1 else self.N
-        if delta.shape[-1] != self.N or (delta.ndim == 2 and delta.shape[0] != B) or delta.ndim > 2:
+        if self.N and (delta.shape[-1] != self.N or (delta.ndim == 2 and delta.shape[0] != B) or delta.ndim > 2):
             raise ValueError("gp_upload: delta must be (N,) or (B, N) with N = %d, B = %d; got %s" % (self.N, B, delta.shape))
         nu_a = _f64(np.broadcast_to(nu, (B,))) if nu is not None else None
         self._ck(self._lib.g3_gp_upload(self._h, C.byref(desc), int(kind), _d(delta), stride, _d(theta), B, _d(nu_a),
@@ -435,6 +476,75 @@ class Context:
                                            _d(var), _d(covm), C.cast(C.byref(beta), _dp), C.cast(C.byref(st), _ip)),
                  "g3_gp_posterior")
         return {"mean": mean, "var": var, "cov": covm, "beta": float(beta.value), "status": int(st.value)}
+
+    # ---- multi-GPU: NCCL communicator owned by the library, block-cyclic exact GP (include/g3b.h)
+    def comm_init(self, nranks, rank, uid):
+        self._ck(self._lib.g3_comm_init(self._h, int(nranks), int(rank), uid), "g3_comm_init")
+        self.nranks, self.rank = int(nranks), int(rank)
+
+    def comm_destroy(self):
+        self._ck(self._lib.g3_comm_destroy(self._h), "g3_comm_destroy")
+
+    def comm_size(self):
+        return int(self._lib.g3_comm_size(self._h))
+
+    def comm_rank(self):
+        return int(self._lib.g3_comm_rank(self._h))
+
+    def comm_barrier(self):
+        self._ck(self._lib.g3_comm_barrier(self._h), "g3_comm_barrier")
+
+    def comm_allgather(self, arr):
+        """arr: this rank's contiguous array; returns (nranks, *arr.shape), rank order."""
+        a = np.ascontiguousarray(arr)
+        out = np.empty((self.comm_size(),) + a.shape, dtype=a.dtype)
+        self._ck(self._lib.g3_comm_allgather(self._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), a.nbytes),
+                 "g3_comm_allgather")
+        return out
+
+    def comm_allreduce(self, vals, op="sum"):
+        v = np.array(vals, dtype=np.float64, copy=True).ravel()
+        self._ck(self._lib.g3_comm_allreduce(self._h, _d(v), v.size, {"sum": 0, "max": 1, "min": 2}[op]), "g3_comm_allreduce")
+        return v
+
+    def dist_factor(self, desc, theta, nb, Pr, Pc, lookahead=True, ring=3):
+        theta = _f64(theta).ravel()
+        if theta.size != desc.n_theta:
+            raise ValueError("dist_factor: theta has %d entries, the descriptor takes %d" % (theta.size, desc.n_theta))
+        ld, info, mg, mp, gib = C.c_double(), C.c_int(), C.c_float(), C.c_float(), C.c_double()
+        flags = (0 if lookahead else 1) | (2 if ring == 2 else 0)
+        self._resident = None
+        self._ck(self._lib.g3_dist_factor(self._h, C.byref(desc), _d(theta), int(nb), int(Pr), int(Pc), flags,
+                                          C.cast(C.byref(ld), _dp), C.cast(C.byref(info), _ip), C.byref(mg), C.byref(mp),
+                                          C.cast(C.byref(gib), _dp)), "g3_dist_factor")
+        return {"logdet": float(ld.value), "info": int(info.value), "ms_gram": float(mg.value), "ms_potrf": float(mp.value),
+                "local_gib": float(gib.value)}
+
+    def dist_solve(self, delta, want_u=False):
+        delta = _f64(delta).ravel()
+        if delta.size != self.N:
+            raise ValueError("dist_solve: delta must have N = %d entries" % self.N)
+        beta, ms = C.c_double(), C.c_float()
+        u = np.empty(self.N) if want_u else None
+        self._ck(self._lib.g3_dist_solve(self._h, _d(delta), C.cast(C.byref(beta), _dp), _d(u), C.byref(ms)), "g3_dist_solve")
+        return {"beta": float(beta.value), "u": u, "ms_solve": float(ms.value)}
+
+    def dist_residual(self, nvec=4, seed=1234):
+        out = np.zeros(4)
+        self._ck(self._lib.g3_dist_residual(self._h, int(nvec), int(seed), _d(out)), "g3_dist_residual")
+        return out[:nvec]
+
+    def dist_read_piece(self, J, nb):
+        cnt = C.c_int()
+        self._ck(self._lib.g3_dist_read_piece(self._h, int(J), None, C.cast(C.byref(cnt), _ip)), "g3_dist_read_piece")
+        if cnt.value == 0:
+            return None
+        out = np.empty((cnt.value * nb, nb))
+        self._ck(self._lib.g3_dist_read_piece(self._h, int(J), _d(out), C.cast(C.byref(cnt), _ip)), "g3_dist_read_piece")
+        return out
+
+    def dist_free(self):
+        self._ck(self._lib.g3_dist_free(self._h), "g3_dist_free")
 
     # ---- big-matrix Cholesky
     def gram_potrf_device(self, desc, theta):

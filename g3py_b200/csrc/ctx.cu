@@ -172,6 +172,7 @@ int g3_ctx_destroy(g3_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  g3_dist_destroy(ctx);
   for (auto& kv : ctx->bufs)
     if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : ctx->pinned)
@@ -201,6 +202,22 @@ int g3_ctx_destroy(g3_ctx* ctx) {
 }
 
 const char* g3_last_error(g3_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+// Free every cached workspace (device and pinned).  The context stays usable: buffers are re-created on demand.
+int g3_ctx_trim(g3_ctx* ctx) {
+  if (!ctx) return -1;
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  G3_CUDA(ctx, cudaDeviceSynchronize());
+  for (auto& kv : ctx->bufs)
+    if (kv.second.p) cudaFree(kv.second.p);
+  ctx->bufs.clear();
+  for (auto& kv : ctx->pinned)
+    if (kv.second.p) cudaFreeHost(kv.second.p);
+  ctx->pinned.clear();
+  ctx->gp.valid = 0;
+  ctx->gp.factor_resident = 0;
+  return 0;
+}
 
 int g3_sync(g3_ctx* ctx) {
   G3_CUDA(ctx, cudaSetDevice(ctx->device));

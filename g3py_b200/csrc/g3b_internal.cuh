@@ -65,7 +65,9 @@ struct g3_ctx {
   int trtri_pipeline = 1, trtri_done = 0;
   int force_left = 0;                  // set by g3_gp_run for batches of more than 8 items (their stream groups hold 8)
   int splitk = 1;                      // allow split-K for few-tile / deep-K GEMM launches (g3_set_splitk)
+  struct g3_dist* dist = nullptr;      // multi-GPU state (dist.cu): NCCL communicator, block-cyclic panels
 };
+void g3_dist_destroy(g3_ctx* ctx);     // called by g3_ctx_destroy
 
 enum { G3_PROF_GEMM = 0, G3_PROF_DIAG = 1, G3_PROF_GRAM = 2, G3_PROF_VJP = 3, G3_PROF_TRSV = 4, G3_PROF_OTHER = 5, G3_PROF_N = 6 };
 void g3_prof_begin(g3_ctx* ctx, int cls);
@@ -134,6 +136,8 @@ int g3_potrf_panel(g3_ctx* ctx, double* P, int rows, int nb, double* Dinv, doubl
 // D[x][y] -= sum_k P[row_off + x][k] P[row_off + y][k]   (D: rowsD x nb, ld = nb; P: rowsP x nb)
 int g3_syrk_panel(g3_ctx* ctx, const double* P, int rowsP, int nb, int row_off, double* D, int rowsD);
 int g3_trsv_panel(g3_ctx* ctx, const double* P, int rows, int nb, const double* Dinv, double* r, double* u, double* beta);
+int g3_panel_solve(g3_ctx* ctx, double* P, int rows, int nb, const double* Ld, const double* Dinv);
+int g3_panel_update(g3_ctx* ctx, double* D, int rows, int nb, const double* A, const double* Bm, int has_diag);
 int g3_trtri_batched(g3_ctx* ctx, const double* L, double* U, int Np, int B, const double* Dinv);
 int g3_lauum_batched(g3_ctx* ctx, const double* U, double* Kinv, int Np, int B);
 int g3_trsv_fwd(g3_ctx* ctx, const double* L, const double* Dinv, double* r, double* u, double* beta,

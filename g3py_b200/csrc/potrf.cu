@@ -596,6 +596,61 @@ int g3_syrk_panel(g3_ctx* ctx, const double* P, int rowsP, int nb, int row_off, 
   return g3_gemm_launch(ctx, tmA, tmB, g, 1);
 }
 
+// Rows of a panel below (or beside) an already factored nb x nb diagonal block Ld (lower, ld = nb) whose 128x128 block
+// inverses are Dinv:  P <- P Ld^-T, tile column by tile column (left-looking), all through the NT GEMM.  P: rows x nb.
+// This is the part of g3_potrf_panel that does not need the diagonal kernel; in the 2-D block-cyclic layout the
+// process rows that do not own the diagonal block run it on a received copy of Ld / Dinv.
+int g3_panel_solve(g3_ctx* ctx, double* P, int rows, int nb, const double* Ld, const double* Dinv) {
+  if (rows % TS || nb % TS || rows <= 0) return g3_fail_msg(ctx, "panel_solve: rows/nb must be positive multiples of 128");
+  const int Tr = rows / TS, w = nb / TS;
+  CUtensorMap tmA, tmL, tmD;
+  int rc;
+  if ((rc = g3_make_tmap(ctx, &tmA, P, nb, rows, 1, nb, (uint64_t)rows * nb, G3_BM))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmL, Ld, nb, nb, 1, nb, (uint64_t)nb * nb, G3_BN))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmD, Dinv, TS, (uint64_t)w * TS, 1, TS, (uint64_t)w * TS * TS, G3_BN))) return rc;
+  for (int j = 0; j < w; ++j) {
+    if (j > 0) {  // P[:, j] -= P[:, 0:j] Ld[j, 0:j]^T
+      GemmArgs g = gemm_zero();
+      g.D = P; g.ldd = nb; g.strideD = 0;
+      g.mode = 0; g.ntx = Tr; g.nty = 1;
+      g.d_r0 = 0; g.d_c0 = j * TS;
+      g.a_r0 = 0; g.a_rx = TS; g.ka0 = 0;
+      g.b_r0 = j * TS; g.kb0 = 0;
+      g.kl0 = j * TS;
+      g.alpha = -1.0; g.beta = 1.0;
+      if ((rc = g3_gemm_launch(ctx, tmA, tmL, g, 1))) return rc;
+    }
+    GemmArgs g = gemm_zero();  // P[:, j] = P[:, j] Linv_jj^T
+    g.D = P; g.ldd = nb; g.strideD = 0;
+    g.mode = 0; g.ntx = Tr; g.nty = 1;
+    g.d_r0 = 0; g.d_c0 = j * TS;
+    g.a_r0 = 0; g.a_rx = TS; g.ka0 = j * TS;
+    g.b_r0 = j * TS; g.kb0 = 0;
+    g.kl0 = TS;
+    g.alpha = 1.0; g.beta = 0.0; g.tri_b = 1;
+    if ((rc = g3_gemm_launch(ctx, tmA, tmD, g, 1))) return rc;
+  }
+  return 0;
+}
+
+// D[x][y] -= sum_k A[x][k] Bm[y][k]   (D, A: rows x nb, ld = nb; Bm: nb x nb).  has_diag: the first nb rows of D are a
+// diagonal block of the symmetric matrix (only its lower triangle is needed: tiles above it are skipped).
+int g3_panel_update(g3_ctx* ctx, double* D, int rows, int nb, const double* A, const double* Bm, int has_diag) {
+  if (rows % TS || nb % TS || rows <= 0) return g3_fail_msg(ctx, "panel_update: bad geometry");
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = g3_make_tmap(ctx, &tmA, A, nb, rows, 1, nb, (uint64_t)rows * nb, G3_BM))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmB, Bm, nb, nb, 1, nb, (uint64_t)nb * nb, G3_BN))) return rc;
+  GemmArgs g = gemm_zero();
+  g.D = D; g.ldd = nb; g.strideD = 0;
+  g.mode = 0; g.ntx = rows / TS; g.nty = nb / TS;
+  g.a_r0 = 0; g.a_rx = TS;
+  g.b_r0 = 0; g.b_ry = TS;
+  g.kl0 = nb;
+  g.alpha = -1.0; g.beta = 1.0; g.upper = has_diag ? (1 | 4) : 0;
+  return g3_gemm_launch(ctx, tmA, tmB, g, 1);
+}
+
 // U = L^-T (row-major upper).  Diagonal tiles of U are Linv_jj^T, rebuilt here from Dinv.
 namespace {
 __global__ void __launch_bounds__(256)

@@ -100,6 +100,9 @@ enum { G3_POST_NOISE = 1,   /* noise=True: K** gets the Noise variance (elliptic
  * where theano's `perform` keeps device state between calls (libs/tensors.py:215-222). */
 int g3_ctx_create(int device, g3_ctx** out);
 int g3_ctx_destroy(g3_ctx* ctx);
+/* Release every cached workspace of the context (they are re-created on demand): lets one process run a 60 GiB
+ * single-matrix factorisation after a batched evaluation that held 16 GiB of workspaces. */
+int g3_ctx_trim(g3_ctx* ctx);
 const char* g3_last_error(g3_ctx* ctx);
 int g3_sync(g3_ctx* ctx);
 /* constants of the reference graph, supplied by the host so that "strict" (float32-rounded)
@@ -226,11 +229,54 @@ int g3_gp_posterior(g3_ctx* ctx, const g3_kernel_desc* desc, const double* Xs, i
                     double* mean_out, double* var_out, double* cov_out_or_NULL,
                     double* beta_out_or_NULL, int* status);
 
-/* ---- multi-GPU exact GP: device-pointer building blocks ---------------------------------------
- * Used by g3py_b200/dist_potrf.py (2-D block-cyclic Cholesky on a 1 x G process grid, panel
- * broadcast over NCCL).  Not in the reference.  All pointers below are DEVICE
- * pointers owned by the caller (torch tensors); work is issued on the context's stream, which
- * g3_set_stream can point at the caller's stream so that it orders with torch.distributed.
+/* ---- multi-GPU (SURVEY §8 b/e) ---------------------------------------------------------------------------------
+ * One process per GPU; the library owns the NCCL communicator (libnccl.so.2 is dlopen'ed on first use; no torch).
+ * Not in the reference: its only parallelism is multiprocessing.Pool.map over chain groups
+ * (g3py/processes/stochastic.py:775-783).  The host distributes the 128-byte id of rank 0 to the other ranks
+ * (g3py_b200/comm.py: file or TCP rendezvous from MASTER_ADDR / MASTER_PORT / RANK / WORLD_SIZE).
+ *   g3_comm_allgather : host buffers, bytes_per_rank from every rank, rank order - the (logp, dlogp) rows of a sharded
+ *                       theta batch / chains, 8 B (P + 1) bytes per rank
+ *   g3_comm_allreduce : host doubles in place, op 0 sum / 1 max / 2 min (max-over-ranks device times)
+ */
+#define G3_COMM_ID_BYTES 128
+int g3_comm_get_unique_id(char* id_out /* G3_COMM_ID_BYTES */);
+int g3_comm_init(g3_ctx* ctx, int nranks, int rank, const char* id /* G3_COMM_ID_BYTES; may be NULL for nranks == 1 */);
+int g3_comm_destroy(g3_ctx* ctx);
+int g3_comm_size(g3_ctx* ctx);
+int g3_comm_rank(g3_ctx* ctx);
+int g3_comm_barrier(g3_ctx* ctx);
+int g3_comm_allgather(g3_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank);
+int g3_comm_allreduce(g3_ctx* ctx, double* vals, int n, int op);
+
+/* Exact GP too large / too slow for one GPU: 2-D block-cyclic Cholesky of K = tt_to_cov(cov(X; theta)) for the data of
+ * g3_set_data (replicated on every rank) on a Pr x Pc process grid, Pr * Pc = communicator size (1 x 1 without a
+ * communicator).  Block size nb (multiple of 128 dividing N); rank r = q Pr + p holds, for every panel J = q (mod Pc),
+ * the blocks (I, J), I >= J, I = p (mod Pr).  Semantics of the factor: CholeskyRobust.perform without the jitter ladder
+ * (g3py/libs/tensors.py:197-201); *info = 1-based index of the first non-positive pivot, 0 if none.  The pieces stay on
+ * the devices for g3_dist_solve / g3_dist_residual until g3_dist_free or the next g3_dist_factor.
+ * Times are device times (CUDA events), max over ranks.  All ranks must make the same calls in the same order. */
+enum { G3_DIST_NO_LOOKAHEAD = 1,   /* factor panel J+1 only after the whole trailing update of panel J (for comparison) */
+       G3_DIST_RING2 = 2 };        /* two panel buffers instead of three */
+int g3_dist_factor(g3_ctx* ctx, const g3_kernel_desc* desc, const double* theta, int nb, int Pr, int Pc, int flags,
+                   double* logdet /* sum log diag L */, int* info, float* ms_gram, float* ms_potrf, double* local_gib);
+/* u = L^-1 delta (delta: N host doubles, read on rank 0), beta = u'u - the quadratic form of logp_cho
+ * (g3py/processes/gaussian.py:212-215); u_out_or_NULL receives u (N) on every rank. */
+int g3_dist_solve(g3_ctx* ctx, const double* delta, double* beta, double* u_out_or_NULL, float* ms);
+/* Correctness probe on the hardware: nvec (<= 4) seeded +-1 vectors v, rel_err[k] = max|L (L^T v) - K v| / max|K v| with
+ * K regenerated from X (never stored). */
+int g3_dist_residual(g3_ctx* ctx, int nvec, unsigned seed, double* rel_err);
+/* Test accessor: this rank's piece of panel J (count * nb x nb row-major) -> host (may be NULL to query *count). */
+int g3_dist_read_piece(g3_ctx* ctx, int J, double* host_or_NULL, int* count);
+int g3_dist_free(g3_ctx* ctx);
+/* Layout arithmetic only (no device): out4 = {owner rank of block (I, J), first block row of piece (J, p),
+ * blocks in piece (J, p), index of block (I, J) inside its piece}. */
+int g3_dist_layout(int N, int nb, int Pr, int Pc, int I, int J, int p, int* out4);
+/* factor + solve in one call (ms3 = {gram, potrf, solve}). */
+int g3_potrf_2d(g3_ctx* ctx, const g3_kernel_desc* desc, const double* theta, int nb, int Pr, int Pc, int flags,
+                const double* delta_or_NULL, double* logdet, double* beta_or_NULL, int* info, float* ms3);
+
+/* Device-pointer building blocks (kept for callers that own device memory themselves; work is issued on the context's
+ * stream, which g3_set_stream can point at the caller's stream).
  *   g3_dev_gram_block : K[row0:row0+rows, col0:col0+cols] of cov(X) for the resident X (tt_to_cov
  *                       shift `diag_shift` and Noise on the global diagonal), into out (leading dim ld)
  *   g3_dev_potrf_panel: P (rows x nb, ld = nb): Cholesky of the top nb x nb block, rows below solved;

@@ -375,28 +375,83 @@ def test_repeat_runs_bitwise_identical(ctx):
     assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2])
 
 
-def test_block_cyclic_cholesky_single_gpu():
-    """The multi-GPU Cholesky driver with world=1 (device panel primitives g3_dev_*): factor == NumPy's."""
-    from g3py_b200.dist_potrf import run_dist_cholesky
+def _gpu_count():
+    import ctypes
+    try:
+        n = ctypes.c_int(0)
+        rt = ctypes.CDLL("libcuda.so.1")
+        rt.cuInit(0)
+        rt.cuDeviceGetCount(ctypes.byref(n))
+        return n.value
+    except OSError:
+        return 0
+
+
+@pytest.mark.parametrize("N,nb,lookahead", [(2048, 256, True), (2048, 256, False), (1536, 512, True), (1024, 1024, True)])
+def test_block_cyclic_cholesky_single_gpu(N, nb, lookahead):
+    """g3_dist_factor / g3_dist_solve / g3_dist_residual on a 1 x 1 grid (no communicator): every piece, u, beta and
+    log-det against NumPy's Cholesky; the residual probe agrees with a host computation of the same quantity."""
+    from g3py_b200.dist import run_dist_cholesky
     from g3py_b200 import workloads
-    N, nb = 2048, 256
-    r = run_dist_cholesky(N, nb=nb, verify=True)
-    X, y = workloads.c5_inputs(N)
-    d = ((X[:, None, :] - X[None, :, :]) ** 2 * 0.5).sum(-1)
-    L = np.linalg.cholesky(np.exp(-d) + 0.01 * np.eye(N))
-    assert r["info"] == 0
-    assert abs(r["logdet"] - np.log(np.diag(L)).sum()) <= 1e-9 * abs(np.log(np.diag(L)).sum())
-    for J, P in r["panels"].items():
-        want = L[J * nb:, J * nb:(J + 1) * nb]
-        assert np.abs(np.tril(P[:nb]) - want[:nb]).max() < 1e-11
-        if P.shape[0] > nb:
-            assert np.abs(P[nb:] - want[nb:]).max() < 1e-11
-    uref = np.linalg.solve(L, y)                                # distributed forward solve (here world = 1)
-    for J, v in r["u"].items():
-        assert np.abs(v - uref[J * nb:(J + 1) * nb]).max() < 1e-10
-    assert abs(r["beta"] - uref @ uref) <= 1e-10 * (uref @ uref)
-    want_logp = -0.5 * N * np.log(2 * np.pi) - 0.5 * (uref @ uref) - np.log(np.diag(L)).sum()
-    assert abs(r["logp"] - want_logp) <= 1e-10 * abs(want_logp)
+    ctx = g3.Context(0)
+    try:
+        r = run_dist_cholesky(ctx, N, nb=nb, lookahead=lookahead, verify=4)
+        X, y = workloads.c5_inputs(N)
+        d = ((X[:, None, :] - X[None, :, :]) ** 2 * 0.5).sum(-1)
+        L = np.linalg.cholesky(np.exp(-d) + 0.01 * np.eye(N))
+        assert r["info"] == 0 and r["grid"] == [1, 1]
+        assert abs(r["logdet"] - np.log(np.diag(L)).sum()) <= 1e-10 * abs(np.log(np.diag(L)).sum())
+        for J in range(N // nb):
+            P = ctx.dist_read_piece(J, nb)
+            want = L[J * nb:, J * nb:(J + 1) * nb]
+            assert P.shape == want.shape
+            assert np.abs(np.tril(P[:nb]) - want[:nb]).max() < 1e-11
+            if P.shape[0] > nb:
+                assert np.abs(P[nb:] - want[nb:]).max() < 1e-11
+        s = ctx.dist_solve(y, want_u=True)
+        uref = np.linalg.solve(L, y)
+        assert np.abs(s["u"] - uref).max() < 1e-10
+        assert abs(r["beta"] - uref @ uref) <= 1e-10 * (uref @ uref) and s["beta"] == r["beta"]
+        want_logp = -0.5 * N * np.log(2 * np.pi) - 0.5 * (uref @ uref) - np.log(np.diag(L)).sum()
+        assert abs(r["logp"] - want_logp) <= 1e-10 * abs(want_logp)
+        assert len(r["residual"]) == 4 and max(r["residual"]) < 1e-12
+    finally:
+        ctx.close()
+
+
+def test_block_cyclic_cholesky_detects_indefinite_matrix():
+    """*info = 1-based index of the first non-positive pivot (no ladder on the distributed path)."""
+    from g3py_b200.dist import se_noise_desc
+    X = np.random.default_rng(0).uniform(0, 3, size=(1024, 2))
+    X[700] = X[10]                                           # duplicated input, no noise: singular at pivot 701
+    ctx = g3.Context(0)
+    try:
+        ctx.set_data(X)
+        f = ctx.dist_factor(se_noise_desc(X), np.array([1.0, 1.0, 1.0, 0.0]), 256, 1, 1)
+        assert 600 < f["info"] <= 701
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("world,grid", [(2, "1x2"), (2, "2x1"), (4, "2x2"), (4, "1x4"), (4, "4x1"), (8, "2x4")])
+def test_block_cyclic_cholesky_multi_gpu(world, grid):
+    """The same checks on `world` GPUs (one process per GPU, NCCL inside libg3b.so, file rendezvous): every rank
+    compares its pieces, u, beta and log-det with NumPy's Cholesky and runs the residual probe.  Needs `world` GPUs."""
+    import os
+    import subprocess
+    import sys
+    if _gpu_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + world), os.path.join(root, "tools", "dist_chol.py"), "4096", "256", "--grid", grid,
+           "--check", "--verify", "--reps", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("check ok") == world
+    import json
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert max(res["residual"]) < 1e-12 and res["max_abs_err_vs_numpy"] < 1e-10
 
 
 def test_c3_full_size_posterior():

@@ -305,64 +305,46 @@ def test_theta_sharding_gloo_world2():
     assert "SHARD_OK" in r.stdout
 
 
-_DIST_WORKER = r'''
+_DIST_WORKER = r"""
 import os, sys
-sys.path.insert(0, os.environ["G3_ROOT"])
-import numpy as np, torch, torch.distributed as dist
-from g3py_b200.dist_potrf import DistCholesky, panel_owner
-world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+sys.path.insert(0, os.environ["G3_ROOT"]); sys.path.insert(0, os.path.join(os.environ["G3_ROOT"], "tests"))
+import numpy as np
+from dist_model import DistModel, LocalComm, GlooComm
+world = int(os.environ.get("WORLD_SIZE", "1"))
 if world > 1:
+    import torch.distributed as dist
     dist.init_process_group("gloo")
-N, nb = 1536, 256
+    comm = GlooComm()
+else:
+    comm = LocalComm()
+N, nb = 1536, 128
 rng = np.random.default_rng(0)
 A = rng.standard_normal((N, N + 8)); K = A @ A.T / N + np.eye(N)
 Lref = np.linalg.cholesky(K)
-
-class NumpyBackend:                       # CPU double of the three g3_dev_* panel primitives
-    def alloc(self, n): return torch.zeros(n, dtype=torch.float64)
-    def scalars(self): return torch.zeros(1, dtype=torch.float64), torch.zeros(1, dtype=torch.int32)
-    def gram(self, out, row0, col0, rows, cols): out.copy_(torch.from_numpy(K[row0:row0 + rows, col0:col0 + cols].copy()).reshape(-1))
-    def factor(self, P, rows, nb, logdet, info, dinv=None):
-        M = P.numpy().reshape(rows, nb)
-        L = np.linalg.cholesky(M[:nb]); M[:nb] = L
-        if rows > nb: M[nb:] = np.linalg.solve(L, M[nb:].T).T
-        logdet += float(np.log(np.diag(L)).sum())
-    def trsv(self, P, rows, nb, dinv, r, u, beta):
-        M = P.numpy().reshape(rows, nb); rv = r.numpy()
-        uu = np.linalg.solve(np.tril(M[:nb]), rv[:nb]); u.copy_(torch.from_numpy(uu))
-        if rows > nb: rv[nb:] -= M[nb:] @ uu
-        beta += float(uu @ uu)
-    def update(self, P, rows_p, nb, row_off, D, rows_d):
-        Pm = P.numpy().reshape(rows_p, nb); Dm = D.numpy().reshape(rows_d, nb)
-        Dm -= Pm[row_off:row_off + rows_d] @ Pm[row_off:row_off + nb].T
-
-for la in (True, False):
-    ch = DistCholesky(N, nb, rank, world, NumpyBackend(), dist if world > 1 else None, lookahead=la)
-    ch.build(); ch.factor()
-    for J in ch.mine:
-        got = ch.panel(J).numpy().reshape(ch.rows[J], nb)
-        want = Lref[J * nb:, J * nb:(J + 1) * nb]
-        err = np.abs(np.tril(got[:nb]) - want[:nb]).max() + (np.abs(got[nb:] - want[nb:]).max() if ch.rows[J] > nb else 0.0)
-        assert err < 1e-10, (la, J, err)
-    ld = ch.logdet.clone()
-    if world > 1: dist.all_reduce(ld)
-    assert abs(ld.item() - np.log(np.diag(Lref)).sum()) < 1e-9
-    dvec = torch.from_numpy(np.sin(np.arange(N) * 0.01))
-    up, beta = ch.solve(dvec, lambda n: torch.zeros(n, dtype=torch.float64), (lambda t: dist.all_reduce(t)) if world > 1 else (lambda t: None))
-    uref = np.linalg.solve(Lref, dvec.numpy())
-    for J, v in up.items():
-        assert np.abs(v.numpy() - uref[J * nb:(J + 1) * nb]).max() < 1e-10
-    if world > 1: dist.all_reduce(beta)
-    assert abs(beta.item() - uref @ uref) < 1e-9 * (uref @ uref)
-    assert ch.local_bytes() == 8 * sum((N - J * nb) * nb for J in range(rank, N // nb, world))
-if rank == 0: print("DIST_OK", flush=True)
+dvec = np.sin(np.arange(N) * 0.01)
+uref = np.linalg.solve(Lref, dvec)
+for Pr in range(1, world + 1):
+    if world % Pr:
+        continue
+    m = DistModel(K, nb, Pr, world // Pr, comm).factor()
+    m.check_against(Lref)
+    ld = float(comm.allreduce(np.array([m.logdet]))[0])
+    assert abs(ld - np.log(np.diag(Lref)).sum()) < 1e-9
+    u, beta = m.solve(dvec)
+    assert np.abs(u - uref).max() < 1e-10 and abs(beta - uref @ uref) < 1e-9 * (uref @ uref)
+    held = sum(v.size for v in m.store.values())
+    tot = float(comm.allreduce(np.array([float(held)]))[0])
+    assert tot == nb * nb * (N // nb) * (N // nb + 1) / 2            # every block of the lower triangle exactly once
+if comm.rank == 0: print("DIST_OK", flush=True)
 if world > 1: dist.destroy_process_group()
-'''
+"""
 
 
-@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("world", [1, 2, 4])
 def test_block_cyclic_cholesky_schedule(world):
-    """Schedule / indexing / look-ahead of the multi-GPU Cholesky with NumPy panel primitives over gloo."""
+    """The 2-D block-cyclic schedule of csrc/dist.cu (pieces, diagonal-block exchange inside a process column, grouped
+    piece broadcasts, per-panel all-reduce of the substitution) restated with NumPy blocks (tests/dist_model.py), one
+    process per rank over gloo, on every Pr x Pc grid of the world size."""
     env = dict(os.environ, G3_ROOT=ROOT, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
     with tempfile.TemporaryDirectory() as d:
         f = os.path.join(d, "w.py")
@@ -375,6 +357,40 @@ def test_block_cyclic_cholesky_schedule(world):
         r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "DIST_OK" in r.stdout
+
+
+def test_dist_layout_of_the_library_matches_the_model():
+    """g3_dist_layout (pure index arithmetic of libg3b.so, no device) against the Python restatement: owner, first
+    block, block count and in-piece index for every block of several grids; every block has exactly one owner."""
+    from dist_model import first_blk, cnt_blk
+    from g3py_b200 import _cabi
+    for (nP, Pr, Pc) in [(6, 1, 1), (7, 1, 3), (8, 2, 1), (9, 2, 2), (12, 2, 4), (10, 4, 2), (5, 3, 1)]:
+        nb, N = 128, 128 * nP
+        seen = {}
+        for J in range(nP):
+            for I in range(J, nP):
+                for p in range(Pr):
+                    lay = _cabi.dist_layout(N, nb, Pr, Pc, I, J, p)
+                    assert lay["first"] == first_blk(J, p, Pr) and lay["count"] == cnt_blk(J, p, Pr, nP)
+                    assert lay["owner"] == (J % Pc) * Pr + I % Pr
+                    assert lay["index"] == (I - first_blk(J, I % Pr, Pr)) // Pr
+                seen[(I, J)] = lay["owner"]
+            assert sum(cnt_blk(J, p, Pr, nP) for p in range(Pr)) == nP - J
+        assert len(seen) == nP * (nP + 1) // 2
+    with pytest.raises(ValueError):
+        _cabi.dist_layout(1000, 128, 1, 1, 0, 0, 0)                  # N not a multiple of nb
+
+
+def test_comm_rendezvous_file(tmp_path, monkeypatch):
+    """g3py_b200.comm: rank 0 publishes the 128-byte NCCL id atomically, the other ranks read the same bytes."""
+    from g3py_b200 import comm
+    monkeypatch.setenv("G3_RDV_FILE", str(tmp_path / "rdv"))
+    monkeypatch.setattr(comm, "_SEQ", [0])
+    uid0, path = comm.exchange_id(0, 2)
+    monkeypatch.setattr(comm, "_SEQ", [0])
+    uid1, _ = comm.exchange_id(1, 2, timeout=5)
+    assert uid0 == uid1 and len(uid0) == 128 and os.path.exists(path)
+    assert comm.grid_for(8) == (2, 4) and comm.grid_for(4) == (2, 2) and comm.grid_for(2) == (1, 2) and comm.grid_for(1) == (1, 1)
 
 
 def test_batched_drivers_on_fake(fake):
