@@ -735,9 +735,22 @@ bool g3_desc_is_additive(const g3_kernel_desc& d);
 void g3_gram_fwd_add_launch(const g3_kernel_desc& desc, const GramArgs& a, int ntx, dim3 grid, cudaStream_t s);
 int g3_gram_vjp_add_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const VjpArgs& a, int ntx, double* partials,
                            int ntiles, dim3 grid, cudaStream_t s);
+// second-generation fast path (gram_add.cu, "fast2"): metric leaves on <= 8 columns, leaf-outer loop nest
+bool g3_desc_is_fast2(const g3_kernel_desc& d, int same);
+int g3_gram_fwd_fast2_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const GramArgs& a, int ntx, dim3 grid, cudaStream_t s);
+int g3_gram_vjp_fast2_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const VjpArgs& a, int ntx, double* partials, int ntiles,
+                             dim3 grid, cudaStream_t s);
+static int fast_mode() {           // G3_NO_FAST=1: generic interpreter only; G3_NO_FAST=2: first-generation fast path only
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("G3_NO_FAST"); mode = e ? atoi(e) : 0; }
+  return mode;
+}
+static bool use_fast2(const g3_kernel_desc& desc, int D, int same) {
+  return fast_mode() == 0 && D <= 8 && g3_desc_is_fast2(desc, same);
+}
 static bool use_fast_path(const g3_kernel_desc& desc, int D) {
   static int off = -1;
-  if (off < 0) { const char* e = getenv("G3_NO_FAST"); off = (e && e[0] == '1') ? 1 : 0; }
+  if (off < 0) off = fast_mode() == 1 ? 1 : 0;
   return !off && D <= 4 && g3_desc_is_additive(desc);
 }
 
@@ -748,7 +761,9 @@ int g3_gram_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const GramArgs& a, i
   const long long ntiles = a.lower_only ? (long long)tr * (tr + 1) / 2 : (long long)tr * tc;
   const size_t smem = sizeof(double) * (2 * TS * a.D + G3_MAX_THETA);
   g3_prof_begin(ctx, G3_PROF_GRAM);
-  if (use_fast_path(desc, a.D))
+  if (use_fast2(desc, a.D, a.same)) {
+    if ((rc = g3_gram_fwd_fast2_launch(ctx, desc, a, tr, dim3((unsigned)ntiles, B), ctx->stream))) return rc;
+  } else if (use_fast_path(desc, a.D))
     g3_gram_fwd_add_launch(desc, a, tr, dim3((unsigned)ntiles, B), ctx->stream);
   else
     gram_fwd_kernel<<<dim3((unsigned)ntiles, B), 256, smem, ctx->stream>>>(desc, a, tr);
@@ -784,7 +799,9 @@ int g3_gram_vjp_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const VjpArgs& a
   }
   if (a.P == 0) return 0;
   g3_prof_begin(ctx, G3_PROF_VJP);
-  if (use_fast_path(desc, a.D)) {
+  if (use_fast2(desc, a.D, a.same)) {
+    if ((rc = g3_gram_vjp_fast2_launch(ctx, desc, a, tr, partials, (int)ntiles, dim3((unsigned)ntiles, B), ctx->stream))) return rc;
+  } else if (use_fast_path(desc, a.D)) {
     if ((rc = g3_gram_vjp_add_launch(ctx, desc, a, tr, partials, (int)ntiles, dim3((unsigned)ntiles, B), ctx->stream))) return rc;
   } else {
     gram_vjp_kernel<<<dim3((unsigned)ntiles, B), 256, smem, ctx->stream>>>(desc, a, tr, partials, (int)ntiles);

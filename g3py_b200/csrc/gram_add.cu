@@ -472,3 +472,481 @@ int g3_gram_vjp_add_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const VjpArg
   }
   return 0;
 }
+
+// ====================================================================================================================
+// Second-generation fast path ("fast2"): additive trees whose leaves are SE / OU / MAT32 / MAT52 / RQ / SIN / Noise / WN
+// on up to 8 input columns.  ncu on the first fast path (r01c): fp64 pipe 40 % busy but issue slots 74 % - 2.7 non-fp64
+// instructions per fp64 instruction (per-element leaf-table loads, a runtime switch per element, shared-memory
+// accumulators in the VJP).  Here the loop nest is turned inside out:
+//   for each leaf (ONE runtime switch per leaf and tile)  ->  templated body, leaf constants in registers
+//     for 16 rows x 4 columns per thread                  ->  straight-line fp64 code
+// and the coordinates are centred on X2[0] and pre-scaled by sqrt(0.5) rate_k per leaf, so the ARD metric costs one DADD
+// and one DFMA per dimension and element:  d = sum_k (s_k (x_ik - o_k) - s_k (x_jk - o_k))^2.  The same origin for every
+// tile keeps K[i][j] == K[j][i] to the bit.  Gradients with respect to rate_k use dK/drate_k = dk/dd * (2 / rate_k) * d_k.
+// ====================================================================================================================
+namespace {
+
+struct Leaf2 {
+  int op, dim0, dim1, var_idx, p0_idx, p1_idx;
+  double var;
+  double s[8];      // SE/MAT/RQ: sqrt(0.5) rate_k; OU: rate_k; SIN: freq_k   (0 outside [dim0, dim1))
+  double r[8];      // rate_k (SIN: rate_k)
+  double alpha;     // RQ
+};
+
+__device__ __forceinline__ int build_leaf2(const g3_kernel_desc& desc, const double* th, Leaf2* tab, int skip_pn, double* noise_var) {
+  int nl = 0;
+  double nv = 0.0;
+  for (int n = 0; n < desc.n_nodes; ++n) {
+    const g3_knode& nd = desc.nodes[n];
+    if (nd.op >= G3_K_SUM) continue;
+    const double var = nd.var_idx >= 0 ? th[nd.var_idx] : nd.value;
+    if (nd.op == G3_K_NOISE) {                      // diagonal-only leaves are folded into one scalar (value); their
+      if (!(skip_pn && (nd.flags & G3_KF_PROCESS_NOISE))) nv += var;    // var gradient is handled by the caller
+      Leaf2& t = tab[nl++];
+      t.op = nd.op; t.var_idx = nd.var_idx; t.var = var; t.dim0 = t.dim1 = 0; t.p0_idx = t.p1_idx = -1;
+      continue;
+    }
+    Leaf2& t = tab[nl++];
+    t.op = nd.op; t.dim0 = nd.dim0; t.dim1 = nd.dim1; t.var_idx = nd.var_idx; t.p0_idx = nd.p0_idx; t.p1_idx = nd.p1_idx;
+    t.var = var;
+    t.alpha = nd.op == G3_K_RQ ? th[nd.p1_idx] : 0.0;
+    for (int k = 0; k < 8; ++k) {
+      t.s[k] = 0.0; t.r[k] = 0.0;
+      if (k >= nd.dim0 && k < nd.dim1 && nd.p0_idx >= 0) {
+        const double r = th[nd.p0_idx + (k - nd.dim0)];
+        t.r[k] = r;
+        t.s[k] = nd.op == G3_K_OU ? r : (nd.op == G3_K_SIN ? th[nd.p1_idx + (k - nd.dim0)] : 0.70710678118654752440 * r);
+      }
+    }
+  }
+  *noise_var = nv;
+  return nl;
+}
+
+// k(d) and (optionally) dk/dd for the metric leaves; d >= 0
+template <int OP, bool GRAD>
+__device__ __forceinline__ void kfun(double d, double alpha, double& kk, double& dk) {
+  if (OP == G3_K_SE || OP == G3_K_OU) {
+    kk = exp(-d);
+    if (GRAD) dk = -kk;
+  } else if (OP == G3_K_MAT32) {
+    const double a = 3.0 * d;
+    const double s = a > 0.0 ? a * rsqrt(a) : 0.0;
+    const double ex = exp(-s);
+    kk = fma(s, ex, ex);
+    if (GRAD) dk = -1.5 * ex;
+  } else if (OP == G3_K_MAT52) {
+    const double a = 5.0 * d;
+    const double s = a > 0.0 ? a * rsqrt(a) : 0.0;
+    const double ex = exp(-s);
+    kk = (1.0 + s + a * (1.0 / 3.0)) * ex;
+    if (GRAD) dk = -(5.0 / 6.0) * fma(s, ex, ex);
+  } else if (OP == G3_K_RQ) {
+    const double base = 1.0 + d / alpha;
+    kk = pow(base, -alpha);
+    if (GRAD) dk = -kk / base;
+  } else {  // SIN: d = sum_k rate_k sin^2(pi df f), k = exp(+2 d)
+    kk = exp(2.0 * d);
+    if (GRAD) dk = 2.0 * kk;
+  }
+}
+
+// metric pieces of one row against the thread's 4 columns.  xs: the thread's column coordinates already scaled for this
+// leaf; xi: the row's scaled coordinates.  dk_[k][e] (per-dimension pieces) only when GRAD.
+template <int OP, int DT, bool GRAD>
+__device__ __forceinline__ void metric4(const double (&xi)[DT], const double (&xs)[DT][4], const double (&rr)[DT], double (&d)[4],
+                                        double (&dk_)[DT][4]) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) d[e] = 0.0;
+#pragma unroll
+  for (int k = 0; k < DT; ++k) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const double df = xi[k] - xs[k][e];
+      double piece;
+      if (OP == G3_K_OU) piece = fabs(df);
+      else if (OP == G3_K_SIN) { const double sn = sinpi(df); piece = rr[k] * sn * sn; }
+      else piece = df * df;
+      if (OP == G3_K_SE || OP == G3_K_MAT32 || OP == G3_K_MAT52 || OP == G3_K_RQ) d[e] = fma(df, df, d[e]);
+      else d[e] += piece;
+      if (GRAD) dk_[k][e] = (OP == G3_K_SIN) ? df : piece;       // SIN keeps the scaled difference (freq gradient)
+    }
+  }
+}
+
+constexpr int RC = 2;      // rows per chunk: the chunk's accumulators / weights stay in registers (static indexing)
+
+template <int OP, int DT>
+__device__ __forceinline__ void leaf_fwd(const Leaf2& t, const double* __restrict__ x1s, const double (&xc)[DT][4], int row0,
+                                         double (&sum)[RC][4]) {
+  double sc[DT], rr[DT], xs[DT][4];
+#pragma unroll
+  for (int k = 0; k < DT; ++k) {
+    sc[k] = t.s[k];
+    rr[k] = t.r[k];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) xs[k][e] = xc[k][e] * sc[k];
+  }
+  const double var = t.var, alpha = t.alpha;
+#pragma unroll
+  for (int q = 0; q < RC; ++q) {
+    const int rl = row0 + 8 * q;
+    double xi[DT], d[4], dummy[DT][4];
+#pragma unroll
+    for (int k = 0; k < DT; ++k) xi[k] = x1s[rl * DT + k] * sc[k];
+    metric4<OP, DT, false>(xi, xs, rr, d, dummy);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      double kk, dk;
+      kfun<OP, false>(d[e], alpha, kk, dk);
+      sum[q][e] = fma(var, kk, sum[q][e]);
+    }
+  }
+}
+
+// COLD: also instantiate the RQ (pow) and SIN (sinpi) leaves, whose large libdevice bodies would otherwise set the register
+// budget of the common exponential / Matern leaves
+template <int DT, bool COLD>
+__global__ void __launch_bounds__(256, 2)
+gram_fwd_fast2_kernel(const __grid_constant__ g3_kernel_desc desc, const GramArgs a, int ntx) {
+  extern __shared__ double sm[];
+  double* x1s = sm;                       // [128][DT]   centred on X2[0]
+  double* x2s = sm + TS * DT;             // [DT][128]
+  double* th = x2s + TS * DT;             // [G3_MAX_THETA]
+  Leaf2* tab = reinterpret_cast<Leaf2*>(th + G3_MAX_THETA);
+  __shared__ int n_leaves;
+  __shared__ double noise_var;
+  const int b = a.bmap ? a.bmap[blockIdx.y] : (int)blockIdx.y;
+  int tx_, ty_;
+  decode_xy(blockIdx.x, a.lower_only, ntx, tx_, ty_);
+  const int r0 = tx_ * TS, c0 = ty_ * TS;
+  for (int idx = threadIdx.x; idx < TS * DT; idx += blockDim.x) {
+    const int r = idx / DT, k = idx - r * DT;
+    const double o = a.X2[k];
+    x1s[idx] = (r0 + r < a.n1) ? a.X1[(long long)(r0 + r) * DT + k] - o : 0.0;
+    x2s[k * TS + r] = (c0 + r < a.n2) ? a.X2[(long long)(c0 + r) * DT + k] - o : 0.0;
+  }
+  for (int p = threadIdx.x; p < a.P; p += blockDim.x) th[p] = a.theta[(long long)b * a.P + p];
+  __syncthreads();
+  if (threadIdx.x == 0) n_leaves = build_leaf2(desc, th, tab, a.skip_process_noise, &noise_var);
+  __syncthreads();
+  const int nl = n_leaves;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int cc[4] = {2 * tx, 2 * tx + 1, 64 + 2 * tx, 64 + 2 * tx + 1};
+  double xc[DT][4];
+#pragma unroll
+  for (int k = 0; k < DT; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) xc[k][e] = x2s[k * TS + cc[e]];
+  const double shift = (a.diag_shift && a.same) ? a.diag_shift[b] : 0.0;
+  const double nvar = a.same ? noise_var : 0.0;
+  double* Kb = a.K + (long long)b * a.strideK;
+  int flag = 0;
+  for (int ch = 0; ch < 16 / RC; ++ch) {
+  const int row0 = ty + 8 * RC * ch;
+  double sum[RC][4];
+#pragma unroll
+  for (int q = 0; q < RC; ++q)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sum[q][e] = 0.0;
+  for (int l = 0; l < nl; ++l) {
+    const Leaf2& t = tab[l];
+    switch (t.op) {
+      case G3_K_SE: leaf_fwd<G3_K_SE, DT>(t, x1s, xc, row0, sum); break;
+      case G3_K_OU: leaf_fwd<G3_K_OU, DT>(t, x1s, xc, row0, sum); break;
+      case G3_K_MAT32: leaf_fwd<G3_K_MAT32, DT>(t, x1s, xc, row0, sum); break;
+      case G3_K_MAT52: leaf_fwd<G3_K_MAT52, DT>(t, x1s, xc, row0, sum); break;
+      case G3_K_RQ: if (COLD) leaf_fwd<G3_K_RQ, DT>(t, x1s, xc, row0, sum); break;
+      case G3_K_SIN: if (COLD) leaf_fwd<G3_K_SIN, DT>(t, x1s, xc, row0, sum); break;
+      default: break;                      // Noise / WN(same): diagonal only, added below
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < RC; ++q) {
+    const int gi = r0 + row0 + 8 * q;
+    double v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int gj = c0 + cc[e];
+      double val = sum[q][e];
+      const bool on_diag = a.same && (gi + a.diag_off == gj);
+      if (on_diag) val += nvar;
+      if (!(fabs(val) <= 1.7976931348623157e308)) { flag = 1; val = isnan(val) ? 0.0 : kInfRepl; }
+      if (on_diag) val += shift;
+      if (gi >= a.n1 || gj >= a.n2) val = (a.pad_identity && gi + a.diag_off == gj) ? 1.0 : 0.0;
+      v[e] = val;
+    }
+    double* rowp = Kb + (long long)gi * a.ldk + c0;
+    *reinterpret_cast<double2*>(rowp + cc[0]) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(rowp + cc[2]) = make_double2(v[2], v[3]);
+  }
+  }
+  if (a.status && flag) atomicOr(a.status + b, G3_ST_NONFINITE_INPUT);
+}
+
+// One leaf of the VJP: accumulates sum_ij w_ij dK_ij/dtheta for the leaf's own hypers in registers over the thread's
+// 16 x 4 elements and adds them to the thread's slots of the shared accumulator once.
+template <int OP, int DT>
+__device__ __forceinline__ void leaf_vjp(const Leaf2& t, const double* __restrict__ x1s, const double (&xc)[DT][4], int row0, int tid,
+                                         const double (&w)[RC][4], double* __restrict__ acc) {
+  double sc[DT], rr[DT], xs[DT][4];
+#pragma unroll
+  for (int k = 0; k < DT; ++k) {
+    sc[k] = t.s[k];
+    rr[k] = t.r[k];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) xs[k][e] = xc[k][e] * sc[k];
+  }
+  const double alpha = t.alpha;
+  double g_var = 0.0, g_alpha = 0.0, g_r[DT], g_f[DT];
+#pragma unroll
+  for (int k = 0; k < DT; ++k) g_r[k] = g_f[k] = 0.0;
+#pragma unroll
+  for (int q = 0; q < RC; ++q) {
+    const int rl = row0 + 8 * q;
+    double xi[DT], d[4], pc[DT][4];
+#pragma unroll
+    for (int k = 0; k < DT; ++k) xi[k] = x1s[rl * DT + k] * sc[k];
+    metric4<OP, DT, true>(xi, xs, rr, d, pc);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      double kk, dk;
+      kfun<OP, true>(d[e], alpha, kk, dk);
+      const double we = w[q][e];
+      g_var = fma(we, kk, g_var);
+      const double gk = we * dk;                       // times var at the end
+      if (OP == G3_K_RQ) g_alpha = fma(we * kk, -log1p(d[e] / alpha) + d[e] / (alpha + d[e]), g_alpha);
+#pragma unroll
+      for (int k = 0; k < DT; ++k) {
+        if (OP == G3_K_SIN) {                          // pc = df * f; d/drate_k = 2 K sin^2, d/dfreq_k = 2 K r sin(2 pi df f) pi df
+          const double sn = sinpi(pc[k][e]);
+          g_r[k] = fma(gk, sn * sn, g_r[k]);
+          g_f[k] = fma(gk, sinpi(2.0 * pc[k][e]) * pc[k][e], g_f[k]);
+        } else {
+          g_r[k] = fma(gk, pc[k][e], g_r[k]);
+        }
+      }
+    }
+  }
+  const double var = t.var;
+  if (t.var_idx >= 0) acc[t.var_idx * 256 + tid] += g_var;
+  if (OP == G3_K_RQ) acc[t.p1_idx * 256 + tid] += var * g_alpha;
+#pragma unroll
+  for (int k = 0; k < DT; ++k) {
+    if (k >= t.dim0 && k < t.dim1) {
+      if (OP == G3_K_SIN) {
+        // gk = w dk = 2 w K/var;  d/drate_k = var * (w K 2 sn^2) = var * gk sn^2;  d/dfreq_k = var gk r_k sin(2 pi u) pi u / f_k, u = df f
+        acc[(t.p0_idx + k - t.dim0) * 256 + tid] += var * g_r[k];
+        acc[(t.p1_idx + k - t.dim0) * 256 + tid] += var * g_f[k] * rr[k] * M_PI / sc[k];
+      } else if (OP == G3_K_OU) {
+        acc[(t.p0_idx + k - t.dim0) * 256 + tid] += var * g_r[k] / rr[k];          // pc = r |df|:  d d/dr = |df|
+      } else {
+        acc[(t.p0_idx + k - t.dim0) * 256 + tid] += var * g_r[k] * (2.0 / rr[k]);  // pc = 0.5 r^2 df^2: d d/dr = 2 pc / r
+      }
+    }
+  }
+}
+
+template <int DT, bool COLD>
+__global__ void __launch_bounds__(256, 2)
+gram_vjp_fast2_kernel(const __grid_constant__ g3_kernel_desc desc, const VjpArgs a, int ntx, double* __restrict__ partials,
+                      int ntiles) {
+  extern __shared__ double sm[];
+  double* x1s = sm;
+  double* x2s = sm + TS * DT;
+  double* th = x2s + TS * DT;
+  double* al_r = th + G3_MAX_THETA;
+  double* al_c = al_r + TS;
+  Leaf2* tab = reinterpret_cast<Leaf2*>(al_c + TS);
+  double* acc = reinterpret_cast<double*>(tab + G3_MAX_NODES);   // [P][256]
+  __shared__ int n_leaves;
+  __shared__ double noise_var;
+  __shared__ double red[8];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  int tx_, ty_;
+  decode_xy(blockIdx.x, a.lower_only, ntx, tx_, ty_);
+  const int r0 = tx_ * TS, c0 = ty_ * TS;
+  for (int idx = tid; idx < TS * DT; idx += blockDim.x) {
+    const int r = idx / DT, k = idx - r * DT;
+    const double o = a.X2[k];
+    x1s[idx] = (r0 + r < a.n1) ? a.X1[(long long)(r0 + r) * DT + k] - o : 0.0;
+    x2s[k * TS + r] = (c0 + r < a.n2) ? a.X2[(long long)(c0 + r) * DT + k] - o : 0.0;
+  }
+  for (int p = tid; p < a.P; p += blockDim.x) th[p] = a.theta[(long long)b * a.P + p];
+  if (a.alpha && tid < TS) {
+    al_r[tid] = (r0 + tid < a.n1) ? a.alpha[(long long)b * a.strideAlpha + r0 + tid] : 0.0;
+    al_c[tid] = (c0 + tid < a.n2) ? a.alpha[(long long)b * a.strideAlpha + c0 + tid] : 0.0;
+  }
+  for (int p = 0; p < a.P; ++p) acc[p * 256 + tid] = 0.0;
+  __syncthreads();
+  if (tid == 0) n_leaves = build_leaf2(desc, th, tab, 0, &noise_var);
+  __syncthreads();
+  const int nl = n_leaves;
+  const double cf = (a.alpha && a.cfac) ? a.cfac[b] : 1.0;
+  const int tx = tid & 31, ty = tid >> 5;
+  const int cc[4] = {2 * tx, 2 * tx + 1, 64 + 2 * tx, 64 + 2 * tx + 1};
+  double xc[DT][4];
+#pragma unroll
+  for (int k = 0; k < DT; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) xc[k][e] = x2s[k * TS + cc[e]];
+  const double* Wb = a.W + (long long)b * a.strideW;
+  double alc[4] = {0.0, 0.0, 0.0, 0.0};
+  if (a.alpha) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) alc[e] = al_c[cc[e]];
+  }
+  for (int ch = 0; ch < 16 / RC; ++ch) {
+    const int row0 = ty + 8 * RC * ch;
+    // weights of the chunk's RC x 4 elements (all loads in flight before the first use)
+    double w[RC][4];
+    double wdiag = 0.0;                                   // sum of the weights on the diagonal (Noise / WN var gradient)
+    {
+      double2 w01[RC], w23[RC];
+#pragma unroll
+      for (int q = 0; q < RC; ++q) {
+        const int gi = r0 + row0 + 8 * q;
+        const double* wrow = Wb + (long long)gi * a.ldw + c0;
+        w01[q] = make_double2(0.0, 0.0);
+        w23[q] = make_double2(0.0, 0.0);
+        if (gi < a.n1) {
+          w01[q] = *reinterpret_cast<const double2*>(wrow + cc[0]);
+          w23[q] = *reinterpret_cast<const double2*>(wrow + cc[2]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < RC; ++q) {
+        const int gi = r0 + row0 + 8 * q;
+        const double ar = a.alpha ? cf * al_r[row0 + 8 * q] : 0.0;
+        const double wv[4] = {w01[q].x, w01[q].y, w23[q].x, w23[q].y};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int gj = c0 + cc[e];
+          double v = a.alpha ? fma(ar, alc[e], -wv[e]) : wv[e];
+          double f = 1.0;
+          if (a.lower_only) f = (gi > gj) ? 2.0 : (gi == gj ? 1.0 : 0.0);
+          if (gi >= a.n1 || gj >= a.n2) f = 0.0;
+          v = f == 0.0 ? 0.0 : v * f;
+          w[q][e] = v;
+          if (a.same && gi == gj) wdiag += v;
+        }
+      }
+    }
+    for (int l = 0; l < nl; ++l) {
+      const Leaf2& t = tab[l];
+      switch (t.op) {
+        case G3_K_SE: leaf_vjp<G3_K_SE, DT>(t, x1s, xc, row0, tid, w, acc); break;
+        case G3_K_OU: leaf_vjp<G3_K_OU, DT>(t, x1s, xc, row0, tid, w, acc); break;
+        case G3_K_MAT32: leaf_vjp<G3_K_MAT32, DT>(t, x1s, xc, row0, tid, w, acc); break;
+        case G3_K_MAT52: leaf_vjp<G3_K_MAT52, DT>(t, x1s, xc, row0, tid, w, acc); break;
+        case G3_K_RQ: if (COLD) leaf_vjp<G3_K_RQ, DT>(t, x1s, xc, row0, tid, w, acc); break;
+        case G3_K_SIN: if (COLD) leaf_vjp<G3_K_SIN, DT>(t, x1s, xc, row0, tid, w, acc); break;
+        default:                                           // Noise / WN(same): dK/dvar = I
+          if (t.var_idx >= 0) acc[t.var_idx * 256 + tid] += wdiag;
+          break;
+      }
+    }
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int p = 0; p < a.P; ++p) {
+    double v = acc[p * 256 + tid];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int w2 = 0; w2 < 8; ++w2) s += red[w2];
+      partials[((long long)b * ntiles + blockIdx.x) * a.P + p] = s;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+// fast2 applies to additive trees of metric leaves; WN only in the cov(x) form (its cross form counts equal coordinates)
+bool g3_desc_is_fast2(const g3_kernel_desc& d, int same) {
+  for (int n = 0; n < d.n_nodes; ++n) {
+    const int op = d.nodes[n].op;
+    if (op >= G3_K_SUM) {
+      if (op != G3_K_SUM) return false;
+      continue;
+    }
+    if (op == G3_K_WN) {
+      if (!same) return false;
+      continue;
+    }
+    if (op > G3_K_NOISE) return false;                  // COS / SINC / SM / DOT / BW / VAR: first-generation paths
+    if (d.nodes[n].dim1 > 8) return false;
+  }
+  return true;
+}
+
+static bool desc_has_cold(const g3_kernel_desc& d) {
+  for (int n = 0; n < d.n_nodes; ++n)
+    if (d.nodes[n].op == G3_K_RQ || d.nodes[n].op == G3_K_SIN) return true;
+  return false;
+}
+
+size_t g3_fast2_fwd_smem(int D) { return sizeof(double) * (2 * TS * D + G3_MAX_THETA) + sizeof(Leaf2) * G3_MAX_NODES; }
+size_t g3_fast2_vjp_smem(int D, int P) {
+  return sizeof(double) * (2 * TS * D + G3_MAX_THETA + 2 * TS + (size_t)P * 256) + sizeof(Leaf2) * G3_MAX_NODES;
+}
+
+template <int DT>
+static int fast2_fwd_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const GramArgs& a, int ntx, dim3 grid, cudaStream_t s) {
+  const size_t smem = g3_fast2_fwd_smem(DT);
+  static bool attr = false;
+  if (!attr) {
+    G3_CUDA(ctx, cudaFuncSetAttribute(gram_fwd_fast2_kernel<DT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    G3_CUDA(ctx, cudaFuncSetAttribute(gram_fwd_fast2_kernel<DT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr = true;
+  }
+  if (desc_has_cold(desc)) gram_fwd_fast2_kernel<DT, true><<<grid, 256, smem, s>>>(desc, a, ntx);
+  else gram_fwd_fast2_kernel<DT, false><<<grid, 256, smem, s>>>(desc, a, ntx);
+  return 0;
+}
+
+template <int DT>
+static int fast2_vjp_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const VjpArgs& a, int ntx, double* partials, int ntiles,
+                            dim3 grid, cudaStream_t s) {
+  const size_t smem = g3_fast2_vjp_smem(DT, a.P);
+  static bool attr = false;
+  if (!attr) {
+    G3_CUDA(ctx, cudaFuncSetAttribute(gram_vjp_fast2_kernel<DT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    G3_CUDA(ctx, cudaFuncSetAttribute(gram_vjp_fast2_kernel<DT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  if (desc_has_cold(desc)) gram_vjp_fast2_kernel<DT, true><<<grid, 256, smem, s>>>(desc, a, ntx, partials, ntiles);
+  else gram_vjp_fast2_kernel<DT, false><<<grid, 256, smem, s>>>(desc, a, ntx, partials, ntiles);
+  return 0;
+}
+
+int g3_gram_fwd_fast2_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const GramArgs& a, int ntx, dim3 grid, cudaStream_t s) {
+  switch (a.D) {
+    case 1: return fast2_fwd_launch<1>(ctx, desc, a, ntx, grid, s);
+    case 2: return fast2_fwd_launch<2>(ctx, desc, a, ntx, grid, s);
+    case 3: return fast2_fwd_launch<3>(ctx, desc, a, ntx, grid, s);
+    case 4: return fast2_fwd_launch<4>(ctx, desc, a, ntx, grid, s);
+    case 5: return fast2_fwd_launch<5>(ctx, desc, a, ntx, grid, s);
+    case 6: return fast2_fwd_launch<6>(ctx, desc, a, ntx, grid, s);
+    case 7: return fast2_fwd_launch<7>(ctx, desc, a, ntx, grid, s);
+    default: return fast2_fwd_launch<8>(ctx, desc, a, ntx, grid, s);
+  }
+}
+
+int g3_gram_vjp_fast2_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const VjpArgs& a, int ntx, double* partials, int ntiles,
+                             dim3 grid, cudaStream_t s) {
+  switch (a.D) {
+    case 1: return fast2_vjp_launch<1>(ctx, desc, a, ntx, partials, ntiles, grid, s);
+    case 2: return fast2_vjp_launch<2>(ctx, desc, a, ntx, partials, ntiles, grid, s);
+    case 3: return fast2_vjp_launch<3>(ctx, desc, a, ntx, partials, ntiles, grid, s);
+    case 4: return fast2_vjp_launch<4>(ctx, desc, a, ntx, partials, ntiles, grid, s);
+    case 5: return fast2_vjp_launch<5>(ctx, desc, a, ntx, partials, ntiles, grid, s);
+    case 6: return fast2_vjp_launch<6>(ctx, desc, a, ntx, partials, ntiles, grid, s);
+    case 7: return fast2_vjp_launch<7>(ctx, desc, a, ntx, partials, ntiles, grid, s);
+    default: return fast2_vjp_launch<8>(ctx, desc, a, ntx, partials, ntiles, grid, s);
+  }
+}
