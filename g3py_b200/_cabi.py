@@ -77,6 +77,8 @@ SIGNATURES = {
     "g3_dist_factor": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _ip,
                                  C.POINTER(C.c_float), C.POINTER(C.c_float), _dp]),
     "g3_dist_solve": (C.c_int, [_ctxp, _dp, _dp, _dp, C.POINTER(C.c_float)]),
+    "g3_dist_posterior": (C.c_int, [_ctxp, _dp, C.c_int, C.c_int, _dp, _dp]),
+    "g3_dist_grad": (C.c_int, [_ctxp, C.c_double, _dp, _dp, C.POINTER(C.c_float)]),
     "g3_dist_residual": (C.c_int, [_ctxp, C.c_int, C.c_uint, _dp]),
     "g3_dist_read_piece": (C.c_int, [_ctxp, C.c_int, _dp, _ip]),
     "g3_dist_free": (C.c_int, [_ctxp]),
@@ -528,6 +530,24 @@ class Context:
         u = np.empty(self.N) if want_u else None
         self._ck(self._lib.g3_dist_solve(self._h, _d(delta), C.cast(C.byref(beta), _dp), _d(u), C.byref(ms)), "g3_dist_solve")
         return {"beta": float(beta.value), "u": u, "ms_solve": float(ms.value)}
+
+    def dist_posterior(self, Xs, noise=False):
+        Xs = _f64(Xs)
+        if Xs.ndim == 1:
+            Xs = Xs[:, None]
+        if Xs.shape[1] != self.D:
+            raise ValueError("dist_posterior: Xs must have D = %d columns" % self.D)
+        M = Xs.shape[0]
+        mean, var = np.empty(M), np.empty(M)
+        self._ck(self._lib.g3_dist_posterior(self._h, _d(Xs), M, POST_NOISE if noise else 0, _d(mean), _d(var)), "g3_dist_posterior")
+        return mean, var
+
+    def dist_grad(self, n_theta, cfac=1.0, want_ddelta=True):
+        dth = np.zeros(max(int(n_theta), 1))
+        ddl = np.empty(self.N) if want_ddelta else None
+        ms = (C.c_float * 3)()
+        self._ck(self._lib.g3_dist_grad(self._h, float(cfac), _d(dth), _d(ddl), ms), "g3_dist_grad")
+        return {"dtheta": dth[:n_theta], "ddelta": ddl, "ms_alpha": float(ms[0]), "ms_inverse": float(ms[1]), "ms_contract": float(ms[2])}
 
     def dist_residual(self, nvec=4, seed=1234):
         out = np.zeros(4)

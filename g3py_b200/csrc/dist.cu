@@ -44,6 +44,7 @@ struct NcclApi {
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -73,6 +74,7 @@ NcclApi* nccl_api(std::string* err) {
       LOADSYM(Broadcast, "ncclBroadcast")
       LOADSYM(AllReduce, "ncclAllReduce")
       LOADSYM(AllGather, "ncclAllGather")
+      LOADSYM(Reduce, "ncclReduce")
       LOADSYM(Send, "ncclSend")
       LOADSYM(Recv, "ncclRecv")
       LOADSYM(GroupStart, "ncclGroupStart")
@@ -112,7 +114,7 @@ struct g3_dist {
               ev_t[4] = {};
   g3_kernel_desc desc;
   int P = 0;
-  bool factored = false;
+  bool factored = false, solved = false;
   int lookahead = 1;
 };
 
@@ -248,6 +250,72 @@ dense_gemv_kernel(const double* __restrict__ Kc, int rows, long long n, const do
 #pragma unroll
     for (int v = 0; v < NV; ++v) y[(long long)r * NV + v] = acc[v];
   }
+}
+
+
+// dst[c][r] = src[r][c] for an (rows x cols) block, 32 x 32 tiles through shared memory (rows, cols multiples of 32)
+__global__ void __launch_bounds__(256)
+transpose_kernel(const double* __restrict__ src, long long ld_src, double* __restrict__ dst, long long ld_dst, int rows, int cols) {
+  __shared__ double tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;      // bx: column block of src, by: row block of src
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8)
+    if (by + r < rows && bx + tx < cols) tile[r][tx] = src[(long long)(by + r) * ld_src + bx + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (bx + r < cols && by + tx < rows) dst[(long long)(bx + r) * ld_dst + by + tx] = tile[tx][r];
+}
+
+// deterministic column sums of a tall panel against a vector: part[chunk][c] = sum_{r in chunk} P[r][c] x[r]
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const double* __restrict__ P, int rows, int nb, const double* __restrict__ x, double* __restrict__ part, int chunk_rows) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= nb) return;
+  const int r0 = blockIdx.y * chunk_rows, r1 = min(rows, r0 + chunk_rows);
+  double acc = 0.0;
+  for (int r = r0; r < r1; ++r) acc += P[(long long)r * nb + c] * x[r];
+  part[(long long)blockIdx.y * nb + c] = acc;
+}
+// rhs[c] = u[c] - sum_chunks part[chunk][c]
+__global__ void colsum_finish_kernel(const double* __restrict__ part, int nchunk, int nb, const double* __restrict__ u, double* __restrict__ rhs) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nb) return;
+  double acc = 0.0;
+  for (int k = 0; k < nchunk; ++k) acc += part[(long long)k * nb + c];
+  rhs[c] = u[c] - acc;
+}
+__global__ void identity_kernel(double* __restrict__ A, int n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < (long long)n * n) A[i] = (i / n == i % n) ? 1.0 : 0.0;
+}
+// mean[m] += sum_c V[m][c] u[c];  nrm[m] += sum_c V[m][c]^2   (one warp per test point, V: M x nb)
+__global__ void __launch_bounds__(256)
+post_accum_kernel(const double* __restrict__ V, int M, int nb, const double* __restrict__ u, double* __restrict__ mean, double* __restrict__ nrm) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const double* row = V + (long long)m * nb;
+  double s1 = 0.0, s2 = 0.0;
+  for (int c = lane; c < nb; c += 32) {
+    const double v = row[c];
+    s1 += v * u[c];
+    s2 += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) {
+    mean[m] += s1;
+    nrm[m] += s2;
+  }
+}
+// R[m][c] = Ks[m][c] - C[m][c]  (M x nb blocks with different leading dimensions)
+__global__ void sub_block_kernel(const double* __restrict__ Ks, long long ldk, const double* __restrict__ Cc, long long ldc, double* __restrict__ R,
+                                 int M, int nb) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)M * nb) return;
+  const long long m = i / nb, c = i - m * nb;
+  R[i] = Ks[m * ldk + c] - Cc[m * ldc + c];
 }
 
 void dist_free_matrix(g3_dist* d) {
@@ -715,6 +783,7 @@ int g3_dist_factor(g3_ctx* ctx, const g3_kernel_desc* desc, const double* theta,
   if (ms_potrf) *ms_potrf = (float)mx[1];
   if (local_gib) *local_gib = (double)(sizeof(double) * (tot + (d->ring ? d->slot_elems * d->nslot : 0))) / (double)(1ull << 30);
   d->factored = true;
+  d->solved = false;
   return 0;
 }
 
@@ -771,6 +840,7 @@ int g3_dist_solve(g3_ctx* ctx, const double* delta, double* beta_out, double* u_
   if ((rc = g3_comm_allreduce(ctx, mx, 1, 1))) return rc;
   *beta_out = red[0];
   if (ms) *ms = (float)mx[0];
+  d->solved = true;
   return 0;
 }
 
@@ -841,6 +911,266 @@ int g3_dist_residual(g3_ctx* ctx, int nvec, unsigned seed, double* rel_err) {
     }
     rel_err[v] = (num == num && den > 0.0) ? num / den : INFINITY;
   }
+  return 0;
+}
+
+
+// Posterior moments of the distributed exact GP at M test points (elliptical.py:78-107 semantics, Cholesky route):
+//   mean = K* K^-1 delta = V u,  var = max(k** - |V_m|^2, 0),  V = K* L^-T
+// by blocked forward substitution over the panels: the owner of panel J turns the true residual of its column block into
+// V_J = R_J L_JJ^-T, folds V_J u_J and |V_J|^2 into the running moments and pushes V_J L_IJ^T (I > J) into its own
+// accumulator; the residual of the next block is the sum of the accumulators over the ranks (one reduce of Mc x nb per
+// step).  K* blocks are generated on the fly by the owner.  Needs g3_dist_factor + g3_dist_solve (for u) on a 1 x G grid.
+int g3_dist_posterior(g3_ctx* ctx, const double* Xs, int M, int flags, double* mean_out, double* var_out) {
+  if (!ctx || !Xs || M <= 0 || !mean_out || !var_out) return g3_fail_msg(ctx, "g3_dist_posterior: bad arguments");
+  g3_dist* d = ctx->dist;
+  if (!d || !d->factored || !d->solved) return g3_fail_msg(ctx, "g3_dist_posterior: call g3_dist_factor and g3_dist_solve first");
+  if (d->Pr != 1) return g3_fail_msg(ctx, "g3_dist_posterior: needs a 1 x G process grid");
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  NcclApi* api = d->nranks > 1 ? nccl_api(&ctx->err) : nullptr;
+  if (d->nranks > 1 && !api) return -5;
+  const int N = d->N, nb = d->nb, nP = d->nP, G = d->nranks, D = ctx->D;
+  const int Mc = std::min(g3_pad(M), 4096);
+  cudaStream_t MS = ctx->stream;
+  const int skip_pn = (flags & G3_POST_NOISE) ? 0 : 1;
+  double* dXs = (double*)g3_ws(ctx, "dp_xs", sizeof(double) * (size_t)g3_pad(M) * D);
+  double* C = (double*)g3_ws(ctx, "dp_c", sizeof(double) * (size_t)Mc * N);
+  double* R = (double*)g3_ws(ctx, "dp_r", sizeof(double) * (size_t)Mc * nb * 2);
+  double* mom = (double*)g3_ws(ctx, "dp_mom", sizeof(double) * (size_t)g3_pad(M) * 3);
+  double* kss = (double*)g3_ws(ctx, "dp_kss", sizeof(double) * 4);
+  if (!dXs || !C || !R || !mom || !kss) return -2;
+  double* S = R + (size_t)Mc * nb;                       // packed block of the accumulator (reduce buffer)
+  const int Mp = g3_pad(M);
+  double *mean = mom, *nrm = mom + Mp, *kvec = mom + 2 * (size_t)Mp;
+  G3_CUDA(ctx, cudaMemsetAsync(dXs, 0, sizeof(double) * (size_t)Mp * D, MS));
+  G3_CUDA(ctx, cudaMemcpyAsync(dXs, Xs, sizeof(double) * (size_t)M * D, cudaMemcpyHostToDevice, MS));
+  G3_CUDA(ctx, cudaMemsetAsync(mom, 0, sizeof(double) * (size_t)Mp * 3, MS));
+  int rc;
+  if ((rc = g3_gram_diag_min(ctx, d->desc, dXs, M, D, d->dtheta, d->P, 1, kss, kss + 1, nullptr, skip_pn, kvec))) return rc;
+  for (int m0 = 0; m0 < M; m0 += Mc) {
+    const int mc = std::min(Mc, Mp - m0);                // rows of this chunk (multiple of 128; padding rows are zero inputs)
+    const int mreal = std::min(mc, M - m0);
+    G3_CUDA(ctx, cudaMemsetAsync(C, 0, sizeof(double) * (size_t)mc * N, MS));
+    for (int J = 0; J < nP; ++J) {
+      const int owner = J % G;
+      const bool mine = owner == d->rank;
+      // pack my accumulator block J (strided in C) for the sum over the ranks onto the owner
+      if (G > 1)
+        G3_CUDA(ctx, cudaMemcpy2DAsync(S, sizeof(double) * nb, C + (size_t)J * nb, sizeof(double) * N, sizeof(double) * nb, (size_t)mc,
+                                       cudaMemcpyDeviceToDevice, MS));
+      if (mine) {
+        GramArgs a;                                      // K*[chunk, J] (cross form: Noise contributes zeros, kernels.py:367-371)
+        memset(&a, 0, sizeof a);
+        a.X1 = dXs + (size_t)m0 * D; a.X2 = ctx->dX + (size_t)J * nb * D; a.n1 = mreal; a.n2 = nb; a.D = D; a.same = 0;
+        a.skip_process_noise = skip_pn;
+        a.theta = d->dtheta; a.P = d->P; a.K = R; a.ldk = nb;
+        if (mreal < mc) G3_CUDA(ctx, cudaMemsetAsync(R, 0, sizeof(double) * (size_t)mc * nb, MS));
+        if ((rc = g3_gram_launch(ctx, d->desc, a, 1))) return rc;
+      }
+      if (G > 1) G3_NCCL(ctx, api, api->Reduce(S, S, (size_t)mc * nb, ncclDouble, ncclSum, owner, d->comm, MS));
+      if (!mine) continue;
+      const double* acc = G > 1 ? S : C + (size_t)J * nb;
+      sub_block_kernel<<<(unsigned)(((size_t)mc * nb + 255) / 256), 256, 0, MS>>>(R, nb, acc, G > 1 ? nb : N, R, mc, nb);
+      G3_LAUNCH_CHECK(ctx);
+      double* piece = d->store + d->off[J];
+      if ((rc = g3_panel_solve(ctx, R, mc, nb, piece, d->dinv + d->dinv_off[J]))) return rc;     // V_J = R_J L_JJ^-T
+      post_accum_kernel<<<(mreal + 7) / 8, 256, 0, MS>>>(R, mreal, nb, d->u + (size_t)J * nb, mean + m0, nrm + m0);
+      G3_LAUNCH_CHECK(ctx);
+      const int below = (nP - 1 - J) * nb;
+      if (below > 0 &&
+          (rc = g3_panel_gemm(ctx, C + (size_t)(J + 1) * nb, N, mc, below, R, nb, piece + blk_elems(d), nb, nb, 1.0, 1.0)))
+        return rc;
+    }
+  }
+  std::vector<double> h((size_t)Mp * 3);
+  double hk[4];
+  G3_CUDA(ctx, cudaMemcpyAsync(h.data(), mom, sizeof(double) * (size_t)Mp * 3, cudaMemcpyDeviceToHost, MS));
+  G3_CUDA(ctx, cudaMemcpyAsync(hk, kss, sizeof hk, cudaMemcpyDeviceToHost, MS));
+  G3_CUDA(ctx, cudaStreamSynchronize(MS));
+  std::vector<double> red(2 * (size_t)M);
+  for (int m = 0; m < M; ++m) { red[m] = h[m]; red[M + m] = h[Mp + m]; }
+  if ((rc = g3_comm_allreduce(ctx, red.data(), 2 * M, 0))) return rc;
+  const double shift = ((flags & G3_POST_NOISE) && !(hk[0] > 0.0)) ? ctx->jitter_rel - hk[0] : 0.0;    // tt_to_cov on K** (elliptical.py:70)
+  for (int m = 0; m < M; ++m) {
+    mean_out[m] = red[m];
+    const double v = (h[2 * (size_t)Mp + m] + shift) - red[M + m];
+    var_out[m] = v < 0.0 ? 0.0 : v;                      // tt_to_bounded(.., 0)  elliptical.py:94-97
+  }
+  return 0;
+}
+
+// Gradient of the distributed exact GP (SURVEY §8 a10 on the block-cyclic layout, 1 x G grid):
+//   alpha = L^-T u (backward substitution over the panels),  X = L^-1 in place (right-looking, panel by panel from the last:
+//   X[J+1:, J] = -(X[J+1:, J+1:] L[J+1:, J]) L_JJ^-1, the product summed over the ranks' own column panels and reduced onto
+//   the owner),  K^-1[I][J] = sum_{M >= I} X[M, I]^T X[M, J] for every block pair I >= J (X panels broadcast one by one, the
+//   ranks pair them with their own panels, both transposed to K-contiguous form), each block contracted at once with
+//   dK[I][J]/dtheta regenerated from X (gram_vjp) - K^-1 is never stored:
+//   dtheta[p] = 1/2 sum_ij (c alpha_i alpha_j - K^-1_ij) dK_ij/dtheta_p,  ddelta = -c alpha.
+// The factor is consumed (L is overwritten by L^-1).  Device times (max over ranks) in ms3 = {alpha, inverse, contraction}.
+int g3_dist_grad(g3_ctx* ctx, double cfac, double* dtheta_out, double* ddelta_out_or_NULL, float* ms3) {
+  if (!ctx || !dtheta_out) return g3_fail_msg(ctx, "g3_dist_grad: bad arguments");
+  g3_dist* d = ctx->dist;
+  if (!d || !d->factored || !d->solved) return g3_fail_msg(ctx, "g3_dist_grad: call g3_dist_factor and g3_dist_solve first");
+  if (d->Pr != 1) return g3_fail_msg(ctx, "g3_dist_grad: needs a 1 x G process grid");
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  NcclApi* api = d->nranks > 1 ? nccl_api(&ctx->err) : nullptr;
+  if (d->nranks > 1 && !api) return -5;
+  const int N = d->N, nb = d->nb, nP = d->nP, G = d->nranks, w = d->w, P = d->P, D = ctx->D;
+  const size_t be = blk_elems(d), de = (size_t)w * TS * TS;
+  cudaStream_t MS = ctx->stream;
+  int nloc = 0;
+  for (int J = d->rank; J < nP; J += G) ++nloc;
+  const int nchunk = 64;
+  double* alpha = (double*)g3_ws(ctx, "dg_alpha", sizeof(double) * ((size_t)N + nb + 8));
+  double* part = (double*)g3_ws(ctx, "dg_part", sizeof(double) * (size_t)nchunk * nb);
+  double* BT = (double*)g3_ws(ctx, "dg_bt", sizeof(double) * (size_t)N * nb);
+  double* Y = (double*)g3_ws(ctx, "dg_y", sizeof(double) * (size_t)N * nb);
+  double* LT = (double*)g3_ws(ctx, "dg_lt", sizeof(double) * (2 * be + de));
+  if (!alpha || !part || !BT || !Y || !LT) return -2;
+  double* rhs = alpha + N;                               // nb scratch
+  double* cf_dev = alpha + N + nb;
+  double* EYE = LT + be;                                 // nb x nb
+  double* DT = LT + 2 * be;                              // transposed 128-block inverses
+  int rc;
+  d->factored = false;                                   // L is consumed
+  if ((rc = g3_comm_barrier(ctx))) return rc;
+  G3_CUDA(ctx, cudaMemcpyAsync(cf_dev, &cfac, sizeof(double), cudaMemcpyHostToDevice, MS));
+  G3_CUDA(ctx, cudaEventRecord(d->ev_t[0], MS));
+  // ---- alpha = L^-T u
+  for (int J = nP - 1; J >= 0; --J) {
+    const int owner = J % G;
+    double* aJ = alpha + (size_t)J * nb;
+    if (owner == d->rank) {
+      double* piece = d->store + d->off[J];
+      const int below = (nP - 1 - J) * nb;
+      int nch = 0;
+      if (below > 0) {
+        const int chunk_rows = (below + nchunk - 1) / nchunk;
+        nch = (below + chunk_rows - 1) / chunk_rows;
+        colsum_partial_kernel<<<dim3((nb + 255) / 256, nch), 256, 0, MS>>>(piece + be, below, nb, alpha + (size_t)(J + 1) * nb, part, chunk_rows);
+        G3_LAUNCH_CHECK(ctx);
+      }
+      colsum_finish_kernel<<<(nb + 255) / 256, 256, 0, MS>>>(part, nch, nb, d->u + (size_t)J * nb, rhs);
+      G3_LAUNCH_CHECK(ctx);
+      if ((rc = g3_trsv_bwd(ctx, piece, d->dinv + d->dinv_off[J], rhs, aJ, nb, 1))) return rc;
+    }
+    if (G > 1) G3_NCCL(ctx, api, api->Broadcast(aJ, aJ, nb, ncclDouble, owner, d->comm, MS));
+  }
+  G3_CUDA(ctx, cudaEventRecord(d->ev_t[1], MS));
+  // ---- X = L^-1 in place, panels from the last to the first
+  for (int J = nP - 1; J >= 0; --J) {
+    const int owner = J % G;
+    const bool mine = owner == d->rank;
+    const int below = (nP - 1 - J) * nb;
+    double* piece = mine ? d->store + d->off[J] : nullptr;
+    if (below > 0) {
+      if (mine) {  // BT[K] = L[K, J]^T for K > J
+        for (int k = 0; k < nP - 1 - J; ++k) {
+          transpose_kernel<<<dim3(nb / 32, nb / 32), 256, 0, MS>>>(piece + (size_t)(k + 1) * be, nb, BT + (size_t)k * be, nb, nb, nb);
+          G3_LAUNCH_CHECK(ctx);
+        }
+      }
+      if (G > 1) G3_NCCL(ctx, api, api->Broadcast(BT, BT, (size_t)below * nb, ncclDouble, owner, d->comm, MS));
+      G3_CUDA(ctx, cudaMemsetAsync(Y, 0, sizeof(double) * (size_t)below * nb, MS));
+      int K0 = J + 1;
+      while (K0 % G != d->rank) ++K0;
+      for (int K = K0; K < nP; K += G) {                 // Y[I >= K] += X[I, K] L[K, J]
+        const int rows = (nP - K) * nb;
+        if ((rc = g3_panel_gemm(ctx, Y + (size_t)(K - J - 1) * be, nb, rows, nb, d->store + d->off[K], nb, BT + (size_t)(K - J - 1) * be, nb, nb,
+                                1.0, 1.0)))
+          return rc;
+      }
+      if (G > 1) G3_NCCL(ctx, api, api->Reduce(Y, Y, (size_t)below * nb, ncclDouble, ncclSum, owner, d->comm, MS));
+    }
+    if (mine) {
+      const double* Dj = d->dinv + d->dinv_off[J];
+      transpose_kernel<<<dim3(nb / 32, nb / 32), 256, 0, MS>>>(piece, nb, LT, nb, nb, nb);          // L_JJ^T (stale upper tiles of
+      G3_LAUNCH_CHECK(ctx);                                                                          //  L_JJ land below: never read)
+      for (int t = 0; t < w; ++t) {
+        transpose_kernel<<<dim3(TS / 32, TS / 32), 256, 0, MS>>>(Dj + (size_t)t * TS * TS, TS, DT + (size_t)t * TS * TS, TS, TS, TS);
+        G3_LAUNCH_CHECK(ctx);
+      }
+      if (below > 0) {                                   // X[J+1:, J] = -Y L_JJ^-1
+        if ((rc = g3_panel_rsolve(ctx, Y, below, nb, LT, DT, 1.0, -1.0))) return rc;
+        G3_CUDA(ctx, cudaMemcpyAsync(piece + be, Y, sizeof(double) * (size_t)below * nb, cudaMemcpyDeviceToDevice, MS));
+      }
+      identity_kernel<<<(unsigned)((be + 255) / 256), 256, 0, MS>>>(EYE, nb);                       // X_JJ = L_JJ^-1 (exact zeros above)
+      G3_LAUNCH_CHECK(ctx);
+      if ((rc = g3_panel_rsolve(ctx, EYE, nb, nb, LT, DT, -1.0, 1.0))) return rc;
+      G3_CUDA(ctx, cudaMemcpyAsync(piece, EYE, sizeof(double) * be, cudaMemcpyDeviceToDevice, MS));
+    }
+  }
+  G3_CUDA(ctx, cudaEventRecord(d->ev_t[2], MS));
+  // ---- K^-1 blocks and their contraction with dK/dtheta
+  double* XT = (double*)g3_ws(ctx, "dg_xt", sizeof(double) * (size_t)std::max(nloc, 1) * nb * N);
+  double* XTb = (double*)g3_ws(ctx, "dg_xtb", sizeof(double) * (size_t)nb * N);
+  double* Kb = (double*)g3_ws(ctx, "dg_kblk", sizeof(double) * (size_t)nb * std::max(nloc, 1) * nb);
+  const size_t npairs_max = (size_t)nloc * nP;
+  double* outp = (double*)g3_ws(ctx, "dg_out", sizeof(double) * std::max<size_t>(npairs_max, 1) * std::max(P, 1));
+  if (!XT || !XTb || !Kb || !outp) return -2;
+  G3_CUDA(ctx, cudaMemsetAsync(XT, 0, sizeof(double) * (size_t)std::max(nloc, 1) * nb * N, MS));
+  for (int x = 0; x < nloc; ++x) {                       // XT[x][n][M] = X[M, J nb + n]
+    const int J = d->rank + x * G, rows = (nP - J) * nb;
+    transpose_kernel<<<dim3(nb / 32, rows / 32), 256, 0, MS>>>(d->store + d->off[J], nb, XT + (size_t)x * nb * N + (size_t)J * nb, N, rows, nb);
+    G3_LAUNCH_CHECK(ctx);
+  }
+  size_t npairs = 0;
+  const long long ldk = (long long)std::max(nloc, 1) * nb;
+  for (int I = 0; I < nP; ++I) {
+    const int owner = I % G, rows = (nP - I) * nb;
+    double* Xi = owner == d->rank ? d->store + d->off[I] : BT;                                     // panel I (rows x nb)
+    if (G > 1) G3_NCCL(ctx, api, api->Broadcast(Xi, Xi, (size_t)rows * nb, ncclDouble, owner, d->comm, MS));
+    int nuse = 0;
+    for (int J = d->rank; J <= I; J += G) ++nuse;        // my panels J <= I are my first `nuse` ones
+    if (nuse == 0) continue;
+    transpose_kernel<<<dim3(nb / 32, rows / 32), 256, 0, MS>>>(Xi, nb, XTb + (size_t)I * nb, N, rows, nb);
+    G3_LAUNCH_CHECK(ctx);
+    // Kb[m][x nb + n] = sum_{M >= I nb} XTb[m][M] XT[x][n][M]
+    {
+      CUtensorMap tmA, tmB;
+      if ((rc = g3_make_tmap(ctx, &tmA, XTb, (uint64_t)N, nb, 1, (uint64_t)N, (uint64_t)nb * N, G3_BM))) return rc;
+      if ((rc = g3_make_tmap(ctx, &tmB, XT, (uint64_t)N, (uint64_t)nuse * nb, 1, (uint64_t)N, (uint64_t)nuse * nb * N, G3_BN))) return rc;
+      GemmArgs g;
+      memset(&g, 0, sizeof g);
+      g.D = Kb; g.ldd = ldk; g.strideD = 0;
+      g.mode = 0; g.ntx = nb / TS; g.nty = nuse * (nb / TS);
+      g.a_r0 = 0; g.a_rx = TS; g.b_r0 = 0; g.b_ry = TS;
+      g.ka0 = I * nb; g.kb0 = I * nb; g.kl0 = rows;
+      g.alpha = 1.0; g.beta = 0.0;
+      if ((rc = g3_gemm_launch(ctx, tmA, tmB, g, 1))) return rc;
+    }
+    for (int x = 0; x < nuse; ++x) {
+      const int J = d->rank + x * G;
+      VjpArgs v;
+      memset(&v, 0, sizeof v);
+      v.X1 = ctx->dX + (size_t)I * nb * D; v.X2 = ctx->dX + (size_t)J * nb * D; v.n1 = nb; v.n2 = nb; v.D = D;
+      v.same = I == J; v.lower_only = I == J;
+      v.theta = d->dtheta; v.P = P;
+      v.W = Kb + (size_t)x * nb; v.ldw = ldk; v.strideW = 0;
+      v.alpha = alpha + (size_t)I * nb; v.alpha2 = alpha + (size_t)J * nb; v.strideAlpha = 0; v.cfac = cf_dev;
+      v.scale = I == J ? 0.5 : 1.0;                      // off-diagonal blocks stand for (I, J) and (J, I)
+      v.dtheta = outp + npairs * std::max(P, 1);
+      if ((rc = g3_gram_vjp_launch(ctx, d->desc, v, 1))) return rc;
+      ++npairs;
+    }
+  }
+  G3_CUDA(ctx, cudaEventRecord(d->ev_t[3], MS));
+  std::vector<double> ho(npairs * std::max(P, 1)), ha(N);
+  if (npairs) G3_CUDA(ctx, cudaMemcpyAsync(ho.data(), outp, sizeof(double) * ho.size(), cudaMemcpyDeviceToHost, MS));
+  G3_CUDA(ctx, cudaMemcpyAsync(ha.data(), alpha, sizeof(double) * N, cudaMemcpyDeviceToHost, MS));
+  G3_CUDA(ctx, cudaStreamSynchronize(MS));
+  std::vector<double> g(std::max(P, 1), 0.0);
+  for (size_t k = 0; k < npairs; ++k)
+    for (int p2 = 0; p2 < P; ++p2) g[p2] += ho[k * P + p2];
+  if (P > 0 && (rc = g3_comm_allreduce(ctx, g.data(), P, 0))) return rc;
+  for (int p2 = 0; p2 < P; ++p2) dtheta_out[p2] = g[p2];
+  if (ddelta_out_or_NULL)
+    for (int i = 0; i < N; ++i) ddelta_out_or_NULL[i] = -cfac * ha[i];
+  float t[3];
+  for (int k = 0; k < 3; ++k) G3_CUDA(ctx, cudaEventElapsedTime(&t[k], d->ev_t[k], d->ev_t[k + 1]));
+  double mx[3] = {t[0], t[1], t[2]};
+  if ((rc = g3_comm_allreduce(ctx, mx, 3, 1))) return rc;
+  if (ms3) { ms3[0] = (float)mx[0]; ms3[1] = (float)mx[1]; ms3[2] = (float)mx[2]; }
   return 0;
 }
 

@@ -138,6 +138,9 @@ int g3_syrk_panel(g3_ctx* ctx, const double* P, int rowsP, int nb, int row_off, 
 int g3_trsv_panel(g3_ctx* ctx, const double* P, int rows, int nb, const double* Dinv, double* r, double* u, double* beta);
 int g3_panel_solve(g3_ctx* ctx, double* P, int rows, int nb, const double* Ld, const double* Dinv);
 int g3_panel_update(g3_ctx* ctx, double* D, int rows, int nb, const double* A, const double* Bm, int has_diag);
+int g3_panel_gemm(g3_ctx* ctx, double* D, long long ldd, int rows, int ncols, const double* A, long long lda, const double* Bm,
+                  long long ldb, long long kdim, double alpha, double beta);
+int g3_panel_rsolve(g3_ctx* ctx, double* Y, int rows, int nb, const double* LT, const double* DinvT, double s_upd, double s_mul);
 int g3_trtri_batched(g3_ctx* ctx, const double* L, double* U, int Np, int B, const double* Dinv);
 int g3_lauum_batched(g3_ctx* ctx, const double* U, double* Kinv, int Np, int B);
 int g3_trsv_fwd(g3_ctx* ctx, const double* L, const double* Dinv, double* r, double* u, double* beta,
@@ -172,6 +175,7 @@ struct VjpArgs {
   const double* theta; int P;
   const double* W; long long ldw, strideW;   // weights; if alpha != null: W_ij = cfac*alpha_i*alpha_j - W_ij
   const double* alpha; long long strideAlpha; const double* cfac;
+  const double* alpha2;     // optional: the column factor of the outer product (off-diagonal blocks: W_ij = c a_i a2_j - W_ij); null = alpha
   double scale;             // result multiplied by scale (0.5 for the GP gradient)
   double* dtheta;           // B x P
   double* partials;         // optional caller-provided scratch: B x ntiles x P

@@ -385,7 +385,7 @@ gram_vjp_kernel(const __grid_constant__ g3_kernel_desc desc, const VjpArgs a, in
   for (int p = tid; p < a.P; p += blockDim.x) th[p] = a.theta[(long long)b * a.P + p];
   if (a.alpha && tid < TS) {
     al_r[tid] = (r0 + tid < a.n1) ? a.alpha[(long long)b * a.strideAlpha + r0 + tid] : 0.0;
-    al_c[tid] = (c0 + tid < a.n2) ? a.alpha[(long long)b * a.strideAlpha + c0 + tid] : 0.0;
+    al_c[tid] = (c0 + tid < a.n2) ? (a.alpha2 ? a.alpha2 : a.alpha)[(long long)b * a.strideAlpha + c0 + tid] : 0.0;
   }
   for (int p = 0; p < a.P; ++p) acc[p * 256 + tid] = 0.0;
   __syncthreads();

@@ -270,7 +270,7 @@ gram_vjp_add_kernel(const __grid_constant__ g3_kernel_desc desc, const VjpArgs a
   for (int p = tid; p < a.P; p += blockDim.x) th[p] = a.theta[(long long)b * a.P + p];
   if (a.alpha && tid < TS) {
     al_r[tid] = (r0 + tid < a.n1) ? a.alpha[(long long)b * a.strideAlpha + r0 + tid] : 0.0;
-    al_c[tid] = (c0 + tid < a.n2) ? a.alpha[(long long)b * a.strideAlpha + c0 + tid] : 0.0;
+    al_c[tid] = (c0 + tid < a.n2) ? (a.alpha2 ? a.alpha2 : a.alpha)[(long long)b * a.strideAlpha + c0 + tid] : 0.0;
   }
   for (int p = 0; p < a.P; ++p) acc[p * 256 + tid] = 0.0;
   __syncthreads();
@@ -501,7 +501,7 @@ __device__ __forceinline__ int build_leaf2(const g3_kernel_desc& desc, const dou
     const g3_knode& nd = desc.nodes[n];
     if (nd.op >= G3_K_SUM) continue;
     const double var = nd.var_idx >= 0 ? th[nd.var_idx] : nd.value;
-    if (nd.op == G3_K_NOISE) {                      // diagonal-only leaves are folded into one scalar (value); their
+    if (nd.op == G3_K_NOISE || nd.op == G3_K_WN) {  // diagonal-only leaves (WN: cov(x) form only, see g3_desc_is_fast2) are folded into one scalar; their
       if (!(skip_pn && (nd.flags & G3_KF_PROCESS_NOISE))) nv += var;    // var gradient is handled by the caller
       Leaf2& t = tab[nl++];
       t.op = nd.op; t.var_idx = nd.var_idx; t.var = var; t.dim0 = t.dim1 = 0; t.p0_idx = t.p1_idx = -1;
@@ -776,7 +776,7 @@ gram_vjp_fast2_kernel(const __grid_constant__ g3_kernel_desc desc, const VjpArgs
   for (int p = tid; p < a.P; p += blockDim.x) th[p] = a.theta[(long long)b * a.P + p];
   if (a.alpha && tid < TS) {
     al_r[tid] = (r0 + tid < a.n1) ? a.alpha[(long long)b * a.strideAlpha + r0 + tid] : 0.0;
-    al_c[tid] = (c0 + tid < a.n2) ? a.alpha[(long long)b * a.strideAlpha + c0 + tid] : 0.0;
+    al_c[tid] = (c0 + tid < a.n2) ? (a.alpha2 ? a.alpha2 : a.alpha)[(long long)b * a.strideAlpha + c0 + tid] : 0.0;
   }
   for (int p = 0; p < a.P; ++p) acc[p * 256 + tid] = 0.0;
   __syncthreads();

@@ -651,6 +651,62 @@ int g3_panel_update(g3_ctx* ctx, double* D, int rows, int nb, const double* A, c
   return g3_gemm_launch(ctx, tmA, tmB, g, 1);
 }
 
+// General panel GEMM: D[x][y] = beta D[x][y] + alpha sum_k A[x][k] Bm[y][k]   (D: rows x ncols with leading dimension ldd,
+// A: rows x kdim (lda), Bm: ncols x kdim (ldb)); everything a multiple of 128 (kdim of 16).
+int g3_panel_gemm(g3_ctx* ctx, double* D, long long ldd, int rows, int ncols, const double* A, long long lda, const double* Bm,
+                  long long ldb, long long kdim, double alpha, double beta) {
+  if (rows % TS || ncols % TS || kdim % G3_BK || rows <= 0 || ncols <= 0 || kdim <= 0) return g3_fail_msg(ctx, "panel_gemm: bad geometry");
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = g3_make_tmap(ctx, &tmA, A, (uint64_t)kdim, rows, 1, (uint64_t)lda, (uint64_t)rows * lda, G3_BM))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmB, Bm, (uint64_t)kdim, ncols, 1, (uint64_t)ldb, (uint64_t)ncols * ldb, G3_BN))) return rc;
+  GemmArgs g = gemm_zero();
+  g.D = D; g.ldd = ldd; g.strideD = 0;
+  g.mode = 0; g.ntx = rows / TS; g.nty = ncols / TS;
+  g.a_r0 = 0; g.a_rx = TS;
+  g.b_r0 = 0; g.b_ry = TS;
+  g.kl0 = (int)kdim;
+  g.alpha = alpha; g.beta = beta;
+  return g3_gemm_launch(ctx, tmA, tmB, g, 1);
+}
+
+// Right-hand triangular solve with a NON-transposed lower factor: Y <- s_mul * (Y' L^-1) computed tile column by tile column from
+// the last to the first,  T_j = Y[:, j] + s_upd * sum_{k > j} Z[:, k] L[k][j],  Z[:, j] = s_mul * T_j Linv_jj   (in place).
+// LT = L^T (nb x nb row-major), DinvT = the w transposed 128-block inverses stacked (w*128 x 128).  Used by the distributed
+// triangular inversion: (s_upd, s_mul) = (-1, +1) solves Z L = Y, (+1, -1) gives Z = -Y L^-1.
+int g3_panel_rsolve(g3_ctx* ctx, double* Y, int rows, int nb, const double* LT, const double* DinvT, double s_upd, double s_mul) {
+  if (rows % TS || nb % TS || rows <= 0) return g3_fail_msg(ctx, "panel_rsolve: bad geometry");
+  const int Tr = rows / TS, w = nb / TS;
+  CUtensorMap tmY, tmL, tmD;
+  int rc;
+  if ((rc = g3_make_tmap(ctx, &tmY, Y, nb, rows, 1, nb, (uint64_t)rows * nb, G3_BM))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmL, LT, nb, nb, 1, nb, (uint64_t)nb * nb, G3_BN))) return rc;
+  if ((rc = g3_make_tmap(ctx, &tmD, DinvT, TS, (uint64_t)w * TS, 1, TS, (uint64_t)w * TS * TS, G3_BN))) return rc;
+  for (int j = w - 1; j >= 0; --j) {
+    if (j < w - 1) {
+      GemmArgs g = gemm_zero();
+      g.D = Y; g.ldd = nb; g.strideD = 0;
+      g.mode = 0; g.ntx = Tr; g.nty = 1;
+      g.d_r0 = 0; g.d_c0 = j * TS;
+      g.a_r0 = 0; g.a_rx = TS; g.ka0 = (j + 1) * TS;
+      g.b_r0 = j * TS; g.kb0 = (j + 1) * TS;
+      g.kl0 = (w - 1 - j) * TS;
+      g.alpha = s_upd; g.beta = 1.0;
+      if ((rc = g3_gemm_launch(ctx, tmY, tmL, g, 1))) return rc;
+    }
+    GemmArgs g = gemm_zero();
+    g.D = Y; g.ldd = nb; g.strideD = 0;
+    g.mode = 0; g.ntx = Tr; g.nty = 1;
+    g.d_r0 = 0; g.d_c0 = j * TS;
+    g.a_r0 = 0; g.a_rx = TS; g.ka0 = j * TS;
+    g.b_r0 = j * TS; g.kb0 = 0;
+    g.kl0 = TS;
+    g.alpha = s_mul; g.beta = 0.0;
+    if ((rc = g3_gemm_launch(ctx, tmY, tmD, g, 1))) return rc;
+  }
+  return 0;
+}
+
 // U = L^-T (row-major upper).  Diagonal tiles of U are Linv_jj^T, rebuilt here from Dinv.
 namespace {
 __global__ void __launch_bounds__(256)

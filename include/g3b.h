@@ -262,6 +262,15 @@ int g3_dist_factor(g3_ctx* ctx, const g3_kernel_desc* desc, const double* theta,
 /* u = L^-1 delta (delta: N host doubles, read on rank 0), beta = u'u - the quadratic form of logp_cho
  * (g3py/processes/gaussian.py:212-215); u_out_or_NULL receives u (N) on every rank. */
 int g3_dist_solve(g3_ctx* ctx, const double* delta, double* beta, double* u_out_or_NULL, float* ms);
+/* Posterior moments at M test points (Xs: M x D host doubles; flags: G3_POST_NOISE) from the distributed factor:
+ * mean_out = K* K^-1 delta (caller adds m(X*)), var_out = max(diag(K** - K* K^-1 K*'), 0) - g3_gp_posterior's semantics
+ * (elliptical.py:78-107) without gathering L.  Needs g3_dist_factor + g3_dist_solve on a 1 x G grid; results on every rank. */
+int g3_dist_posterior(g3_ctx* ctx, const double* Xs, int M, int flags, double* mean_out, double* var_out);
+/* Gradient from the distributed factor (consumes it: L is overwritten by L^-1; 1 x G grid):
+ *   dtheta[p] = 1/2 sum_ij (cfac alpha_i alpha_j - K^-1_ij) dK_ij/dtheta_p (natural space), ddelta = -cfac alpha, alpha = K^-1 delta
+ * i.e. the dtheta / ddelta of g3_gp_logp_grad; cfac = 1 (gauss) or (nu + N) / (nu - 2 + beta) (student).  K^-1 is formed block
+ * pair by block pair and contracted at once, never stored.  ms3 = device times {alpha, inverse, contraction}, max over ranks. */
+int g3_dist_grad(g3_ctx* ctx, double cfac, double* dtheta, double* ddelta_or_NULL, float* ms3);
 /* Correctness probe on the hardware: nvec (<= 4) seeded +-1 vectors v, rel_err[k] = max|L (L^T v) - K v| / max|K v| with
  * K regenerated from X (never stored). */
 int g3_dist_residual(g3_ctx* ctx, int nvec, unsigned seed, double* rel_err);

@@ -419,6 +419,43 @@ def test_block_cyclic_cholesky_single_gpu(N, nb, lookahead):
         ctx.close()
 
 
+@pytest.mark.parametrize("N,nb", [(1536, 256), (2048, 512), (1024, 1024)])
+def test_block_cyclic_gradient_and_posterior_single_gpu(N, nb):
+    """g3_dist_grad / g3_dist_posterior on a 1 x 1 grid against the single-GPU fused path (g3_gp_logp_grad /
+    g3_gp_posterior) on the same kernel, data and hypers: dtheta, ddelta, posterior mean and variance."""
+    from g3py_b200.dist import se_noise_desc
+    from g3py_b200 import workloads
+    X, y = workloads.c5_inputs(N)
+    desc = se_noise_desc(X)
+    th = np.array([1.3, 0.9, 1.1, 0.8, 0.02])
+    ref = g3.Context(0)
+    ctx = g3.Context(0)
+    try:
+        ref.set_data(X)
+        want = ref.gp_logp_grad(desc, cabi.KIND_GAUSS, y, th[None], want_grad=True)
+        Xs = np.random.default_rng(3).uniform(0, N ** (1.0 / 3.0), size=(333, 3))
+        wp = ref.gp_posterior(desc, Xs, y, th, noise=False)
+        wpn = ref.gp_posterior(desc, Xs, y, th, noise=True)
+        ctx.set_data(X)
+        f = ctx.dist_factor(desc, th, nb, 1, 1)
+        s = ctx.dist_solve(y)
+        assert f["info"] == 0
+        assert abs(f["logdet"] - want["logdet"][0]) <= 1e-11 * abs(want["logdet"][0])
+        assert abs(s["beta"] - want["beta"][0]) <= 1e-11 * abs(want["beta"][0])
+        m, v = ctx.dist_posterior(Xs, noise=False)
+        assert scaled_err(m, wp["mean"]) < 1e-10 and scaled_err(v, wp["var"]) < 1e-10
+        m2, v2 = ctx.dist_posterior(Xs, noise=True)
+        assert scaled_err(m2, wpn["mean"]) < 1e-10 and scaled_err(v2, wpn["var"]) < 1e-10
+        g = ctx.dist_grad(desc.n_theta, cfac=1.0)
+        assert scaled_err(g["dtheta"], want["dtheta"][0]) < 1e-10
+        assert scaled_err(g["ddelta"], want["ddelta"][0]) < 1e-10
+        with pytest.raises(cabi.G3Error):
+            ctx.dist_grad(desc.n_theta)                          # the factor was consumed
+    finally:
+        ref.close()
+        ctx.close()
+
+
 def test_block_cyclic_cholesky_detects_indefinite_matrix():
     """*info = 1-based index of the first non-positive pivot (no ladder on the distributed path)."""
     from g3py_b200.dist import se_noise_desc

@@ -64,7 +64,33 @@ def main():
         assert abs(s["beta"] - uref @ uref) < 1e-10 * (uref @ uref) and abs(r["logdet"] - ld) < 1e-10 * abs(ld), (r, ld)
         r["max_abs_err_vs_numpy"] = float(ctx.comm_allreduce([err], "max")[0])
         r["max_abs_err_u"] = float(ctx.comm_allreduce([err_u], "max")[0])
+        if Pr == 1:                              # posterior and gradient from the distributed factor (1 x G grids)
+            K = np.exp(-d) + 0.01 * np.eye(N)
+            rng = np.random.default_rng(7)
+            Xs = rng.uniform(0, N ** (1.0 / 3.0), size=(300, 3))
+            ds = ((Xs[:, None, :] - X[None, :, :]) ** 2 * 0.5).sum(-1)
+            Ks = np.exp(-ds)
+            V = np.linalg.solve(L, Ks.T)
+            m, v = ctx.dist_posterior(Xs, noise=False)
+            e_m = float(np.abs(m - V.T @ uref).max() / np.abs(V.T @ uref).max())
+            e_v = float(np.abs(v - np.maximum(1.0 - (V * V).sum(0), 0.0)).max())
+            g = ctx.dist_grad(5, cfac=1.0)
+            Kinv = np.linalg.inv(K)
+            al = Kinv @ y
+            W = 0.5 * (np.outer(al, al) - Kinv)
+            E = np.exp(-d)
+            want = [np.sum(W * E)] + [np.sum(W * E * (-(X[:, None, k] - X[None, :, k]) ** 2)) for k in range(3)] + [np.trace(W)]
+            e_g = float(np.abs(g["dtheta"] - want).max() / np.abs(want).max())
+            e_a = float(np.abs(g["ddelta"] + al).max() / np.abs(al).max())
+            assert e_m < 1e-9 and e_v < 1e-9 and e_g < 1e-9 and e_a < 1e-9, (rank, e_m, e_v, e_g, e_a)
+            r.update(post_mean_err=e_m, post_var_err=e_v, grad_err=e_g, alpha_err=e_a, ms_alpha=g["ms_alpha"],
+                     ms_inverse=g["ms_inverse"], ms_contract=g["ms_contract"])
         print("rank", rank, "check ok", err, err_u, flush=True)
+    if "--grad" in sys.argv:                     # timing of the distributed gradient at full size (1 x G grid)
+        g = ctx.dist_grad(5, cfac=1.0, want_ddelta=False)
+        n = float(N)
+        r.update(ms_alpha=g["ms_alpha"], ms_inverse=g["ms_inverse"], ms_contract=g["ms_contract"], dtheta=[float(v) for v in g["dtheta"]],
+                 grad_tflops=2.0 * n ** 3 / 3.0 / ((g["ms_inverse"] + g["ms_contract"]) * 1e-3) / 1e12)
     if rank == 0:
         print(json.dumps(r), flush=True)
     ctx.dist_free()
