@@ -442,7 +442,7 @@ int dist_factor(g3_ctx* ctx, g3_dist* d) {
     const bool diag_owner = in_col && p == pd;
     cudaStream_t S = look ? PS : MS;
     ctx->stream = S;
-    if (in_col && cnt > 0 && J >= 1) {
+    if (look && in_col && cnt > 0 && J >= 1) {          // without look-ahead trailing(J-1) already applied panel J-1 to this piece
       if (J >= 2) cudaStreamWaitEvent(S, d->ev_upd[J % 4], 0);       // main-stream updates of this piece by panels < J-1
       cudaStreamWaitEvent(S, d->ev_ready[(J - 1) % nslot], 0);       // panel J-1 is here
       if ((rc = update(J, J - 1))) return rc;

@@ -586,7 +586,7 @@ __device__ __forceinline__ void leaf_fwd(const Leaf2& t, const double* __restric
     sc[k] = t.s[k];
     rr[k] = t.r[k];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) xs[k][e] = xc[k][e] * sc[k];
+    for (int e = 0; e < 4; ++e) xs[k][e] = __dmul_rn(xc[k][e], sc[k]);   // no FMA contraction with the subtraction below:
   }
   const double var = t.var, alpha = t.alpha;
 #pragma unroll
@@ -594,7 +594,7 @@ __device__ __forceinline__ void leaf_fwd(const Leaf2& t, const double* __restric
     const int rl = row0 + 8 * q;
     double xi[DT], d[4], dummy[DT][4];
 #pragma unroll
-    for (int k = 0; k < DT; ++k) xi[k] = x1s[rl * DT + k] * sc[k];
+    for (int k = 0; k < DT; ++k) xi[k] = __dmul_rn(x1s[rl * DT + k], sc[k]);   // df_ij must equal -df_ji to the bit (K symmetric)
     metric4<OP, DT, false>(xi, xs, rr, d, dummy);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -696,7 +696,7 @@ __device__ __forceinline__ void leaf_vjp(const Leaf2& t, const double* __restric
     sc[k] = t.s[k];
     rr[k] = t.r[k];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) xs[k][e] = xc[k][e] * sc[k];
+    for (int e = 0; e < 4; ++e) xs[k][e] = __dmul_rn(xc[k][e], sc[k]);   // no FMA contraction with the subtraction below:
   }
   const double alpha = t.alpha;
   double g_var = 0.0, g_alpha = 0.0, g_r[DT], g_f[DT];
@@ -707,7 +707,7 @@ __device__ __forceinline__ void leaf_vjp(const Leaf2& t, const double* __restric
     const int rl = row0 + 8 * q;
     double xi[DT], d[4], pc[DT][4];
 #pragma unroll
-    for (int k = 0; k < DT; ++k) xi[k] = x1s[rl * DT + k] * sc[k];
+    for (int k = 0; k < DT; ++k) xi[k] = __dmul_rn(x1s[rl * DT + k], sc[k]);   // df_ij must equal -df_ji to the bit (K symmetric)
     metric4<OP, DT, true>(xi, xs, rr, d, pc);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {

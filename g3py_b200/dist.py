@@ -18,7 +18,7 @@ def se_noise_desc(X):
     k.check_dims(X)
     k.check_hypers("", reg)
     b = g3.DescBuilder(X.shape[1])
-    k.compile(b)
+    k.compile(b, process_noise=True)         # the Noise leaf is the process noise: noise=False selectors drop it (elliptical.py:73-74)
     return b.finish()
 
 

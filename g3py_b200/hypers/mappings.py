@@ -9,7 +9,7 @@ import numpy as np
 from . import Hypers, HyperVar
 
 __all__ = ["Mapping", "Identity", "LinearMapping", "LogShifted", "BoxCoxShifted", "BoxCoxLinear", "ArcsinhLinear",
-           "SinhArcsinh", "MappingComposed", "Logistic", "WarpingTanh", "WarpingBoxCox"]
+           "SinhArcsinh", "MappingComposed", "MappingInvSum", "BoxCoxLinear2", "Logistic", "WarpingTanh", "WarpingBoxCox"]
 
 _F32_1EM32 = float(np.float32(1e-32))
 _F32_1EM5 = float(np.float32(1e-5))
@@ -120,6 +120,73 @@ class MappingComposed(Mapping):      # mappings.py:56-71
         for k, v in dl2.items():
             dld[k] = v
         return dinv, dld
+
+
+class MappingInvSum(MappingComposed):   # mappings.py:73-85: inv(y) = m1.inv(y) + m2.inv(y)
+    """The reference leaves `__call__` empty (`pass`) and `logdet_dinv` commented out, so the density uses the base-class
+    numeric log-Jacobian sum(log(diag(jacobian(inv)))) (`mappings.py:17-22`): for element-wise maps that is
+    sum(log(m1.inv'(y) + m2.inv'(y))).  The forward map has no closed form; it is obtained like the Newton warpings
+    (`inverse_function`, libs/tensors.py:134-171: damped Newton, step 0.1, tolerance 1e-3 on the whole vector)."""
+
+    def __init__(self, m1, m2):
+        super().__init__(m1, m2)
+        self.name = m1.name + " +^ " + m2.name
+
+    def inv(self, y, p):
+        return self.m1.inv(y, p) + self.m2.inv(y, p)
+
+    def dinv_dy(self, y, p):
+        return self.m1.dinv_dy(y, p) + self.m2.dinv_dy(y, p)
+
+    def logdet_dinv(self, y, p):
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return float(np.sum(np.log(self.dinv_dy(y, p))))
+
+    def dlog_dinv_dy(self, y, p):
+        d1, d2 = self.m1.dinv_dy(y, p), self.m2.dinv_dy(y, p)
+        return (d1 * self.m1.dlog_dinv_dy(y, p) + d2 * self.m2.dlog_dinv_dy(y, p)) / (d1 + d2)
+
+    def __call__(self, z, p, tol=1e-3, n_steps=1024, alpha=0.1):
+        z = np.asarray(z, dtype=np.float64)
+        y = z.copy()
+        for _ in range(n_steps):                                           # libs/tensors.py:134-171
+            r = self.inv(y, p) - z
+            if np.sqrt(np.sum(r * r)) < tol:
+                break
+            y = y - alpha * r / self.dinv_dy(y, p)
+        return y
+
+    def grads(self, y, p):
+        """d inv / d h is the owning map's; d logdet / d h = sum_i (d (m.inv')(y_i) / d h) / (m1.inv' + m2.inv'), with
+        d m.inv' / d h = m.inv' * d log(m.inv') / d h taken from the owning map's own log-Jacobian gradient by a
+        4th-order central difference in h (exact maps, scalar hypers: a handful of O(N) evaluations)."""
+        di1, _ = self.m1.grads(y, p)
+        di2, _ = self.m2.grads(y, p)
+        dinv = dict(di1)
+        dinv.update(di2)
+        tot = self.dinv_dy(y, p)
+        dld = {}
+        for m, di in ((self.m1, di1), (self.m2, di2)):
+            for h in di:
+                dld[h] = _fd_hyper(lambda pp: m.dinv_dy(y, pp), p, h, weight=1.0 / tot)
+        return dinv, dld
+
+
+def _fd_hyper(fun, p, h, weight):
+    """sum(weight * d fun / d h) by 4th-order central differences on the natural-space value of hyper h (per component)."""
+    base = np.atleast_1d(np.asarray(p(h), dtype=np.float64)).copy()
+    out = np.zeros(base.size)
+    for c in range(base.size):
+        step = 1e-4 * max(1.0, abs(base[c]))
+
+        def at(s):
+            v = base.copy()
+            v[c] += s * step
+            val = v if not getattr(h, "scalar", base.size == 1) else float(v[0])
+            return fun(lambda q: val if q is h else p(q))
+        d = (-at(2.0) + 8.0 * at(1.0) - 8.0 * at(-1.0) + at(-2.0)) / (12.0 * step)
+        out[c] = float(np.sum(weight * d))
+    return out if out.size > 1 else float(out[0])
 
 
 class Identity(Mapping):             # mappings.py:88-99
@@ -303,6 +370,66 @@ class BoxCoxLinear(_BoxCox):         # mappings.py:182-215
 
     def grads(self, y, p):
         d_shift, d_scale, d_power, ld_shift, ld_scale, ld_power = self._grads(y, p)
+        return ({self.shift: d_shift, self.scale: d_scale, self.power: d_power},
+                {self.shift: ld_shift, self.scale: ld_scale, self.power: ld_power})
+
+
+class BoxCoxLinear2(Mapping):        # mappings.py:218-251: shifted = scale * y + shift (BoxCoxLinear: scale * (y + shift))
+    def __init__(self, y=None, name=None, shift=None, scale=None, power=None):
+        super().__init__(y, name)
+        self.shift, self.scale, self.power = shift, scale, power
+
+    def check_hypers(self, parent="", reg=None):
+        self._reg(parent, reg, "shift", False)
+        self._reg(parent, reg, "scale", True)
+        self._reg(parent, reg, "power", True)
+
+    def default_hypers(self, x=None, y=None):
+        return {h: 1.0 for h in (self.shift, self.scale, self.power) if isinstance(h, HyperVar)}
+
+    def _params(self, p):
+        return _v(p, self.shift), _v(p, self.scale), _v(p, self.power)
+
+    def __call__(self, z, p):
+        shift, scale, power = self._params(p)
+        sc = power * z + 1.0
+        return (np.sign(sc) * np.abs(sc) ** (1.0 / power) - shift) / scale
+
+    def inv(self, y, p):
+        shift, scale, power = self._params(p)
+        sh = scale * y + shift
+        with np.errstate(invalid="ignore", divide="ignore"):
+            if power < _F32_1EM5:
+                return np.log(sh)
+            return (np.sign(sh) * np.abs(sh) ** power - 1.0) / power
+
+    def logdet_dinv(self, y, p):
+        shift, scale, power = self._params(p)
+        e = -1.0 if power < _F32_1EM5 else power - 1.0
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return e * np.sum(np.log(np.abs(scale * y + shift))) + float(y.shape[0]) * np.log(scale)
+
+    def dinv_dy(self, y, p):
+        shift, scale, power = self._params(p)
+        return np.abs(scale * y + shift) ** (power - 1.0) * scale
+
+    def dlog_dinv_dy(self, y, p):
+        shift, scale, power = self._params(p)
+        return (power - 1.0) * scale / (scale * y + shift)
+
+    def grads(self, y, p):
+        shift, scale, power = self._params(p)
+        n = float(y.shape[0])
+        sh = scale * y + shift
+        a = np.abs(sh)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            sp = np.sign(sh) * a ** power
+            d_shift = a ** (power - 1.0)
+            d_scale = a ** (power - 1.0) * y
+            d_power = (sp * np.log(a) * power - (sp - 1.0)) / power ** 2
+            ld_shift = (power - 1.0) * float(np.sum(1.0 / sh))
+            ld_scale = (power - 1.0) * float(np.sum(y / sh)) + n / scale
+            ld_power = float(np.sum(np.log(a)))
         return ({self.shift: d_shift, self.scale: d_scale, self.power: d_power},
                 {self.shift: ld_shift, self.scale: ld_scale, self.power: ld_power})
 

@@ -7,7 +7,7 @@ import numpy as np
 
 from . import Hypers, HyperVar
 
-__all__ = ["Mean", "Location", "Zero", "Bias", "Linear", "MeanSum", "MeanProd", "MeanScale", "MeanShift"]
+__all__ = ["Mean", "Location", "Zero", "Bias", "Linear", "Power", "BlackBox", "MeanSum", "MeanProd", "MeanScale", "MeanShift"]
 
 
 def _val(p, h):
@@ -182,3 +182,54 @@ class Linear(Mean):                  # means.py:140-159
         if isinstance(self.coeff, HyperVar):
             out[self.coeff] = x.T.copy()
         return out
+
+
+class Power(Mean):                   # means.py:162-182: constant + dot(x**n, coeff)
+    def __init__(self, x=None, name=None, constant=None, coeff=None, n=2):
+        super().__init__(x, name)
+        self.constant = constant
+        self.coeff = coeff
+        self.n = n
+
+    def check_hypers(self, parent="", reg=None):
+        if self.constant is None:
+            self.constant = reg.Flat(parent + self.name + "_Constant")
+        if self.coeff is None:
+            self.coeff = reg.Flat(parent + self.name + "_Coeff", shape=self.shape)
+        for h in (self.constant, self.coeff):
+            if isinstance(h, HyperVar) and h not in self.hypers:
+                self.hypers += [h]
+
+    def default_hypers(self, x=None, y=None):
+        d = {}
+        if isinstance(self.constant, HyperVar):
+            d[self.constant] = float(np.mean(y))
+        if isinstance(self.coeff, HyperVar):
+            d[self.coeff] = np.mean(y) / (x ** self.n).mean(axis=0)
+        return d
+
+    def eval(self, x, p):
+        return float(_val(p, self.constant)) + (x ** self.n).dot(np.atleast_1d(_val(p, self.coeff)))
+
+    def jac(self, x, p):
+        out = {}
+        if isinstance(self.constant, HyperVar):
+            out[self.constant] = np.ones((1, x.shape[0]))
+        if isinstance(self.coeff, HyperVar):
+            out[self.coeff] = (x ** self.n).T.copy()
+        return out
+
+
+class BlackBox(Mean):                # means.py:32-41: a fixed vector, element[:len(x)]; no hypers
+    def __init__(self, element, x=None, name=None):
+        super().__init__(x, name)
+        self.element = np.asarray(element, dtype=np.float64).reshape(-1)
+
+    def eval(self, x, p):
+        return self.element[:x.shape[0]].copy()
+
+    def __call__(self, x, p):
+        return self.element[:np.asarray(x).shape[0]].copy()
+
+    def jacobian(self, x, p):
+        return {}

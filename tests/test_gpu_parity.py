@@ -457,15 +457,20 @@ def test_block_cyclic_gradient_and_posterior_single_gpu(N, nb):
 
 
 def test_block_cyclic_cholesky_detects_indefinite_matrix():
-    """*info = 1-based index of the first non-positive pivot (no ladder on the distributed path)."""
+    """*info = 1-based index of the first non-positive pivot (no ladder on the distributed path): K = -exp(-d) shifted by
+    tt_to_cov to a 1e-6 diagonal is indefinite at its second pivot; a pivot failure deep inside (block 3 of 4) is located too."""
     from g3py_b200.dist import se_noise_desc
     X = np.random.default_rng(0).uniform(0, 3, size=(1024, 2))
-    X[700] = X[10]                                           # duplicated input, no noise: singular at pivot 701
     ctx = g3.Context(0)
     try:
         ctx.set_data(X)
-        f = ctx.dist_factor(se_noise_desc(X), np.array([1.0, 1.0, 1.0, 0.0]), 256, 1, 1)
-        assert 600 < f["info"] <= 701
+        f = ctx.dist_factor(se_noise_desc(X), np.array([-1.0, 1.0, 1.0, 0.0]), 256, 1, 1)
+        assert f["info"] == 2
+        Xw = np.random.default_rng(1).uniform(0, 300, size=(1024, 2))     # nearly diagonal K: well conditioned ...
+        Xw[700:] = Xw[:324]                                                # ... but rows 700.. repeat rows 0..: singular from 701 on
+        ctx.set_data(Xw)
+        f = ctx.dist_factor(se_noise_desc(Xw), np.array([1.0, 1.0, 1.0, -1e-9]), 256, 1, 1)
+        assert 701 <= f["info"] <= 704
     finally:
         ctx.close()
 

@@ -170,3 +170,64 @@ def test_composed_mapping_gradients_are_the_analytic_chain(pair):
     # and the slope itself
     fd = g3.hypers.mappings.Mapping.dlog_dinv_dy(comp, y, lookup(theta))
     assert scaled_err(comp.dlog_dinv_dy(y, lookup(theta)), fd) < 1e-8
+
+
+def test_power_blackbox_means_and_new_mappings_on_fake(monkeypatch):
+    """Power / BlackBox means (means.py:32-41,162-182), BoxCoxLinear2 and MappingInvSum (mappings.py:73-85,218-251) through
+    the public API on the NumPy device double: Power(n) equals Linear on x**n, BlackBox(m) equals a GP on y - m, and the
+    gradients of the new warpings agree with central differences of logp."""
+    import g3py_b200 as g3
+    from fake_ctx import FakeContext
+    ctx = FakeContext()
+    monkeypatch.setattr(g3.processes, "get_context", lambda device=0: ctx)
+    rng = np.random.default_rng(5)
+    X = rng.uniform(0.5, 3.0, size=(40, 2))
+    y = np.sin(X[:, 0]) + 0.3 * X[:, 1] ** 2 + 0.05 * rng.standard_normal(40)
+    a = g3.GP(X, g3.Power(X, n=2), g3.SE(X))
+    b = g3.GP(X ** 2, g3.Linear(X ** 2), g3.SE(X ** 2))
+    a.observed(X, y)
+    b.observed(X ** 2, y)
+    assert [n.split("_", 2)[2] for n, _, _ in a.layout][:2] == ["Constant", "Coeff"]
+    pa, pb = a.dict_to_array(a.params_default), b.dict_to_array(b.params_default)
+    assert np.allclose(pa[:3], pb[:3])                       # same defaults for constant / coeff (means.py:178-180)
+    th = pa.copy()
+    th[3:] = [0.1, -0.2, 0.3, np.log(0.05)]
+    tb = th.copy()
+    tb[4:6] = th[4:6] - np.log(2.0) - np.log(np.mean(X, axis=0)) * 0       # different metric: compare means only
+    m = rng.standard_normal(40)
+    c = g3.GP(X, g3.BlackBox(m), g3.SE(X))
+    d = g3.GP(X, g3.Zero(), g3.SE(X))
+    c.observed(X, y)
+    d.observed(X, y - m)
+    t0 = np.array([0.1, -0.2, 0.3, np.log(0.05)])
+    assert c.logp(t0, array=True) == pytest.approx(d.logp(t0, array=True), rel=1e-12)
+    assert np.allclose(c.dlogp(t0, array=True), d.dlogp(t0, array=True), rtol=1e-10)
+    # Power mean value / jacobian
+    nat = a.natural(th)
+    p = a._accessor(nat)
+    assert np.allclose(a.f_location(X, p), nat[0] + (X ** 2) @ nat[1:3])
+    g = a.dlogp(th, array=True)
+    for i in range(3):
+        e = np.zeros_like(th)
+        e[i] = 1e-5
+        fd = (a.logp(th + e, array=True) - a.logp(th - e, array=True)) / 2e-5
+        assert g[i] == pytest.approx(fd, rel=1e-5, abs=1e-6)
+    # new warpings: gradient of logp wrt every hyper against central differences
+    yp = np.exp(0.4 * y) + 0.3
+    for mp in (g3.BoxCoxLinear2(), g3.MappingInvSum(g3.BoxCoxLinear2(name="A"), g3.LogShifted(name="B"))):
+        w = g3.WGP(X, g3.Bias(), g3.SE(X), mp)
+        w.observed(X, yp)
+        tw = w.dict_to_array(w.params_default)
+        lay = [n for n, s, _ in w.layout for _ in range(s)]
+        tw[lay.index("WGP_Noise_var")] = np.log(0.05)
+        for k, nm in enumerate(lay):
+            if nm.endswith("_shift"):
+                tw[k] = 0.4
+        gw = w.dlogp(tw, array=True)
+        for i in range(len(tw)):
+            e = np.zeros_like(tw)
+            e[i] = 1e-5
+            fd = (w.logp(tw + e, array=True) - w.logp(tw - e, array=True)) / 2e-5
+            assert gw[i] == pytest.approx(fd, rel=2e-5, abs=1e-5), (type(mp).__name__, lay[i])
+        pr = w.predict(tw, space=X[:5], array=True, var=True, median=True)
+        assert np.all(np.isfinite(pr["mean"])) and np.all(pr["variance"] >= 0)
