@@ -445,6 +445,12 @@ class _Mean:
             self.hypers = (_Hyper(self.name + "_Bias", 1, False),)
         elif self.kind == "Linear":                            # means.py:147-152
             self.hypers = (_Hyper(self.name + "_Constant", 1, False), _Hyper(self.name + "_Coeff", nd, False))
+        elif self.kind == "Power":                             # means.py:162-182: constant + dot(x**n, coeff)
+            self.hypers = (_Hyper(self.name + "_Constant", 1, False), _Hyper(self.name + "_Coeff", nd, False))
+            self.power = spec.get("n", 2)
+        elif self.kind == "BlackBox":                          # means.py:32-41: element[:len(x)], no hypers
+            self.hypers = ()
+            self.element = np.asarray(spec["element"], dtype=np.float64)
         else:
             raise ValueError(self.kind)
 
@@ -460,7 +466,11 @@ class _Mean:
             return np.zeros(n)
         if self.kind == "Bias":                                # means.py:136-137
             return th[0] * np.ones(n)
+        if self.kind == "BlackBox":                            # means.py:37-41
+            return self.element[:n].copy()
         xs = x[:, self.dims[0]:self.dims[1]]
+        if self.kind == "Power":                               # means.py:181-182
+            return th[0] + (xs ** self.power).dot(th[1:])
         return th[0] + xs.dot(th[1:])                          # means.py:158-159
 
     def jac(self, th, x):
@@ -470,7 +480,11 @@ class _Mean:
             return np.zeros((0, n))
         if self.kind == "Bias":
             return np.ones((1, n))
+        if self.kind == "BlackBox":
+            return np.zeros((0, n))
         xs = x[:, self.dims[0]:self.dims[1]]
+        if self.kind == "Power":
+            return np.vstack([np.ones((1, n)), (xs ** self.power).T])
         return np.vstack([np.ones((1, n)), xs.T])
 
 
@@ -803,8 +817,123 @@ class _MappingComposed:
     grads_fd = None                                            # bound below (same finite differences as _Mapping)
 
 
+class _MappingBoxCoxLinear2:
+    """BoxCoxLinear2 (processes/hypers/mappings.py:218-251): shifted = scale * y + shift;
+    inv = log(shifted) if power < float32(1e-5) else (sgn |shifted|^power - 1) / power;
+    logdet_dinv = (power - 1 | -1) * sum(log|shifted|) + N log(scale); forward T(z) = (sgn|power z + 1|^(1/power) - shift) / scale."""
+
+    def __init__(self, spec):
+        self.kind = "BoxCoxLinear2"
+        self.name = spec.get("name", "BoxCoxLinear2")
+        self.hypers = (_Hyper(self.name + "_shift", 1, False), _Hyper(self.name + "_scale", 1, True),
+                       _Hyper(self.name + "_power", 1, True))
+        self.n = 1
+        self.thr = float(np.float32(1e-5))
+
+    def layout(self):
+        return list(self.hypers)
+
+    def n_theta(self):
+        return 3
+
+    def inv(self, th, y):
+        shift, scale, power = th
+        sh = scale * y + shift
+        with np.errstate(all="ignore"):
+            return np.log(sh) if power < self.thr else (np.sign(sh) * np.abs(sh) ** power - 1.0) / power
+
+    def logdet_dinv(self, th, y):
+        shift, scale, power = th
+        with np.errstate(all="ignore"):
+            return (-1.0 if power < self.thr else power - 1.0) * np.sum(np.log(np.abs(scale * y + shift))) + len(y) * np.log(scale)
+
+    def forward(self, th, z):
+        shift, scale, power = th
+        sc = power * z + 1.0
+        return (np.sign(sc) * np.abs(sc) ** (1.0 / power) - shift) / scale
+
+    def dinv_dy(self, th, y):
+        shift, scale, power = th
+        return np.abs(scale * y + shift) ** (power - 1.0) * scale
+
+    def dlog_dinv_dy(self, th, y):
+        shift, scale, power = th
+        return (power - 1.0) * scale / (scale * y + shift)
+
+    def grads(self, th, y):
+        shift, scale, power = th
+        sh = scale * y + shift
+        a = np.abs(sh)
+        with np.errstate(all="ignore"):
+            sp = np.sign(sh) * a ** power
+            dinv = np.vstack([a ** (power - 1.0), a ** (power - 1.0) * y, (sp * np.log(a) * power - (sp - 1.0)) / power ** 2])
+            dld = np.array([(power - 1.0) * np.sum(1.0 / sh), (power - 1.0) * np.sum(y / sh) + len(y) / scale, np.sum(np.log(a))])
+        return dinv, dld
+
+
+class _MappingInvSum:
+    """MappingInvSum (processes/hypers/mappings.py:73-85): inv(y) = m1.inv(y) + m2.inv(y).  Its logdet_dinv is commented
+    out in the reference, so the base class' numeric form applies (mappings.py:17-22): sum(log(diag(jacobian(inv)))) =
+    sum(log(m1.inv'(y) + m2.inv'(y))); `__call__` is `pass` (the forward map does not exist in the reference: no predict)."""
+
+    def __init__(self, spec):
+        self.kind = "invsum"
+        self.m1, self.m2 = make_mapping(spec["m1"]), make_mapping(spec["m2"])
+        self.name = self.m1.name + " +^ " + self.m2.name
+        self.hypers = tuple(self.m1.layout()) + tuple(self.m2.layout())
+        self.n = 1
+
+    def layout(self):
+        return list(self.hypers)
+
+    def n_theta(self):
+        return self.m1.n_theta() + self.m2.n_theta()
+
+    def _split(self, th):
+        return th[:self.m1.n_theta()], th[self.m1.n_theta():]
+
+    def inv(self, th, y):
+        t1, t2 = self._split(th)
+        return self.m1.inv(t1, y) + self.m2.inv(t2, y)
+
+    def dinv_dy(self, th, y):
+        t1, t2 = self._split(th)
+        return self.m1.dinv_dy(t1, y) + self.m2.dinv_dy(t2, y)
+
+    def logdet_dinv(self, th, y):
+        with np.errstate(all="ignore"):
+            return float(np.sum(np.log(self.dinv_dy(th, y))))
+
+    def forward(self, th, z):
+        raise NotImplementedError("MappingInvSum.__call__ is `pass` in the reference")
+
+    def grads(self, th, y):
+        """d inv / d h from the owning map; d logdet / d h = sum(d m.inv'(y) / d h / (m1.inv' + m2.inv')) with the
+        hyper-derivative of inv' by 4th-order central differences (closed-form inv')."""
+        t1, t2 = self._split(th)
+        di1, _ = self.m1.grads(t1, y)
+        di2, _ = self.m2.grads(t2, y)
+        tot = self.dinv_dy(th, y)
+        dld = np.zeros(len(th))
+        for k in range(len(th)):
+            h = 1e-4 * max(1.0, abs(th[k]))
+
+            def at(s):
+                t = np.array(th, dtype=np.float64)
+                t[k] += s * h
+                return self.dinv_dy(t, y)
+            dld[k] = np.sum((-at(2) + 8 * at(1) - 8 * at(-1) + at(-2)) / (12 * h) / tot)
+        return np.vstack([di1, di2]), dld
+
+
 def make_mapping(spec):
-    return _MappingComposed(spec) if spec["type"] == "composed" else _Mapping(spec)
+    if spec["type"] == "composed":
+        return _MappingComposed(spec)
+    if spec["type"] == "invsum":
+        return _MappingInvSum(spec)
+    if spec["type"] == "BoxCoxLinear2":
+        return _MappingBoxCoxLinear2(spec)
+    return _Mapping(spec)
 _MappingComposed.grads_fd = _Mapping.grads_fd
 
 

@@ -104,6 +104,12 @@ def ref_transport(g3, spec, X):
 def ref_mapping(g3, mp):
     if mp['type'] == 'composed':
         return ref_mapping(g3, mp['m1']) @ ref_mapping(g3, mp['m2'])
+    if mp['type'] == 'invsum':
+        from g3py.processes.hypers.mappings import MappingInvSum
+        return MappingInvSum(ref_mapping(g3, mp['m1']), ref_mapping(g3, mp['m2']))
+    if mp['type'] == 'BoxCoxLinear2':
+        from g3py.processes.hypers.mappings import BoxCoxLinear2
+        return _pot(BoxCoxLinear2(**({'name': mp['name']} if 'name' in mp else {})), mp)
     mkw = {'name': mp['name']} if 'name' in mp else {}
     if 'n' in mp:
         mkw['n'] = mp['n']
@@ -120,7 +126,15 @@ def ref_process(g3, spec, X):
            ('student', True): g3.WTP}[(kind, warped)]
     loc = spec.get('location', {'type': 'Zero'})
     lkw = {'name': loc['name']} if 'name' in loc else {}
-    location = _pot(getattr(g3, loc['type'])(_x_arg(X, loc.get('dims')), **lkw), loc)
+    if loc['type'] == 'Power':
+        from g3py.processes.hypers.means import Power
+        location = _pot(Power(_x_arg(X, loc.get('dims')), n=loc.get('n', 2), **lkw), loc)
+    elif loc['type'] == 'BlackBox':
+        from g3py.processes.hypers.means import BlackBox
+        import theano.tensor as tt                      # the element is sliced with a symbolic length: it must be a tensor
+        location = BlackBox(tt.as_tensor_variable(np.asarray(loc['element'], dtype=np.float64)), _x_arg(X, loc.get('dims')), **lkw)
+    else:
+        location = _pot(getattr(g3, loc['type'])(_x_arg(X, loc.get('dims')), **lkw), loc)
     mapping = ref_mapping(g3, mp)
     kw = {'name': spec['name']} if 'name' in spec else {}
     return cls(X, location, ref_kernel(g3, spec['kernel'], X), mapping, noisy=spec.get('noisy', True), **kw)
@@ -221,6 +235,14 @@ CASES = {
     'map_comp_lin_warptanh': dict(spec=dict(kind='gauss', warped=True, location=K('Bias'), kernel=K('SE'),
                                             mapping=K('composed', m1=K('LinearMapping'), m2=K('WarpingTanh', n=2))),
                                   N=24, D=1, M=7, seed=54),
+    # operator-surface leftovers: Power / BlackBox means, BoxCoxLinear2, MappingInvSum
+    'mean_power':      dict(spec=dict(kind='gauss', location=K('Power', n=2), kernel=K('SE')), N=24, D=2, M=7, seed=90),
+    'mean_blackbox':   dict(spec=dict(kind='gauss', location=K('BlackBox', element=[round(0.3 * np.sin(0.7 * i), 6) for i in range(32)]),
+                                      kernel=K('MAT32')), N=24, D=2, M=7, seed=91),
+    'map_boxcoxlin2':  dict(spec=dict(kind='gauss', warped=True, location=K('Bias'), kernel=K('SE'), mapping=K('BoxCoxLinear2')),
+                            N=24, D=1, M=7, seed=92, positive=True),
+    # MappingInvSum cannot be pinned: its `__call__` is `pass`, so EllipticalProcess.th_define_process (elliptical.py:64:
+    # tt_to_num(self.f_mapping(self.th_outputs))) raises before any method exists - dead code in the reference.
     'wtp_boxcox':      dict(spec=dict(kind='student', warped=True, location=K('Bias'), kernel=K('MAT52'),
                                       mapping=K('BoxCoxShifted')), N=32, D=2, M=9, seed=45, positive=True),
     # TransportGaussianProcess (SURVEY f-3): chains [ID | TMapping | TLocation]* @ TKernel

@@ -9,7 +9,7 @@ LEAVES = {"SE": g3.SE, "OU": g3.OU, "MAT32": g3.MAT32, "MAT52": g3.MAT52, "RQ": 
 MAPS = {"Identity": g3.Identity, "LinearMapping": g3.LinearMapping, "LogShifted": g3.LogShifted,
         "BoxCoxShifted": g3.BoxCoxShifted, "BoxCoxLinear": g3.BoxCoxLinear, "ArcsinhLinear": g3.ArcsinhLinear,
         "SinhArcsinh": g3.SinhArcsinh, "Logistic": g3.Logistic, "WarpingTanh": g3.WarpingTanh,
-        "WarpingBoxCox": g3.WarpingBoxCox}
+        "WarpingBoxCox": g3.WarpingBoxCox, "BoxCoxLinear2": g3.BoxCoxLinear2}
 MEANS = {"Zero": g3.Zero, "Bias": g3.Bias, "Linear": g3.Linear}
 
 
@@ -74,6 +74,8 @@ def build_transport(spec, X):
 def build_mapping(mp):
     if mp["type"] == "composed":
         return build_mapping(mp["m1"]) @ build_mapping(mp["m2"])
+    if mp["type"] == "invsum":
+        return g3.MappingInvSum(build_mapping(mp["m1"]), build_mapping(mp["m2"]))
     mkw = {"name": mp["name"]} if "name" in mp else {}
     if "n" in mp:
         mkw["n"] = mp["n"]
@@ -89,7 +91,12 @@ def build_process(spec, X, strict=True):
     cls = {("gauss", False): g3.GP, ("gauss", True): g3.WGP, ("student", False): g3.TP, ("student", True): g3.WTP}[(kind, warped)]
     loc = spec.get("location", {"type": "Zero"})
     lkw = {"name": loc["name"]} if "name" in loc else {}
-    location = _pot(MEANS[loc["type"]](_x_arg(X, loc.get("dims")), **lkw), loc)
+    if loc["type"] == "Power":
+        location = _pot(g3.Power(_x_arg(X, loc.get("dims")), n=loc.get("n", 2), **lkw), loc)
+    elif loc["type"] == "BlackBox":
+        location = g3.BlackBox(loc["element"], _x_arg(X, loc.get("dims")), **lkw)
+    else:
+        location = _pot(MEANS[loc["type"]](_x_arg(X, loc.get("dims")), **lkw), loc)
     mapping = build_mapping(spec.get("mapping", {"type": "Identity"}))
     kw = {}
     if "name" in spec:

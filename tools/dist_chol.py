@@ -86,6 +86,18 @@ def main():
             r.update(post_mean_err=e_m, post_var_err=e_v, grad_err=e_g, alpha_err=e_a, ms_alpha=g["ms_alpha"],
                      ms_inverse=g["ms_inverse"], ms_contract=g["ms_contract"])
         print("rank", rank, "check ok", err, err_u, flush=True)
+    for i, a in enumerate(sys.argv):             # --post M: distributed posterior moments at M test points (1 x G grid)
+        if a == "--post":
+            import time
+            M = int(sys.argv[i + 1])
+            Xs = np.random.default_rng(11).uniform(0, N ** (1.0 / 3.0), size=(M, 3))
+            ctx.comm_barrier()
+            t0 = time.perf_counter()
+            m, v = ctx.dist_posterior(Xs, noise=False)
+            ctx.comm_barrier()
+            dt = time.perf_counter() - t0
+            r.update(post_M=M, ms_posterior=1e3 * dt, post_tflops=float(N) ** 2 * M * 2 / 2 / dt / 1e12 * 1.0,
+                     post_finite=bool(np.all(np.isfinite(m)) and np.all(v >= 0) and np.all(v <= 1.0 + 1e-9)))
     if "--grad" in sys.argv:                     # timing of the distributed gradient at full size (1 x G grid)
         g = ctx.dist_grad(5, cfac=1.0, want_ddelta=False)
         n = float(N)
