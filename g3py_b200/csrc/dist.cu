@@ -377,6 +377,7 @@ int dist_events(g3_ctx* ctx, g3_dist* d) {
 
 // K pieces of this rank, generated from the replicated X
 int dist_build(g3_ctx* ctx, g3_dist* d) {
+  G3_NVTX("g3_dist:gram pieces");
   const int nb = d->nb, D = ctx->D;
   double* Xg = (double*)g3_ws(ctx, "dist_xg", sizeof(double) * (size_t)d->N * D);
   if (!Xg) return -2;
@@ -413,6 +414,7 @@ int dist_build(g3_ctx* ctx, g3_dist* d) {
 }
 
 int dist_factor(g3_ctx* ctx, g3_dist* d) {
+  G3_NVTX("g3_dist:block-cyclic potrf");
   NcclApi* api = d->nranks > 1 ? nccl_api(&ctx->err) : nullptr;
   if (d->nranks > 1 && !api) return -5;
   const int nP = d->nP, nb = d->nb, Pr = d->Pr, Pc = d->Pc, p = d->p, q = d->q, nslot = d->nslot, w = d->w;
@@ -792,6 +794,7 @@ int g3_dist_factor(g3_ctx* ctx, const g3_kernel_desc* desc, const double* theta,
 // solves with the diagonal block, u_J goes to every rank (nb doubles), and the column ranks push L_IJ u_J into their c.
 // No panel data moves; L is read once.
 int g3_dist_solve(g3_ctx* ctx, const double* delta, double* beta_out, double* u_out_or_NULL, float* ms) {
+  G3_NVTX("g3_dist_solve");
   if (!ctx || !delta || !beta_out) return g3_fail_msg(ctx, "g3_dist_solve: bad arguments");
   g3_dist* d = ctx->dist;
   if (!d || !d->factored) return g3_fail_msg(ctx, "g3_dist_solve: call g3_dist_factor first");
@@ -922,6 +925,7 @@ int g3_dist_residual(g3_ctx* ctx, int nvec, unsigned seed, double* rel_err) {
 // accumulator; the residual of the next block is the sum of the accumulators over the ranks (one reduce of Mc x nb per
 // step).  K* blocks are generated on the fly by the owner.  Needs g3_dist_factor + g3_dist_solve (for u) on a 1 x G grid.
 int g3_dist_posterior(g3_ctx* ctx, const double* Xs, int M, int flags, double* mean_out, double* var_out) {
+  G3_NVTX("g3_dist_posterior");
   if (!ctx || !Xs || M <= 0 || !mean_out || !var_out) return g3_fail_msg(ctx, "g3_dist_posterior: bad arguments");
   g3_dist* d = ctx->dist;
   if (!d || !d->factored || !d->solved) return g3_fail_msg(ctx, "g3_dist_posterior: call g3_dist_factor and g3_dist_solve first");
@@ -935,11 +939,11 @@ int g3_dist_posterior(g3_ctx* ctx, const double* Xs, int M, int flags, double* m
   const int skip_pn = (flags & G3_POST_NOISE) ? 0 : 1;
   double* dXs = (double*)g3_ws(ctx, "dp_xs", sizeof(double) * (size_t)g3_pad(M) * D);
   double* C = (double*)g3_ws(ctx, "dp_c", sizeof(double) * (size_t)Mc * N);
-  double* R = (double*)g3_ws(ctx, "dp_r", sizeof(double) * (size_t)Mc * nb * 2);
+  double* R = (double*)g3_ws(ctx, "dp_r", sizeof(double) * (size_t)Mc * nb * 4);      // 2 x [V_J | packed reduce block]
+  const size_t be = blk_elems(d);
   double* mom = (double*)g3_ws(ctx, "dp_mom", sizeof(double) * (size_t)g3_pad(M) * 3);
   double* kss = (double*)g3_ws(ctx, "dp_kss", sizeof(double) * 4);
   if (!dXs || !C || !R || !mom || !kss) return -2;
-  double* S = R + (size_t)Mc * nb;                       // packed block of the accumulator (reduce buffer)
   const int Mp = g3_pad(M);
   double *mean = mom, *nrm = mom + Mp, *kvec = mom + 2 * (size_t)Mp;
   G3_CUDA(ctx, cudaMemsetAsync(dXs, 0, sizeof(double) * (size_t)Mp * D, MS));
@@ -947,41 +951,68 @@ int g3_dist_posterior(g3_ctx* ctx, const double* Xs, int M, int flags, double* m
   G3_CUDA(ctx, cudaMemsetAsync(mom, 0, sizeof(double) * (size_t)Mp * 3, MS));
   int rc;
   if ((rc = g3_gram_diag_min(ctx, d->desc, dXs, M, D, d->dtheta, d->P, 1, kss, kss + 1, nullptr, skip_pn, kvec))) return rc;
+  // The owner's push V_J L_IJ^T into its accumulator is split into three launches on a background stream: the next column
+  // block (needed by the very next step), the blocks up to this rank's next own panel, and the rest.  A step only waits for
+  // the piece of this rank's latest panel that contains its column block (the stream is in order, so earlier panels are
+  // done too), so the pushes of G - 1 ranks overlap with the reduce / solve chain of the current owner.
+  cudaStream_t BS = ctx->panel_stream;
+  cudaEvent_t ev_piece[3] = {d->ev_upd[0], d->ev_upd[1], d->ev_upd[2]}, ev_main = d->ev_upd[3];
   for (int m0 = 0; m0 < M; m0 += Mc) {
     const int mc = std::min(Mc, Mp - m0);                // rows of this chunk (multiple of 128; padding rows are zero inputs)
     const int mreal = std::min(mc, M - m0);
+    G3_CUDA(ctx, cudaEventRecord(d->ev_join, BS));       // pushes of the previous chunk still read / write C and R
+    G3_CUDA(ctx, cudaStreamWaitEvent(MS, d->ev_join, 0));
     G3_CUDA(ctx, cudaMemsetAsync(C, 0, sizeof(double) * (size_t)mc * N, MS));
+    int Jm = -1;                                         // my latest own panel
     for (int J = 0; J < nP; ++J) {
       const int owner = J % G;
       const bool mine = owner == d->rank;
+      if (Jm >= 0) {                                     // my contributions to column block J are complete?
+        const int piece = J == Jm + 1 ? 0 : (J < Jm + G ? 1 : 2);
+        G3_CUDA(ctx, cudaStreamWaitEvent(MS, ev_piece[piece], 0));
+      }
+      double* Rj = R + (size_t)((J / G) & 1) * Mc * nb * 2;     // V_J buffer, alternating between this rank's own panels
+      double* Sj = Rj + (size_t)Mc * nb;
       // pack my accumulator block J (strided in C) for the sum over the ranks onto the owner
       if (G > 1)
-        G3_CUDA(ctx, cudaMemcpy2DAsync(S, sizeof(double) * nb, C + (size_t)J * nb, sizeof(double) * N, sizeof(double) * nb, (size_t)mc,
+        G3_CUDA(ctx, cudaMemcpy2DAsync(Sj, sizeof(double) * nb, C + (size_t)J * nb, sizeof(double) * N, sizeof(double) * nb, (size_t)mc,
                                        cudaMemcpyDeviceToDevice, MS));
       if (mine) {
         GramArgs a;                                      // K*[chunk, J] (cross form: Noise contributes zeros, kernels.py:367-371)
         memset(&a, 0, sizeof a);
         a.X1 = dXs + (size_t)m0 * D; a.X2 = ctx->dX + (size_t)J * nb * D; a.n1 = mreal; a.n2 = nb; a.D = D; a.same = 0;
         a.skip_process_noise = skip_pn;
-        a.theta = d->dtheta; a.P = d->P; a.K = R; a.ldk = nb;
-        if (mreal < mc) G3_CUDA(ctx, cudaMemsetAsync(R, 0, sizeof(double) * (size_t)mc * nb, MS));
+        a.theta = d->dtheta; a.P = d->P; a.K = Rj; a.ldk = nb;
+        if (mreal < mc) G3_CUDA(ctx, cudaMemsetAsync(Rj, 0, sizeof(double) * (size_t)mc * nb, MS));
         if ((rc = g3_gram_launch(ctx, d->desc, a, 1))) return rc;
       }
-      if (G > 1) G3_NCCL(ctx, api, api->Reduce(S, S, (size_t)mc * nb, ncclDouble, ncclSum, owner, d->comm, MS));
+      if (G > 1) G3_NCCL(ctx, api, api->Reduce(Sj, Sj, (size_t)mc * nb, ncclDouble, ncclSum, owner, d->comm, MS));
       if (!mine) continue;
-      const double* acc = G > 1 ? S : C + (size_t)J * nb;
-      sub_block_kernel<<<(unsigned)(((size_t)mc * nb + 255) / 256), 256, 0, MS>>>(R, nb, acc, G > 1 ? nb : N, R, mc, nb);
+      const double* acc = G > 1 ? Sj : C + (size_t)J * nb;
+      sub_block_kernel<<<(unsigned)(((size_t)mc * nb + 255) / 256), 256, 0, MS>>>(Rj, nb, acc, G > 1 ? nb : N, Rj, mc, nb);
       G3_LAUNCH_CHECK(ctx);
       double* piece = d->store + d->off[J];
-      if ((rc = g3_panel_solve(ctx, R, mc, nb, piece, d->dinv + d->dinv_off[J]))) return rc;     // V_J = R_J L_JJ^-T
-      post_accum_kernel<<<(mreal + 7) / 8, 256, 0, MS>>>(R, mreal, nb, d->u + (size_t)J * nb, mean + m0, nrm + m0);
+      if ((rc = g3_panel_solve(ctx, Rj, mc, nb, piece, d->dinv + d->dinv_off[J]))) return rc;     // V_J = R_J L_JJ^-T
+      post_accum_kernel<<<(mreal + 7) / 8, 256, 0, MS>>>(Rj, mreal, nb, d->u + (size_t)J * nb, mean + m0, nrm + m0);
       G3_LAUNCH_CHECK(ctx);
-      const int below = (nP - 1 - J) * nb;
-      if (below > 0 &&
-          (rc = g3_panel_gemm(ctx, C + (size_t)(J + 1) * nb, N, mc, below, R, nb, piece + blk_elems(d), nb, nb, 1.0, 1.0)))
-        return rc;
+      // pushes on the background stream, in column order
+      G3_CUDA(ctx, cudaEventRecord(ev_main, MS));
+      G3_CUDA(ctx, cudaStreamWaitEvent(BS, ev_main, 0));
+      ctx->stream = BS;
+      const int c0[3] = {J + 1, J + 2, std::max(J + G, J + 2)};
+      const int c1[3] = {std::min(J + 2, nP), std::min(std::max(J + G, J + 2), nP), nP};
+      for (int k = 0; k < 3 && !rc; ++k) {
+        if (c1[k] > c0[k])
+          rc = g3_panel_gemm(ctx, C + (size_t)c0[k] * nb, N, mc, (c1[k] - c0[k]) * nb, Rj, nb, piece + (size_t)(c0[k] - J) * be, nb, nb, 1.0, 1.0);
+        cudaEventRecord(ev_piece[k], BS);
+      }
+      ctx->stream = MS;
+      if (rc) return rc;
+      Jm = J;
     }
   }
+  G3_CUDA(ctx, cudaEventRecord(d->ev_join, BS));
+  G3_CUDA(ctx, cudaStreamWaitEvent(MS, d->ev_join, 0));
   std::vector<double> h((size_t)Mp * 3);
   double hk[4];
   G3_CUDA(ctx, cudaMemcpyAsync(h.data(), mom, sizeof(double) * (size_t)Mp * 3, cudaMemcpyDeviceToHost, MS));
@@ -1008,6 +1039,7 @@ int g3_dist_posterior(g3_ctx* ctx, const double* Xs, int M, int flags, double* m
 //   dtheta[p] = 1/2 sum_ij (c alpha_i alpha_j - K^-1_ij) dK_ij/dtheta_p,  ddelta = -c alpha.
 // The factor is consumed (L is overwritten by L^-1).  Device times (max over ranks) in ms3 = {alpha, inverse, contraction}.
 int g3_dist_grad(g3_ctx* ctx, double cfac, double* dtheta_out, double* ddelta_out_or_NULL, float* ms3) {
+  G3_NVTX("g3_dist_grad");
   if (!ctx || !dtheta_out) return g3_fail_msg(ctx, "g3_dist_grad: bad arguments");
   g3_dist* d = ctx->dist;
   if (!d || !d->factored || !d->solved) return g3_fail_msg(ctx, "g3_dist_grad: call g3_dist_factor and g3_dist_solve first");

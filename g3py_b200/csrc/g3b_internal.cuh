@@ -8,6 +8,14 @@
 #include <map>
 #include "../../include/g3b.h"
 
+// NVTX ranges around the host-side stages (header-only nvtx3: no link dependency; a no-op without a profiler attached)
+#include <nvtx3/nvToolsExt.h>
+struct g3_nvtx_range {
+  explicit g3_nvtx_range(const char* name) { nvtxRangePushA(name); }
+  ~g3_nvtx_range() { nvtxRangePop(); }
+};
+#define G3_NVTX(name) g3_nvtx_range g3_nvtx_scope_##__LINE__(name)
+
 #define G3_TILE 128          // factorisation block size: every device matrix is padded to a multiple
 #define G3_BM 64             // GEMM CTA tile rows   (two CTAs per 128-row block)
 #define G3_BN 128            // GEMM CTA tile cols

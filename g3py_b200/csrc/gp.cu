@@ -251,6 +251,7 @@ static GpBufs gp_view(const GpBufs& w, int b0, int N, int P, int delta_stride) {
 static int gp_grad_stage(g3_ctx* ctx, GpBufs& w, int B);
 
 static int gp_after_potrf(g3_ctx* ctx, GpBufs& w, int B) {
+  G3_NVTX("g3:solve+beta");
   const g3_gp_state& st = ctx->gp;
   const int N = ctx->N, Np = g3_pad(N);
   int rc;
@@ -269,6 +270,7 @@ static int gp_after_potrf(g3_ctx* ctx, GpBufs& w, int B) {
 
 // Gradient stages on a resident factor: alpha = L^-T u, U = L^-T, K^-1 = U U^T (over L), W-contraction, d/d delta.
 static int gp_grad_stage(g3_ctx* ctx, GpBufs& w, int B) {
+  G3_NVTX("g3:gradient(alpha,trtri,lauum,vjp)");
   const g3_gp_state& st = ctx->gp;
   const int N = ctx->N, Np = g3_pad(N), T = Np / TS, P = st.desc.n_theta;
   int rc;
@@ -294,6 +296,7 @@ static int gp_grad_stage(g3_ctx* ctx, GpBufs& w, int B) {
 }
 
 static int gp_build_and_factor(g3_ctx* ctx, GpBufs& w, int B, const double* shift, const int* bmap, int nb) {
+  G3_NVTX("g3:gram+potrf");
   const g3_gp_state& st = ctx->gp;
   const int N = ctx->N, Np = g3_pad(N);
   GramArgs a;
@@ -375,6 +378,7 @@ int g3_gp_upload(g3_ctx* ctx, const g3_kernel_desc* desc, int kind, const double
 }
 
 int g3_gp_run(g3_ctx* ctx) {
+  G3_NVTX("g3_gp_run");
   if (!ctx || !ctx->gp.valid) return g3_fail_msg(ctx, "g3_gp_run: nothing uploaded");
   G3_CUDA(ctx, cudaSetDevice(ctx->device));
   const g3_gp_state& st = ctx->gp;
@@ -420,6 +424,7 @@ int g3_gp_run(g3_ctx* ctx) {
 
 int g3_gp_download(g3_ctx* ctx, double* beta, double* logdet, double* dtheta_or_NULL, double* ddelta_or_NULL,
                    int* status) {
+  G3_NVTX("g3_gp_download");
   if (!ctx || !ctx->gp.valid) return g3_fail_msg(ctx, "g3_gp_download: nothing uploaded");
   G3_CUDA(ctx, cudaSetDevice(ctx->device));
   const g3_gp_state& st = ctx->gp;
@@ -512,6 +517,7 @@ int g3_gp_download(g3_ctx* ctx, double* beta, double* logdet, double* dtheta_or_
 }
 
 int g3_gp_grad_resume(g3_ctx* ctx, double* dtheta, double* ddelta) {
+  G3_NVTX("g3_gp_grad_resume");
   if (!ctx || !ctx->gp.valid || !ctx->gp.factor_resident || ctx->gp.want_grad)
     return g3_fail_msg(ctx, "g3_gp_grad_resume: no resident factor (call g3_gp_logp_grad without gradient outputs first)");
   G3_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -395,6 +395,7 @@ static void launch_u_diag(g3_ctx* ctx, const double* Dinv, double* U, int Np, in
 
 int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, double* logdet, int* info,
                      const int* bmap, int nb, int w_outer, double* U_pipe) {
+  G3_NVTX("g3:potrf");
   ctx->trtri_done = 0;
   const int T = Np / TS;
   if (!ctx->diag_ready) {
@@ -788,6 +789,7 @@ static void launch_u_diag(g3_ctx* ctx, const double* Dinv, double* U, int Np, in
 }
 
 int g3_trtri_batched(g3_ctx* ctx, const double* L, double* U, int Np, int B, const double* Dinv) {
+  G3_NVTX("g3:trtri");
   const int T = Np / TS;
   int rc;
   launch_u_diag(ctx, Dinv, U, Np, T, B, 0, T);
@@ -808,6 +810,7 @@ int g3_trtri_batched(g3_ctx* ctx, const double* L, double* U, int Np, int B, con
 }
 
 int g3_lauum_batched(g3_ctx* ctx, const double* U, double* Kinv, int Np, int B) {
+  G3_NVTX("g3:lauum");
   const int T = Np / TS;
   int rc;
   CUtensorMap tmA, tmB;
