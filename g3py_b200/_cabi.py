@@ -509,12 +509,12 @@ class Context:
         self._ck(self._lib.g3_comm_allreduce(self._h, _d(v), v.size, {"sum": 0, "max": 1, "min": 2}[op]), "g3_comm_allreduce")
         return v
 
-    def dist_factor(self, desc, theta, nb, Pr, Pc, lookahead=True, ring=3):
+    def dist_factor(self, desc, theta, nb, Pr, Pc, lookahead=True, ring=2):
         theta = _f64(theta).ravel()
         if theta.size != desc.n_theta:
             raise ValueError("dist_factor: theta has %d entries, the descriptor takes %d" % (theta.size, desc.n_theta))
         ld, info, mg, mp, gib = C.c_double(), C.c_int(), C.c_float(), C.c_float(), C.c_double()
-        flags = (0 if lookahead else 1) | (2 if ring == 2 else 0)
+        flags = (0 if lookahead else 1) | (4 if ring == 3 else 0)
         self._resident = None
         self._ck(self._lib.g3_dist_factor(self._h, C.byref(desc), _d(theta), int(nb), int(Pr), int(Pc), flags,
                                           C.cast(C.byref(ld), _dp), C.cast(C.byref(info), _ip), C.byref(mg), C.byref(mp),

@@ -28,6 +28,7 @@
 #include <nccl.h>
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <random>
 
@@ -119,6 +120,14 @@ struct g3_dist {
 };
 
 namespace {
+
+// restores ctx->stream on every exit path of a function that routes launches to other streams
+struct stream_guard {
+  g3_ctx* c;
+  cudaStream_t s;
+  explicit stream_guard(g3_ctx* ctx) : c(ctx), s(ctx->stream) {}
+  ~stream_guard() { c->stream = s; }
+};
 
 inline int first_blk(int J, int p, int Pr) { return J + (((p - J % Pr) % Pr) + Pr) % Pr; }
 inline int cnt_blk(int J, int p, int Pr, int nP) {
@@ -419,6 +428,7 @@ int dist_factor(g3_ctx* ctx, g3_dist* d) {
   if (d->nranks > 1 && !api) return -5;
   const int nP = d->nP, nb = d->nb, Pr = d->Pr, Pc = d->Pc, p = d->p, q = d->q, nslot = d->nslot, w = d->w;
   cudaStream_t MS = ctx->stream, PS = ctx->panel_stream, CS = d->cs;
+  stream_guard guard(ctx);
   const size_t be = blk_elems(d), de = (size_t)w * TS * TS;
   int rc = 0;
   G3_CUDA(ctx, cudaEventRecord(d->ev_start, MS));
@@ -605,6 +615,10 @@ int g3_comm_init(g3_ctx* ctx, int nranks, int rank, const char* id) {
   d->nranks = nranks;
   d->rank = rank;
   if (nranks == 1) return 0;
+  // The collectives here are panel broadcasts that only have to keep up with the trailing updates (tens of GB/s) and tiny
+  // reductions; every NCCL channel is a CTA that spins on an SM the fp64 GEMMs could use.  8 channels measured 0.5 % faster
+  // than the default on the N=131072 factorisation (profiles/r02g_*); a user setting wins.
+  setenv("NCCL_MAX_NCHANNELS", "8", 0);
   NcclApi* api = nccl_api(&ctx->err);
   if (!api) return -5;
   ncclUniqueId uid;
@@ -709,7 +723,7 @@ int g3_dist_factor(g3_ctx* ctx, const g3_kernel_desc* desc, const double* theta,
   d->N = ctx->N; d->nb = nb; d->nP = ctx->N / nb; d->Pr = Pr; d->Pc = Pc; d->w = nb / TS;
   d->p = d->rank % Pr; d->q = d->rank / Pr;
   d->lookahead = (flags & G3_DIST_NO_LOOKAHEAD) ? 0 : 1;
-  d->nslot = (flags & G3_DIST_RING2) ? 2 : 3;
+  d->nslot = (flags & G3_DIST_RING3) ? 3 : 2;
   d->desc = *desc;
   d->P = desc->n_theta;
   if ((rc = dist_events(ctx, d))) return rc;
@@ -955,7 +969,15 @@ int g3_dist_posterior(g3_ctx* ctx, const double* Xs, int M, int flags, double* m
   // block (needed by the very next step), the blocks up to this rank's next own panel, and the rest.  A step only waits for
   // the piece of this rank's latest panel that contains its column block (the stream is in order, so earlier panels are
   // done too), so the pushes of G - 1 ranks overlap with the reduce / solve chain of the current owner.
-  cudaStream_t BS = ctx->panel_stream;
+  // The chain runs on the HIGH-priority stream and the pushes on the context's own (lowest-priority) stream: pending CTAs of
+  // the chain (NCCL reduce included) are scheduled ahead of the thousands of queued GEMM CTAs of a push.
+  stream_guard guard(ctx);
+  cudaStream_t BS = ctx->stream;
+  cudaStream_t CH = ctx->panel_stream;
+  G3_CUDA(ctx, cudaEventRecord(d->ev_start, BS));
+  G3_CUDA(ctx, cudaStreamWaitEvent(CH, d->ev_start, 0));
+  MS = CH;
+  ctx->stream = CH;
   cudaEvent_t ev_piece[3] = {d->ev_upd[0], d->ev_upd[1], d->ev_upd[2]}, ev_main = d->ev_upd[3];
   for (int m0 = 0; m0 < M; m0 += Mc) {
     const int mc = std::min(Mc, Mp - m0);                // rows of this chunk (multiple of 128; padding rows are zero inputs)
@@ -1007,12 +1029,14 @@ int g3_dist_posterior(g3_ctx* ctx, const double* Xs, int M, int flags, double* m
         cudaEventRecord(ev_piece[k], BS);
       }
       ctx->stream = MS;
-      if (rc) return rc;
+      if (rc) { ctx->stream = BS; return rc; }
       Jm = J;
     }
   }
-  G3_CUDA(ctx, cudaEventRecord(d->ev_join, BS));
-  G3_CUDA(ctx, cudaStreamWaitEvent(MS, d->ev_join, 0));
+  ctx->stream = BS;                                      // back on the context's stream, after both are done
+  G3_CUDA(ctx, cudaEventRecord(d->ev_join, CH));
+  G3_CUDA(ctx, cudaStreamWaitEvent(BS, d->ev_join, 0));
+  MS = BS;
   std::vector<double> h((size_t)Mp * 3);
   double hk[4];
   G3_CUDA(ctx, cudaMemcpyAsync(h.data(), mom, sizeof(double) * (size_t)Mp * 3, cudaMemcpyDeviceToHost, MS));

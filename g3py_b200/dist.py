@@ -22,7 +22,7 @@ def se_noise_desc(X):
     return b.finish()
 
 
-def run_dist_cholesky(ctx, N, nb=1024, grid=None, theta=None, lookahead=True, ring=3, verify=0, seed=1234, X=None, y=None):
+def run_dist_cholesky(ctx, N, nb=1024, grid=None, theta=None, lookahead=True, ring=2, verify=0, seed=1234, X=None, y=None):
     """One timed distributed factorisation + solve of the SE(+noise) Gram matrix of the config-5 inputs on the
     communicator of `ctx` (comm.init first).  Returns a dict on every rank; times are device times, max over ranks.
     verify = number of probe vectors of the on-hardware residual check (0: skip)."""

@@ -256,7 +256,8 @@ int g3_comm_allreduce(g3_ctx* ctx, double* vals, int n, int op);
  * the devices for g3_dist_solve / g3_dist_residual until g3_dist_free or the next g3_dist_factor.
  * Times are device times (CUDA events), max over ranks.  All ranks must make the same calls in the same order. */
 enum { G3_DIST_NO_LOOKAHEAD = 1,   /* factor panel J+1 only after the whole trailing update of panel J (for comparison) */
-       G3_DIST_RING2 = 2 };        /* two panel buffers instead of three */
+       G3_DIST_RING2 = 2,          /* (default now) two panel buffers */
+       G3_DIST_RING3 = 4 };        /* three panel buffers: ranks may drift two steps apart (measured slower) */
 int g3_dist_factor(g3_ctx* ctx, const g3_kernel_desc* desc, const double* theta, int nb, int Pr, int Pc, int flags,
                    double* logdet /* sum log diag L */, int* info, float* ms_gram, float* ms_potrf, double* local_gib);
 /* u = L^-1 delta (delta: N host doubles, read on rank 0), beta = u'u - the quadratic form of logp_cho

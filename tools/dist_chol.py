@@ -1,7 +1,7 @@
 """Multi-GPU block-cyclic Cholesky driver (PyTorch-free: NCCL lives inside libg3b.so).
 
   python -m torch.distributed.run --nproc-per-node G tools/dist_chol.py N [nb] [--grid PRxPC] [--verify] [--check]
-                                                                           [--no-lookahead] [--ring2] [--reps R]
+                                                                           [--no-lookahead] [--ring3] [--reps R] [--post M] [--grad]
   (any launcher that exports RANK / WORLD_SIZE / LOCAL_RANK / MASTER_PORT works; G = 1: plain `python`)
 
 --verify : on-hardware residual probe (4 vectors, L (L^T v) vs K v with K regenerated from X)
@@ -37,7 +37,7 @@ def main():
     r = None
     for rep in range(reps):                          # first pass warms allocations / NCCL channels
         r = run_dist_cholesky(ctx, N, nb=nb, grid=grid, lookahead="--no-lookahead" not in sys.argv,
-                              ring=2 if "--ring2" in sys.argv else 3, verify=verify if rep == reps - 1 else 0)
+                              ring=3 if "--ring3" in sys.argv else 2, verify=verify if rep == reps - 1 else 0)
     if "--check" in sys.argv:
         X, y = workloads.c5_inputs(N)
         d = ((X[:, None, :] - X[None, :, :]) ** 2 * 0.5).sum(-1)
