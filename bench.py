@@ -305,6 +305,36 @@ def main():
     ms_step = ms / args.steps
     value = world * B / (ms_step * 1e-3)
 
+    # ---- the same step with the deep panel updates on the int8 tensor cores (g3_set_gemm_mode(G3_GEMM_OZAKI)) ----------
+    gemm_modes = None
+    if world == 1 and not args.no_extras:
+        try:
+            ctx.set_gemm_mode("ozaki", 1024)
+            k0 = ctx.ozaki_launch_count()
+            ctx.gp_run()
+            ctx.sync()
+            ctx.timer_begin()
+            for _ in range(args.steps):
+                ctx.gp_run()
+            ms_oz = ctx.timer_end() / args.steps
+            ro = ctx.gp_download()
+            gemm_modes = {"dmma": {"ms_per_step": ms_step, "value": value},
+                          "ozaki_int8": {"ms_per_step": ms_oz, "value": B / (ms_oz * 1e-3), "min_k": 1024,
+                                         "int8_update_launches_per_step": (ctx.ozaki_launch_count() - k0) // (args.steps + 1),
+                                         "max_rel_diff_vs_dmma": {"logdet": float(np.max(np.abs(ro["logdet"] - res["logdet"]) / np.abs(res["logdet"]))),
+                                                                  "dtheta": float(np.max(np.abs(ro["dtheta"] - res["dtheta"])) / np.max(np.abs(res["dtheta"])))},
+                                         "status_ok": bool(np.all(ro["status"] == 0))},
+                          "default": "dmma",
+                          "note": "tcgen05.mma kind::i8 slice products (9 slices of 7 bits, exact int32 accumulation in tensor memory) "
+                                  "for the block-column updates of the batched Cholesky with contraction >= 1024; fp64-equivalent "
+                                  "results, but at N=4096 x 64 the left-looking block-column update has no A-operand reuse across "
+                                  "CTAs and re-reads the slice planes from HBM (45 slice-pair passes), so it only matches the DMMA "
+                                  "rate here - DMMA stays the default (DESIGN.md section 6)"}
+        except Exception as e:                                 # reported, never hidden
+            gemm_modes = {"error": repr(e)}
+        finally:
+            ctx.set_gemm_mode("dmma")
+
     # ---- end to end through the public API ----------------------------------------------------
     if world == 1:
         call = lambda: gp.logp_dlogp_batch(Theta)
@@ -402,6 +432,8 @@ def main():
                                                   % (elems / 1e9, elems * 80 * 2 / (pk["dfma_tflops"] * 1e12) * 1e3, pk["dfma_tflops"],
                                                      gram_ms, prof["gram_vjp"]["ms"] / prof_steps)}
     line.update(extras)
+    if gemm_modes is not None:
+        line["gemm_modes"] = gemm_modes
     if not args.no_metric2:
         try:
             ctx.trim()

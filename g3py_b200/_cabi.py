@@ -51,6 +51,8 @@ SIGNATURES = {
     "g3_set_splitk": (C.c_int, [_ctxp, C.c_int]),
     "g3_set_trtri_pipeline": (C.c_int, [_ctxp, C.c_int]),
     "g3_set_groups": (C.c_int, [_ctxp, C.c_int]),
+    "g3_set_gemm_mode": (C.c_int, [_ctxp, C.c_int, C.c_int]),
+    "g3_ozaki_launch_count": (C.c_int64, [_ctxp]),
     "g3_timer_begin": (C.c_int, [_ctxp]),
     "g3_timer_end": (C.c_int, [_ctxp, C.POINTER(C.c_float)]),
     "g3_launch_count": (C.c_int64, [_ctxp]),
@@ -217,6 +219,14 @@ class Context:
 
     def set_splitk(self, on):
         self._ck(self._lib.g3_set_splitk(self._h, int(bool(on))), "g3_set_splitk")
+
+    def set_gemm_mode(self, mode, min_k=0):
+        """'dmma' (default) or 'ozaki': deep panel updates of the batched Cholesky on the int8 tensor cores (include/g3b.h)."""
+        m = {"dmma": 0, "ozaki": 1}.get(mode, mode)
+        self._ck(self._lib.g3_set_gemm_mode(self._h, int(m), int(min_k)), "g3_set_gemm_mode")
+
+    def ozaki_launch_count(self):
+        return int(self._lib.g3_ozaki_launch_count(self._h))
 
     def set_groups(self, n):
         self._ck(self._lib.g3_set_groups(self._h, int(n)), "g3_set_groups")

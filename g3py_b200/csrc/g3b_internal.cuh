@@ -74,6 +74,9 @@ struct g3_ctx {
   int force_left = 0;                  // set by g3_gp_run for batches of more than 8 items (their stream groups hold 8)
   int splitk = 1;                      // allow split-K for few-tile / deep-K GEMM launches (g3_set_splitk)
   struct g3_dist* dist = nullptr;      // multi-GPU state (dist.cu): NCCL communicator, block-cyclic panels
+  int gemm_mode = 0;                   // G3_GEMM_DMMA / G3_GEMM_OZAKI (g3_set_gemm_mode)
+  int oz_min_k = 1024;                 // Ozaki updates only for contractions at least this deep (DMMA below)
+  int64_t oz_launches = 0;             // int8 tensor-core update launches since creation
 };
 void g3_dist_destroy(g3_ctx* ctx);     // called by g3_ctx_destroy
 
@@ -154,6 +157,18 @@ int g3_lauum_batched(g3_ctx* ctx, const double* U, double* Kinv, int Np, int B);
 int g3_trsv_fwd(g3_ctx* ctx, const double* L, const double* Dinv, double* r, double* u, double* beta,
                 int Np, int B);
 int g3_trsv_bwd(g3_ctx* ctx, const double* L, const double* Dinv, double* s, double* alpha, int Np, int B);
+
+// ---- int8 tensor-core (Ozaki) panel updates (ozaki.cu) ----
+struct g3_oz_state {
+  int Np = 0, B = 0;
+  long long plane_stride = 0;          // bytes between significance planes: B * Np * Np
+  int8_t* planes = nullptr;            // [9][B Np][Np] slices of L
+  double* scale = nullptr;             // [B Np] power-of-two row scales
+  CUtensorMap tmA, tmB;
+};
+int g3_oz_prepare(g3_ctx* ctx, const double* A, int Np, int B, g3_oz_state* st);
+int g3_oz_slice(g3_ctx* ctx, const g3_oz_state* st, const double* A, int j0, int j1);
+int g3_oz_update(g3_ctx* ctx, const g3_oz_state* st, double* A, int j0, int j1);
 
 // ---- Gram (gram.cu) ----
 struct GramArgs {

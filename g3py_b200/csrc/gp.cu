@@ -335,6 +335,15 @@ int g3_set_splitk(g3_ctx* ctx, int on) {
   return 0;
 }
 
+int g3_set_gemm_mode(g3_ctx* ctx, int mode, int min_k) {
+  if (mode != G3_GEMM_DMMA && mode != G3_GEMM_OZAKI) return g3_fail_msg(ctx, "g3_set_gemm_mode: unknown mode");
+  ctx->gemm_mode = mode;
+  if (min_k > 0) ctx->oz_min_k = (min_k + 127) / 128 * 128;
+  return 0;
+}
+
+int64_t g3_ozaki_launch_count(g3_ctx* ctx) { return ctx->oz_launches; }
+
 int g3_set_groups(g3_ctx* ctx, int n_groups) {
   ctx->n_groups = n_groups < 1 ? 1 : (n_groups > G3_MAX_GROUPS ? G3_MAX_GROUPS : n_groups);
   return 0;

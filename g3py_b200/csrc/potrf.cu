@@ -467,6 +467,35 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
     return g3_gemm_launch(ctx, tmA, tmB, g, B);
   };
 
+  // ---- batched, fully left-looking, int8 tensor-core mode: 256-wide block columns; the update of a block column with ALL
+  // earlier columns (contraction depth jo * 128) runs as exact int8 slice products (ozaki.cu) once it is deep enough, the
+  // work inside the block column (depth 128) and the triangular solves stay on the DMMA GEMM.
+  if (ctx->gemm_mode == G3_GEMM_OZAKI && w_outer >= T && bmap == nullptr && T >= 4) {
+    g3_oz_state oz;
+    if ((rc = g3_oz_prepare(ctx, A, Np, B, &oz))) return rc;
+    for (int jo = 0; jo < T; jo += 2) {
+      const int je = jo + 2 < T ? jo + 2 : T;
+      if (jo > 0) {
+        if (jo * TS >= ctx->oz_min_k) {
+          if ((rc = g3_oz_update(ctx, &oz, A, jo, je))) return rc;
+          ctx->oz_launches++;
+        } else {  // shallow contraction: one DMMA launch for both tile columns, rows >= jo
+          GemmArgs g = gemm_zero();
+          g.D = A; g.ldd = Np; g.strideD = strideA;
+          g.mode = 0; g.ntx = T - jo; g.nty = je - jo;
+          g.d_r0 = jo * TS; g.d_c0 = jo * TS;
+          g.a_r0 = jo * TS; g.a_rx = TS;
+          g.b_r0 = jo * TS; g.b_ry = TS;
+          g.ka0 = 0; g.kb0 = 0; g.kl0 = jo * TS;
+          g.alpha = -1.0; g.beta = 1.0; g.upper = 1 | 4;
+          if ((rc = g3_gemm_launch(ctx, tmA, tmB, g, B))) return rc;
+        }
+      }
+      if ((rc = factor_block(jo, je))) return rc;
+      if (je < T && (rc = g3_oz_slice(ctx, &oz, A, jo, je))) return rc;
+    }
+    return 0;
+  }
   const bool look = ctx->lookahead && w_outer < T;              // at least two outer blocks
   if (!look) {
     for (int jo = 0; jo < T; jo += w_outer) {

@@ -121,6 +121,16 @@ int g3_set_splitk(g3_ctx* ctx, int on);
 /* Gradient path of few large matrices: compute U = L^-T block by block on a third stream while the look-ahead
  * factorisation is still running (default on; results do not depend on it). */
 int g3_set_trtri_pipeline(g3_ctx* ctx, int on);
+/* Arithmetic of the deep panel updates of the batched (B > 8) Cholesky:
+ *   G3_GEMM_DMMA  (default) fp64 tensor-core GEMM (mma.sync m8n8k4, gemm.cu) everywhere;
+ *   G3_GEMM_OZAKI the update of a 256-wide block column with all earlier columns runs on the INT8 tensor cores
+ *                 (tcgen05.mma kind::i8, accumulators in tensor memory) as exact products of 9 seven-bit slices of L - fp64-
+ *                 equivalent (error of an fp64 dot product), past the DMMA peak for contractions >= min_k (0 keeps the current
+ *                 threshold, default 1024).  Everything else (in-block work, solves, K^-1) stays on the DMMA GEMM.
+ * Replaces nothing in the reference (the arithmetic lives inside LAPACK dpotrf there, g3py/libs/tensors.py:198). */
+enum { G3_GEMM_DMMA = 0, G3_GEMM_OZAKI = 1 };
+int g3_set_gemm_mode(g3_ctx* ctx, int mode, int min_k);
+int64_t g3_ozaki_launch_count(g3_ctx* ctx);
 /* Number of batch groups g3_gp_run processes concurrently on separate streams (default 4, max 8;
  * 1 = a single stream, which is what the per-kernel timers of g3_prof_* need). */
 int g3_set_groups(g3_ctx* ctx, int n_groups);

@@ -821,3 +821,41 @@ def test_threads_get_their_own_context():
             assert scaled_err(lp, want_lp[t::4]) < 1e-11      # 6-item batches take the blocked schedule, 24 the batched one
             assert scaled_err(g, want_g[t::4]) < 1e-9
         assert np.array_equal(out[t][0][0], out[t][2][0]) and np.array_equal(out[t][0][1], out[t][2][1])   # repeatable
+
+
+@pytest.mark.parametrize("N,B,min_k", [(1100, 10, 256), (2048, 12, 256), (1920, 9, 512)])
+def test_ozaki_int8_panel_updates_match_dmma(N, B, min_k):
+    """g3_set_gemm_mode(G3_GEMM_OZAKI): the deep block-column updates of the batched Cholesky run as exact int8 slice
+    products on the tcgen05 tensor cores (csrc/ozaki.cu).  Factor element-wise, beta, log-det against the DMMA mode at
+    1e-13, logp / gradient against the oracle at 1e-9; odd tile counts exercise the 128-wide last block column."""
+    X, y, Theta = orc.c2_inputs(N, B)
+    gp = build_process(SPECS["C2"], X)
+    gp.observed(X, y)
+    ctx = g3.Context(0)
+    try:
+        ctx.set_jitter(gp.consts.jitter, 20)
+        ctx.set_data(X)
+        nat = gp.natural(Theta)
+        delta, _, _, _ = gp._host_terms(nat, X, y, False)
+        delta = np.array(delta)
+        thk = gp._kernel_theta(nat)
+        Np = (N + 127) // 128 * 128
+        out = {}
+        for mode in ("dmma", "ozaki"):
+            ctx.set_gemm_mode(mode, min_k)
+            n0 = ctx.ozaki_launch_count()
+            r = ctx.gp_logp_grad(gp.desc, cabi.KIND_GAUSS, delta, thk, want_grad=False)
+            L = np.tril(ctx.debug_read("gp_A", (B, Np, Np)))
+            g = ctx.gp_logp_grad(gp.desc, cabi.KIND_GAUSS, delta, thk, want_grad=True)
+            out[mode] = (r, L, g, ctx.ozaki_launch_count() - n0)
+        (r0, L0, g0, k0), (r1, L1, g1, k1) = out["dmma"], out["ozaki"]
+        assert k0 == 0 and k1 > 0                                # the int8 kernel ran in ozaki mode only
+        assert np.all(r1["status"] == 0)
+        assert np.max(np.abs(L1 - L0)) <= 1e-13 * np.max(np.abs(L0))
+        assert scaled_err(r1["beta"], r0["beta"]) < 1e-12 and scaled_err(r1["logdet"], r0["logdet"]) < 1e-13
+        assert scaled_err(g1["dtheta"], g0["dtheta"]) < 1e-11 and scaled_err(g1["ddelta"], g0["ddelta"]) < 1e-11
+        op = orc.OracleProcess(SPECS["C2"], X.shape[1])
+        t = op.logp_terms(Theta[0], X, y)
+        assert abs(r1["beta"][0] - t["beta"]) <= TOL * abs(t["beta"]) and abs(r1["logdet"][0] - t["logdet"]) <= TOL * abs(t["logdet"])
+    finally:
+        ctx.close()

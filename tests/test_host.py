@@ -482,3 +482,17 @@ def test_per_call_inputs_do_not_replace_observations(fake):
     loc = gp.location(Th[0], space=X[:5], inputs=X7, outputs=y7, array=True)
     assert scaled_err(loc, pr["location"] if "location" in pr else op.posterior(Th[0], X[:5], X7, y7)["location"]) < 1e-9
     assert np.array_equal(gp.outputs, y) and gp.loglike(Th[0], array=True) == base
+
+
+def test_library_carries_blackwell_native_code():
+    """SASS evidence (B200_PROFILING.md): the fp64 GEMM is DMMA fed by TMA, the int8 panel update is tcgen05 (UTCIMMA) with
+    tensor-memory loads (LDTM) and TMA - checked on the built libg3b.so with cuobjdump (no GPU needed)."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    r = subprocess.run(["cuobjdump", "-sass", g3.lib_path()], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0
+    sass = r.stdout
+    for mnemonic in ("DMMA.8x8x4", "UTMALDG", "UTCIMMA", "LDTM"):
+        assert mnemonic in sass, mnemonic
+    assert "HGMMA" not in sass and "sm_100a" in sass
