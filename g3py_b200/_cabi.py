@@ -51,6 +51,8 @@ SIGNATURES = {
     "g3_set_splitk": (C.c_int, [_ctxp, C.c_int]),
     "g3_set_trtri_pipeline": (C.c_int, [_ctxp, C.c_int]),
     "g3_set_groups": (C.c_int, [_ctxp, C.c_int]),
+    "g3_set_graphs": (C.c_int, [_ctxp, C.c_int]),
+    "g3_graph_replays": (C.c_int64, [_ctxp]),
     "g3_set_gemm_mode": (C.c_int, [_ctxp, C.c_int, C.c_int]),
     "g3_ozaki_launch_count": (C.c_int64, [_ctxp]),
     "g3_timer_begin": (C.c_int, [_ctxp]),
@@ -219,6 +221,13 @@ class Context:
 
     def set_splitk(self, on):
         self._ck(self._lib.g3_set_splitk(self._h, int(bool(on))), "g3_set_splitk")
+
+    def set_graphs(self, on):
+        """CUDA-graph replay of small-batch evaluations (default on)."""
+        self._ck(self._lib.g3_set_graphs(self._h, int(bool(on))), "g3_set_graphs")
+
+    def graph_replays(self):
+        return int(self._lib.g3_graph_replays(self._h))
 
     def set_gemm_mode(self, mode, min_k=0):
         """'dmma' (default) or 'ozaki': deep panel updates of the batched Cholesky on the int8 tensor cores (include/g3b.h)."""

@@ -25,6 +25,7 @@ void* g3_ws(g3_ctx* ctx, const char* name, size_t bytes) {
     b.bytes = 0;
   }
   size_t want = (bytes + 255) & ~size_t(255);
+  ctx->ws_gen++;                                  // addresses change: cached CUDA graphs are stale
   cudaError_t e = cudaMalloc(&b.p, want);
   if (e != cudaSuccess) {
     char buf[256];
@@ -173,6 +174,7 @@ int g3_ctx_destroy(g3_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   g3_dist_destroy(ctx);
+  g3_graph_drop(ctx);
   for (auto& kv : ctx->bufs)
     if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : ctx->pinned)
@@ -211,6 +213,8 @@ int g3_ctx_trim(g3_ctx* ctx) {
   for (auto& kv : ctx->bufs)
     if (kv.second.p) cudaFree(kv.second.p);
   ctx->bufs.clear();
+  ctx->ws_gen++;
+  g3_graph_drop(ctx);
   for (auto& kv : ctx->pinned)
     if (kv.second.p) cudaFreeHost(kv.second.p);
   ctx->pinned.clear();
@@ -256,6 +260,7 @@ int g3_set_data(g3_ctx* ctx, const double* X, int N, int D) {
   if (!X || N <= 0 || D <= 0 || D > G3_MAX_DIM) return g3_fail_msg(ctx, "g3_set_data: bad arguments (1 <= D <= 16)");
   G3_CUDA(ctx, cudaSetDevice(ctx->device));
   G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->ws_gen++;
   if (ctx->dX) { cudaFree(ctx->dX); ctx->dX = nullptr; }
   G3_CUDA(ctx, cudaMalloc(&ctx->dX, sizeof(double) * (size_t)N * D));
   G3_CUDA(ctx, cudaMemcpyAsync(ctx->dX, X, sizeof(double) * (size_t)N * D, cudaMemcpyHostToDevice, ctx->stream));

@@ -74,11 +74,18 @@ struct g3_ctx {
   int force_left = 0;                  // set by g3_gp_run for batches of more than 8 items (their stream groups hold 8)
   int splitk = 1;                      // allow split-K for few-tile / deep-K GEMM launches (g3_set_splitk)
   struct g3_dist* dist = nullptr;      // multi-GPU state (dist.cu): NCCL communicator, block-cyclic panels
+  // CUDA-graph replay of the launch sequence of small batches (gp.cu: g3_gp_run)
+  int graphs_on = 1;
+  uint64_t ws_gen = 0;                 // bumped whenever a workspace or the resident X is (re)allocated: cached graphs hold addresses
+  void* graph_exec = nullptr;          // cudaGraphExec_t
+  std::string graph_key, graph_warm_key;
+  int64_t graph_launches = 0, graph_replays = 0;
   int gemm_mode = 0;                   // G3_GEMM_DMMA / G3_GEMM_OZAKI (g3_set_gemm_mode)
   int oz_min_k = 1024;                 // Ozaki updates only for contractions at least this deep (DMMA below)
   int64_t oz_launches = 0;             // int8 tensor-core update launches since creation
 };
 void g3_dist_destroy(g3_ctx* ctx);     // called by g3_ctx_destroy
+void g3_graph_drop(g3_ctx* ctx);       // forget the cached CUDA graph (gp.cu)
 
 enum { G3_PROF_GEMM = 0, G3_PROF_DIAG = 1, G3_PROF_GRAM = 2, G3_PROF_VJP = 3, G3_PROF_TRSV = 4, G3_PROF_OTHER = 5, G3_PROF_N = 6 };
 void g3_prof_begin(g3_ctx* ctx, int cls);

@@ -386,10 +386,94 @@ int g3_gp_upload(g3_ctx* ctx, const g3_kernel_desc* desc, int kind, const double
   return 0;
 }
 
+}  // extern "C"
+
+static int gp_run_body(g3_ctx* ctx);
+
+// The launch sequence of one evaluation of up to 8 matrices (one MCMC chain / a BFGS step: ~150 dependent launches on
+// three streams at N=2048) depends only on (kernel tree, kind, B, N, gradient or not, schedule switches, workspace
+// addresses).  The second call with the same key captures it into a CUDA graph (stream capture: the look-ahead and
+// pipelined-trtri streams fork from and join the context's stream through the events the schedule already uses);
+// later calls replay the graph - one cudaGraphLaunch instead of ~150 launches, event records and tensor-map encodes.
+static std::string gp_graph_key(const g3_ctx* ctx) {
+  const g3_gp_state& st = ctx->gp;
+  std::string k((const char*)&st.desc, sizeof st.desc);
+  long long v[] = {st.kind, st.B, st.want_grad, st.delta_stride, ctx->N, ctx->D, ctx->potrf_w, ctx->lookahead, ctx->splitk,
+                   ctx->trtri_pipeline, ctx->gemm_mode, ctx->oz_min_k, ctx->n_groups, (long long)ctx->ws_gen,
+                   (long long)(intptr_t)ctx->dX, (long long)(intptr_t)ctx->stream};
+  k.append((const char*)v, sizeof v);
+  k.append((const char*)&ctx->jitter_rel, sizeof(double));
+  return k;
+}
+
+void g3_graph_drop(g3_ctx* ctx) {
+  if (ctx->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)ctx->graph_exec);
+  ctx->graph_exec = nullptr;
+  ctx->graph_key.clear();
+  ctx->graph_warm_key.clear();
+}
+
+extern "C" {
+
+int64_t g3_graph_replays(g3_ctx* ctx) { return ctx->graph_replays; }
+
+int g3_set_graphs(g3_ctx* ctx, int on) {
+  ctx->graphs_on = on ? 1 : 0;
+  if (!on) g3_graph_drop(ctx);
+  return 0;
+}
+
 int g3_gp_run(g3_ctx* ctx) {
   G3_NVTX("g3_gp_run");
   if (!ctx || !ctx->gp.valid) return g3_fail_msg(ctx, "g3_gp_run: nothing uploaded");
   G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->graphs_on || ctx->gp.B > 8 || ctx->prof_on) return gp_run_body(ctx);
+  const std::string key = gp_graph_key(ctx);
+  if (ctx->graph_exec && key == ctx->graph_key) {               // replay
+    G3_CUDA(ctx, cudaGraphLaunch((cudaGraphExec_t)ctx->graph_exec, ctx->stream));
+    ctx->launches += ctx->graph_launches;
+    ctx->graph_replays++;
+    return 0;
+  }
+  if (key != ctx->graph_warm_key) {                             // first call with this key: plain run (allocations, attributes)
+    const int rc = gp_run_body(ctx);
+    ctx->graph_warm_key = rc ? std::string() : gp_graph_key(ctx);   // the run may have (re)allocated workspaces
+    return rc;
+  }
+  g3_graph_drop(ctx);                                           // second call: capture, instantiate, launch
+  const int64_t l0 = ctx->launches;
+  cudaStream_t s = ctx->stream;
+  G3_CUDA(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+  int rc = gp_run_body(ctx);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(s, &graph);
+  ctx->stream = s;
+  if (rc || e != cudaSuccess || !graph || gp_graph_key(ctx) != key) {   // could not capture (or buffers moved): run it plainly
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    ctx->launches = l0;
+    ctx->graph_warm_key.clear();
+    return rc ? rc : gp_run_body(ctx);
+  }
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess || !exec) {
+    cudaGetLastError();
+    ctx->launches = l0;
+    ctx->graph_warm_key.clear();
+    return gp_run_body(ctx);
+  }
+  ctx->graph_exec = exec;
+  ctx->graph_key = key;
+  ctx->graph_launches = ctx->launches - l0;
+  G3_CUDA(ctx, cudaGraphLaunch(exec, s));
+  return 0;
+}
+
+}  // extern "C"
+
+static int gp_run_body(g3_ctx* ctx) {
   const g3_gp_state& st = ctx->gp;
   const int B = st.B, N = ctx->N, P = st.desc.n_theta;
   GpBufs w;
@@ -430,6 +514,8 @@ int g3_gp_run(g3_ctx* ctx) {
   ctx->force_left = 0;
   return rc;
 }
+
+extern "C" {
 
 int g3_gp_download(g3_ctx* ctx, double* beta, double* logdet, double* dtheta_or_NULL, double* ddelta_or_NULL,
                    int* status) {

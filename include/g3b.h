@@ -131,6 +131,11 @@ int g3_set_trtri_pipeline(g3_ctx* ctx, int on);
 enum { G3_GEMM_DMMA = 0, G3_GEMM_OZAKI = 1 };
 int g3_set_gemm_mode(g3_ctx* ctx, int mode, int min_k);
 int64_t g3_ozaki_launch_count(g3_ctx* ctx);
+/* CUDA-graph replay for evaluations of up to 8 matrices (one chain / one BFGS step): the second g3_gp_run with the same
+ * (kernel tree, kind, B, N, gradient, schedule switches, workspaces) captures its launch sequence, later ones replay it
+ * with one cudaGraphLaunch.  Default on; results are identical (same kernels, same order).  g3_graph_replays counts replays. */
+int g3_set_graphs(g3_ctx* ctx, int on);
+int64_t g3_graph_replays(g3_ctx* ctx);
 /* Number of batch groups g3_gp_run processes concurrently on separate streams (default 4, max 8;
  * 1 = a single stream, which is what the per-kernel timers of g3_prof_* need). */
 int g3_set_groups(g3_ctx* ctx, int n_groups);
