@@ -64,6 +64,9 @@ SIGNATURES = {
     "g3_debug_potrf_stress": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, C.c_int, _ip, _dp]),
     "g3_debug_gemm_stress": (C.c_int, [_ctxp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
     "g3_debug_fp64_peak": (C.c_int, [_ctxp, C.c_double, _dp, _dp, _dp]),
+    "g3_set_diag_variant": (C.c_int, [_ctxp, C.c_int]),
+    "g3_debug_diag_time": (C.c_int, [_ctxp, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_float),
+                                     C.POINTER(C.c_longlong), _dp]),
     "g3_set_stream": (C.c_int, [_ctxp, C.c_void_p]),
     "g3_dev_gram_block": (C.c_int, [_ctxp, C.POINTER(KernelDesc), _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                     C.c_void_p, C.c_longlong]),
@@ -315,6 +318,19 @@ class Context:
         self._ck(self._lib.g3_debug_fp64_peak(self._h, float(seconds), C.cast(C.byref(a), _dp), C.cast(C.byref(b), _dp),
                                               C.cast(C.byref(c), _dp) if copy else None), "g3_debug_fp64_peak")
         return {"dmma_tflops": float(a.value), "dfma_tflops": float(b.value), "copy_gbs": float(c.value) if copy else None}
+
+    def set_diag_variant(self, variant):
+        """2 = low-latency diagonal-tile kernel (default), 1 = the first kernel (A/B timing)."""
+        self._ck(self._lib.g3_set_diag_variant(self._h, int(variant)), "g3_set_diag_variant")
+
+    def debug_diag_time(self, variant=2, B=1, reps=20, cond_shift=0.05):
+        """Microseconds per launch of the 128x128 factor+inverse kernel alone, its phase clocks and host-checked errors."""
+        us = C.c_float()
+        stamps = (C.c_longlong * 64)()
+        err = np.zeros(4)
+        self._ck(self._lib.g3_debug_diag_time(self._h, int(variant), int(B), int(reps), float(cond_shift), C.byref(us), stamps,
+                                              _d(err)), "g3_debug_diag_time")
+        return float(us.value), np.array(list(stamps), dtype=np.int64), err
 
     def launch_count(self):
         return int(self._lib.g3_launch_count(self._h))

@@ -55,7 +55,8 @@ struct g3_ctx {
   g3_gp_state gp;
   void* encode_fn = nullptr;           // cuTensorMapEncodeTiled
   int sm_count = 148;
-  bool gemm_ready = false, diag_ready = false;
+  bool gemm_ready = false, diag_ready = false, diag2_ready = false;
+  int diag_variant = 2;                // 128x128 diagonal-tile kernel: 2 = diag.cu (low latency), 1 = the first kernel in potrf.cu
   // optional per-launch-class device timing (bench.py roofline): event pairs recorded around launches
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_events;     // pairs
@@ -151,6 +152,13 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
                      const int* bmap, int nb, int w_outer, double* U_pipe = nullptr);
 // Tall panel (rows x nb, ld = nb, rows/nb multiples of 128): factor the top nb x nb block and solve the rows below.
 int g3_potrf_panel(g3_ctx* ctx, double* P, int rows, int nb, double* Dinv, double* logdet, int* info);
+// diag.cu: factor + invert the diagonal tile j of B matrices (one CTA each); stamps (optional) receives clock64 phase marks of CTA 0
+int g3_diag2_launch(g3_ctx* ctx, double* A, int Np, long long strideA, int j, double* Dinv, int T, double* logdet, int* info,
+                    const int* bmap, int B, long long* stamps, int dbg = 0);
+// around every set of diagonal tiles g3_diag2_launch factors, on the same stream: prepare before the first tile (zeros above
+// the diagonal of the Dinv tiles), finish after the last GEMM update of the factorisation (zeros above the diagonal of A's tiles)
+int g3_diag2_prepare(g3_ctx* ctx, int j0, int nj, double* Dinv, int T, const int* bmap, int B);
+int g3_diag2_finish(g3_ctx* ctx, double* A, int Np, long long strideA, int j0, int nj, const int* bmap, int B);
 // D[x][y] -= sum_k P[row_off + x][k] P[row_off + y][k]   (D: rowsD x nb, ld = nb; P: rowsP x nb)
 int g3_syrk_panel(g3_ctx* ctx, const double* P, int rowsP, int nb, int row_off, double* D, int rowsD);
 int g3_trsv_panel(g3_ctx* ctx, const double* P, int rows, int nb, const double* Dinv, double* r, double* u, double* beta);

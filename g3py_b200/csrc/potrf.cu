@@ -369,6 +369,25 @@ trsv_bwd_step_kernel(const double* __restrict__ L, const double* __restrict__ Di
 
 static constexpr int kDiagSmem = (TS * LDS_ + 7 * SB * LDT) * (int)sizeof(double);
 
+// Factor + invert the diagonal tile j of B matrices: the low-latency kernel of diag.cu unless the first one is asked for.
+static int g3_diag_launch(g3_ctx* ctx, double* A, int Np, long long strideA, int j, double* Dinv, int T, double* logdet,
+                          int* info, const int* bmap, int B) {
+  g3_prof_begin(ctx, G3_PROF_DIAG);
+  if (ctx->diag_variant == 1) {
+    if (!ctx->diag_ready) {
+      G3_CUDA(ctx, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem));
+      ctx->diag_ready = true;
+    }
+    potrf_diag_kernel<<<B, 256, kDiagSmem, ctx->stream>>>(A, Np, strideA, j, Dinv, T, nullptr, logdet, info, bmap);
+  } else {
+    const int rc = g3_diag2_launch(ctx, A, Np, strideA, j, Dinv, T, logdet, info, bmap, B, nullptr);
+    if (rc) return rc;
+  }
+  g3_prof_end(ctx);
+  G3_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 static GemmArgs gemm_zero() {
   GemmArgs g;
   memset(&g, 0, sizeof g);
@@ -393,15 +412,24 @@ static int trtri_block(g3_ctx* ctx, const CUtensorMap& tmU, const CUtensorMap& t
                        int Np, int B, int io, int ie);
 static void launch_u_diag(g3_ctx* ctx, const double* Dinv, double* U, int Np, int T, int B, int j0, int nj);
 
+static int potrf_batched_impl(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, double* logdet, int* info,
+                              const int* bmap, int nb, int w_outer, double* U_pipe);
+
 int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, double* logdet, int* info,
                      const int* bmap, int nb, int w_outer, double* U_pipe) {
+  const int T = Np / TS, B = bmap ? nb : Btotal;
+  int rc;
+  if (ctx->diag_variant == 2 && (rc = g3_diag2_prepare(ctx, 0, T, Dinv, T, bmap, B))) return rc;
+  if ((rc = potrf_batched_impl(ctx, A, Np, Btotal, Dinv, logdet, info, bmap, nb, w_outer, U_pipe))) return rc;
+  if (ctx->diag_variant == 2 && (rc = g3_diag2_finish(ctx, A, Np, (long long)Np * Np, 0, T, bmap, B))) return rc;
+  return 0;
+}
+
+static int potrf_batched_impl(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, double* logdet, int* info,
+                              const int* bmap, int nb, int w_outer, double* U_pipe) {
   G3_NVTX("g3:potrf");
   ctx->trtri_done = 0;
   const int T = Np / TS;
-  if (!ctx->diag_ready) {
-    G3_CUDA(ctx, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem));
-    ctx->diag_ready = true;
-  }
   const int Blaunch = bmap ? nb : Btotal;
   if (w_outer < 1) {
     // auto: fully left-looking when the batch supplies the parallelism (a column update launches 2*B*(T-j) CTAs);
@@ -433,10 +461,7 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
         g.alpha = -1.0; g.beta = 1.0; g.bmap = bmap; g.upper = 2;
         if ((rc = g3_gemm_launch(ctx, tmA, tmB, g, B))) return rc;
       }
-      g3_prof_begin(ctx, G3_PROF_DIAG);
-      potrf_diag_kernel<<<B, 256, kDiagSmem, ctx->stream>>>(A, Np, strideA, j, Dinv, T, nullptr, logdet, info, bmap);
-      g3_prof_end(ctx);
-      G3_LAUNCH_CHECK(ctx);
+      if ((rc = g3_diag_launch(ctx, A, Np, strideA, j, Dinv, T, logdet, info, bmap, B))) return rc;
       if (j < T - 1) {  // L[i][j] = A[i][j] Linv_jj^T for the tiles below the diagonal
         GemmArgs g = gemm_zero();
         g.D = A; g.ldd = Np; g.strideD = strideA;
@@ -569,15 +594,12 @@ int g3_potrf_batched(g3_ctx* ctx, double* A, int Np, int Btotal, double* Dinv, d
 int g3_potrf_panel(g3_ctx* ctx, double* P, int rows, int nb, double* Dinv, double* logdet, int* info) {
   if (rows % TS || nb % TS || rows < nb) return g3_fail_msg(ctx, "potrf_panel: rows/nb must be multiples of 128, rows >= nb");
   const int Tr = rows / TS, w = nb / TS;
-  if (!ctx->diag_ready) {
-    G3_CUDA(ctx, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem));
-    ctx->diag_ready = true;
-  }
   CUtensorMap tmA, tmB, tmD;
   int rc;
   if ((rc = g3_make_tmap(ctx, &tmA, P, nb, rows, 1, nb, (uint64_t)rows * nb, G3_BM))) return rc;
   if ((rc = g3_make_tmap(ctx, &tmB, P, nb, rows, 1, nb, (uint64_t)rows * nb, G3_BN))) return rc;
   if ((rc = g3_make_tmap(ctx, &tmD, Dinv, TS, (uint64_t)w * TS, 1, TS, (uint64_t)w * TS * TS, G3_BN))) return rc;
+  if (ctx->diag_variant == 2 && (rc = g3_diag2_prepare(ctx, 0, w, Dinv, w, nullptr, 1))) return rc;
   for (int j = 0; j < w; ++j) {
     if (j > 0) {  // left-looking inside the panel
       GemmArgs g = gemm_zero();
@@ -590,10 +612,7 @@ int g3_potrf_panel(g3_ctx* ctx, double* P, int rows, int nb, double* Dinv, doubl
       g.alpha = -1.0; g.beta = 1.0; g.upper = 2;
       if ((rc = g3_gemm_launch(ctx, tmA, tmB, g, 1))) return rc;
     }
-    g3_prof_begin(ctx, G3_PROF_DIAG);
-    potrf_diag_kernel<<<1, 256, kDiagSmem, ctx->stream>>>(P, nb, 0, j, Dinv, w, nullptr, logdet, info, nullptr);
-    g3_prof_end(ctx);
-    G3_LAUNCH_CHECK(ctx);
+    if ((rc = g3_diag_launch(ctx, P, nb, 0, j, Dinv, w, logdet, info, nullptr, 1))) return rc;
     if (Tr - j - 1 > 0) {
       GemmArgs g = gemm_zero();
       g.D = P; g.ldd = nb; g.strideD = 0;
@@ -606,6 +625,7 @@ int g3_potrf_panel(g3_ctx* ctx, double* P, int rows, int nb, double* Dinv, doubl
       if ((rc = g3_gemm_launch(ctx, tmA, tmD, g, 1))) return rc;
     }
   }
+  if (ctx->diag_variant == 2 && (rc = g3_diag2_finish(ctx, P, nb, 0, 0, w, nullptr, 1))) return rc;
   return 0;
 }
 
@@ -891,5 +911,97 @@ int g3_trsv_bwd(g3_ctx* ctx, const double* L, const double* Dinv, double* s, dou
     G3_LAUNCH_CHECK(ctx);
   }
   g3_prof_end(ctx);
+  return 0;
+}
+
+int g3_set_diag_variant(g3_ctx* ctx, int variant) {
+  if (variant != 1 && variant != 2) return g3_fail_msg(ctx, "g3_set_diag_variant: 1 or 2");
+  if (ctx->diag_variant != variant) g3_graph_drop(ctx);
+  ctx->diag_variant = variant;
+  return 0;
+}
+
+// Times the diagonal-tile kernel alone (reps back-to-back launches of B CTAs on fresh SPD tiles) and checks tile 0 on the
+// host: err[0] = max |L L^T - A| / max |A|, err[1] = max |Dinv L - I|, err[2] = |logdet - host logdet|, err[3] = info.
+int g3_debug_diag_time(g3_ctx* ctx, int variant, int B, int reps, double cond_shift, float* us_per_launch, long long* stamps32,
+                       double* err4) {
+  G3_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (B < 1 || reps < 1) return g3_fail_msg(ctx, "diag_time: B, reps >= 1");
+  const size_t tile = (size_t)TS * TS;
+  std::vector<double> M(tile), Ah(tile);
+  unsigned long long z = 0x1234567ull;
+  for (size_t i = 0; i < tile; ++i) {
+    z = z * 6364136223846793005ull + 1442695040888963407ull;
+    M[i] = (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+  }
+  for (int r = 0; r < TS; ++r)
+    for (int c = 0; c < TS; ++c) {
+      double acc = 0.0;
+      for (int k = 0; k < TS; ++k) acc += M[r * TS + k] * M[c * TS + k];
+      Ah[r * TS + c] = acc / TS + (r == c ? fabs(cond_shift) : 0.0);
+    }
+  double* dA0 = (double*)g3_ws(ctx, "dt_A0", sizeof(double) * tile);
+  double* dA = (double*)g3_ws(ctx, "dt_A", sizeof(double) * tile * B * reps);
+  double* dD = (double*)g3_ws(ctx, "dt_D", sizeof(double) * tile * B * reps);
+  double* dld = (double*)g3_ws(ctx, "dt_ld", sizeof(double) * B * reps);
+  int* dinfo = (int*)g3_ws(ctx, "dt_info", sizeof(int) * B * reps);
+  long long* dst = (long long*)g3_ws(ctx, "dt_stamps", sizeof(long long) * 64);
+  if (!dA0 || !dA || !dD || !dld || !dinfo || !dst) return -2;
+  G3_CUDA(ctx, cudaMemcpyAsync(dA0, Ah.data(), sizeof(double) * tile, cudaMemcpyHostToDevice, ctx->stream));
+  for (size_t q = 0; q < (size_t)B * reps; ++q)
+    G3_CUDA(ctx, cudaMemcpyAsync(dA + q * tile, dA0, sizeof(double) * tile, cudaMemcpyDeviceToDevice, ctx->stream));
+  G3_CUDA(ctx, cudaMemsetAsync(dld, 0, sizeof(double) * B * reps, ctx->stream));
+  G3_CUDA(ctx, cudaMemsetAsync(dinfo, 0, sizeof(int) * B * reps, ctx->stream));
+  G3_CUDA(ctx, cudaMemsetAsync(dst, 0, sizeof(long long) * 64, ctx->stream));
+  const int keep = ctx->diag_variant;
+  ctx->diag_variant = variant;
+  int rc = 0;
+  if (variant == 2) rc = g3_diag2_prepare(ctx, 0, 1, dD, 1, nullptr, B * reps);
+  // warm-up launch on the last repetition's tiles (re-copied afterwards)
+  if (!rc) rc = g3_diag_launch(ctx, dA + (size_t)(reps - 1) * B * tile, TS, (long long)tile, 0, dD, 1, dld, dinfo, nullptr, B);
+  for (int q = 0; q < B && !rc; ++q)
+    cudaMemcpyAsync(dA + ((size_t)(reps - 1) * B + q) * tile, dA0, sizeof(double) * tile, cudaMemcpyDeviceToDevice, ctx->stream);
+  cudaMemsetAsync(dld, 0, sizeof(double) * B * reps, ctx->stream);
+  if (!rc) rc = g3_timer_begin(ctx);
+  for (int it = 0; it < reps && !rc; ++it)
+    rc = g3_diag_launch(ctx, dA + (size_t)it * B * tile, TS, (long long)tile, 0, dD + (size_t)it * B * tile, 1, dld + (size_t)it * B,
+                        dinfo + (size_t)it * B, nullptr, B);
+  float ms = 0.f;
+  if (!rc) rc = g3_timer_end(ctx, &ms);
+  if (!rc && variant == 2 && stamps32) {  // one more launch with the phase clocks on
+    cudaMemcpyAsync(dA, dA0, sizeof(double) * tile, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaMemsetAsync(dld, 0, sizeof(double), ctx->stream);
+    rc = g3_diag2_launch(ctx, dA, TS, (long long)tile, 0, dD, 1, dld, dinfo, nullptr, 1, dst, cond_shift < 0 ? 1 : 0);
+  }
+  if (!rc && variant == 2) rc = g3_diag2_finish(ctx, dA, TS, (long long)tile, 0, 1, nullptr, 1);
+  ctx->diag_variant = keep;
+  if (rc) return rc;
+  std::vector<double> Lh(tile), Xh(tile);
+  double ld = 0.0;
+  int inf = 0;
+  G3_CUDA(ctx, cudaMemcpyAsync(Lh.data(), dA, sizeof(double) * tile, cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaMemcpyAsync(Xh.data(), dD, sizeof(double) * tile, cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaMemcpyAsync(&ld, dld, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaMemcpyAsync(&inf, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (stamps32) G3_CUDA(ctx, cudaMemcpyAsync(stamps32, dst, sizeof(long long) * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  G3_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (us_per_launch) *us_per_launch = ms * 1000.f / reps;
+  if (err4) {
+    double amax = 0.0, e0 = 0.0, e1 = 0.0, hld = 0.0;
+    for (size_t i = 0; i < tile; ++i) amax = fmax(amax, fabs(Ah[i]));
+    for (int r = 0; r < TS; ++r)
+      for (int c = 0; c < TS; ++c) {
+        double acc = 0.0, acc2 = 0.0;
+        for (int k = 0; k < TS; ++k) {
+          acc += Lh[r * TS + k] * Lh[c * TS + k];
+          acc2 += Xh[r * TS + k] * Lh[k * TS + c];
+        }
+        const double d0 = fabs(acc - Ah[r * TS + c]) / amax, d1 = fabs(acc2 - (r == c ? 1.0 : 0.0));
+        e0 = (d0 > e0 || d0 != d0) ? d0 : e0;
+        e1 = (d1 > e1 || d1 != d1) ? d1 : e1;
+      }
+    for (int k = 0; k < TS; ++k) hld += log(Lh[k * TS + k]);
+    err4[0] = e0; err4[1] = e1; err4[2] = fabs(hld - ld); err4[3] = (double)inf;
+  }
   return 0;
 }

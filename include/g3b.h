@@ -161,6 +161,17 @@ int g3_debug_gemm_stress(g3_ctx* ctx, int rows, int B, int launches, int inplace
  * `seconds` with CUDA events on the context's stream.  Any output pointer may be NULL (that leg is skipped).
  * Replaces nothing in the reference. */
 int g3_debug_fp64_peak(g3_ctx* ctx, double seconds, double* dmma_tflops, double* dfma_tflops, double* copy_gbs);
+/* Which kernel factors and inverts the 128x128 diagonal tiles of the blocked Cholesky (the serial head of every tile
+ * column; replaces the unblocked part of dpotrf behind CholeskyRobust.perform, libs/tensors.py:198):
+ * 2 (default) = the low-latency kernel of csrc/diag.cu, 1 = the first, bulk-synchronous one (kept for A/B timing). */
+int g3_set_diag_variant(g3_ctx* ctx, int variant);
+/* Times that kernel alone: `reps` back-to-back launches of B CTAs on copies of one synthetic SPD tile
+ * (M M^T / 128 + cond_shift I), microseconds per launch from CUDA events; checks tile 0 on the host:
+ * err4 = {max |L L^T - A| / max |A|, max |Dinv L - I|, |logdet - host|, info}.  For variant 2, stamps32 (64 entries) receives
+ * the clock64 marks of the kernel's phases (CTA 0); a negative cond_shift (|.| is used) runs that extra launch with nothing in
+ * the shadow of the serial factorisation (timing experiment; its outputs are incomplete).  Replaces nothing in the reference. */
+int g3_debug_diag_time(g3_ctx* ctx, int variant, int B, int reps, double cond_shift, float* us_per_launch,
+                       long long* stamps32, double* err4);
 /* Number of kernels launched by this context since creation (bench.py "gpu_launches"). */
 int64_t g3_launch_count(g3_ctx* ctx);
 
