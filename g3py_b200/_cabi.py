@@ -17,9 +17,10 @@ G3_MAX_DIM = 16
 # leaf / node opcodes (include/g3b.h)
 K_SE, K_OU, K_MAT32, K_MAT52, K_RQ, K_SIN, K_NOISE, K_WN = 1, 2, 3, 4, 5, 6, 7, 8
 K_COS, K_SINC, K_SM = 9, 10, 11
-K_DOT, K_BW, K_VAR = 12, 13, 14
+K_DOT, K_BW, K_VAR, K_EQ = 12, 13, 14, 15
 K_SUM, K_PROD, K_SCALE, K_SHIFT, K_MAX = 16, 17, 18, 19, 20
 KF_PROCESS_NOISE = 1
+KF_NN, KF_EQ2 = 0x10000, 0x20000
 
 ST_NONFINITE_INPUT, ST_DIAG_SHIFT, ST_JITTER, ST_POTRF_FAILED, ST_NONFINITE_RESULT = 1, 2, 4, 8, 16
 KIND_GAUSS, KIND_STUDENT = 0, 1

@@ -123,7 +123,7 @@ struct AxpyTail<N, N> {
 template <int K, int H>
 struct FStep {
   static __device__ __forceinline__ void run(double (&a)[16], uint32_t vtb, uint32_t vtl, uint32_t ttl, uint32_t dnb, uint32_t dnl,
-                                             int il, double d, double y, double& dmine, int& bad, uint32_t zero) {
+                                             int il, double d, double y, double& dmine, int& bad) {
     constexpr uint32_t PAR = (K & 1) * 256, NPAR = ((K + 1) & 1) * 256;
     // the two mailbox values the next pivot needs come first: everything shared below is ordered behind them
     double w1 = 0.0, ad = 0.0;
@@ -145,21 +145,18 @@ struct FStep {
       dn = fma(-(w1 * w1), r, ad);
       yn = rcp_seed(dn);
       AxpyTail<K + 1, 16>::run(a, t, vtb + K * VS * 8);
-      // `zero` is 0 at run time but opaque to the compiler: the publish address "depends" on the seed, so the MUFU is issued
-      // the moment the pivot is known instead of being sunk to its first use behind the warp barrier
-      const uint32_t tie = (uint32_t)__double2hiint(yn) & zero;
-      stso<(K + 1) * VS * 8>(vtl + tie, a[(K + 1) & 15]);
+      stso<(K + 1) * VS * 8>(vtl, a[(K + 1) & 15]);
       stso<NPAR>(dnl, a[(K + 2) & 15]);
     }
     if constexpr (H == 0) stso<K * VS * 8>(ttl, -t);
     __syncwarp();
-    FStep<K + 1, H>::run(a, vtb, vtl, ttl, dnb, dnl, il, dn, yn, dmine, bad, zero);
+    FStep<K + 1, H>::run(a, vtb, vtl, ttl, dnb, dnl, il, dn, yn, dmine, bad);
   }
 };
 template <int H>
 struct FStep<16, H> {
   static __device__ __forceinline__ void run(double (&)[16], uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, int, double, double,
-                                             double&, int&, uint32_t) {}
+                                             double&, int&) {}
 };
 
 template <int M, int N>
@@ -178,7 +175,7 @@ struct LoadRow<N, N> {
 // Warp 0: Cholesky of the 32x32 diagonal sub-block at offset o, left as its raw pivot columns VT[k][m] = L[m][k] sqrt(d_k) with
 // 1/sqrt(d_k) in invd[o + k] and 1/d_k in RV[k] (the scaled block is written into S by other warps afterwards).
 // Returns the first failed pivot (or -1).  sb = shared byte address of S[0][0].
-__device__ __forceinline__ int factor32(uint32_t sb, int o, int lane, long long* st, uint32_t zero) {
+__device__ __forceinline__ int factor32(uint32_t sb, int o, int lane, long long* st) {
   const uint32_t vt = sb + OFF_VT * B8, tt = sb + OFF_TT * B8, dnb = sb + OFF_DN * B8;
   const uint32_t invd = sb + (OFF_INVD + o) * B8;
   const uint32_t row = sb + ((o + lane) * LD + o) * B8;
@@ -192,7 +189,7 @@ __device__ __forceinline__ int factor32(uint32_t sb, int o, int lane, long long*
   __syncwarp();
   {
     const double d = ldso<0>(vt);
-    FStep<0, 0>::run(a, vt, vt + lane * B8, tt + lane * B8, dnb, dnb + lane * B8, lane, d, rcp_seed(d), dA, bad, zero);
+    FStep<0, 0>::run(a, vt, vt + lane * B8, tt + lane * B8, dnb, dnb + lane * B8, lane, d, rcp_seed(d), dA, bad);
   }
   if (st) st[0] = clock64();
   // ---- trailing 16x16 (rows / columns 16..31 of the sub-block) += TT^T VT on the tensor pipe: tiles (0,0), (1,0), (1,1) ----
@@ -228,7 +225,7 @@ __device__ __forceinline__ int factor32(uint32_t sb, int o, int lane, long long*
     stso<0>(dnb + il * B8, c[1]);
     __syncwarp();
     const double d = ldso<0>(vtb2);
-    FStep<0, 1>::run(c, vtb2, vtl2, 0u, dnb, dnb + il * B8, il, d, rcp_seed(d), dC, bad, zero);
+    FStep<0, 1>::run(c, vtb2, vtl2, 0u, dnb, dnb + il * B8, il, d, rcp_seed(d), dC, bad);
   }
   if (st) st[2] = clock64();
   // ---- 1/sqrt and 1/ of the pivots, one per lane ----
@@ -247,17 +244,20 @@ __device__ __forceinline__ int factor32(uint32_t sb, int o, int lane, long long*
 // rows scaled by 1/sqrt(d), i.e. what the raw columns of L21 must be multiplied with) to TT.
 template <int K>
 struct HalfSolve {
-  static __device__ __forceinline__ void run(double (&b)[16], uint32_t vth, uint32_t rvh, uint32_t ivh, uint32_t zl, uint32_t xl) {
-    const double y = b[K] * ldso<K * 8>(rvh);
-    stso<K * 8>(xl, b[K] * ldso<K * 8>(ivh));
-    stso<K * VS * 8>(zl, y);
+  // results stay in registers (xs, ys) until the end: a shared store inside the loop would order the next step's loads behind it
+  static __device__ __forceinline__ void run(double (&b)[16], double (&xs)[16], double (&ys)[16], uint32_t vth, const double (&rv)[16],
+                                             const double (&iv)[16]) {
+    const double y = b[K] * rv[K];
+    ys[K] = y;
+    xs[K] = b[K] * iv[K];
     AxpyTail<K + 1, 16>::run(b, y, vth + K * VS * 8);
-    HalfSolve<K + 1>::run(b, vth, rvh, ivh, zl, xl);
+    HalfSolve<K + 1>::run(b, xs, ys, vth, rv, iv);
   }
 };
 template <>
 struct HalfSolve<16> {
-  static __device__ __forceinline__ void run(double (&)[16], uint32_t, uint32_t, uint32_t, uint32_t, uint32_t) {}
+  static __device__ __forceinline__ void run(double (&)[16], double (&)[16], double (&)[16], uint32_t, const double (&)[16],
+                                             const double (&)[16]) {}
 };
 // Level 2 on the tensor pipe: T = L21 X11 = V21 Z11 (TQ), then X21 = -X22 T.
 __device__ __forceinline__ void inverse32(uint32_t sb, int kb, int o, int lane) {
@@ -265,11 +265,21 @@ __device__ __forceinline__ void inverse32(uint32_t sb, int kb, int o, int lane) 
   const uint32_t xd = sb + (OFF_XDT + kb * 32 * XS) * B8;
   {
     const int h = lane >> 4, c = lane & 15;
-    double bcol[16];
+    double bcol[16], xs[16], ys[16], rv[16], iv[16];
+    const uint32_t rvp = sb + (OFF_RV + 16 * h) * B8, ivp = sb + (OFF_INVD + o + 16 * h) * B8;
 #pragma unroll
-    for (int m = 0; m < 16; ++m) bcol[m] = (m == c) ? 1.0 : 0.0;
-    HalfSolve<0>::run(bcol, vt + (16 * h * VS + 16 * h) * B8, sb + (OFF_RV + 16 * h) * B8, sb + (OFF_INVD + o + 16 * h) * B8,
-                      zs + lane * B8, xd + ((16 * h + c) * XS + 16 * h) * B8);
+    for (int m = 0; m < 16; ++m) {
+      bcol[m] = (m == c) ? 1.0 : 0.0;
+      rv[m] = lds(rvp + m * B8);
+      iv[m] = lds(ivp + m * B8);
+    }
+    HalfSolve<0>::run(bcol, xs, ys, vt + (16 * h * VS + 16 * h) * B8, rv, iv);
+    const uint32_t zl = zs + lane * B8, xl = xd + ((16 * h + c) * XS + 16 * h) * B8;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      sts(xl + m * B8, xs[m]);
+      sts(zl + m * VS * B8, ys[m]);
+    }
   }
   __syncwarp();
   const int fr = lane >> 2, fk = lane & 3;
@@ -535,7 +545,7 @@ potrf_diag2_kernel(double* __restrict__ A, int Np, long long strideA, int j, dou
     G3_STAMP();
     // ---- F: warp 0 factors the diagonal sub-block; the others load / store / work on the inverse ----
     if (warp == 0) {
-      const int bad = factor32(sb, o, lane, (stamps && tid == 0 && blockIdx.x == 0) ? stamps + 32 + kb * 4 : nullptr, blockDim.x >> 10);
+      const int bad = factor32(sb, o, lane, (stamps && tid == 0 && blockIdx.x == 0) ? stamps + 32 + kb * 4 : nullptr);
       if (lane == 0 && bad >= 0 && first_bad < 0) first_bad = o + bad;
       G3_STAMP();
       --nstamp;

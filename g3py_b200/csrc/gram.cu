@@ -78,6 +78,22 @@ __device__ __forceinline__ double ipow(double m, int p) {
   return r;
 }
 
+// the NN flavour of the dot leaf: value and derivative with respect to the metric m of arcsin(2m / (1 + 2m)^2)
+__device__ __forceinline__ void nn_value(double m, double& kk, double& dk) {
+  const double q = 1.0 + 2.0 * m, u = 2.0 * m / (q * q);
+  kk = asin(u);
+  dk = (2.0 * (1.0 - 2.0 * m) / (q * q * q)) * rsqrt(1.0 - u * u);
+}
+__device__ __forceinline__ double eq_second(const g3_knode& nd) {
+  return (nd.flags & G3_KF_EQ2) ? __hiloint2double(nd.p1_idx, nd.p0_idx) : nd.value;
+}
+// DeltaEq / DeltaEq2 term of one coordinate pair
+__device__ __forceinline__ double eq_term(const g3_knode& nd, double e2, double xi, double xj) {
+  double t = (xi == nd.value && xj == e2) ? 1.0 : 0.0;
+  if ((nd.flags & G3_KF_EQ2) && xi == e2 && xj == nd.value) t += 1.0;
+  return t;
+}
+
 // value of one leaf on the diagonal of cov(x, x) (same = 1, i == j) for the row `x`
 __device__ __forceinline__ double leaf_diag(const g3_knode& nd, const double* __restrict__ th,
                                             const double* __restrict__ x, int skip_pn) {
@@ -90,7 +106,18 @@ __device__ __forceinline__ double leaf_diag(const g3_knode& nd, const double* __
     case G3_K_DOT: {
       double m = nd.p1_idx >= 0 ? th[nd.p1_idx] : 0.0;
       for (int k = nd.dim0; k < nd.dim1; ++k) { const double r = th[nd.p0_idx + k - nd.dim0]; m += r * r * x[k] * x[k]; }
+      if (nd.flags & G3_KF_NN) {
+        double kk, dk;
+        nn_value(m, kk, dk);
+        return var * kk;
+      }
       return var * ipow(m, G3_KF_POWER(nd.flags));
+    }
+    case G3_K_EQ: {
+      const double e2 = eq_second(nd);
+      double m = 0.0;
+      for (int k = nd.dim0; k < nd.dim1; ++k) m += eq_term(nd, e2, x[k], x[k]);
+      return m;
     }
     case G3_K_BW: {
       double m = 1.0;
@@ -192,6 +219,15 @@ __device__ __forceinline__ void leaf_value4(const g3_knode& nd, const double* __
         for (int e = 0; e < 4; ++e) pr[e] *= fmin(xi, x2[cc[e]]);
       }
       break;
+    case G3_K_EQ: {
+      const double e2 = eq_second(nd);
+      for (int k = 0; k < nd_; ++k) {
+        const double xi = x1row[nd.dim0 + k];
+        const double* x2 = x2s + (nd.dim0 + k) * TS;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) d[e] += eq_term(nd, e2, xi, x2[cc[e]]);
+      }
+    } break;
     default:
       break;
   }
@@ -232,7 +268,16 @@ __device__ __forceinline__ void leaf_value4(const g3_knode& nd, const double* __
         v = same ? (same_diag[e] ? var : 0.0) : var * d[e];
         break;
       case G3_K_DOT:
-        v = var * ipow((nd.p1_idx >= 0 ? th[nd.p1_idx] : 0.0) + d[e], G3_KF_POWER(nd.flags));
+        if (nd.flags & G3_KF_NN) {
+          double kk, dk;
+          nn_value((nd.p1_idx >= 0 ? th[nd.p1_idx] : 0.0) + d[e], kk, dk);
+          v = var * kk;
+        } else {
+          v = var * ipow((nd.p1_idx >= 0 ? th[nd.p1_idx] : 0.0) + d[e], G3_KF_POWER(nd.flags));
+        }
+        break;
+      case G3_K_EQ:
+        v = d[e];
         break;
       case G3_K_BW:
         v = var * pr[e];
@@ -425,10 +470,18 @@ gram_vjp_kernel(const __grid_constant__ g3_kernel_desc desc, const VjpArgs a, in
     for (int n = 0; n < desc.n_nodes; ++n) {
       const g3_knode& nd = desc.nodes[n];
       if (nd.op < G3_K_SUM) {
-        const double var = nd.var_idx >= 0 ? th[nd.var_idx] : nd.value;
+        const double var = nd.op == G3_K_EQ ? 1.0 : (nd.var_idx >= 0 ? th[nd.var_idx] : nd.value);
         const int nd_ = nd.dim1 - nd.dim0;
         double d[4] = {0.0, 0.0, 0.0, 0.0};
-        if (nd.op == G3_K_SE || nd.op == G3_K_MAT32 || nd.op == G3_K_MAT52 || nd.op == G3_K_RQ) {
+        if (nd.op == G3_K_EQ) {
+          const double e2 = eq_second(nd);
+          for (int k = 0; k < nd_; ++k) {
+            const double xi = x1row[nd.dim0 + k];
+            const double* x2 = x2s + (nd.dim0 + k) * TS;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) d[e] += eq_term(nd, e2, xi, x2[cc[e]]);
+          }
+        } else if (nd.op == G3_K_SE || nd.op == G3_K_MAT32 || nd.op == G3_K_MAT52 || nd.op == G3_K_RQ) {
           for (int k = 0; k < nd_; ++k) {
             const double r = th[nd.p0_idx + k];
             const double hr2 = 0.5 * r * r, xi = x1row[nd.dim0 + k];
@@ -507,7 +560,9 @@ gram_vjp_kernel(const __grid_constant__ g3_kernel_desc desc, const VjpArgs a, in
             case G3_K_WN: kk = a.same ? (sd[e] ? 1.0 : 0.0) : d[e]; break;
             case G3_K_DOT: { const int pw = G3_KF_POWER(nd.flags);
                              const double m = (nd.p1_idx >= 0 ? th[nd.p1_idx] : 0.0) + d[e];
+                             if (nd.flags & G3_KF_NN) { nn_value(m, kk, dk); break; }
                              const double m1 = ipow(m, pw - 1); kk = m1 * m; dk = (double)pw * m1; } break;   // dk = d kk / d m
+            case G3_K_EQ: kk = d[e]; break;
             case G3_K_BW: kk = pr[e]; break;
             case G3_K_VAR: kk = 1.0; break;
             default: kk = 0.0;
@@ -701,14 +756,14 @@ int g3_check_desc(g3_ctx* ctx, const g3_kernel_desc& d, int D) {
   for (int n = 0; n < d.n_nodes; ++n) {
     const g3_knode& nd = d.nodes[n];
     if (nd.op < G3_K_SUM) {
-      if (nd.op < G3_K_SE || nd.op > G3_K_VAR) return g3_fail_msg(ctx, "kernel desc: unknown leaf op");
+      if (nd.op < G3_K_SE || nd.op > G3_K_EQ) return g3_fail_msg(ctx, "kernel desc: unknown leaf op");
       if (nd.op != G3_K_NOISE && (nd.dim0 < 0 || nd.dim1 > D || nd.dim1 <= nd.dim0))
         return g3_fail_msg(ctx, "kernel desc: leaf dims outside [0, D)");
       const int w = nd.dim1 - nd.dim0;
       if (nd.var_idx >= d.n_theta) return g3_fail_msg(ctx, "kernel desc: var_idx outside theta");
-      if (nd.op == 15) return g3_fail_msg(ctx, "kernel desc: unknown leaf op");
+      if (nd.op == G3_K_EQ && nd.var_idx >= 0) return g3_fail_msg(ctx, "kernel desc: the equality leaf has no variance hyper");
       const bool has_rate = nd.op != G3_K_NOISE && nd.op != G3_K_WN && nd.op != G3_K_COS && nd.op != G3_K_SINC &&
-                            nd.op != G3_K_BW && nd.op != G3_K_VAR;
+                            nd.op != G3_K_BW && nd.op != G3_K_VAR && nd.op != G3_K_EQ;
       if (has_rate && (nd.p0_idx < 0 || nd.p0_idx + w > d.n_theta)) return g3_fail_msg(ctx, "kernel desc: rate index outside theta");
       if (nd.op == G3_K_RQ && (nd.p1_idx < 0 || nd.p1_idx >= d.n_theta)) return g3_fail_msg(ctx, "kernel desc: alpha index outside theta");
       const bool has_freq = nd.op == G3_K_SIN || nd.op == G3_K_COS || nd.op == G3_K_SINC || nd.op == G3_K_SM;

@@ -11,7 +11,16 @@ from .. import _cabi as cabi
 
 __all__ = ["Kernel", "KernelStationary", "KernelSum", "KernelProd", "KernelScale", "KernelShift", "KernelNoise", "WN",
            "SE", "OU", "MAT32", "MAT52", "RQ", "SIN", "COS", "SINC", "SM", "KernelPeriodic", "DescBuilder",
-           "KernelDot", "LIN", "POL", "BW", "VAR", "KernelMax"]
+           "KernelDot", "LIN", "POL", "BW", "VAR", "KernelMax", "NN", "NIL", "KernelEquals", "KernelEquals2", "kernel_leaves"]
+
+
+def kernel_leaves(k):
+    """Leaves of a kernel expression, left to right."""
+    if hasattr(k, "k1"):
+        return kernel_leaves(k.k1) + kernel_leaves(k.k2)
+    if hasattr(k, "k") and isinstance(getattr(k, "k"), Kernel):
+        return kernel_leaves(k.k)
+    return [k]
 
 
 class DescBuilder:
@@ -401,6 +410,7 @@ class KernelDot(KernelStationary):
     OPCODE = cabi.K_DOT
     BIAS = False
     POWER = 1
+    FLAGS = 0
 
     def __init__(self, x=None, name=None, var=None, rate=None, bias=None):
         super().__init__(x, name, var, rate)
@@ -430,7 +440,7 @@ class KernelDot(KernelStationary):
         d0, d1, nd, vi, val = self._common(b)
         p0 = b.slot(self.rate, nd)
         p1 = b.slot(self.bias, 1) if self.BIAS else -1
-        return b.node(self.OPCODE, d0, d1, vi, p0, p1, (int(self.POWER) & 0xff) << 8, val)
+        return b.node(self.OPCODE, d0, d1, vi, p0, p1, ((int(self.POWER) & 0xff) << 8) | self.FLAGS, val)
 
 
 class LIN(KernelDot):                # kernels.py:319-321: var fixed to 1
@@ -450,6 +460,15 @@ class POL(KernelDot):                # kernels.py:324-336: var * (bias + sum_k r
         self.p = self.POWER = int(p)
 
 
+class NN(KernelDot):                 # kernels.py:339-351: var * arcsin(2m / (1 + 2m)^2), m = bias + sum_k rate_k^2 x_ik x_jk
+    """The neural-network kernel as its single-argument `cov(x1)` is written in the reference: elementwise in the Gram
+    entry m_ij (not normalised by m_ii, m_jj).  The two-argument form multiplies an N1xN1 by an N2xN2 matrix
+    (kernels.py:351) and only broadcasts when N1 == N2, so the posterior methods raise here as they do there."""
+    BIAS = True
+    FLAGS = cabi.KF_NN
+    TRAINING_GRAM_ONLY = True
+
+
 class BW(Kernel):                    # kernels.py:291-293 with the Minimum metric (metrics.py:49-51): Brownian motion
     OPCODE = cabi.K_BW
 
@@ -464,6 +483,37 @@ class BW(Kernel):                    # kernels.py:291-293 with the Minimum metri
 
 class VAR(BW):                       # kernels.py:296-306: constant kernel var * ones
     OPCODE = cabi.K_VAR
+
+
+class NIL(Kernel):                   # kernels.py:309-320: zeros, no hypers (var=1 is never used)
+    def __init__(self, x=None, name=None, var=1):
+        super().__init__(x, name, 1)
+
+    def compile(self, b, process_noise=False):
+        d0, d1 = self.dim_range(b.D)
+        return b.node(cabi.K_VAR, d0, d1, -1, -1, -1, 0, 0.0)
+
+
+class KernelEquals(Kernel):          # kernels.py:262-274 over DeltaEq (metrics.py:38-43): sum_k [x_ik == eq][x_jk == eq]
+    def __init__(self, x=None, name=None, eq=0):
+        super().__init__(x, name, 1)
+        self.eq = float(eq)
+
+    def compile(self, b, process_noise=False):
+        d0, d1 = self.dim_range(b.D)
+        return b.node(cabi.K_EQ, d0, d1, -1, -1, -1, 0, self.eq)
+
+
+class KernelEquals2(Kernel):         # kernels.py:277-288 over DeltaEq2 (metrics.py:46-51)
+    def __init__(self, x=None, name=None, eq1=0, eq2=0):
+        super().__init__(x, name, 1)
+        self.eq1, self.eq2 = float(eq1), float(eq2)
+
+    def compile(self, b, process_noise=False):
+        import struct
+        d0, d1 = self.dim_range(b.D)
+        lo, hi = struct.unpack("<ii", struct.pack("<d", self.eq2))       # the second constant travels in the two index words
+        return b.node(cabi.K_EQ, d0, d1, -1, lo, hi, cabi.KF_EQ2, self.eq1)
 
 
 class KernelNoise(Kernel):           # kernels.py:360-371

@@ -651,6 +651,12 @@ class EllipticalProcess(StochasticProcess):
                     K = K + (self.consts.jitter - m) * np.eye(len(K))        # tt_to_cov, elliptical.py:70
             out.update(location=loc_s, kernel_diag=np.maximum(np.diag(K), 0.0), kernel=K if cov else None)
             return out, nat, p
+        from .hypers.kernels import kernel_leaves
+        for leaf in kernel_leaves(self.f_kernel):
+            if getattr(leaf, "TRAINING_GRAM_ONLY", False):
+                raise NotImplementedError("%s.cov(x1, x2) does not exist in the reference either: its two-argument form multiplies an "
+                                          "N1xN1 by an N2xN2 matrix (hypers/kernels.py:351); only the training Gram (logp, gradient, "
+                                          "prior kernel) is defined" % type(leaf).__name__)
         with np.errstate(all="ignore"):
             delta = tt_to_num(self.f_mapping.inv(y, p)) - self.f_location(X, p)   # elliptical.py:63,83
         r = self.ctx.gp_posterior(self.desc, space, delta, thk, noise=noise, cov=cov)

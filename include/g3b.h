@@ -50,10 +50,18 @@ enum {
                      ARD_DotBias (bias = theta[p1_idx]); integer p >= 1 in flags bits 8..15 (0 means 1)
                      kernels.py:82-96,319-336, metrics.py:110-137 */
   G3_K_BW = 13,   /* var*prod_k min(x_ik, x_jk)  (Brownian)                  kernels.py:291-293, metrics.py:49-51 */
-  G3_K_VAR = 14,  /* var (constant kernel)                                   kernels.py:296-306 */
+  G3_K_VAR = 14,  /* var (constant kernel; NIL = var fixed to 0)              kernels.py:296-306, 309-320 */
+  G3_K_EQ = 15,   /* sum_k [x_ik == e1][x_jk == e2] (+ [x_ik == e2][x_jk == e1] with G3_KF_EQ2): KernelEquals / KernelEquals2 over the
+                   * DeltaEq / DeltaEq2 metrics.  e1 = `value`; e2 = e1, or with G3_KF_EQ2 the double whose low / high words are
+                   * p0_idx / p1_idx.  No variance, no hypers (var_idx = -1).      kernels.py:262-288, metrics.py:38-51 */
   G3_K_SUM = 16, G3_K_PROD = 17, G3_K_SCALE = 18, G3_K_SHIFT = 19,
   G3_K_MAX = 20   /* elementwise max(k1, k2); ties send the gradient to both (Theano's maximum)  kernels.py:247-257 */
 };
+/* flags of G3_K_DOT: bits 8..15 the integer power p; G3_KF_NN = the NN kernel var*arcsin(2m/(1+2m)^2) on the same
+ * metric m = bias + sum_k rate_k^2 x_ik x_jk, as its single-argument cov() is written (elementwise in m_ij; kernels.py:339-348).
+ * flag of G3_K_EQ: G3_KF_EQ2. */
+#define G3_KF_NN 0x10000
+#define G3_KF_EQ2 0x20000
 #define G3_KF_POWER(flags) ((((flags) >> 8) & 0xff) ? (((flags) >> 8) & 0xff) : 1)
 
 typedef struct {

@@ -187,6 +187,9 @@ class _Leaf(KernelNode):
         self.fixed_var = spec.get("var")                      # KernelProd second var = 1.0 (kernels.py:215-219)
         if self.kind in ("LIN", "POL") and "var" not in spec:
             self.fixed_var = 1.0                               # kernels.py:320,325: LIN / POL default var=1
+        if self.kind in ("NIL", "KernelEquals", "KernelEquals2"):
+            self.fixed_var = 1.0                               # kernels.py:264,275,312: var=1, and cov() never multiplies by it
+        self.eq = (float(spec.get("eq", spec.get("eq1", 0.0))), float(spec.get("eq2", spec.get("eq", 0.0))))
         hy = []
         if self.fixed_var is None:
             hy.append(_Hyper(self.name + "_var", 1, True))     # kernels.py:22-24
@@ -200,7 +203,7 @@ class _Leaf(KernelNode):
             hy.append(_Hyper(self.name + "_rate", self.nd, True))
         if k in ("COS", "SINC"):                               # kernels.py:463,476: rate=1.0 constant, freq only
             hy.append(_Hyper(self.name + "_freq", self.nd, True))
-        if k in ("KernelDot", "LIN", "POL"):                   # metrics.py:79-83 (ARD.rate), :126-128 (bias after rate)
+        if k in ("KernelDot", "LIN", "POL", "NN"):             # metrics.py:79-83 (ARD.rate), :126-128 (bias after rate)
             hy.append(_Hyper(self.name + "_rate", self.nd, True))
             if k != "KernelDot":
                 hy.append(_Hyper(self.name + "_bias", 1, True))
@@ -271,13 +274,27 @@ class _Leaf(KernelNode):
             return p["var"] * np.prod(np.minimum(a - b * 0, b - a * 0), axis=2)
         if k == "VAR":                                         # kernels.py:296-306
             return p["var"] * np.ones((n1, n2))
+        if k == "NIL":                                         # kernels.py:309-320: zeros
+            return np.zeros((n1, n2))
+        if k in ("KernelEquals", "KernelEquals2"):             # kernels.py:262-288; metrics.py:38-51 DeltaEq / DeltaEq2
+            a = x1[:, self.dims[0]:self.dims[1]][:, None, :]
+            b = x2[:, self.dims[0]:self.dims[1]][None, :, :]
+            e1, e2 = self.eq
+            if k == "KernelEquals":
+                return tt_to_num(((a == e1) * (b == e1)).sum(axis=2).astype(np.float64))
+            return tt_to_num(((a == e1) * (b == e2) + (a == e2) * (b == e1)).sum(axis=2).astype(np.float64))
+        if k == "NN":                                          # kernels.py:339-351.  cov(x1) (x2 is None) is elementwise in the Gram
+            if not same:                                       # xx_ij; the two-argument form multiplies an N1xN1 by an N2xN2 matrix
+                raise NotImplementedError("NN.cov(x1, x2): the reference form only broadcasts when N1 == N2 (kernels.py:351)")
+            xx = self._dot_metric(p, x1, x2)
+            return p["var"] * np.arcsin(2 * xx / (1 + 2 * xx) ** 2)
         raise ValueError(k)
 
     def _dot_metric(self, p, x1, x2):
         a = x1[:, self.dims[0]:self.dims[1]][:, None, :]
         b = x2[:, self.dims[0]:self.dims[1]][None, :, :]
         m = np.dot(a * b, p["rate"] ** 2)                      # metrics.py:111-112 ARD_Dot
-        return m if self.kind == "KernelDot" else p["bias"] + m    # metrics.py:131-132 ARD_DotBias
+        return m if self.kind == "KernelDot" else p["bias"] + m    # metrics.py:131-132 ARD_DotBias (LIN, POL, NN)
 
     def dcov(self, th, x1, x2, same, nan_quirk=False):
         """List of dK/dtheta_p (natural space), one N1xN2 array per scalar hyper, layout order.
@@ -295,13 +312,17 @@ class _Leaf(KernelNode):
         K = self.cov(th, x1, x2, same)
         if self.fixed_var is None:
             out.append(K / p["var"])
-        if k in ("Noise", "WN", "BW", "VAR"):
+        if k in ("Noise", "WN", "BW", "VAR", "NIL", "KernelEquals", "KernelEquals2"):
             return out
-        if k in ("KernelDot", "LIN", "POL"):
+        if k in ("KernelDot", "LIN", "POL", "NN"):
             a = x1[:, self.dims[0]:self.dims[1]][:, None, :]
             b = x2[:, self.dims[0]:self.dims[1]][None, :, :]
             m = self._dot_metric(p, x1, x2)
-            dm = p["var"] * self.power * m ** (self.power - 1)
+            if k == "NN":                                      # u = 2m / (1 + 2m)^2, d arcsin(u) = du / sqrt(1 - u^2)
+                u = 2 * m / (1 + 2 * m) ** 2
+                dm = p["var"] * (2 * (1 - 2 * m) / (1 + 2 * m) ** 3) / np.sqrt(1 - u * u)
+            else:
+                dm = p["var"] * self.power * m ** (self.power - 1)
             for j in range(self.nd):
                 out.append(dm * 2 * p["rate"][j] * a[:, :, j] * b[:, :, j])
             if k != "KernelDot":

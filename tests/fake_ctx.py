@@ -69,8 +69,13 @@ def _eval_desc(desc, th, X1, X2, same, skip_pn=False, grad=False):
                 a, b2 = X1[:, None, nd.dim0:nd.dim1], X2[None, :, nd.dim0:nd.dim1]
                 m = (a * b2 * r ** 2).sum(-1) + (th[nd.p1_idx] if nd.p1_idx >= 0 else 0.0)
                 pw = ((nd.flags >> 8) & 0xff) or 1
-                k = m ** pw
-                dm = var * pw * m ** (pw - 1)
+                if nd.flags & cabi.KF_NN:                      # var * arcsin(2m / (1 + 2m)^2)
+                    u = 2 * m / (1 + 2 * m) ** 2
+                    k = np.arcsin(u)
+                    dm = var * (2 * (1 - 2 * m) / (1 + 2 * m) ** 3) / np.sqrt(1 - u * u)
+                else:
+                    k = m ** pw
+                    dm = var * pw * m ** (pw - 1)
                 for j in range(w):
                     g[nd.p0_idx + j] = dm * 2 * r[j] * a[:, :, j] * b2[:, :, j]
                 if nd.p1_idx >= 0:
@@ -79,6 +84,15 @@ def _eval_desc(desc, th, X1, X2, same, skip_pn=False, grad=False):
                 k = np.minimum(X1[:, None, nd.dim0:nd.dim1], X2[None, :, nd.dim0:nd.dim1]).prod(-1)
             elif op == cabi.K_VAR:
                 k = np.ones((n1, n2))
+            elif op == cabi.K_EQ:
+                import struct
+                e1 = nd.value
+                e2 = struct.unpack("<d", struct.pack("<ii", nd.p0_idx, nd.p1_idx))[0] if nd.flags & cabi.KF_EQ2 else e1
+                a, b2 = X1[:, None, nd.dim0:nd.dim1], X2[None, :, nd.dim0:nd.dim1]
+                k = ((a == e1) * (b2 == e2)).sum(-1).astype(float)
+                if nd.flags & cabi.KF_EQ2:
+                    k = k + ((a == e2) * (b2 == e1)).sum(-1)
+                var = 1.0
             elif op == cabi.K_NOISE:
                 k = eye * (0.0 if (skip_pn and nd.flags & cabi.KF_PROCESS_NOISE) else 1.0)
             elif op == cabi.K_WN:

@@ -80,6 +80,9 @@ def _ref_kernel(g3, spec, X):
         kw['var'] = spec['var']
     if t == 'POL' and 'p' in spec:
         kw['p'] = spec['p']
+    for key in ('eq', 'eq1', 'eq2'):
+        if key in spec:
+            kw[key] = spec[key]
     cls = g3.KernelNoise if t == 'Noise' else getattr(g3, t)
     return cls(_x_arg(X, spec.get('dims')), **kw)
 
@@ -241,6 +244,15 @@ CASES = {
                                       kernel=K('MAT32')), N=24, D=2, M=7, seed=91),
     'map_boxcoxlin2':  dict(spec=dict(kind='gauss', warped=True, location=K('Bias'), kernel=K('SE'), mapping=K('BoxCoxLinear2')),
                             N=24, D=1, M=7, seed=92, positive=True),
+    # NN (training Gram only: its two-argument cov does not broadcast, kernels.py:351), NIL, KernelEquals / KernelEquals2 on
+    # inputs whose first column is rounded to integers so that the equality metrics are not identically zero
+    'leaf_nn':         dict(spec=dict(kind='gauss', location=K('Zero'), kernel=K('NN')), N=24, D=2, M=7, seed=93, logp_only=True,
+                            theta_shift={'NN_var': -1.5, 'Noise_var': 2.0}),
+    'leaf_nil_equals': dict(spec=dict(kind='gauss', location=K('Bias'),
+                                      kernel=K('sum', k1=K('sum', k1=K('SE'), k2=K('NIL')),
+                                               k2=K('sum', k1=K('scale', c=0.3, k=K('KernelEquals', eq=1.0, dims=[0, 1])),
+                                                    k2=K('scale', c=0.01, k=K('KernelEquals2', eq1=0.0, eq2=1.0, dims=[0, 1]))))),
+                            N=24, D=2, M=7, seed=94, int_col=True, theta_shift={'Noise_var': 2.0}),
     # MappingInvSum cannot be pinned: its `__call__` is `pass`, so EllipticalProcess.th_define_process (elliptical.py:64:
     # tt_to_num(self.f_mapping(self.th_outputs))) raises before any method exists - dead code in the reference.
     'wtp_boxcox':      dict(spec=dict(kind='student', warped=True, location=K('Bias'), kernel=K('MAT52'),
@@ -315,6 +327,9 @@ def theta_for(layout, y, rng, case):
             v = np.full(size, np.nanmin(y) - 0.5)
         elif name.endswith('_shift'):
             v = 0.05 * v
+        for suffix, shift in case.get('theta_shift', {}).items():      # per-case nudges (log space for positive hypers)
+            if name.endswith(suffix):
+                v = v + shift
         th.append(v)
     return np.concatenate(th) if th else np.zeros(0)
 
@@ -444,16 +459,26 @@ def fullsize(g3):
 def main():
     g3 = _import_reference()
     shim_self_check(g3)
-    c1_find_map(g3)
-    if '--no-fullsize' not in sys.argv:
-        fullsize(g3)
+    if not any(a.startswith('--only=') for a in sys.argv):
+        c1_find_map(g3)
+        if '--no-fullsize' not in sys.argv:
+            fullsize(g3)
     from oracle import g3_oracle as orc     # only for the neutral layout (names / order), not for any value
     out = {}
+    only = [a.split('=', 1)[1].split(',') for a in sys.argv if a.startswith('--only=')]
+    if only:                                 # regenerate the named cases only and merge them into the committed file
+        with open(os.path.join(HERE, 'reference_g3py.json')) as f:
+            out = json.load(f)
     for cname, case in CASES.items():
+        if only and cname not in only[0]:
+            continue
         X, y, Xs = _data(case['seed'], case['N'], case['D'], case['M'], case.get('positive', False))
         if case.get('duplicate'):
             X[1::2] = X[0::2]                       # exact duplicates: singular noise-free Gram
             y[1::2] = y[0::2]
+        if case.get('int_col'):
+            X[:, 0] = np.floor(X[:, 0] / 2.0)            # {0, 1, 2}
+            Xs[:, 0] = np.floor(Xs[:, 0] / 2.0)
         spec = case['spec']
         proc = ref_process(g3, spec, X)
         proc.observed(X, y)

@@ -5,7 +5,8 @@ import numpy as np
 import g3py_b200 as g3
 
 LEAVES = {"SE": g3.SE, "OU": g3.OU, "MAT32": g3.MAT32, "MAT52": g3.MAT52, "RQ": g3.RQ, "SIN": g3.SIN, "COS": g3.COS, "SINC": g3.SINC, "SM": g3.SM, "WN": g3.WN,
-          "Noise": g3.KernelNoise, "KernelDot": g3.KernelDot, "LIN": g3.LIN, "POL": g3.POL, "BW": g3.BW, "VAR": g3.VAR}
+          "Noise": g3.KernelNoise, "KernelDot": g3.KernelDot, "LIN": g3.LIN, "POL": g3.POL, "BW": g3.BW, "VAR": g3.VAR,
+          "NN": g3.NN, "NIL": g3.NIL, "KernelEquals": g3.KernelEquals, "KernelEquals2": g3.KernelEquals2}
 MAPS = {"Identity": g3.Identity, "LinearMapping": g3.LinearMapping, "LogShifted": g3.LogShifted,
         "BoxCoxShifted": g3.BoxCoxShifted, "BoxCoxLinear": g3.BoxCoxLinear, "ArcsinhLinear": g3.ArcsinhLinear,
         "SinhArcsinh": g3.SinhArcsinh, "Logistic": g3.Logistic, "WarpingTanh": g3.WarpingTanh,
@@ -48,6 +49,9 @@ def _build_kernel(spec, X):
         kw["var"] = spec["var"]
     if t == "POL" and "p" in spec:
         kw["p"] = spec["p"]
+    for key in ("eq", "eq1", "eq2"):
+        if key in spec:
+            kw[key] = spec[key]
     return LEAVES[t](_x_arg(X, spec.get("dims")), **kw)
 
 

@@ -22,8 +22,15 @@ SPECS = {
     "potentials": dict(kind="gauss", warped=True, location=dict(type="Bias", potential=["Bias", "L2", 0.3]),
                        kernel=dict(type="sum", potential=["var", "L1", 0.7], k1=K("SE"), k2=dict(type="RQ", potential=["alpha", "L2", 0.2])),
                        mapping=dict(type="BoxCoxShifted", potential=["power", "L1", 0.4])),
+    # NN is defined for the training Gram only (kernels.py:351): logp / gradient, no posterior
+    "nn": dict(kind="gauss", location=K("Zero"), kernel=K("sum", k1=K("NN"), k2=K("SE"))),
+    "nil_equals": dict(kind="gauss", location=K("Bias"),
+                       kernel=K("sum", k1=K("sum", k1=K("SE"), k2=K("NIL")),
+                                k2=K("sum", k1=K("scale", c=0.3, k=K("KernelEquals", eq=1.0, dims=[0, 1])),
+                                     k2=K("scale", c=0.002, k=K("KernelEquals2", eq1=0.0, eq2=1.0, dims=[0, 1]))))),
 }
 POSITIVE = {"tgp", "warpboxcox", "logistic", "potentials"}
+LOGP_ONLY = {"nn"}
 
 
 def _problem(name, N, B, seed=0):
@@ -33,12 +40,14 @@ def _problem(name, N, B, seed=0):
     y = np.sin(X[:, 0]) + 0.4 * np.cos(0.7 * X[:, 1]) + 0.1 * rng.standard_normal(N)
     if name in POSITIVE:
         y = np.exp(0.5 * y) + 0.2
+    if name == "nil_equals":
+        X[:, 0] = np.floor(X[:, 0] / 2.0)                   # {0, 1, 2}: the equality metrics are not identically zero
     op = orc.build_process(SPECS[name], D)
     th = []
     for nm, size, pos in op.layout():
         v = 0.1 * rng.standard_normal((B, size))
         if "Noise" in nm:                      # max(k1, k2) is not PSD in general: more noise keeps K definite
-            v += np.log((2.0 if name == "max" else 0.05) * np.var(y))
+            v += np.log((2.0 if name in ("max", "nn", "nil_equals") else 0.05) * np.var(y))
         elif nm.endswith("_var"):
             v += np.log(np.var(y))
         elif nm.endswith("_bias"):
@@ -75,7 +84,11 @@ def _check(name, N, B, M):
         want = op.logp(Th[b], X, y)
         assert abs(lp[b] - want) <= 1e-9 * abs(want), (name, b)
         assert scaled_err(g[b], op.dlogp(Th[b], X, y, nan_quirk=True)) < 1e-9, (name, b)
+    if name in LOGP_ONLY:
+        return
     Xs = X[:M] + 0.05
+    if name == "nil_equals":
+        Xs[:, 0] = X[:M, 0]
     if SPECS[name].get("kind") == "transport":
         v = np.random.default_rng(5).standard_normal(M)
         for prior in (True, False):
@@ -231,3 +244,41 @@ def test_power_blackbox_means_and_new_mappings_on_fake(monkeypatch):
             assert gw[i] == pytest.approx(fd, rel=2e-5, abs=1e-5), (type(mp).__name__, lay[i])
         pr = w.predict(tw, space=X[:5], array=True, var=True, median=True)
         assert np.all(np.isfinite(pr["mean"])) and np.all(pr["variance"] >= 0)
+
+
+def test_nn_nil_equals_kernels_on_fake(monkeypatch):
+    """NN / NIL / KernelEquals / KernelEquals2 (kernels.py:262-288,309-351) through the public API on the NumPy device
+    double: NIL adds nothing, the equality kernels count coordinates equal to their constants, the NN gradient agrees with
+    central differences, and the posterior of an NN model raises as the reference's two-argument cov does (kernels.py:351)."""
+    import g3py_b200 as g3
+    from fake_ctx import FakeContext
+    ctx = FakeContext()
+    monkeypatch.setattr(g3.processes, "get_context", lambda device=0: ctx)
+    rng = np.random.default_rng(11)
+    X = rng.uniform(0.0, 2.0, size=(30, 2))
+    X[:, 0] = np.floor(X[:, 0] * 1.5)                                  # {0, 1, 2}
+    y = np.sin(X[:, 1]) + 0.3 * (X[:, 0] == 1.0) + 0.05 * rng.standard_normal(30)
+    base = g3.GP(X, g3.Zero(), g3.SE(X))
+    with_nil = g3.GP(X, g3.Zero(), g3.SE(X) + g3.NIL(X))
+    base.observed(X, y)
+    with_nil.observed(X, y)
+    t0 = np.array([0.1, -0.2, 0.3, np.log(0.05)])
+    assert with_nil.ndim == base.ndim                                  # NIL has no hypers
+    assert with_nil.logp(t0, array=True) == pytest.approx(base.logp(t0, array=True), rel=1e-13)
+    K1 = g3.KernelEquals(X[:, :1], eq=1.0).cov(X[:, :1])
+    assert np.array_equal(K1, np.outer(X[:, 0] == 1.0, X[:, 0] == 1.0).astype(float))
+    K2 = g3.KernelEquals2(X[:, :1], eq1=0.0, eq2=2.0).cov(X[:, :1], X[:5, :1])
+    a, b = X[:, 0][:, None], X[:5, 0][None, :]
+    assert np.array_equal(K2, ((a == 0.0) & (b == 2.0)).astype(float) + ((a == 2.0) & (b == 0.0)))
+    nn = g3.GP(X, g3.Zero(), g3.NN(X))
+    nn.observed(X, y)
+    assert [n.split("_", 1)[1] for n, _, _ in nn.layout] == ["NN_var", "NN_rate", "NN_bias", "Noise_var"]
+    th = np.array([np.log(0.2), np.log(0.9), np.log(1.1), np.log(0.6), np.log(0.2)])
+    g = nn.dlogp(th, array=True)
+    for i in range(len(th)):
+        e = np.zeros_like(th)
+        e[i] = 1e-5
+        fd = (nn.logp(th + e, array=True) - nn.logp(th - e, array=True)) / 2e-5
+        assert g[i] == pytest.approx(fd, rel=2e-5, abs=1e-6)
+    with pytest.raises(NotImplementedError):
+        nn.predict(th, space=X[:4], array=True)

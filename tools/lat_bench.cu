@@ -1,5 +1,6 @@
 // Dependent-issue latencies on sm_100a that the diagonal-tile kernel's critical path is made of (one warp, one CTA).
 #include <cstdio>
+#include <cmath>
 #include <cuda_runtime.h>
 #include <mma.h>
 #define N 4096
@@ -130,6 +131,21 @@ __global__ void k_dmma4(double* out, long long* cyc, double x) {   // 4 independ
   long long t1 = clock64();
   out[threadIdx.x] = fc[0].x[0] + fc[1].x[1] + fc[2].x[0] + fc[3].x[1]; if (threadIdx.x == 0) cyc[0] = t1 - t0;
 }
+__global__ void k_seed_err(double* out) {   // max |1 - d * rcp.approx(d)| and max |1 - d * rsqrt.approx(d)^2| over 2^22 mantissas x a few exponents
+  double m1 = 0.0, m2 = 0.0;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (1u << 22); i += gridDim.x * blockDim.x) {
+    for (int e = -3; e <= 3; e += 3) {
+      const double d = ldexp(1.0 + (double)i / (double)(1u << 22) + 1.1e-9, e);
+      double y, z;
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+      asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(z) : "d"(d));
+      m1 = fmax(m1, fabs(fma(-d, y, 1.0)));
+      m2 = fmax(m2, fabs(fma(-d * z, z, 1.0)));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) { m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o)); m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, o)); }
+  if ((threadIdx.x & 31) == 0) { atomicMax((unsigned long long*)out, __double_as_longlong(m1)); atomicMax((unsigned long long*)out + 1, __double_as_longlong(m2)); }
+}
 int main() {
   double* out; long long* cyc; float* fout;
   cudaMalloc(&out, 8 * 1024); cudaMalloc(&fout, 4 * 1024); cudaMalloc(&cyc, 8);
@@ -157,5 +173,10 @@ int main() {
   // 16 warps: aggregate DFMA throughput of one SM with 16 chains per thread
   RUN("DFMA 16 chains, 16 warps", "16 ops", (k_dfma16<<<1, 512>>>(out, cyc, 1.0, 0.999)));
   RUN("DMMA 4 chains, 16 warps", "4 ops", (k_dmma4<<<1, 512>>>(out, cyc, 1.0)));
+  cudaMemset(out, 0, 16);
+  k_seed_err<<<148, 256>>>(out);
+  double he[2];
+  cudaMemcpy(he, out, 16, cudaMemcpyDeviceToHost);
+  printf("seed error: rcp.approx.f64 max |1 - d y| = %.3e = 2^%.1f;  rsqrt.approx.f64 max |1 - d z^2| = %.3e = 2^%.1f\n", he[0], log2(he[0]), he[1], log2(he[1]));
   return 0;
 }
