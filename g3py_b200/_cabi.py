@@ -10,8 +10,8 @@ import os
 
 import numpy as np
 
-G3_MAX_NODES = 16
-G3_MAX_THETA = 32
+G3_MAX_NODES = 32
+G3_MAX_THETA = 64
 G3_MAX_DIM = 16
 
 # leaf / node opcodes (include/g3b.h)

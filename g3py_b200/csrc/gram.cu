@@ -750,8 +750,8 @@ vjp_reduce_kernel(const double* __restrict__ partials, int ntiles, int P, double
 }  // namespace
 
 int g3_check_desc(g3_ctx* ctx, const g3_kernel_desc& d, int D) {
-  if (d.n_nodes < 1 || d.n_nodes > G3_MAX_NODES) return g3_fail_msg(ctx, "kernel desc: 1 <= n_nodes <= 16");
-  if (d.n_theta < 0 || d.n_theta > G3_MAX_THETA) return g3_fail_msg(ctx, "kernel desc: n_theta <= 32");
+  if (d.n_nodes < 1 || d.n_nodes > G3_MAX_NODES) return g3_fail_msg(ctx, "kernel desc: 1 <= n_nodes <= 32");
+  if (d.n_theta < 0 || d.n_theta > G3_MAX_THETA) return g3_fail_msg(ctx, "kernel desc: n_theta <= 64");
   int depth = 0;
   for (int n = 0; n < d.n_nodes; ++n) {
     const g3_knode& nd = d.nodes[n];
@@ -800,13 +800,15 @@ static int fast_mode() {           // G3_NO_FAST=1: generic interpreter only; G3
   if (mode < 0) { const char* e = getenv("G3_NO_FAST"); mode = e ? atoi(e) : 0; }
   return mode;
 }
+// the fast paths keep their shared-memory budget: small trees only (the usual case); larger ones take the generic interpreter
+static bool small_tree(const g3_kernel_desc& desc) { return desc.n_nodes <= 16 && desc.n_theta <= 32; }
 static bool use_fast2(const g3_kernel_desc& desc, int D, int same) {
-  return fast_mode() == 0 && D <= 8 && g3_desc_is_fast2(desc, same);
+  return fast_mode() == 0 && D <= 8 && small_tree(desc) && g3_desc_is_fast2(desc, same);
 }
 static bool use_fast_path(const g3_kernel_desc& desc, int D) {
   static int off = -1;
   if (off < 0) off = fast_mode() == 1 ? 1 : 0;
-  return !off && D <= 4 && g3_desc_is_additive(desc);
+  return !off && D <= 4 && small_tree(desc) && g3_desc_is_additive(desc);
 }
 
 int g3_gram_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const GramArgs& a, int B) {
@@ -849,7 +851,7 @@ int g3_gram_vjp_launch(g3_ctx* ctx, const g3_kernel_desc& desc, const VjpArgs& a
   const size_t smem = sizeof(double) * (2 * TS * a.D + G3_MAX_THETA + 2 * TS + (size_t)a.P * 256);
   static bool attr = false;
   if (!attr) {
-    G3_CUDA(ctx, cudaFuncSetAttribute(gram_vjp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    G3_CUDA(ctx, cudaFuncSetAttribute(gram_vjp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   if (a.P == 0) return 0;

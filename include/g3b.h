@@ -76,8 +76,8 @@ typedef struct {
 
 enum { G3_KF_PROCESS_NOISE = 1 };
 
-#define G3_MAX_NODES 16
-#define G3_MAX_THETA 32
+#define G3_MAX_NODES 32   /* up to 16 leaves and their 15 operators (+1); trees of <= 16 nodes and <= 32 slots keep the fast Gram paths */
+#define G3_MAX_THETA 64
 #define G3_MAX_DIM 16
 
 typedef struct {

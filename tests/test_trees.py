@@ -124,11 +124,28 @@ def cases2(n=16):
     return out
 
 
+# third family: trees beyond the first ABI limits (17..32 nodes, up to 64 hyper slots): generic interpreter only
+def cases3(n=6):
+    rng = np.random.default_rng(8096)
+    out = []
+    while len(out) < n:
+        D = int(rng.integers(2, 6))
+        names = []
+        spec = random_spec2(rng, D, 2, names)
+        for _ in range(int(rng.integers(5, 9))):        # a long left-nested sum / product chain keeps the stack shallow
+            spec = {"type": "sum" if rng.random() < 0.7 else "prod", "k1": spec, "k2": random_spec2(rng, D, 1, names)}
+        if 17 <= n_nodes2(spec) <= 32:
+            out.append((D, spec))
+    return out
+
+
 def _case(idx):
-    return cases()[idx] if idx < 24 else cases2()[idx - 24]
+    if idx < 24:
+        return cases()[idx]
+    return cases2()[idx - 24] if idx < 40 else cases3()[idx - 40]
 
 
-@pytest.mark.parametrize("idx", range(40))
+@pytest.mark.parametrize("idx", range(46))
 def test_descriptor_matches_oracle_cpu(idx):
     D, spec = _case(idx)
     rng = np.random.default_rng(idx)
@@ -148,7 +165,7 @@ def test_descriptor_matches_oracle_cpu(idx):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("idx", range(40))
+@pytest.mark.parametrize("idx", range(46))
 def test_descriptor_matches_oracle_gpu(idx):
     D, spec = _case(idx)
     rng = np.random.default_rng(idx)
