@@ -66,6 +66,7 @@ SIGNATURES = {
     "g3_debug_gemm_stress": (C.c_int, [_ctxp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
     "g3_debug_fp64_peak": (C.c_int, [_ctxp, C.c_double, _dp, _dp, _dp]),
     "g3_set_diag_variant": (C.c_int, [_ctxp, C.c_int]),
+    "g3_set_tile_split": (C.c_int, [_ctxp, C.c_int]),
     "g3_debug_diag_time": (C.c_int, [_ctxp, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_float),
                                      C.POINTER(C.c_longlong), _dp]),
     "g3_set_stream": (C.c_int, [_ctxp, C.c_void_p]),
@@ -224,7 +225,12 @@ class Context:
         self._ck(self._lib.g3_set_trtri_pipeline(self._h, int(bool(on))), "g3_set_trtri_pipeline")
 
     def set_splitk(self, on):
-        self._ck(self._lib.g3_set_splitk(self._h, int(bool(on))), "g3_set_splitk")
+        """0 off, 1 (default) at least 128 of the contraction per share, 2 shares down to 32 and triangular solves too (measured slower)."""
+        self._ck(self._lib.g3_set_splitk(self._h, int(on)), "g3_set_splitk")
+
+    def set_tile_split(self, on):
+        """Spread each tile of a few-tile GEMM launch over 2 / 4 CTAs by columns (default on)."""
+        self._ck(self._lib.g3_set_tile_split(self._h, int(bool(on))), "g3_set_tile_split")
 
     def set_graphs(self, on):
         """CUDA-graph replay of small-batch evaluations (default on)."""

@@ -63,8 +63,14 @@ __device__ __forceinline__ void lds128(uint32_t addr, double& x, double& y) {
   asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
 }
 
+// NJ = 8-column fragments per warp: 4 = the CTA computes the whole 64 x 128 tile; 2 / 1 = a half / a quarter of its columns
+// (the other CTAs of the tile load the same operand boxes).  Launches of a few tiles are bound by ONE SM's fp64 rate --
+// 8.3 us for a 64 x 128 x 128 tile -- so the column updates and triangular solves of single-matrix evaluations spread
+// each tile over 2 or 4 SMs.
+template <int NJ>
 __global__ void __launch_bounds__(256, 2)
 dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  constexpr int CS = 4 / NJ;                 // CTAs per 64-row half tile
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + G3_STAGES * kStageBytes);
 
@@ -76,8 +82,11 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int wm = warp & 1, wn = warp < 4 ? (warp >> 1) : 3 - ((warp - 4) >> 1);
 
   // ---- tile decode -------------------------------------------------------------------
-  const int h = blockIdx.x & 1;  // which 64-row half of the 128-row block
-  const int tile = blockIdx.x >> 1;
+  // blockIdx.x = (tile * 2 + h) * CS + cs: the CS CTAs that share one operand box are consecutive = one thread-block cluster
+  const int cs = (int)blockIdx.x % CS;
+  const int h = ((int)blockIdx.x / CS) & 1;  // which 64-row half of the 128-row block
+  const int tile = (int)blockIdx.x / (2 * CS);
+  const int col0 = cs * (32 * NJ) + wn * (8 * NJ);          // this warp's first column inside the 128-wide tile
   int x, y;
   if (g.mode == 0) {
     x = tile % g.ntx;
@@ -92,8 +101,8 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const bool diag_tile = ((g.upper & 1) && x == y) || ((g.upper & 2) && x == 0);
   // warps whose 32x32 block lies strictly above the diagonal of a diagonal tile have nothing to compute; they
   // only pace the ring (rows h*64 + wm*32 .. +31, columns wn*32 .. +31)
-  const bool idle = diag_tile && wn > 2 * h + wm;
-  const int kt_lim = g.tri_b ? 2 * wn + 2 : 0x7fffffff;     // triangular B: k-tiles this warp's columns reach
+  const bool idle = diag_tile && col0 >= h * 64 + wm * 32 + 32;
+  const int kt_lim = g.tri_b ? (col0 + 8 * NJ + 15) / 16 : 0x7fffffff;     // triangular B: k-tiles this warp's columns reach
   const int bidx = g.bmap ? g.bmap[blockIdx.y] : (int)blockIdx.y;
   const int a_row = g.a_r0 + x * g.a_rx + y * g.a_ry + h * G3_BM;
   const int b_row = g.b_r0 + x * g.b_rx + y * g.b_ry;
@@ -101,9 +110,11 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   int kb = g.kb0 + x * g.kb_x + y * g.kb_y;
   int nk = (g.kl0 + x * g.kl_x + y * g.kl_y) / G3_BK;
   const int sk = g.splitk > 1 ? (int)blockIdx.z : 0;
+  int kt0 = 0;         // first k-tile of this CTA's share (the triangular-B skipping counts absolute k-tiles)
   if (g.splitk > 1) {  // this CTA's share of the contraction: k-tiles [sk*chunk, (sk+1)*chunk)
     const int chunk = (nk + g.splitk - 1) / g.splitk;
     const int lo = sk * chunk;
+    kt0 = lo;
     nk = nk - lo < chunk ? nk - lo : chunk;
     if (nk < 0) nk = 0;
     ka += lo * G3_BK;
@@ -144,14 +155,14 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   // beta != 0: the D tile enters through the accumulators (acc = (beta/alpha) * D, loaded while the TMA pipeline
   // fills), so the epilogue is a pure store and no global-load latency sits between the last DMMA and the write.
-  double acc[4][4][2];
+  double acc[4][NJ][2];
   if (g.beta != 0.0 && !idle && sk == 0) {
     const double sc = g.beta / g.alpha;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const double* rowp = Dt + (long long)(wm * 32 + i * 8 + grp) * g.ldd + wn * 32 + 2 * t4;
+      const double* rowp = Dt + (long long)(wm * 32 + i * 8 + grp) * g.ldd + col0 + 2 * t4;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         const double2 v = *reinterpret_cast<const double2*>(rowp + j * 8);
         acc[i][j][0] = sc * v.x;
         acc[i][j][1] = sc * v.y;
@@ -161,12 +172,12 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   }
 
   // per-thread fragment offsets inside a stage: row*128 + ((chunk ^ (row&7)) << 4), row&7 == grp
   const uint32_t offA = (uint32_t)((wm * 32 + grp) * 128);
-  const uint32_t offB = (uint32_t)(kStageBytesA + (wn * 32 + grp) * 128);
+  const uint32_t offB = (uint32_t)(kStageBytesA + (col0 + grp) * 128);
   const uint32_t sw0 = (uint32_t)(((2 * t4 + 0) ^ grp) << 4);
   const uint32_t sw1 = (uint32_t)(((2 * t4 + 1) ^ grp) << 4);
 
@@ -181,21 +192,21 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     mbar_wait(full_bar(s), ph);
     const uint32_t st = smem_base + s * kStageBytes;
-    if (!idle && kt < kt_lim) {
+    if (!idle && kt0 + kt < kt_lim) {
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const uint32_t sw = c ? sw1 : sw0;
-      double a[4][2], b[4][2];
+      double a[4][2], b[NJ][2];
 #pragma unroll
       for (int i = 0; i < 4; ++i) lds128(st + offA + i * 1024 + sw, a[i][0], a[i][1]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) lds128(st + offB + j * 1024 + sw, b[j][0], b[j][1]);
+      for (int j = 0; j < NJ; ++j) lds128(st + offB + j * 1024 + sw, b[j][0], b[j][1]);
 #pragma unroll
       for (int e = 0; e < 2; ++e)
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i][e], b[j][e]);
+          for (int j = 0; j < NJ; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i][e], b[j][e]);
     }
     }
     // Release the stage.  The LDS above are asynchronous: ptxas hoists the arrive right behind the last LDS
@@ -209,6 +220,12 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 
   // ---- epilogue ------------------------------------------------------------------------
+  if (CS > 1) {
+    // In-place launches (L_ij = A_ij Linv^T, U_ji = -S_ji Linv^T) read the tile they overwrite: every CTA of the cluster
+    // must have consumed its copy of the operand box before any of them stores its columns.
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   if (g.splitk > 1) {
     // split-K: park the partial tile, count arrivals; the last CTA of the tile adds the partials in split order
     __shared__ int is_last;
@@ -218,8 +235,8 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<double2*>(part + (wm * 32 + i * 8 + grp) * G3_BN + wn * 32 + j * 8 + 2 * t4) =
+        for (int j = 0; j < NJ; ++j)
+          *reinterpret_cast<double2*>(part + (wm * 32 + i * 8 + grp) * G3_BN + col0 + j * 8 + 2 * t4) =
               make_double2(acc[i][j][0], acc[i][j][1]);
     }
     __threadfence();
@@ -235,10 +252,10 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const double* base = g.sk_ws + tile_lin * g.splitk * (long long)(G3_BM * G3_BN);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      double* rowp = Dt + (long long)(wm * 32 + i * 8 + grp) * g.ldd + wn * 32 + 2 * t4;
+      double* rowp = Dt + (long long)(wm * 32 + i * 8 + grp) * g.ldd + col0 + 2 * t4;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const long long off = (wm * 32 + i * 8 + grp) * G3_BN + wn * 32 + j * 8 + 2 * t4;
+      for (int j = 0; j < NJ; ++j) {
+        const long long off = (wm * 32 + i * 8 + grp) * G3_BN + col0 + j * 8 + 2 * t4;
         double2 sum = make_double2(0.0, 0.0);
         for (int q = 0; q < g.splitk; ++q) {
           const double2 v = __ldcg(reinterpret_cast<const double2*>(base + (long long)q * (G3_BM * G3_BN) + off));
@@ -254,9 +271,9 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const double alpha = g.alpha;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    double* rowp = Dt + (long long)(wm * 32 + i * 8 + grp) * g.ldd + wn * 32 + 2 * t4;
+    double* rowp = Dt + (long long)(wm * 32 + i * 8 + grp) * g.ldd + col0 + 2 * t4;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < NJ; ++j)
       *reinterpret_cast<double2*>(rowp + j * 8) = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
   }
 }
@@ -265,8 +282,12 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 int g3_gemm_launch(g3_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int B) {
   if (!ctx->gemm_ready) {
-    G3_CUDA(ctx, cudaFuncSetAttribute(dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    G3_CUDA(ctx, cudaFuncSetAttribute(dgemm_nt_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    G3_CUDA(ctx, cudaFuncSetAttribute(dgemm_nt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    G3_CUDA(ctx, cudaFuncSetAttribute(dgemm_nt_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    G3_CUDA(ctx, cudaFuncSetAttribute(dgemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    G3_CUDA(ctx, cudaFuncSetAttribute(dgemm_nt_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    G3_CUDA(ctx, cudaFuncSetAttribute(dgemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    G3_CUDA(ctx, cudaFuncSetAttribute(dgemm_nt_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     ctx->gemm_ready = true;
   }
   long long ntiles = a.mode == 0 ? (long long)a.ntx * a.nty : (long long)a.ntx * (a.ntx + 1) / 2;
@@ -275,10 +296,19 @@ int g3_gemm_launch(g3_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   g.splitk = 1;
   g.sk_ws = nullptr;
   g.sk_cnt = nullptr;
-  // Few tiles with a deep contraction (column updates of a single matrix, rows of trtri) leave most SMs idle and
-  // each CTA runs at one SM's fp64 rate: split the contraction over up to 8 CTAs per tile.
-  const long long ctas = ntiles * 2 * B;
-  if (ctx->splitk && !a.tri_b && ctas * 2 <= 2 * ctx->sm_count) {
+  // Few tiles with a deep contraction (column updates of a single matrix, rows of trtri) leave most SMs idle and each CTA
+  // runs at one SM's fp64 rate: split the contraction over up to 8 CTAs per tile, at least one 128-block per share.
+  // (g3_set_splitk(ctx, 2) goes down to 32 per share and also splits the triangular solves, whose 64 x 128 tile costs
+  // 8.3 us on one SM even at depth 128 -- measured SLOWER on B200, profiles/r02t_splitk_ab.txt: the partial-tile round trip
+  // through L2 and the extra CTAs cost more than the shorter main loop saves.)
+  // column split of the tiles while one CTA per SM is not reached (g3_set_tile_split)
+  int csplit = 1;
+  if (ctx->tile_split) {
+    const long long base = ntiles * 2 * B;
+    csplit = base * 4 <= ctx->sm_count ? 4 : (base * 2 <= ctx->sm_count ? 2 : 1);
+  }
+  const long long ctas = ntiles * 2 * B * csplit;
+  if (ctx->splitk && ctas * 2 <= 2 * ctx->sm_count) {
     int kmax = a.kl0;
     if (a.mode == 0) {
       const int kx = a.kl0 + a.kl_x * (a.ntx - 1), ky = a.kl0 + a.kl_y * (a.nty - 1);
@@ -286,7 +316,9 @@ int g3_gemm_launch(g3_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, 
       kmax = kmax > ky ? kmax : ky;
     }
     int sk = (int)(2 * ctx->sm_count / ctas);
-    if (sk > kmax / 128) sk = kmax / 128;                      // at least 8 k-tiles (one 128-block) per share
+    const int min_share = ctx->splitk >= 2 ? 32 : 128;
+    if (a.tri_b && ctx->splitk < 2) sk = 1;
+    if (sk > kmax / min_share) sk = kmax / min_share;
     if (sk > 8) sk = 8;
     if (sk >= 2) {
       // per-stream scratch: launches on one stream are ordered, different streams (batch groups, look-ahead) are not
@@ -305,9 +337,27 @@ int g3_gemm_launch(g3_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, 
       }
     }
   }
-  dim3 grid((unsigned)(ntiles * 2), (unsigned)B, (unsigned)g.splitk);
+  dim3 grid((unsigned)(ntiles * 2 * csplit), (unsigned)B, (unsigned)g.splitk);
   g3_prof_begin(ctx, G3_PROF_GEMM);
-  dgemm_nt_kernel<<<grid, 256, kSmemBytes, ctx->stream>>>(tmA, tmB, g);
+  if (csplit > 1) {   // the CTAs of one tile half form a cluster (barrier before the stores, see the kernel)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)csplit;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = csplit == 4 ? cudaLaunchKernelEx(&cfg, dgemm_nt_kernel<1>, tmA, tmB, g)
+                                : cudaLaunchKernelEx(&cfg, dgemm_nt_kernel<2>, tmA, tmB, g);
+    if (e != cudaSuccess) return g3_fail(ctx, "cudaLaunchKernelEx(dgemm_nt, cluster)", e, __FILE__, __LINE__);
+  } else {
+    dgemm_nt_kernel<4><<<grid, 256, kSmemBytes, ctx->stream>>>(tmA, tmB, g);
+  }
   g3_prof_end(ctx);
   G3_LAUNCH_CHECK(ctx);
   return 0;

@@ -330,8 +330,15 @@ int g3_set_trtri_pipeline(g3_ctx* ctx, int on) {
   return 0;
 }
 
+int g3_set_tile_split(g3_ctx* ctx, int on) {
+  if (ctx->tile_split != (on ? 1 : 0)) g3_graph_drop(ctx);
+  ctx->tile_split = on ? 1 : 0;
+  return 0;
+}
+
 int g3_set_splitk(g3_ctx* ctx, int on) {
-  ctx->splitk = on ? 1 : 0;
+  if (ctx->splitk != on) g3_graph_drop(ctx);
+  ctx->splitk = on < 0 ? 0 : (on > 2 ? 2 : on);
   return 0;
 }
 

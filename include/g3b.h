@@ -123,9 +123,14 @@ int g3_set_potrf_block(g3_ctx* ctx, int w_outer);
 /* Look-ahead of the blocked (right-looking) factorisation: the next panel is updated and factored on a second,
  * high-priority stream while the rest of the trailing update runs (default on; results do not depend on it). */
 int g3_set_lookahead(g3_ctx* ctx, int on);
-/* Split-K for GEMM launches with few tiles and a deep contraction (single-matrix evaluations): up to 8 CTAs share
- * one output tile, partial tiles are added in a fixed order (bitwise reproducible).  Default on. */
+/* Split-K for GEMM launches with few tiles and a deep contraction (single-matrix evaluations): up to 8 CTAs share one
+ * output tile, partial tiles are added in a fixed order (bitwise reproducible).  on = 1 (default): at least 128 of the
+ * contraction per share; 2: shares down to 32 and the triangular solves too (experiment, measured slower); 0: off. */
 int g3_set_splitk(g3_ctx* ctx, int on);
+/* Column split of GEMM tiles: a launch of a few 64 x 128 tiles (triangular solves and column updates of single-matrix
+ * evaluations) is bound by one SM's fp64 rate per tile, so each tile is spread over 2 or 4 CTAs (halves / quarters of its
+ * columns; same summation order, bitwise identical results) until one CTA per SM is reached.  Default on. */
+int g3_set_tile_split(g3_ctx* ctx, int on);
 /* Gradient path of few large matrices: compute U = L^-T block by block on a third stream while the look-ahead
  * factorisation is still running (default on; results do not depend on it). */
 int g3_set_trtri_pipeline(g3_ctx* ctx, int on);
