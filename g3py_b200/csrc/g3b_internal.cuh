@@ -74,6 +74,7 @@ struct g3_ctx {
   int trtri_pipeline = 1, trtri_done = 0;
   int force_left = 0;                  // set by g3_gp_run for batches of more than 8 items (their stream groups hold 8)
   int splitk = 1;                      // allow split-K for few-tile / deep-K GEMM launches (g3_set_splitk)
+  int trsv_fused = 1;                  // whole triangular solves in one launch (flags between CTAs) instead of T dependent launches
   int tile_split = 1;                  // spread each output tile of a few-tile GEMM launch over 2 / 4 CTAs by columns (g3_set_tile_split)
   struct g3_dist* dist = nullptr;      // multi-GPU state (dist.cu): NCCL communicator, block-cyclic panels
   // CUDA-graph replay of the launch sequence of small batches (gp.cu: g3_gp_run)

@@ -330,6 +330,12 @@ int g3_set_trtri_pipeline(g3_ctx* ctx, int on) {
   return 0;
 }
 
+int g3_set_trsv_fused(g3_ctx* ctx, int on) {
+  if (ctx->trsv_fused != (on ? 1 : 0)) g3_graph_drop(ctx);
+  ctx->trsv_fused = on ? 1 : 0;
+  return 0;
+}
+
 int g3_set_tile_split(g3_ctx* ctx, int on) {
   if (ctx->tile_split != (on ? 1 : 0)) g3_graph_drop(ctx);
   ctx->tile_split = on ? 1 : 0;

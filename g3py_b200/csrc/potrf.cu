@@ -365,6 +365,143 @@ trsv_bwd_step_kernel(const double* __restrict__ L, const double* __restrict__ Di
   if (tid < TS) sb[i * TS + tid] -= part[0][tid] + part[1][tid];
 }
 
+
+// ---- whole triangular solves in ONE launch ---------------------------------------------------------------------------
+// The step kernels above make a substitution a chain of T dependent launches (10 us each: 0.32 ms of a 1.4 ms evaluation
+// at N = 2048).  Here one CTA owns one 128-row block of one right-hand side for the whole solve: it subtracts
+// L[i][j] u_j as the u_j appear (release / acquire flags in global memory), then applies the inverse of its diagonal tile
+// and publishes u_i.  CTAs take their (item, block) from a ticket counter in dependency order, so every block a CTA waits
+// for has already started: no co-residency requirement.  sync[0] = ticket counter, sync[1 + item*T + block] = flags.
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+trsv_fwd_fused_kernel(const double* __restrict__ L, const double* __restrict__ Dinv, const double* __restrict__ r,
+                      double* __restrict__ u, double* __restrict__ beta, int Np, int T, int* __restrict__ sync,
+                      double* __restrict__ part) {
+  __shared__ int s_t;
+  __shared__ double rs[TS], us[TS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) s_t = atomicAdd(&sync[0], 1);
+  __syncthreads();
+  const int b = s_t / T, i = s_t % T;
+  int* flags = sync + 1 + (long long)b * T;
+  const double* Lb = L + (long long)b * Np * Np;
+  const double* ub = u + (long long)b * Np;
+  if (tid < TS) rs[tid] = r[(long long)b * Np + i * TS + tid];
+  // the inverse of the diagonal tile is needed last and depends on nothing: fetched first
+  double4 dv[16];
+  {
+    const double* Dj = Dinv + ((long long)b * T + i) * TS * TS;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) dv[q] = *reinterpret_cast<const double4*>(Dj + (warp + 8 * q) * TS + lane * 4);
+  }
+  for (int j = 0; j < i; ++j) {
+    // the tile does not depend on the flag: its loads are in flight while this CTA waits
+    const double* Lt = Lb + (long long)i * TS * Np + (long long)j * TS;
+    double4 v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = *reinterpret_cast<const double4*>(Lt + (long long)(warp + 8 * q) * Np + lane * 4);
+    if (tid == 0)
+      while (ld_acquire(flags + j) == 0) {}
+    __syncthreads();
+    if (tid < TS) us[tid] = __ldcg(ub + j * TS + tid);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      double acc = v[q].x * us[lane * 4] + v[q].y * us[lane * 4 + 1] + v[q].z * us[lane * 4 + 2] + v[q].w * us[lane * 4 + 3];
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) rs[warp + 8 * q] -= acc;
+    }
+  }
+  {
+    __syncthreads();                       // rs complete; everybody is past its last read of us
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      double acc = dv[q].x * rs[lane * 4] + dv[q].y * rs[lane * 4 + 1] + dv[q].z * rs[lane * 4 + 2] + dv[q].w * rs[lane * 4 + 3];
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) us[warp + 8 * q] = acc;
+    }
+  }
+  __syncthreads();
+  if (tid < TS) u[(long long)b * Np + i * TS + tid] = us[tid];
+  double mine = 0.0;
+  if (warp == 0) {
+    for (int k = lane; k < TS; k += 32) mine += us[k] * us[k];
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+    if (lane == 0) part[(long long)b * T + i] = mine;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    st_release(flags + i, 1);
+    if (i == T - 1 && beta) {              // every earlier flag of this item has been acquired: add the partial sums in block order
+      double sum = 0.0;
+      for (int k = 0; k < T - 1; ++k) sum += __ldcg(part + (long long)b * T + k);
+      beta[b] += sum + mine;
+    }
+  }
+}
+
+// alpha = L^-T s, blocks from the last to the first: alpha_i = Linv_ii^T (s_i - sum_{j > i} L[j][i]^T alpha_j)
+__global__ void __launch_bounds__(512)
+trsv_bwd_fused_kernel(const double* __restrict__ L, const double* __restrict__ Dinv, const double* __restrict__ s,
+                      double* __restrict__ alpha, int Np, int T, int* __restrict__ sync) {
+  __shared__ int s_t;
+  __shared__ double ss[TS], as[TS], pt[4][TS];
+  const int tid = threadIdx.x;
+  if (tid == 0) s_t = atomicAdd(&sync[0], 1);
+  __syncthreads();
+  const int b = s_t / T, i = T - 1 - s_t % T;
+  int* flags = sync + 1 + (long long)b * T;
+  const double* Lb = L + (long long)b * Np * Np;
+  const double* ab = alpha + (long long)b * Np;
+  const int c = tid & 127, qr = tid >> 7;  // thread = column c, rows qr*32 .. +31 of a tile
+  double dv[32];                           // the inverse of the diagonal tile is needed last and depends on nothing: fetched first
+  {
+    const double* Dj = Dinv + ((long long)b * T + i) * TS * TS;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) dv[q] = Dj[(qr * 32 + q) * TS + c];
+  }
+  double acc = 0.0;                        // this thread's quarter of sum_j (L[j][i]^T alpha_j)[c]
+  for (int j = T - 1; j > i; --j) {
+    // the tile does not depend on the flag: its loads are in flight while this CTA waits
+    const double* Lt = Lb + (long long)j * TS * Np + (long long)i * TS;
+    double t[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) t[q] = Lt[(long long)(qr * 32 + q) * Np + c];
+    if (tid == 0)
+      while (ld_acquire(flags + j) == 0) {}
+    __syncthreads();
+    if (tid < TS) as[tid] = __ldcg(ab + j * TS + tid);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 32; ++q) acc += t[q] * as[qr * 32 + q];
+  }
+  pt[qr][c] = acc;
+  if (tid < TS) ss[tid] = s[(long long)b * Np + i * TS + tid];
+  __syncthreads();
+  if (tid < TS) ss[tid] -= (pt[0][tid] + pt[1][tid]) + (pt[2][tid] + pt[3][tid]);
+  __syncthreads();
+  {
+    double a2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) a2 += dv[q] * ss[qr * 32 + q];
+    pt[qr][c] = a2;
+  }
+  __syncthreads();
+  if (tid < TS) alpha[(long long)b * Np + i * TS + tid] = (pt[0][tid] + pt[1][tid]) + (pt[2][tid] + pt[3][tid]);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) st_release(flags + i, 1);
+}
+
 }  // namespace
 
 static constexpr int kDiagSmem = (TS * LDS_ + 7 * SB * LDT) * (int)sizeof(double);
@@ -877,8 +1014,32 @@ int g3_lauum_batched(g3_ctx* ctx, const double* U, double* Kinv, int Np, int B) 
   return g3_gemm_launch(ctx, tmA, tmB, g, B);
 }
 
+static int* trsv_sync(g3_ctx* ctx, int n, double** part) {
+  char name[64];
+  snprintf(name, sizeof name, "trsv_sync_%p", (void*)ctx->stream);     // per stream: batch groups solve concurrently
+  int* sync = (int*)g3_ws(ctx, name, sizeof(int) * (size_t)(n + 1) + sizeof(double) * (size_t)n + 16);
+  if (!sync) return nullptr;
+  *part = reinterpret_cast<double*>(reinterpret_cast<char*>(sync) + ((sizeof(int) * (size_t)(n + 1) + 15) / 16) * 16);
+  cudaMemsetAsync(sync, 0, sizeof(int) * (size_t)(n + 1), ctx->stream);
+  return sync;
+}
+
+// one launch for few right-hand sides (the chain of launches is what costs there); a big batch keeps the step kernels, whose
+// (T - j) x B CTAs per step are throughput-bound (measured: 2.84 ms against 3.46 ms per step of the N = 4096 x 64 bench)
+static bool trsv_use_fused(const g3_ctx* ctx, int B) { return ctx->trsv_fused && B <= 8; }
+
 int g3_trsv_fwd(g3_ctx* ctx, const double* L, const double* Dinv, double* r, double* u, double* beta, int Np, int B) {
   const int T = Np / TS;
+  if (trsv_use_fused(ctx, B)) {
+    double* part = nullptr;
+    int* sync = trsv_sync(ctx, T * B, &part);
+    if (!sync) return -2;
+    g3_prof_begin(ctx, G3_PROF_TRSV);
+    trsv_fwd_fused_kernel<<<T * B, 256, 0, ctx->stream>>>(L, Dinv, r, u, beta, Np, T, sync, part);
+    g3_prof_end(ctx);
+    G3_LAUNCH_CHECK(ctx);
+    return 0;
+  }
   g3_prof_begin(ctx, G3_PROF_TRSV);
   for (int j = 0; j < T; ++j) {
     trsv_fwd_step_kernel<<<dim3(T - j, B), 256, 0, ctx->stream>>>(L, Dinv, r, u, beta, j, Np, T);
@@ -905,6 +1066,16 @@ int g3_trsv_panel(g3_ctx* ctx, const double* P, int rows, int nb, const double* 
 
 int g3_trsv_bwd(g3_ctx* ctx, const double* L, const double* Dinv, double* s, double* alpha, int Np, int B) {
   const int T = Np / TS;
+  if (trsv_use_fused(ctx, B)) {
+    double* part = nullptr;
+    int* sync = trsv_sync(ctx, T * B, &part);
+    if (!sync) return -2;
+    g3_prof_begin(ctx, G3_PROF_TRSV);
+    trsv_bwd_fused_kernel<<<T * B, 512, 0, ctx->stream>>>(L, Dinv, s, alpha, Np, T, sync);
+    g3_prof_end(ctx);
+    G3_LAUNCH_CHECK(ctx);
+    return 0;
+  }
   g3_prof_begin(ctx, G3_PROF_TRSV);
   for (int j = T - 1; j >= 0; --j) {
     trsv_bwd_step_kernel<<<dim3(j + 1, B), 256, 0, ctx->stream>>>(L, Dinv, s, alpha, j, Np, T);

@@ -131,6 +131,10 @@ int g3_set_splitk(g3_ctx* ctx, int on);
  * evaluations) is bound by one SM's fp64 rate per tile, so each tile is spread over 2 or 4 CTAs (halves / quarters of its
  * columns; same summation order, bitwise identical results) until one CTA per SM is reached.  Default on. */
 int g3_set_tile_split(g3_ctx* ctx, int on);
+/* Triangular solves u = L^-1 r and alpha = L^-T u (gaussian.py:219-231 solve_lower_triangular / the reverse sweep of the
+ * analytic gradient) as ONE launch each: a CTA owns a 128-row block and waits on release / acquire flags for the blocks it
+ * depends on, instead of T = N/128 dependent launches.  Fixed summation order (bitwise reproducible).  Default on. */
+int g3_set_trsv_fused(g3_ctx* ctx, int on);
 /* Gradient path of few large matrices: compute U = L^-T block by block on a third stream while the look-ahead
  * factorisation is still running (default on; results do not depend on it). */
 int g3_set_trtri_pipeline(g3_ctx* ctx, int on);
