@@ -5,18 +5,19 @@ A transport pushes white noise to the observations: y = t_1(t_2(... t_n(eps))), 
 linear piece `TKernel` is the Cholesky factor of a Gram matrix and is where the device path enters
 (`transports.py:200-257`).  `TransportGaussianProcess` (g3py_b200/transport.py) evaluates chains of the form
 
-    [ID | TMapping | TLocation]* @ TKernel
+    [ID | TMapping]* @ [TScale]? @ [ID | TLocation]* @ TKernel
 
 i.e. any number of element-wise transports outside exactly one kernel transport, which is the structure whose
-density is the warped-GP density (`processes/transport.py:214-246`).  `TScale` and `TTriangular`
-(`transports.py:165-181,260-263`; the latter is unfinished in the reference) are not built.
+density is the warped-GP density (`processes/transport.py:214-246`).  `TScale` (`transports.py:165-181`) multiplies by a
+parametric function of the INPUTS; between the warpings and the locations it acts as one more (input-dependent) linear
+warping, y = T(s(x) (m(x) + L eps)).  `TTriangular` (`transports.py:260-263`, unfinished in the reference) is not built.
 """
 from . import Hypers
 from .kernels import Kernel, KernelSum, KernelNoise
 from .mappings import Mapping
 from .means import Mean
 
-__all__ = ["Transport", "TransportComposed", "ID", "TLocation", "TMapping", "TKernel"]
+__all__ = ["Transport", "TransportComposed", "ID", "TLocation", "TMapping", "TKernel", "TScale"]
 
 
 class Transport(Hypers):
@@ -91,6 +92,17 @@ class TLocation(Transport):
             raise TypeError("TLocation needs a Mean")
         self.location = location
         self.parametrics.append(location)
+
+
+class TScale(Transport):
+    """transports.py:165-181: outputs * scale(inputs); inverse outputs / scale(inputs); log|d inv| = -sum log scale(inputs)."""
+
+    def __init__(self, scale=None, x=None, name=None):
+        super().__init__(x, name)
+        if not isinstance(scale, Mean):
+            raise TypeError("TScale needs a Mean (a parametric function of the inputs)")
+        self.scale = scale
+        self.parametrics.append(scale)
 
 
 class TMapping(Transport):

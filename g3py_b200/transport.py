@@ -15,12 +15,68 @@ the device by `g3_potrf_robust`.
 import numpy as np
 
 from . import _cabi as cabi
-from .hypers.mappings import Identity, MappingComposed
+import contextlib
+
+from .hypers.mappings import Identity, Mapping, MappingComposed
 from .hypers.means import MeanSum, Zero
-from .hypers.transports import ID, TKernel, TLocation, TMapping, Transport
+from .hypers.transports import ID, TKernel, TLocation, TMapping, TScale, Transport
 from .processes import DictObj, EllipticalProcess, StochasticProcess
 
 __all__ = ["TransportGaussianProcess", "TGP"]
+
+
+class _ScaleWarp(Mapping):
+    """TScale seen as a warping (transports.py:165-181): y = z * s(x), inv = y / s(x), log|d inv| = -sum log s(x).  It depends
+    on the inputs, which the Mapping interface does not carry: the process sets `.X` to the points the vector lives on (the
+    observed inputs for the density, `space` for a transported draw) around every use."""
+
+    def __init__(self, scale):
+        self.scale = scale
+        self.hypers = []
+        self.name = scale.name
+        self.dims = None
+        self.shape = None
+        self.potential = None
+        self.X = None
+
+    def check_hypers(self, parent="", reg=None):
+        self.scale.check_hypers(parent, reg)
+        self.hypers = list(self.scale.hypers)
+
+    def check_dims(self, x=None):
+        self.scale.check_dims(x)
+
+    def default_hypers_dims(self, x=None, y=None):
+        return self.scale.default_hypers_dims(x, y)
+
+    def _s(self, p):
+        if self.X is None:
+            raise RuntimeError("TScale evaluated without its inputs")
+        return self.scale(self.X, p)
+
+    def __call__(self, z, p):
+        return z * self._s(p)
+
+    def inv(self, y, p):
+        return y / self._s(p)
+
+    def logdet_dinv(self, y, p):
+        return -float(np.sum(np.log(self._s(p))))
+
+    def dinv_dy(self, y, p):
+        return 1.0 / self._s(p)
+
+    def dlog_dinv_dy(self, y, p):
+        return np.zeros(len(y))
+
+    def grads(self, y, p):
+        s = self._s(p)
+        dinv, dld = {}, {}
+        for h, J in self.scale.jacobian(self.X, p).items():       # J = d s / d h: (N,) or (size, N)
+            J = np.asarray(J, dtype=np.float64)
+            dinv[h] = -(y / (s * s)) * J
+            dld[h] = -np.sum(J / s, axis=-1)
+        return dinv, dld
 
 
 class TransportGaussianProcess(EllipticalProcess):
@@ -35,14 +91,22 @@ class TransportGaussianProcess(EllipticalProcess):
         if not isinstance(chain[-1], TKernel) or any(isinstance(t, TKernel) for t in chain[:-1]):
             raise NotImplementedError("supported chains: [ID | TMapping | TLocation]* @ TKernel (one kernel, innermost)")
         kinds = [type(t) for t in chain[:-1]]
-        if any(k not in (ID, TMapping, TLocation) for k in kinds):
-            raise NotImplementedError("only ID, TMapping and TLocation may precede the TKernel")
+        if any(k not in (ID, TMapping, TLocation, TScale) for k in kinds):
+            raise NotImplementedError("only ID, TMapping, TScale and TLocation may precede the TKernel")
         order = [k for k in kinds if k is not ID]
         if TLocation in order and TMapping in order[order.index(TLocation):]:
             raise NotImplementedError("TMapping inside a TLocation is not supported (put the mappings outermost)")
+        if order.count(TScale) > 1 or (TScale in order and (TMapping in order[order.index(TScale):] or
+                                                            TLocation in order[:order.index(TScale)])):
+            raise NotImplementedError("supported: at most one TScale, inside the TMappings and outside the TLocations")
         self.f_transport = transport
         self.n_id = kinds.count(ID)
         maps = [t.mapping for t in chain[:-1] if isinstance(t, TMapping)]
+        self._scale_warp = None
+        for t in chain[:-1]:
+            if isinstance(t, TScale):
+                self._scale_warp = _ScaleWarp(t.scale)
+                maps.append(self._scale_warp)                       # innermost warping: inv = scale.inv(maps.inv(y))
         locs = [t.location for t in chain[:-1] if isinstance(t, TLocation)]
         self.f_mapping = Identity()
         if maps:
@@ -75,6 +139,23 @@ class TransportGaussianProcess(EllipticalProcess):
         # potentials set on the pieces of a transport are never registered in the reference
         self._finish_layout()
 
+    @contextlib.contextmanager
+    def _scale_at(self, X):
+        """The points a TScale is evaluated on while warpings act on a vector living on X."""
+        if self._scale_warp is None:
+            yield
+            return
+        keep = self._scale_warp.X
+        self._scale_warp.X = X
+        try:
+            yield
+        finally:
+            self._scale_warp.X = keep
+
+    def _host_terms(self, nat2d, inputs, outputs, want_grad):
+        with self._scale_at(inputs):
+            return super()._host_terms(nat2d, inputs, outputs, want_grad)
+
     def _eval_batch(self, Theta, inputs=None, outputs=None, want_grad=True, nan_quirk=None):
         ll, g, info = super()._eval_batch(Theta, inputs, outputs, want_grad, nan_quirk)
         if self.n_id:                                         # ID.logdet_dinv = tt.ones(()) (transports.py:129-130)
@@ -101,7 +182,7 @@ class TransportGaussianProcess(EllipticalProcess):
     def _tk_posterior(self, space, pred, nat, p, noise_pred):
         """TKernel.posterior (transports.py:236-257) with noise_obs=True."""
         X, y = self.inputs, self.outputs
-        with np.errstate(all="ignore"):
+        with np.errstate(all="ignore"), self._scale_at(X):
             pre = self.f_mapping.inv(y, p) - self.f_location(X, p)
         Kxx = self._gram(X, None, nat, True)
         u = self._chol_solve(Kxx, pre)
@@ -131,15 +212,18 @@ class TransportGaussianProcess(EllipticalProcess):
         if not prior:
             # TKernel.posterior and TElemwise.posterior ignore their `inv` / `diag` flags: the three posterior
             # selectors coincide in the reference (transports.py:134-136,236-257)
-            return self.f_mapping(self.f_location(space, p) + self._tk_posterior(space, v, nat, p, noise), p)
+            post = self._tk_posterior(space, v, nat, p, noise)
+            with self._scale_at(space):
+                return self.f_mapping(self.f_location(space, p) + post, p)
         if which == "inv":                                    # transports.py:227-232 after the element-wise inverses
-            with np.errstate(all="ignore"):
+            with np.errstate(all="ignore"), self._scale_at(space):
                 pre = self.f_mapping.inv(v, p) - self.f_location(space, p)
             return self._chol_solve(self._gram(space, None, nat, noise), pre)
         K = self._gram(space, None, nat, noise)
         if which == "diag" and not elementwise:               # TKernel.diag (transports.py:218-225)
             return np.sqrt(np.diag(K)) * v
-        return self.f_mapping(self.f_location(space, p) + self._chol(K) @ v, p)
+        with self._scale_at(space):
+            return self.f_mapping(self.f_location(space, p) + self._chol(K) @ v, p)
 
     def transport(self, params=None, space=None, inputs=None, outputs=None, vector=None, prior=False, noise=False,
                   array=False):

@@ -1284,6 +1284,9 @@ class OracleTransportProcess:
             elif t["t"] == "TLocation":
                 obj = _Mean(t["location"], D)
                 hy = obj.layout()
+            elif t["t"] == "TScale":                             # transports.py:165-181
+                obj = _Mean(t["scale"], D)
+                hy = obj.layout()
             elif t["t"] == "TKernel":
                 k = build_kernel(t["kernel"], D)
                 self.f_kernel = k
@@ -1333,6 +1336,8 @@ class OracleTransportProcess:
             return obj.forward(th, v)                            # :190-191
         if kind == "TLocation":
             return v + obj(th, X)                                # :152-156
+        if kind == "TScale":
+            return v * obj(th, X)                                # :171-172
         return cholesky_robust(self._cov(th, X, None, noise), self.consts).dot(v)     # :210-216
 
     def _inv1(self, part, nat, X, v, noise):
@@ -1344,6 +1349,8 @@ class OracleTransportProcess:
             return obj.inv(th, v)                                # :193-194
         if kind == "TLocation":
             return v - obj(th, X)                                # :158-159
+        if kind == "TScale":
+            return v / obj(th, X)                                # :174-175
         return sla.solve_triangular(cholesky_robust(self._cov(th, X, None, noise), self.consts), v, lower=True)  # :227-232
 
     def _logdet1(self, part, nat, X, v):
@@ -1355,6 +1362,8 @@ class OracleTransportProcess:
             return obj.logdet_dinv(th, v)                        # :196-197
         if kind == "TLocation":
             return 0.0                                           # :161-162
+        if kind == "TScale":
+            return -float(np.sum(np.log(obj(th, X))))            # :177-181
         return -float(np.sum(np.log(np.diag(cholesky_robust(self._cov(th, X, None, True), self.consts)))))   # :234-236
 
     # ---- chain (TransportComposed, transports.py:93-119) ---------------------------------------
@@ -1390,6 +1399,16 @@ class OracleTransportProcess:
 
     def dlogp(self, theta, X, y, nan_quirk=False):
         """Gradient through the equivalent warped GP (same density, permuted theta)."""
+        if any(t["t"] == "TScale" for t in self.chain):          # no warped-GP equivalent: 4th-order central differences
+            theta = np.asarray(theta, dtype=np.float64)
+            g = np.zeros(self.P)
+            for k in range(self.P):
+                h = 1e-4 * max(1.0, abs(theta[k]))
+                e = np.zeros(self.P)
+                e[k] = h
+                f = lambda t: self.logp(t, X, y)
+                g[k] = (-f(theta + 2 * e) + 8 * f(theta + e) - 8 * f(theta - e) + f(theta - 2 * e)) / (12 * h)
+            return g
         loc = next((t["location"] for t in self.chain if t["t"] == "TLocation"), {"type": "Zero"})
         mp = next((t["mapping"] for t in self.chain if t["t"] == "TMapping"), {"type": "Identity"})
         tk = self.chain[-1]

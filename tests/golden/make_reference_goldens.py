@@ -96,6 +96,9 @@ def ref_transport(g3, spec, X):
             parts.append(g3.TMapping(getattr(g3, t['mapping']['type'])()))
         elif t['t'] == 'TLocation':
             parts.append(g3.TLocation(getattr(g3, t['location']['type'])(_x_arg(X, t['location'].get('dims')))))
+        elif t['t'] == 'TScale':
+            sc = t['scale']
+            parts.append(g3.TScale(getattr(g3, sc['type'])(_x_arg(X, sc.get('dims')), **({'name': sc['name']} if 'name' in sc else {}))))
         else:
             parts.append(g3.TKernel(ref_kernel(g3, t['kernel'], X), noisy=t.get('noisy', False)))
     tr = parts[0]
@@ -271,6 +274,11 @@ CASES = {
                                                                dict(t='TKernel', kernel=K('sum', k1=K('SE'), k2=K('WN')),
                                                                     noisy=False)]),
                             N=20, D=1, M=6, seed=63),
+    # TScale (transports.py:165-181) between the location and nothing: y = s (m + L eps), s a Bias mean named 'Scale'
+    'tgp_scale':       dict(spec=dict(kind='transport', chain=[dict(t='TScale', scale=K('Bias', name='Scale')),
+                                                               dict(t='TLocation', location=K('Bias')),
+                                                               dict(t='TKernel', kernel=K('SE'), noisy=True)]),
+                            N=24, D=1, M=7, seed=64, theta_shift={'Scale_Bias': 1.2}),
     # tt_to_cov (a5): a negative shift makes the Gram diagonal <= 0, so the reference adds (1e-6 - min diag) I.
     # logp only: Theano differentiates THROUGH the shift, and its max/min gradient gives every tied element the full
     # upstream gradient (all N diagonal entries of a stationary kernel tie), which torch (even split) does not mimic;

@@ -63,6 +63,9 @@ def build_transport(spec, X):
         elif t["t"] == "TMapping":
             mp = t["mapping"]
             parts.append(g3.TMapping(MAPS[mp["type"]](**({"name": mp["name"]} if "name" in mp else {}))))
+        elif t["t"] == "TScale":
+            sc = t["scale"]
+            parts.append(g3.TScale(MEANS[sc["type"]](_x_arg(X, sc.get("dims")), **({"name": sc["name"]} if "name" in sc else {}))))
         elif t["t"] == "TLocation":
             loc = t["location"]
             parts.append(g3.TLocation(MEANS[loc["type"]](_x_arg(X, loc.get("dims")),

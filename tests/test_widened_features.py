@@ -12,6 +12,8 @@ K = lambda t, **kw: dict(type=t, **kw)
 SPECS = {
     "tgp": dict(kind="transport", chain=[dict(t="TMapping", mapping=K("BoxCoxShifted")), dict(t="TLocation", location=K("Bias")),
                                          dict(t="TKernel", kernel=K("SE"), noisy=True)]),
+    "tgp_scale": dict(kind="transport", chain=[dict(t="TMapping", mapping=K("BoxCoxShifted")), dict(t="TScale", scale=K("Bias", name="Scale")),
+                                               dict(t="TLocation", location=K("Bias")), dict(t="TKernel", kernel=K("SE"), noisy=True)]),
     "lin_se": dict(kind="gauss", location=K("Zero"), kernel=K("sum", k1=K("LIN"), k2=K("SE"))),
     "pol3": dict(kind="gauss", location=K("Bias"), kernel=K("sum", k1=K("POL", p=3), k2=K("SE"))),
     "dot_bw_var": dict(kind="gauss", location=K("Zero"), kernel=K("sum", k1=K("sum", k1=K("KernelDot"), k2=K("BW")), k2=K("VAR"))),
@@ -29,7 +31,7 @@ SPECS = {
                                 k2=K("sum", k1=K("scale", c=0.3, k=K("KernelEquals", eq=1.0, dims=[0, 1])),
                                      k2=K("scale", c=0.002, k=K("KernelEquals2", eq1=0.0, eq2=1.0, dims=[0, 1]))))),
 }
-POSITIVE = {"tgp", "warpboxcox", "logistic", "potentials"}
+POSITIVE = {"tgp", "tgp_scale", "warpboxcox", "logistic", "potentials"}
 LOGP_ONLY = {"nn"}
 
 
@@ -46,7 +48,9 @@ def _problem(name, N, B, seed=0):
     th = []
     for nm, size, pos in op.layout():
         v = 0.1 * rng.standard_normal((B, size))
-        if "Noise" in nm:                      # max(k1, k2) is not PSD in general: more noise keeps K definite
+        if nm.endswith("Scale_Bias"):          # the TScale factor must stay positive
+            v += 1.3
+        elif "Noise" in nm:                    # max(k1, k2) is not PSD in general: more noise keeps K definite
             v += np.log((2.0 if name in ("max", "nn", "nil_equals") else 0.05) * np.var(y))
         elif nm.endswith("_var"):
             v += np.log(np.var(y))
