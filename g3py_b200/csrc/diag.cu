@@ -480,6 +480,7 @@ __host__ __device__ constexpr unsigned long long blocks(unsigned b0, unsigned b1
 }
 __device__ __forceinline__ void store_tasks(uint32_t sb, double* __restrict__ At, int Np, double* __restrict__ Dj, int nblk,
                                             unsigned long long code, int w0, int nw, int lane) {
+  if (w0 < 0) return;
   for (int t = w0; t < 4 * nblk; t += nw) {
     const unsigned e = (unsigned)(code >> (5 * (t >> 2))) & 31u;
     store_slab(sb, At, Np, Dj, e & 1, (e >> 1) & 3, (e >> 3) & 3, t & 3, lane);
@@ -527,9 +528,10 @@ potrf_diag2_kernel(double* __restrict__ A, int Np, long long strideA, int j, dou
   __syncthreads();
   G3_STAMP();
 
-  // DMMA fillers: the 12 warps that do not share warp 0's scheduler; warps 4, 8, 12 only move data
+  // the 12 warps that do not share warp 0's scheduler work in the shadow of F; warps 4, 8, 12 stay idle there (anything
+  // issued on warp 0's sub-partition slows the serial factorisation, which is issue-bound)
   const int f = (warp & 3) ? (warp >> 2) * 3 + (warp & 3) - 1 : -1;
-  const int wi = warp - 1;     // index among the 15 warps that are free during F
+  const int wi = f;            // index among those 12 warps (-1: not a shadow worker)
   double ldacc = 0.0;          // warp 15: sum of log L[k][k]
   for (int kb = 0; kb < 4; ++kb) {
     const int o = kb * 32;
@@ -551,47 +553,49 @@ potrf_diag2_kernel(double* __restrict__ A, int Np, long long strideA, int j, dou
       --nstamp;
     } else if (dbg & 1) {
       if (kb == 2 || kb == 3) filler_barrier();   // timing experiment: F alone, nothing in its shadow (results are incomplete)
-    } else if (kb == 0) {
-      // rows 32..127 of the lower triangle (pairs of columns), 13 loads in flight per thread
+    } else if (kb == 0 && wi >= 0) {
+      // rows 32..127 of the lower triangle (pairs of columns), 16 loads in flight per thread of the 12 shadow warps
       const int q0 = wi * 32 + lane;
-      double2 v[13];
+      double2 v[16];
 #pragma unroll
-      for (int it = 0; it < 13; ++it) {
-        const int p = q0 + 480 * it, r = 32 + (p >> 6), c = (p & 63) * 2;
+      for (int it = 0; it < 16; ++it) {
+        const int p = q0 + 384 * it, r = 32 + (p >> 6), c = (p & 63) * 2;
         v[it] = make_double2(0.0, 0.0);
         if (p < 96 * 64 && c <= r) v[it] = __ldg(reinterpret_cast<const double2*>(At + (long long)r * Np + c));
       }
 #pragma unroll
-      for (int it = 0; it < 13; ++it) {
-        const int p = q0 + 480 * it, r = 32 + (p >> 6), c = (p & 63) * 2;
+      for (int it = 0; it < 16; ++it) {
+        const int p = q0 + 384 * it, r = 32 + (p >> 6), c = (p & 63) * 2;
         if (p < 96 * 64 && c <= r) {
           const uint32_t sp = sb + (r * LD + c) * B8;
           sts(sp, v[it].x);
           sts(sp + 8, v[it].y);
         }
       }
+    } else if (kb == 0) {
+      // warps 4, 8, 12: nothing
     } else if (kb == 1) {
       // T[I][0] = L[I][0] Xd_0, I = 1..3 (12 items of 8 x 32)
       if (f >= 0) t_item(sb, 1 + (f >> 2), 0, 0, 1, (f & 3) * 8, lane);
-      store_tasks(sb, At, Np, Dj, 5, blocks(blk(0, 0, 0), blk(0, 1, 0), blk(0, 2, 0), blk(0, 3, 0), blk(1, 0, 0)), wi, 15, lane);
+      store_tasks(sb, At, Np, Dj, 5, blocks(blk(0, 0, 0), blk(0, 1, 0), blk(0, 2, 0), blk(0, 3, 0), blk(1, 0, 0)), wi, 12, lane);
     } else if (kb == 2) {
       // X[1][0] in place (4 items of 32 x 8)  ||  T[I][1] = L[I][1] Xd_1, I = 2, 3 (8 items)
       if (f >= 0 && f < 4) x_item(sb, 1, 0, f * 8, lane);
       else if (f >= 4) t_item(sb, 2 + ((f - 4) >> 2), 1, 1, 1, ((f - 4) & 3) * 8, lane);
-      store_tasks(sb, At, Np, Dj, 4, blocks(blk(0, 1, 1), blk(0, 2, 1), blk(0, 3, 1), blk(1, 1, 1)), wi, 15, lane);
+      store_tasks(sb, At, Np, Dj, 4, blocks(blk(0, 1, 1), blk(0, 2, 1), blk(0, 3, 1), blk(1, 1, 1)), wi, 12, lane);
       filler_barrier();
       // T[I][0] += L[I][1] X[1][0], I = 2, 3
       if (f >= 0 && f < 8) t_item(sb, 2 + (f >> 2), 0, 1, 0, (f & 3) * 8, lane);
-      store_tasks(sb, At, Np, Dj, 1, blocks(blk(1, 1, 0)), wi, 15, lane);
+      store_tasks(sb, At, Np, Dj, 1, blocks(blk(1, 1, 0)), wi, 12, lane);
     } else {
       // X[2][0], X[2][1] in place (8 items)  ||  T[3][2] = L[3][2] Xd_2 (4 items)
       if (f >= 0 && f < 8) x_item(sb, 2, f >> 2, (f & 3) * 8, lane);
       else if (f >= 8) t_item(sb, 3, 2, 2, 1, (f - 8) * 8, lane);
-      store_tasks(sb, At, Np, Dj, 3, blocks(blk(0, 2, 2), blk(0, 3, 2), blk(1, 2, 2)), wi, 15, lane);
+      store_tasks(sb, At, Np, Dj, 3, blocks(blk(0, 2, 2), blk(0, 3, 2), blk(1, 2, 2)), wi, 12, lane);
       filler_barrier();
       // T[3][J] += L[3][2] X[2][J], J = 0, 1
       if (f >= 0 && f < 8) t_item(sb, 3, f >> 2, 2, 0, (f & 3) * 8, lane);
-      store_tasks(sb, At, Np, Dj, 2, blocks(blk(1, 2, 0), blk(1, 2, 1)), wi, 15, lane);
+      store_tasks(sb, At, Np, Dj, 2, blocks(blk(1, 2, 0), blk(1, 2, 1)), wi, 12, lane);
     }
     ++nstamp;
     __syncthreads();
