@@ -190,6 +190,33 @@ def run_reference(args, rank, world):
     emit(line)
 
 
+def single_eval_latency():
+    """One theta per call through the public API (NumPy in / out), the pattern of one NUTS / BFGS chain: wall time of
+    `logp` and of the fused `logp_dlogp` at N = 200 (BASELINE config 1), 1024, 2048, 4096 (config 2 inputs), device default
+    settings (CUDA-graph replay, tile split, one-launch solves)."""
+    import g3py_b200 as g3
+    from g3py_b200 import workloads
+    out = {}
+    for n_obs in (200, 1024, 2048, 4096):
+        x, y = workloads.c1_inputs() if n_obs == 200 else workloads.c2_inputs(n_obs, 1)[:2]
+        gp = g3.GP(x, g3.Bias(), g3.SE(x))
+        gp.observed(x, y)
+        th = gp.dict_to_array(gp.params_default)
+        reps = 40 if n_obs <= 2048 else 12
+        res = []
+        for fn in (lambda: gp.logp(th, array=True), lambda: gp.logp_dlogp(th)):
+            for _ in range(4):
+                fn()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            res.append(1e6 * (time.perf_counter() - t0) / reps)
+        out[str(n_obs)] = {"logp_us": round(res[0], 1), "logp_dlogp_us": round(res[1], 1),
+                           "tflops": round(n_obs ** 3 / res[1] / 1e6, 3)}
+    out["note"] = "wall clock around the public call, host work and copies included; flops = N^3 per logp+grad"
+    return out
+
+
 def op_path_rate(gp, Theta, steps):
     """Value-and-gradient through the Theano Op boundary (GPLogpOp.perform followed by GPLogpGradOp.perform on the
     same inputs, one theta per call - what PyMC3's NUTS / find_MAP drive): evaluations per second, and how many of the
@@ -380,6 +407,11 @@ def main():
                 extras["op_path"] = op_path_rate(gp, Theta, max(args.steps, 2))
         except Exception as e:
             extras["op_path"] = {"error": repr(e)}
+        try:
+            if rank == 0 and world == 1:
+                extras["single_eval_latency"] = single_eval_latency()
+        except Exception as e:
+            extras["single_eval_latency"] = {"error": repr(e)}
         ctx.comm_barrier()
 
     pk = peaks(ctx)
