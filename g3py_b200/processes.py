@@ -82,6 +82,8 @@ class DictObj(dict):
 def tt_to_num(r, nan=0.0, inf=1e10):
     """libs/tensors.py:90-92 applied to host vectors (the gradient scrub of stochastic.py:308-309)."""
     r = np.asarray(r, dtype=np.float64)
+    if np.isfinite(r).all():                 # nothing to scrub (the usual case; saves two np.where per call on the hot path)
+        return r
     return np.where(np.isnan(r), nan, np.where(np.isinf(r), inf, r))
 
 
@@ -214,6 +216,7 @@ class StochasticProcess:
         self.positive_mask = np.zeros(off, dtype=bool)
         for v in self.registry.vars:
             self.positive_mask[v.offset:v.offset + v.size] = v.positive
+        self._pos_idx = np.flatnonzero(self.positive_mask)
 
     @property
     def layout(self):
@@ -247,10 +250,12 @@ class StochasticProcess:
         return out
 
     def natural(self, theta):
-        theta = np.asarray(theta, dtype=np.float64)
-        m = self.positive_mask
-        with np.errstate(over="ignore"):
-            return np.where(m, np.exp(np.where(m, theta, 0.0)), theta)
+        out = np.array(theta, dtype=np.float64)          # a copy: the positive entries are overwritten with their exp
+        idx = self._pos_idx
+        if idx.size:
+            with np.errstate(over="ignore"):
+                out[..., idx] = np.exp(out[..., idx])
+        return out
 
     @property
     def params_test(self):
@@ -368,8 +373,36 @@ class EllipticalProcess(StochasticProcess):
             return float(v[0]) if h.scalar else v
         return p
 
+    def _slot_gather(self):
+        """(theta indices, slot indices) when every free kernel hyper occupies exactly one slot of the compiled descriptor
+        (no shared hypers): the slot <-> theta copies of the hot path become one fancy-indexed assignment each."""
+        hit = self.__dict__.get("_slot_gather_cache")
+        if hit is not None and hit[0] is self._slots:
+            return hit[1]
+        dst, src = [], []
+        for h, off, size, const in self._slots:
+            if h is not None:
+                dst += list(range(h.offset, h.offset + h.size))
+                src += list(range(off, off + size))
+        out = (np.array(dst, dtype=np.intp), np.array(src, dtype=np.intp)) if len(set(dst)) == len(dst) else None
+        self._slot_gather_cache = (self._slots, out)
+        return out
+
     def _kernel_theta(self, nat2d, slots=None, n_theta=None):
         """(B, n_slots) natural-space kernel hypers in the slot order of the compiled descriptor."""
+        if slots is None and n_theta is None:
+            hit = self.__dict__.get("_theta_template")
+            if hit is None or hit[0] is not self._slots:
+                tmpl = np.zeros(max(self.desc.n_theta, 1))
+                for h, off, size, const in self._slots:
+                    if h is None:
+                        tmpl[off:off + size] = const
+                hit = self._theta_template = (self._slots, tmpl)
+            gather = self._slot_gather()
+            if gather is not None:
+                th = np.tile(hit[1], (nat2d.shape[0], 1))
+                th[:, gather[1]] = nat2d[:, gather[0]]
+                return th[:, :self.desc.n_theta]
         slots = self._slots if slots is None else slots
         n_theta = self.desc.n_theta if n_theta is None else n_theta
         B = nat2d.shape[0]
@@ -388,12 +421,14 @@ class EllipticalProcess(StochasticProcess):
         deg = nat2d[:, d.offset] if isinstance(d, HyperVar) else np.full(nat2d.shape[0], float(d))
         return self.f_degree.bound + deg                                  # hypers/__init__.py:159-160
 
-    def logprior_batch(self, Theta):
+    def logprior_batch(self, Theta, nat=None):
         """Free-RV terms (Flat = 0, NonTransformLog barrier -inf at exp(theta) <= 1e-6) plus the `pm.Potential`
         regularisers (stochastic.py:300-306: logp = sum of RV terms + potentials, for prior and posterior alike)."""
-        nat = self.natural(np.atleast_2d(Theta))
-        bad = np.any((nat <= 1e-6) & self.positive_mask[None, :], axis=1)
-        return np.where(bad, -np.inf, 0.0) + self._potentials(nat)[0]
+        if nat is None:
+            nat = self.natural(np.atleast_2d(Theta))
+        bad = (nat[:, self._pos_idx] <= 1e-6).any(axis=1)
+        lp = np.where(bad, -np.inf, 0.0)
+        return lp + self._potentials(nat)[0] if self.registry.potentials else lp
 
     def _potentials(self, nat2d):
         """(sum of potentials (B,), d/d natural hypers (B, P)); hypers/__init__.py:94-109 on natural-space values."""
@@ -454,10 +489,17 @@ class EllipticalProcess(StochasticProcess):
         aff = self._affine_location(inputs) if not map_h else None
         if aff is not None:                        # no free warping hypers, affine location: no per-row Python work
             loc0, J, idx = aff
-            p0 = self._accessor(nat2d[0])
-            with np.errstate(all="ignore"):
-                minv = np.asarray(self.f_mapping.inv(outputs, p0), dtype=np.float64)
-                det = float(self.f_mapping.logdet_dinv(outputs, p0))
+            key = (self._data_version, id(self.f_mapping), id(outputs))
+            hit = self.__dict__.get("_minv_cache")
+            if hit is not None and hit[0] == key:           # the warping has no free hypers: T^-1(y) and its log-Jacobian are constants
+                minv, det = hit[1], hit[2]
+            else:
+                p0 = self._accessor(nat2d[0])
+                with np.errstate(all="ignore"):
+                    minv = np.asarray(self.f_mapping.inv(outputs, p0), dtype=np.float64)
+                    det = float(self.f_mapping.logdet_dinv(outputs, p0))
+                if not self.f_mapping.hypers:               # (a warping with FIXED numeric hypers is constant too, but keep it simple)
+                    self._minv_cache = (key, minv, det)
             rows = nat2d if varying else nat2d[:1]
             tls = _TLS.__dict__.setdefault("delta_buf", {})   # reused per thread: a fresh (B, N) array costs more in page faults
             shp = (rows.shape[0], len(minv))                  # consumed by the device call before this thread's next use
@@ -516,8 +558,9 @@ class EllipticalProcess(StochasticProcess):
         thk = self._kernel_theta(nat)
         res = self.ctx.gp_logp_grad(self.desc, self.KIND, delta, thk, nu=nu, want_grad=want_grad)
         beta, logdet, st = res["beta"], res["logdet"], res["status"]
-        failed = (st & cabi.ST_POTRF_FAILED) != 0
-        if np.any(failed):      # CholeskyRobust.perform fallback L = 1e-10 * I (tensors.py:218-222)
+        clean = not st.any()                                              # no status bit anywhere: the usual case
+        failed = None if clean else (st & cabi.ST_POTRF_FAILED) != 0
+        if not clean and np.any(failed):      # CholeskyRobust.perform fallback L = 1e-10 * I (tensors.py:218-222)
             d2 = np.sum(np.atleast_2d(delta) ** 2, axis=1)
             d2 = np.broadcast_to(d2, (B,))
             beta = np.where(failed, d2 / c.fallback ** 2, beta)
@@ -531,25 +574,35 @@ class EllipticalProcess(StochasticProcess):
                 r2 = np.where(nu >= 1e6, -n * 0.5 * c.log_2pi_student,
                               gammaln((nu + n) * 0.5) - gammaln(nu * 0.5) - 0.5 * n * np.log((nu - 2.0) * c.pi))
                 ll = r1 + r2 + (-logdet) + det_m
-        # guards (gaussian.py:234-241): non-finite delta / det_m / L / lcho -> float32(-1e30)
-        dev_bad = ((st & cabi.ST_NONFINITE_RESULT) != 0) & ~failed          # fallback items: L = 1e-10*I is finite
-        bad = dev_bad | ~np.isfinite(det_m) | ~np.isfinite(beta) | ~np.isfinite(logdet)
-        ll = np.where(bad, c.guard, ll)
-        info = {"beta": beta, "logdet": logdet, "det_m": det_m, "status": st, "nu": nu}
+            # guards (gaussian.py:234-241): non-finite delta / det_m / L / lcho -> float32(-1e30)
+            finite = np.isfinite(det_m + beta + logdet)                   # any non-finite term makes the sum non-finite
+        if clean and finite.all():
+            bad = None
+        else:
+            if failed is None:
+                failed = np.zeros(B, dtype=bool)
+            dev_bad = ((st & cabi.ST_NONFINITE_RESULT) != 0) & ~failed      # fallback items: L = 1e-10*I is finite
+            bad = dev_bad | ~np.isfinite(det_m) | ~np.isfinite(beta) | ~np.isfinite(logdet)
+            ll = np.where(bad, c.guard, ll)
+        info = {"beta": beta, "logdet": logdet, "det_m": det_m, "status": st, "nu": nu, "nat": nat}
         self.executed["logp"] += B
         if not want_grad:
             return ll, None, info
         self.executed["dlogp"] += B
-        if np.any(st & cabi.ST_DIAG_SHIFT):
+        if not clean and np.any(st & cabi.ST_DIAG_SHIFT):
             # tensors.py:95-98 differentiates through m = min(diag K); the shift enters the gradient here as a constant
             warnings.warn("dlogp: the tt_to_cov diagonal shift is active (min diag K <= 0) for %d item(s); the gradient "
                           "treats the shift as a constant (logp parity only in this regime)"
                           % int(np.count_nonzero(st & cabi.ST_DIAG_SHIFT)), RuntimeWarning, stacklevel=3)
         g_nat = np.zeros((B, self.ndim))
         dth, ddl = res["dtheta"], res["ddelta"]
-        for h, off, size, const in self._slots:
-            if h is not None:
-                g_nat[:, h.offset:h.offset + h.size] += dth[:, off:off + size]
+        gather = self._slot_gather()
+        if gather is not None:                                            # every free hyper sits in exactly one slot
+            g_nat[:, gather[0]] = dth[:, gather[1]]
+        else:
+            for h, off, size, const in self._slots:
+                if h is not None:
+                    g_nat[:, h.offset:h.offset + h.size] += dth[:, off:off + size]
         if isinstance(jac, tuple):                                        # affine location: d delta / d loc = -J
             _, J, idx = jac
             if len(idx):
@@ -569,8 +622,10 @@ class EllipticalProcess(StochasticProcess):
                 d_r2 = np.where(nu >= 1e6, 0.0,
                                 0.5 * digamma((nu + n) * 0.5) - 0.5 * digamma(nu * 0.5) - 0.5 * n / (nu - 2.0))
             g_nat[:, self.f_degree.degree.offset] += d_r1 + d_r2
-        g = np.where(self.positive_mask[None, :], g_nat * nat, g_nat)     # chain rule through exp
-        g[failed | bad] = 0.0
+        g = g_nat                                                         # chain rule through exp, in place
+        g[:, self._pos_idx] *= nat[:, self._pos_idx]
+        if bad is not None:
+            g[failed | bad] = 0.0
         if self.registry.potentials:                                      # potentials do not depend on the data
             gp_nat = self._potentials(nat)[1]
             g = g + np.where(self.positive_mask[None, :], gp_nat * nat, gp_nat)
@@ -605,8 +660,8 @@ class EllipticalProcess(StochasticProcess):
         return g[0]
 
     def logp_dlogp(self, theta, reference_nan_quirk=None):
-        ll, g, _ = self._eval_batch(theta, want_grad=True, nan_quirk=reference_nan_quirk)
-        return float(self.logprior_batch(theta)[0] + ll[0]), g[0]
+        ll, g, info = self._eval_batch(theta, want_grad=True, nan_quirk=reference_nan_quirk)
+        return float(self.logprior_batch(theta, info["nat"])[0] + ll[0]), g[0]
 
     # batched entries replacing the per-theta loops of stochastic.py:515-564
     def logp_batch(self, Theta, prior=False):
@@ -624,7 +679,7 @@ class EllipticalProcess(StochasticProcess):
     def logp_dlogp_batch(self, Theta, reference_nan_quirk=None):
         Theta = np.atleast_2d(Theta)
         ll, g, info = self._eval_batch(Theta, want_grad=True, nan_quirk=reference_nan_quirk)
-        return self.logprior_batch(Theta) + ll, g, info
+        return self.logprior_batch(Theta, info["nat"]) + ll, g, info
 
     def logp_chain(self, chain, prior=False):
         """stochastic.py:515-520, vectorised (the reference's own TODO)."""
