@@ -41,6 +41,12 @@ class Mapping(Hypers):
         """({HyperVar: d inv/d h (n,)}, {HyperVar: d logdet/d h}) in natural space."""
         return {}, {}
 
+    def batch_terms(self, y, col, want_grad):
+        """Optional vectorised form of (inv, logdet_dinv, grads) for a batch of hyper rows: `col(h)` is the (B,) column of
+        natural-space values of hyper h.  Returns (inv (B, n), logdet (B,), {h: d inv/d h (B, n)}, {h: d logdet/d h (B,)})
+        or None when the map has no such form (the caller then loops over the rows)."""
+        return None
+
     def dinv_dy(self, y, p):
         """d inv / d y (n,), needed to chain composed maps."""
         raise NotImplementedError
@@ -312,6 +318,29 @@ class _BoxCox(Mapping):
         return d_shift, d_scale, d_power, ld_shift, power * n / scale, ld_power
 
 
+def _boxcox_batch(y, shift, scale, power, thr, want_grad):
+    """The Box-Cox family for (B, 1) columns of hypers: one log and one exp pass over the (B, n) block serve the inverse, the
+    log-Jacobian and every derivative (|sh|^(power-1) = exp((power-1) log|sh|)).  None if any row takes the log branch."""
+    if np.any(power < thr):
+        return None
+    ys = y[None, :] + shift
+    sh = scale * ys
+    a = np.abs(sh)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        la = np.log(a)
+        ap1 = np.exp((power - 1.0) * la)
+        sp = np.sign(sh) * (ap1 * a)
+        inv = (sp - 1.0) / power
+        if not want_grad:
+            return inv, la, None
+        d_shift = ap1 * scale
+        d_scale = ap1 * ys
+        d_power = (sp * la * power - (sp - 1.0)) / (power * power)
+        ld_shift = (power[:, 0] - 1.0) * np.sum(1.0 / ys, axis=1)
+        ld_power = np.sum(la, axis=1)
+    return inv, la, (d_shift, d_scale, d_power, ld_shift, ld_power)
+
+
 class BoxCoxShifted(_BoxCox):        # mappings.py:152-179
     def __init__(self, y=None, name="BoxShift", shift=None, power=None):
         super().__init__(y, name)
@@ -340,6 +369,20 @@ class BoxCoxShifted(_BoxCox):        # mappings.py:152-179
     def grads(self, y, p):
         d_shift, _, d_power, ld_shift, _, ld_power = self._grads(y, p)
         return {self.shift: d_shift, self.power: d_power}, {self.shift: ld_shift, self.power: ld_power}
+
+    def batch_terms(self, y, col, want_grad):
+        if not (isinstance(self.shift, HyperVar) and isinstance(self.power, HyperVar)):
+            return None
+        shift, power = col(self.shift)[:, None], col(self.power)[:, None]
+        out = _boxcox_batch(np.asarray(y, dtype=np.float64), shift, 1.0, power, 1e-5, want_grad)
+        if out is None:
+            return None
+        inv, la, d = out
+        logdet = (power[:, 0] - 1.0) * np.sum(la, axis=1)          # scale = 1: log|y + shift| = la
+        if d is None:
+            return inv, logdet, {}, {}
+        d_shift, _, d_power, ld_shift, ld_power = d
+        return inv, logdet, {self.shift: d_shift, self.power: d_power}, {self.shift: ld_shift, self.power: ld_power}
 
 
 class BoxCoxLinear(_BoxCox):         # mappings.py:182-215

@@ -520,6 +520,16 @@ class EllipticalProcess(StochasticProcess):
                 buf[:] = loc0
             np.subtract(minv, buf, out=buf)
             return (buf if varying else buf[0]), np.full(B, det), ("affine", J, idx), varying
+        if varying and map_h:
+            # every row has its own warping hypers: one vectorised pass when the map offers it and the location is affine
+            aff = self._affine_location(inputs)
+            if aff is not None:
+                loc0, J, idx = aff
+                bt = self.f_mapping.batch_terms(outputs, lambda h: nat2d[:, h.offset], want_grad)
+                if bt is not None:
+                    inv, det_m, dinv, dld = bt
+                    loc = loc0 + nat2d[:, idx] @ J if len(idx) else loc0
+                    return inv - loc, det_m, ("batch", J, idx, dinv, dld), True
         rows = B if varying else 1
         delta = np.empty((rows, len(outputs)))
         det_m = np.empty(rows)
@@ -604,9 +614,12 @@ class EllipticalProcess(StochasticProcess):
                 if h is not None:
                     g_nat[:, h.offset:h.offset + h.size] += dth[:, off:off + size]
         if isinstance(jac, tuple):                                        # affine location: d delta / d loc = -J
-            _, J, idx = jac
+            J, idx = jac[1], jac[2]
             if len(idx):
                 g_nat[:, idx] += -(ddl @ J.T)
+            if jac[0] == "batch":                                         # vectorised warping terms (scalar hypers)
+                for h, Jm in jac[3].items():
+                    g_nat[:, h.offset] += np.einsum("bn,bn->b", Jm, ddl) + jac[4][h]
             jac = []
         for b in range(B if jac else 0):
             jl, dinv, dld = jac[b if varying else 0]
