@@ -68,6 +68,7 @@ SIGNATURES = {
     "g3_set_diag_variant": (C.c_int, [_ctxp, C.c_int]),
     "g3_set_tile_split": (C.c_int, [_ctxp, C.c_int]),
     "g3_set_trsv_fused": (C.c_int, [_ctxp, C.c_int]),
+    "g3_set_speculate_grad": (C.c_int, [_ctxp, C.c_int]),
     "g3_debug_diag_time": (C.c_int, [_ctxp, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_float),
                                      C.POINTER(C.c_longlong), _dp]),
     "g3_set_stream": (C.c_int, [_ctxp, C.c_void_p]),
@@ -228,6 +229,10 @@ class Context:
     def set_splitk(self, on):
         """0 off, 1 (default) at least 128 of the contraction per share, 2 shares down to 32 and triangular solves too (measured slower)."""
         self._ck(self._lib.g3_set_splitk(self._h, int(on)), "g3_set_splitk")
+
+    def set_speculate_grad(self, on):
+        """logp-only evaluations also prepare U = L^-T for a gradient that follows (gp_grad_resume); default off."""
+        self._ck(self._lib.g3_set_speculate_grad(self._h, int(bool(on))), "g3_set_speculate_grad")
 
     def set_trsv_fused(self, on):
         """Whole triangular solves in one launch (default on); off = one launch per 128-row block."""

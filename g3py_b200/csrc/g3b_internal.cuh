@@ -32,6 +32,7 @@ struct g3_gp_state {
   g3_kernel_desc desc;
   int kind = 0, B = 0, want_grad = 0, delta_stride = 0, valid = 0;
   int factor_resident = 0;     // L, Dinv, u of the last logp-only evaluation are still in the workspaces
+  int trtri_spec = 0;          // ... and U = L^-T too: it was pipelined behind that factorisation (g3_set_speculate_grad)
 };
 
 struct g3_ctx {
@@ -74,6 +75,8 @@ struct g3_ctx {
   int trtri_pipeline = 1, trtri_done = 0;
   int force_left = 0;                  // set by g3_gp_run for batches of more than 8 items (their stream groups hold 8)
   int splitk = 1;                      // allow split-K for few-tile / deep-K GEMM launches (g3_set_splitk)
+  int speculate_grad = 0;              // logp-only evaluations of <= 8 matrices also pipeline U = L^-T behind the factorisation
+  int graph_trtri_spec = 0;            // whether the cached graph of such an evaluation contains that pipeline
   int trsv_fused = 1;                  // whole triangular solves in one launch (flags between CTAs) instead of T dependent launches
   int tile_split = 1;                  // spread each output tile of a few-tile GEMM launch over 2 / 4 CTAs by columns (g3_set_tile_split)
   struct g3_dist* dist = nullptr;      // multi-GPU state (dist.cu): NCCL communicator, block-cyclic panels

@@ -216,7 +216,7 @@ static int gp_alloc(g3_ctx* ctx, GpBufs& w, int B, int P, int N, int want_grad, 
   WS(bmap, "gp_bmap", sizeof(int) * B);
   w.partials = nullptr;
   w.partials_per_item = 0;
-  if (want_grad) {
+  if (want_grad || (ctx->speculate_grad && B <= 8)) {
     WS(U, "gp_U", mat);
     w.partials_per_item = (size_t)T * (T + 1) / 2 * (P > 0 ? P : 1);
     WS(partials, "gp_vjp_partials", sizeof(double) * (size_t)B * w.partials_per_item);
@@ -309,8 +309,11 @@ static int gp_build_and_factor(g3_ctx* ctx, GpBufs& w, int B, const double* shif
   a.status = w.status; a.bmap = bmap;
   int rc;
   if ((rc = g3_gram_launch(ctx, st.desc, a, bmap ? nb : B))) return rc;
+  // U = L^-T pipelined behind the factorisation: when the gradient follows in this call, or (g3_set_speculate_grad) when the
+  // caller announced that it will ask for it right after a logp-only evaluation (g3_gp_grad_resume)
+  const bool spec = ctx->speculate_grad && !st.want_grad && B <= 8;
   return g3_potrf_batched(ctx, w.A, Np, B, w.Dinv, w.logdet, w.info, bmap, nb, ctx->potrf_w,
-                          (st.want_grad && !bmap) ? w.U : nullptr);
+                          ((st.want_grad || spec) && !bmap) ? w.U : nullptr);
 }
 
 extern "C" {
@@ -327,6 +330,11 @@ int g3_set_lookahead(g3_ctx* ctx, int on) {
 
 int g3_set_trtri_pipeline(g3_ctx* ctx, int on) {
   ctx->trtri_pipeline = on ? 1 : 0;
+  return 0;
+}
+
+int g3_set_speculate_grad(g3_ctx* ctx, int on) {
+  ctx->speculate_grad = on ? 1 : 0;        // part of the graph key: no need to drop the cached graph
   return 0;
 }
 
@@ -377,6 +385,7 @@ int g3_gp_upload(g3_ctx* ctx, const g3_kernel_desc* desc, int kind, const double
   const int drows = delta_stride ? B : 1;
   if ((rc = gp_alloc(ctx, w, B, P, N, want_grad, drows))) return rc;
   ctx->gp.factor_resident = 0;
+  ctx->gp.trtri_spec = 0;
   ctx->gp.desc = *desc;
   ctx->gp.kind = kind;
   ctx->gp.B = B;
@@ -412,7 +421,7 @@ static std::string gp_graph_key(const g3_ctx* ctx) {
   const g3_gp_state& st = ctx->gp;
   std::string k((const char*)&st.desc, sizeof st.desc);
   long long v[] = {st.kind, st.B, st.want_grad, st.delta_stride, ctx->N, ctx->D, ctx->potrf_w, ctx->lookahead, ctx->splitk,
-                   ctx->trtri_pipeline, ctx->gemm_mode, ctx->oz_min_k, ctx->n_groups, (long long)ctx->ws_gen,
+                   ctx->speculate_grad, ctx->tile_split, ctx->trsv_fused, ctx->diag_variant, ctx->trtri_pipeline, ctx->gemm_mode, ctx->oz_min_k, ctx->n_groups, (long long)ctx->ws_gen,
                    (long long)(intptr_t)ctx->dX, (long long)(intptr_t)ctx->stream};
   k.append((const char*)v, sizeof v);
   k.append((const char*)&ctx->jitter_rel, sizeof(double));
@@ -446,6 +455,7 @@ int g3_gp_run(g3_ctx* ctx) {
     G3_CUDA(ctx, cudaGraphLaunch((cudaGraphExec_t)ctx->graph_exec, ctx->stream));
     ctx->launches += ctx->graph_launches;
     ctx->graph_replays++;
+    ctx->gp.trtri_spec = ctx->graph_trtri_spec;
     return 0;
   }
   if (key != ctx->graph_warm_key) {                             // first call with this key: plain run (allocations, attributes)
@@ -480,6 +490,7 @@ int g3_gp_run(g3_ctx* ctx) {
   ctx->graph_exec = exec;
   ctx->graph_key = key;
   ctx->graph_launches = ctx->launches - l0;
+  ctx->graph_trtri_spec = ctx->gp.trtri_spec;
   G3_CUDA(ctx, cudaGraphLaunch(exec, s));
   return 0;
 }
@@ -507,6 +518,10 @@ static int gp_run_body(g3_ctx* ctx) {
   if (groups == 1) {
     rc = gp_build_and_factor(ctx, w, B, w.shift, nullptr, 0);
     if (!rc) rc = gp_after_potrf(ctx, w, B);
+    if (!st.want_grad) {                   // speculative U (if any) belongs to the resident factor, not to the next call
+      ctx->gp.trtri_spec = rc ? 0 : ctx->trtri_done;
+      ctx->trtri_done = 0;
+    }
     ctx->force_left = 0;
     return rc;
   }
@@ -548,6 +563,7 @@ int g3_gp_download(g3_ctx* ctx, double* beta, double* logdet, double* dtheta_or_
     if (info[b] != 0) failed.push_back(b);
   std::vector<int> tries(B, 0), exhausted(B, 0);
   if (!failed.empty()) {
+    ctx->gp.trtri_spec = 0;                // the ladder refactors: a speculative U of the first pass is stale
     // CholeskyRobust._cholesky ladder (tensors.py:203-213): dK = mean(diag K) * jitter, x10 per try.
     std::vector<double> dmean(B), shift(B), dK(B), sh2(B);
     G3_CUDA(ctx, cudaMemcpyAsync(dmean.data(), w.dmean, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream));
@@ -635,7 +651,8 @@ int g3_gp_grad_resume(g3_ctx* ctx, double* dtheta, double* ddelta) {
   int rc;
   if ((rc = gp_alloc(ctx, w, B, P, N, 1, st.delta_stride ? B : 1))) return rc;
   ctx->gp.factor_resident = 0;                     // K^-1 is about to overwrite L
-  ctx->trtri_done = 0;
+  ctx->trtri_done = ctx->gp.trtri_spec;            // U already there (pipelined behind the logp-only factorisation)?
+  ctx->gp.trtri_spec = 0;
   ctx->force_left = B > 8;
   rc = gp_grad_stage(ctx, w, B);
   ctx->force_left = 0;

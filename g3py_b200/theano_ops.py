@@ -207,7 +207,15 @@ def build_ops(theano=None):
             ctx = _ctx(self.device)
             ctx.set_data_if_changed(X)
             nu_a = np.atleast_1d(np.asarray(nu, dtype=np.float64)) if self.kind == cabi.KIND_STUDENT else None
-            r = ctx.gp_logp_grad(self.desc, self.kind, delta, theta, nu=nu_a, want_grad=False)
+            # the gradient Op of the same inputs normally follows (NUTS, BFGS): have U = L^-T prepared behind the factorisation
+            spec = getattr(ctx, "set_speculate_grad", None)
+            if spec is not None:
+                spec(1)
+            try:
+                r = ctx.gp_logp_grad(self.desc, self.kind, delta, theta, nu=nu_a, want_grad=False)
+            finally:
+                if spec is not None:
+                    spec(0)
             ctx._op_last = {"status": r["status"], "beta": r["beta"]}      # GPLogpGradOp may finish from this factor
             beta, logdet, st = float(r["beta"][0]), float(r["logdet"][0]), int(r["status"][0])
             n = float(len(delta))

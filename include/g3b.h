@@ -135,6 +135,11 @@ int g3_set_tile_split(g3_ctx* ctx, int on);
  * analytic gradient) as ONE launch each: a CTA owns a 128-row block and waits on release / acquire flags for the blocks it
  * depends on, instead of T = N/128 dependent launches.  Fixed summation order (bitwise reproducible).  Default on. */
 int g3_set_trsv_fused(g3_ctx* ctx, int on);
+/* Value-then-gradient callers (the Theano Ops: GPLogpOp.perform followed by GPLogpGradOp.perform on the same inputs, what
+ * NUTS / BFGS drive through libs/tensors.py:174-263): with on = 1 a logp-only evaluation of <= 8 matrices also computes
+ * U = L^-T behind its factorisation (side stream, as the fused value-and-gradient call does), so that g3_gp_grad_resume
+ * starts from it.  Wasted work if no gradient follows; default off. */
+int g3_set_speculate_grad(g3_ctx* ctx, int on);
 /* Gradient path of few large matrices: compute U = L^-T block by block on a third stream while the look-ahead
  * factorisation is still running (default on; results do not depend on it). */
 int g3_set_trtri_pipeline(g3_ctx* ctx, int on);
