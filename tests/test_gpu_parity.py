@@ -790,6 +790,42 @@ def test_gradient_resumed_from_resident_factor(ctx, N, B):
     assert not c.resident_matches(gp.desc, cabi.KIND_GAUSS, delta, thk, None)
 
 
+@pytest.mark.parametrize("N,B,ladder", [(600, 1, False), (1100, 2, False), (300, 1, True), (520, 3, True)])
+def test_gradient_resumed_with_speculative_inverse(ctx, N, B, ladder):
+    """g3_set_speculate_grad: a logp-only evaluation that also pipelines U = L^-T behind its factorisation (what
+    GPLogpOp.perform asks for) followed by g3_gp_grad_resume gives the fused gradient - several times in a row (CUDA-graph
+    replay of the speculative sequence) and also when the jitter ladder refactors after the speculative pass (duplicated
+    inputs without noise: the U of the first, failed pass must not be used)."""
+    X, y, Theta = orc.c2_inputs(N, B)
+    spec = SPECS["C2"]
+    if ladder:
+        X = X.copy()
+        X[N // 2:] = X[:N - N // 2]
+        spec = {"kind": "gauss", "location": {"type": "Zero"}, "kernel": {"type": "SE"}, "noisy": False}
+    gp = build_process(spec, X)
+    gp.observed(X, y)
+    Theta = np.tile(gp.dict_to_array(gp.params_default), (B, 1)) + 0.01 * np.arange(B)[:, None] if ladder else Theta
+    nat = gp.natural(Theta)
+    delta, _, _, _ = gp._host_terms(nat, X, y, False)
+    delta = np.array(delta)
+    thk = gp._kernel_theta(nat)
+    c = gp.ctx
+    full = c.gp_logp_grad(gp.desc, cabi.KIND_GAUSS, delta, thk, want_grad=True)
+    if ladder:
+        assert np.all(full["status"] & cabi.ST_JITTER)
+    c.set_speculate_grad(1)
+    try:
+        for rep in range(4):                                 # plain run, capture, replays
+            lo = c.gp_logp_grad(gp.desc, cabi.KIND_GAUSS, delta, thk, want_grad=False)
+            dth, ddl = c.gp_grad_resume()
+            assert np.array_equal(lo["status"], full["status"])
+            assert scaled_err(lo["logdet"], full["logdet"]) < 1e-13 and scaled_err(lo["beta"], full["beta"]) < 1e-12
+            tol = 1e-6 if ladder else 1e-12                  # singular up to the jitter: the two schedules differ by conditioning
+            assert scaled_err(dth, full["dtheta"]) < tol and scaled_err(ddl, full["ddelta"]) < tol, rep
+    finally:
+        c.set_speculate_grad(0)
+
+
 def test_threads_get_their_own_context():
     """Contexts are per thread (a g3_ctx is not re-entrant and ctypes releases the GIL): four threads evaluating
     different hyper samples on the SAME process object concurrently give exactly the sequential results
