@@ -23,11 +23,23 @@ def _vec(p, h, n):
     return np.broadcast_to(np.asarray(p(h) if isinstance(h, HyperVar) else h, dtype=np.float64).reshape(-1), (n,))
 
 
+def _signed_root(sc, power):
+    """sign(sc) |sc|^(1/power) as exp(log|sc| / power): about a third of the time of NumPy's float pow on the 1e5-element
+    grids of the Gauss-Hermite moments (same value to a few ulp; 0 stays 0, inf stays inf)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.sign(sc) * np.exp(np.log(np.abs(sc)) / power)
+
+
 def _tt_to_num(r):
     return np.where(np.isnan(r), 0.0, np.where(np.isinf(r), 1e10, r))
 
 
 class Mapping(Hypers):
+    # True when the forward map acts on every element independently (closed forms).  The Newton-inverse warpings iterate on the
+    # WHOLE vector with one stopping test (libs/tensors.py:134-171), so their value at a point depends on what else is in the
+    # vector: callers that want the reference's numbers must hand them the same vectors the reference does.
+    elementwise_forward = True
+
     def __call__(self, z, p):
         raise NotImplementedError
 
@@ -72,6 +84,10 @@ class Mapping(Hypers):
 
 
 class MappingComposed(Mapping):      # mappings.py:56-71
+    @property
+    def elementwise_forward(self):
+        return self.m1.elementwise_forward and self.m2.elementwise_forward
+
     def __init__(self, m1, m2):
         self.m1, self.m2 = m1, m2
         self.hypers = []
@@ -133,6 +149,8 @@ class MappingInvSum(MappingComposed):   # mappings.py:73-85: inv(y) = m1.inv(y) 
     numeric log-Jacobian sum(log(diag(jacobian(inv)))) (`mappings.py:17-22`): for element-wise maps that is
     sum(log(m1.inv'(y) + m2.inv'(y))).  The forward map has no closed form; it is obtained like the Newton warpings
     (`inverse_function`, libs/tensors.py:134-171: damped Newton, step 0.1, tolerance 1e-3 on the whole vector)."""
+
+    elementwise_forward = False          # forward map by the whole-vector Newton iteration
 
     def __init__(self, m1, m2):
         super().__init__(m1, m2)
@@ -359,7 +377,7 @@ class BoxCoxShifted(_BoxCox):        # mappings.py:152-179
     def __call__(self, z, p):
         shift, _, power, _ = self._params(p)
         sc = power * z + 1.0
-        return np.sign(sc) * np.abs(sc) ** (1.0 / power) - shift
+        return _signed_root(sc, power) - shift
 
     def logdet_dinv(self, y, p):
         shift, _, power, _ = self._params(p)
@@ -404,7 +422,7 @@ class BoxCoxLinear(_BoxCox):         # mappings.py:182-215
     def __call__(self, z, p):
         shift, scale, power, _ = self._params(p)
         sc = power * z + 1.0
-        return np.sign(sc) * np.abs(sc) ** (1.0 / power) / scale - shift
+        return _signed_root(sc, power) / scale - shift
 
     def logdet_dinv(self, y, p):
         shift, scale, power, _ = self._params(p)
@@ -436,7 +454,7 @@ class BoxCoxLinear2(Mapping):        # mappings.py:218-251: shifted = scale * y 
     def __call__(self, z, p):
         shift, scale, power = self._params(p)
         sc = power * z + 1.0
-        return (np.sign(sc) * np.abs(sc) ** (1.0 / power) - shift) / scale
+        return (_signed_root(sc, power) - shift) / scale
 
     def inv(self, y, p):
         shift, scale, power = self._params(p)
@@ -610,6 +628,8 @@ class Logistic(Mapping):             # mappings.py:363-397
 
 
 class _NewtonWarping(Mapping):
+    elementwise_forward = False
+
     """Warpings given by their inverse only: the forward map is `inverse_function(self.inv, z)` (mappings.py:11-12,
     libs/tensors.py:134-145) -- a damped Newton iteration from 0 (step 0.1, slopes below 1 replaced by their sign)
     stopped when max|inv(x) - z| < 1e-3 over the whole vector.  Reproduced literally, so T(z) carries the reference's

@@ -79,6 +79,34 @@ class DictObj(dict):
         return DictObj(self.copy())
 
 
+_HERMGAUSS10 = np.polynomial.hermite.hermgauss(10)     # gaussian.py:127-174 uses 10 nodes; computing them costs 0.45 ms per call
+
+
+def _gauss_hermite_moments(T, mu, sd, block=8192):
+    """E[T(z)] and E[T(z)^2] for z ~ N(mu, sd^2) by the reference's 10-node Gauss-Hermite rule (gaussian.py:127-174:
+    grid mu + sd sqrt(2) a_k, weights w_k / sqrt(pi)).  The grid is walked node by node in blocks of points, so every
+    temporary stays below glibc's mmap threshold: the one-shot (10, M) formulation spends most of its time in page faults
+    of fresh 800 KB arrays (3.6 ms for M = 10 000 against 1 ms)."""
+    a, w = _HERMGAUSS10
+    M = len(mu)
+    m1, m2 = np.empty(M), np.empty(M)
+    c = 1.0 / np.sqrt(np.pi)
+    r2 = np.sqrt(2.0)
+    for i0 in range(0, M, block):
+        sl = slice(i0, min(i0 + block, M))
+        mu_b, sd_b = mu[sl], sd[sl] * r2
+        s1 = np.zeros(len(mu_b))
+        s2 = np.zeros(len(mu_b))
+        for k in range(len(a)):
+            tg = np.asarray(T(mu_b + sd_b * a[k]), dtype=np.float64)
+            s1 += w[k] * tg
+            tg *= tg
+            s2 += w[k] * tg
+        m1[sl] = s1 * c
+        m2[sl] = s2 * c
+    return m1, m2
+
+
 def tt_to_num(r, nan=0.0, inf=1e10):
     """libs/tensors.py:90-92 applied to host vectors (the gradient scrub of stochastic.py:308-309)."""
     r = np.asarray(r, dtype=np.float64)
@@ -770,11 +798,14 @@ class EllipticalProcess(StochasticProcess):
         scaling = 1.0 if prior else self._scaling(post, nat)
         values = DictObj()
         if self.WARPED:                                                      # gaussian.py:127-174
-            a, w = np.polynomial.hermite.hermgauss(10)
-            grille = mu[None, :] + sd[None, :] * np.sqrt(2.0) * a[:, None]
-            tg = T(grille.ravel()).reshape(grille.shape)
-            m1 = w.dot(tg) / np.sqrt(np.pi)
-            m2 = w.dot(tg ** 2) / np.sqrt(np.pi)
+            if getattr(self.f_mapping, "elementwise_forward", False):
+                m1, m2 = _gauss_hermite_moments(T, mu, sd)
+            else:          # Newton-inverse warpings: the whole (10, M) grid in ONE call, as the reference hands it over
+                a, w = _HERMGAUSS10
+                grille = mu[None, :] + sd[None, :] * np.sqrt(2.0) * a[:, None]
+                tg = T(grille.ravel()).reshape(grille.shape)
+                m1 = w.dot(tg) / np.sqrt(np.pi)
+                m2 = w.dot(tg ** 2) / np.sqrt(np.pi)
             v_mean, v_var = m1, m2 - m1 ** 2
         else:                                                                # elliptical.py:194-200, studentT.py:45-46
             v_mean, v_var = T(mu), kd * scaling

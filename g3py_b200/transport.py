@@ -30,6 +30,8 @@ class _ScaleWarp(Mapping):
     on the inputs, which the Mapping interface does not carry: the process sets `.X` to the points the vector lives on (the
     observed inputs for the density, `space` for a transported draw) around every use."""
 
+    elementwise_forward = False          # tied to the points in `.X`: the vector cannot be cut into blocks
+
     def __init__(self, scale):
         self.scale = scale
         self.hypers = []
