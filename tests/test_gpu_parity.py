@@ -826,6 +826,29 @@ def test_gradient_resumed_with_speculative_inverse(ctx, N, B, ladder):
         c.set_speculate_grad(0)
 
 
+@pytest.mark.parametrize("N,B", [(700, 1), (1100, 3)])
+def test_scheduling_knobs_do_not_change_results(ctx, N, B):
+    """The latency switches of round 2 (clustered few-tile GEMM launches, one-launch triangular solves, the two diagonal-tile
+    kernels, CUDA-graph replay) only reschedule the same arithmetic: logp and the gradient agree to rounding whatever they
+    are set to, and the defaults are restored."""
+    X, y, Theta = orc.c2_inputs(N, B)
+    gp = build_process(SPECS["C2"], X)
+    gp.observed(X, y)
+    c = gp.ctx
+    ref_lp, ref_g, _ = gp.logp_dlogp_batch(Theta)
+    for setter, vals in ((c.set_tile_split, (0, 1)), (c.set_trsv_fused, (0, 1)), (c.set_diag_variant, (1, 2)),
+                         (c.set_graphs, (0, 1))):
+        try:
+            for v in vals:
+                setter(v)
+                for _ in range(3):                               # plain run, graph capture, replay
+                    lp, g, info = gp.logp_dlogp_batch(Theta)
+                    assert np.all(info["status"] == 0)
+                    assert scaled_err(lp, ref_lp) < 1e-11 and scaled_err(g, ref_g) < 1e-9, (setter.__name__, v)
+        finally:
+            setter(vals[-1])                                     # the default of every switch is the last value tried
+
+
 def test_threads_get_their_own_context():
     """Contexts are per thread (a g3_ctx is not re-entrant and ctypes releases the GIL): four threads evaluating
     different hyper samples on the SAME process object concurrently give exactly the sequential results
